@@ -1,0 +1,121 @@
+/* libubssfp -- C ABI of the B200-native hot path of SomeUserName1/UNet-bSSFP.
+ *
+ * The reference has no FFI: the seam is Python class identity (Generator / Discriminator /
+ * DownSampleConv / BasicUNet / L1Loss / BCEWithLogitsLoss, ref:src/model.py:15-92,126,155) and the
+ * NumPy arithmetic of eval.py (ref:src/eval.py:154-166,217-258). This header is the C boundary a
+ * drop-in replacement exports for that path; each entry names the reference
+ * op it replaces. Conventions:
+ *   - plain C: pointers + sizes, no C++/torch types, no exceptions;
+ *   - every entry returns 0 on success, <0 on error; ub_last_error() gives the thread-local message;
+ *   - the caller owns ALL device memory (activations, workspaces, outputs);
+ *   - all work is enqueued on the caller's cudaStream_t (passed as void*); no internal sync;
+ *   - activations are NDHWC bf16 with the channel count padded to a multiple of 32 ("cp");
+ *     tensors at the module boundary are NCDHW fp32 as in the reference;
+ *   - there is no CPU fallback and no cuDNN dispatch: an unsupported shape is an error.
+ */
+#ifndef UB_API_H_
+#define UB_API_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int ub_version(void);
+const char* ub_last_error(void);
+
+/* ---- convolution family ------------------------------------------------------------------ */
+enum {
+  UB_CONV_K3S1P1 = 0,   /* nn.Conv3d(k=3,s=1,p=1): monai BasicUNet Convolution, ref:model.py:22-28 */
+  UB_CONV_K1 = 1,       /* nn.Conv3d(k=1): input heads ref:model.py:19-21, final convs ref:model.py:83 */
+  UB_CONV_K4S2P1 = 2,   /* nn.Conv3d(k=4,s=2,p=1): DownSampleConv in the PatchGAN, ref:model.py:50,72-82 */
+  UB_DECONV_K2S2 = 3    /* nn.ConvTranspose3d(k=2,s=2): monai UpSample "deconv" in UpCat */
+};
+
+typedef struct {
+  int kind;        /* UB_CONV_* */
+  int n, d, h, w;  /* batch and spatial size of the forward INPUT activation */
+  int c0, c0p;     /* real / padded channels of input source 0 */
+  int c1, c1p;     /* real / padded channels of input source 1 (skip concat [src0, src1]); 0 = none */
+  int co, cop;     /* real / padded output channels */
+} ub_conv_desc;
+
+/* number of bf16 elements of a packed weight buffer; dir 0 = forward, 1 = dgrad */
+long long ub_packed_weight_elems(const ub_conv_desc* d, int dir);
+/* torch-layout fp32 weights ([co][ci][k..] or [ci][co][2][2][2] for the transposed conv) -> packed bf16 */
+int ub_pack_conv_weights(const ub_conv_desc* d, int dir, const float* w, void* packed, void* stream);
+
+/* number of output tiles of the forward launch == rows of the statistics partial buffer */
+int ub_conv_num_tiles(const ub_conv_desc* d);
+/* y = conv(cat[src0, src1]) + bias; optional LeakyReLU; optional per-tile sum / sumsq partials
+ * stats_partial: [ub_conv_num_tiles][2][cop] floats or NULL */
+int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* src1, const void* w_packed,
+                const float* bias, int act, float slope, void* out, float* stats_partial, void* stream);
+/* d src = conv_transpose(dy); dsrc1 may be NULL when the op has one source */
+int ub_conv_dgrad(const ub_conv_desc* d, const void* dy, const void* w_packed_dgrad, void* dsrc0,
+                  void* dsrc1, void* stream);
+/* dw (fp32, torch layout) = sum_voxels src (x) dy; workspace holds the split-K partials */
+long long ub_conv_wgrad_workspace_bytes(const ub_conv_desc* d);
+int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void* src1, const void* dy,
+                  void* workspace, float* dw, void* stream);
+
+/* ---- layout at the module boundary --------------------------------------------------------- */
+/* cat[a (ca ch), b (cb ch)] NCDHW fp32 -> NDHWC bf16 with cp channels (b may be NULL); replaces the
+ * torch.cat of ref:model.py:86 and Lightning's host tensor layout */
+int ub_pack_ncdhw(const float* a, int ca, const float* b, int cb, int n, long long voxels, int cp,
+                  void* out, void* stream);
+/* NDHWC bf16 (cp channels) -> NCDHW fp32, channels [c_begin, c_begin + c) */
+int ub_unpack_ncdhw(const void* src, int cp, int c_begin, int c, int n, long long voxels, float* out,
+                    void* stream);
+
+/* ---- normalisation + dropout + activation --------------------------------------------------- */
+enum { UB_NORM_INSTANCE = 0, UB_NORM_BATCH_TRAIN = 1, UB_NORM_BATCH_EVAL = 2, UB_NORM_NONE = 3 };
+/* InstanceNorm3d(affine) / BatchNorm3d statistics from the conv epilogue partials.
+ * scale/shift/mean/rstd: [n][cp] floats. running_* updated in UB_NORM_BATCH_TRAIN (momentum 0.1,
+ * unbiased variance), read in UB_NORM_BATCH_EVAL. ref: monai ADN "N"; ref:model.py:53-54 */
+int ub_norm_finalize(const float* stats_partial, int tiles_per_sample, int n, int cp, int c,
+                     double voxels_per_sample, const float* gamma, const float* beta, float eps, int mode,
+                     float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                     float* mean, float* rstd, void* stream);
+/* a = LeakyReLU_slope(Dropout_p(y * scale + shift)); pooled (may be NULL) = MaxPool3d(2)(a).
+ * scale == NULL: no normalisation. ref: monai ADN "NDA" + Down.max_pooling */
+int ub_norm_act_fwd(const void* y, const float* scale, const float* shift, float slope, float drop_p,
+                    uint32_t drop_seed, int n, int d, int h, int w, int cp, void* a, void* pooled,
+                    void* stream);
+long long ub_norm_act_bwd_workspace_bytes(int n, int cp);
+/* backward of the block above: dy from dA; dgamma/dbeta/dbias (fp32 [c]) may be NULL.
+ * mean == NULL (UB_NORM_NONE): plain activation backward. */
+int ub_norm_act_bwd(const void* dA, const void* a, const void* y, int mode, const float* mean,
+                    const float* rstd, const float* scale, float slope, float drop_p, uint32_t drop_seed,
+                    int n, long long voxels, int cp, int c, void* workspace, void* dy, float* dgamma,
+                    float* dbeta, float* dbias, void* stream);
+/* MaxPool3d(2) backward; accumulate != 0 adds onto the gradient already in dA (skip path) */
+int ub_maxpool_bwd(const void* a, const void* dP, void* dA, int accumulate, int n, int d, int h, int w,
+                   int cp, void* stream);
+/* out[c] = sum over rows of x[rows][cp] (bias gradients of convs without a following norm) */
+long long ub_colsum_workspace_bytes(int cp);
+int ub_colsum(const void* x, long long rows, int cp, int c, void* workspace, float* out, void* stream);
+
+/* ---- losses -------------------------------------------------------------------------------------- */
+long long ub_l1_workspace_bytes(void);
+/* nn.L1Loss (mean), ref:model.py:126,136 */
+int ub_l1_fwd(const float* a, const float* b, long long numel, void* workspace, float* loss, void* stream);
+int ub_l1_bwd(const float* a, const float* b, const float* grad_out, long long numel, float* da, void* stream);
+/* nn.BCEWithLogitsLoss (mean) against a constant target, ref:model.py:155,173-175,187-192;
+ * dx_unit (may be NULL) = d loss / d x for an upstream gradient of 1 */
+int ub_bce_logits(const float* x, float target, int numel, float* loss, float* dx_unit, void* stream);
+int ub_scale(const float* x, const float* scalar, long long numel, float* y, void* stream);
+
+/* ---- evaluation -------------------------------------------------------------------------------- */
+/* ref:eval.py:154-166 (relative / angular error map) fused with ref:eval.py:217-258 (masked,
+ * probseg-weighted ROI means). Volumes are channel-last [X][Y][Z][C] fp32. diff, mask, probseg may be
+ * NULL. sums: [r][c] doubles, norms: [r] doubles (zeroed by the call). c <= 8, r <= 3. */
+int ub_relerr_map_reduce(const float* pred, const float* target, const unsigned char* mask,
+                         const float* probseg, int c, int r, long long voxels, int angular, float* diff,
+                         double* sums, double* norms, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UB_API_H_ */

@@ -1,0 +1,130 @@
+"""GPU parity: the tcgen05 implicit-GEMM convolutions (through the C ABI) against torch.nn.functional
+on identical bf16-rounded inputs and weights (fp32 math, TF32 off). Tolerance: 1e-2 relative to the
+largest magnitude (north_star bf16 bar); expected ~4e-3 from the bf16 output rounding."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import bf16_round, from_internal, rel_to_max, rel_l2, strict_fp32, to_internal
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+def _ops():
+    from unet_bssfp_b200 import ops
+    return ops
+
+
+def _ref_conv(kind, x, w, b):
+    if kind == 0:
+        return F.conv3d(x, w, b, stride=1, padding=1)
+    if kind == 1:
+        return F.conv3d(x, w, b)
+    if kind == 2:
+        return F.conv3d(x, w, b, stride=2, padding=1)
+    return F.conv_transpose3d(x, w, b, stride=2)
+
+
+def _weight_shape(kind, ci, co):
+    k = {0: 3, 1: 1, 2: 4, 3: 2}[kind]
+    return (ci, co, k, k, k) if kind == 3 else (co, ci, k, k, k)
+
+
+CASES = [
+    # kind, c0, c1, co, (n, d, h, w)
+    (0, 32, 0, 32, (2, 8, 16, 8)),
+    (0, 24, 0, 32, (1, 6, 20, 12)),      # channel padding + ragged tiles in d, h, w
+    (0, 64, 0, 64, (1, 4, 16, 16)),
+    (0, 32, 64, 32, (1, 5, 16, 8)),      # skip concat [32 | 64] as two sources, split dgrad destinations
+    (0, 128, 0, 256, (1, 4, 8, 8)),      # several N tiles, plane smaller than the 16x8 tile
+    (0, 256, 256, 256, (1, 2, 4, 4)),
+    (1, 24, 0, 24, (2, 4, 16, 8)),
+    (1, 32, 0, 6, (1, 4, 16, 8)),
+    (1, 512, 0, 1, (2, 2, 2, 2)),
+    (2, 30, 0, 32, (1, 16, 32, 16)),
+    (2, 32, 0, 64, (2, 8, 8, 8)),
+    (2, 256, 0, 512, (2, 4, 4, 4)),
+    (3, 64, 0, 64, (1, 4, 16, 8)),
+    (3, 512, 0, 256, (2, 2, 4, 4)),
+    (3, 128, 0, 64, (1, 3, 6, 5)),
+]
+
+
+def _make(kind, c0, c1, co, shape, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    n, d, h, w = shape
+    ci = c0 + c1
+    x = bf16_round(torch.randn((n, ci, d, h, w), device="cuda", generator=g))
+    wt = bf16_round(torch.randn(_weight_shape(kind, ci, co), device="cuda", generator=g) / (ci ** 0.5))
+    b = torch.randn((co,), device="cuda", generator=g)
+    return x, wt, b
+
+
+@pytest.mark.parametrize("kind,c0,c1,co,shape", CASES)
+def test_conv_forward_and_stats(kind, c0, c1, co, shape):
+    strict_fp32()
+    ops = _ops()
+    x, wt, b = _make(kind, c0, c1, co, shape)
+    spec = ops.ConvSpec(kind, c0, co, c1)
+    wpk = ops.pack_conv_weights(spec, wt, 0)
+    s0 = to_internal(x[:, :c0])
+    s1 = to_internal(x[:, c0:]) if c1 else None
+    want_stats = kind != 3
+    y, stats = ops.conv_fwd(spec, s0, s1, wpk, b, want_stats=want_stats)
+    torch.cuda.synchronize()
+    ref = _ref_conv(kind, x, wt, b)
+    got = from_internal(y, co)
+    assert got.shape == ref.shape
+    assert rel_to_max(got, ref) < TOL
+    # padded output channels are exactly zero
+    if spec.cop > co:
+        assert y[..., co:].abs().max().item() == 0.0
+    if want_stats:
+        n = shape[0]
+        tiles = stats.shape[0] // n
+        s = stats.view(n, tiles, 2, spec.cop).sum(1)
+        ref_s = got.sum(dim=(2, 3, 4))
+        ref_q = (got * got).sum(dim=(2, 3, 4))
+        assert rel_to_max(s[:, 0, :co], ref_s) < 1e-3
+        assert rel_to_max(s[:, 1, :co], ref_q) < 1e-3
+
+
+@pytest.mark.parametrize("kind,c0,c1,co,shape", CASES)
+def test_conv_dgrad(kind, c0, c1, co, shape):
+    strict_fp32()
+    ops = _ops()
+    x, wt, b = _make(kind, c0, c1, co, shape, seed=1)
+    spec = ops.ConvSpec(kind, c0, co, c1)
+    x.requires_grad_(True)
+    ref_y = _ref_conv(kind, x, wt, None)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    dy = bf16_round(torch.randn(ref_y.shape, device="cuda", generator=g))
+    (ref_dx,) = torch.autograd.grad(ref_y, x, dy)
+    wpk = ops.pack_conv_weights(spec, wt, 1)
+    d0, d1 = ops.conv_dgrad(spec, to_internal(dy), wpk, shape[1:])
+    torch.cuda.synchronize()
+    got = from_internal(d0, c0)
+    if c1:
+        got = torch.cat([got, from_internal(d1, c1)], dim=1)
+    assert rel_to_max(got, ref_dx) < TOL
+
+
+@pytest.mark.parametrize("kind,c0,c1,co,shape", CASES)
+def test_conv_wgrad(kind, c0, c1, co, shape):
+    strict_fp32()
+    ops = _ops()
+    x, wt, b = _make(kind, c0, c1, co, shape, seed=2)
+    spec = ops.ConvSpec(kind, c0, co, c1)
+    wt.requires_grad_(True)
+    ref_y = _ref_conv(kind, x, wt, None)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    dy = bf16_round(torch.randn(ref_y.shape, device="cuda", generator=g))
+    (ref_dw,) = torch.autograd.grad(ref_y, wt, dy)
+    s0 = to_internal(x[:, :c0])
+    s1 = to_internal(x[:, c0:]) if c1 else None
+    dw = ops.conv_wgrad(spec, s0, s1, to_internal(dy), tuple(wt.shape))
+    torch.cuda.synchronize()
+    assert dw.shape == ref_dw.shape
+    assert rel_to_max(dw, ref_dw) < 2e-3      # fp32 accumulate of exact bf16 products
+    assert rel_l2(dw, ref_dw) < 1e-3

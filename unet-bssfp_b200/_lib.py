@@ -1,0 +1,83 @@
+"""ctypes binding of ``libubssfp.so`` (C ABI declared in ``include/ub_api.h``).
+
+The library is the product: there is no Python/CPU fallback. ``load()`` raises if the shared object
+has not been built (``python -c 'import __graft_entry__ as g; g.build()'``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libubssfp.so")
+
+UB_CONV_K3S1P1, UB_CONV_K1, UB_CONV_K4S2P1, UB_DECONV_K2S2 = 0, 1, 2, 3
+UB_NORM_INSTANCE, UB_NORM_BATCH_TRAIN, UB_NORM_BATCH_EVAL, UB_NORM_NONE = 0, 1, 2, 3
+
+
+class ConvDesc(C.Structure):
+    """Mirror of ``ub_conv_desc`` (include/ub_api.h)."""
+    _fields_ = [(k, C.c_int) for k in ("kind", "n", "d", "h", "w", "c0", "c0p", "c1", "c1p", "co", "cop")]
+
+
+_P = C.c_void_p
+_F = C.c_float
+_I = C.c_int
+_LL = C.c_longlong
+_U32 = C.c_uint32
+_D = C.c_double
+_DP = C.POINTER(ConvDesc)
+
+# name -> (restype, argtypes); every symbol of include/ub_api.h
+SIGNATURES = {
+    "ub_version": (_I, []),
+    "ub_last_error": (C.c_char_p, []),
+    "ub_packed_weight_elems": (_LL, [_DP, _I]),
+    "ub_pack_conv_weights": (_I, [_DP, _I, _P, _P, _P]),
+    "ub_conv_num_tiles": (_I, [_DP]),
+    "ub_conv_fwd": (_I, [_DP, _P, _P, _P, _P, _I, _F, _P, _P, _P]),
+    "ub_conv_dgrad": (_I, [_DP, _P, _P, _P, _P, _P]),
+    "ub_conv_wgrad_workspace_bytes": (_LL, [_DP]),
+    "ub_conv_wgrad": (_I, [_DP, _P, _P, _P, _P, _P, _P]),
+    "ub_pack_ncdhw": (_I, [_P, _I, _P, _I, _I, _LL, _I, _P, _P]),
+    "ub_unpack_ncdhw": (_I, [_P, _I, _I, _I, _I, _LL, _P, _P]),
+    "ub_norm_finalize": (_I, [_P, _I, _I, _I, _I, _D, _P, _P, _F, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "ub_norm_act_fwd": (_I, [_P, _P, _P, _F, _F, _U32, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "ub_norm_act_bwd_workspace_bytes": (_LL, [_I, _I]),
+    "ub_norm_act_bwd": (_I, [_P, _P, _P, _I, _P, _P, _P, _F, _F, _U32, _I, _LL, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "ub_maxpool_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "ub_colsum_workspace_bytes": (_LL, [_I]),
+    "ub_colsum": (_I, [_P, _LL, _I, _I, _P, _P, _P]),
+    "ub_l1_workspace_bytes": (_LL, []),
+    "ub_l1_fwd": (_I, [_P, _P, _LL, _P, _P, _P]),
+    "ub_l1_bwd": (_I, [_P, _P, _P, _LL, _P, _P]),
+    "ub_bce_logits": (_I, [_P, _F, _I, _P, _P, _P]),
+    "ub_scale": (_I, [_P, _P, _LL, _P, _P]),
+    "ub_relerr_map_reduce": (_I, [_P, _P, _P, _P, _I, _I, _LL, _I, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library and bind every entry point; raise loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built and there is no fallback. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` at the repo root.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().ub_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libubssfp {what} failed (rc={rc}): {msg}")

@@ -1,0 +1,324 @@
+// Tap-table implicit-GEMM convolution for sm_100a: TMA halo tiles -> shifted UMMA views -> TMEM.
+//
+// One kernel serves every "activation x weights -> activation" contraction on the hot path:
+//   * Conv3d 3x3x3 s1 p1 forward and its dgrad (flipped/transposed weight pack)   ref:model.py:22-28 (BasicUNet)
+//   * Conv3d 4x4x4 s2 p1 forward (8 parity tiles loaded with TMA elementStrides=2)  ref:model.py:50,72-82
+//     and its dgrad (8 output parity classes, scatter store)
+//   * ConvTranspose3d k2 s2 forward (1 tap, scatter store) and dgrad (8 parity tiles) ref:BasicUNet UpCat
+//   * 1x1x1 convs (heads, final convs)                                            ref:model.py:19-21,83
+//
+// Geometry: an output tile is TD planes x 16 (h) x 8 (w) voxels. Every plane is one UMMA M=128
+// accumulator of NT fp32 columns in TMEM. For each K chunk (kc = 16 or 32 input channels, one
+// swizzle span per voxel row) the producer loads the *halo* of the tile once per A-tile
+// ((16+KH-1) x (8+KW-1) rows per plane) and the MMA thread addresses each filter tap as a
+// row-shifted view of that halo (start address + row offset, SBO = box-width rows) -- no im2col
+// re-load per tap. The skip concatenation is a second tensor map: chunks [0,n0) come from source 0,
+// the rest from source 1, so the concat tensor never exists. Weights stream through a TMA ring,
+// one [NT x kc] tile per (chunk, tap), shared by the TD planes.
+//
+// Epilogue (4 warps, thread <-> accumulator row): tcgen05.ld -> +bias -> optional LeakyReLU ->
+// per-channel sum / sum-of-squares partials (register transpose-reduce with shuffles, one partial
+// record per CTA, no atomics) -> bf16 -> 16-byte global stores (optionally scattered with stride 2).
+#pragma once
+#include "sm100_ptx.cuh"
+
+namespace ub {
+
+constexpr int kMaxTaps = 64;
+constexpr int kMaxATiles = 8;
+constexpr int kMaxNTiles = 4;
+
+struct IgemmTap {
+  uint16_t atile;      // which A tile of the stage
+  uint16_t row_off;    // row offset inside the tile plane (kh * box_w + kw)
+  uint16_t plane_off;  // plane offset (kd)
+  uint16_t wblock;     // weight row block (rows [wblock * w_rows_per_block + n0, ...))
+};
+
+struct IgemmNTile {
+  int n0;             // first output column (row inside a weight block)
+  int nt;             // columns in this tile (multiple of 16, <= 128)
+  void* out;          // destination tensor (bf16, NDHWC)
+  int out_cpitch;     // channels per voxel in the destination
+  int out_coff;       // channel offset inside the destination voxel
+  int split;          // columns [split, nt) go to out2 instead (split == nt: single destination)
+  void* out2;         // second destination (dgrad of a skip-concat conv: [d skip | d upsampled])
+  int out2_cpitch;
+};
+
+struct IgemmParams {
+  CUtensorMap tm_src[2];
+  CUtensorMap tm_w;
+  int n_chunks_src0, n_chunks_total, kc;
+  int n_atiles, bw, bh, n_in_planes, in_stride;
+  int atile_off[kMaxATiles][3];  // (w, h, d) added to in_stride * tile origin
+  int ntaps;
+  IgemmTap taps[kMaxTaps];
+  int w_rows_per_block;
+  int td;
+  int Nb, Do, Ho, Wo;            // tile space (output voxels before the optional scatter)
+  int tiles_w, tiles_h, tiles_d;
+  int n_ntiles;
+  IgemmNTile ntile[kMaxNTiles];
+  int out_s, out_p[3];           // destination voxel = tile-space voxel * out_s + out_p (w,h,d)
+  int oD, oH, oW;                // destination tensor dims
+  const float* bias;             // [bias_n] real output channels, or nullptr
+  int bias_n;
+  int act;                       // 0 none, 1 LeakyReLU(act_slope)
+  float act_slope;
+  float* stats;                  // [tile][2][w_rows_per_block] partial sum / sumsq, or nullptr
+  // shared memory plan (bytes)
+  int plane_stride, a_stage_bytes, b_stage_bytes, nsa, nsb, tmem_cols;
+};
+
+__device__ __forceinline__ void tmem_alloc_rt(uint32_t smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_rt(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Sum over the 32 lanes of a warp of 32 per-lane values; lane l ends with the total of v[l].
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < n / 2) {
+        const float send = hi ? v[i] : v[i + n / 2];
+        const float keep = hi ? v[i + n / 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+constexpr int kIgemmThreads = 192;  // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
+
+__global__ void __launch_bounds__(kIgemmThreads, 1)
+igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t a_base = base;
+  const uint32_t b_base = a_base + P.nsa * P.a_stage_bytes;
+  const uint32_t bar_base = b_base + P.nsb * P.b_stage_bytes;  // 8-byte mbarriers
+  // barrier layout: a_full[nsa] a_empty[nsa] b_full[nsb] b_empty[nsb] acc_full
+  const uint32_t a_full = bar_base, a_empty = a_full + 8 * P.nsa, b_full = a_empty + 8 * P.nsa,
+                 b_empty = b_full + 8 * P.nsb, acc_full = b_empty + 8 * P.nsb;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (acc_full + 8 - base));
+  float* red = reinterpret_cast<float*>(sm + (acc_full + 16 - base));  // [4][2][128] floats
+
+  // ---- tile coordinates
+  int t = blockIdx.x;
+  const int tw_i = t % P.tiles_w; t /= P.tiles_w;
+  const int th_i = t % P.tiles_h; t /= P.tiles_h;
+  const int td_i = t % P.tiles_d; t /= P.tiles_d;
+  const int nb = t;
+  const int w0 = tw_i * 8, h0 = th_i * 16, d0 = td_i * P.td;
+  const IgemmNTile NT = P.ntile[blockIdx.y];
+  const int ntc = (NT.nt + 31) & ~31;  // TMEM columns per plane accumulator
+  int planes = P.Do - d0; if (planes > P.td) planes = P.td;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P.nsa; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < P.nsb; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&P.tm_src[0]);
+    if (P.n_chunks_total > P.n_chunks_src0) tma_prefetch_desc(&P.tm_src[1]);
+    tma_prefetch_desc(&P.tm_w);
+  }
+  if (warp == 5) tmem_alloc_rt(smem_u32(tmem_slot), P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int pitch = P.kc * 2;
+
+  if (warp == 4) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      const uint32_t a_bytes = (uint32_t)(P.n_atiles * P.n_in_planes * P.bh * P.bw * pitch);
+      const uint32_t b_bytes = (uint32_t)(NT.nt * pitch);
+      int it = 0;
+      for (int ch = 0; ch < P.n_chunks_total; ++ch) {
+        const int sa = ch % P.nsa;
+        mbar_wait(a_empty + 8 * sa, ((ch / P.nsa) & 1) ^ 1);
+        mbar_expect_tx(a_full + 8 * sa, a_bytes);
+        const bool s1 = ch >= P.n_chunks_src0;
+        const CUtensorMap* tm = &P.tm_src[s1 ? 1 : 0];
+        const int c0 = (s1 ? ch - P.n_chunks_src0 : ch) * P.kc;
+        for (int at = 0; at < P.n_atiles; ++at) {
+          const int cw = w0 * P.in_stride + P.atile_off[at][0];
+          const int chh = h0 * P.in_stride + P.atile_off[at][1];
+          for (int p = 0; p < P.n_in_planes; ++p) {
+            const int cd = (d0 + p) * P.in_stride + P.atile_off[at][2];
+            const uint32_t dst = a_base + sa * P.a_stage_bytes + (at * P.n_in_planes + p) * P.plane_stride;
+            tma_load_5d(dst, tm, a_full + 8 * sa, c0, cw, chh, cd, nb);
+          }
+        }
+        for (int tp = 0; tp < P.ntaps; ++tp, ++it) {
+          const int sb = it % P.nsb;
+          mbar_wait(b_empty + 8 * sb, ((it / P.nsb) & 1) ^ 1);
+          mbar_expect_tx(b_full + 8 * sb, b_bytes);
+          tma_load_2d(b_base + sb * P.b_stage_bytes, &P.tm_w, b_full + 8 * sb, ch * P.kc,
+                      P.taps[tp].wblock * P.w_rows_per_block + NT.n0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t swz = P.kc == 32 ? SWZ_64B : (P.kc == 16 ? SWZ_32B : SWZ_128B);
+      const uint32_t idesc = make_idesc_bf16(128, NT.nt, 0, 0);
+      const uint64_t a_desc0 = make_smem_desc(0, 16, P.bw * pitch, swz);
+      const uint64_t b_desc0 = make_smem_desc(0, 16, 8 * pitch, swz);
+      const int ksteps = P.kc / 16;
+      int it = 0;
+      for (int ch = 0; ch < P.n_chunks_total; ++ch) {
+        const int sa = ch % P.nsa;
+        mbar_wait(a_full + 8 * sa, (ch / P.nsa) & 1);
+        tc_fence_after();
+        const uint32_t a_stage = a_base + sa * P.a_stage_bytes;
+        for (int tp = 0; tp < P.ntaps; ++tp, ++it) {
+          const int sb = it % P.nsb;
+          mbar_wait(b_full + 8 * sb, (it / P.nsb) & 1);
+          tc_fence_after();
+          const IgemmTap T = P.taps[tp];
+          const uint32_t a_tap = a_stage + (T.atile * P.n_in_planes + T.plane_off) * P.plane_stride +
+                                 T.row_off * pitch;
+          const uint32_t b_tile = b_base + sb * P.b_stage_bytes;
+          const uint32_t acc = (ch | tp) != 0;
+          for (int o = 0; o < planes; ++o) {
+            const uint32_t a_pl = a_tap + o * P.plane_stride;
+#pragma unroll 2
+            for (int k = 0; k < ksteps; ++k) {
+              umma_bf16(tmem + o * ntc, a_desc0 + (uint64_t)((a_pl + k * 32) >> 4),
+                        b_desc0 + (uint64_t)((b_tile + k * 32) >> 4), idesc, acc | (uint32_t)(k != 0));
+            }
+          }
+          umma_commit(b_empty + 8 * sb);
+        }
+        umma_commit(a_empty + 8 * sa);
+      }
+      umma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    // =========================== epilogue (warps 0-3) ===========================
+    const int r = warp * 32 + lane;
+    const int h = h0 + (r >> 3), w = w0 + (r & 7);
+    const bool valid_hw = (h < P.Ho) && (w < P.Wo);
+    float s_acc[4] = {0.f, 0.f, 0.f, 0.f}, q_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int nchunks = (NT.nt + 31) >> 5;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(NT.out);
+    for (int o = 0; o < planes; ++o) {
+      const int d = d0 + o;
+      const size_t vox = (((size_t)nb * P.oD + (size_t)(d * P.out_s + P.out_p[2])) * P.oH +
+                          (size_t)(h * P.out_s + P.out_p[1])) * P.oW + (size_t)(w * P.out_s + P.out_p[0]);
+      __nv_bfloat16* dst = outp + vox * NT.out_cpitch + NT.out_coff;
+      __nv_bfloat16* dst2 = reinterpret_cast<__nv_bfloat16*>(NT.out2) + vox * NT.out2_cpitch;
+#pragma unroll 1
+      for (int cc = 0; cc < nchunks; ++cc) {
+        const int ncol = (NT.nt - cc * 32) >= 32 ? 32 : 16;
+        uint32_t rr[32];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + o * ntc + cc * 32;
+        if (ncol == 32) {
+          tmem_ld_32x32b_x32(taddr, rr);
+        } else {
+          uint32_t r16[16];
+          tmem_ld_32x32b_x16(taddr, r16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { rr[j] = r16[j]; rr[j + 16] = 0u; }
+        }
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(rr[j]);
+          if (P.bias != nullptr && NT.n0 + cc * 32 + j < P.bias_n) x += __ldg(P.bias + NT.n0 + cc * 32 + j);
+          if (P.act == 1) x = x > 0.f ? x : x * P.act_slope;
+          v[j] = x;
+        }
+        if (valid_hw) {
+          uint4* d4 = cc * 32 < NT.split ? reinterpret_cast<uint4*>(dst + cc * 32)
+                                         : reinterpret_cast<uint4*>(dst2 + (cc * 32 - NT.split));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j * 8 < ncol) {
+              uint4 pk;
+              pk.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]);
+              pk.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
+              pk.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]);
+              pk.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
+              d4[j] = pk;
+            }
+          }
+        }
+        if (P.stats != nullptr) {
+          // statistics of the values as stored (bf16-rounded), so the consumer normalises exactly
+          // what it reads
+          float a[32], b[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float xr = valid_hw ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.f;
+            a[j] = xr;
+            b[j] = xr * xr;
+          }
+          const float sa_ = warp_transpose_reduce32(a, lane);
+          const float sq_ = warp_transpose_reduce32(b, lane);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q == cc) { s_acc[q] += sa_; q_acc[q] += sq_; }
+        }
+      }
+    }
+    if (P.stats != nullptr) {
+      for (int cc = 0; cc < nchunks; ++cc) {
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k == cc) { s = s_acc[k]; q = q_acc[k]; }
+        red[(warp * 2 + 0) * 128 + cc * 32 + lane] = s;
+        red[(warp * 2 + 1) * 128 + cc * 32 + lane] = q;
+      }
+      named_bar_sync(1, 128);
+      const int c = threadIdx.x;
+      if (c < NT.nt) {
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 4; ++wq) { s += red[(wq * 2 + 0) * 128 + c]; q += red[(wq * 2 + 1) * 128 + c]; }
+        float* st = P.stats + (size_t)blockIdx.x * 2 * P.w_rows_per_block;
+        st[NT.n0 + c] = s;
+        st[P.w_rows_per_block + NT.n0 + c] = q;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc_rt(tmem, P.tmem_cols);
+}
+
+}  // namespace ub

@@ -1,0 +1,185 @@
+// Weight-gradient implicit GEMM for sm_100a: dW[tap][ci][co] = sum_voxels X[v + tap][ci] * dY[v][co].
+//
+// Both operands are read where the forward pass left them -- NDHWC bf16, channels contiguous -- so
+// they are *MN-major* UMMA operands (the reduction index K is the voxel row):
+//   A (M side) = a halo tile of X, one 32-channel chunk (64-byte rows, SWIZZLE_64B). One UMMA covers
+//                M = 128 = 4 atoms of 32 channels; atom a starts `a` rows later (LBO = one row), i.e.
+//                the atoms are the kw = 0,1,2 taps of one (kd,kh) pair (+1 unused atom). K = 16 voxels
+//                per instruction = two h-rows of 8 w (SBO = box-width rows).
+//   B (N side) = the matching 16x8 dY plane tile, NT channels (one or two swizzle atoms).
+// Accumulators: one [128 x NT] fp32 block per kh group in TMEM, kept for the CTA's whole share of
+// the voxel tiles (split-K over CTAs), then written once to a per-split partial buffer
+// [split][tap][ci][co] (fp32). A small reduce kernel sums the splits in a fixed order
+// (deterministic) and converts to the torch weight layout.
+//
+// Work decomposition: blockIdx.x = voxel split; blockIdx.y enumerates (ci chunk, variant, co tile).
+// A "variant" fixes the X-tile origin offset and the dY parity offset: kd for 3x3x3, (parity, jd)
+// for the 4x4x4 stride-2 conv, the sub-position for the transposed conv.
+#pragma once
+#include "igemm_fwd.cuh"
+
+namespace ub {
+
+constexpr int kMaxWgVariants = 16;
+
+struct WgradParams {
+  CUtensorMap tm_x[2];
+  CUtensorMap tm_dy;
+  int n_chunks_src0, n_chunks_total;     // 32-channel chunks of X (both sources)
+  int bw, bh;                            // X tile box rows
+  int x_stride;                          // X coordinate = tile coord * x_stride + off
+  int dy_stride;                         // dY coordinate = tile coord * dy_stride + off
+  int n_variants;
+  int x_off[kMaxWgVariants][3];          // (w,h,d)
+  int dy_off[kMaxWgVariants][3];
+  int ngroups, group_row_step;           // groups per variant (kh), rows between group starts
+  int natoms;                            // useful atoms per group (kw), <= 4
+  int n_cotiles, nt;                     // dY column tiles of nt channels each
+  int ncb;                               // channels per dY TMA box (min(nt,64)); swizzle = ncb*2 bytes
+  int Nb, Dt, Ht, Wt;                    // tile space (voxels the reduction runs over)
+  int tiles_w, tiles_h;
+  int ci_total, co_total;                // padded totals (partial buffer pitch)
+  float* partial;                        // [nsplit][n_variants*ngroups*natoms][ci_total][co_total]
+  int x_stage_bytes, dy_stage_bytes, nstages, tmem_cols;
+};
+
+__global__ void __launch_bounds__(kIgemmThreads, 1)
+igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stage_bytes = P.x_stage_bytes + P.dy_stage_bytes;
+  const uint32_t bar_base = base + P.nstages * stage_bytes;
+  const uint32_t full = bar_base, empty = full + 8 * P.nstages, acc_full = empty + 8 * P.nstages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (acc_full + 8 - base));
+
+  // ---- work item
+  int y = blockIdx.y;
+  const int cot = y % P.n_cotiles; y /= P.n_cotiles;
+  const int var = y % P.n_variants; y /= P.n_variants;
+  const int chunk = y;
+  const int n0 = cot * P.nt;
+  const bool s1 = chunk >= P.n_chunks_src0;
+  const int c0 = (s1 ? chunk - P.n_chunks_src0 : chunk) * 32;
+  const int ntc = (P.nt + 31) & ~31;
+
+  // ---- this CTA's share of the plane tiles
+  const long long total = (long long)P.Nb * P.Dt * P.tiles_h * P.tiles_w;
+  const long long per = (total + gridDim.x - 1) / gridDim.x;
+  const long long t_begin = (long long)blockIdx.x * per;
+  long long t_end = t_begin + per; if (t_end > total) t_end = total;
+  const int niter = t_end > t_begin ? (int)(t_end - t_begin) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P.nstages; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&P.tm_x[s1 ? 1 : 0]);
+    tma_prefetch_desc(&P.tm_dy);
+  }
+  if (warp == 5) tmem_alloc_rt(smem_u32(tmem_slot), P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int nboxes = P.nt / P.ncb;
+  const int dy_pitch = P.ncb * 2;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(P.bh * P.bw * 64 + 128 * P.nt * 2);
+      const CUtensorMap* tmx = &P.tm_x[s1 ? 1 : 0];
+      for (int it = 0; it < niter; ++it) {
+        long long tt = t_begin + it;
+        const int tw_i = (int)(tt % P.tiles_w); tt /= P.tiles_w;
+        const int th_i = (int)(tt % P.tiles_h); tt /= P.tiles_h;
+        const int d = (int)(tt % P.Dt); tt /= P.Dt;
+        const int nb = (int)tt;
+        const int st = it % P.nstages;
+        mbar_wait(empty + 8 * st, ((it / P.nstages) & 1) ^ 1);
+        mbar_expect_tx(full + 8 * st, bytes);
+        const uint32_t xs = base + st * stage_bytes;
+        tma_load_5d(xs, tmx, full + 8 * st, c0, tw_i * 8 * P.x_stride + P.x_off[var][0],
+                    th_i * 16 * P.x_stride + P.x_off[var][1], d * P.x_stride + P.x_off[var][2], nb);
+        for (int b = 0; b < nboxes; ++b)
+          tma_load_5d(xs + P.x_stage_bytes + b * 128 * dy_pitch, &P.tm_dy, full + 8 * st, n0 + b * P.ncb,
+                      tw_i * 8 * P.dy_stride + P.dy_off[var][0], th_i * 16 * P.dy_stride + P.dy_off[var][1],
+                      d * P.dy_stride + P.dy_off[var][2], nb);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t swz_b = dy_pitch == 128 ? SWZ_128B : (dy_pitch == 64 ? SWZ_64B : SWZ_32B);
+      const uint32_t idesc = make_idesc_bf16(128, P.nt, 1, 1);
+      const uint64_t a_desc0 = make_smem_desc(0, /*lbo: next atom = next row*/ 64, /*sbo*/ P.bw * 64, SWZ_64B);
+      const uint64_t b_desc0 = make_smem_desc(0, /*lbo: next 64-channel box*/ 128 * dy_pitch, 8 * dy_pitch, swz_b);
+      for (int it = 0; it < niter; ++it) {
+        const int st = it % P.nstages;
+        mbar_wait(full + 8 * st, (it / P.nstages) & 1);
+        tc_fence_after();
+        const uint32_t xs = base + st * stage_bytes;
+        const uint32_t ys = xs + P.x_stage_bytes;
+        for (int g = 0; g < P.ngroups; ++g) {
+          const uint32_t a_g = xs + g * P.group_row_step * 64;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            umma_bf16(tmem + g * ntc, a_desc0 + (uint64_t)((a_g + ks * 2 * P.bw * 64) >> 4),
+                      b_desc0 + (uint64_t)((ys + ks * 16 * dy_pitch) >> 4), idesc, (uint32_t)((it | ks) != 0));
+          }
+        }
+        umma_commit(empty + 8 * st);
+      }
+      umma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    // epilogue: row = atom * 32 + ci  ->  warp index is the atom (kw), lane is the channel
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int ntaps_v = P.ngroups * P.natoms;
+    const size_t tap_elems = (size_t)P.ci_total * P.co_total;
+    float* outb = P.partial + (size_t)blockIdx.x * ((size_t)P.n_variants * ntaps_v) * tap_elems;
+    for (int g = 0; g < P.ngroups; ++g) {
+      const int tap = (var * P.ngroups + g) * P.natoms + warp;
+      float* dst = outb + (size_t)tap * tap_elems + (size_t)(chunk * 32 + lane) * P.co_total + n0;
+      for (int cc = 0; cc * 32 < P.nt; ++cc) {
+        const int ncol = (P.nt - cc * 32) >= 32 ? 32 : 16;
+        uint32_t rr[32];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + g * ntc + cc * 32;
+        if (ncol == 32) {
+          tmem_ld_32x32b_x32(taddr, rr);
+        } else {
+          uint32_t r16[16];
+          tmem_ld_32x32b_x16(taddr, r16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { rr[j] = r16[j]; rr[j + 16] = 0u; }
+        }
+        tmem_ld_wait();
+        if (warp < P.natoms) {
+          float4* d4 = reinterpret_cast<float4*>(dst + cc * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j * 4 < ncol) {
+              float4 o;
+              if (niter > 0) {
+                o.x = __uint_as_float(rr[j * 4 + 0]); o.y = __uint_as_float(rr[j * 4 + 1]);
+                o.z = __uint_as_float(rr[j * 4 + 2]); o.w = __uint_as_float(rr[j * 4 + 3]);
+              } else {
+                o = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              d4[j] = o;
+            }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc_rt(tmem, P.tmem_cols);
+}
+
+}  // namespace ub

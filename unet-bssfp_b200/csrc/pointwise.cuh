@@ -1,0 +1,660 @@
+// Memory-bound kernels of the hot path (sm_100a): layout pack/unpack, norm statistics finalisation,
+// fused norm-apply + dropout + LeakyReLU (+ 2x2x2 max-pool), their backward passes, max-pool
+// backward, weight packing, split-K reduction of weight gradients, the L1 / BCE-with-logits losses
+// and the evaluation's relative-error map + ROI reduction.
+// Activations are NDHWC bf16 with the channel count padded to a multiple of 16; every kernel moves
+// 16-byte vectors (8 channels) per thread and is bounded by HBM bandwidth.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace ub {
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+// Counter-based dropout mask (replaces torch's Philox stream, which cannot be reproduced bit-exactly;
+// ref: monai ADN "D" = nn.Dropout(p), element-wise). One 32-bit hash decides two consecutive elements.
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+// keep mask for the 8 consecutive elements starting at element index e0 (multiple of 8)
+__device__ __forceinline__ uint32_t dropout_keep8(unsigned long long e0, uint32_t seed, uint32_t thresh16) {
+  uint32_t m = 0;
+  const uint32_t hi = (uint32_t)(e0 >> 33);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t pair = (uint32_t)((e0 >> 1) + i);
+    const uint32_t h = hash32(pair * 0x9E3779B1u ^ seed ^ (hi * 0x7FEB352Du));
+    m |= ((h & 0xFFFFu) >= thresh16 ? 1u : 0u) << (2 * i);
+    m |= ((h >> 16) >= thresh16 ? 1u : 0u) << (2 * i + 1);
+  }
+  return m;
+}
+
+struct NormActArgs {
+  const float* scale;   // [N][Cp]  gamma * rstd          (or nullptr: identity)
+  const float* shift;   // [N][Cp]  beta - mean * scale
+  float slope;          // LeakyReLU negative slope (1.0f = no activation)
+  float drop_p;         // 0 = no dropout
+  uint32_t drop_seed;
+  uint32_t drop_thresh; // round(p * 65536)
+};
+
+__device__ __forceinline__ void norm_act_apply8(float (&x)[8], const NormActArgs& A, int n, int Cp, int c0,
+                                                unsigned long long e0) {
+  if (A.scale != nullptr) {
+    const float4* sc = reinterpret_cast<const float4*>(A.scale + (size_t)n * Cp + c0);
+    const float4* sh = reinterpret_cast<const float4*>(A.shift + (size_t)n * Cp + c0);
+    const float4 s0 = __ldg(sc), s1 = __ldg(sc + 1), h0 = __ldg(sh), h1 = __ldg(sh + 1);
+    x[0] = fmaf(x[0], s0.x, h0.x); x[1] = fmaf(x[1], s0.y, h0.y);
+    x[2] = fmaf(x[2], s0.z, h0.z); x[3] = fmaf(x[3], s0.w, h0.w);
+    x[4] = fmaf(x[4], s1.x, h1.x); x[5] = fmaf(x[5], s1.y, h1.y);
+    x[6] = fmaf(x[6], s1.z, h1.z); x[7] = fmaf(x[7], s1.w, h1.w);
+  }
+  if (A.drop_p > 0.f) {
+    const uint32_t keep = dropout_keep8(e0, A.drop_seed, A.drop_thresh);
+    const float inv = 1.f / (1.f - A.drop_p);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = (keep >> i) & 1u ? x[i] * inv : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = x[i] > 0.f ? x[i] : x[i] * A.slope;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout: NCDHW fp32 <-> NDHWC bf16 (channel padded)
+// ------------------------------------------------------------------------------------------------
+// thread per voxel; reads are coalesced per channel plane, writes are CP*2 contiguous bytes.
+// Two optional inputs a (ca channels) and b (cb channels) are concatenated: this is the torch.cat of
+// the PatchGAN input (ref: model.py:86) folded into the layout change.
+template <int CP>
+__global__ void pack_ncdhw_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
+                                  __nv_bfloat16* __restrict__ dst, long long V, long long total /* N*V */) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long n = i / V, v = i - n * V;
+  const float* sa = a + (size_t)n * ca * V + v;
+  const float* sb = b ? b + (size_t)n * cb * V + v : nullptr;
+  bf16x8* d = reinterpret_cast<bf16x8*>(dst + (size_t)i * CP);
+#pragma unroll
+  for (int j = 0; j < CP / 8; ++j) {
+    float g[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = j * 8 + k;
+      float x = 0.f;
+      if (c < ca) x = __ldg(sa + (size_t)c * V);
+      else if (c < ca + cb) x = __ldg(sb + (size_t)(c - ca) * V);
+      g[k] = x;
+    }
+    d[j] = pack8(g);
+  }
+}
+
+// channels [c_begin, c_begin + c) of an NDHWC bf16 tensor -> NCDHW fp32
+__global__ void unpack_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int cp,
+                                    int c_begin, int c, long long V, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long n = i / V, v = i - n * V;
+  const __nv_bfloat16* s = src + (size_t)i * cp + c_begin;
+  float* d = dst + (size_t)n * c * V + v;
+  for (int k = 0; k < c; ++k) d[(size_t)k * V] = __bfloat162float(s[k]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// statistics: reduce the conv epilogue's per-tile partials to scale / shift (and saved mean, rstd)
+// ------------------------------------------------------------------------------------------------
+// mode 0: InstanceNorm (per sample, per channel; biased variance)       ref: monai ADN "N"
+// mode 1: BatchNorm, training (per channel over N and voxels; updates running stats with
+//         momentum and the unbiased variance)                           ref: model.py:53-54
+// mode 2: BatchNorm, eval (running statistics; partials unused)
+// grid = (Cp/32, N); block = (32, 8)
+__global__ void stats_finalize_kernel(const float* __restrict__ partial, int tiles_per_sample, int Nb, int Cp, int C,
+                                      double count_per_sample, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, float eps, int mode, float momentum,
+                                      float* __restrict__ running_mean, float* __restrict__ running_var,
+                                      float* __restrict__ scale, float* __restrict__ shift,
+                                      float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  __shared__ double sh_s[8][32], sh_q[8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int n = blockIdx.y;
+  double s = 0.0, q = 0.0;
+  if (mode != 2) {
+    const int t0 = mode == 0 ? n * tiles_per_sample : 0;
+    const int t1 = mode == 0 ? t0 + tiles_per_sample : Nb * tiles_per_sample;
+    for (int t = t0 + threadIdx.y; t < t1; t += 8) {
+      s += (double)partial[((size_t)t * 2 + 0) * Cp + c];
+      q += (double)partial[((size_t)t * 2 + 1) * Cp + c];
+    }
+  }
+  sh_s[threadIdx.y][threadIdx.x] = s;
+  sh_q[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y != 0) return;
+  for (int k = 1; k < 8; ++k) { s += sh_s[k][threadIdx.x]; q += sh_q[k][threadIdx.x]; }
+  double mean, var;
+  if (mode == 2) {
+    mean = c < C ? (double)running_mean[c] : 0.0;
+    var = c < C ? (double)running_var[c] : 1.0;
+  } else {
+    const double cnt = mode == 0 ? count_per_sample : count_per_sample * Nb;
+    mean = s / cnt;
+    var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    if (mode == 1 && n == 0 && c < C && running_mean != nullptr) {
+      const double unbiased = cnt > 1.0 ? var * cnt / (cnt - 1.0) : var;
+      running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+      running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+    }
+  }
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  const float g = c < C ? gamma[c] : 0.f, b = c < C ? beta[c] : 0.f;
+  const size_t o = (size_t)n * Cp + c;
+  scale[o] = (float)(g * rstd);
+  shift[o] = (float)(b - mean * g * rstd);
+  mean_out[o] = (float)mean;
+  rstd_out[o] = (float)rstd;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward: a = LeakyReLU(Dropout(y * scale + shift)); optional fused MaxPool3d(2)
+// ------------------------------------------------------------------------------------------------
+__global__ void norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a,
+                                    NormActArgs A, int Cp, long long V, long long total8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int c8 = Cp >> 3;
+  const long long vox = i / c8;
+  const int c0 = (int)(i - vox * c8) * 8;
+  const int n = (int)(vox / V);
+  float x[8];
+  unpack8(reinterpret_cast<const bf16x8*>(y)[i], x);
+  norm_act_apply8(x, A, n, Cp, c0, (unsigned long long)i * 8ull);
+  reinterpret_cast<bf16x8*>(a)[i] = pack8(x);
+}
+
+// thread = (pooled voxel, 8 channels): writes the 8 activated voxels and their max
+__global__ void norm_act_pool_fwd_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a,
+                                         __nv_bfloat16* __restrict__ pooled, NormActArgs A, int Cp, int Nb, int D,
+                                         int H, int W, long long total8 /* pooled voxels * Cp/8 */) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int c8 = Cp >> 3;
+  long long pv = i / c8;
+  const int c0 = (int)(i - pv * c8) * 8;
+  const int Wp = W >> 1, Hp = H >> 1, Dp = D >> 1;
+  const int wx = (int)(pv % Wp); pv /= Wp;
+  const int hy = (int)(pv % Hp); pv /= Hp;
+  const int dz = (int)(pv % Dp);
+  const int n = (int)(pv / Dp);
+  float m[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int d = 2 * dz + (j >> 2), h = 2 * hy + ((j >> 1) & 1), w = 2 * wx + (j & 1);
+    const size_t vox = (((size_t)n * D + d) * H + h) * W + w;
+    const size_t e = vox * c8 + (c0 >> 3);
+    float x[8];
+    unpack8(reinterpret_cast<const bf16x8*>(y)[e], x);
+    norm_act_apply8(x, A, n, Cp, c0, (unsigned long long)e * 8ull);
+    const bf16x8 pk = pack8(x);
+    reinterpret_cast<bf16x8*>(a)[e] = pk;
+    float xr[8];
+    unpack8(pk, xr);  // max over the stored (rounded) values
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = xr[k] > m[k] ? xr[k] : m[k];
+  }
+  reinterpret_cast<bf16x8*>(pooled)[i] = pack8(m);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of (norm -> dropout -> LeakyReLU)
+//   dz1 = dA * lrelu'(a) * keep / (1-p)          (sign(a) == sign of the pre-activation, slope > 0)
+//   reduce: S1[n,c] = sum dz1, S2[n,c] = sum dz1 * xhat,   xhat = (y - mean) * rstd
+//   apply : dy = g*rstd * (dz1 - c1 - xhat * c2),  c1 = S1/cnt, c2 = S2/cnt   (c1 = c2 = 0 in eval-BN / no-norm)
+// ------------------------------------------------------------------------------------------------
+struct NormBwdArgs {
+  const float* mean;    // [N][Cp] (nullptr: no norm)
+  const float* rstd;    // [N][Cp]
+  const float* gscale;  // [N][Cp] gamma * rstd
+  const float* c1;      // [N][Cp]
+  const float* c2;      // [N][Cp]
+  float slope, drop_p;
+  uint32_t drop_seed, drop_thresh;
+};
+
+__device__ __forceinline__ void dz1_8(const bf16x8& da8, const bf16x8& a8, const NormBwdArgs& B,
+                                      unsigned long long e0, float (&dz)[8]) {
+  float da[8], av[8];
+  unpack8(da8, da);
+  unpack8(a8, av);
+  uint32_t keep = 0xFFu;
+  float inv = 1.f;
+  if (B.drop_p > 0.f) {
+    keep = dropout_keep8(e0, B.drop_seed, B.drop_thresh);
+    inv = 1.f / (1.f - B.drop_p);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float g = av[i] > 0.f ? da[i] : da[i] * B.slope;
+    dz[i] = (keep >> i) & 1u ? g * inv : 0.f;
+  }
+}
+
+// grid = (blocks_per_sample, N); each block strides over the voxels of one sample; partial sums are
+// written per block: part[(n * blocks_per_sample + b)][2][Cp]. blockDim.x must be a multiple of Cp/8.
+__global__ void norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a,
+                                           const __nv_bfloat16* __restrict__ y, NormBwdArgs B, int Cp, long long V,
+                                           float* __restrict__ part) {
+  extern __shared__ float sh[];  // [2][blockDim.x][8]
+  const int c8 = Cp >> 3;
+  const int n = blockIdx.y;
+  const int lanes_v = blockDim.x / c8;           // voxels processed per block iteration
+  const int cidx = threadIdx.x % c8, vlane = threadIdx.x / c8;
+  const int c0 = cidx * 8;
+  float mean[8], rstd[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    mean[k] = B.mean ? B.mean[(size_t)n * Cp + c0 + k] : 0.f;
+    rstd[k] = B.rstd ? B.rstd[(size_t)n * Cp + c0 + k] : 0.f;
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+  for (long long v = (long long)blockIdx.x * lanes_v + vlane; v < V; v += (long long)gridDim.x * lanes_v) {
+    const size_t e = ((size_t)n * V + v) * c8 + cidx;
+    float dz[8], yy[8];
+    dz1_8(reinterpret_cast<const bf16x8*>(dA)[e], reinterpret_cast<const bf16x8*>(a)[e], B,
+          (unsigned long long)e * 8ull, dz);
+    unpack8(reinterpret_cast<const bf16x8*>(y)[e], yy);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s1[k] += dz[k];
+      s2[k] += dz[k] * (yy[k] - mean[k]) * rstd[k];
+    }
+  }
+  float* sh1 = sh;
+  float* sh2 = sh + blockDim.x * 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sh1[threadIdx.x * 8 + k] = s1[k]; sh2[threadIdx.x * 8 + k] = s2[k]; }
+  __syncthreads();
+  // threads [0, Cp): channel c sums over the voxel lanes
+  if (threadIdx.x < Cp) {
+    const int c = threadIdx.x;
+    float t1 = 0.f, t2 = 0.f;
+    for (int l = 0; l < lanes_v; ++l) {
+      t1 += sh1[(l * c8 + (c >> 3)) * 8 + (c & 7)];
+      t2 += sh2[(l * c8 + (c >> 3)) * 8 + (c & 7)];
+    }
+    float* p = part + ((size_t)(n * gridDim.x + blockIdx.x) * 2) * Cp;
+    p[c] = t1;
+    p[Cp + c] = t2;
+  }
+}
+
+// Reduce block partials -> c1, c2 per (n,c) and accumulate dgamma / dbeta (/ bias grad in eval-BN).
+// mode as in stats_finalize. grid = (Cp/32), block = 32 threads (tiny).
+__global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, int blocks_per_sample, int Nb, int Cp, int C,
+                                         double count_per_sample, int mode, const float* __restrict__ xscale,
+                                         float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
+                                         float* __restrict__ dbeta, float* __restrict__ dbias) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (c >= Cp) return;
+  double tot1 = 0.0, tot2 = 0.0;
+  for (int n = 0; n < Nb; ++n) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = 0; b < blocks_per_sample; ++b) {
+      const float* p = part + ((size_t)(n * blocks_per_sample + b) * 2) * Cp;
+      s1 += (double)p[c];
+      s2 += (double)p[Cp + c];
+    }
+    tot1 += s1;
+    tot2 += s2;
+    if (mode == 0) {
+      c1[(size_t)n * Cp + c] = (float)(s1 / count_per_sample);
+      c2[(size_t)n * Cp + c] = (float)(s2 / count_per_sample);
+    }
+  }
+  if (mode != 0) {
+    const double cnt = count_per_sample * Nb;
+    for (int n = 0; n < Nb; ++n) {
+      c1[(size_t)n * Cp + c] = mode == 1 ? (float)(tot1 / cnt) : 0.f;
+      c2[(size_t)n * Cp + c] = mode == 1 ? (float)(tot2 / cnt) : 0.f;
+    }
+  }
+  if (c < C) {
+    if (dgamma) dgamma[c] = (float)tot2;
+    if (dbeta) dbeta[c] = (float)tot1;
+    // conv bias feeding a batch-statistics norm has an analytically zero gradient; with running
+    // statistics (eval BatchNorm) it is gamma * rstd * S1.
+    if (dbias) dbias[c] = mode == 2 ? (float)(tot1 * (double)xscale[c]) : 0.f;
+  }
+}
+
+__global__ void norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a,
+                                          const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dy,
+                                          NormBwdArgs B, int Cp, long long V, long long total8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int c8 = Cp >> 3;
+  const long long vox = i / c8;
+  const int c0 = (int)(i - vox * c8) * 8;
+  const int n = (int)(vox / V);
+  float dz[8];
+  dz1_8(reinterpret_cast<const bf16x8*>(dA)[i], reinterpret_cast<const bf16x8*>(a)[i], B,
+        (unsigned long long)i * 8ull, dz);
+  if (B.mean != nullptr) {
+    float yy[8];
+    unpack8(reinterpret_cast<const bf16x8*>(y)[i], yy);
+    const size_t o = (size_t)n * Cp + c0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (yy[k] - B.mean[o + k]) * B.rstd[o + k];
+      dz[k] = B.gscale[o + k] * (dz[k] - B.c1[o + k] - xh * B.c2[o + k]);
+    }
+  }
+  reinterpret_cast<bf16x8*>(dy)[i] = pack8(dz);
+}
+
+// ------------------------------------------------------------------------------------------------
+// MaxPool3d(2) backward: route dP to the first maximum of each window (d,h,w scan order, as torch)
+// thread = (pooled voxel, 8 channels). accumulate != 0: dA += routed grad (skip-path grad already there)
+// ------------------------------------------------------------------------------------------------
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ dP,
+                                   __nv_bfloat16* __restrict__ dA, int accumulate, int Cp, int Nb, int D, int H, int W,
+                                   long long total8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int c8 = Cp >> 3;
+  long long pv = i / c8;
+  const int cidx = (int)(i - pv * c8);
+  const int Wp = W >> 1, Hp = H >> 1, Dp = D >> 1;
+  const int wx = (int)(pv % Wp); pv /= Wp;
+  const int hy = (int)(pv % Hp); pv /= Hp;
+  const int dz = (int)(pv % Dp);
+  const int n = (int)(pv / Dp);
+  float g[8];
+  unpack8(reinterpret_cast<const bf16x8*>(dP)[i], g);
+  float best[8];
+  int arg[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; arg[k] = 0; }
+  size_t e[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int d = 2 * dz + (j >> 2), h = 2 * hy + ((j >> 1) & 1), w = 2 * wx + (j & 1);
+    e[j] = ((((size_t)n * D + d) * H + h) * W + w) * c8 + cidx;
+    float x[8];
+    unpack8(reinterpret_cast<const bf16x8*>(a)[e[j]], x);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (x[k] > best[k]) { best[k] = x[k]; arg[k] = j; }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float o[8];
+    if (accumulate) unpack8(reinterpret_cast<const bf16x8*>(dA)[e[j]], o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = (accumulate ? o[k] : 0.f) + (arg[k] == j ? g[k] : 0.f);
+    reinterpret_cast<bf16x8*>(dA)[e[j]] = pack8(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums of a bf16 [rows][Cp] matrix -> fp32 [C] (bias gradients of convs without a norm)
+// grid = nblocks; block = 256; part[nblocks][Cp]; second launch with rows=nblocks reduces partials
+// ------------------------------------------------------------------------------------------------
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int Cp,
+                                   float* __restrict__ part) {
+  extern __shared__ float sh[];
+  const int c8 = Cp >> 3;
+  const int lanes_v = blockDim.x / c8;
+  const int cidx = threadIdx.x % c8, vlane = threadIdx.x / c8;
+  float s[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = 0.f;
+  if (vlane < lanes_v)
+    for (long long r = (long long)blockIdx.x * lanes_v + vlane; r < rows; r += (long long)gridDim.x * lanes_v) {
+      float v[8];
+      unpack8(reinterpret_cast<const bf16x8*>(x)[(size_t)r * c8 + cidx], v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] += v[k];
+    }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sh[threadIdx.x * 8 + k] = vlane < lanes_v ? s[k] : 0.f;
+  __syncthreads();
+  if (threadIdx.x < Cp) {
+    const int c = threadIdx.x;
+    float t = 0.f;
+    for (int l = 0; l < lanes_v; ++l) t += sh[(l * c8 + (c >> 3)) * 8 + (c & 7)];
+    part[(size_t)blockIdx.x * Cp + c] = t;
+  }
+}
+__global__ void colsum_finish_kernel(const float* __restrict__ part, int nblocks, int Cp, int C,
+                                     float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double t = 0.0;
+  for (int b = 0; b < nblocks; ++b) t += (double)part[(size_t)b * Cp + c];
+  out[c] = (float)t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights: torch fp32 layout -> packed bf16 [block][rows_pad][cols_pad] (K-major rows), and back
+// ------------------------------------------------------------------------------------------------
+struct WeightPackArgs {
+  int nblocks, rows, cols, rows_pad, cols_pad;
+  long long stride_row, stride_col;  // element strides in the fp32 source for (row, col)
+  int src_tap_stride;                // element stride of the source tap index
+  int split_pad, split_real;         // concat: padded channel p >= split_pad maps to real p - split_pad + split_real
+  int split_on_rows;                 // the concatenated (input-channel) axis is rows (dgrad) or cols (fwd)
+  int tapmap[64];                    // packed block -> source tap index
+};
+// padded concat index -> real channel index, or -1 for a pad slot
+__device__ __forceinline__ int concat_real_index(int p, int split_pad, int split_real, int n_real) {
+  if (split_pad == 0) return p < n_real ? p : -1;
+  if (p < split_pad) return p < split_real ? p : -1;
+  const int r = p - split_pad + split_real;
+  return r < n_real ? r : -1;
+}
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, WeightPackArgs A) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)A.nblocks * A.rows_pad * A.cols_pad;
+  if (i >= total) return;
+  const int col = (int)(i % A.cols_pad);
+  const int row = (int)((i / A.cols_pad) % A.rows_pad);
+  const int blk = (int)(i / ((long long)A.cols_pad * A.rows_pad));
+  const int rr = A.split_on_rows ? concat_real_index(row, A.split_pad, A.split_real, A.rows) : (row < A.rows ? row : -1);
+  const int cc = A.split_on_rows ? (col < A.cols ? col : -1) : concat_real_index(col, A.split_pad, A.split_real, A.cols);
+  float v = 0.f;
+  if (rr >= 0 && cc >= 0)
+    v = w[(size_t)rr * A.stride_row + (size_t)cc * A.stride_col + (size_t)A.tapmap[blk] * A.src_tap_stride];
+  out[i] = __float2bfloat16_rn(v);
+}
+
+// split-K reduction of wgrad partials [nsplit][ntap][ci_total][co_total] -> torch layout fp32 grad
+struct WgradReduceArgs {
+  int nsplit, ntap, ci_total, co_total, ci, co;
+  long long stride_ci, stride_co;    // element strides in the destination for (ci, co)
+  int dst_tap_stride;
+  int split_pad, split_real;         // concat mapping of the padded ci index (see WeightPackArgs)
+  int tapmap[64];                    // partial tap index -> destination tap index (-1: skip)
+};
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ grad, WgradReduceArgs A) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_split = (long long)A.ntap * A.ci_total * A.co_total;
+  if (i >= per_split) return;
+  const int co = (int)(i % A.co_total);
+  const int ci = (int)((i / A.co_total) % A.ci_total);
+  const int tap = (int)(i / ((long long)A.co_total * A.ci_total));
+  const int cir = concat_real_index(ci, A.split_pad, A.split_real, A.ci);
+  if (co >= A.co || cir < 0 || A.tapmap[tap] < 0) return;
+  float s = 0.f;
+  for (int k = 0; k < A.nsplit; ++k) s += part[(size_t)k * per_split + i];
+  grad[(size_t)cir * A.stride_ci + (size_t)co * A.stride_co + (size_t)A.tapmap[tap] * A.dst_tap_stride] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// losses (fp32 NCDHW tensors at the module boundary)
+// ------------------------------------------------------------------------------------------------
+// L1: loss = mean |a - b|  (ref: model.py:126,136).  Block partials + last-block finish.
+__global__ void l1_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                              double* __restrict__ part, unsigned int* __restrict__ ticket, float* __restrict__ loss) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i), y = __ldg(reinterpret_cast<const float4*>(b) + i);
+    s += (double)(fabsf(x.x - y.x) + fabsf(x.y - y.y) + fabsf(x.z - y.z) + fabsf(x.w - y.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; ++i) s += (double)fabsf(a[i] - b[i]);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+    part[blockIdx.x] = t;
+    __threadfence();
+    const unsigned int k = atomicAdd(ticket, 1u);
+    if (k == gridDim.x - 1) {
+      double tot = 0.0;
+      for (unsigned int j = 0; j < gridDim.x; ++j) tot += ((volatile double*)part)[j];
+      *loss = (float)(tot / (double)n);
+      *ticket = 0u;
+    }
+  }
+}
+// d a = sign(a - b) * g / n ; g is a device scalar (upstream gradient)
+__global__ void l1_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ g,
+                              long long n, float* __restrict__ da) {
+  const float gs = __ldg(g) / (float)n;
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i), y = __ldg(reinterpret_cast<const float4*>(b) + i);
+    float4 o;
+    o.x = x.x > y.x ? gs : (x.x < y.x ? -gs : 0.f);
+    o.y = x.y > y.y ? gs : (x.y < y.y ? -gs : 0.f);
+    o.z = x.z > y.z ? gs : (x.z < y.z ? -gs : 0.f);
+    o.w = x.w > y.w ? gs : (x.w < y.w ? -gs : 0.f);
+    reinterpret_cast<float4*>(da)[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; ++i) da[i] = a[i] > b[i] ? gs : (a[i] < b[i] ? -gs : 0.f);
+}
+
+// BCE with logits against a constant target t in {0,1} (ref: model.py:155,175,191-192):
+// loss = mean(max(x,0) - x t + log1p(exp(-|x|))); unit gradient (sigmoid(x) - t) / n is emitted in the
+// same pass. One block (the PatchGAN logit map is tiny).
+__global__ void bce_logits_kernel(const float* __restrict__ x, float target, int n, float* __restrict__ loss,
+                                  float* __restrict__ dx_unit) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = x[i];
+    s += (double)(fmaxf(v, 0.f) - v * target + log1pf(expf(-fabsf(v))));
+    if (dx_unit) dx_unit[i] = (1.f / (1.f + expf(-v)) - target) / (float)n;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+    *loss = (float)(t / n);
+  }
+}
+
+// y[i] = x[i] * (*g)   (scale a unit gradient by a device scalar)
+__global__ void scale_by_scalar_kernel(const float* __restrict__ x, const float* __restrict__ g, long long n,
+                                       float* __restrict__ y) {
+  const float gs = __ldg(g);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = x[i] * gs;
+}
+
+// ------------------------------------------------------------------------------------------------
+// evaluation: per-voxel relative error + masked, probseg-weighted ROI means
+//   ref: eval.py:154-166 (do_calc_diff_maps) and eval.py:217-258 (do_calc_error_avg)
+// Volumes are channel-last [X][Y][Z][C] as nibabel stores them (np.moveaxis(0,-1), model.py:344-346).
+//   angular == 0: diff = |p - t| / t          (division by zero gives inf / nan exactly as numpy)
+//   angular == 1: d = (p - t) mod 360 (python sign convention), diff = d < 180 ? d : 360 - d
+// Reduction: e = |diff|; e = mask > 0 ? e : 0; e = (e == inf) ? 0 : e (NaN kept);
+//            sums[r][c] += probseg[v][r] * e;  norms[r] += probseg[v][r]
+// ------------------------------------------------------------------------------------------------
+__global__ void relerr_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
+                              const unsigned char* __restrict__ mask, const float* __restrict__ probseg, int C, int R,
+                              long long nvox, int angular, float* __restrict__ diff, double* __restrict__ sums,
+                              double* __restrict__ norms) {
+  // per-thread accumulators for up to 3 ROIs x 8 channels
+  double acc[3][8];
+  double nrm[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    nrm[r] = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[r][c] = 0.0;
+  }
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (long long)gridDim.x * blockDim.x) {
+    float ps[3] = {0.f, 0.f, 0.f};
+    if (probseg)
+      for (int r = 0; r < R; ++r) { ps[r] = probseg[(size_t)v * R + r]; nrm[r] += (double)ps[r]; }
+    const bool in_mask = mask ? mask[v] > 0 : true;
+    for (int c = 0; c < C; ++c) {
+      const float p = pred[(size_t)v * C + c], t = tgt[(size_t)v * C + c];
+      float d;
+      if (!angular) {
+        d = fabsf(p - t) / t;
+      } else {
+        float m = fmodf(p - t, 360.f);
+        if (m < 0.f) m += 360.f;
+        d = m < 180.f ? m : 360.f - m;
+      }
+      if (diff) diff[(size_t)v * C + c] = d;
+      float e = fabsf(d);
+      e = in_mask ? e : 0.f;
+      e = isinf(e) ? 0.f : e;
+      if (probseg)
+        for (int r = 0; r < R; ++r) acc[r][c] += (double)ps[r] * (double)e;
+    }
+  }
+  if (!probseg) return;
+  // warp reduce then one atomic per warp per entry (3*8+3 doubles)
+  for (int r = 0; r < R; ++r) {
+    double t = nrm[r];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(norms + r, t);
+    for (int c = 0; c < C; ++c) {
+      double s = acc[r][c];
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if ((threadIdx.x & 31) == 0) atomicAdd(sums + r * C + c, s);
+    }
+  }
+}
+
+}  // namespace ub

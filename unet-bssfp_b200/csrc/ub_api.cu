@@ -1,0 +1,759 @@
+// libubssfp.so -- host planners + C ABI (include/ub_api.h) over the sm_100a kernels.
+// No torch types cross this boundary; no CPU fallback exists: an unsupported request is an error.
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include "../../include/ub_api.h"
+#include "igemm_fwd.cuh"
+#include "igemm_wgrad.cuh"
+#include "pointwise.cuh"
+
+using namespace ub;
+
+// --------------------------------------------------------------------------------------------------
+// errors
+// --------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define UB_CUDA(x)                                                                         \
+  do {                                                                                     \
+    cudaError_t e_ = (x);                                                                  \
+    if (e_ != cudaSuccess) return fail(-3, "%s failed: %s", #x, cudaGetErrorString(e_));   \
+  } while (0)
+#define UB_LAUNCH_CHECK()                                                                  \
+  do {                                                                                     \
+    cudaError_t e_ = cudaGetLastError();                                                   \
+    if (e_ != cudaSuccess) return fail(-3, "kernel launch failed: %s", cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" int ub_version(void) { return 100; }
+extern "C" const char* ub_last_error(void) { return g_err; }
+
+// --------------------------------------------------------------------------------------------------
+// tensor maps
+// --------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+static int ensure_encode() {
+  std::call_once(g_encode_once, [] {
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess)
+      g_encode = (EncodeTiledFn)fn;
+  });
+  return g_encode ? 0 : fail(-3, "cuTensorMapEncodeTiled unavailable (no CUDA driver / no GPU)");
+}
+static CUtensorMapSwizzle swz_for_bytes(int b) {
+  return b == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : b == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+// NDHWC bf16 activation: dims (C, W, H, D, N); box (box_c, bw*es, bh*es, 1, 1); element stride es on w,h
+static int make_act_map(CUtensorMap* m, const void* ptr, int cp, int W, int H, int D, int N, int box_c, int bw,
+                        int bh, int es) {
+  cuuint64_t gd[5] = {(cuuint64_t)cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t gs[4] = {(cuuint64_t)cp * 2, (cuuint64_t)W * cp * 2, (cuuint64_t)H * W * cp * 2,
+                      (cuuint64_t)D * H * W * cp * 2};
+  cuuint32_t bx[5] = {(cuuint32_t)box_c, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), 1, 1};
+  cuuint32_t st[5] = {1, (cuuint32_t)es, (cuuint32_t)es, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), gd, gs, bx, st,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz_for_bytes(box_c * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : fail(-3, "cuTensorMapEncodeTiled(act) failed: %d", (int)r);
+}
+// packed weights [rows][K] bf16: dims (K, rows); box (kc, nt)
+static int make_w_map(CUtensorMap* m, const void* ptr, long long K, long long rows, int kc, int nt) {
+  cuuint64_t gd[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gs[1] = {(cuuint64_t)K * 2};
+  cuuint32_t bx[2] = {(cuuint32_t)kc, (cuuint32_t)nt};
+  cuuint32_t st[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gd, gs, bx, st,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz_for_bytes(kc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : fail(-3, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+}
+
+// --------------------------------------------------------------------------------------------------
+// descriptor helpers
+// --------------------------------------------------------------------------------------------------
+static int check_desc(const ub_conv_desc* d) {
+  if (!d) return fail(-1, "null conv desc");
+  if (d->kind < 0 || d->kind > 3) return fail(-1, "bad conv kind %d", d->kind);
+  if (d->n <= 0 || d->d <= 0 || d->h <= 0 || d->w <= 0) return fail(-1, "bad conv dims");
+  if (d->c0p <= 0 || d->c0p % 32 || d->c1p % 32 || d->cop <= 0 || d->cop % 32)
+    return fail(-1, "padded channel counts must be positive multiples of 32 (c0p=%d c1p=%d cop=%d)", d->c0p, d->c1p,
+                d->cop);
+  if (d->c0 > d->c0p || d->c1 > d->c1p || d->co > d->cop) return fail(-1, "real channels exceed padded channels");
+  if (d->kind == UB_CONV_K4S2P1 && ((d->d | d->h | d->w) & 1)) return fail(-1, "k4s2p1 needs even input dims");
+  if (d->kind == UB_DECONV_K2S2 && d->c1p) return fail(-1, "transposed conv takes one source");
+  if (d->cop > 128 && d->cop % 128) return fail(-1, "cop > 128 must be a multiple of 128");
+  return 0;
+}
+static int ntaps_of(int kind) { return kind == UB_CONV_K3S1P1 ? 27 : kind == UB_CONV_K1 ? 1 : kind == UB_CONV_K4S2P1 ? 64 : 8; }
+static void out_dims(const ub_conv_desc* d, int* od, int* oh, int* ow) {
+  if (d->kind == UB_CONV_K4S2P1) { *od = d->d / 2; *oh = d->h / 2; *ow = d->w / 2; }
+  else if (d->kind == UB_DECONV_K2S2) { *od = d->d * 2; *oh = d->h * 2; *ow = d->w * 2; }
+  else { *od = d->d; *oh = d->h; *ow = d->w; }
+}
+static inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static int next_pow2_cols(int c) { int p = 32; while (p < c) p <<= 1; return p; }
+
+extern "C" long long ub_packed_weight_elems(const ub_conv_desc* d, int dir) {
+  if (check_desc(d)) return -1;
+  const long long cin = d->c0p + d->c1p;
+  (void)dir;
+  return (long long)ntaps_of(d->kind) * d->cop * cin;
+}
+
+extern "C" int ub_pack_conv_weights(const ub_conv_desc* d, int dir, const float* w, void* packed, void* stream) {
+  if (int e = check_desc(d)) return e;
+  if (!w || !packed) return fail(-1, "null weight pointer");
+  const int nt = ntaps_of(d->kind);
+  const int ci = d->c0 + d->c1;
+  WeightPackArgs A;
+  memset(&A, 0, sizeof(A));
+  A.nblocks = nt;
+  const bool deconv = d->kind == UB_DECONV_K2S2;
+  // source strides of (co, ci, tap)
+  const long long s_co = deconv ? nt : (long long)ci * nt;
+  const long long s_ci = deconv ? (long long)d->co * nt : nt;
+  if (dir == 0) {  // rows = co, cols = ci
+    A.rows = d->co; A.rows_pad = d->cop; A.cols = ci; A.cols_pad = d->c0p + d->c1p;
+    A.stride_row = s_co; A.stride_col = s_ci;
+    for (int t = 0; t < nt; ++t) A.tapmap[t] = t;
+  } else {         // rows = ci, cols = co ; 3x3x3 dgrad correlates with the flipped filter
+    A.rows = ci; A.rows_pad = d->c0p + d->c1p; A.cols = d->co; A.cols_pad = d->cop;
+    A.stride_row = s_ci; A.stride_col = s_co;
+    for (int t = 0; t < nt; ++t) A.tapmap[t] = d->kind == UB_CONV_K3S1P1 ? nt - 1 - t : t;
+  }
+  A.src_tap_stride = 1;
+  // concat split: padded index -> real channel (source 1 starts at c0p in padded space, c0 in real space)
+  A.split_pad = d->c1p ? d->c0p : 0;
+  A.split_real = d->c1p ? d->c0 : 0;
+  A.split_on_rows = dir == 1;
+  const long long total = (long long)A.nblocks * A.rows_pad * A.cols_pad;
+  pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(packed), A);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------
+// igemm launch plumbing
+// --------------------------------------------------------------------------------------------------
+static const int kSmemBudget = 220 * 1024;
+
+struct IgemmPlan {
+  IgemmParams P;
+  dim3 grid;
+  int smem;
+};
+
+// Fill the smem plan / grid once the geometry fields of P are set. nt_max = widest N tile.
+static int finish_plan(IgemmPlan* pl, int nt_max) {
+  IgemmParams& P = pl->P;
+  const int pitch = P.kc * 2;
+  P.plane_stride = align_up(P.bh * P.bw * pitch, 1024);
+  P.a_stage_bytes = P.n_atiles * P.n_in_planes * P.plane_stride;
+  P.b_stage_bytes = align_up(nt_max * pitch, 1024);
+  P.nsb = 4;
+  const int misc = 8 * 64 + 16 + 4096 + 1024;
+  P.nsa = 2;
+  if (2 * P.a_stage_bytes + P.nsb * P.b_stage_bytes + misc > kSmemBudget) P.nsa = 1;
+  if (P.n_chunks_total == 1) P.nsa = 1;
+  pl->smem = P.nsa * P.a_stage_bytes + P.nsb * P.b_stage_bytes + misc;
+  if (pl->smem > 227 * 1024) return fail(-2, "igemm smem plan too large: %d bytes", pl->smem);
+  P.tmem_cols = next_pow2_cols(P.td * align_up(nt_max, 32));
+  if (P.tmem_cols > 512) return fail(-2, "igemm TMEM plan too large: %d columns", P.tmem_cols);
+  P.tiles_w = cdiv(P.Wo, 8);
+  P.tiles_h = cdiv(P.Ho, 16);
+  P.tiles_d = cdiv(P.Do, P.td);
+  pl->grid = dim3((unsigned)(P.Nb * P.tiles_d * P.tiles_h * P.tiles_w), (unsigned)P.n_ntiles, 1);
+  return 0;
+}
+
+static int launch_igemm(const IgemmPlan& pl, cudaStream_t st) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(igemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) return fail(-3, "cudaFuncSetAttribute(igemm_fwd): %s", cudaGetErrorString(attr_err));
+  igemm_fwd_kernel<<<pl.grid, kIgemmThreads, pl.smem, st>>>(pl.P);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+// Map the output columns onto N tiles of <= 128. Two destinations (dgrad of a skip-concat conv:
+// columns [0,n0p) -> dst0, [n0p, n0p+n1p) -> dst1) share one tile when they fit in 128 columns.
+static void make_ntiles(IgemmParams& P, int n0p, void* dst0, int n1p, void* dst1) {
+  P.n_ntiles = 0;
+  if (n1p && n0p + n1p <= 128) {
+    IgemmNTile& T = P.ntile[P.n_ntiles++];
+    T.n0 = 0; T.nt = n0p + n1p; T.out = dst0; T.out_cpitch = n0p; T.out_coff = 0;
+    T.split = n0p; T.out2 = dst1; T.out2_cpitch = n1p;
+    return;
+  }
+  for (int s = 0; s < 2; ++s) {
+    const int np = s ? n1p : n0p;
+    void* dst = s ? dst1 : dst0;
+    for (int c = 0; c < np; c += 128) {
+      IgemmNTile& T = P.ntile[P.n_ntiles++];
+      T.n0 = (s ? n0p : 0) + c;
+      T.nt = np - c < 128 ? np - c : 128;
+      T.out = dst;
+      T.out_cpitch = np;
+      T.out_coff = c;
+      T.split = T.nt; T.out2 = dst; T.out2_cpitch = np;
+    }
+  }
+}
+
+// per-axis decomposition of the k=4,s=2,p=1 filter index: input i = 2*o - 1 + k
+//   k -> (parity of i, shift inside the parity tile whose origin offset is (parity ? -1 : 0))
+static inline int k4_parity(int k) { return (k & 1) ? 0 : 1; }
+static inline int k4_shift(int k) { return k >> 1; }
+
+extern "C" int ub_conv_num_tiles(const ub_conv_desc* d) {
+  if (check_desc(d)) return -1;
+  int od, oh, ow;
+  out_dims(d, &od, &oh, &ow);
+  int td = 4;
+  int Dt = od, Ht = oh, Wt = ow;
+  if (d->kind == UB_CONV_K4S2P1) td = 1;
+  if (d->kind == UB_DECONV_K2S2) { Dt = d->d; Ht = d->h; Wt = d->w; }
+  if (td > Dt) td = Dt;
+  return d->n * cdiv(Dt, td) * cdiv(Ht, 16) * cdiv(Wt, 8);
+}
+
+extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* src1, const void* w_packed,
+                           const float* bias, int act, float slope, void* out, float* stats_partial, void* stream) {
+  if (int e = check_desc(d)) return e;
+  if (int e = ensure_encode()) return e;
+  if (!src0 || !w_packed || !out) return fail(-1, "null pointer in ub_conv_fwd");
+  if (d->c1p && !src1) return fail(-1, "second source missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  int od, oh, ow;
+  out_dims(d, &od, &oh, &ow);
+  const int ktot = d->c0p + d->c1p;
+  const int ntaps = ntaps_of(d->kind);
+
+  IgemmPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  IgemmParams& P = pl.P;
+  P.kc = 32;
+  P.n_chunks_src0 = d->c0p / 32;
+  P.n_chunks_total = ktot / 32;
+  P.w_rows_per_block = d->cop;
+  P.Nb = d->n;
+  P.bias = bias;
+  P.bias_n = d->co;
+  P.act = act;
+  P.act_slope = slope;
+  P.stats = stats_partial;
+  P.oD = od; P.oH = oh; P.oW = ow;
+  P.out_s = 1;
+  make_ntiles(P, d->cop, out, 0, nullptr);
+  const int nt_max = d->cop < 128 ? d->cop : 128;
+  if (int e = make_w_map(&P.tm_w, w_packed, ktot, (long long)ntaps * d->cop, 32, nt_max)) return e;
+  if (d->cop > 128 || d->cop == nt_max) { /* all N tiles have nt_max columns */ }
+
+  if (d->kind == UB_CONV_K3S1P1 || d->kind == UB_CONV_K1) {
+    const int k = d->kind == UB_CONV_K3S1P1 ? 3 : 1;
+    P.td = d->d < 4 ? d->d : 4;
+    P.Do = od; P.Ho = oh; P.Wo = ow;
+    P.n_atiles = 1; P.bw = 8 + k - 1; P.bh = 16 + k - 1; P.n_in_planes = P.td + k - 1; P.in_stride = 1;
+    P.atile_off[0][0] = P.atile_off[0][1] = P.atile_off[0][2] = -(k / 2);
+    P.ntaps = ntaps;
+    int t = 0;
+    for (int kd = 0; kd < k; ++kd)
+      for (int kh = 0; kh < k; ++kh)
+        for (int kw = 0; kw < k; ++kw, ++t)
+          P.taps[t] = IgemmTap{0, (uint16_t)(kh * P.bw + kw), (uint16_t)kd, (uint16_t)t};
+    if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 1)) return e;
+    if (d->c1p)
+      if (int e = make_act_map(&P.tm_src[1], src1, d->c1p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 1)) return e;
+    if (int e = finish_plan(&pl, nt_max)) return e;
+    return launch_igemm(pl, st);
+  }
+  if (d->kind == UB_CONV_K4S2P1) {
+    P.td = 1;
+    P.Do = od; P.Ho = oh; P.Wo = ow;
+    P.n_atiles = 8; P.bw = 9; P.bh = 17; P.n_in_planes = 2; P.in_stride = 2;
+    for (int pd = 0; pd < 2; ++pd)
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+          const int at = (pd * 2 + ph) * 2 + pw;
+          P.atile_off[at][0] = pw ? -1 : 0;
+          P.atile_off[at][1] = ph ? -1 : 0;
+          P.atile_off[at][2] = pd ? -1 : 0;
+        }
+    P.ntaps = 64;
+    int t = 0;
+    for (int kd = 0; kd < 4; ++kd)
+      for (int kh = 0; kh < 4; ++kh)
+        for (int kw = 0; kw < 4; ++kw, ++t) {
+          const int at = (k4_parity(kd) * 2 + k4_parity(kh)) * 2 + k4_parity(kw);
+          P.taps[t] = IgemmTap{(uint16_t)at, (uint16_t)(k4_shift(kh) * P.bw + k4_shift(kw)), (uint16_t)k4_shift(kd),
+                               (uint16_t)t};
+        }
+    if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 2)) return e;
+    if (d->c1p)
+      if (int e = make_act_map(&P.tm_src[1], src1, d->c1p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 2)) return e;
+    if (int e = finish_plan(&pl, nt_max)) return e;
+    return launch_igemm(pl, st);
+  }
+  // UB_DECONV_K2S2 forward: 8 sub-position launches, 1 tap each, scatter store with stride 2
+  P.td = d->d < 4 ? d->d : 4;
+  P.Do = d->d; P.Ho = d->h; P.Wo = d->w;
+  P.n_atiles = 1; P.bw = 8; P.bh = 16; P.n_in_planes = P.td; P.in_stride = 1;
+  P.ntaps = 1;
+  P.out_s = 2;
+  if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 1)) return e;
+  if (int e = finish_plan(&pl, nt_max)) return e;
+  if (stats_partial) return fail(-1, "statistics are not produced by the transposed conv forward");
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j)
+      for (int k = 0; k < 2; ++k) {
+        P.taps[0] = IgemmTap{0, 0, 0, (uint16_t)((i * 2 + j) * 2 + k)};
+        P.out_p[0] = k; P.out_p[1] = j; P.out_p[2] = i;
+        if (int e = launch_igemm(pl, st)) return e;
+      }
+  return 0;
+}
+
+extern "C" int ub_conv_dgrad(const ub_conv_desc* d, const void* dy, const void* w_packed_dgrad, void* dsrc0,
+                             void* dsrc1, void* stream) {
+  if (int e = check_desc(d)) return e;
+  if (int e = ensure_encode()) return e;
+  if (!dy || !w_packed_dgrad || !dsrc0) return fail(-1, "null pointer in ub_conv_dgrad");
+  if (d->c1p && !dsrc1) return fail(-1, "second gradient destination missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  int od, oh, ow;
+  out_dims(d, &od, &oh, &ow);
+  const int ntaps = ntaps_of(d->kind);
+  const int ncols = d->c0p + d->c1p;
+
+  IgemmPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  IgemmParams& P = pl.P;
+  P.kc = 32;
+  P.n_chunks_src0 = d->cop / 32;
+  P.n_chunks_total = d->cop / 32;
+  P.w_rows_per_block = ncols;
+  P.Nb = d->n;
+  P.oD = d->d; P.oH = d->h; P.oW = d->w;
+  P.out_s = 1;
+  make_ntiles(P, d->c0p, dsrc0, d->c1p, dsrc1);
+  int nt_max = 0;
+  for (int i = 0; i < P.n_ntiles; ++i) nt_max = P.ntile[i].nt > nt_max ? P.ntile[i].nt : nt_max;
+  // N tiles may have different widths; the weight box uses the widest, narrower tiles read extra rows
+  // of the following tap block / pad rows (never used by their MMA: idesc N = nt)
+  if (int e = make_w_map(&P.tm_w, w_packed_dgrad, d->cop, (long long)ntaps * ncols, 32, nt_max)) return e;
+  bool uniform = true;
+  for (int i = 0; i < P.n_ntiles; ++i) uniform = uniform && P.ntile[i].nt == nt_max;
+  if (!uniform) return fail(-2, "dgrad N tiles of unequal width are not supported (c0p=%d c1p=%d)", d->c0p, d->c1p);
+
+  if (d->kind == UB_CONV_K3S1P1 || d->kind == UB_CONV_K1) {
+    const int k = d->kind == UB_CONV_K3S1P1 ? 3 : 1;
+    P.td = d->d < 4 ? d->d : 4;
+    P.Do = d->d; P.Ho = d->h; P.Wo = d->w;
+    P.n_atiles = 1; P.bw = 8 + k - 1; P.bh = 16 + k - 1; P.n_in_planes = P.td + k - 1; P.in_stride = 1;
+    P.atile_off[0][0] = P.atile_off[0][1] = P.atile_off[0][2] = -(k / 2);
+    P.ntaps = ntaps;
+    int t = 0;
+    for (int kd = 0; kd < k; ++kd)
+      for (int kh = 0; kh < k; ++kh)
+        for (int kw = 0; kw < k; ++kw, ++t)
+          P.taps[t] = IgemmTap{0, (uint16_t)(kh * P.bw + kw), (uint16_t)kd, (uint16_t)t};
+    if (int e = make_act_map(&P.tm_src[0], dy, d->cop, ow, oh, od, d->n, 32, P.bw, P.bh, 1)) return e;
+    if (int e = finish_plan(&pl, nt_max)) return e;
+    return launch_igemm(pl, st);
+  }
+  if (d->kind == UB_CONV_K4S2P1) {
+    // 8 input parity classes; class p (per axis): p=0 -> taps (o=q-1,k=3),(o=q,k=1); p=1 -> (o=q,k=2),(o=q+1,k=0)
+    P.td = od < 4 ? od : 4;
+    P.Do = od; P.Ho = oh; P.Wo = ow;  // tile space = q grid (same size as dy)
+    P.n_atiles = 1; P.bw = 9; P.bh = 17; P.n_in_planes = P.td + 1; P.in_stride = 1;
+    P.ntaps = 8;
+    P.out_s = 2;
+    if (int e = make_act_map(&P.tm_src[0], dy, d->cop, ow, oh, od, d->n, 32, P.bw, P.bh, 1)) return e;
+    if (int e = finish_plan(&pl, nt_max)) return e;
+    for (int pd = 0; pd < 2; ++pd)
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+          P.atile_off[0][0] = pw ? 0 : -1;
+          P.atile_off[0][1] = ph ? 0 : -1;
+          P.atile_off[0][2] = pd ? 0 : -1;
+          P.out_p[0] = pw; P.out_p[1] = ph; P.out_p[2] = pd;
+          int t = 0;
+          for (int sd = 0; sd < 2; ++sd)
+            for (int sh = 0; sh < 2; ++sh)
+              for (int sw = 0; sw < 2; ++sw, ++t) {
+                // shift s of class p: p=0 -> k = 3 - 2 s ; p=1 -> k = 2 - 2 s
+                const int kd = pd ? 2 - 2 * sd : 3 - 2 * sd;
+                const int kh = ph ? 2 - 2 * sh : 3 - 2 * sh;
+                const int kw = pw ? 2 - 2 * sw : 3 - 2 * sw;
+                P.taps[t] = IgemmTap{0, (uint16_t)(sh * P.bw + sw), (uint16_t)sd, (uint16_t)((kd * 4 + kh) * 4 + kw)};
+              }
+          if (int e = launch_igemm(pl, st)) return e;
+        }
+    return 0;
+  }
+  // UB_DECONV_K2S2 dgrad: gather the 8 fine sub-positions (parity tiles of dy, element stride 2)
+  P.td = d->d < 2 ? d->d : 2;
+  P.Do = d->d; P.Ho = d->h; P.Wo = d->w;
+  P.n_atiles = 8; P.bw = 8; P.bh = 16; P.n_in_planes = P.td; P.in_stride = 2;
+  P.ntaps = 8;
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j)
+      for (int k = 0; k < 2; ++k) {
+        const int at = (i * 2 + j) * 2 + k;
+        P.atile_off[at][0] = k; P.atile_off[at][1] = j; P.atile_off[at][2] = i;
+        P.taps[at] = IgemmTap{(uint16_t)at, 0, 0, (uint16_t)at};
+      }
+  if (int e = make_act_map(&P.tm_src[0], dy, d->cop, ow, oh, od, d->n, 32, P.bw, P.bh, 2)) return e;
+  if (int e = finish_plan(&pl, nt_max)) return e;
+  return launch_igemm(pl, st);
+}
+
+// --------------------------------------------------------------------------------------------------
+// wgrad
+// --------------------------------------------------------------------------------------------------
+struct WgradPlan {
+  WgradParams P;
+  dim3 grid;
+  int smem;
+  int ntap_lin;
+  int tapmap[64];
+};
+
+static int plan_wgrad(const ub_conv_desc* d, WgradPlan* pl) {
+  WgradParams& P = pl->P;
+  memset(pl, 0, sizeof(*pl));
+  int od, oh, ow;
+  out_dims(d, &od, &oh, &ow);
+  P.n_chunks_src0 = d->c0p / 32;
+  P.n_chunks_total = (d->c0p + d->c1p) / 32;
+  P.ci_total = d->c0p + d->c1p;
+  P.co_total = d->cop;
+  P.nt = d->cop < 128 ? d->cop : 128;
+  P.n_cotiles = d->cop / P.nt;
+  P.ncb = P.nt < 64 ? P.nt : 64;
+  P.Nb = d->n;
+  P.x_stride = 1; P.dy_stride = 1;
+  for (int i = 0; i < 64; ++i) pl->tapmap[i] = -1;
+  if (d->kind == UB_CONV_K3S1P1) {
+    P.bw = 10; P.bh = 18; P.Dt = od; P.Ht = oh; P.Wt = ow;
+    P.n_variants = 3; P.ngroups = 3; P.group_row_step = P.bw; P.natoms = 3;
+    for (int kd = 0; kd < 3; ++kd) { P.x_off[kd][0] = -1; P.x_off[kd][1] = -1; P.x_off[kd][2] = kd - 1; }
+    for (int t = 0; t < 27; ++t) pl->tapmap[t] = t;
+  } else if (d->kind == UB_CONV_K1) {
+    P.bw = 8; P.bh = 16; P.Dt = od; P.Ht = oh; P.Wt = ow;
+    P.n_variants = 1; P.ngroups = 1; P.group_row_step = 0; P.natoms = 1;
+    pl->tapmap[0] = 0;
+  } else if (d->kind == UB_CONV_K4S2P1) {
+    P.bw = 9; P.bh = 17; P.Dt = od; P.Ht = oh; P.Wt = ow;
+    P.x_stride = 2;
+    P.n_variants = 16; P.ngroups = 2; P.group_row_step = P.bw; P.natoms = 2;
+    for (int pd = 0; pd < 2; ++pd)
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw)
+          for (int sd = 0; sd < 2; ++sd) {
+            const int v = ((pd * 2 + ph) * 2 + pw) * 2 + sd;
+            P.x_off[v][0] = pw ? -1 : 0;
+            P.x_off[v][1] = ph ? -1 : 0;
+            P.x_off[v][2] = 2 * sd + (pd ? -1 : 0);
+            for (int sh = 0; sh < 2; ++sh)
+              for (int sw = 0; sw < 2; ++sw) {
+                const int kd = 2 * sd + (1 - pd), kh = 2 * sh + (1 - ph), kw = 2 * sw + (1 - pw);
+                pl->tapmap[(v * 2 + sh) * 2 + sw] = (kd * 4 + kh) * 4 + kw;
+              }
+          }
+  } else {  // deconv: X coarse (no halo), dy = fine grid at parity (i,j,k)
+    P.bw = 8; P.bh = 16; P.Dt = d->d; P.Ht = d->h; P.Wt = d->w;
+    P.dy_stride = 2;
+    P.n_variants = 8; P.ngroups = 1; P.group_row_step = 0; P.natoms = 1;
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 2; ++j)
+        for (int k = 0; k < 2; ++k) {
+          const int v = (i * 2 + j) * 2 + k;
+          P.dy_off[v][0] = k; P.dy_off[v][1] = j; P.dy_off[v][2] = i;
+          pl->tapmap[v] = v;
+        }
+  }
+  pl->ntap_lin = P.n_variants * P.ngroups * P.natoms;
+  P.tiles_w = cdiv(P.Wt, 8);
+  P.tiles_h = cdiv(P.Ht, 16);
+  P.x_stage_bytes = align_up(P.bh * P.bw * 64, 1024);
+  P.dy_stage_bytes = 128 * P.nt * 2;
+  const int stage = P.x_stage_bytes + P.dy_stage_bytes;
+  P.nstages = (200 * 1024) / stage;
+  if (P.nstages > 4) P.nstages = 4;
+  if (P.nstages < 2) return fail(-2, "wgrad stage too large");
+  pl->smem = P.nstages * stage + 8 * 16 + 64 + 1024;
+  P.tmem_cols = next_pow2_cols(P.ngroups * align_up(P.nt, 32));
+  const long long total_tiles = (long long)P.Nb * P.Dt * P.tiles_h * P.tiles_w;
+  const int items = P.n_chunks_total * P.n_variants * P.n_cotiles;
+  long long nsplit = cdiv(2 * 148, items);
+  if (nsplit > total_tiles) nsplit = total_tiles;
+  if (nsplit < 1) nsplit = 1;
+  pl->grid = dim3((unsigned)nsplit, (unsigned)items, 1);
+  return 0;
+}
+
+extern "C" long long ub_conv_wgrad_workspace_bytes(const ub_conv_desc* d) {
+  if (check_desc(d)) return -1;
+  WgradPlan pl;
+  if (plan_wgrad(d, &pl)) return -1;
+  return (long long)pl.grid.x * pl.ntap_lin * pl.P.ci_total * pl.P.co_total * 4;
+}
+
+extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void* src1, const void* dy,
+                             void* workspace, float* dw, void* stream) {
+  if (int e = check_desc(d)) return e;
+  if (int e = ensure_encode()) return e;
+  if (!src0 || !dy || !workspace || !dw) return fail(-1, "null pointer in ub_conv_wgrad");
+  if (d->c1p && !src1) return fail(-1, "second source missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  WgradPlan pl;
+  if (int e = plan_wgrad(d, &pl)) return e;
+  WgradParams& P = pl.P;
+  int od, oh, ow;
+  out_dims(d, &od, &oh, &ow);
+  P.partial = reinterpret_cast<float*>(workspace);
+  if (int e = make_act_map(&P.tm_x[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, P.x_stride)) return e;
+  if (d->c1p)
+    if (int e = make_act_map(&P.tm_x[1], src1, d->c1p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, P.x_stride)) return e;
+  if (int e = make_act_map(&P.tm_dy, dy, d->cop, ow, oh, od, d->n, P.ncb, 8, 16, P.dy_stride)) return e;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) return fail(-3, "cudaFuncSetAttribute(igemm_wgrad): %s", cudaGetErrorString(attr_err));
+  igemm_wgrad_kernel<<<pl.grid, kIgemmThreads, pl.smem, st>>>(P);
+  UB_LAUNCH_CHECK();
+
+  // split-K reduce + conversion to the torch layout
+  WgradReduceArgs R;
+  memset(&R, 0, sizeof(R));
+  const int ntaps = ntaps_of(d->kind);
+  const int ci = d->c0 + d->c1;
+  R.nsplit = (int)pl.grid.x; R.ntap = pl.ntap_lin; R.ci_total = P.ci_total; R.co_total = P.co_total;
+  R.ci = ci; R.co = d->co;
+  if (d->kind == UB_DECONV_K2S2) { R.stride_ci = (long long)d->co * ntaps; R.stride_co = ntaps; }
+  else { R.stride_ci = ntaps; R.stride_co = (long long)ci * ntaps; }
+  R.dst_tap_stride = 1;
+  R.split_pad = d->c1p ? d->c0p : 0;
+  R.split_real = d->c1p ? d->c0 : 0;
+  for (int i = 0; i < 64; ++i) R.tapmap[i] = i < pl.ntap_lin ? pl.tapmap[i] : -1;
+  const long long per_split = (long long)R.ntap * R.ci_total * R.co_total;
+  wgrad_reduce_kernel<<<(unsigned)((per_split + 255) / 256), 256, 0, st>>>(P.partial, dw, R);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------
+// layout
+// --------------------------------------------------------------------------------------------------
+extern "C" int ub_pack_ncdhw(const float* a, int ca, const float* b, int cb, int n, long long voxels, int cp,
+                             void* out, void* stream) {
+  if (!a || !out || ca <= 0 || (cb > 0 && !b)) return fail(-1, "bad arguments to ub_pack_ncdhw");
+  if (ca + cb > cp || cp % 32 || cp > 64) return fail(-1, "ub_pack_ncdhw supports cp in {32, 64}, got ca=%d cb=%d cp=%d", ca, cb, cp);
+  const long long total = (long long)n * voxels;
+  const unsigned blocks = (unsigned)((total + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cp == 32) pack_ncdhw_kernel<32><<<blocks, 128, 0, st>>>(a, ca, b, cb, reinterpret_cast<__nv_bfloat16*>(out), voxels, total);
+  else pack_ncdhw_kernel<64><<<blocks, 128, 0, st>>>(a, ca, b, cb, reinterpret_cast<__nv_bfloat16*>(out), voxels, total);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ub_unpack_ncdhw(const void* src, int cp, int c_begin, int c, int n, long long voxels, float* out,
+                               void* stream) {
+  if (!src || !out || c <= 0 || c_begin < 0 || c_begin + c > cp || cp % 8) return fail(-1, "bad arguments to ub_unpack_ncdhw");
+  const long long total = (long long)n * voxels;
+  unpack_ncdhw_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), out, cp, c_begin, c, voxels, total);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------
+// norm / act
+// --------------------------------------------------------------------------------------------------
+extern "C" int ub_norm_finalize(const float* stats_partial, int tiles_per_sample, int n, int cp, int c,
+                                double voxels_per_sample, const float* gamma, const float* beta, float eps, int mode,
+                                float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                                float* mean, float* rstd, void* stream) {
+  if (mode < 0 || mode > 2) return fail(-1, "bad norm mode %d", mode);
+  if ((mode != 2 && !stats_partial) || !gamma || !beta || !scale || !shift || !mean || !rstd || cp % 32)
+    return fail(-1, "bad arguments to ub_norm_finalize");
+  if (mode == 2 && (!running_mean || !running_var)) return fail(-1, "eval BatchNorm needs running statistics");
+  stats_finalize_kernel<<<dim3(cp / 32, n), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      stats_partial, tiles_per_sample, n, cp, c, voxels_per_sample, gamma, beta, eps, mode, momentum, running_mean,
+      running_var, scale, shift, mean, rstd);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+static uint32_t drop_thresh(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
+
+extern "C" int ub_norm_act_fwd(const void* y, const float* scale, const float* shift, float slope, float drop_p,
+                               uint32_t drop_seed, int n, int d, int h, int w, int cp, void* a, void* pooled,
+                               void* stream) {
+  if (!y || !a || cp % 8) return fail(-1, "bad arguments to ub_norm_act_fwd");
+  if (drop_p < 0.f || drop_p >= 1.f) return fail(-1, "dropout p out of range");
+  NormActArgs A{scale, shift, slope, drop_p, drop_seed, drop_thresh(drop_p)};
+  const long long V = (long long)d * h * w;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!pooled) {
+    const long long total8 = (long long)n * V * (cp / 8);
+    norm_act_fwd_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<__nv_bfloat16*>(a), A, cp, V, total8);
+  } else {
+    if ((d | h | w) & 1) return fail(-1, "fused max-pool needs even dims");
+    const long long total8 = (long long)n * (V / 8) * (cp / 8);
+    norm_act_pool_fwd_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<__nv_bfloat16*>(a),
+        reinterpret_cast<__nv_bfloat16*>(pooled), A, cp, n, d, h, w, total8);
+  }
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+static const int kBwdBlocksPerSample = 128;
+extern "C" long long ub_norm_act_bwd_workspace_bytes(int n, int cp) {
+  // block partials + c1 + c2
+  return ((long long)n * kBwdBlocksPerSample * 2 * cp + 2ll * n * cp) * 4;
+}
+
+extern "C" int ub_norm_act_bwd(const void* dA, const void* a, const void* y, int mode, const float* mean,
+                               const float* rstd, const float* scale, float slope, float drop_p, uint32_t drop_seed,
+                               int n, long long voxels, int cp, int c, void* workspace, void* dy, float* dgamma,
+                               float* dbeta, float* dbias, void* stream) {
+  if (!dA || !a || !dy || cp % 8) return fail(-1, "bad arguments to ub_norm_act_bwd");
+  cudaStream_t st = (cudaStream_t)stream;
+  NormBwdArgs B;
+  memset(&B, 0, sizeof(B));
+  B.slope = slope; B.drop_p = drop_p; B.drop_seed = drop_seed; B.drop_thresh = drop_thresh(drop_p);
+  const long long total8 = (long long)n * voxels * (cp / 8);
+  if (mode != UB_NORM_NONE) {
+    if (!y || !mean || !rstd || !scale || !workspace) return fail(-1, "norm backward needs y, mean, rstd, scale, workspace");
+    if (cp > 512) return fail(-2, "norm backward supports cp <= 512");
+    float* part = reinterpret_cast<float*>(workspace);
+    float* c1 = part + (size_t)n * kBwdBlocksPerSample * 2 * cp;
+    float* c2 = c1 + (size_t)n * cp;
+    B.mean = mean; B.rstd = rstd; B.gscale = scale; B.c1 = c1; B.c2 = c2;
+    int threads = 256;
+    if (threads < cp) threads = cp;
+    long long bps = kBwdBlocksPerSample;
+    const int lanes_v = threads / (cp / 8);
+    if (bps * lanes_v > voxels) bps = (voxels + lanes_v - 1) / lanes_v;
+    if (bps < 1) bps = 1;
+    norm_act_bwd_reduce_kernel<<<dim3((unsigned)bps, n), threads, 2 * threads * 8 * sizeof(float), st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dA), reinterpret_cast<const __nv_bfloat16*>(a),
+        reinterpret_cast<const __nv_bfloat16*>(y), B, cp, voxels, part);
+    UB_LAUNCH_CHECK();
+    norm_bwd_finalize_kernel<<<(cp + 31) / 32, 32, 0, st>>>(part, (int)bps, n, cp, c, (double)voxels, mode, scale, c1, c2,
+                                                           dgamma, dbeta, dbias);
+    UB_LAUNCH_CHECK();
+  }
+  norm_act_bwd_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dA), reinterpret_cast<const __nv_bfloat16*>(a),
+      reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<__nv_bfloat16*>(dy), B, cp, voxels, total8);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ub_maxpool_bwd(const void* a, const void* dP, void* dA, int accumulate, int n, int d, int h, int w,
+                              int cp, void* stream) {
+  if (!a || !dP || !dA || cp % 8 || ((d | h | w) & 1)) return fail(-1, "bad arguments to ub_maxpool_bwd");
+  const long long total8 = (long long)n * ((long long)d * h * w / 8) * (cp / 8);
+  maxpool_bwd_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(dP),
+      reinterpret_cast<__nv_bfloat16*>(dA), accumulate, cp, n, d, h, w, total8);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+static const int kColsumBlocks = 592;
+extern "C" long long ub_colsum_workspace_bytes(int cp) { return (long long)kColsumBlocks * cp * 4; }
+extern "C" int ub_colsum(const void* x, long long rows, int cp, int c, void* workspace, float* out, void* stream) {
+  if (!x || !workspace || !out || cp % 8 || cp > 512) return fail(-1, "bad arguments to ub_colsum");
+  cudaStream_t st = (cudaStream_t)stream;
+  int threads = 256;
+  if (threads < cp) threads = cp;
+  colsum_bf16_kernel<<<kColsumBlocks, threads, threads * 8 * sizeof(float), st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), rows, cp, reinterpret_cast<float*>(workspace));
+  UB_LAUNCH_CHECK();
+  colsum_finish_kernel<<<(c + 63) / 64, 64, 0, st>>>(reinterpret_cast<const float*>(workspace), kColsumBlocks, cp, c, out);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------
+// losses
+// --------------------------------------------------------------------------------------------------
+static const int kL1Blocks = 1184;
+extern "C" long long ub_l1_workspace_bytes(void) { return (long long)kL1Blocks * 8 + 16; }
+extern "C" int ub_l1_fwd(const float* a, const float* b, long long numel, void* workspace, float* loss, void* stream) {
+  if (!a || !b || !workspace || !loss || numel <= 0) return fail(-1, "bad arguments to ub_l1_fwd");
+  if (((uintptr_t)a | (uintptr_t)b) & 15) return fail(-1, "ub_l1_fwd needs 16-byte aligned inputs");
+  double* part = reinterpret_cast<double*>(workspace);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(part + kL1Blocks);  // must be zero on first use
+  l1_fwd_kernel<<<kL1Blocks, 256, 0, (cudaStream_t)stream>>>(a, b, numel, part, ticket, loss);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int ub_l1_bwd(const float* a, const float* b, const float* grad_out, long long numel, float* da, void* stream) {
+  if (!a || !b || !grad_out || !da || numel <= 0) return fail(-1, "bad arguments to ub_l1_bwd");
+  if (((uintptr_t)a | (uintptr_t)b | (uintptr_t)da) & 15) return fail(-1, "ub_l1_bwd needs 16-byte aligned tensors");
+  l1_bwd_kernel<<<kL1Blocks, 256, 0, (cudaStream_t)stream>>>(a, b, grad_out, numel, da);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int ub_bce_logits(const float* x, float target, int numel, float* loss, float* dx_unit, void* stream) {
+  if (!x || !loss || numel <= 0) return fail(-1, "bad arguments to ub_bce_logits");
+  bce_logits_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(x, target, numel, loss, dx_unit);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int ub_scale(const float* x, const float* scalar, long long numel, float* y, void* stream) {
+  if (!x || !scalar || !y || numel <= 0) return fail(-1, "bad arguments to ub_scale");
+  long long blocks = (numel + 255) / 256;
+  if (blocks > 2368) blocks = 2368;
+  scale_by_scalar_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, scalar, numel, y);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------
+// evaluation
+// --------------------------------------------------------------------------------------------------
+extern "C" int ub_relerr_map_reduce(const float* pred, const float* target, const unsigned char* mask,
+                                    const float* probseg, int c, int r, long long voxels, int angular, float* diff,
+                                    double* sums, double* norms, void* stream) {
+  if (!pred || !target || c <= 0 || c > 8 || r < 0 || r > 3 || voxels <= 0) return fail(-1, "bad arguments to ub_relerr_map_reduce");
+  if (probseg && (!sums || !norms || r == 0)) return fail(-1, "ROI reduction needs sums, norms and r > 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (probseg) {
+    UB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * r * c, st));
+    UB_CUDA(cudaMemsetAsync(norms, 0, sizeof(double) * r, st));
+  }
+  long long blocks = (voxels + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  relerr_kernel<<<(unsigned)blocks, 256, 0, st>>>(pred, target, mask, probseg, c, r, voxels, angular, diff, sums, norms);
+  UB_LAUNCH_CHECK();
+  return 0;
+}

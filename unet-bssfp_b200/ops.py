@@ -1,0 +1,302 @@
+"""Tensor-level wrappers over the C ABI (``include/ub_api.h``).
+
+torch is plumbing here: device memory (caching allocator), the current CUDA stream, dtype tags.
+Every function enqueues hand-written sm_100a kernels through ``libubssfp.so`` and never falls back
+to a torch / cuDNN op. Internal activations are ``(N, D, H, W, Cp)`` bf16 tensors, ``Cp`` = channel
+count padded to a multiple of 32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import (ConvDesc, UB_CONV_K1, UB_CONV_K3S1P1, UB_CONV_K4S2P1, UB_DECONV_K2S2, UB_NORM_BATCH_EVAL,
+                   UB_NORM_BATCH_TRAIN, UB_NORM_INSTANCE, UB_NORM_NONE)
+
+__all__ = [
+    "ConvSpec", "pad32", "pack_conv_weights", "conv_fwd", "conv_dgrad", "conv_wgrad", "pack_ncdhw", "unpack_ncdhw",
+    "norm_finalize", "norm_act_fwd", "norm_act_bwd", "maxpool_bwd", "colsum", "l1_fwd", "l1_bwd", "bce_logits",
+    "scale_by", "relerr_map_reduce",
+]
+
+
+def pad32(c: int) -> int:
+    return (c + 31) // 32 * 32
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("unet_bssfp_b200 kernels run on CUDA tensors only (there is no CPU fallback)")
+
+
+@dataclass(frozen=True)
+class ConvSpec:
+    """Static description of one convolution of the hot path (mirrors ``ub_conv_desc``)."""
+    kind: int
+    c0: int
+    co: int
+    c1: int = 0
+
+    @property
+    def c0p(self):
+        return pad32(self.c0)
+
+    @property
+    def c1p(self):
+        return pad32(self.c1) if self.c1 else 0
+
+    @property
+    def cop(self):
+        return pad32(self.co)
+
+    def desc(self, n, d, h, w) -> ConvDesc:
+        return ConvDesc(self.kind, n, d, h, w, self.c0, self.c0p, self.c1, self.c1p, self.co, self.cop)
+
+    def out_dims(self, d, h, w):
+        if self.kind == UB_CONV_K4S2P1:
+            return d // 2, h // 2, w // 2
+        if self.kind == UB_DECONV_K2S2:
+            return d * 2, h * 2, w * 2
+        return d, h, w
+
+
+# ---------------------------------------------------------------------------------------------------
+# convolution family
+# ---------------------------------------------------------------------------------------------------
+def pack_conv_weights(spec: ConvSpec, w: torch.Tensor, direction: int) -> torch.Tensor:
+    """fp32 torch-layout weight -> packed bf16 [tap][rows_pad][cols_pad]; direction 0 fwd, 1 dgrad."""
+    _require_cuda(w)
+    lib = _lib.load()
+    d = spec.desc(1, 2, 2, 2)
+    n = lib.ub_packed_weight_elems(C.byref(d), direction)
+    if n < 0:
+        _lib.check(-1, "ub_packed_weight_elems")
+    out = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+    w32 = w.detach().contiguous().float()
+    _lib.check(lib.ub_pack_conv_weights(C.byref(d), direction, _p(w32), _p(out), _stream()), "ub_pack_conv_weights")
+    return out
+
+
+def conv_fwd(spec: ConvSpec, src0, src1, w_packed, bias, act=0, slope=0.0, want_stats=False):
+    """-> (out (N,Do,Ho,Wo,cop) bf16, stats_partial [tiles][2][cop] fp32 | None)."""
+    _require_cuda(src0, src1, w_packed, bias)
+    lib = _lib.load()
+    n, d, h, w, _ = src0.shape
+    desc = spec.desc(n, d, h, w)
+    od, oh, ow = spec.out_dims(d, h, w)
+    out = torch.empty((n, od, oh, ow, spec.cop), dtype=torch.bfloat16, device=src0.device)
+    stats = None
+    if want_stats:
+        tiles = lib.ub_conv_num_tiles(C.byref(desc))
+        stats = torch.empty((tiles, 2, spec.cop), dtype=torch.float32, device=src0.device)
+    _lib.check(lib.ub_conv_fwd(C.byref(desc), _p(src0), _p(src1), _p(w_packed), _p(bias), act, slope, _p(out),
+                               _p(stats), _stream()), "ub_conv_fwd")
+    return out, stats
+
+
+def conv_dgrad(spec: ConvSpec, dy, w_packed_dgrad, in_dhw):
+    """dy (N,Do,Ho,Wo,cop) -> (dsrc0, dsrc1|None), each (N,d,h,w,c*p) bf16."""
+    _require_cuda(dy, w_packed_dgrad)
+    lib = _lib.load()
+    n = dy.shape[0]
+    d, h, w = in_dhw
+    desc = spec.desc(n, d, h, w)
+    d0 = torch.empty((n, d, h, w, spec.c0p), dtype=torch.bfloat16, device=dy.device)
+    d1 = torch.empty((n, d, h, w, spec.c1p), dtype=torch.bfloat16, device=dy.device) if spec.c1 else None
+    _lib.check(lib.ub_conv_dgrad(C.byref(desc), _p(dy), _p(w_packed_dgrad), _p(d0), _p(d1), _stream()), "ub_conv_dgrad")
+    return d0, d1
+
+
+def conv_wgrad(spec: ConvSpec, src0, src1, dy, weight_shape):
+    """-> dw fp32 in the torch weight layout ``weight_shape``."""
+    _require_cuda(src0, src1, dy)
+    lib = _lib.load()
+    n, d, h, w, _ = src0.shape
+    desc = spec.desc(n, d, h, w)
+    nbytes = lib.ub_conv_wgrad_workspace_bytes(C.byref(desc))
+    if nbytes < 0:
+        _lib.check(-1, "ub_conv_wgrad_workspace_bytes")
+    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dy.device)
+    dw = torch.zeros(weight_shape, dtype=torch.float32, device=dy.device)
+    _lib.check(lib.ub_conv_wgrad(C.byref(desc), _p(src0), _p(src1), _p(dy), _p(ws), _p(dw), _stream()), "ub_conv_wgrad")
+    return dw
+
+
+# ---------------------------------------------------------------------------------------------------
+# layout
+# ---------------------------------------------------------------------------------------------------
+def pack_ncdhw(a: torch.Tensor, b: torch.Tensor | None = None) -> torch.Tensor:
+    """cat[a, b] NCDHW fp32 -> (N,D,H,W,32) bf16."""
+    _require_cuda(a, b)
+    lib = _lib.load()
+    a = a.contiguous().float()
+    n, ca, d, h, w = a.shape
+    cb = 0
+    if b is not None:
+        b = b.contiguous().float()
+        cb = b.shape[1]
+    cp = pad32(ca + cb)
+    out = torch.empty((n, d, h, w, cp), dtype=torch.bfloat16, device=a.device)
+    _lib.check(lib.ub_pack_ncdhw(_p(a), ca, _p(b), cb, n, d * h * w, cp, _p(out), _stream()), "ub_pack_ncdhw")
+    return out
+
+
+def unpack_ncdhw(x: torch.Tensor, c: int, c_begin: int = 0) -> torch.Tensor:
+    """(N,D,H,W,Cp) bf16 -> NCDHW fp32 of channels [c_begin, c_begin + c)."""
+    _require_cuda(x)
+    lib = _lib.load()
+    n, d, h, w, cp = x.shape
+    out = torch.empty((n, c, d, h, w), dtype=torch.float32, device=x.device)
+    _lib.check(lib.ub_unpack_ncdhw(_p(x), cp, c_begin, c, n, d * h * w, _p(out), _stream()), "ub_unpack_ncdhw")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# norm / dropout / activation
+# ---------------------------------------------------------------------------------------------------
+def norm_finalize(stats, n, voxels, cp, c, gamma, beta, eps, mode, momentum=0.1, running_mean=None,
+                  running_var=None):
+    """-> (scale, shift, mean, rstd), each [n][cp] fp32."""
+    lib = _lib.load()
+    dev = gamma.device
+    scale = torch.empty((n, cp), dtype=torch.float32, device=dev)
+    shift = torch.empty_like(scale)
+    mean = torch.empty_like(scale)
+    rstd = torch.empty_like(scale)
+    tiles_per_sample = 0 if stats is None else stats.shape[0] // n
+    _lib.check(lib.ub_norm_finalize(_p(stats), tiles_per_sample, n, cp, c, float(voxels), _p(gamma), _p(beta), eps,
+                                    mode, momentum, _p(running_mean), _p(running_var), _p(scale), _p(shift), _p(mean),
+                                    _p(rstd), _stream()), "ub_norm_finalize")
+    return scale, shift, mean, rstd
+
+
+def norm_act_fwd(y, scale, shift, slope, drop_p=0.0, drop_seed=0, pool=False):
+    """-> (a, pooled|None)."""
+    lib = _lib.load()
+    n, d, h, w, cp = y.shape
+    a = torch.empty_like(y)
+    pooled = torch.empty((n, d // 2, h // 2, w // 2, cp), dtype=y.dtype, device=y.device) if pool else None
+    _lib.check(lib.ub_norm_act_fwd(_p(y), _p(scale), _p(shift), slope, drop_p, drop_seed & 0xFFFFFFFF, n, d, h, w, cp,
+                                   _p(a), _p(pooled), _stream()), "ub_norm_act_fwd")
+    return a, pooled
+
+
+def norm_act_bwd(dA, a, y, mode, mean, rstd, scale, slope, drop_p, drop_seed, c, want_param_grads=True,
+                 want_bias_grad=True):
+    """-> (dy, dgamma|None, dbeta|None, dbias|None)."""
+    lib = _lib.load()
+    n, d, h, w, cp = a.shape
+    voxels = d * h * w
+    dev = a.device
+    dy = torch.empty_like(a)
+    ws = None
+    dgamma = dbeta = dbias = None
+    if mode != UB_NORM_NONE:
+        ws = torch.empty(lib.ub_norm_act_bwd_workspace_bytes(n, cp) // 4, dtype=torch.float32, device=dev)
+        if want_param_grads:
+            dgamma = torch.empty(c, dtype=torch.float32, device=dev)
+            dbeta = torch.empty(c, dtype=torch.float32, device=dev)
+        if want_bias_grad:
+            dbias = torch.empty(c, dtype=torch.float32, device=dev)
+    _lib.check(lib.ub_norm_act_bwd(_p(dA), _p(a), _p(y), mode, _p(mean), _p(rstd), _p(scale), slope, drop_p,
+                                   drop_seed & 0xFFFFFFFF, n, voxels, cp, c, _p(ws), _p(dy), _p(dgamma), _p(dbeta),
+                                   _p(dbias), _stream()), "ub_norm_act_bwd")
+    return dy, dgamma, dbeta, dbias
+
+
+def maxpool_bwd(a, dP, dA=None):
+    """Route dP to the arg-max voxels of ``a``; accumulates onto ``dA`` if given, else creates it."""
+    lib = _lib.load()
+    n, d, h, w, cp = a.shape
+    acc = 1
+    if dA is None:
+        dA = torch.empty_like(a)
+        acc = 0
+    _lib.check(lib.ub_maxpool_bwd(_p(a), _p(dP), _p(dA), acc, n, d, h, w, cp, _stream()), "ub_maxpool_bwd")
+    return dA
+
+
+def colsum(x, c):
+    lib = _lib.load()
+    cp = x.shape[-1]
+    rows = x.numel() // cp
+    ws = torch.empty(lib.ub_colsum_workspace_bytes(cp) // 4, dtype=torch.float32, device=x.device)
+    out = torch.empty(c, dtype=torch.float32, device=x.device)
+    _lib.check(lib.ub_colsum(_p(x), rows, cp, c, _p(ws), _p(out), _stream()), "ub_colsum")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# losses
+# ---------------------------------------------------------------------------------------------------
+_l1_ws = {}
+
+
+def _l1_workspace(dev):
+    ws = _l1_ws.get(dev)
+    if ws is None:
+        ws = torch.zeros(_lib.load().ub_l1_workspace_bytes() // 8 + 1, dtype=torch.float64, device=dev)
+        _l1_ws[dev] = ws
+    return ws
+
+
+def l1_fwd(a, b):
+    lib = _lib.load()
+    loss = torch.empty((), dtype=torch.float32, device=a.device)
+    _lib.check(lib.ub_l1_fwd(_p(a), _p(b), a.numel(), _p(_l1_workspace(a.device)), _p(loss), _stream()), "ub_l1_fwd")
+    return loss
+
+
+def l1_bwd(a, b, grad_out):
+    lib = _lib.load()
+    da = torch.empty_like(a)
+    _lib.check(lib.ub_l1_bwd(_p(a), _p(b), _p(grad_out), a.numel(), _p(da), _stream()), "ub_l1_bwd")
+    return da
+
+
+def bce_logits(x, target: float, want_grad=True):
+    lib = _lib.load()
+    loss = torch.empty((), dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x) if want_grad else None
+    _lib.check(lib.ub_bce_logits(_p(x), float(target), x.numel(), _p(loss), _p(dx), _stream()), "ub_bce_logits")
+    return loss, dx
+
+
+def scale_by(x, scalar):
+    lib = _lib.load()
+    y = torch.empty_like(x)
+    _lib.check(lib.ub_scale(_p(x), _p(scalar), x.numel(), _p(y), _stream()), "ub_scale")
+    return y
+
+
+# ---------------------------------------------------------------------------------------------------
+# evaluation
+# ---------------------------------------------------------------------------------------------------
+def relerr_map_reduce(pred, target, mask=None, probseg=None, angular=False, want_map=True):
+    """pred/target: (..., C) fp32 channel-last. -> (diff|None, sums [R][C] f64|None, norms [R] f64|None)."""
+    _require_cuda(pred, target, mask, probseg)
+    lib = _lib.load()
+    c = pred.shape[-1]
+    voxels = pred.numel() // c
+    diff = torch.empty_like(pred) if want_map else None
+    sums = norms = None
+    r = 0
+    if probseg is not None:
+        r = probseg.shape[-1]
+        sums = torch.empty((r, c), dtype=torch.float64, device=pred.device)
+        norms = torch.empty((r,), dtype=torch.float64, device=pred.device)
+    _lib.check(lib.ub_relerr_map_reduce(_p(pred), _p(target), _p(mask), _p(probseg), c, r, voxels, int(angular),
+                                        _p(diff), _p(sums), _p(norms), _stream()), "ub_relerr_map_reduce")
+    return diff, sums, norms
