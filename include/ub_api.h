@@ -102,9 +102,11 @@ long long ub_l1_workspace_bytes(void);
 /* nn.L1Loss (mean), ref:model.py:126,136 */
 int ub_l1_fwd(const float* a, const float* b, long long numel, void* workspace, float* loss, void* stream);
 int ub_l1_bwd(const float* a, const float* b, const float* grad_out, long long numel, float* da, void* stream);
-/* nn.BCEWithLogitsLoss (mean) against a constant target, ref:model.py:155,173-175,187-192;
+/* nn.BCEWithLogitsLoss (mean), ref:model.py:155,173-175,187-192. target: per-element tensor, or NULL
+ * to use target_const (the reference only ever passes all-ones / all-zeros);
  * dx_unit (may be NULL) = d loss / d x for an upstream gradient of 1 */
-int ub_bce_logits(const float* x, float target, int numel, float* loss, float* dx_unit, void* stream);
+int ub_bce_logits(const float* x, const float* target, float target_const, int numel, float* loss,
+                  float* dx_unit, void* stream);
 int ub_scale(const float* x, const float* scalar, long long numel, float* y, void* stream);
 
 /* ---- evaluation -------------------------------------------------------------------------------- */

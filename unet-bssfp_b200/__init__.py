@@ -5,3 +5,7 @@ Public surface mirrors the reference's seam (ref:src/model.py:15-92): ``Generato
 relative-error reduction, all running on hand-written CUDA through ``libubssfp.so``.
 """
 __version__ = "0.1.0"
+
+from .modules import (BasicUNet, BCEWithLogitsLoss, Discriminator, DownSampleConv, Generator,  # noqa: E402,F401
+                      L1Loss)
+from . import ops  # noqa: E402,F401

@@ -51,7 +51,7 @@ SIGNATURES = {
     "ub_l1_workspace_bytes": (_LL, []),
     "ub_l1_fwd": (_I, [_P, _P, _LL, _P, _P, _P]),
     "ub_l1_bwd": (_I, [_P, _P, _P, _LL, _P, _P]),
-    "ub_bce_logits": (_I, [_P, _F, _I, _P, _P, _P]),
+    "ub_bce_logits": (_I, [_P, _P, _F, _I, _P, _P, _P]),
     "ub_scale": (_I, [_P, _P, _LL, _P, _P]),
     "ub_relerr_map_reduce": (_I, [_P, _P, _P, _P, _I, _I, _LL, _I, _P, _P, _P, _P]),
 }

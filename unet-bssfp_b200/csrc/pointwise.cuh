@@ -571,12 +571,13 @@ __global__ void l1_bwd_kernel(const float* __restrict__ a, const float* __restri
 // BCE with logits against a constant target t in {0,1} (ref: model.py:155,175,191-192):
 // loss = mean(max(x,0) - x t + log1p(exp(-|x|))); unit gradient (sigmoid(x) - t) / n is emitted in the
 // same pass. One block (the PatchGAN logit map is tiny).
-__global__ void bce_logits_kernel(const float* __restrict__ x, float target, int n, float* __restrict__ loss,
-                                  float* __restrict__ dx_unit) {
+__global__ void bce_logits_kernel(const float* __restrict__ x, const float* __restrict__ target_ptr, float target_const,
+                                  int n, float* __restrict__ loss, float* __restrict__ dx_unit) {
   __shared__ double sh[32];
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float v = x[i];
+    const float target = target_ptr ? target_ptr[i] : target_const;
     s += (double)(fmaxf(v, 0.f) - v * target + log1pf(expf(-fabsf(v))));
     if (dx_unit) dx_unit[i] = (1.f / (1.f + expf(-v)) - target) / (float)n;
   }

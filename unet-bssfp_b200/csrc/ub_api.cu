@@ -723,9 +723,10 @@ extern "C" int ub_l1_bwd(const float* a, const float* b, const float* grad_out, 
   UB_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int ub_bce_logits(const float* x, float target, int numel, float* loss, float* dx_unit, void* stream) {
+extern "C" int ub_bce_logits(const float* x, const float* target, float target_const, int numel, float* loss,
+                             float* dx_unit, void* stream) {
   if (!x || !loss || numel <= 0) return fail(-1, "bad arguments to ub_bce_logits");
-  bce_logits_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(x, target, numel, loss, dx_unit);
+  bce_logits_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(x, target, target_const, numel, loss, dx_unit);
   UB_LAUNCH_CHECK();
   return 0;
 }

@@ -1,0 +1,580 @@
+"""Drop-in ``torch.nn.Module`` mirror of the reference's hot-path classes, executing on sm_100a kernels.
+
+Same constructor signatures, attribute names and state-dict keys as ref:src/model.py:15-92 (and the
+monai==1.3.0 ``BasicUNet`` tree it instantiates, ref:src/model.py:22-28), so checkpoints interchange
+and ``bSSFPToDWITensorModel`` (ref:src/model.py:141-361) can use these classes unchanged:
+
+    Generator(input_modality)(x)            -> (B, 6, D, H, W)
+    Discriminator(modality)(x, y)           -> (B, 1, D/32, H/32, W/32)
+    DownSampleConv(in, out, kernel, strides, padding, activation, batchnorm)(x)
+    L1Loss()(a, b), BCEWithLogitsLoss()(logits, target)
+
+The ``torch.nn`` layer objects inside (Conv3d, BatchNorm3d, InstanceNorm3d, ...) are parameter and
+buffer *containers* only (names, shapes, default init, ``.to()``, ``state_dict``): their ``forward``
+is never called. Each network runs as ONE ``torch.autograd.Function`` whose forward/backward enqueue
+the kernels of ``libubssfp.so`` (no cuDNN, no CPU fallback); gradients reach ``Parameter.grad``
+through autograd, so DDP hooks and ``requires_grad`` toggling (ref:src/model.py:264,274) behave as
+with the reference.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import (UB_CONV_K1, UB_CONV_K3S1P1, UB_CONV_K4S2P1, UB_DECONV_K2S2, UB_NORM_BATCH_EVAL,
+                   UB_NORM_BATCH_TRAIN, UB_NORM_INSTANCE, UB_NORM_NONE)
+
+UNET_FEATURES = (32, 64, 128, 256, 512, 32)
+
+
+# ---------------------------------------------------------------------------------------------------
+# packed-weight cache: bf16 operand copies of the fp32 Parameters, refreshed when the optimiser
+# (in-place update => tensor._version bump) or load_state_dict changes them
+# ---------------------------------------------------------------------------------------------------
+class _PackedWeights:
+    def __init__(self):
+        self._cache = {}
+
+    def get(self, spec, weight, direction):
+        key = (id(weight), direction)
+        ver = (weight._version, weight.data_ptr(), weight.device)
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        packed = ops.pack_conv_weights(spec, weight, direction)
+        self._cache[key] = (ver, packed)
+        return packed
+
+
+# ---------------------------------------------------------------------------------------------------
+# one convolution (+ optional norm, dropout, LeakyReLU, max-pool) of the network graph
+# ---------------------------------------------------------------------------------------------------
+class _Block:
+    """conv -> [InstanceNorm | BatchNorm] -> [Dropout] -> [LeakyReLU] (-> MaxPool3d(2))."""
+
+    def __init__(self, name, spec, conv, norm=None, norm_kind=None, slope=1.0, drop_p=0.0, fused_act=False):
+        self.name = name
+        self.spec = spec
+        self.conv = conv            # nn.Conv3d / nn.ConvTranspose3d container
+        self.norm = norm            # nn.InstanceNorm3d / nn.BatchNorm3d container or None
+        self.norm_kind = norm_kind  # "instance" | "batch" | None
+        self.slope = slope
+        self.drop_p = drop_p
+        self.fused_act = fused_act  # activation applied in the conv epilogue (no norm in between)
+
+    def params(self):
+        ps = [self.conv.weight, self.conv.bias]
+        if self.norm is not None:
+            ps += [self.norm.weight, self.norm.bias]
+        return ps
+
+
+class _Saved:
+    __slots__ = ("src0", "src1", "y", "a", "mean", "rstd", "scale", "seed", "mode", "in_dhw", "drop_p")
+
+
+def _block_forward(blk: _Block, cache: _PackedWeights, src0, src1, training, seed, pool=False, save=True):
+    """-> (a, pooled, saved)."""
+    spec = blk.spec
+    w = cache.get(spec, blk.conv.weight, 0)
+    n, d, h, wd, _ = src0.shape
+    od, oh, ow = spec.out_dims(d, h, wd)
+    sv = _Saved() if save else None
+    if blk.norm is None:
+        act = 1 if blk.fused_act else 0
+        a, _ = ops.conv_fwd(spec, src0, src1, w, blk.conv.bias, act=act, slope=blk.slope)
+        if save:
+            sv.src0, sv.src1, sv.y, sv.a, sv.mode, sv.in_dhw = src0, src1, None, a, UB_NORM_NONE, (d, h, wd)
+            sv.mean = sv.rstd = sv.scale = None
+            sv.seed, sv.drop_p = 0, 0.0
+        return a, None, sv
+    y, stats = ops.conv_fwd(spec, src0, src1, w, blk.conv.bias, want_stats=True)
+    nm = blk.norm
+    if blk.norm_kind == "instance":
+        mode = UB_NORM_INSTANCE
+        rm = rv = None
+    else:
+        mode = UB_NORM_BATCH_TRAIN if (training or not nm.track_running_stats) else UB_NORM_BATCH_EVAL
+        rm, rv = nm.running_mean, nm.running_var
+        if mode == UB_NORM_BATCH_TRAIN and nm.num_batches_tracked is not None:
+            nm.num_batches_tracked.add_(1)
+    momentum = getattr(nm, "momentum", 0.1) or 0.1
+    scale, shift, mean, rstd = ops.norm_finalize(stats, n, od * oh * ow, spec.cop, spec.co, nm.weight, nm.bias,
+                                                 nm.eps, mode, momentum, rm, rv)
+    drop_p = blk.drop_p if training else 0.0
+    a, pooled = ops.norm_act_fwd(y, scale, shift, blk.slope, drop_p, seed, pool=pool)
+    if save:
+        sv.src0, sv.src1, sv.y, sv.a, sv.mode, sv.in_dhw = src0, src1, y, a, mode, (d, h, wd)
+        sv.mean, sv.rstd, sv.scale, sv.seed, sv.drop_p = mean, rstd, scale, seed, drop_p
+    return a, pooled, sv
+
+
+def _block_backward(blk: _Block, cache: _PackedWeights, sv: _Saved, dA, need_w, need_in, grads):
+    """Accumulates parameter grads into ``grads`` (dict id(param) -> tensor); returns (d_src0, d_src1)."""
+    spec = blk.spec
+    co = spec.co
+    if blk.norm is not None:
+        dy, dgamma, dbeta, dbias = ops.norm_act_bwd(dA, sv.a, sv.y, sv.mode, sv.mean, sv.rstd, sv.scale, blk.slope,
+                                                    sv.drop_p, sv.seed, co, want_param_grads=need_w,
+                                                    want_bias_grad=need_w)
+        if need_w:
+            grads[id(blk.norm.weight)] = dgamma
+            grads[id(blk.norm.bias)] = dbeta
+            grads[id(blk.conv.bias)] = dbias
+    else:
+        if blk.fused_act:
+            dy, _, _, _ = ops.norm_act_bwd(dA, sv.a, None, UB_NORM_NONE, None, None, None, blk.slope, 0.0, 0, co)
+        else:
+            dy = dA
+        if need_w:
+            grads[id(blk.conv.bias)] = ops.colsum(dy, co)
+    if need_w:
+        grads[id(blk.conv.weight)] = ops.conv_wgrad(spec, sv.src0, sv.src1, dy, tuple(blk.conv.weight.shape))
+    if need_in:
+        return ops.conv_dgrad(spec, dy, cache.get(spec, blk.conv.weight, 1), sv.in_dhw)
+    return None, None
+
+
+def _fresh_seed() -> int:
+    # host RNG (follows torch.manual_seed), no device sync
+    return int(torch.empty((), dtype=torch.int64).random_().item()) & 0x7FFFFFFF
+
+
+# ---------------------------------------------------------------------------------------------------
+# parameter containers with the reference's names
+# ---------------------------------------------------------------------------------------------------
+class DownSampleConv(nn.Module):
+    """ref:src/model.py:42-65. Supported kernels on the sm_100a path: (kernel=1, strides=1, padding=0)
+    and (kernel=4, strides=2, padding=1); anything else raises (there is no fallback)."""
+
+    def __init__(self, in_channels, out_channels, kernel=4, strides=2, padding=1, activation=True, batchnorm=True):
+        super().__init__()
+        self.activation = activation
+        self.batchnorm = batchnorm
+        self.conv = nn.Conv3d(in_channels, out_channels, kernel, strides, padding)
+        if batchnorm:
+            self.bn = nn.BatchNorm3d(out_channels)
+        if activation:
+            self.act = nn.LeakyReLU(0.2)
+        if (kernel, strides, padding) == (1, 1, 0):
+            kind = UB_CONV_K1
+        elif (kernel, strides, padding) == (4, 2, 1):
+            kind = UB_CONV_K4S2P1
+        else:
+            raise NotImplementedError(
+                f"DownSampleConv(kernel={kernel}, strides={strides}, padding={padding}) has no sm_100a kernel")
+        self._cache = _PackedWeights()
+        self._kind = kind
+
+    def _block(self, name="dsc"):
+        spec = ops.ConvSpec(self._kind, self.conv.in_channels, self.conv.out_channels)
+        slope = 0.2 if self.activation else 1.0
+        if self.batchnorm:
+            return _Block(name, spec, self.conv, self.bn, "batch", slope=slope)
+        return _Block(name, spec, self.conv, None, None, slope=slope, fused_act=self.activation)
+
+    def forward(self, x):
+        blk = self._block()
+        params = blk.params()
+        return _ChainFunction.apply(x, None, _Chain([blk], self._cache, self, blk.spec.co), torch.is_grad_enabled(),
+                                    *params)
+
+
+class _ADN(nn.Sequential):
+    def __init__(self, channels, dropout):
+        super().__init__()
+        self.add_module("N", nn.InstanceNorm3d(channels, affine=True))
+        if dropout is not None and dropout > 0:
+            self.add_module("D", nn.Dropout(dropout))
+        self.add_module("A", nn.LeakyReLU(negative_slope=0.1, inplace=True))
+
+
+class _Convolution(nn.Sequential):
+    def __init__(self, in_chns, out_chns, dropout):
+        super().__init__()
+        self.add_module("conv", nn.Conv3d(in_chns, out_chns, kernel_size=3, stride=1, padding=1, bias=True))
+        self.add_module("adn", _ADN(out_chns, dropout))
+
+
+class _TwoConv(nn.Sequential):
+    def __init__(self, in_chns, out_chns, dropout):
+        super().__init__()
+        self.add_module("conv_0", _Convolution(in_chns, out_chns, dropout))
+        self.add_module("conv_1", _Convolution(out_chns, out_chns, dropout))
+
+
+class _Down(nn.Sequential):
+    def __init__(self, in_chns, out_chns, dropout):
+        super().__init__()
+        self.add_module("max_pooling", nn.MaxPool3d(kernel_size=2))
+        self.add_module("convs", _TwoConv(in_chns, out_chns, dropout))
+
+
+class _UpSample(nn.Sequential):
+    def __init__(self, in_chns, out_chns):
+        super().__init__()
+        self.add_module("deconv", nn.ConvTranspose3d(in_chns, out_chns, kernel_size=2, stride=2, bias=True))
+
+
+class _UpCat(nn.Module):
+    def __init__(self, in_chns, cat_chns, out_chns, dropout, halves=True):
+        super().__init__()
+        up_chns = in_chns // 2 if halves else in_chns
+        self.upsample = _UpSample(in_chns, up_chns)
+        self.convs = _TwoConv(cat_chns + up_chns, out_chns, dropout)
+
+
+class BasicUNet(nn.Module):
+    """Parameter tree of monai==1.3.0 ``BasicUNet(spatial_dims=3, ...)`` (keys of SURVEY.md Appendix A).
+    ``forward`` runs the sm_100a engine (same path ``Generator`` uses, without an input head)."""
+
+    def __init__(self, spatial_dims=3, in_channels=24, out_channels=6, features=UNET_FEATURES, dropout=0.05):
+        super().__init__()
+        if spatial_dims != 3:
+            raise NotImplementedError("only spatial_dims=3 is on the hot path")
+        f = tuple(features)
+        self.in_channels, self.out_channels, self.features, self.dropout = in_channels, out_channels, f, dropout
+        self.conv_0 = _TwoConv(in_channels, f[0], dropout)
+        self.down_1 = _Down(f[0], f[1], dropout)
+        self.down_2 = _Down(f[1], f[2], dropout)
+        self.down_3 = _Down(f[2], f[3], dropout)
+        self.down_4 = _Down(f[3], f[4], dropout)
+        self.upcat_4 = _UpCat(f[4], f[3], f[3], dropout)
+        self.upcat_3 = _UpCat(f[3], f[2], f[2], dropout)
+        self.upcat_2 = _UpCat(f[2], f[1], f[1], dropout)
+        self.upcat_1 = _UpCat(f[1], f[0], f[5], dropout, halves=False)
+        self.final_conv = nn.Conv3d(f[5], out_channels, kernel_size=1)
+        self._cache = _PackedWeights()
+
+    def forward(self, x):
+        net = _UNetGraph(None, self, self._cache)
+        return _GeneratorFunction.apply(x, net, torch.is_grad_enabled(), *net.params)
+
+
+# ---------------------------------------------------------------------------------------------------
+# generic chain of blocks (DownSampleConv standalone, Discriminator)
+# ---------------------------------------------------------------------------------------------------
+class _Chain:
+    def __init__(self, blocks, cache, owner, out_channels):
+        self.blocks = blocks
+        self.cache = cache
+        self.owner = owner
+        self.out_channels = out_channels
+        self.params = []
+        seen = set()
+        for b in blocks:
+            for p in b.params():
+                if id(p) not in seen:
+                    seen.add(id(p))
+                    self.params.append(p)
+
+
+class _ChainFunction(torch.autograd.Function):
+    """x (and optionally y, concatenated on channels) -> blocks... -> NCDHW fp32."""
+
+    @staticmethod
+    def forward(ctx, x, y, chain: _Chain, grad_enabled, *params):
+        need_bwd = grad_enabled and (x.requires_grad or (y is not None and y.requires_grad) or
+                                     any(p.requires_grad for p in params))
+        training = chain.owner.training
+        a = ops.pack_ncdhw(x, y)
+        saved = []
+        for blk in chain.blocks:
+            a, _, sv = _block_forward(blk, chain.cache, a, None, training, 0, save=need_bwd)
+            saved.append(sv)
+        out = ops.unpack_ncdhw(a, chain.out_channels)
+        ctx.chain, ctx.saved = chain, saved
+        ctx.cx = x.shape[1]
+        ctx.cy = y.shape[1] if y is not None else 0
+        ctx.in_dtype = x.dtype
+        return out.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, dout):
+        chain, saved = ctx.chain, ctx.saved
+        need_x, need_y = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        pneed = {id(p): ctx.needs_input_grad[4 + i] for i, p in enumerate(chain.params)}
+        grads = {}
+        dA = ops.pack_ncdhw(dout.contiguous().float())
+        nblk = len(chain.blocks)
+        d0 = None
+        for i in range(nblk - 1, -1, -1):
+            blk = chain.blocks[i]
+            need_w = any(pneed[id(p)] for p in blk.params())
+            need_in = i > 0 or need_x or need_y
+            d0, _ = _block_backward(blk, chain.cache, saved[i], dA, need_w, need_in, grads)
+            saved[i] = None
+            dA = d0
+        dx = ops.unpack_ncdhw(d0, ctx.cx, 0).to(ctx.in_dtype) if need_x else None
+        dy = ops.unpack_ncdhw(d0, ctx.cy, ctx.cx).to(ctx.in_dtype) if need_y else None
+        ctx.saved = None
+        pg = [grads.get(id(p)) if pneed[id(p)] else None for p in chain.params]
+        return (dx, dy, None, None, *pg)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Generator graph: head -> U-Net with skip concat folded into the consumer conv
+# ---------------------------------------------------------------------------------------------------
+class _UNetGraph:
+    def __init__(self, head: DownSampleConv | None, unet: BasicUNet, cache: _PackedWeights):
+        self.head_mod = head
+        self.unet = unet
+        self.cache = cache
+        p = unet.dropout or 0.0
+        f = unet.features
+        K3 = UB_CONV_K3S1P1
+
+        def cb(name, mod, cin, cout, c1=0):
+            return _Block(name, ops.ConvSpec(K3, cin, cout, c1), mod.conv, mod.adn.N, "instance", slope=0.1, drop_p=p)
+
+        self.head = head._block("head") if head is not None else None
+        self.enc = [(cb("conv_0.conv_0", unet.conv_0.conv_0, unet.in_channels, f[0]),
+                     cb("conv_0.conv_1", unet.conv_0.conv_1, f[0], f[0]))]
+        for k, dn in enumerate((unet.down_1, unet.down_2, unet.down_3, unet.down_4), start=1):
+            self.enc.append((cb(f"down_{k}.conv_0", dn.convs.conv_0, f[k - 1], f[k]),
+                             cb(f"down_{k}.conv_1", dn.convs.conv_1, f[k], f[k])))
+        self.dec = []  # upcat_4 .. upcat_1
+        for k, up in zip((4, 3, 2, 1), (unet.upcat_4, unet.upcat_3, unet.upcat_2, unet.upcat_1)):
+            dc = up.upsample.deconv
+            cin, cup = dc.in_channels, dc.out_channels
+            cat = f[k - 1]
+            cout = f[5] if k == 1 else f[k - 1]
+            self.dec.append((
+                _Block(f"upcat_{k}.deconv", ops.ConvSpec(UB_DECONV_K2S2, cin, cup), dc),
+                cb(f"upcat_{k}.conv_0", up.convs.conv_0, cat, cout, c1=cup),
+                cb(f"upcat_{k}.conv_1", up.convs.conv_1, cout, cout),
+            ))
+        self.final = _Block("final_conv", ops.ConvSpec(UB_CONV_K1, f[5], unet.out_channels), unet.final_conv)
+        self.blocks = ([self.head] if self.head else []) + [b for pair in self.enc for b in pair] + \
+                      [b for tri in self.dec for b in tri] + [self.final]
+        self.params = []
+        seen = set()
+        for b in self.blocks:
+            for q in b.params():
+                if id(q) not in seen:
+                    seen.add(id(q))
+                    self.params.append(q)
+
+    @property
+    def training(self):
+        return self.unet.training
+
+
+def _check_unet_dims(d, h, w):
+    if d % 16 or h % 16 or w % 16:
+        raise RuntimeError(f"U-Net input size ({d},{h},{w}) must be divisible by 16 (the replicate-pad branch of "
+                           "monai UpCat for odd sizes is not on the sm_100a path)")
+
+
+class _GeneratorFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, net: _UNetGraph, grad_enabled, *params):
+        need_bwd = grad_enabled and (x.requires_grad or any(p.requires_grad for p in params))
+        _check_unet_dims(*x.shape[2:])
+        training = net.training
+        head_training = net.head_mod.training if net.head_mod is not None else training
+        base_seed = _fresh_seed() if training else 0
+        cache = net.cache
+        S = {}          # block name -> saved
+        lid = [0]
+
+        def run(blk, s0, s1=None, pool=False, tr=training):
+            lid[0] += 1
+            a, pooled, sv = _block_forward(blk, cache, s0, s1, tr, (base_seed + 7919 * lid[0]) & 0x7FFFFFFF,
+                                           pool=pool, save=need_bwd)
+            S[blk.name] = sv
+            return a, pooled
+
+        a = ops.pack_ncdhw(x)
+        if net.head is not None:
+            a, _ = run(net.head, a, tr=head_training)
+        skips = []
+        cur = a
+        for lvl, (c0, c1) in enumerate(net.enc):
+            t, _ = run(c0, cur)
+            last = lvl == len(net.enc) - 1
+            xk, pooled = run(c1, t, pool=not last)
+            skips.append(xk)
+            cur = xk if last else pooled
+        u = skips[-1]
+        for j, (dc, c0, c1) in enumerate(net.dec):
+            x_e = skips[-2 - j]
+            up, _ = run(dc, u)
+            t, _ = run(c0, x_e, up)
+            u, _ = run(c1, t)
+        yf, _ = run(net.final, u)
+        out = ops.unpack_ncdhw(yf, net.unet.out_channels)
+        ctx.net, ctx.S = net, (S if need_bwd else None)
+        ctx.cx = x.shape[1]
+        ctx.in_dtype = x.dtype
+        return out.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, dout):
+        net, S = ctx.net, ctx.S
+        if S is None:
+            raise RuntimeError("Generator backward called but no activations were saved")
+        cache = net.cache
+        pneed = {id(p): ctx.needs_input_grad[3 + i] for i, p in enumerate(net.params)}
+        need_x = ctx.needs_input_grad[0]
+        grads = {}
+
+        def bwd(blk, dA, need_in=True):
+            need_w = any(pneed[id(p)] for p in blk.params())
+            r = _block_backward(blk, cache, S[blk.name], dA, need_w, need_in, grads)
+            S[blk.name] = None
+            return r
+
+        dA = ops.pack_ncdhw(dout.contiguous().float())
+        du, _ = bwd(net.final, dA)
+        nlev = len(net.enc)
+        dskip = [None] * nlev
+        for j in range(len(net.dec) - 1, -1, -1):      # upcat_1 first
+            dc, c0, c1 = net.dec[j]
+            dt, _ = bwd(c1, du)
+            d_xe, d_up = bwd(c0, dt)
+            dskip[nlev - 2 - j] = d_xe
+            du, _ = bwd(dc, d_up)
+        dcur = du                                        # grad of x4 (bottom)
+        for lvl in range(nlev - 1, -1, -1):
+            c0, c1 = net.enc[lvl]
+            if lvl != nlev - 1:
+                # dcur is the grad of the pooled tensor; route it onto the skip grad of x_lvl
+                xk = S[c1.name].a
+                dcur = ops.maxpool_bwd(xk, dcur, dskip[lvl])
+            dt, _ = bwd(c1, dcur)
+            first = lvl == 0
+            dcur, _ = bwd(c0, dt, need_in=(not first) or net.head is not None or need_x)
+        dx = None
+        if net.head is not None:
+            dcur, _ = bwd(net.head, dcur, need_in=need_x)
+        if need_x:
+            dx = ops.unpack_ncdhw(dcur, ctx.cx).to(ctx.in_dtype)
+        ctx.S = None
+        pg = [grads.get(id(p)) if pneed[id(p)] else None for p in net.params]
+        return (dx, None, None, *pg)
+
+
+class Generator(nn.Module):
+    """ref:src/model.py:15-39 -- 1x1x1 input head + BasicUNet(24 -> 6, features 32..512, dropout 0.05)."""
+
+    def __init__(self, input_modality):
+        super().__init__()
+        self.input_modality = input_modality
+        dwi_tensor_input = DownSampleConv(6, 24, kernel=1, strides=1, padding=0)
+        bssfp_input = DownSampleConv(24, 24, kernel=1, strides=1, padding=0)
+        unet = BasicUNet(spatial_dims=3, in_channels=24, out_channels=6, features=UNET_FEATURES, dropout=0.05)
+        self.blocks = nn.ModuleDict({
+            "dwi-tensor": dwi_tensor_input,
+            "pc-bssfp": bssfp_input,
+            "bssfp": bssfp_input,
+            "t1w": dwi_tensor_input,
+            "unet": unet,
+        })
+        self._cache = _PackedWeights()
+        self._graph = None
+
+    def _net(self):
+        if self._graph is None:
+            self._graph = _UNetGraph(self.blocks[self.input_modality], self.blocks["unet"], self._cache)
+        return self._graph
+
+    def forward(self, x):
+        net = self._net()
+        return _GeneratorFunction.apply(x, net, torch.is_grad_enabled(), *net.params)
+
+
+class Discriminator(nn.Module):
+    """ref:src/model.py:68-92 -- PatchGAN on cat[x, y] (the concat is folded into the layout pack)."""
+
+    def __init__(self, modality):
+        super().__init__()
+        self.modality = modality
+        d1_bssfp = DownSampleConv(30, 32, batchnorm=False)
+        d1_dwi = DownSampleConv(12, 32, batchnorm=False)
+        self.d1 = self.blocks = nn.ModuleDict({
+            "dwi-tensor": d1_dwi,
+            "pc-bssfp": d1_bssfp,
+            "bssfp": d1_bssfp,
+            "t1w": d1_dwi,
+        })
+        self.d2 = DownSampleConv(32, 64)
+        self.d3 = DownSampleConv(64, 128)
+        self.d4 = DownSampleConv(128, 256)
+        self.d5 = DownSampleConv(256, 512)
+        self.final = nn.Conv3d(512, 1, kernel_size=1)
+        self._cache = _PackedWeights()
+        self._chain = None
+
+    def _net(self):
+        if self._chain is None:
+            blocks = [self.d1[self.modality]._block("d1"), self.d2._block("d2"), self.d3._block("d3"),
+                      self.d4._block("d4"), self.d5._block("d5"),
+                      _Block("final", ops.ConvSpec(UB_CONV_K1, 512, 1), self.final)]
+            self._chain = _Chain(blocks, self._cache, self, 1)
+        return self._chain
+
+    def forward(self, x, y):
+        d, h, w = x.shape[2:]
+        if d % 32 or h % 32 or w % 32:
+            raise RuntimeError(f"PatchGAN input size ({d},{h},{w}) must be divisible by 32")
+        chain = self._net()
+        return _ChainFunction.apply(x, y, chain, torch.is_grad_enabled(), *chain.params)
+
+
+# ---------------------------------------------------------------------------------------------------
+# losses
+# ---------------------------------------------------------------------------------------------------
+class _L1Function(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a32, b32 = a.contiguous().float(), b.contiguous().float()
+        ctx.save_for_backward(a32, b32)
+        ctx.dt = (a.dtype, b.dtype)
+        return ops.l1_fwd(a32, b32).to(a.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        a32, b32 = ctx.saved_tensors
+        g32 = g.contiguous().float()
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            da = ops.l1_bwd(a32, b32, g32).to(ctx.dt[0])
+        if ctx.needs_input_grad[1]:
+            db = ops.l1_bwd(b32, a32, g32).to(ctx.dt[1])
+        return da, db
+
+
+class L1Loss(nn.Module):
+    """Drop-in for ``torch.nn.L1Loss()`` (mean reduction), ref:src/model.py:126,136."""
+
+    def forward(self, input, target):
+        if input.shape != target.shape:
+            raise RuntimeError("L1Loss: shape mismatch")
+        return _L1Function.apply(input, target)
+
+
+class _BCEFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, target):
+        x32 = x.contiguous().float()
+        t32 = target.contiguous().float()
+        loss, dx = ops.bce_logits(x32, t32, want_grad=True)
+        ctx.save_for_backward(dx)
+        ctx.dt = x.dtype
+        return loss.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        (dx,) = ctx.saved_tensors
+        return ops.scale_by(dx, g.contiguous().float()).to(ctx.dt), None
+
+
+class BCEWithLogitsLoss(nn.Module):
+    """Drop-in for ``torch.nn.BCEWithLogitsLoss()`` (mean reduction), ref:src/model.py:155."""
+
+    def forward(self, input, target):
+        if input.shape != target.shape:
+            raise RuntimeError("BCEWithLogitsLoss: shape mismatch")
+        return _BCEFunction.apply(input, target)

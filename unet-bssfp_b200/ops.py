@@ -266,11 +266,13 @@ def l1_bwd(a, b, grad_out):
     return da
 
 
-def bce_logits(x, target: float, want_grad=True):
+def bce_logits(x, target, want_grad=True):
+    """target: python float (constant) or a tensor shaped like x."""
     lib = _lib.load()
     loss = torch.empty((), dtype=torch.float32, device=x.device)
     dx = torch.empty_like(x) if want_grad else None
-    _lib.check(lib.ub_bce_logits(_p(x), float(target), x.numel(), _p(loss), _p(dx), _stream()), "ub_bce_logits")
+    tptr, tconst = (None, float(target)) if not torch.is_tensor(target) else (_p(target), 0.0)
+    _lib.check(lib.ub_bce_logits(_p(x), tptr, tconst, x.numel(), _p(loss), _p(dx), _stream()), "ub_bce_logits")
     return loss, dx
 
 
