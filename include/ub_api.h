@@ -24,6 +24,8 @@ extern "C" {
 
 int ub_version(void);
 const char* ub_last_error(void);
+/* number of CUDA kernels this library has launched in the process (bench.py reports the delta) */
+long long ub_launch_count(void);
 
 /* ---- convolution family ------------------------------------------------------------------ */
 enum {

@@ -32,6 +32,7 @@ _DP = C.POINTER(ConvDesc)
 SIGNATURES = {
     "ub_version": (_I, []),
     "ub_last_error": (C.c_char_p, []),
+    "ub_launch_count": (_LL, []),
     "ub_packed_weight_elems": (_LL, [_DP, _I]),
     "ub_pack_conv_weights": (_I, [_DP, _I, _P, _P, _P]),
     "ub_conv_num_tiles": (_I, [_DP]),

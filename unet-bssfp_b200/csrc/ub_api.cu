@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
+#include <atomic>
 #include "../../include/ub_api.h"
 #include "igemm_fwd.cuh"
 #include "igemm_wgrad.cuh"
@@ -27,14 +28,17 @@ static int fail(int code, const char* fmt, ...) {
     cudaError_t e_ = (x);                                                                  \
     if (e_ != cudaSuccess) return fail(-3, "%s failed: %s", #x, cudaGetErrorString(e_));   \
   } while (0)
+static std::atomic<long long> g_launches{0};
 #define UB_LAUNCH_CHECK()                                                                  \
   do {                                                                                     \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
     cudaError_t e_ = cudaGetLastError();                                                   \
     if (e_ != cudaSuccess) return fail(-3, "kernel launch failed: %s", cudaGetErrorString(e_)); \
   } while (0)
 
 extern "C" int ub_version(void) { return 100; }
 extern "C" const char* ub_last_error(void) { return g_err; }
+extern "C" long long ub_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // --------------------------------------------------------------------------------------------------
 // tensor maps

@@ -1,0 +1,103 @@
+"""GAN optimisation step with the reference's ``training_step`` semantics (ref:src/model.py:259-281,
+170-193) on the sm_100a modules, plus the data-parallel gradient all-reduce Lightning DDP performs
+inside ``manual_backward`` (ref:src/train.py:30-32).
+
+The perceptual term of ``PerceptualL1Loss`` is out of scope (its MedicalNet weights need the network,
+SURVEY.md section 2 row 8) and is fixed to 0 while keeping the reference's averaging over its two
+loss terms: ``recon = (L1 + 0) / 2 * recon_factor`` (ref:src/model.py:209).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .modules import BCEWithLogitsLoss, L1Loss
+
+RECON_FACTOR = 1e2   # ref:src/model.py:147
+N_RECON_TERMS = 2    # ref:src/model.py:138 (L1, Perceptual)
+
+
+def _set_requires_grad(module, flag):
+    for p in module.parameters():
+        p.requires_grad_(flag)
+
+
+class GradAllReducer:
+    """Averages the gradients of one network over the data-parallel ranks with ONE NCCL all-reduce on
+    a persistent flat fp32 buffer (what DDP's bucketed reducer does for the live network's slots)."""
+
+    def __init__(self, module, group=None):
+        self.params = [p for p in module.parameters()]
+        self.group = group
+        self.flat = None
+
+    def __call__(self):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return
+        live = [p for p in self.params if p.grad is not None]
+        if not live:
+            return
+        n = sum(p.grad.numel() for p in live)
+        if self.flat is None or self.flat.numel() != n or self.flat.device != live[0].grad.device:
+            self.flat = torch.empty(n, dtype=torch.float32, device=live[0].grad.device)
+        views, off = [], 0
+        for p in live:
+            views.append(self.flat[off:off + p.grad.numel()].view_as(p.grad))
+            off += p.grad.numel()
+        torch._foreach_copy_(views, [p.grad for p in live])
+        dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        torch._foreach_copy_([p.grad for p in live], views)
+
+
+class GanTrainer:
+    """Holds the two networks, their AdamW optimisers (ref:src/model.py:359-361) and the loss modules."""
+
+    def __init__(self, gen, discr, lr=1e-3, fused_optimizer=True):
+        self.gen, self.discr = gen, discr
+        cuda = next(gen.parameters()).is_cuda
+        kw = {"fused": True} if (fused_optimizer and cuda) else {}
+        self.opt_g = torch.optim.AdamW(gen.parameters(), lr=lr, **kw)
+        self.opt_d = torch.optim.AdamW(discr.parameters(), lr=lr, **kw)
+        self.l1 = L1Loss()
+        self.bce = BCEWithLogitsLoss()
+        self.reduce_g = GradAllReducer(gen)
+        self.reduce_d = GradAllReducer(discr)
+
+    def recon_loss(self, y_hat, y):
+        return self.l1(y_hat, y) / N_RECON_TERMS * RECON_FACTOR
+
+    def gen_loss(self, x, y):
+        """ref:src/model.py:170-181."""
+        y_hat = self.gen(x)
+        logits = self.discr(x, y_hat)
+        adv = self.bce(logits, torch.ones_like(logits))
+        return adv + self.recon_loss(y_hat, y), y_hat
+
+    def discr_loss(self, x, y):
+        """ref:src/model.py:183-193."""
+        with torch.no_grad():
+            y_hat = self.gen(x)
+        logits_hat = self.discr(x, y_hat)
+        logits = self.discr(x, y)
+        loss_hat = self.bce(logits_hat, torch.zeros_like(logits_hat))
+        loss = self.bce(logits, torch.ones_like(logits))
+        return (loss + loss_hat) / 2
+
+    def step(self, x, y):
+        """One ``training_step``: G phase (D frozen), AdamW, D phase on a fresh G forward, AdamW."""
+        _set_requires_grad(self.discr, False)
+        g_loss, _ = self.gen_loss(x, y)
+        g_loss.backward()
+        self.reduce_g()
+        self.opt_g.step()
+        self.opt_g.zero_grad(set_to_none=True)
+        _set_requires_grad(self.discr, True)
+
+        _set_requires_grad(self.gen, False)
+        d_loss = self.discr_loss(x, y)
+        d_loss.backward()
+        self.reduce_d()
+        self.opt_d.step()
+        self.opt_d.zero_grad(set_to_none=True)
+        _set_requires_grad(self.gen, True)
+        return g_loss.detach(), d_loss.detach()
