@@ -159,70 +159,76 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
     if (lane == 0) {
       const uint32_t a_bytes = (uint32_t)(P.n_atiles * P.n_in_planes * P.bh * P.bw * pitch);
       const uint32_t b_bytes = (uint32_t)(NT.nt * pitch);
-      int it = 0;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
       for (int ch = 0; ch < P.n_chunks_total; ++ch) {
-        const int sa = ch % P.nsa;
-        mbar_wait(a_empty + 8 * sa, ((ch / P.nsa) & 1) ^ 1);
+        mbar_wait(a_empty + 8 * sa, pa ^ 1);
         mbar_expect_tx(a_full + 8 * sa, a_bytes);
         const bool s1 = ch >= P.n_chunks_src0;
         const CUtensorMap* tm = &P.tm_src[s1 ? 1 : 0];
         const int c0 = (s1 ? ch - P.n_chunks_src0 : ch) * P.kc;
+        uint32_t dst = a_base + sa * P.a_stage_bytes;
         for (int at = 0; at < P.n_atiles; ++at) {
           const int cw = w0 * P.in_stride + P.atile_off[at][0];
           const int chh = h0 * P.in_stride + P.atile_off[at][1];
-          for (int p = 0; p < P.n_in_planes; ++p) {
+          for (int p = 0; p < P.n_in_planes; ++p, dst += P.plane_stride) {
             const int cd = (d0 + p) * P.in_stride + P.atile_off[at][2];
-            const uint32_t dst = a_base + sa * P.a_stage_bytes + (at * P.n_in_planes + p) * P.plane_stride;
             tma_load_5d(dst, tm, a_full + 8 * sa, c0, cw, chh, cd, nb);
           }
         }
-        for (int tp = 0; tp < P.ntaps; ++tp, ++it) {
-          const int sb = it % P.nsb;
-          mbar_wait(b_empty + 8 * sb, ((it / P.nsb) & 1) ^ 1);
+        for (int tp = 0; tp < P.ntaps; ++tp) {
+          mbar_wait(b_empty + 8 * sb, pb ^ 1);
           mbar_expect_tx(b_full + 8 * sb, b_bytes);
           tma_load_2d(b_base + sb * P.b_stage_bytes, &P.tm_w, b_full + 8 * sb, ch * P.kc,
                       P.taps[tp].wblock * P.w_rows_per_block + NT.n0);
+          if (++sb == P.nsb) { sb = 0; pb ^= 1; }
         }
+        if (++sa == P.nsa) { sa = 0; pa ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 5) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      const uint32_t swz = P.kc == 32 ? SWZ_64B : (P.kc == 16 ? SWZ_32B : SWZ_128B);
-      const uint32_t idesc = make_idesc_bf16(128, NT.nt, 0, 0);
-      const uint64_t a_desc0 = make_smem_desc(0, 16, P.bw * pitch, swz);
-      const uint64_t b_desc0 = make_smem_desc(0, 16, 8 * pitch, swz);
-      const int ksteps = P.kc / 16;
-      int it = 0;
-      for (int ch = 0; ch < P.n_chunks_total; ++ch) {
-        const int sa = ch % P.nsa;
-        mbar_wait(a_full + 8 * sa, (ch / P.nsa) & 1);
+    // The whole warp walks the pipeline (uniform control flow); one elected lane issues.
+    const uint32_t swz = P.kc == 32 ? SWZ_64B : (P.kc == 16 ? SWZ_32B : SWZ_128B);
+    const uint32_t idesc = make_idesc_bf16(128, NT.nt, 0, 0);
+    const uint32_t a_hi = (uint32_t)(make_smem_desc(0, 16, P.bw * pitch, swz) >> 32);
+    const uint32_t b_hi = (uint32_t)(make_smem_desc(0, 16, 8 * pitch, swz) >> 32);
+    const uint32_t lbo_lo = 1u << 16;  // LBO field (16 bytes) lives in the low word
+    const uint32_t plane16 = (uint32_t)P.plane_stride >> 4;
+    const bool leader = elect_one();
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int ch = 0; ch < P.n_chunks_total; ++ch) {
+      mbar_wait(a_full + 8 * sa, pa);
+      tc_fence_after();
+      const uint32_t a_stage = a_base + sa * P.a_stage_bytes;
+      for (int tp = 0; tp < P.ntaps; ++tp) {
+        mbar_wait(b_full + 8 * sb, pb);
         tc_fence_after();
-        const uint32_t a_stage = a_base + sa * P.a_stage_bytes;
-        for (int tp = 0; tp < P.ntaps; ++tp, ++it) {
-          const int sb = it % P.nsb;
-          mbar_wait(b_full + 8 * sb, (it / P.nsb) & 1);
-          tc_fence_after();
+        if (leader) {
           const IgemmTap T = P.taps[tp];
-          const uint32_t a_tap = a_stage + (T.atile * P.n_in_planes + T.plane_off) * P.plane_stride +
-                                 T.row_off * pitch;
-          const uint32_t b_tile = b_base + sb * P.b_stage_bytes;
+          const uint32_t a_lo = lbo_lo | ((a_stage + (T.atile * P.n_in_planes + T.plane_off) * P.plane_stride +
+                                           T.row_off * pitch) >> 4);
+          const uint32_t b_lo = lbo_lo | ((b_base + sb * P.b_stage_bytes) >> 4);
           const uint32_t acc = (ch | tp) != 0;
-          for (int o = 0; o < planes; ++o) {
-            const uint32_t a_pl = a_tap + o * P.plane_stride;
-#pragma unroll 2
-            for (int k = 0; k < ksteps; ++k) {
-              umma_bf16(tmem + o * ntc, a_desc0 + (uint64_t)((a_pl + k * 32) >> 4),
-                        b_desc0 + (uint64_t)((b_tile + k * 32) >> 4), idesc, acc | (uint32_t)(k != 0));
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            if (o < planes) {
+              umma_bf16_lohi(tmem + o * ntc, a_lo + o * plane16, a_hi, b_lo, b_hi, idesc, acc);
+              umma_bf16_lohi(tmem + o * ntc, a_lo + o * plane16 + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
             }
           }
           umma_commit(b_empty + 8 * sb);
         }
-        umma_commit(a_empty + 8 * sa);
+        __syncwarp();
+        if (++sb == P.nsb) { sb = 0; pb ^= 1; }
       }
-      umma_commit(acc_full);
+      if (leader) umma_commit(a_empty + 8 * sa);
+      __syncwarp();
+      if (++sa == P.nsa) { sa = 0; pa ^= 1; }
     }
+    if (leader) umma_commit(acc_full);
     __syncwarp();
   } else {
     // =========================== epilogue (warps 0-3) ===========================

@@ -92,14 +92,15 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)(P.bh * P.bw * 64 + 128 * P.nt * 2);
       const CUtensorMap* tmx = &P.tm_x[s1 ? 1 : 0];
+      long long tt = t_begin;
+      int tw_i = (int)(tt % P.tiles_w); tt /= P.tiles_w;
+      int th_i = (int)(tt % P.tiles_h); tt /= P.tiles_h;
+      int d = (int)(tt % P.Dt); tt /= P.Dt;
+      int nb = (int)tt;
+      int st = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < niter; ++it) {
-        long long tt = t_begin + it;
-        const int tw_i = (int)(tt % P.tiles_w); tt /= P.tiles_w;
-        const int th_i = (int)(tt % P.tiles_h); tt /= P.tiles_h;
-        const int d = (int)(tt % P.Dt); tt /= P.Dt;
-        const int nb = (int)tt;
-        const int st = it % P.nstages;
-        mbar_wait(empty + 8 * st, ((it / P.nstages) & 1) ^ 1);
+        mbar_wait(empty + 8 * st, ph ^ 1);
         mbar_expect_tx(full + 8 * st, bytes);
         const uint32_t xs = base + st * stage_bytes;
         tma_load_5d(xs, tmx, full + 8 * st, c0, tw_i * 8 * P.x_stride + P.x_off[var][0],
@@ -108,33 +109,48 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
           tma_load_5d(xs + P.x_stage_bytes + b * 128 * dy_pitch, &P.tm_dy, full + 8 * st, n0 + b * P.ncb,
                       tw_i * 8 * P.dy_stride + P.dy_off[var][0], th_i * 16 * P.dy_stride + P.dy_off[var][1],
                       d * P.dy_stride + P.dy_off[var][2], nb);
+        if (++st == P.nstages) { st = 0; ph ^= 1; }
+        if (++tw_i == P.tiles_w) {
+          tw_i = 0;
+          if (++th_i == P.tiles_h) {
+            th_i = 0;
+            if (++d == P.Dt) { d = 0; ++nb; }
+          }
+        }
       }
     }
     __syncwarp();
   } else if (warp == 5) {
-    if (lane == 0) {
-      const uint32_t swz_b = dy_pitch == 128 ? SWZ_128B : (dy_pitch == 64 ? SWZ_64B : SWZ_32B);
-      const uint32_t idesc = make_idesc_bf16(128, P.nt, 1, 1);
-      const uint64_t a_desc0 = make_smem_desc(0, /*lbo: next atom = next row*/ 64, /*sbo*/ P.bw * 64, SWZ_64B);
-      const uint64_t b_desc0 = make_smem_desc(0, /*lbo: next 64-channel box*/ 128 * dy_pitch, 8 * dy_pitch, swz_b);
-      for (int it = 0; it < niter; ++it) {
-        const int st = it % P.nstages;
-        mbar_wait(full + 8 * st, (it / P.nstages) & 1);
-        tc_fence_after();
+    const uint32_t swz_b = dy_pitch == 128 ? SWZ_128B : (dy_pitch == 64 ? SWZ_64B : SWZ_32B);
+    const uint32_t idesc = make_idesc_bf16(128, P.nt, 1, 1);
+    const uint64_t a_desc0 = make_smem_desc(0, /*lbo: next atom = next row*/ 64, /*sbo*/ P.bw * 64, SWZ_64B);
+    const uint64_t b_desc0 = make_smem_desc(0, /*lbo: next 64-channel box*/ 128 * dy_pitch, 8 * dy_pitch, swz_b);
+    const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+    const uint32_t a_lo0 = (uint32_t)a_desc0, b_lo0 = (uint32_t)b_desc0;   // LBO fields, address 0
+    const uint32_t a_kstep = (uint32_t)(2 * P.bw * 64) >> 4, b_kstep = (uint32_t)(16 * dy_pitch) >> 4;
+    const uint32_t g_step = (uint32_t)(P.group_row_step * 64) >> 4;
+    const bool leader = elect_one();
+    int st = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < niter; ++it) {
+      mbar_wait(full + 8 * st, ph);
+      tc_fence_after();
+      if (leader) {
         const uint32_t xs = base + st * stage_bytes;
-        const uint32_t ys = xs + P.x_stage_bytes;
+        const uint32_t a_lo = a_lo0 + (xs >> 4);
+        const uint32_t b_lo = b_lo0 + ((xs + P.x_stage_bytes) >> 4);
         for (int g = 0; g < P.ngroups; ++g) {
-          const uint32_t a_g = xs + g * P.group_row_step * 64;
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            umma_bf16(tmem + g * ntc, a_desc0 + (uint64_t)((a_g + ks * 2 * P.bw * 64) >> 4),
-                      b_desc0 + (uint64_t)((ys + ks * 16 * dy_pitch) >> 4), idesc, (uint32_t)((it | ks) != 0));
-          }
+          for (int ks = 0; ks < 8; ++ks)
+            umma_bf16_lohi(tmem + g * ntc, a_lo + g * g_step + ks * a_kstep, a_hi, b_lo + ks * b_kstep, b_hi, idesc,
+                           (uint32_t)((it | ks) != 0));
         }
         umma_commit(empty + 8 * st);
       }
-      umma_commit(acc_full);
+      __syncwarp();
+      if (++st == P.nstages) { st = 0; ph ^= 1; }
     }
+    if (leader) umma_commit(acc_full);
     __syncwarp();
   } else {
     // epilogue: row = atom * 32 + ci  ->  warp index is the atom (kw), lane is the channel

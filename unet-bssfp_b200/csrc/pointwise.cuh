@@ -131,21 +131,33 @@ __global__ void unpack_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float
 // mode 1: BatchNorm, training (per channel over N and voxels; updates running stats with
 //         momentum and the unbiased variance)                           ref: model.py:53-54
 // mode 2: BatchNorm, eval (running statistics; partials unused)
-// grid = (Cp/32, N); block = (32, 8)
+// grid = (Cp/32, N); block = (32, 32)
 __global__ void stats_finalize_kernel(const float* __restrict__ partial, int tiles_per_sample, int Nb, int Cp, int C,
                                       double count_per_sample, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, float eps, int mode, float momentum,
                                       float* __restrict__ running_mean, float* __restrict__ running_var,
                                       float* __restrict__ scale, float* __restrict__ shift,
                                       float* __restrict__ mean_out, float* __restrict__ rstd_out) {
-  __shared__ double sh_s[8][32], sh_q[8][32];
+  __shared__ double sh_s[32][32], sh_q[32][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int n = blockIdx.y;
   double s = 0.0, q = 0.0;
   if (mode != 2) {
     const int t0 = mode == 0 ? n * tiles_per_sample : 0;
     const int t1 = mode == 0 ? t0 + tiles_per_sample : Nb * tiles_per_sample;
-    for (int t = t0 + threadIdx.y; t < t1; t += 8) {
+    // four independent accumulation chains per thread keep enough loads in flight
+    float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
+    int t = t0 + threadIdx.y;
+    for (; t + 96 < t1; t += 128) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        fs[u] = partial[((size_t)(t + 32 * u) * 2 + 0) * Cp + c];
+        fq[u] = partial[((size_t)(t + 32 * u) * 2 + 1) * Cp + c];
+      }
+      s += ((double)fs[0] + (double)fs[1]) + ((double)fs[2] + (double)fs[3]);
+      q += ((double)fq[0] + (double)fq[1]) + ((double)fq[2] + (double)fq[3]);
+    }
+    for (; t < t1; t += 32) {
       s += (double)partial[((size_t)t * 2 + 0) * Cp + c];
       q += (double)partial[((size_t)t * 2 + 1) * Cp + c];
     }
@@ -154,7 +166,7 @@ __global__ void stats_finalize_kernel(const float* __restrict__ partial, int til
   sh_q[threadIdx.y][threadIdx.x] = q;
   __syncthreads();
   if (threadIdx.y != 0) return;
-  for (int k = 1; k < 8; ++k) { s += sh_s[k][threadIdx.x]; q += sh_q[k][threadIdx.x]; }
+  for (int k = 1; k < 32; ++k) { s += sh_s[k][threadIdx.x]; q += sh_q[k][threadIdx.x]; }
   double mean, var;
   if (mode == 2) {
     mean = c < C ? (double)running_mean[c] : 0.0;
@@ -317,28 +329,36 @@ __global__ void norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA,
 }
 
 // Reduce block partials -> c1, c2 per (n,c) and accumulate dgamma / dbeta (/ bias grad in eval-BN).
-// mode as in stats_finalize. grid = (Cp/32), block = 32 threads (tiny).
+// mode as in stats_finalize. grid = (Cp/32), block = (32 channels, 32 lanes over the partial blocks).
 __global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, int blocks_per_sample, int Nb, int Cp, int C,
                                          double count_per_sample, int mode, const float* __restrict__ xscale,
                                          float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
                                          float* __restrict__ dbeta, float* __restrict__ dbias) {
+  __shared__ double sh1[32][33], sh2[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
-  if (c >= Cp) return;
   double tot1 = 0.0, tot2 = 0.0;
   for (int n = 0; n < Nb; ++n) {
     double s1 = 0.0, s2 = 0.0;
-    for (int b = 0; b < blocks_per_sample; ++b) {
+    for (int b = threadIdx.y; b < blocks_per_sample; b += 32) {
       const float* p = part + ((size_t)(n * blocks_per_sample + b) * 2) * Cp;
       s1 += (double)p[c];
       s2 += (double)p[Cp + c];
     }
-    tot1 += s1;
-    tot2 += s2;
-    if (mode == 0) {
-      c1[(size_t)n * Cp + c] = (float)(s1 / count_per_sample);
-      c2[(size_t)n * Cp + c] = (float)(s2 / count_per_sample);
+    sh1[threadIdx.y][threadIdx.x] = s1;
+    sh2[threadIdx.y][threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+      for (int k = 1; k < 32; ++k) { s1 += sh1[k][threadIdx.x]; s2 += sh2[k][threadIdx.x]; }
+      tot1 += s1;
+      tot2 += s2;
+      if (mode == 0) {
+        c1[(size_t)n * Cp + c] = (float)(s1 / count_per_sample);
+        c2[(size_t)n * Cp + c] = (float)(s2 / count_per_sample);
+      }
     }
+    __syncthreads();
   }
+  if (threadIdx.y != 0) return;
   if (mode != 0) {
     const double cnt = count_per_sample * Nb;
     for (int n = 0; n < Nb; ++n) {

@@ -604,7 +604,7 @@ extern "C" int ub_norm_finalize(const float* stats_partial, int tiles_per_sample
   if ((mode != 2 && !stats_partial) || !gamma || !beta || !scale || !shift || !mean || !rstd || cp % 32)
     return fail(-1, "bad arguments to ub_norm_finalize");
   if (mode == 2 && (!running_mean || !running_var)) return fail(-1, "eval BatchNorm needs running statistics");
-  stats_finalize_kernel<<<dim3(cp / 32, n), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+  stats_finalize_kernel<<<dim3(cp / 32, n), dim3(32, 32), 0, (cudaStream_t)stream>>>(
       stats_partial, tiles_per_sample, n, cp, c, voxels_per_sample, gamma, beta, eps, mode, momentum, running_mean,
       running_var, scale, shift, mean, rstd);
   UB_LAUNCH_CHECK();
@@ -669,7 +669,7 @@ extern "C" int ub_norm_act_bwd(const void* dA, const void* a, const void* y, int
         reinterpret_cast<const __nv_bfloat16*>(dA), reinterpret_cast<const __nv_bfloat16*>(a),
         reinterpret_cast<const __nv_bfloat16*>(y), B, cp, voxels, part);
     UB_LAUNCH_CHECK();
-    norm_bwd_finalize_kernel<<<(cp + 31) / 32, 32, 0, st>>>(part, (int)bps, n, cp, c, (double)voxels, mode, scale, c1, c2,
+    norm_bwd_finalize_kernel<<<cp / 32, dim3(32, 32), 0, st>>>(part, (int)bps, n, cp, c, (double)voxels, mode, scale, c1, c2,
                                                            dgamma, dbeta, dbias);
     UB_LAUNCH_CHECK();
   }
