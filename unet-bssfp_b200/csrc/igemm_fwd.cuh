@@ -235,23 +235,34 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
     const int r = warp * 32 + lane;
     const int h = h0 + (r >> 3), w = w0 + (r & 7);
     const bool valid_hw = (h < P.Ho) && (w < P.Wo);
+    const bool do_stats = P.stats != nullptr;
+    const bool do_act = P.act == 1;
+    const float slope = P.act_slope;
     float s_acc[4] = {0.f, 0.f, 0.f, 0.f}, q_acc[4] = {0.f, 0.f, 0.f, 0.f};
     const int nchunks = (NT.nt + 31) >> 5;
+    // bias of this N tile -> smem (zero where there is none), read back as broadcast float4
+    float* bias_s = red + 1024;  // [128]
+    {
+      const int c = threadIdx.x;
+      bias_s[c] = (P.bias != nullptr && c < NT.nt && NT.n0 + c < P.bias_n) ? __ldg(P.bias + NT.n0 + c) : 0.f;
+    }
+    named_bar_sync(1, 128);
     mbar_wait(acc_full, 0);
     tc_fence_after();
     __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(NT.out);
+    __nv_bfloat16* outp2 = reinterpret_cast<__nv_bfloat16*>(NT.out2);
+    const size_t vox_hw = (size_t)(h * P.out_s + P.out_p[1]) * P.oW + (size_t)(w * P.out_s + P.out_p[0]);
     for (int o = 0; o < planes; ++o) {
       const int d = d0 + o;
-      const size_t vox = (((size_t)nb * P.oD + (size_t)(d * P.out_s + P.out_p[2])) * P.oH +
-                          (size_t)(h * P.out_s + P.out_p[1])) * P.oW + (size_t)(w * P.out_s + P.out_p[0]);
+      const size_t vox = ((size_t)nb * P.oD + (size_t)(d * P.out_s + P.out_p[2])) * P.oH * P.oW + vox_hw;
       __nv_bfloat16* dst = outp + vox * NT.out_cpitch + NT.out_coff;
-      __nv_bfloat16* dst2 = reinterpret_cast<__nv_bfloat16*>(NT.out2) + vox * NT.out2_cpitch;
+      __nv_bfloat16* dst2 = outp2 + vox * NT.out2_cpitch;
 #pragma unroll 1
       for (int cc = 0; cc < nchunks; ++cc) {
-        const int ncol = (NT.nt - cc * 32) >= 32 ? 32 : 16;
+        const bool full32 = (NT.nt - cc * 32) >= 32;
         uint32_t rr[32];
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + o * ntc + cc * 32;
-        if (ncol == 32) {
+        if (full32) {
           tmem_ld_32x32b_x32(taddr, rr);
         } else {
           uint32_t r16[16];
@@ -260,38 +271,40 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
           for (int j = 0; j < 16; ++j) { rr[j] = r16[j]; rr[j + 16] = 0u; }
         }
         tmem_ld_wait();
-        float v[32];
+        uint32_t pk[16];
+        const float4* b4 = reinterpret_cast<const float4*>(bias_s + cc * 32);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(rr[j]);
-          if (P.bias != nullptr && NT.n0 + cc * 32 + j < P.bias_n) x += __ldg(P.bias + NT.n0 + cc * 32 + j);
-          if (P.act == 1) x = x > 0.f ? x : x * P.act_slope;
-          v[j] = x;
+        for (int j = 0; j < 8; ++j) {
+          const float4 bv = b4[j];
+          float x0 = __uint_as_float(rr[4 * j + 0]) + bv.x, x1 = __uint_as_float(rr[4 * j + 1]) + bv.y;
+          float x2 = __uint_as_float(rr[4 * j + 2]) + bv.z, x3 = __uint_as_float(rr[4 * j + 3]) + bv.w;
+          if (do_act) {
+            x0 = x0 > 0.f ? x0 : x0 * slope; x1 = x1 > 0.f ? x1 : x1 * slope;
+            x2 = x2 > 0.f ? x2 : x2 * slope; x3 = x3 > 0.f ? x3 : x3 * slope;
+          }
+          pk[2 * j] = pack_bf16x2(x0, x1);
+          pk[2 * j + 1] = pack_bf16x2(x2, x3);
         }
         if (valid_hw) {
           uint4* d4 = cc * 32 < NT.split ? reinterpret_cast<uint4*>(dst + cc * 32)
                                          : reinterpret_cast<uint4*>(dst2 + (cc * 32 - NT.split));
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j * 8 < ncol) {
-              uint4 pk;
-              pk.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]);
-              pk.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
-              pk.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]);
-              pk.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
-              d4[j] = pk;
-            }
+          d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          if (full32) {
+            d4[2] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
+            d4[3] = make_uint4(pk[12], pk[13], pk[14], pk[15]);
           }
         }
-        if (P.stats != nullptr) {
+        if (do_stats) {
           // statistics of the values as stored (bf16-rounded), so the consumer normalises exactly
           // what it reads
           float a[32], b[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float xr = valid_hw ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.f;
-            a[j] = xr;
-            b[j] = xr * xr;
+          for (int j = 0; j < 16; ++j) {
+            const float lo = valid_hw ? __uint_as_float(pk[j] << 16) : 0.f;
+            const float hi = valid_hw ? __uint_as_float(pk[j] & 0xFFFF0000u) : 0.f;
+            a[2 * j] = lo; a[2 * j + 1] = hi;
+            b[2 * j] = lo * lo; b[2 * j + 1] = hi * hi;
           }
           const float sa_ = warp_transpose_reduce32(a, lane);
           const float sq_ = warp_transpose_reduce32(b, lane);
@@ -301,7 +314,7 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
         }
       }
     }
-    if (P.stats != nullptr) {
+    if (do_stats) {
       for (int cc = 0; cc < nchunks; ++cc) {
         float s = 0.f, q = 0.f;
 #pragma unroll

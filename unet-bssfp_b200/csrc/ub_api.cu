@@ -169,11 +169,19 @@ static int finish_plan(IgemmPlan* pl, int nt_max) {
   P.plane_stride = align_up(P.bh * P.bw * pitch, 1024);
   P.a_stage_bytes = P.n_atiles * P.n_in_planes * P.plane_stride;
   P.b_stage_bytes = align_up(nt_max * pitch, 1024);
-  P.nsb = 4;
-  const int misc = 8 * 64 + 16 + 4096 + 1024;
+  const int misc = 8 * 80 + 16 + 4096 + 512 + 1024;
+  // A stages: double-buffer when there is more than one K chunk and it fits. B ring: as deep as the
+  // remaining budget allows (<= 16): a weight tile is consumed in td*2 MMAs, far faster than one TMA
+  // round trip, so the ring must cover ~2k cycles of latency.
   P.nsa = 2;
-  if (2 * P.a_stage_bytes + P.nsb * P.b_stage_bytes + misc > kSmemBudget) P.nsa = 1;
-  if (P.n_chunks_total == 1) P.nsa = 1;
+  if (P.n_chunks_total == 1 || 2 * P.a_stage_bytes + 4 * P.b_stage_bytes + misc > kSmemBudget) P.nsa = 1;
+  int budget = kSmemBudget;
+  // single-chunk, small-N layers: stay under half the SM so two CTAs co-reside (epilogue of one
+  // overlaps the main loop of the other)
+  if (P.nsa == 1 && P.a_stage_bytes + 8 * P.b_stage_bytes + misc <= 112 * 1024) budget = 112 * 1024;
+  P.nsb = (budget - P.nsa * P.a_stage_bytes - misc) / P.b_stage_bytes;
+  if (P.nsb > 16) P.nsb = 16;
+  if (P.nsb < 2) return fail(-2, "igemm smem plan: no room for the weight ring");
   pl->smem = P.nsa * P.a_stage_bytes + P.nsb * P.b_stage_bytes + misc;
   if (pl->smem > 227 * 1024) return fail(-2, "igemm smem plan too large: %d bytes", pl->smem);
   P.tmem_cols = next_pow2_cols(P.td * align_up(nt_max, 32));
