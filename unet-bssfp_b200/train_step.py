@@ -45,7 +45,8 @@ class GradAllReducer:
             views.append(self.flat[off:off + p.grad.numel()].view_as(p.grad))
             off += p.grad.numel()
         torch._foreach_copy_(views, [p.grad for p in live])
-        dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)   # SUM + scale: works on nccl and gloo
+        self.flat.mul_(1.0 / dist.get_world_size(self.group))
         torch._foreach_copy_([p.grad for p in live], views)
 
 
