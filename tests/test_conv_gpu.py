@@ -36,6 +36,9 @@ CASES = [
     (0, 32, 0, 32, (2, 8, 16, 8)),
     (0, 24, 0, 32, (1, 6, 20, 12)),      # channel padding + ragged tiles in d, h, w
     (0, 64, 0, 64, (1, 4, 16, 16)),
+    (0, 32, 0, 32, (1, 40, 16, 8)),      # marching kernel: ring wrap-around, 5 d-segments with halos
+    (0, 32, 0, 64, (1, 9, 24, 16)),      # dgrad on the marching kernel with K = 64
+    (0, 64, 0, 32, (2, 11, 16, 24)),     # forward on the marching kernel with two K chunks of one source
     (0, 32, 64, 32, (1, 5, 16, 8)),      # skip concat [32 | 64] as two sources, split dgrad destinations
     (0, 128, 0, 256, (1, 4, 8, 8)),      # several N tiles, plane smaller than the 16x8 tile
     (0, 256, 256, 256, (1, 2, 4, 4)),

@@ -123,7 +123,7 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
   const uint32_t a_full = bar_base, a_empty = a_full + 8 * P.nsa, b_full = a_empty + 8 * P.nsa,
                  b_empty = b_full + 8 * P.nsb, acc_full = b_empty + 8 * P.nsb;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (acc_full + 8 - base));
-  float* red = reinterpret_cast<float*>(sm + (acc_full + 16 - base));  // [4][2][128] floats
+  float* red = reinterpret_cast<float*>(sm + (((acc_full + 16 + 15) & ~15u) - base));  // [4][2][128] + bias[128], 16-B aligned
 
   // ---- tile coordinates
   int t = blockIdx.x;

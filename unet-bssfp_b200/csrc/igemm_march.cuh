@@ -1,0 +1,234 @@
+// Marching-plane implicit GEMM for the 3x3x3 s1 p1 convolutions with 32 output channels -- the
+// full-resolution layers that hold 57 % of the generator FLOPs.
+//
+// Why a second kernel: with N = C_out = 32 a 128x32x16 UMMA reads 5 KB of shared memory in 16 tensor
+// cycles (320 B/clk against 128 B/clk of smem bandwidth), so igemm_fwd_kernel tops out below 50 % of
+// tensor peak on these layers. Here the depth taps are folded into N:
+//
+//     P[d'][(kd, co)][h, w] = sum_{kh, kw, c} X[d', h+kh-1, w+kw-1, c] * W[kd, kh, kw][co][c]      (N = 96)
+//     out[d][co][h, w]      = P[d-1][(0, co)] + P[d][(1, co)] + P[d+1][(2, co)]
+//
+// One CTA owns a 16x8 (h, w) column and *marches* along d: every input plane is loaded once (TMA halo
+// tile, 18x10 rows), multiplied by the 9 (kh, kw) weight tiles of N = 96 rows (18 UMMAs per 32-channel
+// chunk instead of 54), and lands in one of four TMEM accumulators. The epilogue warps, one plane
+// behind, add the three 32-column slices that belong to output plane d -- same thread, three TMEM
+// loads, no cross-lane traffic -- while the MMA thread already works on the next plane (TMEM ring of
+// 4 x 96 columns). The full weight set (9 x 96 x C_in bf16, <= 162 KB for the 96->32 skip-concat conv)
+// stays resident in shared memory for the CTA's lifetime.
+#pragma once
+#include "igemm_fwd.cuh"
+
+namespace ub {
+
+struct MarchParams {
+  CUtensorMap tm_src[2];
+  CUtensorMap tm_w;                 // [9 * 96][Kpad] bf16, box (32, 96)
+  int n_chunks_src0, n_chunks_total;
+  int Nb, D, H, W;
+  int tiles_w, tiles_h, nseg, seg_len;
+  void* out;                        // [N][D][H][W][32] bf16
+  const float* bias;
+  int bias_n;
+  float* stats;                     // [item][2][32] or nullptr
+  int nsa;                          // A (plane, chunk) stages
+};
+
+constexpr int kMarchPlaneBytes = 12288;   // 180 rows x 64 B, padded to a multiple of 1024
+constexpr int kMarchWTileBytes = 96 * 64;  // one (chunk, kh, kw) weight tile
+
+__global__ void __launch_bounds__(kIgemmThreads, 1)
+igemm_march_kernel(const __grid_constant__ MarchParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nch = P.n_chunks_total;
+
+  const uint32_t w_base = base;
+  const uint32_t a_base = w_base + nch * 9 * kMarchWTileBytes;
+  const uint32_t bar_base = a_base + P.nsa * kMarchPlaneBytes;
+  // barriers: w_full | a_full[nsa] | a_empty[nsa] | acc_full[4] | acc_empty[4]
+  const uint32_t w_full = bar_base, a_full = w_full + 8, a_empty = a_full + 8 * P.nsa,
+                 acc_full = a_empty + 8 * P.nsa, acc_empty = acc_full + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (acc_empty + 32 - base));
+  float* red = reinterpret_cast<float*>(sm + (((acc_empty + 48 + 15) & ~15u) - base));  // [4][2][32] + bias[32], 16-B aligned
+
+  // ---- work item: (n, h tile, w tile, d segment)
+  int t = blockIdx.x;
+  const int seg = t % P.nseg; t /= P.nseg;
+  const int tw_i = t % P.tiles_w; t /= P.tiles_w;
+  const int th_i = t % P.tiles_h; t /= P.tiles_h;
+  const int nb = t;
+  const int w0 = tw_i * 8, h0 = th_i * 16;
+  const int d_begin = seg * P.seg_len;
+  int d_end = d_begin + P.seg_len; if (d_end > P.D) d_end = P.D;
+  const int p_first = d_begin > 0 ? d_begin - 1 : 0;           // input planes [p_first, p_last]
+  const int p_last = d_end < P.D ? d_end : P.D - 1;
+
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    for (int i = 0; i < P.nsa; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 4); }
+    fence_mbar_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&P.tm_src[0]);
+    if (nch > P.n_chunks_src0) tma_prefetch_desc(&P.tm_src[1]);
+    tma_prefetch_desc(&P.tm_w);
+  }
+  if (warp == 5) tmem_alloc_rt(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      mbar_expect_tx(w_full, (uint32_t)(nch * 9 * kMarchWTileBytes));
+      for (int c = 0; c < nch; ++c)
+        for (int tp = 0; tp < 9; ++tp)
+          tma_load_2d(w_base + (c * 9 + tp) * kMarchWTileBytes, &P.tm_w, w_full, c * 32, tp * 96);
+      int sa = 0;
+      uint32_t pa = 0;
+      for (int p = p_first; p <= p_last; ++p) {
+        for (int c = 0; c < nch; ++c) {
+          mbar_wait(a_empty + 8 * sa, pa ^ 1);
+          mbar_expect_tx(a_full + 8 * sa, 180 * 64);
+          const bool s1 = c >= P.n_chunks_src0;
+          tma_load_5d(a_base + sa * kMarchPlaneBytes, &P.tm_src[s1 ? 1 : 0], a_full + 8 * sa,
+                      (s1 ? c - P.n_chunks_src0 : c) * 32, w0 - 1, h0 - 1, p, nb);
+          if (++sa == P.nsa) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // =========================== MMA issuer ===========================
+    const uint32_t idesc = make_idesc_bf16(128, 96, 0, 0);
+    const uint32_t a_hi = (uint32_t)(make_smem_desc(0, 16, 10 * 64, SWZ_64B) >> 32);
+    const uint32_t b_hi = (uint32_t)(make_smem_desc(0, 16, 8 * 64, SWZ_64B) >> 32);
+    const uint32_t lbo_lo = 1u << 16;
+    const bool leader = elect_one();
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    int sa = 0;
+    uint32_t pa = 0;
+    int slot = 0;
+    uint32_t pacc = 0;
+    for (int p = p_first; p <= p_last; ++p) {
+      mbar_wait(acc_empty + 8 * slot, pacc ^ 1);
+      tc_fence_after();
+      const uint32_t acc = tmem + slot * 96;
+      for (int c = 0; c < nch; ++c) {
+        mbar_wait(a_full + 8 * sa, pa);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t a_lo = lbo_lo | ((a_base + sa * kMarchPlaneBytes) >> 4);
+          const uint32_t b_lo = lbo_lo | ((w_base + c * 9 * kMarchWTileBytes) >> 4);
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const uint32_t ao = (uint32_t)((kh * 10 + kw) * 64) >> 4;
+              const uint32_t bo = (uint32_t)((kh * 3 + kw) * kMarchWTileBytes) >> 4;
+              umma_bf16_lohi(acc, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc, (uint32_t)((c | kh | kw) != 0));
+              umma_bf16_lohi(acc, a_lo + ao + 2, a_hi, b_lo + bo + 2, b_hi, idesc, 1u);
+            }
+          umma_commit(a_empty + 8 * sa);
+        }
+        __syncwarp();
+        if (++sa == P.nsa) { sa = 0; pa ^= 1; }
+      }
+      if (leader) umma_commit(acc_full + 8 * slot);
+      __syncwarp();
+      if (++slot == 4) { slot = 0; pacc ^= 1; }
+    }
+  } else {
+    // =========================== epilogue (warps 0-3) ===========================
+    const int r = warp * 32 + lane;
+    const int h = h0 + (r >> 3), w = w0 + (r & 7);
+    const bool valid_hw = (h < P.H) && (w < P.W);
+    const bool do_stats = P.stats != nullptr;
+    float* bias_s = red + 256;
+    if (threadIdx.x < 32)
+      bias_s[threadIdx.x] = (P.bias != nullptr && threadIdx.x < P.bias_n) ? __ldg(P.bias + threadIdx.x) : 0.f;
+    named_bar_sync(1, 128);
+    float s_acc = 0.f, q_acc = 0.f;
+    __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(P.out);
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int d = d_begin; d < d_end; ++d) {
+      // newest plane this output needs
+      const int pnew = d + 1 <= p_last ? d + 1 : p_last;
+      const int pi = pnew - p_first;
+      mbar_wait(acc_full + 8 * (pi & 3), (uint32_t)(pi >> 2) & 1u);
+      tc_fence_after();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd) {
+        const int p = d + kd - 1;
+        if (p >= 0 && p < P.D) {            // uniform over the CTA
+          uint32_t rr[32];
+          tmem_ld_32x32b_x32(lane_base + (uint32_t)(((p - p_first) & 3) * 96 + kd * 32), rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(rr[j]);
+        }
+      }
+      // plane d-1 is no longer needed by anyone: hand its accumulator back to the MMA thread
+      if (d - 1 >= p_first) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + 8 * ((d - 1 - p_first) & 3));
+      }
+      uint32_t pk[16];
+      const float4* b4 = reinterpret_cast<const float4*>(bias_s);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 bv = b4[j];
+        pk[2 * j] = pack_bf16x2(v[4 * j + 0] + bv.x, v[4 * j + 1] + bv.y);
+        pk[2 * j + 1] = pack_bf16x2(v[4 * j + 2] + bv.z, v[4 * j + 3] + bv.w);
+      }
+      if (valid_hw) {
+        const size_t vox = (((size_t)nb * P.D + d) * P.H + h) * P.W + w;
+        uint4* d4 = reinterpret_cast<uint4*>(outp + vox * 32);
+        d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        d4[2] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
+        d4[3] = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+      }
+      if (do_stats) {
+        float a[32], b[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float lo = valid_hw ? __uint_as_float(pk[j] << 16) : 0.f;
+          const float hi = valid_hw ? __uint_as_float(pk[j] & 0xFFFF0000u) : 0.f;
+          a[2 * j] = lo; a[2 * j + 1] = hi;
+          b[2 * j] = lo * lo; b[2 * j + 1] = hi * hi;
+        }
+        s_acc += warp_transpose_reduce32(a, lane);
+        q_acc += warp_transpose_reduce32(b, lane);
+      }
+    }
+    if (do_stats) {
+      red[(warp * 2 + 0) * 32 + lane] = s_acc;
+      red[(warp * 2 + 1) * 32 + lane] = q_acc;
+      named_bar_sync(1, 128);
+      if (threadIdx.x < 32) {
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 4; ++wq) { s += red[(wq * 2 + 0) * 32 + lane]; q += red[(wq * 2 + 1) * 32 + lane]; }
+        float* st = P.stats + (size_t)blockIdx.x * 64;
+        st[lane] = s;
+        st[32 + lane] = q;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc_rt(tmem, 512);
+}
+
+}  // namespace ub

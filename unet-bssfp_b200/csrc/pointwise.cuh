@@ -492,6 +492,7 @@ struct WeightPackArgs {
   int src_tap_stride;                // element stride of the source tap index
   int split_pad, split_real;         // concat: padded channel p >= split_pad maps to real p - split_pad + split_real
   int split_on_rows;                 // the concatenated (input-channel) axis is rows (dgrad) or cols (fwd)
+  int rows_fold, fold_tap_stride;    // rows_fold > 0: row = fold * rows_fold + r, source tap += fold * fold_tap_stride
   int tapmap[64];                    // packed block -> source tap index
 };
 // padded concat index -> real channel index, or -1 for a pad slot
@@ -506,13 +507,18 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
   const long long total = (long long)A.nblocks * A.rows_pad * A.cols_pad;
   if (i >= total) return;
   const int col = (int)(i % A.cols_pad);
-  const int row = (int)((i / A.cols_pad) % A.rows_pad);
+  int row = (int)((i / A.cols_pad) % A.rows_pad);
   const int blk = (int)(i / ((long long)A.cols_pad * A.rows_pad));
+  int tap = A.tapmap[blk];
+  if (A.rows_fold > 0) {
+    tap += (row / A.rows_fold) * A.fold_tap_stride;
+    row = row % A.rows_fold;
+  }
   const int rr = A.split_on_rows ? concat_real_index(row, A.split_pad, A.split_real, A.rows) : (row < A.rows ? row : -1);
   const int cc = A.split_on_rows ? (col < A.cols ? col : -1) : concat_real_index(col, A.split_pad, A.split_real, A.cols);
   float v = 0.f;
   if (rr >= 0 && cc >= 0)
-    v = w[(size_t)rr * A.stride_row + (size_t)cc * A.stride_col + (size_t)A.tapmap[blk] * A.src_tap_stride];
+    v = w[(size_t)rr * A.stride_row + (size_t)cc * A.stride_col + (size_t)tap * A.src_tap_stride];
   out[i] = __float2bfloat16_rn(v);
 }
 

@@ -8,6 +8,7 @@
 #include "../../include/ub_api.h"
 #include "igemm_fwd.cuh"
 #include "igemm_wgrad.cuh"
+#include "igemm_march.cuh"
 #include "pointwise.cuh"
 
 using namespace ub;
@@ -111,6 +112,14 @@ static inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static int next_pow2_cols(int c) { int p = 32; while (p < c) p <<= 1; return p; }
 
+// The marching-plane kernel (igemm_march.cuh) serves the 3x3x3 convs whose GEMM N is 32:
+//   forward with cop == 32 (K = c0p + c1p <= 96), dgrad with a single 32-channel source (K = cop <= 96).
+static bool use_march(const ub_conv_desc* d, int dir) {
+  if (d->kind != UB_CONV_K3S1P1) return false;
+  if (dir == 0) return d->cop == 32 && d->c0p + d->c1p <= 96;
+  return d->c1p == 0 && d->c0p == 32 && d->cop <= 96;
+}
+
 extern "C" long long ub_packed_weight_elems(const ub_conv_desc* d, int dir) {
   if (check_desc(d)) return -1;
   const long long cin = d->c0p + d->c1p;
@@ -140,6 +149,14 @@ extern "C" int ub_pack_conv_weights(const ub_conv_desc* d, int dir, const float*
     for (int t = 0; t < nt; ++t) A.tapmap[t] = d->kind == UB_CONV_K3S1P1 ? nt - 1 - t : t;
   }
   A.src_tap_stride = 1;
+  if (use_march(d, dir)) {
+    // [kh*3+kw][kd*32 + n][K]: the depth taps are folded into the GEMM N dimension
+    A.nblocks = 9;
+    A.rows_fold = 32;
+    A.rows_pad = 96;
+    A.fold_tap_stride = dir == 0 ? 9 : -9;
+    for (int t = 0; t < 9; ++t) A.tapmap[t] = dir == 0 ? t : 26 - t;
+  }
   // concat split: padded index -> real channel (source 1 starts at c0p in padded space, c0 in real space)
   A.split_pad = d->c1p ? d->c0p : 0;
   A.split_real = d->c1p ? d->c0 : 0;
@@ -230,6 +247,50 @@ static void make_ntiles(IgemmParams& P, int n0p, void* dst0, int n1p, void* dst1
   }
 }
 
+static void march_geometry(int n, int D, int H, int W, int* tiles_w, int* tiles_h, int* nseg, int* seg_len) {
+  *tiles_w = cdiv(W, 8);
+  *tiles_h = cdiv(H, 16);
+  const int columns = n * *tiles_h * *tiles_w;
+  int ns = cdiv(4 * 148, columns);
+  const int max_seg = D / 8 > 1 ? D / 8 : 1;
+  if (ns > max_seg) ns = max_seg;
+  if (ns < 1) ns = 1;
+  *seg_len = cdiv(D, ns);
+  *nseg = cdiv(D, *seg_len);
+}
+
+static int launch_march(const void* src0, int c0p, const void* src1, int c1p, int n, int D, int H, int W,
+                        const void* w_packed, const float* bias, int bias_n, void* out, float* stats,
+                        cudaStream_t st) {
+  MarchParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_chunks_src0 = c0p / 32;
+  P.n_chunks_total = (c0p + c1p) / 32;
+  P.Nb = n; P.D = D; P.H = H; P.W = W;
+  march_geometry(n, D, H, W, &P.tiles_w, &P.tiles_h, &P.nseg, &P.seg_len);
+  P.out = out; P.bias = bias; P.bias_n = bias_n; P.stats = stats;
+  const int wbytes = P.n_chunks_total * 9 * kMarchWTileBytes;
+  const int misc = 8 * 32 + 64 + 1280 + 1024;
+  P.nsa = (220 * 1024 - wbytes - misc) / kMarchPlaneBytes;
+  if (P.nsa > 8) P.nsa = 8;
+  if (P.nsa < 2) return fail(-2, "march smem plan: no room for the plane ring");
+  const int smem = wbytes + P.nsa * kMarchPlaneBytes + misc;
+  if (int e = make_act_map(&P.tm_src[0], src0, c0p, W, H, D, n, 32, 10, 18, 1)) return e;
+  if (c1p)
+    if (int e = make_act_map(&P.tm_src[1], src1, c1p, W, H, D, n, 32, 10, 18, 1)) return e;
+  if (int e = make_w_map(&P.tm_w, w_packed, c0p + c1p, 9 * 96, 32, 96)) return e;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(igemm_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) return fail(-3, "cudaFuncSetAttribute(igemm_march): %s", cudaGetErrorString(attr_err));
+  const unsigned grid = (unsigned)(n * P.tiles_h * P.tiles_w * P.nseg);
+  igemm_march_kernel<<<grid, kIgemmThreads, smem, st>>>(P);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
 // per-axis decomposition of the k=4,s=2,p=1 filter index: input i = 2*o - 1 + k
 //   k -> (parity of i, shift inside the parity tile whose origin offset is (parity ? -1 : 0))
 static inline int k4_parity(int k) { return (k & 1) ? 0 : 1; }
@@ -239,6 +300,11 @@ extern "C" int ub_conv_num_tiles(const ub_conv_desc* d) {
   if (check_desc(d)) return -1;
   int od, oh, ow;
   out_dims(d, &od, &oh, &ow);
+  if (use_march(d, 0)) {
+    int tw, th, ns, sl;
+    march_geometry(d->n, d->d, d->h, d->w, &tw, &th, &ns, &sl);
+    return d->n * th * tw * ns;
+  }
   int td = 4;
   int Dt = od, Ht = oh, Wt = ow;
   if (d->kind == UB_CONV_K4S2P1) td = 1;
@@ -258,6 +324,11 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
   out_dims(d, &od, &oh, &ow);
   const int ktot = d->c0p + d->c1p;
   const int ntaps = ntaps_of(d->kind);
+  if (use_march(d, 0)) {
+    if (act) return fail(-2, "fused activation is not available on the marching conv path");
+    return launch_march(src0, d->c0p, src1, d->c1p, d->n, d->d, d->h, d->w, w_packed, bias, d->co, out,
+                        stats_partial, st);
+  }
 
   IgemmPlan pl;
   memset(&pl, 0, sizeof(pl));
@@ -354,6 +425,8 @@ extern "C" int ub_conv_dgrad(const ub_conv_desc* d, const void* dy, const void* 
   out_dims(d, &od, &oh, &ow);
   const int ntaps = ntaps_of(d->kind);
   const int ncols = d->c0p + d->c1p;
+  if (use_march(d, 1))
+    return launch_march(dy, d->cop, nullptr, 0, d->n, d->d, d->h, d->w, w_packed_dgrad, nullptr, 0, dsrc0, nullptr, st);
 
   IgemmPlan pl;
   memset(&pl, 0, sizeof(pl));
