@@ -156,7 +156,7 @@ def dominant_kernel_roofline(dev, batch, size, peaks, iters=5):
     ms = statistics.median(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
     flops = 2.0 * batch * size ** 3 * 27 * 96 * 32
     ach = flops / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "igemm_fwd_kernel[upcat_1.conv_0 96->32 k3]", "achieved": ach,
+    return {"bound": "tensor", "kernel": "igemm_march_kernel[upcat_1.conv_0 fwd, cat[32|64]->32 k3, 8x128^3]", "achieved": ach,
             "peak": peaks["bf16_burst"], "peak_src": peaks["src"] + " (burst: kernel timed alone)", "unit": "TFLOP/s",
             "frac": ach / peaks["bf16_burst"], "ms_per_launch": ms, "flops_per_launch": flops, "traffic": None}
 

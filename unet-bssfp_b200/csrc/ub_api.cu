@@ -9,6 +9,7 @@
 #include "igemm_fwd.cuh"
 #include "igemm_wgrad.cuh"
 #include "igemm_march.cuh"
+#include "wgrad_march.cuh"
 #include "pointwise.cuh"
 
 using namespace ub;
@@ -596,8 +597,16 @@ static int plan_wgrad(const ub_conv_desc* d, WgradPlan* pl) {
   return 0;
 }
 
+static bool use_wgrad_march(const ub_conv_desc* d) { return d->kind == UB_CONV_K3S1P1 && d->cop == 32; }
+static int wgrad_march_splits(const ub_conv_desc* d) {
+  const int chunks = (d->c0p + d->c1p) / 32;
+  int ns = 148 / chunks;
+  return ns < 1 ? 1 : ns;
+}
+
 extern "C" long long ub_conv_wgrad_workspace_bytes(const ub_conv_desc* d) {
   if (check_desc(d)) return -1;
+  if (use_wgrad_march(d)) return (long long)wgrad_march_splits(d) * 27 * (d->c0p + d->c1p) * 32 * 4;
   WgradPlan pl;
   if (plan_wgrad(d, &pl)) return -1;
   return (long long)pl.grid.x * pl.ntap_lin * pl.P.ci_total * pl.P.co_total * 4;
@@ -610,6 +619,42 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
   if (!src0 || !dy || !workspace || !dw) return fail(-1, "null pointer in ub_conv_wgrad");
   if (d->c1p && !src1) return fail(-1, "second source missing");
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_wgrad_march(d)) {
+    WgradMarchParams M;
+    memset(&M, 0, sizeof(M));
+    M.n_chunks_src0 = d->c0p / 32;
+    M.n_chunks_total = (d->c0p + d->c1p) / 32;
+    M.Nb = d->n; M.D = d->d; M.H = d->h; M.W = d->w;
+    march_geometry(d->n, d->d, d->h, d->w, &M.tiles_w, &M.tiles_h, &M.nseg, &M.seg_len);
+    M.ci_total = d->c0p + d->c1p;
+    M.partial = reinterpret_cast<float*>(workspace);
+    if (int e = make_act_map(&M.tm_x[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, 10, 18, 1)) return e;
+    if (d->c1p)
+      if (int e = make_act_map(&M.tm_x[1], src1, d->c1p, d->w, d->h, d->d, d->n, 32, 10, 18, 1)) return e;
+    if (int e = make_act_map(&M.tm_dy, dy, 32, d->w, d->h, d->d, d->n, 32, 8, 16, 1)) return e;
+    static std::once_flag once_m;
+    static cudaError_t attr_err_m = cudaSuccess;
+    std::call_once(once_m, [] {
+      attr_err_m = cudaFuncSetAttribute(wgrad_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    if (attr_err_m != cudaSuccess) return fail(-3, "cudaFuncSetAttribute(wgrad_march): %s", cudaGetErrorString(attr_err_m));
+    const int nsplit = wgrad_march_splits(d);
+    const int smem = kWmXStages * kWmXBytes + (kWmYSlots + 2) * kWmYBytes + 8 * 32 + 64 + 1024;
+    wgrad_march_kernel<<<dim3((unsigned)nsplit, (unsigned)M.n_chunks_total), kIgemmThreads, smem, st>>>(M);
+    UB_LAUNCH_CHECK();
+    WgradReduceArgs R;
+    memset(&R, 0, sizeof(R));
+    const int ci = d->c0 + d->c1;
+    R.nsplit = nsplit; R.ntap = 27; R.ci_total = M.ci_total; R.co_total = 32; R.ci = ci; R.co = d->co;
+    R.stride_ci = 27; R.stride_co = (long long)ci * 27; R.dst_tap_stride = 1;
+    R.split_pad = d->c1p ? d->c0p : 0;
+    R.split_real = d->c1p ? d->c0 : 0;
+    for (int i = 0; i < 64; ++i) R.tapmap[i] = i < 27 ? i : -1;
+    const long long per_split = 27ll * R.ci_total * 32;
+    wgrad_reduce_kernel<<<(unsigned)((per_split + 255) / 256), 256, 0, st>>>(M.partial, dw, R);
+    UB_LAUNCH_CHECK();
+    return 0;
+  }
   WgradPlan pl;
   if (int e = plan_wgrad(d, &pl)) return e;
   WgradParams& P = pl.P;
