@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libubssfp.so")
 
-UB_CONV_K3S1P1, UB_CONV_K1, UB_CONV_K4S2P1, UB_DECONV_K2S2 = 0, 1, 2, 3
+UB_CONV_K3S1P1, UB_CONV_K1, UB_CONV_K4S2P1, UB_DECONV_K2S2, UB_CONV_K4S2P1_S2D = 0, 1, 2, 3, 4
 UB_NORM_INSTANCE, UB_NORM_BATCH_TRAIN, UB_NORM_BATCH_EVAL, UB_NORM_NONE = 0, 1, 2, 3
 
 
@@ -41,6 +41,7 @@ SIGNATURES = {
     "ub_conv_wgrad_workspace_bytes": (_LL, [_DP]),
     "ub_conv_wgrad": (_I, [_DP, _P, _P, _P, _P, _P, _P]),
     "ub_pack_ncdhw": (_I, [_P, _I, _P, _I, _I, _LL, _I, _P, _P]),
+    "ub_pack_ncdhw_s2d": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "ub_unpack_ncdhw": (_I, [_P, _I, _I, _I, _I, _LL, _P, _P]),
     "ub_norm_finalize": (_I, [_P, _I, _I, _I, _I, _D, _P, _P, _F, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "ub_norm_act_fwd": (_I, [_P, _P, _P, _F, _F, _U32, _I, _I, _I, _I, _I, _P, _P, _P]),

@@ -51,6 +51,11 @@ struct IgemmParams {
   CUtensorMap tm_w;
   int n_chunks_src0, n_chunks_total, kc;
   int n_atiles, bw, bh, n_in_planes, in_stride;
+  // chunks_per_group > 0 ("group mode", space-to-depth sources): chunk ch belongs to group
+  // g = ch / chunks_per_group (the input parity class); the stage holds ONE tile whose origin offset
+  // is atile_off[g] and the taps of that chunk are taps[g * ntaps + tp]. The weight K coordinate is
+  // (ch % chunks_per_group) * kc.
+  int chunks_per_group;
   int atile_off[kMaxATiles][3];  // (w, h, d) added to in_stride * tile origin
   int ntaps;
   IgemmTap taps[kMaxTaps];
@@ -167,20 +172,24 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
         const bool s1 = ch >= P.n_chunks_src0;
         const CUtensorMap* tm = &P.tm_src[s1 ? 1 : 0];
         const int c0 = (s1 ? ch - P.n_chunks_src0 : ch) * P.kc;
+        const int grp = P.chunks_per_group ? ch / P.chunks_per_group : 0;
         uint32_t dst = a_base + sa * P.a_stage_bytes;
         for (int at = 0; at < P.n_atiles; ++at) {
-          const int cw = w0 * P.in_stride + P.atile_off[at][0];
-          const int chh = h0 * P.in_stride + P.atile_off[at][1];
+          const int oi = P.chunks_per_group ? grp : at;
+          const int cw = w0 * P.in_stride + P.atile_off[oi][0];
+          const int chh = h0 * P.in_stride + P.atile_off[oi][1];
           for (int p = 0; p < P.n_in_planes; ++p, dst += P.plane_stride) {
-            const int cd = (d0 + p) * P.in_stride + P.atile_off[at][2];
+            const int cd = (d0 + p) * P.in_stride + P.atile_off[oi][2];
             tma_load_5d(dst, tm, a_full + 8 * sa, c0, cw, chh, cd, nb);
           }
         }
+        const int wk = (P.chunks_per_group ? ch % P.chunks_per_group : ch) * P.kc;
+        const IgemmTap* taps = P.taps + grp * P.ntaps;
         for (int tp = 0; tp < P.ntaps; ++tp) {
           mbar_wait(b_empty + 8 * sb, pb ^ 1);
           mbar_expect_tx(b_full + 8 * sb, b_bytes);
-          tma_load_2d(b_base + sb * P.b_stage_bytes, &P.tm_w, b_full + 8 * sb, ch * P.kc,
-                      P.taps[tp].wblock * P.w_rows_per_block + NT.n0);
+          tma_load_2d(b_base + sb * P.b_stage_bytes, &P.tm_w, b_full + 8 * sb, wk,
+                      taps[tp].wblock * P.w_rows_per_block + NT.n0);
           if (++sb == P.nsb) { sb = 0; pb ^= 1; }
         }
         if (++sa == P.nsa) { sa = 0; pa ^= 1; }
@@ -203,11 +212,12 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
       mbar_wait(a_full + 8 * sa, pa);
       tc_fence_after();
       const uint32_t a_stage = a_base + sa * P.a_stage_bytes;
+      const int tbase = P.chunks_per_group ? (ch / P.chunks_per_group) * P.ntaps : 0;
       for (int tp = 0; tp < P.ntaps; ++tp) {
         mbar_wait(b_full + 8 * sb, pb);
         tc_fence_after();
         if (leader) {
-          const IgemmTap T = P.taps[tp];
+          const IgemmTap T = P.taps[tbase + tp];
           const uint32_t a_lo = lbo_lo | ((a_stage + (T.atile * P.n_in_planes + T.plane_off) * P.plane_stride +
                                            T.row_off * pitch) >> 4);
           const uint32_t b_lo = lbo_lo | ((b_base + sb * P.b_stage_bytes) >> 4);

@@ -86,30 +86,50 @@ __device__ __forceinline__ void norm_act_apply8(float (&x)[8], const NormActArgs
 // ------------------------------------------------------------------------------------------------
 // layout: NCDHW fp32 <-> NDHWC bf16 (channel padded)
 // ------------------------------------------------------------------------------------------------
-// thread per voxel; reads are coalesced per channel plane, writes are CP*2 contiguous bytes.
+// thread = (voxel, channel octet): a warp covers 8 (CP = 32) or 4 (CP = 64) consecutive voxels x all
+// octets, so every load instruction reads whole 32-byte sectors of the channel planes and every store
+// instruction writes one contiguous run of CP*2-byte voxel rows (no partial sectors on either side).
 // Two optional inputs a (ca channels) and b (cb channels) are concatenated: this is the torch.cat of
 // the PatchGAN input (ref: model.py:86) folded into the layout change.
-template <int CP>
-__global__ void pack_ncdhw_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
-                                  __nv_bfloat16* __restrict__ dst, long long V, long long total /* N*V */) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const long long n = i / V, v = i - n * V;
-  const float* sa = a + (size_t)n * ca * V + v;
-  const float* sb = b ? b + (size_t)n * cb * V + v : nullptr;
-  bf16x8* d = reinterpret_cast<bf16x8*>(dst + (size_t)i * CP);
+// S2D: the destination is the space-to-depth layout [N][D/2][H/2][W/2][(pd,ph,pw)][CP] that the
+// stride-2 PatchGAN stem reads with plain (unstrided) TMA boxes.
+template <int CP, bool S2D, int UNROLL>
+__global__ void __launch_bounds__(256)
+pack_ncdhw_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
+                  __nv_bfloat16* __restrict__ dst, long long V, int D, int H, int W) {
+  constexpr int OCT = CP / 8;            // octets per voxel
+  constexpr int VPB = 256 / OCT;         // voxels per block pass
+  const int n = blockIdx.y;
+  const int oct = threadIdx.x % OCT;
+  const long long v0 = (long long)blockIdx.x * (VPB * UNROLL) + threadIdx.x / OCT;
+  const float* src[8];
 #pragma unroll
-  for (int j = 0; j < CP / 8; ++j) {
-    float g[8];
+  for (int k = 0; k < 8; ++k) {
+    const int c = oct * 8 + k;
+    src[k] = c < ca ? a + ((size_t)n * ca + c) * V : (c < ca + cb ? b + ((size_t)n * cb + (c - ca)) * V : nullptr);
+  }
+  float g[UNROLL][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = j * 8 + k;
-      float x = 0.f;
-      if (c < ca) x = __ldg(sa + (size_t)c * V);
-      else if (c < ca + cb) x = __ldg(sb + (size_t)(c - ca) * V);
-      g[k] = x;
+  for (int u = 0; u < UNROLL; ++u) {
+    const long long v = v0 + (long long)u * VPB;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[u][k] = (src[k] != nullptr && v < V) ? __ldg(src[k] + v) : 0.f;
+  }
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    const long long v = v0 + (long long)u * VPB;
+    if (v >= V) continue;
+    size_t row;
+    if (S2D) {
+      const int w = (int)(v % W);
+      const long long t = v / W;
+      const int h = (int)(t % H), d = (int)(t / H);
+      const size_t q = (((size_t)n * (D >> 1) + (d >> 1)) * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
+      row = q * 8 + ((d & 1) * 4 + (h & 1) * 2 + (w & 1));
+    } else {
+      row = (size_t)n * V + v;
     }
-    d[j] = pack8(g);
+    reinterpret_cast<bf16x8*>(dst + row * CP)[oct] = pack8(g[u]);
   }
 }
 
@@ -194,18 +214,64 @@ __global__ void stats_finalize_kernel(const float* __restrict__ partial, int til
 // ------------------------------------------------------------------------------------------------
 // forward: a = LeakyReLU(Dropout(y * scale + shift)); optional fused MaxPool3d(2)
 // ------------------------------------------------------------------------------------------------
-__global__ void norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a,
-                                    NormActArgs A, int Cp, long long V, long long total8) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total8) return;
-  const int c8 = Cp >> 3;
-  const long long vox = i / c8;
-  const int c0 = (int)(i - vox * c8) * 8;
-  const int n = (int)(vox / V);
-  float x[8];
-  unpack8(reinterpret_cast<const bf16x8*>(y)[i], x);
-  norm_act_apply8(x, A, n, Cp, c0, (unsigned long long)i * 8ull);
-  reinterpret_cast<bf16x8*>(a)[i] = pack8(x);
+// grid = (ceil(vps / (256 * UNROLL)), N), vps = vectors (8 channels) per sample. FIXED: Cp/8 divides
+// 256, so a thread keeps the same channel octet for all its vectors and the per-channel scale / shift
+// live in registers. No 64-bit divisions on the path.
+template <int UNROLL, bool FIXED>
+__global__ void __launch_bounds__(256)
+norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a, NormActArgs A, int Cp,
+                    uint32_t vps) {
+  const int n = blockIdx.y;
+  const uint32_t c8 = (uint32_t)Cp >> 3;
+  const size_t base = (size_t)n * vps;
+  const bf16x8* yv = reinterpret_cast<const bf16x8*>(y) + base;
+  bf16x8* av = reinterpret_cast<bf16x8*>(a) + base;
+  const uint32_t i0 = blockIdx.x * (256u * UNROLL) + threadIdx.x;
+  const bool has_norm = A.scale != nullptr;
+  const bool has_drop = A.drop_p > 0.f;
+  const float inv = has_drop ? 1.f / (1.f - A.drop_p) : 1.f;
+  float sc[8], sh[8];
+  if (FIXED) {
+    const int c0 = (int)(threadIdx.x % c8) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      sc[k] = has_norm ? __ldg(A.scale + (size_t)n * Cp + c0 + k) : 1.f;
+      sh[k] = has_norm ? __ldg(A.shift + (size_t)n * Cp + c0 + k) : 0.f;
+    }
+  }
+  bf16x8 in[UNROLL];
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    const uint32_t idx = i0 + u * 256u;
+    if (idx < vps) in[u] = yv[idx];
+  }
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    const uint32_t idx = i0 + u * 256u;
+    if (idx >= vps) continue;
+    float x[8];
+    unpack8(in[u], x);
+    if (!FIXED && has_norm) {
+      const int c0 = (int)(idx % c8) * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        sc[k] = __ldg(A.scale + (size_t)n * Cp + c0 + k);
+        sh[k] = __ldg(A.shift + (size_t)n * Cp + c0 + k);
+      }
+    }
+    if (has_norm) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = fmaf(x[k], sc[k], sh[k]);
+    }
+    if (has_drop) {
+      const uint32_t keep = dropout_keep8((unsigned long long)(base + idx) * 8ull, A.drop_seed, A.drop_thresh);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = (keep >> k) & 1u ? x[k] * inv : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = x[k] > 0.f ? x[k] : x[k] * A.slope;
+    av[idx] = pack8(x);
+  }
 }
 
 // thread = (pooled voxel, 8 channels): writes the 8 activated voxels and their max
@@ -277,36 +343,56 @@ __device__ __forceinline__ void dz1_8(const bf16x8& da8, const bf16x8& a8, const
   }
 }
 
-// grid = (blocks_per_sample, N); each block strides over the voxels of one sample; partial sums are
-// written per block: part[(n * blocks_per_sample + b)][2][Cp]. blockDim.x must be a multiple of Cp/8.
-__global__ void norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a,
-                                           const __nv_bfloat16* __restrict__ y, NormBwdArgs B, int Cp, long long V,
-                                           float* __restrict__ part) {
+// grid = (blocks_per_sample, N); each block strides over the vectors of one sample; partial sums are
+// written per block: part[(n * blocks_per_sample + b)][2][Cp]. Cp/8 must divide blockDim.x (256), so a
+// thread keeps one channel octet; two vectors per thread are in flight per iteration.
+__global__ void __launch_bounds__(512)
+norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a,
+                           const __nv_bfloat16* __restrict__ y, NormBwdArgs B, int Cp, uint32_t vps,
+                           float* __restrict__ part) {
   extern __shared__ float sh[];  // [2][blockDim.x][8]
-  const int c8 = Cp >> 3;
+  const uint32_t c8 = (uint32_t)Cp >> 3;
   const int n = blockIdx.y;
-  const int lanes_v = blockDim.x / c8;           // voxels processed per block iteration
-  const int cidx = threadIdx.x % c8, vlane = threadIdx.x / c8;
+  const int lanes_v = blockDim.x / c8;
+  const int cidx = threadIdx.x % c8;
   const int c0 = cidx * 8;
-  float mean[8], rstd[8];
+  const size_t base = (size_t)n * vps;
+  const bf16x8* dAv = reinterpret_cast<const bf16x8*>(dA) + base;
+  const bf16x8* av = reinterpret_cast<const bf16x8*>(a) + base;
+  const bf16x8* yv = reinterpret_cast<const bf16x8*>(y) + base;
+  float rstd[8], moff[8];   // xhat = y * rstd + moff
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    mean[k] = B.mean ? B.mean[(size_t)n * Cp + c0 + k] : 0.f;
+    const float m = B.mean ? B.mean[(size_t)n * Cp + c0 + k] : 0.f;
     rstd[k] = B.rstd ? B.rstd[(size_t)n * Cp + c0 + k] : 0.f;
+    moff[k] = -m * rstd[k];
   }
   float s1[8], s2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
-  for (long long v = (long long)blockIdx.x * lanes_v + vlane; v < V; v += (long long)gridDim.x * lanes_v) {
-    const size_t e = ((size_t)n * V + v) * c8 + cidx;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < vps; i += 2 * stride) {
+    const uint32_t j = i + stride;
+    const bool two = j < vps;
+    const bf16x8 d0 = dAv[i], a0 = av[i], y0 = yv[i];
+    bf16x8 d1 = d0, a1 = a0, y1 = y0;
+    if (two) { d1 = dAv[j]; a1 = av[j]; y1 = yv[j]; }
     float dz[8], yy[8];
-    dz1_8(reinterpret_cast<const bf16x8*>(dA)[e], reinterpret_cast<const bf16x8*>(a)[e], B,
-          (unsigned long long)e * 8ull, dz);
-    unpack8(reinterpret_cast<const bf16x8*>(y)[e], yy);
+    dz1_8(d0, a0, B, (unsigned long long)(base + i) * 8ull, dz);
+    unpack8(y0, yy);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       s1[k] += dz[k];
-      s2[k] += dz[k] * (yy[k] - mean[k]) * rstd[k];
+      s2[k] = fmaf(dz[k], fmaf(yy[k], rstd[k], moff[k]), s2[k]);
+    }
+    if (two) {
+      dz1_8(d1, a1, B, (unsigned long long)(base + j) * 8ull, dz);
+      unpack8(y1, yy);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s1[k] += dz[k];
+        s2[k] = fmaf(dz[k], fmaf(yy[k], rstd[k], moff[k]), s2[k]);
+      }
     }
   }
   float* sh1 = sh;
@@ -375,29 +461,57 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, int blo
   }
 }
 
-__global__ void norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a,
-                                          const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dy,
-                                          NormBwdArgs B, int Cp, long long V, long long total8) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total8) return;
-  const int c8 = Cp >> 3;
-  const long long vox = i / c8;
-  const int c0 = (int)(i - vox * c8) * 8;
-  const int n = (int)(vox / V);
-  float dz[8];
-  dz1_8(reinterpret_cast<const bf16x8*>(dA)[i], reinterpret_cast<const bf16x8*>(a)[i], B,
-        (unsigned long long)i * 8ull, dz);
-  if (B.mean != nullptr) {
-    float yy[8];
-    unpack8(reinterpret_cast<const bf16x8*>(y)[i], yy);
-    const size_t o = (size_t)n * Cp + c0;
+// dy = g*rstd * (dz1 - c1 - xhat * c2) = ka * dz1 + kc * y + kb with per-(n,c) constants held in
+// registers (Cp/8 divides 256: fixed channel octet per thread). grid = (ceil(vps / (256*UNROLL)), N).
+template <int UNROLL>
+__global__ void __launch_bounds__(256)
+norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a,
+                          const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dy, NormBwdArgs B, int Cp,
+                          uint32_t vps) {
+  const int n = blockIdx.y;
+  const uint32_t c8 = (uint32_t)Cp >> 3;
+  const size_t base = (size_t)n * vps;
+  const bf16x8* dAv = reinterpret_cast<const bf16x8*>(dA) + base;
+  const bf16x8* av = reinterpret_cast<const bf16x8*>(a) + base;
+  const bf16x8* yv = reinterpret_cast<const bf16x8*>(y) + base;
+  bf16x8* dyv = reinterpret_cast<bf16x8*>(dy) + base;
+  const bool has_norm = B.mean != nullptr;
+  float ka[8], kb[8], kc[8];
+  if (has_norm) {
+    const size_t o = (size_t)n * Cp + (threadIdx.x % c8) * 8;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float xh = (yy[k] - B.mean[o + k]) * B.rstd[o + k];
-      dz[k] = B.gscale[o + k] * (dz[k] - B.c1[o + k] - xh * B.c2[o + k]);
+      const float g = B.gscale[o + k], r = B.rstd[o + k], m = B.mean[o + k];
+      ka[k] = g;
+      kc[k] = -g * r * B.c2[o + k];
+      kb[k] = -g * B.c1[o + k] - kc[k] * m;
     }
   }
-  reinterpret_cast<bf16x8*>(dy)[i] = pack8(dz);
+  const uint32_t i0 = blockIdx.x * (256u * UNROLL) + threadIdx.x;
+  bf16x8 d_[UNROLL], a_[UNROLL], y_[UNROLL];
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    const uint32_t idx = i0 + u * 256u;
+    if (idx < vps) {
+      d_[u] = dAv[idx];
+      a_[u] = av[idx];
+      if (has_norm) y_[u] = yv[idx];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    const uint32_t idx = i0 + u * 256u;
+    if (idx >= vps) continue;
+    float dz[8];
+    dz1_8(d_[u], a_[u], B, (unsigned long long)(base + idx) * 8ull, dz);
+    if (has_norm) {
+      float yy[8];
+      unpack8(y_[u], yy);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dz[k] = fmaf(ka[k], dz[k], fmaf(kc[k], yy[k], kb[k]));
+    }
+    dyv[idx] = pack8(dz);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -90,22 +90,24 @@ static int make_w_map(CUtensorMap* m, const void* ptr, long long K, long long ro
 // --------------------------------------------------------------------------------------------------
 // descriptor helpers
 // --------------------------------------------------------------------------------------------------
+static inline bool is_k4(int kind) { return kind == UB_CONV_K4S2P1 || kind == UB_CONV_K4S2P1_S2D; }
 static int check_desc(const ub_conv_desc* d) {
   if (!d) return fail(-1, "null conv desc");
-  if (d->kind < 0 || d->kind > 3) return fail(-1, "bad conv kind %d", d->kind);
+  if (d->kind < 0 || d->kind > 4) return fail(-1, "bad conv kind %d", d->kind);
   if (d->n <= 0 || d->d <= 0 || d->h <= 0 || d->w <= 0) return fail(-1, "bad conv dims");
   if (d->c0p <= 0 || d->c0p % 32 || d->c1p % 32 || d->cop <= 0 || d->cop % 32)
     return fail(-1, "padded channel counts must be positive multiples of 32 (c0p=%d c1p=%d cop=%d)", d->c0p, d->c1p,
                 d->cop);
   if (d->c0 > d->c0p || d->c1 > d->c1p || d->co > d->cop) return fail(-1, "real channels exceed padded channels");
-  if (d->kind == UB_CONV_K4S2P1 && ((d->d | d->h | d->w) & 1)) return fail(-1, "k4s2p1 needs even input dims");
+  if (is_k4(d->kind) && ((d->d | d->h | d->w) & 1)) return fail(-1, "k4s2p1 needs even input dims");
+  if (d->kind == UB_CONV_K4S2P1_S2D && d->c1p) return fail(-1, "the space-to-depth stem takes one source");
   if (d->kind == UB_DECONV_K2S2 && d->c1p) return fail(-1, "transposed conv takes one source");
   if (d->cop > 128 && d->cop % 128) return fail(-1, "cop > 128 must be a multiple of 128");
   return 0;
 }
-static int ntaps_of(int kind) { return kind == UB_CONV_K3S1P1 ? 27 : kind == UB_CONV_K1 ? 1 : kind == UB_CONV_K4S2P1 ? 64 : 8; }
+static int ntaps_of(int kind) { return kind == UB_CONV_K3S1P1 ? 27 : kind == UB_CONV_K1 ? 1 : is_k4(kind) ? 64 : 8; }
 static void out_dims(const ub_conv_desc* d, int* od, int* oh, int* ow) {
-  if (d->kind == UB_CONV_K4S2P1) { *od = d->d / 2; *oh = d->h / 2; *ow = d->w / 2; }
+  if (is_k4(d->kind)) { *od = d->d / 2; *oh = d->h / 2; *ow = d->w / 2; }
   else if (d->kind == UB_DECONV_K2S2) { *od = d->d * 2; *oh = d->h * 2; *ow = d->w * 2; }
   else { *od = d->d; *oh = d->h; *ow = d->w; }
 }
@@ -369,6 +371,34 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
     if (int e = finish_plan(&pl, nt_max)) return e;
     return launch_igemm(pl, st);
   }
+  if (d->kind == UB_CONV_K4S2P1_S2D) {
+    // source = space-to-depth tensor [n][d/2][h/2][w/2][(pd,ph,pw)][c0p]: chunk group = input parity,
+    // per axis parity 0 pairs filter taps k = 1, 3 with q = o, o+1; parity 1 pairs k = 0, 2 with q = o-1, o
+    P.td = od < 4 ? od : 4;
+    P.Do = od; P.Ho = oh; P.Wo = ow;
+    P.n_atiles = 1; P.bw = 9; P.bh = 17; P.n_in_planes = P.td + 1; P.in_stride = 1;
+    P.chunks_per_group = d->c0p / 32;
+    P.n_chunks_src0 = P.n_chunks_total = 8 * P.chunks_per_group;
+    P.ntaps = 8;
+    for (int pd = 0; pd < 2; ++pd)
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+          const int g = (pd * 2 + ph) * 2 + pw;
+          P.atile_off[g][0] = pw ? -1 : 0;
+          P.atile_off[g][1] = ph ? -1 : 0;
+          P.atile_off[g][2] = pd ? -1 : 0;
+          int t = 0;
+          for (int sd = 0; sd < 2; ++sd)
+            for (int sh = 0; sh < 2; ++sh)
+              for (int sw = 0; sw < 2; ++sw, ++t) {
+                const int kd = 2 * sd + (1 - pd), kh = 2 * sh + (1 - ph), kw = 2 * sw + (1 - pw);
+                P.taps[g * 8 + t] = IgemmTap{0, (uint16_t)(sh * P.bw + sw), (uint16_t)sd, (uint16_t)((kd * 4 + kh) * 4 + kw)};
+              }
+        }
+    if (int e = make_act_map(&P.tm_src[0], src0, 8 * d->c0p, d->w / 2, d->h / 2, d->d / 2, d->n, 32, P.bw, P.bh, 1)) return e;
+    if (int e = finish_plan(&pl, nt_max)) return e;
+    return launch_igemm(pl, st);
+  }
   if (d->kind == UB_CONV_K4S2P1) {
     P.td = 1;
     P.Do = od; P.Ho = oh; P.Wo = ow;
@@ -465,7 +495,7 @@ extern "C" int ub_conv_dgrad(const ub_conv_desc* d, const void* dy, const void* 
     if (int e = finish_plan(&pl, nt_max)) return e;
     return launch_igemm(pl, st);
   }
-  if (d->kind == UB_CONV_K4S2P1) {
+  if (is_k4(d->kind)) {
     // 8 input parity classes; class p (per axis): p=0 -> taps (o=q-1,k=3),(o=q,k=1); p=1 -> (o=q,k=2),(o=q+1,k=0)
     P.td = od < 4 ? od : 4;
     P.Do = od; P.Ho = oh; P.Wo = ow;  // tile space = q grid (same size as dy)
@@ -547,9 +577,10 @@ static int plan_wgrad(const ub_conv_desc* d, WgradPlan* pl) {
     P.bw = 8; P.bh = 16; P.Dt = od; P.Ht = oh; P.Wt = ow;
     P.n_variants = 1; P.ngroups = 1; P.group_row_step = 0; P.natoms = 1;
     pl->tapmap[0] = 0;
-  } else if (d->kind == UB_CONV_K4S2P1) {
+  } else if (is_k4(d->kind)) {
+    const bool s2d = d->kind == UB_CONV_K4S2P1_S2D;
     P.bw = 9; P.bh = 17; P.Dt = od; P.Ht = oh; P.Wt = ow;
-    P.x_stride = 2;
+    P.x_stride = s2d ? 1 : 2;
     P.n_variants = 16; P.ngroups = 2; P.group_row_step = P.bw; P.natoms = 2;
     for (int pd = 0; pd < 2; ++pd)
       for (int ph = 0; ph < 2; ++ph)
@@ -558,7 +589,10 @@ static int plan_wgrad(const ub_conv_desc* d, WgradPlan* pl) {
             const int v = ((pd * 2 + ph) * 2 + pw) * 2 + sd;
             P.x_off[v][0] = pw ? -1 : 0;
             P.x_off[v][1] = ph ? -1 : 0;
-            P.x_off[v][2] = 2 * sd + (pd ? -1 : 0);
+            // plain source: parity tile with element stride 2 (depth in input planes);
+            // space-to-depth source: q-space coordinates, parity selects the channel block
+            P.x_off[v][2] = s2d ? sd + (pd ? -1 : 0) : 2 * sd + (pd ? -1 : 0);
+            P.x_coff[v] = s2d ? ((pd * 2 + ph) * 2 + pw) * d->c0p : 0;
             for (int sh = 0; sh < 2; ++sh)
               for (int sw = 0; sw < 2; ++sw) {
                 const int kd = 2 * sd + (1 - pd), kh = 2 * sh + (1 - ph), kw = 2 * sw + (1 - pw);
@@ -661,7 +695,11 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
   int od, oh, ow;
   out_dims(d, &od, &oh, &ow);
   P.partial = reinterpret_cast<float*>(workspace);
-  if (int e = make_act_map(&P.tm_x[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, P.x_stride)) return e;
+  if (d->kind == UB_CONV_K4S2P1_S2D) {
+    if (int e = make_act_map(&P.tm_x[0], src0, 8 * d->c0p, d->w / 2, d->h / 2, d->d / 2, d->n, 32, P.bw, P.bh, 1)) return e;
+  } else {
+    if (int e = make_act_map(&P.tm_x[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, P.x_stride)) return e;
+  }
   if (d->c1p)
     if (int e = make_act_map(&P.tm_x[1], src1, d->c1p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, P.x_stride)) return e;
   if (int e = make_act_map(&P.tm_dy, dy, d->cop, ow, oh, od, d->n, P.ncb, 8, 16, P.dy_stride)) return e;
@@ -696,17 +734,35 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
 // --------------------------------------------------------------------------------------------------
 // layout
 // --------------------------------------------------------------------------------------------------
-extern "C" int ub_pack_ncdhw(const float* a, int ca, const float* b, int cb, int n, long long voxels, int cp,
-                             void* out, void* stream) {
-  if (!a || !out || ca <= 0 || (cb > 0 && !b)) return fail(-1, "bad arguments to ub_pack_ncdhw");
-  if (ca + cb > cp || cp % 32 || cp > 64) return fail(-1, "ub_pack_ncdhw supports cp in {32, 64}, got ca=%d cb=%d cp=%d", ca, cb, cp);
-  const long long total = (long long)n * voxels;
-  const unsigned blocks = (unsigned)((total + 127) / 128);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (cp == 32) pack_ncdhw_kernel<32><<<blocks, 128, 0, st>>>(a, ca, b, cb, reinterpret_cast<__nv_bfloat16*>(out), voxels, total);
-  else pack_ncdhw_kernel<64><<<blocks, 128, 0, st>>>(a, ca, b, cb, reinterpret_cast<__nv_bfloat16*>(out), voxels, total);
+template <bool S2D>
+static int launch_pack(const float* a, int ca, const float* b, int cb, int n, long long voxels, int d, int h, int w,
+                       int cp, void* out, cudaStream_t st) {
+  constexpr int UNROLL = 4;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (cp == 32) {
+    const unsigned blocks = (unsigned)((voxels + 64 * UNROLL - 1) / (64 * UNROLL));
+    pack_ncdhw_kernel<32, S2D, UNROLL><<<dim3(blocks, n), 256, 0, st>>>(a, ca, b, cb, o, voxels, d, h, w);
+  } else {
+    const unsigned blocks = (unsigned)((voxels + 32 * UNROLL - 1) / (32 * UNROLL));
+    pack_ncdhw_kernel<64, S2D, UNROLL><<<dim3(blocks, n), 256, 0, st>>>(a, ca, b, cb, o, voxels, d, h, w);
+  }
   UB_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int ub_pack_ncdhw(const float* a, int ca, const float* b, int cb, int n, long long voxels, int cp,
+                             void* out, void* stream) {
+  if (!a || !out || ca <= 0 || n <= 0 || n > 65535 || (cb > 0 && !b)) return fail(-1, "bad arguments to ub_pack_ncdhw");
+  if (ca + cb > cp || cp % 32 || cp > 64) return fail(-1, "ub_pack_ncdhw supports cp in {32, 64}, got ca=%d cb=%d cp=%d", ca, cb, cp);
+  return launch_pack<false>(a, ca, b, cb, n, voxels, 0, 0, 0, cp, out, (cudaStream_t)stream);
+}
+
+extern "C" int ub_pack_ncdhw_s2d(const float* a, int ca, const float* b, int cb, int n, int d, int h, int w, int cp,
+                                 void* out, void* stream) {
+  if (!a || !out || ca <= 0 || n <= 0 || n > 65535 || (cb > 0 && !b)) return fail(-1, "bad arguments to ub_pack_ncdhw_s2d");
+  if (ca + cb > cp || cp % 32 || cp > 64) return fail(-1, "ub_pack_ncdhw_s2d supports cp in {32, 64}, got ca=%d cb=%d cp=%d", ca, cb, cp);
+  if (d <= 0 || h <= 0 || w <= 0 || ((d | h | w) & 1)) return fail(-1, "ub_pack_ncdhw_s2d needs even positive dims");
+  return launch_pack<true>(a, ca, b, cb, n, (long long)d * h * w, d, h, w, cp, out, (cudaStream_t)stream);
 }
 
 extern "C" int ub_unpack_ncdhw(const void* src, int cp, int c_begin, int c, int n, long long voxels, float* out,
@@ -748,9 +804,14 @@ extern "C" int ub_norm_act_fwd(const void* y, const float* scale, const float* s
   const long long V = (long long)d * h * w;
   cudaStream_t st = (cudaStream_t)stream;
   if (!pooled) {
-    const long long total8 = (long long)n * V * (cp / 8);
-    norm_act_fwd_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<__nv_bfloat16*>(a), A, cp, V, total8);
+    const long long vps = V * (cp / 8);
+    if (vps >= (1ll << 31) || n > 65535) return fail(-2, "ub_norm_act_fwd: sample too large");
+    constexpr int UNROLL = 4;
+    const dim3 grid((unsigned)((vps + 256 * UNROLL - 1) / (256 * UNROLL)), n);
+    const __nv_bfloat16* yp = reinterpret_cast<const __nv_bfloat16*>(y);
+    __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(a);
+    if (256 % (cp / 8) == 0) norm_act_fwd_kernel<UNROLL, true><<<grid, 256, 0, st>>>(yp, ap, A, cp, (uint32_t)vps);
+    else norm_act_fwd_kernel<UNROLL, false><<<grid, 256, 0, st>>>(yp, ap, A, cp, (uint32_t)vps);
   } else {
     if ((d | h | w) & 1) return fail(-1, "fused max-pool needs even dims");
     const long long total8 = (long long)n * (V / 8) * (cp / 8);
@@ -762,46 +823,53 @@ extern "C" int ub_norm_act_fwd(const void* y, const float* scale, const float* s
   return 0;
 }
 
-static const int kBwdBlocksPerSample = 128;
+// blocks per sample of the backward reduction: enough CTAs to fill the GPU whatever the batch size
+static int bwd_blocks_per_sample(int n) {
+  int b = (1184 + n - 1) / n;
+  return b < 128 ? 128 : b;
+}
 extern "C" long long ub_norm_act_bwd_workspace_bytes(int n, int cp) {
   // block partials + c1 + c2
-  return ((long long)n * kBwdBlocksPerSample * 2 * cp + 2ll * n * cp) * 4;
+  return ((long long)n * bwd_blocks_per_sample(n) * 2 * cp + 2ll * n * cp) * 4;
 }
 
 extern "C" int ub_norm_act_bwd(const void* dA, const void* a, const void* y, int mode, const float* mean,
                                const float* rstd, const float* scale, float slope, float drop_p, uint32_t drop_seed,
                                int n, long long voxels, int cp, int c, void* workspace, void* dy, float* dgamma,
                                float* dbeta, float* dbias, void* stream) {
-  if (!dA || !a || !dy || cp % 8) return fail(-1, "bad arguments to ub_norm_act_bwd");
+  if (!dA || !a || !dy || cp % 8 || n <= 0 || n > 65535) return fail(-1, "bad arguments to ub_norm_act_bwd");
+  const int c8 = cp / 8;
+  if (cp > 512 || 256 % c8) return fail(-2, "norm/activation backward supports cp in {8..512} with cp/8 dividing 256, got %d", cp);
+  const long long vps = voxels * c8;
+  if (vps >= (1ll << 31)) return fail(-2, "ub_norm_act_bwd: sample too large");
   cudaStream_t st = (cudaStream_t)stream;
   NormBwdArgs B;
   memset(&B, 0, sizeof(B));
   B.slope = slope; B.drop_p = drop_p; B.drop_seed = drop_seed; B.drop_thresh = drop_thresh(drop_p);
-  const long long total8 = (long long)n * voxels * (cp / 8);
   if (mode != UB_NORM_NONE) {
     if (!y || !mean || !rstd || !scale || !workspace) return fail(-1, "norm backward needs y, mean, rstd, scale, workspace");
-    if (cp > 512) return fail(-2, "norm backward supports cp <= 512");
+    const int bps_max = bwd_blocks_per_sample(n);
     float* part = reinterpret_cast<float*>(workspace);
-    float* c1 = part + (size_t)n * kBwdBlocksPerSample * 2 * cp;
+    float* c1 = part + (size_t)n * bps_max * 2 * cp;
     float* c2 = c1 + (size_t)n * cp;
     B.mean = mean; B.rstd = rstd; B.gscale = scale; B.c1 = c1; B.c2 = c2;
     int threads = 256;
     if (threads < cp) threads = cp;
-    long long bps = kBwdBlocksPerSample;
-    const int lanes_v = threads / (cp / 8);
-    if (bps * lanes_v > voxels) bps = (voxels + lanes_v - 1) / lanes_v;
+    long long bps = bps_max;
+    if (bps * threads * 2 > vps) bps = (vps + 2ll * threads - 1) / (2ll * threads);
     if (bps < 1) bps = 1;
     norm_act_bwd_reduce_kernel<<<dim3((unsigned)bps, n), threads, 2 * threads * 8 * sizeof(float), st>>>(
         reinterpret_cast<const __nv_bfloat16*>(dA), reinterpret_cast<const __nv_bfloat16*>(a),
-        reinterpret_cast<const __nv_bfloat16*>(y), B, cp, voxels, part);
+        reinterpret_cast<const __nv_bfloat16*>(y), B, cp, (uint32_t)vps, part);
     UB_LAUNCH_CHECK();
     norm_bwd_finalize_kernel<<<cp / 32, dim3(32, 32), 0, st>>>(part, (int)bps, n, cp, c, (double)voxels, mode, scale, c1, c2,
                                                            dgamma, dbeta, dbias);
     UB_LAUNCH_CHECK();
   }
-  norm_act_bwd_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(
+  constexpr int UNROLL = 2;
+  norm_act_bwd_apply_kernel<UNROLL><<<dim3((unsigned)((vps + 256 * UNROLL - 1) / (256 * UNROLL)), n), 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dA), reinterpret_cast<const __nv_bfloat16*>(a),
-      reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<__nv_bfloat16*>(dy), B, cp, voxels, total8);
+      reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<__nv_bfloat16*>(dy), B, cp, (uint32_t)vps);
   UB_LAUNCH_CHECK();
   return 0;
 }

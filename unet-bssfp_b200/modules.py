@@ -22,8 +22,8 @@ import torch
 from torch import nn
 
 from . import ops
-from ._lib import (UB_CONV_K1, UB_CONV_K3S1P1, UB_CONV_K4S2P1, UB_DECONV_K2S2, UB_NORM_BATCH_EVAL,
-                   UB_NORM_BATCH_TRAIN, UB_NORM_INSTANCE, UB_NORM_NONE)
+from ._lib import (UB_CONV_K1, UB_CONV_K3S1P1, UB_CONV_K4S2P1, UB_CONV_K4S2P1_S2D, UB_DECONV_K2S2,
+                   UB_NORM_BATCH_EVAL, UB_NORM_BATCH_TRAIN, UB_NORM_INSTANCE, UB_NORM_NONE)
 
 UNET_FEATURES = (32, 64, 128, 256, 512, 32)
 
@@ -78,7 +78,7 @@ def _block_forward(blk: _Block, cache: _PackedWeights, src0, src1, training, see
     """-> (a, pooled, saved)."""
     spec = blk.spec
     w = cache.get(spec, blk.conv.weight, 0)
-    n, d, h, wd, _ = src0.shape
+    n, d, h, wd = spec.in_dims(src0)
     od, oh, ow = spec.out_dims(d, h, wd)
     sv = _Saved() if save else None
     if blk.norm is None:
@@ -167,8 +167,11 @@ class DownSampleConv(nn.Module):
         self._cache = _PackedWeights()
         self._kind = kind
 
-    def _block(self, name="dsc"):
-        spec = ops.ConvSpec(self._kind, self.conv.in_channels, self.conv.out_channels)
+    def _block(self, name="dsc", s2d_input=False):
+        """``s2d_input``: the block is the first of a chain and reads the space-to-depth pack of the
+        module input (stride-2 stem of the PatchGAN)."""
+        kind = UB_CONV_K4S2P1_S2D if (s2d_input and self._kind == UB_CONV_K4S2P1) else self._kind
+        spec = ops.ConvSpec(kind, self.conv.in_channels, self.conv.out_channels)
         slope = 0.2 if self.activation else 1.0
         if self.batchnorm:
             return _Block(name, spec, self.conv, self.bn, "batch", slope=slope)
@@ -278,7 +281,7 @@ class _ChainFunction(torch.autograd.Function):
         need_bwd = grad_enabled and (x.requires_grad or (y is not None and y.requires_grad) or
                                      any(p.requires_grad for p in params))
         training = chain.owner.training
-        a = ops.pack_ncdhw(x, y)
+        a = ops.pack_ncdhw(x, y, s2d=chain.blocks[0].spec.kind == UB_CONV_K4S2P1_S2D)
         saved = []
         for blk in chain.blocks:
             a, _, sv = _block_forward(blk, chain.cache, a, None, training, 0, save=need_bwd)
@@ -509,7 +512,7 @@ class Discriminator(nn.Module):
 
     def _net(self):
         if self._chain is None:
-            blocks = [self.d1[self.modality]._block("d1"), self.d2._block("d2"), self.d3._block("d3"),
+            blocks = [self.d1[self.modality]._block("d1", s2d_input=True), self.d2._block("d2"), self.d3._block("d3"),
                       self.d4._block("d4"), self.d5._block("d5"),
                       _Block("final", ops.ConvSpec(UB_CONV_K1, 512, 1), self.final)]
             self._chain = _Chain(blocks, self._cache, self, 1)

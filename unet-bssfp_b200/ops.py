@@ -13,8 +13,8 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import (ConvDesc, UB_CONV_K1, UB_CONV_K3S1P1, UB_CONV_K4S2P1, UB_DECONV_K2S2, UB_NORM_BATCH_EVAL,
-                   UB_NORM_BATCH_TRAIN, UB_NORM_INSTANCE, UB_NORM_NONE)
+from ._lib import (ConvDesc, UB_CONV_K1, UB_CONV_K3S1P1, UB_CONV_K4S2P1, UB_CONV_K4S2P1_S2D, UB_DECONV_K2S2,
+                   UB_NORM_BATCH_EVAL, UB_NORM_BATCH_TRAIN, UB_NORM_INSTANCE, UB_NORM_NONE)
 
 __all__ = [
     "ConvSpec", "pad32", "pack_conv_weights", "conv_fwd", "conv_dgrad", "conv_wgrad", "pack_ncdhw", "unpack_ncdhw",
@@ -64,8 +64,15 @@ class ConvSpec:
     def desc(self, n, d, h, w) -> ConvDesc:
         return ConvDesc(self.kind, n, d, h, w, self.c0, self.c0p, self.c1, self.c1p, self.co, self.cop)
 
+    def in_dims(self, src0):
+        """(n, d, h, w) of the ORIGINAL input of this conv given its source tensor."""
+        n, d, h, w, _ = src0.shape
+        if self.kind == UB_CONV_K4S2P1_S2D:      # space-to-depth source (n, d/2, h/2, w/2, 8*c0p)
+            return n, 2 * d, 2 * h, 2 * w
+        return n, d, h, w
+
     def out_dims(self, d, h, w):
-        if self.kind == UB_CONV_K4S2P1:
+        if self.kind in (UB_CONV_K4S2P1, UB_CONV_K4S2P1_S2D):
             return d // 2, h // 2, w // 2
         if self.kind == UB_DECONV_K2S2:
             return d * 2, h * 2, w * 2
@@ -93,7 +100,7 @@ def conv_fwd(spec: ConvSpec, src0, src1, w_packed, bias, act=0, slope=0.0, want_
     """-> (out (N,Do,Ho,Wo,cop) bf16, stats_partial [tiles][2][cop] fp32 | None)."""
     _require_cuda(src0, src1, w_packed, bias)
     lib = _lib.load()
-    n, d, h, w, _ = src0.shape
+    n, d, h, w = spec.in_dims(src0)
     desc = spec.desc(n, d, h, w)
     od, oh, ow = spec.out_dims(d, h, w)
     out = torch.empty((n, od, oh, ow, spec.cop), dtype=torch.bfloat16, device=src0.device)
@@ -123,7 +130,7 @@ def conv_wgrad(spec: ConvSpec, src0, src1, dy, weight_shape):
     """-> dw fp32 in the torch weight layout ``weight_shape``."""
     _require_cuda(src0, src1, dy)
     lib = _lib.load()
-    n, d, h, w, _ = src0.shape
+    n, d, h, w = spec.in_dims(src0)
     desc = spec.desc(n, d, h, w)
     nbytes = lib.ub_conv_wgrad_workspace_bytes(C.byref(desc))
     if nbytes < 0:
@@ -137,8 +144,9 @@ def conv_wgrad(spec: ConvSpec, src0, src1, dy, weight_shape):
 # ---------------------------------------------------------------------------------------------------
 # layout
 # ---------------------------------------------------------------------------------------------------
-def pack_ncdhw(a: torch.Tensor, b: torch.Tensor | None = None) -> torch.Tensor:
-    """cat[a, b] NCDHW fp32 -> (N,D,H,W,32) bf16."""
+def pack_ncdhw(a: torch.Tensor, b: torch.Tensor | None = None, s2d: bool = False) -> torch.Tensor:
+    """cat[a, b] NCDHW fp32 -> (N,D,H,W,Cp) bf16; ``s2d``: space-to-depth layout (N,D/2,H/2,W/2,8*Cp) with
+    channel order (pd, ph, pw, c) -- the input layout of the stride-2 PatchGAN stem."""
     _require_cuda(a, b)
     lib = _lib.load()
     a = a.contiguous().float()
@@ -148,6 +156,10 @@ def pack_ncdhw(a: torch.Tensor, b: torch.Tensor | None = None) -> torch.Tensor:
         b = b.contiguous().float()
         cb = b.shape[1]
     cp = pad32(ca + cb)
+    if s2d:
+        out = torch.empty((n, d // 2, h // 2, w // 2, 8 * cp), dtype=torch.bfloat16, device=a.device)
+        _lib.check(lib.ub_pack_ncdhw_s2d(_p(a), ca, _p(b), cb, n, d, h, w, cp, _p(out), _stream()), "ub_pack_ncdhw_s2d")
+        return out
     out = torch.empty((n, d, h, w, cp), dtype=torch.bfloat16, device=a.device)
     _lib.check(lib.ub_pack_ncdhw(_p(a), ca, _p(b), cb, n, d * h * w, cp, _p(out), _stream()), "ub_pack_ncdhw")
     return out
