@@ -95,9 +95,12 @@ int ub_norm_act_fwd(const void* y, const float* scale, const float* shift, float
                     void* stream);
 long long ub_norm_act_bwd_workspace_bytes(int n, int cp);
 /* backward of the block above: dy from dA; dgamma/dbeta/dbias (fp32 [c]) may be NULL.
- * mean == NULL (UB_NORM_NONE): plain activation backward. */
+ * mean == NULL (UB_NORM_NONE): plain activation backward (reads a).
+ * shift != NULL (norm modes): the LeakyReLU branch is recomputed as sign(y * scale + shift) -- the
+ * forward's own fma -- and `a` is not read (may be NULL): 10 instead of 14 bytes per element. */
 int ub_norm_act_bwd(const void* dA, const void* a, const void* y, int mode, const float* mean,
-                    const float* rstd, const float* scale, float slope, float drop_p, uint32_t drop_seed,
+                    const float* rstd, const float* scale, const float* shift, float slope, float drop_p,
+                    uint32_t drop_seed,
                     int n, long long voxels, int cp, int c, void* workspace, void* dy, float* dgamma,
                     float* dbeta, float* dbias, void* stream);
 /* MaxPool3d(2) backward; accumulate != 0 adds onto the gradient already in dA (skip path) */

@@ -21,13 +21,13 @@ def _ref_conv(kind, x, w, b):
         return F.conv3d(x, w, b, stride=1, padding=1)
     if kind == 1:
         return F.conv3d(x, w, b)
-    if kind == 2:
+    if kind in (2, 4):
         return F.conv3d(x, w, b, stride=2, padding=1)
     return F.conv_transpose3d(x, w, b, stride=2)
 
 
 def _weight_shape(kind, ci, co):
-    k = {0: 3, 1: 1, 2: 4, 3: 2}[kind]
+    k = {0: 3, 1: 1, 2: 4, 3: 2, 4: 4}[kind]
     return (ci, co, k, k, k) if kind == 3 else (co, ci, k, k, k)
 
 
@@ -48,10 +48,23 @@ CASES = [
     (2, 30, 0, 32, (1, 16, 32, 16)),
     (2, 32, 0, 64, (2, 8, 8, 8)),
     (2, 256, 0, 512, (2, 4, 4, 4)),
+    (4, 30, 0, 32, (1, 16, 32, 16)),     # PatchGAN stem reading the space-to-depth pack
+    (4, 12, 0, 32, (2, 6, 36, 20)),      # ragged tiles
+    (4, 64, 0, 64, (1, 8, 8, 8)),        # two 32-channel chunks per parity group
     (3, 64, 0, 64, (1, 4, 16, 8)),
     (3, 512, 0, 256, (2, 2, 4, 4)),
     (3, 128, 0, 64, (1, 3, 6, 5)),
 ]
+
+
+def _src(kind, x):
+    """NCDHW fp32 -> the source tensor layout the conv kind reads."""
+    t = to_internal(x)
+    if kind == 4:
+        n, d, h, w, cp = t.shape
+        t = t.view(n, d // 2, 2, h // 2, 2, w // 2, 2, cp).permute(0, 1, 3, 5, 2, 4, 6, 7).reshape(
+            n, d // 2, h // 2, w // 2, 8 * cp).contiguous()
+    return t
 
 
 def _make(kind, c0, c1, co, shape, seed=0):
@@ -71,7 +84,7 @@ def test_conv_forward_and_stats(kind, c0, c1, co, shape):
     x, wt, b = _make(kind, c0, c1, co, shape)
     spec = ops.ConvSpec(kind, c0, co, c1)
     wpk = ops.pack_conv_weights(spec, wt, 0)
-    s0 = to_internal(x[:, :c0])
+    s0 = _src(kind, x[:, :c0])
     s1 = to_internal(x[:, c0:]) if c1 else None
     want_stats = kind != 3
     y, stats = ops.conv_fwd(spec, s0, s1, wpk, b, want_stats=want_stats)
@@ -124,7 +137,7 @@ def test_conv_wgrad(kind, c0, c1, co, shape):
     g = torch.Generator(device="cuda").manual_seed(9)
     dy = bf16_round(torch.randn(ref_y.shape, device="cuda", generator=g))
     (ref_dw,) = torch.autograd.grad(ref_y, wt, dy)
-    s0 = to_internal(x[:, :c0])
+    s0 = _src(kind, x[:, :c0])
     s1 = to_internal(x[:, c0:]) if c1 else None
     dw = ops.conv_wgrad(spec, s0, s1, to_internal(dy), tuple(wt.shape))
     torch.cuda.synchronize()

@@ -101,6 +101,9 @@ def test_norm_act_forward_backward(mode, c, shape, pool):
     assert rel_l2(dbeta, br.grad) < 2e-2
     if mode != "batch_eval":
         assert dbias.abs().max().item() == 0.0
+    # the product path never reads `a`: LeakyReLU branch recomputed from sign(y * scale + shift)
+    dy2, dgamma2, dbeta2, _ = ops.norm_act_bwd(dA, None, yi, imode, mean, rstd, scale, slope, 0.0, 0, c, shift=shift)
+    assert torch.equal(dy2, dy) and torch.equal(dgamma2, dgamma) and torch.equal(dbeta2, dbeta)
 
 
 def test_maxpool_bwd_ties_and_accumulate():

@@ -11,7 +11,7 @@ spec = ops.ConvSpec(kind, c0, co, c1)
 g = torch.Generator(device=dev).manual_seed(0)
 s0 = torch.randn((n, d, h, w, spec.c0p), device=dev, generator=g).to(torch.bfloat16)
 s1 = torch.randn((n, d, h, w, spec.c1p), device=dev, generator=g).to(torch.bfloat16) if c1 else None
-k = {0: 3, 1: 1, 2: 4, 3: 2}[kind]
+k = {0: 3, 1: 1, 2: 4, 3: 2, 4: 4}[kind]
 wshape = (c0 + c1, co, k, k, k) if kind == 3 else (co, c0 + c1, k, k, k)
 wt = torch.randn(wshape, device=dev, generator=g) * 0.05
 od, oh, ow = spec.out_dims(d, h, w)

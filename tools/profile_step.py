@@ -23,8 +23,8 @@ args = ap.parse_args()
 
 dev = torch.device("cuda:0")
 records = []   # (label, ev0, ev1, flops, bytes)
-KIND = {0: "k3", 1: "k1", 2: "k4s2", 3: "dc2"}
-TAPS = {0: 27, 1: 1, 2: 64, 3: 8}
+KIND = {0: "k3", 1: "k1", 2: "k4s2", 3: "dc2", 4: "k4s2d"}
+TAPS = {0: 27, 1: 1, 2: 64, 3: 8, 4: 64}
 
 
 def _nbytes(*ts):
@@ -52,13 +52,13 @@ def conv_label(spec, vox_in, n):
 
 def conv_flops(spec, n, d, h, w):
     v = n * d * h * w
-    if spec.kind == 2:
+    if spec.kind in (2, 4):
         v //= 8
     return 2.0 * v * (spec.c0 + spec.c1) * spec.co * TAPS[spec.kind]
 
 
 def l_conv_fwd(out, spec, src0, src1, *a, **k):
-    n, d, h, w, _ = src0.shape
+    n, d, h, w = spec.in_dims(src0)
     return conv_label(spec, d, n), conv_flops(spec, n, d, h, w), _nbytes(src0, src1, out[0])
 
 
@@ -69,7 +69,7 @@ def l_conv_dgrad(out, spec, dy, wp, in_dhw):
 
 
 def l_conv_wgrad(out, spec, src0, src1, dy, shape):
-    n, d, h, w, _ = src0.shape
+    n, d, h, w = spec.in_dims(src0)
     return conv_label(spec, d, n), conv_flops(spec, n, d, h, w), _nbytes(src0, src1, dy)
 
 

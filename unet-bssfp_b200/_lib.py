@@ -46,7 +46,7 @@ SIGNATURES = {
     "ub_norm_finalize": (_I, [_P, _I, _I, _I, _I, _D, _P, _P, _F, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "ub_norm_act_fwd": (_I, [_P, _P, _P, _F, _F, _U32, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ub_norm_act_bwd_workspace_bytes": (_LL, [_I, _I]),
-    "ub_norm_act_bwd": (_I, [_P, _P, _P, _I, _P, _P, _P, _F, _F, _U32, _I, _LL, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "ub_norm_act_bwd": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _F, _F, _U32, _I, _LL, _I, _I, _P, _P, _P, _P, _P, _P]),
     "ub_maxpool_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ub_colsum_workspace_bytes": (_LL, [_I]),
     "ub_colsum": (_I, [_P, _LL, _I, _I, _P, _P, _P]),

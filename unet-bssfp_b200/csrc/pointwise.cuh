@@ -321,6 +321,8 @@ struct NormBwdArgs {
   const float* gscale;  // [N][Cp] gamma * rstd
   const float* c1;      // [N][Cp]
   const float* c2;      // [N][Cp]
+  const float* fshift;  // [N][Cp] forward shift (beta - mean * gscale); non-null: the LeakyReLU branch is taken
+                        // from sign(y * gscale + fshift) -- the forward's own fma -- and `a` is not read
   float slope, drop_p;
   uint32_t drop_seed, drop_thresh;
 };
@@ -343,6 +345,25 @@ __device__ __forceinline__ void dz1_8(const bf16x8& da8, const bf16x8& a8, const
   }
 }
 
+// Same with the activation sign recomputed from the raw conv output y (no read of `a`).
+__device__ __forceinline__ void dz1_from_y8(const bf16x8& da8, const float (&yy)[8], const float (&sc)[8],
+                                            const float (&sh)[8], const NormBwdArgs& B, unsigned long long e0,
+                                            float (&dz)[8]) {
+  float da[8];
+  unpack8(da8, da);
+  uint32_t keep = 0xFFu;
+  float inv = 1.f;
+  if (B.drop_p > 0.f) {
+    keep = dropout_keep8(e0, B.drop_seed, B.drop_thresh);
+    inv = 1.f / (1.f - B.drop_p);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float g = fmaf(yy[i], sc[i], sh[i]) > 0.f ? da[i] : da[i] * B.slope;
+    dz[i] = (keep >> i) & 1u ? g * inv : 0.f;
+  }
+}
+
 // grid = (blocks_per_sample, N); each block strides over the vectors of one sample; partial sums are
 // written per block: part[(n * blocks_per_sample + b)][2][Cp]. Cp/8 must divide blockDim.x (256), so a
 // thread keeps one channel octet; two vectors per thread are in flight per iteration.
@@ -361,11 +382,15 @@ norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bflo
   const bf16x8* av = reinterpret_cast<const bf16x8*>(a) + base;
   const bf16x8* yv = reinterpret_cast<const bf16x8*>(y) + base;
   float rstd[8], moff[8];   // xhat = y * rstd + moff
+  float sc[8], sh_[8];
+  const bool from_y = B.fshift != nullptr;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const float m = B.mean ? B.mean[(size_t)n * Cp + c0 + k] : 0.f;
     rstd[k] = B.rstd ? B.rstd[(size_t)n * Cp + c0 + k] : 0.f;
     moff[k] = -m * rstd[k];
+    sc[k] = from_y ? B.gscale[(size_t)n * Cp + c0 + k] : 0.f;
+    sh_[k] = from_y ? B.fshift[(size_t)n * Cp + c0 + k] : 0.f;
   }
   float s1[8], s2[8];
 #pragma unroll
@@ -374,20 +399,27 @@ norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bflo
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < vps; i += 2 * stride) {
     const uint32_t j = i + stride;
     const bool two = j < vps;
-    const bf16x8 d0 = dAv[i], a0 = av[i], y0 = yv[i];
+    const bf16x8 d0 = dAv[i], y0 = yv[i];
+    bf16x8 a0 = y0;
+    if (!from_y) a0 = av[i];
     bf16x8 d1 = d0, a1 = a0, y1 = y0;
-    if (two) { d1 = dAv[j]; a1 = av[j]; y1 = yv[j]; }
+    if (two) {
+      d1 = dAv[j]; y1 = yv[j];
+      if (!from_y) a1 = av[j];
+    }
     float dz[8], yy[8];
-    dz1_8(d0, a0, B, (unsigned long long)(base + i) * 8ull, dz);
     unpack8(y0, yy);
+    if (from_y) dz1_from_y8(d0, yy, sc, sh_, B, (unsigned long long)(base + i) * 8ull, dz);
+    else dz1_8(d0, a0, B, (unsigned long long)(base + i) * 8ull, dz);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       s1[k] += dz[k];
       s2[k] = fmaf(dz[k], fmaf(yy[k], rstd[k], moff[k]), s2[k]);
     }
     if (two) {
-      dz1_8(d1, a1, B, (unsigned long long)(base + j) * 8ull, dz);
       unpack8(y1, yy);
+      if (from_y) dz1_from_y8(d1, yy, sc, sh_, B, (unsigned long long)(base + j) * 8ull, dz);
+      else dz1_8(d1, a1, B, (unsigned long long)(base + j) * 8ull, dz);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         s1[k] += dz[k];
@@ -476,7 +508,8 @@ norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloa
   const bf16x8* yv = reinterpret_cast<const bf16x8*>(y) + base;
   bf16x8* dyv = reinterpret_cast<bf16x8*>(dy) + base;
   const bool has_norm = B.mean != nullptr;
-  float ka[8], kb[8], kc[8];
+  const bool from_y = B.fshift != nullptr;
+  float ka[8], kb[8], kc[8], sh_[8];
   if (has_norm) {
     const size_t o = (size_t)n * Cp + (threadIdx.x % c8) * 8;
 #pragma unroll
@@ -485,6 +518,7 @@ norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloa
       ka[k] = g;
       kc[k] = -g * r * B.c2[o + k];
       kb[k] = -g * B.c1[o + k] - kc[k] * m;
+      sh_[k] = from_y ? B.fshift[o + k] : 0.f;
     }
   }
   const uint32_t i0 = blockIdx.x * (256u * UNROLL) + threadIdx.x;
@@ -494,7 +528,7 @@ norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloa
     const uint32_t idx = i0 + u * 256u;
     if (idx < vps) {
       d_[u] = dAv[idx];
-      a_[u] = av[idx];
+      if (!from_y) a_[u] = av[idx];
       if (has_norm) y_[u] = yv[idx];
     }
   }
@@ -502,11 +536,11 @@ norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloa
   for (int u = 0; u < UNROLL; ++u) {
     const uint32_t idx = i0 + u * 256u;
     if (idx >= vps) continue;
-    float dz[8];
-    dz1_8(d_[u], a_[u], B, (unsigned long long)(base + idx) * 8ull, dz);
+    float dz[8], yy[8];
+    if (has_norm) unpack8(y_[u], yy);
+    if (from_y) dz1_from_y8(d_[u], yy, ka, sh_, B, (unsigned long long)(base + idx) * 8ull, dz);
+    else dz1_8(d_[u], a_[u], B, (unsigned long long)(base + idx) * 8ull, dz);
     if (has_norm) {
-      float yy[8];
-      unpack8(y_[u], yy);
 #pragma unroll
       for (int k = 0; k < 8; ++k) dz[k] = fmaf(ka[k], dz[k], fmaf(kc[k], yy[k], kb[k]));
     }

@@ -834,10 +834,12 @@ extern "C" long long ub_norm_act_bwd_workspace_bytes(int n, int cp) {
 }
 
 extern "C" int ub_norm_act_bwd(const void* dA, const void* a, const void* y, int mode, const float* mean,
-                               const float* rstd, const float* scale, float slope, float drop_p, uint32_t drop_seed,
+                               const float* rstd, const float* scale, const float* shift, float slope, float drop_p,
+                               uint32_t drop_seed,
                                int n, long long voxels, int cp, int c, void* workspace, void* dy, float* dgamma,
                                float* dbeta, float* dbias, void* stream) {
-  if (!dA || !a || !dy || cp % 8 || n <= 0 || n > 65535) return fail(-1, "bad arguments to ub_norm_act_bwd");
+  if (!dA || !dy || cp % 8 || n <= 0 || n > 65535) return fail(-1, "bad arguments to ub_norm_act_bwd");
+  if (!a && (mode == UB_NORM_NONE || !shift)) return fail(-1, "ub_norm_act_bwd needs the activations `a` or (y, scale, shift)");
   const int c8 = cp / 8;
   if (cp > 512 || 256 % c8) return fail(-2, "norm/activation backward supports cp in {8..512} with cp/8 dividing 256, got %d", cp);
   const long long vps = voxels * c8;
@@ -853,6 +855,7 @@ extern "C" int ub_norm_act_bwd(const void* dA, const void* a, const void* y, int
     float* c1 = part + (size_t)n * bps_max * 2 * cp;
     float* c2 = c1 + (size_t)n * cp;
     B.mean = mean; B.rstd = rstd; B.gscale = scale; B.c1 = c1; B.c2 = c2;
+    B.fshift = shift;   // non-null: LeakyReLU branch from sign(y * scale + shift), `a` is not read
     int threads = 256;
     if (threads < cp) threads = cp;
     long long bps = bps_max;

@@ -71,7 +71,7 @@ class _Block:
 
 
 class _Saved:
-    __slots__ = ("src0", "src1", "y", "a", "mean", "rstd", "scale", "seed", "mode", "in_dhw", "drop_p")
+    __slots__ = ("src0", "src1", "y", "a", "mean", "rstd", "scale", "shift", "seed", "mode", "in_dhw", "drop_p")
 
 
 def _block_forward(blk: _Block, cache: _PackedWeights, src0, src1, training, seed, pool=False, save=True):
@@ -86,7 +86,7 @@ def _block_forward(blk: _Block, cache: _PackedWeights, src0, src1, training, see
         a, _ = ops.conv_fwd(spec, src0, src1, w, blk.conv.bias, act=act, slope=blk.slope)
         if save:
             sv.src0, sv.src1, sv.y, sv.a, sv.mode, sv.in_dhw = src0, src1, None, a, UB_NORM_NONE, (d, h, wd)
-            sv.mean = sv.rstd = sv.scale = None
+            sv.mean = sv.rstd = sv.scale = sv.shift = None
             sv.seed, sv.drop_p = 0, 0.0
         return a, None, sv
     y, stats = ops.conv_fwd(spec, src0, src1, w, blk.conv.bias, want_stats=True)
@@ -106,7 +106,7 @@ def _block_forward(blk: _Block, cache: _PackedWeights, src0, src1, training, see
     a, pooled = ops.norm_act_fwd(y, scale, shift, blk.slope, drop_p, seed, pool=pool)
     if save:
         sv.src0, sv.src1, sv.y, sv.a, sv.mode, sv.in_dhw = src0, src1, y, a, mode, (d, h, wd)
-        sv.mean, sv.rstd, sv.scale, sv.seed, sv.drop_p = mean, rstd, scale, seed, drop_p
+        sv.mean, sv.rstd, sv.scale, sv.shift, sv.seed, sv.drop_p = mean, rstd, scale, shift, seed, drop_p
     return a, pooled, sv
 
 
@@ -115,9 +115,9 @@ def _block_backward(blk: _Block, cache: _PackedWeights, sv: _Saved, dA, need_w, 
     spec = blk.spec
     co = spec.co
     if blk.norm is not None:
-        dy, dgamma, dbeta, dbias = ops.norm_act_bwd(dA, sv.a, sv.y, sv.mode, sv.mean, sv.rstd, sv.scale, blk.slope,
+        dy, dgamma, dbeta, dbias = ops.norm_act_bwd(dA, None, sv.y, sv.mode, sv.mean, sv.rstd, sv.scale, blk.slope,
                                                     sv.drop_p, sv.seed, co, want_param_grads=need_w,
-                                                    want_bias_grad=need_w)
+                                                    want_bias_grad=need_w, shift=sv.shift)
         if need_w:
             grads[id(blk.norm.weight)] = dgamma
             grads[id(blk.norm.bias)] = dbeta

@@ -206,13 +206,14 @@ def norm_act_fwd(y, scale, shift, slope, drop_p=0.0, drop_seed=0, pool=False):
 
 
 def norm_act_bwd(dA, a, y, mode, mean, rstd, scale, slope, drop_p, drop_seed, c, want_param_grads=True,
-                 want_bias_grad=True):
-    """-> (dy, dgamma|None, dbeta|None, dbias|None)."""
+                 want_bias_grad=True, shift=None):
+    """-> (dy, dgamma|None, dbeta|None, dbias|None). With ``shift`` (norm modes) the activation sign is
+    recomputed from ``y`` and ``a`` is not read (may be None)."""
     lib = _lib.load()
-    n, d, h, w, cp = a.shape
+    n, d, h, w, cp = dA.shape
     voxels = d * h * w
-    dev = a.device
-    dy = torch.empty_like(a)
+    dev = dA.device
+    dy = torch.empty_like(dA)
     ws = None
     dgamma = dbeta = dbias = None
     if mode != UB_NORM_NONE:
@@ -222,7 +223,7 @@ def norm_act_bwd(dA, a, y, mode, mean, rstd, scale, slope, drop_p, drop_seed, c,
             dbeta = torch.empty(c, dtype=torch.float32, device=dev)
         if want_bias_grad:
             dbias = torch.empty(c, dtype=torch.float32, device=dev)
-    _lib.check(lib.ub_norm_act_bwd(_p(dA), _p(a), _p(y), mode, _p(mean), _p(rstd), _p(scale), slope, drop_p,
+    _lib.check(lib.ub_norm_act_bwd(_p(dA), _p(a), _p(y), mode, _p(mean), _p(rstd), _p(scale), _p(shift), slope, drop_p,
                                    drop_seed & 0xFFFFFFFF, n, voxels, cp, c, _p(ws), _p(dy), _p(dgamma), _p(dbeta),
                                    _p(dbias), _stream()), "ub_norm_act_bwd")
     return dy, dgamma, dbeta, dbias
