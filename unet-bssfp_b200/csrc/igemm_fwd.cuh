@@ -16,9 +16,14 @@
 // the rest from source 1, so the concat tensor never exists. Weights stream through a TMA ring,
 // one [NT x kc] tile per (chunk, tap), shared by the TD planes.
 //
-// Epilogue (4 warps, thread <-> accumulator row): tcgen05.ld -> +bias -> optional LeakyReLU ->
-// per-channel sum / sum-of-squares partials (register transpose-reduce with shuffles, one partial
-// record per CTA, no atomics) -> bf16 -> 16-byte global stores (optionally scattered with stride 2).
+// The kernel is persistent: one CTA per SM walks the tile list (stride gridDim.x); the TMA rings run
+// across tile boundaries and the accumulators are double-buffered in TMEM whenever two sets fit in
+// 512 columns, so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
+//
+// Epilogue (8 warps, two per TMEM lane quarter, thread <-> accumulator row): tcgen05.ld -> +bias ->
+// optional LeakyReLU -> per-channel sum / sum-of-squares partials (register transpose-reduce with
+// shuffles, one partial record per tile, no atomics) -> bf16 -> 16-byte global stores; neighbouring
+// lanes exchange half rows first so that every store instruction writes whole 32-byte sectors.
 #pragma once
 #include "sm100_ptx.cuh"
 
@@ -26,7 +31,7 @@ namespace ub {
 
 constexpr int kMaxTaps = 64;
 constexpr int kMaxATiles = 8;
-constexpr int kMaxNTiles = 4;
+constexpr int kMaxNTiles = 16;
 
 struct IgemmTap {
   uint16_t atile;      // which A tile of the stage
@@ -44,6 +49,8 @@ struct IgemmNTile {
   int split;          // columns [split, nt) go to out2 instead (split == nt: single destination)
   void* out2;         // second destination (dgrad of a skip-concat conv: [d skip | d upsampled])
   int out2_cpitch;
+  int wblock_add;     // added to every tap's weight block (transposed conv: the sub-position's tap)
+  int out_p[3];       // destination voxel = tile-space voxel * out_s + out_p (w,h,d)
 };
 
 struct IgemmParams {
@@ -65,7 +72,7 @@ struct IgemmParams {
   int tiles_w, tiles_h, tiles_d;
   int n_ntiles;
   IgemmNTile ntile[kMaxNTiles];
-  int out_s, out_p[3];           // destination voxel = tile-space voxel * out_s + out_p (w,h,d)
+  int out_s;                     // destination voxel = tile-space voxel * out_s + ntile.out_p
   int oD, oH, oW;                // destination tensor dims
   const float* bias;             // [bias_n] real output channels, or nullptr
   int bias_n;
@@ -74,6 +81,8 @@ struct IgemmParams {
   float* stats;                  // [tile][2][w_rows_per_block] partial sum / sumsq, or nullptr
   // shared memory plan (bytes)
   int plane_stride, a_stage_bytes, b_stage_bytes, nsa, nsb, tmem_cols;
+  int nacc;                      // TMEM accumulator sets (2: the epilogue of a tile overlaps the next tile's MMAs)
+  int total_tiles;
 };
 
 __device__ __forceinline__ void tmem_alloc_rt(uint32_t smem_slot, uint32_t ncols) {
@@ -112,9 +121,26 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-constexpr int kIgemmThreads = 192;  // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
+constexpr int kIgemmThreads = 192;  // marching / wgrad kernels: warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
+constexpr int kFwdEpiWarps = 8;
+constexpr int kFwdThreads = (kFwdEpiWarps + 2) * 32;  // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
+constexpr int kFwdRedFloats = 2 * kFwdEpiWarps * 2 * 128 + 128;  // [parity][warp][sum|sumsq][128] + bias[128]
 
-__global__ void __launch_bounds__(kIgemmThreads, 1)
+struct IgemmTileCoord {
+  int w0, h0, d0, nb, planes;
+};
+__device__ __forceinline__ IgemmTileCoord igemm_tile(const IgemmParams& P, int t) {
+  IgemmTileCoord c;
+  const int tw_i = t % P.tiles_w; t /= P.tiles_w;
+  const int th_i = t % P.tiles_h; t /= P.tiles_h;
+  const int td_i = t % P.tiles_d; t /= P.tiles_d;
+  c.nb = t;
+  c.w0 = tw_i * 8; c.h0 = th_i * 16; c.d0 = td_i * P.td;
+  c.planes = P.Do - c.d0; if (c.planes > P.td) c.planes = P.td;
+  return c;
+}
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
 igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -124,79 +150,75 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
   const uint32_t a_base = base;
   const uint32_t b_base = a_base + P.nsa * P.a_stage_bytes;
   const uint32_t bar_base = b_base + P.nsb * P.b_stage_bytes;  // 8-byte mbarriers
-  // barrier layout: a_full[nsa] a_empty[nsa] b_full[nsb] b_empty[nsb] acc_full
+  // barrier layout: a_full[nsa] a_empty[nsa] b_full[nsb] b_empty[nsb] acc_full[2] acc_empty[2]
   const uint32_t a_full = bar_base, a_empty = a_full + 8 * P.nsa, b_full = a_empty + 8 * P.nsa,
-                 b_empty = b_full + 8 * P.nsb, acc_full = b_empty + 8 * P.nsb;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (acc_full + 8 - base));
-  float* red = reinterpret_cast<float*>(sm + (((acc_full + 16 + 15) & ~15u) - base));  // [4][2][128] + bias[128], 16-B aligned
+                 b_empty = b_full + 8 * P.nsb, acc_full = b_empty + 8 * P.nsb, acc_empty = acc_full + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (acc_empty + 16 - base));
+  float* red = reinterpret_cast<float*>(sm + (((acc_empty + 32 + 15) & ~15u) - base));  // kFwdRedFloats, 16-B aligned
 
-  // ---- tile coordinates
-  int t = blockIdx.x;
-  const int tw_i = t % P.tiles_w; t /= P.tiles_w;
-  const int th_i = t % P.tiles_h; t /= P.tiles_h;
-  const int td_i = t % P.tiles_d; t /= P.tiles_d;
-  const int nb = t;
-  const int w0 = tw_i * 8, h0 = th_i * 16, d0 = td_i * P.td;
   const IgemmNTile NT = P.ntile[blockIdx.y];
   const int ntc = (NT.nt + 31) & ~31;  // TMEM columns per plane accumulator
-  int planes = P.Do - d0; if (planes > P.td) planes = P.td;
+  const int acc_cols = P.td * ntc;     // columns of one accumulator set
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < P.nsa; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < P.nsb; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, kFwdEpiWarps); }
     fence_mbar_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == kFwdEpiWarps && lane == 0) {
     tma_prefetch_desc(&P.tm_src[0]);
     if (P.n_chunks_total > P.n_chunks_src0) tma_prefetch_desc(&P.tm_src[1]);
     tma_prefetch_desc(&P.tm_w);
   }
-  if (warp == 5) tmem_alloc_rt(smem_u32(tmem_slot), P.tmem_cols);
+  if (warp == kFwdEpiWarps + 1) tmem_alloc_rt(smem_u32(tmem_slot), P.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int pitch = P.kc * 2;
 
-  if (warp == 4) {
+  if (warp == kFwdEpiWarps) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       const uint32_t a_bytes = (uint32_t)(P.n_atiles * P.n_in_planes * P.bh * P.bw * pitch);
       const uint32_t b_bytes = (uint32_t)(NT.nt * pitch);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      for (int ch = 0; ch < P.n_chunks_total; ++ch) {
-        mbar_wait(a_empty + 8 * sa, pa ^ 1);
-        mbar_expect_tx(a_full + 8 * sa, a_bytes);
-        const bool s1 = ch >= P.n_chunks_src0;
-        const CUtensorMap* tm = &P.tm_src[s1 ? 1 : 0];
-        const int c0 = (s1 ? ch - P.n_chunks_src0 : ch) * P.kc;
-        const int grp = P.chunks_per_group ? ch / P.chunks_per_group : 0;
-        uint32_t dst = a_base + sa * P.a_stage_bytes;
-        for (int at = 0; at < P.n_atiles; ++at) {
-          const int oi = P.chunks_per_group ? grp : at;
-          const int cw = w0 * P.in_stride + P.atile_off[oi][0];
-          const int chh = h0 * P.in_stride + P.atile_off[oi][1];
-          for (int p = 0; p < P.n_in_planes; ++p, dst += P.plane_stride) {
-            const int cd = (d0 + p) * P.in_stride + P.atile_off[oi][2];
-            tma_load_5d(dst, tm, a_full + 8 * sa, c0, cw, chh, cd, nb);
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        const IgemmTileCoord T = igemm_tile(P, t);
+        for (int ch = 0; ch < P.n_chunks_total; ++ch) {
+          mbar_wait(a_empty + 8 * sa, pa ^ 1);
+          mbar_expect_tx(a_full + 8 * sa, a_bytes);
+          const bool s1 = ch >= P.n_chunks_src0;
+          const CUtensorMap* tm = &P.tm_src[s1 ? 1 : 0];
+          const int c0 = (s1 ? ch - P.n_chunks_src0 : ch) * P.kc;
+          const int grp = P.chunks_per_group ? ch / P.chunks_per_group : 0;
+          uint32_t dst = a_base + sa * P.a_stage_bytes;
+          for (int at = 0; at < P.n_atiles; ++at) {
+            const int oi = P.chunks_per_group ? grp : at;
+            const int cw = T.w0 * P.in_stride + P.atile_off[oi][0];
+            const int chh = T.h0 * P.in_stride + P.atile_off[oi][1];
+            for (int p = 0; p < P.n_in_planes; ++p, dst += P.plane_stride) {
+              const int cd = (T.d0 + p) * P.in_stride + P.atile_off[oi][2];
+              tma_load_5d(dst, tm, a_full + 8 * sa, c0, cw, chh, cd, T.nb);
+            }
           }
+          const int wk = (P.chunks_per_group ? ch % P.chunks_per_group : ch) * P.kc;
+          const IgemmTap* taps = P.taps + grp * P.ntaps;
+          for (int tp = 0; tp < P.ntaps; ++tp) {
+            mbar_wait(b_empty + 8 * sb, pb ^ 1);
+            mbar_expect_tx(b_full + 8 * sb, b_bytes);
+            tma_load_2d(b_base + sb * P.b_stage_bytes, &P.tm_w, b_full + 8 * sb, wk,
+                        (taps[tp].wblock + NT.wblock_add) * P.w_rows_per_block + NT.n0);
+            if (++sb == P.nsb) { sb = 0; pb ^= 1; }
+          }
+          if (++sa == P.nsa) { sa = 0; pa ^= 1; }
         }
-        const int wk = (P.chunks_per_group ? ch % P.chunks_per_group : ch) * P.kc;
-        const IgemmTap* taps = P.taps + grp * P.ntaps;
-        for (int tp = 0; tp < P.ntaps; ++tp) {
-          mbar_wait(b_empty + 8 * sb, pb ^ 1);
-          mbar_expect_tx(b_full + 8 * sb, b_bytes);
-          tma_load_2d(b_base + sb * P.b_stage_bytes, &P.tm_w, b_full + 8 * sb, wk,
-                      taps[tp].wblock * P.w_rows_per_block + NT.n0);
-          if (++sb == P.nsb) { sb = 0; pb ^= 1; }
-        }
-        if (++sa == P.nsa) { sa = 0; pa ^= 1; }
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == kFwdEpiWarps + 1) {
     // =========================== MMA issuer ===========================
     // The whole warp walks the pipeline (uniform control flow); one elected lane issues.
     const uint32_t swz = P.kc == 32 ? SWZ_64B : (P.kc == 16 ? SWZ_32B : SWZ_128B);
@@ -206,72 +228,89 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
     const uint32_t lbo_lo = 1u << 16;  // LBO field (16 bytes) lives in the low word
     const uint32_t plane16 = (uint32_t)P.plane_stride >> 4;
     const bool leader = elect_one();
-    int sa = 0, sb = 0;
-    uint32_t pa = 0, pb = 0;
-    for (int ch = 0; ch < P.n_chunks_total; ++ch) {
-      mbar_wait(a_full + 8 * sa, pa);
+    int sa = 0, sb = 0, slot = 0;
+    uint32_t pa = 0, pb = 0, pacc = 0;
+    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+      const IgemmTileCoord T = igemm_tile(P, t);
+      mbar_wait(acc_empty + 8 * slot, pacc ^ 1);
       tc_fence_after();
-      const uint32_t a_stage = a_base + sa * P.a_stage_bytes;
-      const int tbase = P.chunks_per_group ? (ch / P.chunks_per_group) * P.ntaps : 0;
-      for (int tp = 0; tp < P.ntaps; ++tp) {
-        mbar_wait(b_full + 8 * sb, pb);
+      const uint32_t acc0 = tmem + slot * acc_cols;
+      for (int ch = 0; ch < P.n_chunks_total; ++ch) {
+        mbar_wait(a_full + 8 * sa, pa);
         tc_fence_after();
-        if (leader) {
-          const IgemmTap T = P.taps[tbase + tp];
-          const uint32_t a_lo = lbo_lo | ((a_stage + (T.atile * P.n_in_planes + T.plane_off) * P.plane_stride +
-                                           T.row_off * pitch) >> 4);
-          const uint32_t b_lo = lbo_lo | ((b_base + sb * P.b_stage_bytes) >> 4);
-          const uint32_t acc = (ch | tp) != 0;
+        const uint32_t a_stage = a_base + sa * P.a_stage_bytes;
+        const int tbase = P.chunks_per_group ? (ch / P.chunks_per_group) * P.ntaps : 0;
+        for (int tp = 0; tp < P.ntaps; ++tp) {
+          mbar_wait(b_full + 8 * sb, pb);
+          tc_fence_after();
+          if (leader) {
+            const IgemmTap Tp = P.taps[tbase + tp];
+            const uint32_t a_lo = lbo_lo | ((a_stage + (Tp.atile * P.n_in_planes + Tp.plane_off) * P.plane_stride +
+                                             Tp.row_off * pitch) >> 4);
+            const uint32_t b_lo = lbo_lo | ((b_base + sb * P.b_stage_bytes) >> 4);
+            const uint32_t acc = (ch | tp) != 0;
 #pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            if (o < planes) {
-              umma_bf16_lohi(tmem + o * ntc, a_lo + o * plane16, a_hi, b_lo, b_hi, idesc, acc);
-              umma_bf16_lohi(tmem + o * ntc, a_lo + o * plane16 + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+            for (int o = 0; o < 4; ++o) {
+              if (o < T.planes) {
+                umma_bf16_lohi(acc0 + o * ntc, a_lo + o * plane16, a_hi, b_lo, b_hi, idesc, acc);
+                umma_bf16_lohi(acc0 + o * ntc, a_lo + o * plane16 + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+              }
             }
+            umma_commit(b_empty + 8 * sb);
           }
-          umma_commit(b_empty + 8 * sb);
+          __syncwarp();
+          if (++sb == P.nsb) { sb = 0; pb ^= 1; }
         }
+        if (leader) umma_commit(a_empty + 8 * sa);
         __syncwarp();
-        if (++sb == P.nsb) { sb = 0; pb ^= 1; }
+        if (++sa == P.nsa) { sa = 0; pa ^= 1; }
       }
-      if (leader) umma_commit(a_empty + 8 * sa);
+      if (leader) umma_commit(acc_full + 8 * slot);
       __syncwarp();
-      if (++sa == P.nsa) { sa = 0; pa ^= 1; }
+      if (++slot == P.nacc) { slot = 0; pacc ^= 1; }
     }
-    if (leader) umma_commit(acc_full);
-    __syncwarp();
   } else {
-    // =========================== epilogue (warps 0-3) ===========================
-    const int r = warp * 32 + lane;
-    const int h = h0 + (r >> 3), w = w0 + (r & 7);
-    const bool valid_hw = (h < P.Ho) && (w < P.Wo);
+    // =========================== epilogue (warps 0-7) ===========================
+    // warp w reads TMEM lanes 32*(w%4)..+31 (accumulator rows); the two warps of a lane quarter split
+    // the (plane, 32-column chunk) units of a tile between them.
+    const int q = warp & 3, grp = warp >> 2;
+    const int r = q * 32 + lane;
     const bool do_stats = P.stats != nullptr;
     const bool do_act = P.act == 1;
     const float slope = P.act_slope;
-    float s_acc[4] = {0.f, 0.f, 0.f, 0.f}, q_acc[4] = {0.f, 0.f, 0.f, 0.f};
     const int nchunks = (NT.nt + 31) >> 5;
     // bias of this N tile -> smem (zero where there is none), read back as broadcast float4
-    float* bias_s = red + 1024;  // [128]
-    {
+    float* bias_s = red + 2 * kFwdEpiWarps * 2 * 128;  // [128]
+    if (threadIdx.x < 128) {
       const int c = threadIdx.x;
       bias_s[c] = (P.bias != nullptr && c < NT.nt && NT.n0 + c < P.bias_n) ? __ldg(P.bias + NT.n0 + c) : 0.f;
     }
-    named_bar_sync(1, 128);
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
+    named_bar_sync(1, kFwdEpiWarps * 32);
     __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(NT.out);
     __nv_bfloat16* outp2 = reinterpret_cast<__nv_bfloat16*>(NT.out2);
-    const size_t vox_hw = (size_t)(h * P.out_s + P.out_p[1]) * P.oW + (size_t)(w * P.out_s + P.out_p[0]);
-    for (int o = 0; o < planes; ++o) {
-      const int d = d0 + o;
-      const size_t vox = ((size_t)nb * P.oD + (size_t)(d * P.out_s + P.out_p[2])) * P.oH * P.oW + vox_hw;
-      __nv_bfloat16* dst = outp + vox * NT.out_cpitch + NT.out_coff;
-      __nv_bfloat16* dst2 = outp2 + vox * NT.out2_cpitch;
-#pragma unroll 1
-      for (int cc = 0; cc < nchunks; ++cc) {
+    const bool odd = (lane & 1) != 0;
+    int slot = 0, it = 0;
+    uint32_t pacc = 0;
+    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
+      const IgemmTileCoord T = igemm_tile(P, t);
+      const int h = T.h0 + (r >> 3), w = T.w0 + (r & 7);
+      const bool valid_hw = (h < P.Ho) && (w < P.Wo);
+      const bool valid_pair = (h < P.Ho) && ((w ^ 1) < P.Wo);   // the partner lane's row (w +- 1)
+      // rows of the lane pair: even lane's row first
+      const bool valid_e = odd ? valid_pair : valid_hw, valid_o = odd ? valid_hw : valid_pair;
+      const size_t vox_hw = (size_t)(h * P.out_s + NT.out_p[1]) * P.oW + (size_t)((w & ~1) * P.out_s + NT.out_p[0]);
+      float s_acc[4] = {0.f, 0.f, 0.f, 0.f}, q_acc[4] = {0.f, 0.f, 0.f, 0.f};
+      mbar_wait(acc_full + 8 * slot, pacc);
+      tc_fence_after();
+      const uint32_t acc0 = tmem + ((uint32_t)(q * 32) << 16) + slot * acc_cols;
+      const int units = T.planes * nchunks;
+      for (int u = grp; u < units; u += 2) {
+        const int o = u / nchunks, cc = u - o * nchunks;
+        const int d = T.d0 + o;
+        const size_t vox_e = ((size_t)T.nb * P.oD + (size_t)(d * P.out_s + NT.out_p[2])) * P.oH * P.oW + vox_hw;
         const bool full32 = (NT.nt - cc * 32) >= 32;
         uint32_t rr[32];
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + o * ntc + cc * 32;
+        const uint32_t taddr = acc0 + o * ntc + cc * 32;
         if (full32) {
           tmem_ld_32x32b_x32(taddr, rr);
         } else {
@@ -295,14 +334,32 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
           pk[2 * j] = pack_bf16x2(x0, x1);
           pk[2 * j + 1] = pack_bf16x2(x2, x3);
         }
-        if (valid_hw) {
-          uint4* d4 = cc * 32 < NT.split ? reinterpret_cast<uint4*>(dst + cc * 32)
-                                         : reinterpret_cast<uint4*>(dst2 + (cc * 32 - NT.split));
-          d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          if (full32) {
-            d4[2] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
-            d4[3] = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+        // ---- stores: the lane pair (2k, 2k+1) owns two neighbouring voxel rows (w, w+1). Exchange half
+        // rows so that instruction j writes one whole 32-byte sector per lane pair:
+        //   even lane: row_e chunk 0 | row_e chunk 2 | row_o chunk 0 | row_o chunk 2
+        //   odd  lane: row_e chunk 1 | row_e chunk 3 | row_o chunk 1 | row_o chunk 3
+        {
+          uint32_t sx[8], rx[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            sx[j] = odd ? pk[j] : pk[4 + j];            // odd sends chunk 0, even sends chunk 1
+            sx[4 + j] = odd ? pk[8 + j] : pk[12 + j];   // odd sends chunk 2, even sends chunk 3
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rx[j] = __shfl_xor_sync(0xffffffffu, sx[j], 1);
+          const bool to2 = cc * 32 >= NT.split;
+          __nv_bfloat16* be = to2 ? outp2 + vox_e * NT.out2_cpitch + (cc * 32 - NT.split)
+                                  : outp + vox_e * NT.out_cpitch + NT.out_coff + cc * 32;
+          const size_t row_step = (size_t)P.out_s * (to2 ? NT.out2_cpitch : NT.out_cpitch);
+          uint4* de = reinterpret_cast<uint4*>(be) + (odd ? 1 : 0);
+          uint4* d_o = reinterpret_cast<uint4*>(be + row_step) + (odd ? 1 : 0);
+          if (valid_e) {
+            de[0] = odd ? make_uint4(rx[0], rx[1], rx[2], rx[3]) : make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            if (full32) de[2] = odd ? make_uint4(rx[4], rx[5], rx[6], rx[7]) : make_uint4(pk[8], pk[9], pk[10], pk[11]);
+          }
+          if (valid_o) {
+            d_o[0] = odd ? make_uint4(pk[4], pk[5], pk[6], pk[7]) : make_uint4(rx[0], rx[1], rx[2], rx[3]);
+            if (full32) d_o[2] = odd ? make_uint4(pk[12], pk[13], pk[14], pk[15]) : make_uint4(rx[4], rx[5], rx[6], rx[7]);
           }
         }
         if (do_stats) {
@@ -319,35 +376,41 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
           const float sa_ = warp_transpose_reduce32(a, lane);
           const float sq_ = warp_transpose_reduce32(b, lane);
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (q == cc) { s_acc[q] += sa_; q_acc[q] += sq_; }
+          for (int k = 0; k < 4; ++k)
+            if (k == cc) { s_acc[k] += sa_; q_acc[k] += sq_; }
         }
       }
-    }
-    if (do_stats) {
-      for (int cc = 0; cc < nchunks; ++cc) {
-        float s = 0.f, q = 0.f;
+      // all TMEM reads of this tile are done: hand the accumulator set back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + 8 * slot);
+      if (++slot == P.nacc) { slot = 0; pacc ^= 1; }
+      if (do_stats) {
+        float* rd = red + (it & 1) * (kFwdEpiWarps * 2 * 128);
+        for (int cc = 0; cc < nchunks; ++cc) {
+          float s = 0.f, qq = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k == cc) { s = s_acc[k]; q = q_acc[k]; }
-        red[(warp * 2 + 0) * 128 + cc * 32 + lane] = s;
-        red[(warp * 2 + 1) * 128 + cc * 32 + lane] = q;
-      }
-      named_bar_sync(1, 128);
-      const int c = threadIdx.x;
-      if (c < NT.nt) {
-        float s = 0.f, q = 0.f;
+          for (int k = 0; k < 4; ++k)
+            if (k == cc) { s = s_acc[k]; qq = q_acc[k]; }
+          rd[(warp * 2 + 0) * 128 + cc * 32 + lane] = s;
+          rd[(warp * 2 + 1) * 128 + cc * 32 + lane] = qq;
+        }
+        named_bar_sync(1, kFwdEpiWarps * 32);
+        const int c = threadIdx.x;
+        if (c < NT.nt) {
+          float s = 0.f, qq = 0.f;
 #pragma unroll
-        for (int wq = 0; wq < 4; ++wq) { s += red[(wq * 2 + 0) * 128 + c]; q += red[(wq * 2 + 1) * 128 + c]; }
-        float* st = P.stats + (size_t)blockIdx.x * 2 * P.w_rows_per_block;
-        st[NT.n0 + c] = s;
-        st[P.w_rows_per_block + NT.n0 + c] = q;
+          for (int wq = 0; wq < kFwdEpiWarps; ++wq) { s += rd[(wq * 2 + 0) * 128 + c]; qq += rd[(wq * 2 + 1) * 128 + c]; }
+          float* st = P.stats + (size_t)t * 2 * P.w_rows_per_block;
+          st[NT.n0 + c] = s;
+          st[P.w_rows_per_block + NT.n0 + c] = qq;
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc_rt(tmem, P.tmem_cols);
+  if (warp == kFwdEpiWarps + 1) tmem_dealloc_rt(tmem, P.tmem_cols);
 }
 
 }  // namespace ub

@@ -53,6 +53,24 @@ __device__ __forceinline__ uint32_t dropout_keep8(unsigned long long e0, uint32_
   return m;
 }
 
+// Same mask as dropout_keep8, delivered as per-element factors f[i] = keep ? inv : 0 (no bit packing).
+__device__ __forceinline__ void dropout_factors8(unsigned long long e0, uint32_t seed, uint32_t thresh16, float inv,
+                                                 float (&f)[8]) {
+  const uint32_t salt = seed ^ ((uint32_t)(e0 >> 33) * 0x7FEB352Du);
+  const uint32_t pair0 = (uint32_t)(e0 >> 1);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t h = hash32((pair0 + i) * 0x9E3779B1u ^ salt);
+    f[2 * i] = (h & 0xFFFFu) >= thresh16 ? inv : 0.f;
+    f[2 * i + 1] = (h >> 16) >= thresh16 ? inv : 0.f;
+  }
+}
+// LeakyReLU for slope <= 1 is max(x, slope * x); the general form keeps the select.
+__device__ __forceinline__ float lrelu(float x, float slope, bool slope_le1) {
+  const float t = x * slope;
+  return slope_le1 ? fmaxf(x, t) : (x > 0.f ? x : t);
+}
+
 struct NormActArgs {
   const float* scale;   // [N][Cp]  gamma * rstd          (or nullptr: identity)
   const float* shift;   // [N][Cp]  beta - mean * scale
@@ -229,6 +247,7 @@ norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restri
   const uint32_t i0 = blockIdx.x * (256u * UNROLL) + threadIdx.x;
   const bool has_norm = A.scale != nullptr;
   const bool has_drop = A.drop_p > 0.f;
+  const bool slope_le1 = A.slope <= 1.f;
   const float inv = has_drop ? 1.f / (1.f - A.drop_p) : 1.f;
   float sc[8], sh[8];
   if (FIXED) {
@@ -264,12 +283,13 @@ norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restri
       for (int k = 0; k < 8; ++k) x[k] = fmaf(x[k], sc[k], sh[k]);
     }
     if (has_drop) {
-      const uint32_t keep = dropout_keep8((unsigned long long)(base + idx) * 8ull, A.drop_seed, A.drop_thresh);
+      float f[8];
+      dropout_factors8((unsigned long long)(base + idx) * 8ull, A.drop_seed, A.drop_thresh, inv, f);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) x[k] = (keep >> k) & 1u ? x[k] * inv : 0.f;
+      for (int k = 0; k < 8; ++k) x[k] *= f[k];
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = x[k] > 0.f ? x[k] : x[k] * A.slope;
+    for (int k = 0; k < 8; ++k) x[k] = lrelu(x[k], A.slope, slope_le1);
     av[idx] = pack8(x);
   }
 }
@@ -277,17 +297,19 @@ norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restri
 // thread = (pooled voxel, 8 channels): writes the 8 activated voxels and their max
 __global__ void norm_act_pool_fwd_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a,
                                          __nv_bfloat16* __restrict__ pooled, NormActArgs A, int Cp, int Nb, int D,
-                                         int H, int W, long long total8 /* pooled voxels * Cp/8 */) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total8) return;
-  const int c8 = Cp >> 3;
-  long long pv = i / c8;
-  const int c0 = (int)(i - pv * c8) * 8;
-  const int Wp = W >> 1, Hp = H >> 1, Dp = D >> 1;
+                                         int H, int W, uint32_t per_sample /* pooled voxels * Cp/8 of one sample */) {
+  // grid = (blocks, N): 32-bit index math inside a sample
+  const uint32_t j0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j0 >= per_sample) return;
+  const int n = blockIdx.y;
+  const long long i = (long long)n * per_sample + j0;
+  const uint32_t c8 = (uint32_t)Cp >> 3;
+  uint32_t pv = j0 / c8;
+  const int c0 = (int)(j0 - pv * c8) * 8;
+  const uint32_t Wp = W >> 1, Hp = H >> 1;
   const int wx = (int)(pv % Wp); pv /= Wp;
-  const int hy = (int)(pv % Hp); pv /= Hp;
-  const int dz = (int)(pv % Dp);
-  const int n = (int)(pv / Dp);
+  const int hy = (int)(pv % Hp);
+  const int dz = (int)(pv / Hp);
   float m[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
@@ -332,16 +354,13 @@ __device__ __forceinline__ void dz1_8(const bf16x8& da8, const bf16x8& a8, const
   float da[8], av[8];
   unpack8(da8, da);
   unpack8(a8, av);
-  uint32_t keep = 0xFFu;
-  float inv = 1.f;
-  if (B.drop_p > 0.f) {
-    keep = dropout_keep8(e0, B.drop_seed, B.drop_thresh);
-    inv = 1.f / (1.f - B.drop_p);
-  }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float g = av[i] > 0.f ? da[i] : da[i] * B.slope;
-    dz[i] = (keep >> i) & 1u ? g * inv : 0.f;
+  for (int i = 0; i < 8; ++i) dz[i] = da[i] * (av[i] > 0.f ? 1.f : B.slope);
+  if (B.drop_p > 0.f) {
+    float f[8];
+    dropout_factors8(e0, B.drop_seed, B.drop_thresh, 1.f / (1.f - B.drop_p), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dz[i] *= f[i];
   }
 }
 
@@ -351,16 +370,13 @@ __device__ __forceinline__ void dz1_from_y8(const bf16x8& da8, const float (&yy)
                                             float (&dz)[8]) {
   float da[8];
   unpack8(da8, da);
-  uint32_t keep = 0xFFu;
-  float inv = 1.f;
-  if (B.drop_p > 0.f) {
-    keep = dropout_keep8(e0, B.drop_seed, B.drop_thresh);
-    inv = 1.f / (1.f - B.drop_p);
-  }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float g = fmaf(yy[i], sc[i], sh[i]) > 0.f ? da[i] : da[i] * B.slope;
-    dz[i] = (keep >> i) & 1u ? g * inv : 0.f;
+  for (int i = 0; i < 8; ++i) dz[i] = da[i] * (fmaf(yy[i], sc[i], sh[i]) > 0.f ? 1.f : B.slope);
+  if (B.drop_p > 0.f) {
+    float f[8];
+    dropout_factors8(e0, B.drop_seed, B.drop_thresh, 1.f / (1.f - B.drop_p), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dz[i] *= f[i];
   }
 }
 
@@ -396,30 +412,25 @@ norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bflo
 #pragma unroll
   for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < vps; i += 2 * stride) {
-    const uint32_t j = i + stride;
-    const bool two = j < vps;
-    const bf16x8 d0 = dAv[i], y0 = yv[i];
-    bf16x8 a0 = y0;
-    if (!from_y) a0 = av[i];
-    bf16x8 d1 = d0, a1 = a0, y1 = y0;
-    if (two) {
-      d1 = dAv[j]; y1 = yv[j];
-      if (!from_y) a1 = av[j];
-    }
-    float dz[8], yy[8];
-    unpack8(y0, yy);
-    if (from_y) dz1_from_y8(d0, yy, sc, sh_, B, (unsigned long long)(base + i) * 8ull, dz);
-    else dz1_8(d0, a0, B, (unsigned long long)(base + i) * 8ull, dz);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < vps; i += 4 * stride) {
+    bf16x8 d_[4], y_[4], a_[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      s1[k] += dz[k];
-      s2[k] = fmaf(dz[k], fmaf(yy[k], rstd[k], moff[k]), s2[k]);
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t idx = i + u * stride;
+      if (idx < vps) {
+        d_[u] = dAv[idx];
+        y_[u] = yv[idx];
+        if (!from_y) a_[u] = av[idx];
+      }
     }
-    if (two) {
-      unpack8(y1, yy);
-      if (from_y) dz1_from_y8(d1, yy, sc, sh_, B, (unsigned long long)(base + j) * 8ull, dz);
-      else dz1_8(d1, a1, B, (unsigned long long)(base + j) * 8ull, dz);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t idx = i + u * stride;
+      if (idx >= vps) continue;
+      float dz[8], yy[8];
+      unpack8(y_[u], yy);
+      if (from_y) dz1_from_y8(d_[u], yy, sc, sh_, B, (unsigned long long)(base + idx) * 8ull, dz);
+      else dz1_8(d_[u], a_[u], B, (unsigned long long)(base + idx) * 8ull, dz);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         s1[k] += dz[k];
@@ -496,7 +507,7 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, int blo
 // dy = g*rstd * (dz1 - c1 - xhat * c2) = ka * dz1 + kc * y + kb with per-(n,c) constants held in
 // registers (Cp/8 divides 256: fixed channel octet per thread). grid = (ceil(vps / (256*UNROLL)), N).
 template <int UNROLL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a,
                           const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dy, NormBwdArgs B, int Cp,
                           uint32_t vps) {
@@ -554,17 +565,19 @@ norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloa
 // ------------------------------------------------------------------------------------------------
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ dP,
                                    __nv_bfloat16* __restrict__ dA, int accumulate, int Cp, int Nb, int D, int H, int W,
-                                   long long total8) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total8) return;
-  const int c8 = Cp >> 3;
-  long long pv = i / c8;
-  const int cidx = (int)(i - pv * c8);
-  const int Wp = W >> 1, Hp = H >> 1, Dp = D >> 1;
+                                   uint32_t per_sample /* pooled voxels * Cp/8 of one sample */) {
+  // grid = (blocks, N): 32-bit index math inside a sample
+  const uint32_t j0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j0 >= per_sample) return;
+  const int n = blockIdx.y;
+  const long long i = (long long)n * per_sample + j0;
+  const uint32_t c8 = (uint32_t)Cp >> 3;
+  uint32_t pv = j0 / c8;
+  const int cidx = (int)(j0 - pv * c8);
+  const uint32_t Wp = W >> 1, Hp = H >> 1;
   const int wx = (int)(pv % Wp); pv /= Wp;
-  const int hy = (int)(pv % Hp); pv /= Hp;
-  const int dz = (int)(pv % Dp);
-  const int n = (int)(pv / Dp);
+  const int hy = (int)(pv % Hp);
+  const int dz = (int)(pv / Hp);
   float g[8];
   unpack8(reinterpret_cast<const bf16x8*>(dP)[i], g);
   float best[8];

@@ -182,34 +182,51 @@ struct IgemmPlan {
   int smem;
 };
 
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      n = v;
+    else
+      n = 148;
+  }
+  return n;
+}
+
 // Fill the smem plan / grid once the geometry fields of P are set. nt_max = widest N tile.
+// The kernel is persistent with one CTA per SM: the whole shared memory goes to the TMA rings.
 static int finish_plan(IgemmPlan* pl, int nt_max) {
   IgemmParams& P = pl->P;
   const int pitch = P.kc * 2;
   P.plane_stride = align_up(P.bh * P.bw * pitch, 1024);
   P.a_stage_bytes = P.n_atiles * P.n_in_planes * P.plane_stride;
   P.b_stage_bytes = align_up(nt_max * pitch, 1024);
-  const int misc = 8 * 80 + 16 + 4096 + 512 + 1024;
-  // A stages: double-buffer when there is more than one K chunk and it fits. B ring: as deep as the
-  // remaining budget allows (<= 16): a weight tile is consumed in td*2 MMAs, far faster than one TMA
-  // round trip, so the ring must cover ~2k cycles of latency.
+  const int misc = 8 * 80 + 64 + kFwdRedFloats * 4 + 1024;
+  // A stages: two (the next chunk / next tile loads while this one is multiplied) when they fit.
+  // B ring: as deep as the remaining budget allows (<= 16): a weight tile is consumed in td*2 MMAs,
+  // far faster than one TMA round trip, so the ring must cover ~2k cycles of latency.
   P.nsa = 2;
-  if (P.n_chunks_total == 1 || 2 * P.a_stage_bytes + 4 * P.b_stage_bytes + misc > kSmemBudget) P.nsa = 1;
-  int budget = kSmemBudget;
-  // single-chunk, small-N layers: stay under half the SM so two CTAs co-reside (epilogue of one
-  // overlaps the main loop of the other)
-  if (P.nsa == 1 && P.a_stage_bytes + 8 * P.b_stage_bytes + misc <= 112 * 1024) budget = 112 * 1024;
-  P.nsb = (budget - P.nsa * P.a_stage_bytes - misc) / P.b_stage_bytes;
+  if (2 * P.a_stage_bytes + 4 * P.b_stage_bytes + misc > kSmemBudget) P.nsa = 1;
+  P.nsb = (kSmemBudget - P.nsa * P.a_stage_bytes - misc) / P.b_stage_bytes;
   if (P.nsb > 16) P.nsb = 16;
   if (P.nsb < 2) return fail(-2, "igemm smem plan: no room for the weight ring");
   pl->smem = P.nsa * P.a_stage_bytes + P.nsb * P.b_stage_bytes + misc;
   if (pl->smem > 227 * 1024) return fail(-2, "igemm smem plan too large: %d bytes", pl->smem);
-  P.tmem_cols = next_pow2_cols(P.td * align_up(nt_max, 32));
-  if (P.tmem_cols > 512) return fail(-2, "igemm TMEM plan too large: %d columns", P.tmem_cols);
+  if (pl->smem < 120 * 1024) pl->smem = 120 * 1024;   // never two CTAs on one SM (persistent: one per SM)
+  const int set_cols = P.td * align_up(nt_max, 32);
+  if (set_cols > 512) return fail(-2, "igemm TMEM plan too large: %d columns", set_cols);
+  P.nacc = 2 * set_cols <= 512 ? 2 : 1;
+  P.tmem_cols = next_pow2_cols(P.nacc * set_cols);
   P.tiles_w = cdiv(P.Wo, 8);
   P.tiles_h = cdiv(P.Ho, 16);
   P.tiles_d = cdiv(P.Do, P.td);
-  pl->grid = dim3((unsigned)(P.Nb * P.tiles_d * P.tiles_h * P.tiles_w), (unsigned)P.n_ntiles, 1);
+  P.total_tiles = P.Nb * P.tiles_d * P.tiles_h * P.tiles_w;
+  int gx = sm_count() / P.n_ntiles;
+  if (gx < 1) gx = 1;
+  if (gx > P.total_tiles) gx = P.total_tiles;
+  pl->grid = dim3((unsigned)gx, (unsigned)P.n_ntiles, 1);
   return 0;
 }
 
@@ -220,7 +237,7 @@ static int launch_igemm(const IgemmPlan& pl, cudaStream_t st) {
     attr_err = cudaFuncSetAttribute(igemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) return fail(-3, "cudaFuncSetAttribute(igemm_fwd): %s", cudaGetErrorString(attr_err));
-  igemm_fwd_kernel<<<pl.grid, kIgemmThreads, pl.smem, st>>>(pl.P);
+  igemm_fwd_kernel<<<pl.grid, kFwdThreads, pl.smem, st>>>(pl.P);
   UB_LAUNCH_CHECK();
   return 0;
 }
@@ -426,23 +443,31 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
     if (int e = finish_plan(&pl, nt_max)) return e;
     return launch_igemm(pl, st);
   }
-  // UB_DECONV_K2S2 forward: 8 sub-position launches, 1 tap each, scatter store with stride 2
+  // UB_DECONV_K2S2 forward: one launch; the 8 output sub-positions are extra N tiles (blockIdx.y), each
+  // with its own weight tap and scatter offset (stride 2)
   P.td = d->d < 4 ? d->d : 4;
   P.Do = d->d; P.Ho = d->h; P.Wo = d->w;
   P.n_atiles = 1; P.bw = 8; P.bh = 16; P.n_in_planes = P.td; P.in_stride = 1;
   P.ntaps = 1;
   P.out_s = 2;
+  P.taps[0] = IgemmTap{0, 0, 0, 0};
+  if (stats_partial) return fail(-1, "statistics are not produced by the transposed conv forward");
+  {
+    const int base_tiles = P.n_ntiles;
+    if (base_tiles * 8 > kMaxNTiles) return fail(-2, "transposed conv: too many output channels (%d)", d->cop);
+    for (int sp = 1; sp < 8; ++sp)
+      for (int i = 0; i < base_tiles; ++i) P.ntile[sp * base_tiles + i] = P.ntile[i];
+    for (int sp = 0; sp < 8; ++sp)
+      for (int i = 0; i < base_tiles; ++i) {
+        IgemmNTile& T = P.ntile[sp * base_tiles + i];
+        T.wblock_add = sp;
+        T.out_p[0] = sp & 1; T.out_p[1] = (sp >> 1) & 1; T.out_p[2] = (sp >> 2) & 1;
+      }
+    P.n_ntiles = base_tiles * 8;
+  }
   if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 1)) return e;
   if (int e = finish_plan(&pl, nt_max)) return e;
-  if (stats_partial) return fail(-1, "statistics are not produced by the transposed conv forward");
-  for (int i = 0; i < 2; ++i)
-    for (int j = 0; j < 2; ++j)
-      for (int k = 0; k < 2; ++k) {
-        P.taps[0] = IgemmTap{0, 0, 0, (uint16_t)((i * 2 + j) * 2 + k)};
-        P.out_p[0] = k; P.out_p[1] = j; P.out_p[2] = i;
-        if (int e = launch_igemm(pl, st)) return e;
-      }
-  return 0;
+  return launch_igemm(pl, st);
 }
 
 extern "C" int ub_conv_dgrad(const ub_conv_desc* d, const void* dy, const void* w_packed_dgrad, void* dsrc0,
@@ -510,7 +535,7 @@ extern "C" int ub_conv_dgrad(const ub_conv_desc* d, const void* dy, const void* 
           P.atile_off[0][0] = pw ? 0 : -1;
           P.atile_off[0][1] = ph ? 0 : -1;
           P.atile_off[0][2] = pd ? 0 : -1;
-          P.out_p[0] = pw; P.out_p[1] = ph; P.out_p[2] = pd;
+          for (int i = 0; i < P.n_ntiles; ++i) { P.ntile[i].out_p[0] = pw; P.ntile[i].out_p[1] = ph; P.ntile[i].out_p[2] = pd; }
           int t = 0;
           for (int sd = 0; sd < 2; ++sd)
             for (int sh = 0; sh < 2; ++sh)
@@ -814,10 +839,11 @@ extern "C" int ub_norm_act_fwd(const void* y, const float* scale, const float* s
     else norm_act_fwd_kernel<UNROLL, false><<<grid, 256, 0, st>>>(yp, ap, A, cp, (uint32_t)vps);
   } else {
     if ((d | h | w) & 1) return fail(-1, "fused max-pool needs even dims");
-    const long long total8 = (long long)n * (V / 8) * (cp / 8);
-    norm_act_pool_fwd_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(
+    const long long per_sample = (V / 8) * (cp / 8);
+    if (per_sample >= (1ll << 31) || n > 65535) return fail(-2, "ub_norm_act_fwd: sample too large");
+    norm_act_pool_fwd_kernel<<<dim3((unsigned)((per_sample + 255) / 256), n), 256, 0, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<__nv_bfloat16*>(a),
-        reinterpret_cast<__nv_bfloat16*>(pooled), A, cp, n, d, h, w, total8);
+        reinterpret_cast<__nv_bfloat16*>(pooled), A, cp, n, d, h, w, (uint32_t)per_sample);
   }
   UB_LAUNCH_CHECK();
   return 0;
@@ -859,7 +885,7 @@ extern "C" int ub_norm_act_bwd(const void* dA, const void* a, const void* y, int
     int threads = 256;
     if (threads < cp) threads = cp;
     long long bps = bps_max;
-    if (bps * threads * 2 > vps) bps = (vps + 2ll * threads - 1) / (2ll * threads);
+    if (bps * threads * 4 > vps) bps = (vps + 4ll * threads - 1) / (4ll * threads);
     if (bps < 1) bps = 1;
     norm_act_bwd_reduce_kernel<<<dim3((unsigned)bps, n), threads, 2 * threads * 8 * sizeof(float), st>>>(
         reinterpret_cast<const __nv_bfloat16*>(dA), reinterpret_cast<const __nv_bfloat16*>(a),
@@ -869,7 +895,7 @@ extern "C" int ub_norm_act_bwd(const void* dA, const void* a, const void* y, int
                                                            dgamma, dbeta, dbias);
     UB_LAUNCH_CHECK();
   }
-  constexpr int UNROLL = 2;
+  constexpr int UNROLL = 4;
   norm_act_bwd_apply_kernel<UNROLL><<<dim3((unsigned)((vps + 256 * UNROLL - 1) / (256 * UNROLL)), n), 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dA), reinterpret_cast<const __nv_bfloat16*>(a),
       reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<__nv_bfloat16*>(dy), B, cp, (uint32_t)vps);
@@ -880,10 +906,11 @@ extern "C" int ub_norm_act_bwd(const void* dA, const void* a, const void* y, int
 extern "C" int ub_maxpool_bwd(const void* a, const void* dP, void* dA, int accumulate, int n, int d, int h, int w,
                               int cp, void* stream) {
   if (!a || !dP || !dA || cp % 8 || ((d | h | w) & 1)) return fail(-1, "bad arguments to ub_maxpool_bwd");
-  const long long total8 = (long long)n * ((long long)d * h * w / 8) * (cp / 8);
-  maxpool_bwd_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  const long long per_sample = ((long long)d * h * w / 8) * (cp / 8);
+  if (per_sample >= (1ll << 31) || n <= 0 || n > 65535) return fail(-2, "ub_maxpool_bwd: sample too large");
+  maxpool_bwd_kernel<<<dim3((unsigned)((per_sample + 255) / 256), n), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(dP),
-      reinterpret_cast<__nv_bfloat16*>(dA), accumulate, cp, n, d, h, w, total8);
+      reinterpret_cast<__nv_bfloat16*>(dA), accumulate, cp, n, d, h, w, (uint32_t)per_sample);
   UB_LAUNCH_CHECK();
   return 0;
 }
