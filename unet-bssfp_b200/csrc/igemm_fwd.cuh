@@ -50,6 +50,7 @@ struct IgemmNTile {
   void* out2;         // second destination (dgrad of a skip-concat conv: [d skip | d upsampled])
   int out2_cpitch;
   int wblock_add;     // added to every tap's weight block (transposed conv: the sub-position's tap)
+  int tapset;         // tap table / tile-origin set of this N tile (stride-2 dgrad: the input parity class)
   int out_p[3];       // destination voxel = tile-space voxel * out_s + out_p (w,h,d)
 };
 
@@ -196,7 +197,7 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
           const int grp = P.chunks_per_group ? ch / P.chunks_per_group : 0;
           uint32_t dst = a_base + sa * P.a_stage_bytes;
           for (int at = 0; at < P.n_atiles; ++at) {
-            const int oi = P.chunks_per_group ? grp : at;
+            const int oi = P.chunks_per_group ? grp : at + NT.tapset;
             const int cw = T.w0 * P.in_stride + P.atile_off[oi][0];
             const int chh = T.h0 * P.in_stride + P.atile_off[oi][1];
             for (int p = 0; p < P.n_in_planes; ++p, dst += P.plane_stride) {
@@ -205,7 +206,7 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
             }
           }
           const int wk = (P.chunks_per_group ? ch % P.chunks_per_group : ch) * P.kc;
-          const IgemmTap* taps = P.taps + grp * P.ntaps;
+          const IgemmTap* taps = P.taps + (P.chunks_per_group ? grp : NT.tapset) * P.ntaps;
           for (int tp = 0; tp < P.ntaps; ++tp) {
             mbar_wait(b_empty + 8 * sb, pb ^ 1);
             mbar_expect_tx(b_full + 8 * sb, b_bytes);
@@ -239,7 +240,7 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
         mbar_wait(a_full + 8 * sa, pa);
         tc_fence_after();
         const uint32_t a_stage = a_base + sa * P.a_stage_bytes;
-        const int tbase = P.chunks_per_group ? (ch / P.chunks_per_group) * P.ntaps : 0;
+        const int tbase = (P.chunks_per_group ? ch / P.chunks_per_group : NT.tapset) * P.ntaps;
         for (int tp = 0; tp < P.ntaps; ++tp) {
           mbar_wait(b_full + 8 * sb, pb);
           tc_fence_after();

@@ -528,14 +528,25 @@ extern "C" int ub_conv_dgrad(const ub_conv_desc* d, const void* dy, const void* 
     P.ntaps = 8;
     P.out_s = 2;
     if (int e = make_act_map(&P.tm_src[0], dy, d->cop, ow, oh, od, d->n, 32, P.bw, P.bh, 1)) return e;
-    if (int e = finish_plan(&pl, nt_max)) return e;
+    // one launch: the 8 parity classes are extra N tiles (blockIdx.y), each with its own tap set,
+    // tile origin and scatter offset
+    const int base_tiles = P.n_ntiles;
+    if (base_tiles * 8 > kMaxNTiles) return fail(-2, "stride-2 dgrad: too many input channels (%d)", ncols);
+    for (int cls = 1; cls < 8; ++cls)
+      for (int i = 0; i < base_tiles; ++i) P.ntile[cls * base_tiles + i] = P.ntile[i];
+    P.n_ntiles = base_tiles * 8;
     for (int pd = 0; pd < 2; ++pd)
       for (int ph = 0; ph < 2; ++ph)
         for (int pw = 0; pw < 2; ++pw) {
-          P.atile_off[0][0] = pw ? 0 : -1;
-          P.atile_off[0][1] = ph ? 0 : -1;
-          P.atile_off[0][2] = pd ? 0 : -1;
-          for (int i = 0; i < P.n_ntiles; ++i) { P.ntile[i].out_p[0] = pw; P.ntile[i].out_p[1] = ph; P.ntile[i].out_p[2] = pd; }
+          const int cls = (pd * 2 + ph) * 2 + pw;
+          P.atile_off[cls][0] = pw ? 0 : -1;
+          P.atile_off[cls][1] = ph ? 0 : -1;
+          P.atile_off[cls][2] = pd ? 0 : -1;
+          for (int i = 0; i < base_tiles; ++i) {
+            IgemmNTile& T = P.ntile[cls * base_tiles + i];
+            T.tapset = cls;
+            T.out_p[0] = pw; T.out_p[1] = ph; T.out_p[2] = pd;
+          }
           int t = 0;
           for (int sd = 0; sd < 2; ++sd)
             for (int sh = 0; sh < 2; ++sh)
@@ -544,11 +555,11 @@ extern "C" int ub_conv_dgrad(const ub_conv_desc* d, const void* dy, const void* 
                 const int kd = pd ? 2 - 2 * sd : 3 - 2 * sd;
                 const int kh = ph ? 2 - 2 * sh : 3 - 2 * sh;
                 const int kw = pw ? 2 - 2 * sw : 3 - 2 * sw;
-                P.taps[t] = IgemmTap{0, (uint16_t)(sh * P.bw + sw), (uint16_t)sd, (uint16_t)((kd * 4 + kh) * 4 + kw)};
+                P.taps[cls * 8 + t] = IgemmTap{0, (uint16_t)(sh * P.bw + sw), (uint16_t)sd, (uint16_t)((kd * 4 + kh) * 4 + kw)};
               }
-          if (int e = launch_igemm(pl, st)) return e;
         }
-    return 0;
+    if (int e = finish_plan(&pl, nt_max)) return e;
+    return launch_igemm(pl, st);
   }
   // UB_DECONV_K2S2 dgrad: gather the 8 fine sub-positions (parity tiles of dy, element stride 2)
   P.td = d->d < 2 ? d->d : 2;
@@ -656,16 +667,20 @@ static int plan_wgrad(const ub_conv_desc* d, WgradPlan* pl) {
   return 0;
 }
 
-static bool use_wgrad_march(const ub_conv_desc* d) { return d->kind == UB_CONV_K3S1P1 && d->cop == 32; }
+// The marching wgrad kernel works on (32 ci x 32 co) blocks; it serves the 3x3x3 layers whose planes
+// fill the 16x8 voxel tile reasonably (the deep, tiny-plane layers stay on the generic kernel).
+static bool use_wgrad_march(const ub_conv_desc* d) {
+  return d->kind == UB_CONV_K3S1P1 && d->h >= 16 && d->w >= 8 && (long long)(d->c0p + d->c1p) * d->cop <= 128 * 256;
+}
 static int wgrad_march_splits(const ub_conv_desc* d) {
-  const int chunks = (d->c0p + d->c1p) / 32;
-  int ns = 148 / chunks;
+  const int cols = (d->c0p + d->c1p) / 32 * (d->cop / 32);
+  int ns = sm_count() / cols;
   return ns < 1 ? 1 : ns;
 }
 
 extern "C" long long ub_conv_wgrad_workspace_bytes(const ub_conv_desc* d) {
   if (check_desc(d)) return -1;
-  if (use_wgrad_march(d)) return (long long)wgrad_march_splits(d) * 27 * (d->c0p + d->c1p) * 32 * 4;
+  if (use_wgrad_march(d)) return (long long)wgrad_march_splits(d) * 27 * (d->c0p + d->c1p) * d->cop * 4;
   WgradPlan pl;
   if (plan_wgrad(d, &pl)) return -1;
   return (long long)pl.grid.x * pl.ntap_lin * pl.P.ci_total * pl.P.co_total * 4;
@@ -686,11 +701,13 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
     M.Nb = d->n; M.D = d->d; M.H = d->h; M.W = d->w;
     march_geometry(d->n, d->d, d->h, d->w, &M.tiles_w, &M.tiles_h, &M.nseg, &M.seg_len);
     M.ci_total = d->c0p + d->c1p;
+    M.co_total = d->cop;
+    M.n_cotiles = d->cop / 32;
     M.partial = reinterpret_cast<float*>(workspace);
     if (int e = make_act_map(&M.tm_x[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, 10, 18, 1)) return e;
     if (d->c1p)
       if (int e = make_act_map(&M.tm_x[1], src1, d->c1p, d->w, d->h, d->d, d->n, 32, 10, 18, 1)) return e;
-    if (int e = make_act_map(&M.tm_dy, dy, 32, d->w, d->h, d->d, d->n, 32, 8, 16, 1)) return e;
+    if (int e = make_act_map(&M.tm_dy, dy, d->cop, d->w, d->h, d->d, d->n, 32, 8, 16, 1)) return e;
     static std::once_flag once_m;
     static cudaError_t attr_err_m = cudaSuccess;
     std::call_once(once_m, [] {
@@ -699,17 +716,17 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
     if (attr_err_m != cudaSuccess) return fail(-3, "cudaFuncSetAttribute(wgrad_march): %s", cudaGetErrorString(attr_err_m));
     const int nsplit = wgrad_march_splits(d);
     const int smem = kWmXStages * kWmXBytes + (kWmYSlots + 2) * kWmYBytes + 8 * 32 + 64 + 1024;
-    wgrad_march_kernel<<<dim3((unsigned)nsplit, (unsigned)M.n_chunks_total), kIgemmThreads, smem, st>>>(M);
+    wgrad_march_kernel<<<dim3((unsigned)nsplit, (unsigned)(M.n_chunks_total * M.n_cotiles)), kIgemmThreads, smem, st>>>(M);
     UB_LAUNCH_CHECK();
     WgradReduceArgs R;
     memset(&R, 0, sizeof(R));
     const int ci = d->c0 + d->c1;
-    R.nsplit = nsplit; R.ntap = 27; R.ci_total = M.ci_total; R.co_total = 32; R.ci = ci; R.co = d->co;
+    R.nsplit = nsplit; R.ntap = 27; R.ci_total = M.ci_total; R.co_total = d->cop; R.ci = ci; R.co = d->co;
     R.stride_ci = 27; R.stride_co = (long long)ci * 27; R.dst_tap_stride = 1;
     R.split_pad = d->c1p ? d->c0p : 0;
     R.split_real = d->c1p ? d->c0 : 0;
     for (int i = 0; i < 64; ++i) R.tapmap[i] = i < 27 ? i : -1;
-    const long long per_split = 27ll * R.ci_total * 32;
+    const long long per_split = 27ll * R.ci_total * d->cop;
     wgrad_reduce_kernel<<<(unsigned)((per_split + 255) / 256), 256, 0, st>>>(M.partial, dw, R);
     UB_LAUNCH_CHECK();
     return 0;

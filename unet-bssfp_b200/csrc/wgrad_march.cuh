@@ -1,5 +1,5 @@
-// Marching-plane weight gradient for the 3x3x3 convs with 32 output channels (the full-resolution
-// layers): dW[kd,kh,kw][ci][co] = sum_v X[v + (kd,kh,kw) - 1][ci] * dY[v][co].
+// Marching-plane weight gradient for the 3x3x3 convs, one (32 input channels x 32 output channels)
+// block per CTA column: dW[kd,kh,kw][ci][co] = sum_v X[v + (kd,kh,kw) - 1][ci] * dY[v][co].
 //
 // igemm_wgrad_kernel handles one kd per CTA with N = C_out = 32 (smem-bound UMMA, X planes loaded three
 // times). Here the depth taps are folded into N by shifting dY instead of X: for one X plane p,
@@ -27,7 +27,8 @@ struct WgradMarchParams {
   int Nb, D, H, W;
   int tiles_w, tiles_h, nseg, seg_len;
   int ci_total;             // padded input channels (partial pitch)
-  float* partial;           // [gridDim.x][27][ci_total][32]
+  int co_total, n_cotiles;  // padded output channels, co_total / 32
+  float* partial;           // [gridDim.x][27][ci_total][co_total]
 };
 
 constexpr int kWmXStages = 4, kWmXBytes = 12288;
@@ -46,7 +47,8 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
                  y_empty = y_full + 8 * kWmYSlots, acc_full = y_empty + 8 * kWmYSlots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (acc_full + 8 - base));
 
-  const int chunk = blockIdx.y;
+  const int chunk = blockIdx.y / P.n_cotiles;
+  const int cot = blockIdx.y - chunk * P.n_cotiles;
   const bool s1 = chunk >= P.n_chunks_src0;
   const int c0 = (s1 ? chunk - P.n_chunks_src0 : chunk) * 32;
   // contiguous range of items for this CTA
@@ -81,8 +83,8 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
         mbar_wait(y_empty + 8 * ys, yp ^ 1);
         const bool mirror = ys < 2;
         mbar_expect_tx(y_full + 8 * ys, mirror ? 2 * kWmYBytes : kWmYBytes);
-        tma_load_5d(y_base + ys * kWmYBytes, &P.tm_dy, y_full + 8 * ys, 0, w0, h0, q, nb);
-        if (mirror) tma_load_5d(y_base + (kWmYSlots + ys) * kWmYBytes, &P.tm_dy, y_full + 8 * ys, 0, w0, h0, q, nb);
+        tma_load_5d(y_base + ys * kWmYBytes, &P.tm_dy, y_full + 8 * ys, cot * 32, w0, h0, q, nb);
+        if (mirror) tma_load_5d(y_base + (kWmYSlots + ys) * kWmYBytes, &P.tm_dy, y_full + 8 * ys, cot * 32, w0, h0, q, nb);
         if (++ys == kWmYSlots) { ys = 0; yp ^= 1; }
       };
       for (int it = i_begin; it < i_end; ++it) {
@@ -173,7 +175,7 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const bool any = i_end > i_begin;
-    const size_t tap_elems = (size_t)P.ci_total * 32;
+    const size_t tap_elems = (size_t)P.ci_total * P.co_total;
     float* outb = P.partial + (size_t)blockIdx.x * 27 * tap_elems;
     for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll 1
@@ -184,7 +186,7 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
         if (warp < 3) {   // warp = kw atom (the 4th atom is unused), lane = ci
           const int kd = 2 - j;
           float4* d4 = reinterpret_cast<float4*>(outb + (size_t)((kd * 3 + kh) * 3 + warp) * tap_elems +
-                                                 (size_t)(chunk * 32 + lane) * 32);
+                                                 (size_t)(chunk * 32 + lane) * P.co_total + cot * 32);
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             d4[q] = any ? make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]),
