@@ -304,81 +304,89 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
       mbar_wait(acc_full + 8 * slot, pacc);
       tc_fence_after();
       const uint32_t acc0 = tmem + ((uint32_t)(q * 32) << 16) + slot * acc_cols;
-      const int units = T.planes * nchunks;
-      for (int u = grp; u < units; u += 2) {
-        const int o = u / nchunks, cc = u - o * nchunks;
-        const int d = T.d0 + o;
-        const size_t vox_e = ((size_t)T.nb * P.oD + (size_t)(d * P.out_s + NT.out_p[2])) * P.oH * P.oW + vox_hw;
+      // the two warps of a lane quarter split the tile by 32-column chunk when their number is even,
+      // else by plane; per-channel statistics are summed in registers over the planes of a chunk and
+      // transposed once per (chunk, tile)
+      const bool by_chunk = (nchunks & 1) == 0;
+      for (int cc = by_chunk ? grp : 0; cc < nchunks; cc += by_chunk ? 2 : 1) {
         const bool full32 = (NT.nt - cc * 32) >= 32;
-        uint32_t rr[32];
-        const uint32_t taddr = acc0 + o * ntc + cc * 32;
-        if (full32) {
-          tmem_ld_32x32b_x32(taddr, rr);
-        } else {
-          uint32_t r16[16];
-          tmem_ld_32x32b_x16(taddr, r16);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { rr[j] = r16[j]; rr[j + 16] = 0u; }
-        }
-        tmem_ld_wait();
-        uint32_t pk[16];
+        const bool to2 = cc * 32 >= NT.split;
         const float4* b4 = reinterpret_cast<const float4*>(bias_s + cc * 32);
+        float st_a[32], st_b[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 bv = b4[j];
-          float x0 = __uint_as_float(rr[4 * j + 0]) + bv.x, x1 = __uint_as_float(rr[4 * j + 1]) + bv.y;
-          float x2 = __uint_as_float(rr[4 * j + 2]) + bv.z, x3 = __uint_as_float(rr[4 * j + 3]) + bv.w;
-          if (do_act) {
-            x0 = x0 > 0.f ? x0 : x0 * slope; x1 = x1 > 0.f ? x1 : x1 * slope;
-            x2 = x2 > 0.f ? x2 : x2 * slope; x3 = x3 > 0.f ? x3 : x3 * slope;
-          }
-          pk[2 * j] = pack_bf16x2(x0, x1);
-          pk[2 * j + 1] = pack_bf16x2(x2, x3);
-        }
-        // ---- stores: the lane pair (2k, 2k+1) owns two neighbouring voxel rows (w, w+1). Exchange half
-        // rows so that instruction j writes one whole 32-byte sector per lane pair:
-        //   even lane: row_e chunk 0 | row_e chunk 2 | row_o chunk 0 | row_o chunk 2
-        //   odd  lane: row_e chunk 1 | row_e chunk 3 | row_o chunk 1 | row_o chunk 3
-        {
-          uint32_t sx[8], rx[8];
+        for (int j = 0; j < 32; ++j) { st_a[j] = 0.f; st_b[j] = 0.f; }
+        for (int o = by_chunk ? 0 : grp; o < T.planes; o += by_chunk ? 1 : 2) {
+          const int d = T.d0 + o;
+          const size_t vox_e = ((size_t)T.nb * P.oD + (size_t)(d * P.out_s + NT.out_p[2])) * P.oH * P.oW + vox_hw;
+          uint32_t rr[32];
+          const uint32_t taddr = acc0 + o * ntc + cc * 32;
+          if (full32) {
+            tmem_ld_32x32b_x32(taddr, rr);
+          } else {
+            uint32_t r16[16];
+            tmem_ld_32x32b_x16(taddr, r16);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            sx[j] = odd ? pk[j] : pk[4 + j];            // odd sends chunk 0, even sends chunk 1
-            sx[4 + j] = odd ? pk[8 + j] : pk[12 + j];   // odd sends chunk 2, even sends chunk 3
+            for (int j = 0; j < 16; ++j) { rr[j] = r16[j]; rr[j + 16] = 0u; }
           }
+          tmem_ld_wait();
+          uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) rx[j] = __shfl_xor_sync(0xffffffffu, sx[j], 1);
-          const bool to2 = cc * 32 >= NT.split;
-          __nv_bfloat16* be = to2 ? outp2 + vox_e * NT.out2_cpitch + (cc * 32 - NT.split)
-                                  : outp + vox_e * NT.out_cpitch + NT.out_coff + cc * 32;
-          const size_t row_step = (size_t)P.out_s * (to2 ? NT.out2_cpitch : NT.out_cpitch);
-          uint4* de = reinterpret_cast<uint4*>(be) + (odd ? 1 : 0);
-          uint4* d_o = reinterpret_cast<uint4*>(be + row_step) + (odd ? 1 : 0);
-          if (valid_e) {
-            de[0] = odd ? make_uint4(rx[0], rx[1], rx[2], rx[3]) : make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            if (full32) de[2] = odd ? make_uint4(rx[4], rx[5], rx[6], rx[7]) : make_uint4(pk[8], pk[9], pk[10], pk[11]);
+          for (int j = 0; j < 8; ++j) {
+            const float4 bv = b4[j];
+            float x0 = __uint_as_float(rr[4 * j + 0]) + bv.x, x1 = __uint_as_float(rr[4 * j + 1]) + bv.y;
+            float x2 = __uint_as_float(rr[4 * j + 2]) + bv.z, x3 = __uint_as_float(rr[4 * j + 3]) + bv.w;
+            if (do_act) {
+              x0 = x0 > 0.f ? x0 : x0 * slope; x1 = x1 > 0.f ? x1 : x1 * slope;
+              x2 = x2 > 0.f ? x2 : x2 * slope; x3 = x3 > 0.f ? x3 : x3 * slope;
+            }
+            pk[2 * j] = pack_bf16x2(x0, x1);
+            pk[2 * j + 1] = pack_bf16x2(x2, x3);
           }
-          if (valid_o) {
-            d_o[0] = odd ? make_uint4(pk[4], pk[5], pk[6], pk[7]) : make_uint4(rx[0], rx[1], rx[2], rx[3]);
-            if (full32) d_o[2] = odd ? make_uint4(pk[12], pk[13], pk[14], pk[15]) : make_uint4(rx[4], rx[5], rx[6], rx[7]);
+          // ---- stores: the lane pair (2k, 2k+1) owns two neighbouring voxel rows (w, w+1). Exchange half
+          // rows so that instruction j writes one whole 32-byte sector per lane pair:
+          //   even lane: row_e chunk 0 | row_e chunk 2 | row_o chunk 0 | row_o chunk 2
+          //   odd  lane: row_e chunk 1 | row_e chunk 3 | row_o chunk 1 | row_o chunk 3
+          {
+            uint32_t sx[8], rx[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              sx[j] = odd ? pk[j] : pk[4 + j];            // odd sends chunk 0, even sends chunk 1
+              sx[4 + j] = odd ? pk[8 + j] : pk[12 + j];   // odd sends chunk 2, even sends chunk 3
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rx[j] = __shfl_xor_sync(0xffffffffu, sx[j], 1);
+            __nv_bfloat16* be = to2 ? outp2 + vox_e * NT.out2_cpitch + (cc * 32 - NT.split)
+                                    : outp + vox_e * NT.out_cpitch + NT.out_coff + cc * 32;
+            const size_t row_step = (size_t)P.out_s * (to2 ? NT.out2_cpitch : NT.out_cpitch);
+            uint4* de = reinterpret_cast<uint4*>(be) + (odd ? 1 : 0);
+            uint4* d_o = reinterpret_cast<uint4*>(be + row_step) + (odd ? 1 : 0);
+            if (valid_e) {
+              de[0] = odd ? make_uint4(rx[0], rx[1], rx[2], rx[3]) : make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              if (full32) de[2] = odd ? make_uint4(rx[4], rx[5], rx[6], rx[7]) : make_uint4(pk[8], pk[9], pk[10], pk[11]);
+            }
+            if (valid_o) {
+              d_o[0] = odd ? make_uint4(pk[4], pk[5], pk[6], pk[7]) : make_uint4(rx[0], rx[1], rx[2], rx[3]);
+              if (full32) d_o[2] = odd ? make_uint4(pk[12], pk[13], pk[14], pk[15]) : make_uint4(rx[4], rx[5], rx[6], rx[7]);
+            }
+          }
+          if (do_stats && valid_hw) {
+            // statistics of the values as stored (bf16-rounded), so the consumer normalises exactly
+            // what it reads
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float lo = __uint_as_float(pk[j] << 16);
+              const float hi = __uint_as_float(pk[j] & 0xFFFF0000u);
+              st_a[2 * j] += lo; st_a[2 * j + 1] += hi;
+              st_b[2 * j] = fmaf(lo, lo, st_b[2 * j]); st_b[2 * j + 1] = fmaf(hi, hi, st_b[2 * j + 1]);
+            }
           }
         }
         if (do_stats) {
-          // statistics of the values as stored (bf16-rounded), so the consumer normalises exactly
-          // what it reads
-          float a[32], b[32];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float lo = valid_hw ? __uint_as_float(pk[j] << 16) : 0.f;
-            const float hi = valid_hw ? __uint_as_float(pk[j] & 0xFFFF0000u) : 0.f;
-            a[2 * j] = lo; a[2 * j + 1] = hi;
-            b[2 * j] = lo * lo; b[2 * j + 1] = hi * hi;
-          }
-          const float sa_ = warp_transpose_reduce32(a, lane);
-          const float sq_ = warp_transpose_reduce32(b, lane);
+          const float sa_ = warp_transpose_reduce32(st_a, lane);
+          const float sq_ = warp_transpose_reduce32(st_b, lane);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (k == cc) { s_acc[k] += sa_; q_acc[k] += sq_; }
+            if (k == cc) { s_acc[k] = sa_; q_acc[k] = sq_; }
         }
       }
       // all TMEM reads of this tile are done: hand the accumulator set back to the MMA warp

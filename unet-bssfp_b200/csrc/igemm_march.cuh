@@ -13,7 +13,8 @@
 // chunk instead of 54), and lands in one of four TMEM accumulators. The epilogue warps, one plane
 // behind, add the three 32-column slices that belong to output plane d -- same thread, three TMEM
 // loads, no cross-lane traffic -- while the MMA thread already works on the next plane (TMEM ring of
-// 4 x 96 columns). The full weight set (9 x 96 x C_in bf16, <= 162 KB for the 96->32 skip-concat conv)
+// 5 x 96 columns). Eight epilogue warps (two per TMEM lane quarter) take alternate output planes.
+// The full weight set (9 x 96 x C_in bf16, <= 162 KB for the 96->32 skip-concat conv)
 // stays resident in shared memory for the CTA's lifetime.
 #pragma once
 #include "igemm_fwd.cuh"
@@ -36,7 +37,11 @@ struct MarchParams {
 constexpr int kMarchPlaneBytes = 12288;   // 180 rows x 64 B, padded to a multiple of 1024
 constexpr int kMarchWTileBytes = 96 * 64;  // one (chunk, kh, kw) weight tile
 
-__global__ void __launch_bounds__(kIgemmThreads, 1)
+constexpr int kMarchRing = 5;       // TMEM accumulator ring: 5 x 96 columns
+constexpr int kMarchEpiWarps = 8;
+constexpr int kMarchThreads = (kMarchEpiWarps + 2) * 32;   // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
+
+__global__ void __launch_bounds__(kMarchThreads, 1)
 igemm_march_kernel(const __grid_constant__ MarchParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -47,11 +52,11 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
   const uint32_t w_base = base;
   const uint32_t a_base = w_base + nch * 9 * kMarchWTileBytes;
   const uint32_t bar_base = a_base + P.nsa * kMarchPlaneBytes;
-  // barriers: w_full | a_full[nsa] | a_empty[nsa] | acc_full[4] | acc_empty[4]
+  // barriers: w_full | a_full[nsa] | a_empty[nsa] | acc_full[ring] | acc_empty[ring]
   const uint32_t w_full = bar_base, a_full = w_full + 8, a_empty = a_full + 8 * P.nsa,
-                 acc_full = a_empty + 8 * P.nsa, acc_empty = acc_full + 32;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (acc_empty + 32 - base));
-  float* red = reinterpret_cast<float*>(sm + (((acc_empty + 48 + 15) & ~15u) - base));  // [4][2][32] + bias[32], 16-B aligned
+                 acc_full = a_empty + 8 * P.nsa, acc_empty = acc_full + 8 * kMarchRing;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (acc_empty + 8 * kMarchRing - base));
+  float* red = reinterpret_cast<float*>(sm + (((acc_empty + 8 * kMarchRing + 16 + 15) & ~15u) - base));  // [8][2][32] + bias[32], 16-B aligned
 
   // ---- work item: (n, h tile, w tile, d segment)
   int t = blockIdx.x;
@@ -68,21 +73,21 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
     for (int i = 0; i < P.nsa; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 4); }
+    for (int i = 0; i < kMarchRing; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, kMarchEpiWarps); }
     fence_mbar_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == kMarchEpiWarps && lane == 0) {
     tma_prefetch_desc(&P.tm_src[0]);
     if (nch > P.n_chunks_src0) tma_prefetch_desc(&P.tm_src[1]);
     tma_prefetch_desc(&P.tm_w);
   }
-  if (warp == 5) tmem_alloc_rt(smem_u32(tmem_slot), 512);
+  if (warp == kMarchEpiWarps + 1) tmem_alloc_rt(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == kMarchEpiWarps) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       mbar_expect_tx(w_full, (uint32_t)(nch * 9 * kMarchWTileBytes));
@@ -103,7 +108,7 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == kMarchEpiWarps + 1) {
     // =========================== MMA issuer ===========================
     const uint32_t idesc = make_idesc_bf16(128, 96, 0, 0);
     const uint32_t a_hi = (uint32_t)(make_smem_desc(0, 16, 10 * 64, SWZ_64B) >> 32);
@@ -142,26 +147,33 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
       }
       if (leader) umma_commit(acc_full + 8 * slot);
       __syncwarp();
-      if (++slot == 4) { slot = 0; pacc ^= 1; }
+      if (++slot == kMarchRing) { slot = 0; pacc ^= 1; }
     }
   } else {
-    // =========================== epilogue (warps 0-3) ===========================
-    const int r = warp * 32 + lane;
+    // =========================== epilogue (warps 0-7) ===========================
+    // warp w reads TMEM lanes 32*(w%4)..+31; group w/4 takes the output planes d_begin + group, +2, ...
+    const int q = warp & 3, grp = warp >> 2;
+    const int r = q * 32 + lane;
     const int h = h0 + (r >> 3), w = w0 + (r & 7);
     const bool valid_hw = (h < P.H) && (w < P.W);
+    const bool valid_pair = (h < P.H) && ((w ^ 1) < P.W);
+    const bool odd = (lane & 1) != 0;
+    const bool valid_e = odd ? valid_pair : valid_hw, valid_o = odd ? valid_hw : valid_pair;
     const bool do_stats = P.stats != nullptr;
-    float* bias_s = red + 256;
+    float* bias_s = red + kMarchEpiWarps * 2 * 32;
     if (threadIdx.x < 32)
       bias_s[threadIdx.x] = (P.bias != nullptr && threadIdx.x < P.bias_n) ? __ldg(P.bias + threadIdx.x) : 0.f;
-    named_bar_sync(1, 128);
-    float s_acc = 0.f, q_acc = 0.f;
+    named_bar_sync(1, kMarchEpiWarps * 32);
+    float st_a[32], st_b[32];   // per-thread channel sums over this warp's planes; transposed once at the end
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { st_a[j] = 0.f; st_b[j] = 0.f; }
     __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(P.out);
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int d = d_begin; d < d_end; ++d) {
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    for (int d = d_begin + grp; d < d_end; d += 2) {
       // newest plane this output needs
       const int pnew = d + 1 <= p_last ? d + 1 : p_last;
       const int pi = pnew - p_first;
-      mbar_wait(acc_full + 8 * (pi & 3), (uint32_t)(pi >> 2) & 1u);
+      mbar_wait(acc_full + 8 * (pi % kMarchRing), (uint32_t)(pi / kMarchRing) & 1u);
       tc_fence_after();
       float v[32];
 #pragma unroll
@@ -171,17 +183,21 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
         const int p = d + kd - 1;
         if (p >= 0 && p < P.D) {            // uniform over the CTA
           uint32_t rr[32];
-          tmem_ld_32x32b_x32(lane_base + (uint32_t)(((p - p_first) & 3) * 96 + kd * 32), rr);
+          tmem_ld_32x32b_x32(lane_base + (uint32_t)(((p - p_first) % kMarchRing) * 96 + kd * 32), rr);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(rr[j]);
         }
       }
-      // plane d-1 is no longer needed by anyone: hand its accumulator back to the MMA thread
-      if (d - 1 >= p_first) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty + 8 * ((d - 1 - p_first) & 3));
+      // Accumulator of input plane p is read by the outputs p-1, p, p+1, i.e. twice by one warp group
+      // and once by the other. Each group arrives after ITS last read: on plane d (read only now by
+      // this group) and on plane d-1 (read before at d-2). The first output plane of a segment also
+      // arrives for the other group, which never touches plane d_begin-1.
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(acc_empty + 8 * ((d - p_first) % kMarchRing));
+        if (d - 1 >= p_first) mbar_arrive_n(acc_empty + 8 * ((d - 1 - p_first) % kMarchRing), d == d_begin ? 2u : 1u);
       }
       uint32_t pk[16];
       const float4* b4 = reinterpret_cast<const float4*>(bias_s);
@@ -191,44 +207,58 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
         pk[2 * j] = pack_bf16x2(v[4 * j + 0] + bv.x, v[4 * j + 1] + bv.y);
         pk[2 * j + 1] = pack_bf16x2(v[4 * j + 2] + bv.z, v[4 * j + 3] + bv.w);
       }
-      if (valid_hw) {
-        const size_t vox = (((size_t)nb * P.D + d) * P.H + h) * P.W + w;
-        uint4* d4 = reinterpret_cast<uint4*>(outp + vox * 32);
-        d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        d4[2] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
-        d4[3] = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+      {
+        // lane pairs exchange half rows so that every store instruction writes whole 32-byte sectors
+        // (see igemm_fwd.cuh)
+        uint32_t sx[8], rx[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sx[j] = odd ? pk[j] : pk[4 + j];
+          sx[4 + j] = odd ? pk[8 + j] : pk[12 + j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rx[j] = __shfl_xor_sync(0xffffffffu, sx[j], 1);
+        const size_t vox_e = (((size_t)nb * P.D + d) * P.H + h) * P.W + (w & ~1);
+        uint4* de = reinterpret_cast<uint4*>(outp + vox_e * 32) + (odd ? 1 : 0);
+        uint4* d_o = de + 4;
+        if (valid_e) {
+          de[0] = odd ? make_uint4(rx[0], rx[1], rx[2], rx[3]) : make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          de[2] = odd ? make_uint4(rx[4], rx[5], rx[6], rx[7]) : make_uint4(pk[8], pk[9], pk[10], pk[11]);
+        }
+        if (valid_o) {
+          d_o[0] = odd ? make_uint4(pk[4], pk[5], pk[6], pk[7]) : make_uint4(rx[0], rx[1], rx[2], rx[3]);
+          d_o[2] = odd ? make_uint4(pk[12], pk[13], pk[14], pk[15]) : make_uint4(rx[4], rx[5], rx[6], rx[7]);
+        }
       }
-      if (do_stats) {
-        float a[32], b[32];
+      if (do_stats && valid_hw) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float lo = valid_hw ? __uint_as_float(pk[j] << 16) : 0.f;
-          const float hi = valid_hw ? __uint_as_float(pk[j] & 0xFFFF0000u) : 0.f;
-          a[2 * j] = lo; a[2 * j + 1] = hi;
-          b[2 * j] = lo * lo; b[2 * j + 1] = hi * hi;
+          const float lo = __uint_as_float(pk[j] << 16);
+          const float hi = __uint_as_float(pk[j] & 0xFFFF0000u);
+          st_a[2 * j] += lo; st_a[2 * j + 1] += hi;
+          st_b[2 * j] = fmaf(lo, lo, st_b[2 * j]); st_b[2 * j + 1] = fmaf(hi, hi, st_b[2 * j + 1]);
         }
-        s_acc += warp_transpose_reduce32(a, lane);
-        q_acc += warp_transpose_reduce32(b, lane);
       }
     }
     if (do_stats) {
+      const float s_acc = warp_transpose_reduce32(st_a, lane);
+      const float q_acc = warp_transpose_reduce32(st_b, lane);
       red[(warp * 2 + 0) * 32 + lane] = s_acc;
       red[(warp * 2 + 1) * 32 + lane] = q_acc;
-      named_bar_sync(1, 128);
+      named_bar_sync(1, kMarchEpiWarps * 32);
       if (threadIdx.x < 32) {
-        float s = 0.f, q = 0.f;
+        float s = 0.f, qq = 0.f;
 #pragma unroll
-        for (int wq = 0; wq < 4; ++wq) { s += red[(wq * 2 + 0) * 32 + lane]; q += red[(wq * 2 + 1) * 32 + lane]; }
+        for (int wq = 0; wq < kMarchEpiWarps; ++wq) { s += red[(wq * 2 + 0) * 32 + lane]; qq += red[(wq * 2 + 1) * 32 + lane]; }
         float* st = P.stats + (size_t)blockIdx.x * 64;
         st[lane] = s;
-        st[32 + lane] = q;
+        st[32 + lane] = qq;
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc_rt(tmem, 512);
+  if (warp == kMarchEpiWarps + 1) tmem_dealloc_rt(tmem, 512);
 }
 
 }  // namespace ub

@@ -290,7 +290,7 @@ static int launch_march(const void* src0, int c0p, const void* src1, int c1p, in
   march_geometry(n, D, H, W, &P.tiles_w, &P.tiles_h, &P.nseg, &P.seg_len);
   P.out = out; P.bias = bias; P.bias_n = bias_n; P.stats = stats;
   const int wbytes = P.n_chunks_total * 9 * kMarchWTileBytes;
-  const int misc = 8 * 32 + 64 + 1280 + 1024;
+  const int misc = 8 * 32 + 64 + (kMarchEpiWarps * 2 * 32 + 32) * 4 + 64 + 1024;
   P.nsa = (220 * 1024 - wbytes - misc) / kMarchPlaneBytes;
   if (P.nsa > 8) P.nsa = 8;
   if (P.nsa < 2) return fail(-2, "march smem plan: no room for the plane ring");
@@ -306,7 +306,7 @@ static int launch_march(const void* src0, int c0p, const void* src1, int c1p, in
   });
   if (attr_err != cudaSuccess) return fail(-3, "cudaFuncSetAttribute(igemm_march): %s", cudaGetErrorString(attr_err));
   const unsigned grid = (unsigned)(n * P.tiles_h * P.tiles_w * P.nseg);
-  igemm_march_kernel<<<grid, kIgemmThreads, smem, st>>>(P);
+  igemm_march_kernel<<<grid, kMarchThreads, smem, st>>>(P);
   UB_LAUNCH_CHECK();
   return 0;
 }
