@@ -68,6 +68,12 @@ struct IgemmParams {
   int ntaps;
   IgemmTap taps[kMaxTaps];
   int w_rows_per_block;
+  // kd_fold (3x3x3, nt in {32, 64}): the weight tile of a (chunk, kh, kw) tap holds the three depth
+  // taps stacked as rows [(2 - kd) * nt + n]; input plane p of the halo then feeds the output planes
+  // p-2 .. p of the tile with ONE UMMA of N = 3 * nt (their accumulators are adjacent TMEM columns),
+  // so the A operand is read from shared memory once per three depth taps.
+  int kd_fold;
+  int b_block_rows;              // rows of one weight block in the packed tensor (nt, or 3 * nt when folded)
   int td;
   int Nb, Do, Ho, Wo;            // tile space (output voxels before the optional scatter)
   int tiles_w, tiles_h, tiles_d;
@@ -183,7 +189,7 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       const uint32_t a_bytes = (uint32_t)(P.n_atiles * P.n_in_planes * P.bh * P.bw * pitch);
-      const uint32_t b_bytes = (uint32_t)(NT.nt * pitch);
+      const uint32_t b_bytes = (uint32_t)((P.kd_fold ? 3 : 1) * NT.nt * pitch);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
@@ -211,7 +217,7 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
             mbar_wait(b_empty + 8 * sb, pb ^ 1);
             mbar_expect_tx(b_full + 8 * sb, b_bytes);
             tma_load_2d(b_base + sb * P.b_stage_bytes, &P.tm_w, b_full + 8 * sb, wk,
-                        (taps[tp].wblock + NT.wblock_add) * P.w_rows_per_block + NT.n0);
+                        (taps[tp].wblock + NT.wblock_add) * P.b_block_rows + NT.n0);
             if (++sb == P.nsb) { sb = 0; pb ^= 1; }
           }
           if (++sa == P.nsa) { sa = 0; pa ^= 1; }
@@ -244,7 +250,33 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
         for (int tp = 0; tp < P.ntaps; ++tp) {
           mbar_wait(b_full + 8 * sb, pb);
           tc_fence_after();
-          if (leader) {
+          if (leader && P.kd_fold) {
+            const IgemmTap Tp = P.taps[tp];
+            const uint32_t a_tap = lbo_lo | ((a_stage + Tp.row_off * pitch) >> 4);
+            const uint32_t b_lo0 = lbo_lo | ((b_base + sb * P.b_stage_bytes) >> 4);
+            const uint32_t kd_rows16 = (uint32_t)(NT.nt * pitch) >> 4;   // one depth-tap block of the weight tile
+            const bool first = (ch | tp) == 0;
+            for (int p_in = 0; p_in < T.planes + 2; ++p_in) {
+              const int o_lo = p_in - 2 > 0 ? p_in - 2 : 0;
+              const int o_hi = p_in < T.planes - 1 ? p_in : T.planes - 1;
+              const uint32_t a_lo = a_tap + p_in * plane16;
+              if (!first) {
+                const uint32_t idesc_n = make_idesc_bf16(128, (o_hi - o_lo + 1) * NT.nt, 0, 0);
+                const uint32_t b_lo = b_lo0 + (2 - (p_in - o_lo)) * kd_rows16;
+                umma_bf16_lohi(acc0 + o_lo * ntc, a_lo, a_hi, b_lo, b_hi, idesc_n, 1u);
+                umma_bf16_lohi(acc0 + o_lo * ntc, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc_n, 1u);
+              } else {
+                // first tap of the tile: each output plane's first contribution (kd = 0) overwrites
+                for (int o = o_lo; o <= o_hi; ++o) {
+                  const int kd = p_in - o;
+                  const uint32_t b_lo = b_lo0 + (2 - kd) * kd_rows16;
+                  umma_bf16_lohi(acc0 + o * ntc, a_lo, a_hi, b_lo, b_hi, idesc, (uint32_t)(kd != 0));
+                  umma_bf16_lohi(acc0 + o * ntc, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                }
+              }
+            }
+            umma_commit(b_empty + 8 * sb);
+          } else if (leader) {
             const IgemmTap Tp = P.taps[tbase + tp];
             const uint32_t a_lo = lbo_lo | ((a_stage + (Tp.atile * P.n_in_planes + Tp.plane_off) * P.plane_stride +
                                              Tp.row_off * pitch) >> 4);

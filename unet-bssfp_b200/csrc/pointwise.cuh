@@ -169,7 +169,8 @@ __global__ void unpack_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float
 // mode 1: BatchNorm, training (per channel over N and voxels; updates running stats with
 //         momentum and the unbiased variance)                           ref: model.py:53-54
 // mode 2: BatchNorm, eval (running statistics; partials unused)
-// grid = (Cp/32, N); block = (32, 32)
+// grid = (Cp/32, N) for InstanceNorm, (Cp/32, 1) for the BatchNorm modes (one reduction over all
+// samples, results broadcast to every n); block = (32, 32)
 __global__ void stats_finalize_kernel(const float* __restrict__ partial, int tiles_per_sample, int Nb, int Cp, int C,
                                       double count_per_sample, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, float eps, int mode, float momentum,
@@ -222,11 +223,14 @@ __global__ void stats_finalize_kernel(const float* __restrict__ partial, int til
   }
   const double rstd = 1.0 / sqrt(var + (double)eps);
   const float g = c < C ? gamma[c] : 0.f, b = c < C ? beta[c] : 0.f;
-  const size_t o = (size_t)n * Cp + c;
-  scale[o] = (float)(g * rstd);
-  shift[o] = (float)(b - mean * g * rstd);
-  mean_out[o] = (float)mean;
-  rstd_out[o] = (float)rstd;
+  const int n_lo = mode == 0 ? n : 0, n_hi = mode == 0 ? n + 1 : Nb;
+  for (int nn = n_lo; nn < n_hi; ++nn) {
+    const size_t o = (size_t)nn * Cp + c;
+    scale[o] = (float)(g * rstd);
+    shift[o] = (float)(b - mean * g * rstd);
+    mean_out[o] = (float)mean;
+    rstd_out[o] = (float)rstd;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -123,6 +123,15 @@ static bool use_march(const ub_conv_desc* d, int dir) {
   return d->c1p == 0 && d->c0p == 32 && d->cop <= 96;
 }
 
+// Depth-tap folding in the generic kernel (igemm_fwd.cuh, kd_fold): 3x3x3 layers whose GEMM N is one
+// tile of 32 or 64 columns and that are not served by the marching kernel.
+static bool use_kd_fold(const ub_conv_desc* d, int dir) {
+  if (d->kind != UB_CONV_K3S1P1 || use_march(d, dir)) return false;
+  if (d->d < 2) return false;
+  if (dir == 0) return d->cop == 32 || d->cop == 64;
+  return d->c1p == 0 && (d->c0p == 32 || d->c0p == 64);
+}
+
 extern "C" long long ub_packed_weight_elems(const ub_conv_desc* d, int dir) {
   if (check_desc(d)) return -1;
   const long long cin = d->c0p + d->c1p;
@@ -159,6 +168,14 @@ extern "C" int ub_pack_conv_weights(const ub_conv_desc* d, int dir, const float*
     A.rows_pad = 96;
     A.fold_tap_stride = dir == 0 ? 9 : -9;
     for (int t = 0; t < 9; ++t) A.tapmap[t] = dir == 0 ? t : 26 - t;
+  }
+  if (use_kd_fold(d, dir)) {
+    // [kh*3+kw][(2 - kd) * rows_pad + n][K]
+    A.nblocks = 9;
+    A.rows_fold = A.rows_pad;
+    A.rows_pad = 3 * A.rows_pad;
+    A.fold_tap_stride = dir == 0 ? -9 : 9;
+    for (int t = 0; t < 9; ++t) A.tapmap[t] = dir == 0 ? 18 + t : 8 - t;
   }
   // concat split: padded index -> real channel (source 1 starts at c0p in padded space, c0 in real space)
   A.split_pad = d->c1p ? d->c0p : 0;
@@ -202,7 +219,7 @@ static int finish_plan(IgemmPlan* pl, int nt_max) {
   const int pitch = P.kc * 2;
   P.plane_stride = align_up(P.bh * P.bw * pitch, 1024);
   P.a_stage_bytes = P.n_atiles * P.n_in_planes * P.plane_stride;
-  P.b_stage_bytes = align_up(nt_max * pitch, 1024);
+  P.b_stage_bytes = align_up((P.kd_fold ? 3 : 1) * nt_max * pitch, 1024);
   const int misc = 8 * 80 + 64 + kFwdRedFloats * 4 + 1024;
   // A stages: two (the next chunk / next tile loads while this one is multiplied) when they fit.
   // B ring: as deep as the remaining budget allows (<= 16): a weight tile is consumed in td*2 MMAs,
@@ -367,8 +384,9 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
   P.out_s = 1;
   make_ntiles(P, d->cop, out, 0, nullptr);
   const int nt_max = d->cop < 128 ? d->cop : 128;
-  if (int e = make_w_map(&P.tm_w, w_packed, ktot, (long long)ntaps * d->cop, 32, nt_max)) return e;
-  if (d->cop > 128 || d->cop == nt_max) { /* all N tiles have nt_max columns */ }
+  P.kd_fold = use_kd_fold(d, 0) ? 1 : 0;
+  P.b_block_rows = P.kd_fold ? 3 * d->cop : d->cop;
+  if (int e = make_w_map(&P.tm_w, w_packed, ktot, (long long)ntaps * d->cop, 32, P.kd_fold ? 3 * nt_max : nt_max)) return e;
 
   if (d->kind == UB_CONV_K3S1P1 || d->kind == UB_CONV_K1) {
     const int k = d->kind == UB_CONV_K3S1P1 ? 3 : 1;
@@ -382,6 +400,7 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
       for (int kh = 0; kh < k; ++kh)
         for (int kw = 0; kw < k; ++kw, ++t)
           P.taps[t] = IgemmTap{0, (uint16_t)(kh * P.bw + kw), (uint16_t)kd, (uint16_t)t};
+    if (P.kd_fold) P.ntaps = 9;   // taps 0..8 are (kd = 0, kh, kw): row offsets and weight blocks of the folded pack
     if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 1)) return e;
     if (d->c1p)
       if (int e = make_act_map(&P.tm_src[1], src1, d->c1p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 1)) return e;
@@ -499,7 +518,9 @@ extern "C" int ub_conv_dgrad(const ub_conv_desc* d, const void* dy, const void* 
   for (int i = 0; i < P.n_ntiles; ++i) nt_max = P.ntile[i].nt > nt_max ? P.ntile[i].nt : nt_max;
   // N tiles may have different widths; the weight box uses the widest, narrower tiles read extra rows
   // of the following tap block / pad rows (never used by their MMA: idesc N = nt)
-  if (int e = make_w_map(&P.tm_w, w_packed_dgrad, d->cop, (long long)ntaps * ncols, 32, nt_max)) return e;
+  P.kd_fold = use_kd_fold(d, 1) ? 1 : 0;
+  P.b_block_rows = P.kd_fold ? 3 * ncols : ncols;
+  if (int e = make_w_map(&P.tm_w, w_packed_dgrad, d->cop, (long long)ntaps * ncols, 32, P.kd_fold ? 3 * nt_max : nt_max)) return e;
   bool uniform = true;
   for (int i = 0; i < P.n_ntiles; ++i) uniform = uniform && P.ntile[i].nt == nt_max;
   if (!uniform) return fail(-2, "dgrad N tiles of unequal width are not supported (c0p=%d c1p=%d)", d->c0p, d->c1p);
@@ -516,6 +537,7 @@ extern "C" int ub_conv_dgrad(const ub_conv_desc* d, const void* dy, const void* 
       for (int kh = 0; kh < k; ++kh)
         for (int kw = 0; kw < k; ++kw, ++t)
           P.taps[t] = IgemmTap{0, (uint16_t)(kh * P.bw + kw), (uint16_t)kd, (uint16_t)t};
+    if (P.kd_fold) P.ntaps = 9;
     if (int e = make_act_map(&P.tm_src[0], dy, d->cop, ow, oh, od, d->n, 32, P.bw, P.bh, 1)) return e;
     if (int e = finish_plan(&pl, nt_max)) return e;
     return launch_igemm(pl, st);
@@ -828,7 +850,7 @@ extern "C" int ub_norm_finalize(const float* stats_partial, int tiles_per_sample
   if ((mode != 2 && !stats_partial) || !gamma || !beta || !scale || !shift || !mean || !rstd || cp % 32)
     return fail(-1, "bad arguments to ub_norm_finalize");
   if (mode == 2 && (!running_mean || !running_var)) return fail(-1, "eval BatchNorm needs running statistics");
-  stats_finalize_kernel<<<dim3(cp / 32, n), dim3(32, 32), 0, (cudaStream_t)stream>>>(
+  stats_finalize_kernel<<<dim3(cp / 32, mode == UB_NORM_INSTANCE ? n : 1), dim3(32, 32), 0, (cudaStream_t)stream>>>(
       stats_partial, tiles_per_sample, n, cp, c, voxels_per_sample, gamma, beta, eps, mode, momentum, running_mean,
       running_var, scale, shift, mean, rstd);
   UB_LAUNCH_CHECK();

@@ -136,6 +136,24 @@ def _block_backward(blk: _Block, cache: _PackedWeights, sv: _Saved, dA, need_w, 
     return None, None
 
 
+class _InputPackCache:
+    """bf16 NDHWC pack of the most recent module input. ``training_step`` feeds the same ``x`` to the
+    generator twice per step (ref:src/model.py:171,184); the second call reuses the pack. The entry is
+    keyed on the tensor object (kept alive, so its storage cannot be recycled under the cache), its
+    in-place version counter and its data pointer."""
+
+    def __init__(self):
+        self._x = self._key = self._packed = None
+
+    def get(self, x):
+        key = (x.data_ptr(), x._version, tuple(x.shape), x.dtype, x.device)
+        if self._x is x and self._key == key:
+            return self._packed
+        packed = ops.pack_ncdhw(x)
+        self._x, self._key, self._packed = x, key, packed
+        return packed
+
+
 def _fresh_seed() -> int:
     # host RNG (follows torch.manual_seed), no device sync
     return int(torch.empty((), dtype=torch.int64).random_().item()) & 0x7FFFFFFF
@@ -324,6 +342,7 @@ class _UNetGraph:
         self.head_mod = head
         self.unet = unet
         self.cache = cache
+        self.input_pack = _InputPackCache()
         p = unet.dropout or 0.0
         f = unet.features
         K3 = UB_CONV_K3S1P1
@@ -389,7 +408,7 @@ class _GeneratorFunction(torch.autograd.Function):
             S[blk.name] = sv
             return a, pooled
 
-        a = ops.pack_ncdhw(x)
+        a = net.input_pack.get(x)
         if net.head is not None:
             a, _ = run(net.head, a, tr=head_training)
         skips = []
