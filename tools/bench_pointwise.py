@@ -55,3 +55,38 @@ if CP == 32:
     timeit("pack_ncdhw cat[x, y] s2d", lambda: ops.pack_ncdhw(x, yy, s2d=True), (x.numel() + yy.numel()) * 4 + elems * 2)
     timeit("unpack_ncdhw 6ch", lambda: ops.unpack_ncdhw(y, 6), elems * 2 + yy.numel() * 4)
     timeit("l1_fwd", lambda: ops.l1_fwd(yy, yy), yy.numel() * 8)
+
+# ---- experiment: do power-of-two distances between the streams (each tensor is exactly 2^30 B at the
+# bench shape) cost DRAM bandwidth? Re-run with the tensors carved out of one buffer at skewed offsets.
+if len(sys.argv) > 4:
+    skew = int(sys.argv[4])
+    big = torch.empty(4 * elems + 4 * 1024 * 1024, dtype=torch.bfloat16, device=dev)
+
+    def carve(k):
+        off = k * (elems + skew // 2)
+        return big[off:off + elems].view(N, S, S, S, CP)
+
+    y2, dA2, a2 = carve(0), carve(1), carve(2)
+    y2.copy_(y); dA2.copy_(dA); a2.copy_(a)
+    print(f"skew {skew} B: ptr deltas {dA2.data_ptr() - y2.data_ptr()}")
+    import ctypes as C
+    lib = _lib.load()
+    out = carve(3)
+
+    def raw_bwd(dAx, yx, outx):
+        ws = torch.empty(lib.ub_norm_act_bwd_workspace_bytes(N, CP) // 4, dtype=torch.float32, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(lib.ub_norm_act_bwd(p(dAx), None, p(yx), I, p(mean), p(rstd), p(scale), p(shift), 0.1, 0.05, 123, N,
+                                       S * S * S, CP, CP, p(ws), p(outx), None, None, None, st))
+
+    def raw_fwd(yx, outx):
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(lib.ub_norm_act_fwd(p(yx), p(scale), p(shift), 0.1, 0.05, 123, N, S, S, S, CP, p(outx), None, st))
+
+    timeit("  skewed norm_act_bwd from y p=0.05", lambda: raw_bwd(dA2, y2, out), elems * 10)
+    timeit("  skewed norm_act_fwd p=0.05", lambda: raw_fwd(y2, out), elems * 4)
+    o2 = torch.empty_like(y)
+    timeit("  unskewed raw norm_act_bwd from y p=0.05", lambda: raw_bwd(dA, y, o2), elems * 10)
+    timeit("  unskewed raw norm_act_fwd p=0.05", lambda: raw_fwd(y, o2), elems * 4)

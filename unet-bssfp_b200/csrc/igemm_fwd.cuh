@@ -68,10 +68,10 @@ struct IgemmParams {
   int ntaps;
   IgemmTap taps[kMaxTaps];
   int w_rows_per_block;
-  // kd_fold (3x3x3, nt in {32, 64}): the weight tile of a (chunk, kh, kw) tap holds the three depth
-  // taps stacked as rows [(2 - kd) * nt + n]; input plane p of the halo then feeds the output planes
-  // p-2 .. p of the tile with ONE UMMA of N = 3 * nt (their accumulators are adjacent TMEM columns),
-  // so the A operand is read from shared memory once per three depth taps.
+  // kd_fold = f > 0 (3x3x3, one N tile of nt columns, f * nt <= 256): the weight tile of a (chunk, kh, kw)
+  // tap holds the three depth taps stacked as rows [(2 - kd) * nt + n]; input plane p of the halo
+  // feeds the output planes p-2 .. p of the tile with UMMAs of N = up to f * nt (their accumulators
+  // are adjacent TMEM columns), so the A operand is read from shared memory once per f depth taps.
   int kd_fold;
   int b_block_rows;              // rows of one weight block in the packed tensor (nt, or 3 * nt when folded)
   int td;
@@ -216,8 +216,12 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
           for (int tp = 0; tp < P.ntaps; ++tp) {
             mbar_wait(b_empty + 8 * sb, pb ^ 1);
             mbar_expect_tx(b_full + 8 * sb, b_bytes);
-            tma_load_2d(b_base + sb * P.b_stage_bytes, &P.tm_w, b_full + 8 * sb, wk,
-                        (taps[tp].wblock + NT.wblock_add) * P.b_block_rows + NT.n0);
+            const int brow = (taps[tp].wblock + NT.wblock_add) * P.b_block_rows + NT.n0;
+            tma_load_2d(b_base + sb * P.b_stage_bytes, &P.tm_w, b_full + 8 * sb, wk, brow);
+            if (P.kd_fold) {   // the three depth-tap blocks of the folded tile (TMA boxes hold <= 256 rows)
+              tma_load_2d(b_base + sb * P.b_stage_bytes + NT.nt * pitch, &P.tm_w, b_full + 8 * sb, wk, brow + NT.nt);
+              tma_load_2d(b_base + sb * P.b_stage_bytes + 2 * NT.nt * pitch, &P.tm_w, b_full + 8 * sb, wk, brow + 2 * NT.nt);
+            }
             if (++sb == P.nsb) { sb = 0; pb ^= 1; }
           }
           if (++sa == P.nsa) { sa = 0; pa ^= 1; }
@@ -261,10 +265,13 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
               const int o_hi = p_in < T.planes - 1 ? p_in : T.planes - 1;
               const uint32_t a_lo = a_tap + p_in * plane16;
               if (!first) {
-                const uint32_t idesc_n = make_idesc_bf16(128, (o_hi - o_lo + 1) * NT.nt, 0, 0);
-                const uint32_t b_lo = b_lo0 + (2 - (p_in - o_lo)) * kd_rows16;
-                umma_bf16_lohi(acc0 + o_lo * ntc, a_lo, a_hi, b_lo, b_hi, idesc_n, 1u);
-                umma_bf16_lohi(acc0 + o_lo * ntc, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc_n, 1u);
+                for (int oa = o_lo; oa <= o_hi; oa += P.kd_fold) {
+                  const int ob = oa + P.kd_fold - 1 < o_hi ? oa + P.kd_fold - 1 : o_hi;
+                  const uint32_t idesc_n = make_idesc_bf16(128, (ob - oa + 1) * NT.nt, 0, 0);
+                  const uint32_t b_lo = b_lo0 + (2 - (p_in - oa)) * kd_rows16;
+                  umma_bf16_lohi(acc0 + oa * ntc, a_lo, a_hi, b_lo, b_hi, idesc_n, 1u);
+                  umma_bf16_lohi(acc0 + oa * ntc, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc_n, 1u);
+                }
               } else {
                 // first tap of the tile: each output plane's first contribution (kd = 0) overwrites
                 for (int o = o_lo; o <= o_hi; ++o) {

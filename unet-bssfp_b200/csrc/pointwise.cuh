@@ -34,35 +34,48 @@ __device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
 }
 
 // Counter-based dropout mask (replaces torch's Philox stream, which cannot be reproduced bit-exactly;
-// ref: monai ADN "D" = nn.Dropout(p), element-wise). One 32-bit hash decides two consecutive elements.
-__device__ __forceinline__ uint32_t hash32(uint32_t x) {
-  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
-  return x;
+// ref: monai ADN "D" = nn.Dropout(p), element-wise). Eight consecutive elements (one 16-byte vector)
+// share one counter = the vector index; two rounds of 32x32->64-bit multiply-fold (a "mum" hash) give
+// 128 bits = eight 16-bit uniforms, compared against round(p * 65536).
+__device__ __forceinline__ uint32_t mulfold(uint32_t a, uint32_t b) {
+  const unsigned long long m = (unsigned long long)a * b;
+  return (uint32_t)m ^ (uint32_t)(m >> 32);
+}
+__device__ __forceinline__ void dropout_bits8(unsigned long long e0, uint32_t seed, uint32_t (&u)[4]) {
+  const uint32_t idx = (uint32_t)(e0 >> 3);                     // vector index (low 32 bits)
+  const uint32_t salt = seed ^ ((uint32_t)(e0 >> 35) * 0x7FEB352Du);
+  const uint32_t m = mulfold(idx ^ 0x9E3779B9u, 0x85EBCA6Bu ^ (salt << 1 | 1u)) ^ salt;
+  const unsigned long long p0 = (unsigned long long)(m ^ 0xC2B2AE35u) * 0x27D4EB2Fu;
+  const unsigned long long p1 = (unsigned long long)(m ^ 0x165667B1u) * 0x9E3779B1u;
+  const uint32_t q = mulfold(m + 0x632BE5ABu, 0xD2B74407u);
+  u[0] = (uint32_t)p0 ^ q;
+  u[1] = (uint32_t)(p0 >> 32) ^ (q >> 7 | q << 25);
+  u[2] = (uint32_t)p1 ^ (q >> 13 | q << 19);
+  u[3] = (uint32_t)(p1 >> 32) ^ (q >> 21 | q << 11);
 }
 // keep mask for the 8 consecutive elements starting at element index e0 (multiple of 8)
 __device__ __forceinline__ uint32_t dropout_keep8(unsigned long long e0, uint32_t seed, uint32_t thresh16) {
+  uint32_t u[4];
+  dropout_bits8(e0, seed, u);
   uint32_t m = 0;
-  const uint32_t hi = (uint32_t)(e0 >> 33);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const uint32_t pair = (uint32_t)((e0 >> 1) + i);
-    const uint32_t h = hash32(pair * 0x9E3779B1u ^ seed ^ (hi * 0x7FEB352Du));
-    m |= ((h & 0xFFFFu) >= thresh16 ? 1u : 0u) << (2 * i);
-    m |= ((h >> 16) >= thresh16 ? 1u : 0u) << (2 * i + 1);
+    m |= ((u[i] & 0xFFFFu) >= thresh16 ? 1u : 0u) << (2 * i);
+    m |= ((u[i] >> 16) >= thresh16 ? 1u : 0u) << (2 * i + 1);
   }
   return m;
 }
 
+struct NormActArgs;
 // Same mask as dropout_keep8, delivered as per-element factors f[i] = keep ? inv : 0 (no bit packing).
 __device__ __forceinline__ void dropout_factors8(unsigned long long e0, uint32_t seed, uint32_t thresh16, float inv,
                                                  float (&f)[8]) {
-  const uint32_t salt = seed ^ ((uint32_t)(e0 >> 33) * 0x7FEB352Du);
-  const uint32_t pair0 = (uint32_t)(e0 >> 1);
+  uint32_t u[4];
+  dropout_bits8(e0, seed, u);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const uint32_t h = hash32((pair0 + i) * 0x9E3779B1u ^ salt);
-    f[2 * i] = (h & 0xFFFFu) >= thresh16 ? inv : 0.f;
-    f[2 * i + 1] = (h >> 16) >= thresh16 ? inv : 0.f;
+    f[2 * i] = (u[i] & 0xFFFFu) >= thresh16 ? inv : 0.f;
+    f[2 * i + 1] = (u[i] >> 16) >= thresh16 ? inv : 0.f;
   }
 }
 // LeakyReLU for slope <= 1 is max(x, slope * x); the general form keeps the select.

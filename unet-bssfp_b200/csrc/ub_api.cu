@@ -123,13 +123,15 @@ static bool use_march(const ub_conv_desc* d, int dir) {
   return d->c1p == 0 && d->c0p == 32 && d->cop <= 96;
 }
 
-// Depth-tap folding in the generic kernel (igemm_fwd.cuh, kd_fold): 3x3x3 layers whose GEMM N is one
-// tile of 32 or 64 columns and that are not served by the marching kernel.
-static bool use_kd_fold(const ub_conv_desc* d, int dir) {
-  if (d->kind != UB_CONV_K3S1P1 || use_march(d, dir)) return false;
-  if (d->d < 2) return false;
-  if (dir == 0) return d->cop == 32 || d->cop == 64;
-  return d->c1p == 0 && (d->c0p == 32 || d->c0p == 64);
+// Depth-tap folding in the generic kernel (igemm_fwd.cuh, kd_fold): 3x3x3 layers whose GEMM N is a
+// single tile (<= 128 columns) and that are not served by the marching kernel. Returns the fold
+// factor (depth taps per UMMA, N = factor * nt <= 256) or 0.
+static int use_kd_fold(const ub_conv_desc* d, int dir) {
+  if (d->kind != UB_CONV_K3S1P1 || use_march(d, dir)) return 0;
+  const int nt = dir == 0 ? d->cop : d->c0p + d->c1p;
+  if (nt > 128) return 0;
+  const int f = 256 / nt;
+  return f > 3 ? 3 : f;
 }
 
 extern "C" long long ub_packed_weight_elems(const ub_conv_desc* d, int dir) {
@@ -384,9 +386,9 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
   P.out_s = 1;
   make_ntiles(P, d->cop, out, 0, nullptr);
   const int nt_max = d->cop < 128 ? d->cop : 128;
-  P.kd_fold = use_kd_fold(d, 0) ? 1 : 0;
+  P.kd_fold = use_kd_fold(d, 0);
   P.b_block_rows = P.kd_fold ? 3 * d->cop : d->cop;
-  if (int e = make_w_map(&P.tm_w, w_packed, ktot, (long long)ntaps * d->cop, 32, P.kd_fold ? 3 * nt_max : nt_max)) return e;
+  if (int e = make_w_map(&P.tm_w, w_packed, ktot, (long long)ntaps * d->cop, 32, nt_max)) return e;
 
   if (d->kind == UB_CONV_K3S1P1 || d->kind == UB_CONV_K1) {
     const int k = d->kind == UB_CONV_K3S1P1 ? 3 : 1;
@@ -518,9 +520,9 @@ extern "C" int ub_conv_dgrad(const ub_conv_desc* d, const void* dy, const void* 
   for (int i = 0; i < P.n_ntiles; ++i) nt_max = P.ntile[i].nt > nt_max ? P.ntile[i].nt : nt_max;
   // N tiles may have different widths; the weight box uses the widest, narrower tiles read extra rows
   // of the following tap block / pad rows (never used by their MMA: idesc N = nt)
-  P.kd_fold = use_kd_fold(d, 1) ? 1 : 0;
+  P.kd_fold = use_kd_fold(d, 1);
   P.b_block_rows = P.kd_fold ? 3 * ncols : ncols;
-  if (int e = make_w_map(&P.tm_w, w_packed_dgrad, d->cop, (long long)ntaps * ncols, 32, P.kd_fold ? 3 * nt_max : nt_max)) return e;
+  if (int e = make_w_map(&P.tm_w, w_packed_dgrad, d->cop, (long long)ntaps * ncols, 32, nt_max)) return e;
   bool uniform = true;
   for (int i = 0; i < P.n_ntiles; ++i) uniform = uniform && P.ntile[i].nt == nt_max;
   if (!uniform) return fail(-2, "dgrad N tiles of unequal width are not supported (c0p=%d c1p=%d)", d->c0p, d->c1p);
