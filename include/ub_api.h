@@ -61,6 +61,26 @@ int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* src1, const
 /* d src = conv_transpose(dy); dsrc1 may be NULL when the op has one source */
 int ub_conv_dgrad(const ub_conv_desc* d, const void* dy, const void* w_packed_dgrad, void* dsrc0,
                   void* dsrc1, void* stream);
+/* Optional epilogue fusion of ub_conv_dgrad_fused: dsrc0 is the gradient dA of the activations of a
+ * conv -> norm -> dropout -> LeakyReLU block (the "producer"); while writing it the epilogue also
+ * accumulates that block's norm-backward reductions S1 = sum dz, S2 = sum dz * xhat per (n, c), with
+ * dz = dA * lrelu'(y * scale + shift) * dropout_mask / (1 - p), into per-CTA records
+ * partial[ub_conv_dgrad_fuse_records(desc)][2][32]. Pass them to ub_norm_act_bwd (ext_partial) and its
+ * reduction pass over dA and y is skipped. Available where ub_conv_dgrad_fuse_records() > 0 (3x3x3
+ * convs with one 32-channel source, i.e. the full-resolution layers). */
+typedef struct {
+  const void* y;           /* producer's raw conv output, NDHWC bf16, 32 channels */
+  const float* scale;      /* [n][32] gamma * rstd          (ub_norm_finalize) */
+  const float* shift;      /* [n][32] */
+  const float* mean;       /* [n][32] */
+  const float* rstd;       /* [n][32] */
+  float slope, drop_p;
+  uint32_t drop_seed;
+  float* partial;          /* out: [records][2][32] */
+} ub_norm_bwd_fuse;
+int ub_conv_dgrad_fuse_records(const ub_conv_desc* d);   /* records (n-major, records / n per sample); 0 = unsupported */
+int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const void* w_packed_dgrad, void* dsrc0,
+                        void* dsrc1, const ub_norm_bwd_fuse* fuse, void* stream);
 /* dw (fp32, torch layout) = sum_voxels src (x) dy; workspace holds the split-K partials */
 long long ub_conv_wgrad_workspace_bytes(const ub_conv_desc* d);
 int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void* src1, const void* dy,
@@ -102,7 +122,9 @@ int ub_norm_act_bwd(const void* dA, const void* a, const void* y, int mode, cons
                     const float* rstd, const float* scale, const float* shift, float slope, float drop_p,
                     uint32_t drop_seed,
                     int n, long long voxels, int cp, int c, void* workspace, void* dy, float* dgamma,
-                    float* dbeta, float* dbias, void* stream);
+                    float* dbeta, float* dbias, const float* ext_partial, int ext_records_per_sample, void* stream);
+/* ext_partial != NULL: per-sample partial records [n * ext_records_per_sample][2][cp] produced by
+ * ub_conv_dgrad_fused replace the reduction pass. */
 /* MaxPool3d(2) backward; accumulate != 0 adds onto the gradient already in dA (skip path) */
 int ub_maxpool_bwd(const void* a, const void* dP, void* dA, int accumulate, int n, int d, int h, int w,
                    int cp, void* stream);

@@ -144,3 +144,46 @@ def test_conv_wgrad(kind, c0, c1, co, shape):
     assert dw.shape == ref_dw.shape
     assert rel_to_max(dw, ref_dw) < 2e-3      # fp32 accumulate of exact bf16 products
     assert rel_l2(dw, ref_dw) < 1e-3
+
+
+@pytest.mark.parametrize("mode,drop_p", [("instance", 0.05), ("instance", 0.0), ("batch_train", 0.0)])
+@pytest.mark.parametrize("co,shape", [(32, (2, 9, 24, 16)), (64, (1, 6, 16, 8))])
+def test_dgrad_fused_norm_backward_reduction(mode, drop_p, co, shape):
+    """ub_conv_dgrad_fused: the marching dgrad epilogue accumulates the producer block's norm-backward
+    sums. The gradient it writes is bit-identical to the unfused call, and ub_norm_act_bwd fed with the
+    partial records agrees with its own reduction pass (different summation order only)."""
+    strict_fp32()
+    ops = _ops()
+    from unet_bssfp_b200 import _lib
+    n, d, h, w = shape
+    g = torch.Generator(device="cuda").manual_seed(5)
+    spec = ops.ConvSpec(0, 32, co)
+    wt = bf16_round(torch.randn((co, 32, 3, 3, 3), device="cuda", generator=g) / 30.0)
+    wpk = ops.pack_conv_weights(spec, wt, 1)
+    dy = to_internal(bf16_round(torch.randn((n, co, d, h, w), device="cuda", generator=g)))
+    # the producer block: raw output y (24 real channels: padded channels must stay inert), its statistics
+    c = 24
+    y = to_internal(bf16_round(torch.randn((n, c, d, h, w), device="cuda", generator=g) * 1.3 + 0.2))
+    gamma = torch.rand((c,), device="cuda", generator=g) + 0.5
+    beta = torch.randn((c,), device="cuda", generator=g) * 0.2
+    kspec = ops.ConvSpec(_lib.UB_CONV_K1, c, c)
+    eye = torch.eye(c, device="cuda").view(c, c, 1, 1, 1)
+    yi, stats = ops.conv_fwd(kspec, y, None, ops.pack_conv_weights(kspec, eye, 0), None, want_stats=True)
+    imode = {"instance": _lib.UB_NORM_INSTANCE, "batch_train": _lib.UB_NORM_BATCH_TRAIN}[mode]
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    scale, shift, mean, rstd = ops.norm_finalize(stats, n, d * h * w, 32, c, gamma, beta, 1e-5, imode, 0.1, rm, rv)
+    seed = 4242
+    fuse = ops.NormBwdFusion(yi, scale, shift, mean, rstd, 0.1, drop_p, seed)
+    assert ops.dgrad_fuse_records(spec, n, d, h, w) > 0
+    d0, _ = ops.conv_dgrad(spec, dy, wpk, (d, h, w))
+    f0, _, partial = ops.conv_dgrad(spec, dy, wpk, (d, h, w), fuse=fuse)
+    torch.cuda.synchronize()
+    assert torch.equal(d0, f0)
+    ref = ops.norm_act_bwd(d0, None, yi, imode, mean, rstd, scale, 0.1, drop_p, seed, c, shift=shift)
+    got = ops.norm_act_bwd(d0, None, yi, imode, mean, rstd, scale, 0.1, drop_p, seed, c, shift=shift, partial=partial)
+    torch.cuda.synchronize()
+    assert rel_l2(got[1], ref[1]) < 1e-4 and rel_l2(got[2], ref[2]) < 1e-4          # dgamma, dbeta
+    assert rel_to_max(got[0].float(), ref[0].float()) < 1e-2                          # dy (bf16 roundings of near-ties)
+    assert rel_l2(got[0].float(), ref[0].float()) < 1e-3
+    # a conv whose source has 64 channels has no fused path
+    assert ops.dgrad_fuse_records(ops.ConvSpec(0, 64, 64), n, d, h, w) == 0

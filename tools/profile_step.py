@@ -62,10 +62,11 @@ def l_conv_fwd(out, spec, src0, src1, *a, **k):
     return conv_label(spec, d, n), conv_flops(spec, n, d, h, w), _nbytes(src0, src1, out[0])
 
 
-def l_conv_dgrad(out, spec, dy, wp, in_dhw):
+def l_conv_dgrad(out, spec, dy, wp, in_dhw, fuse=None):
     n = dy.shape[0]
     d, h, w = in_dhw
-    return conv_label(spec, d, n), conv_flops(spec, n, d, h, w), _nbytes(dy, out[0], out[1])
+    tag = " +nbwd" if fuse is not None else ""
+    return conv_label(spec, d, n) + tag, conv_flops(spec, n, d, h, w), _nbytes(dy, out[0], out[1])
 
 
 def l_conv_wgrad(out, spec, src0, src1, dy, shape):

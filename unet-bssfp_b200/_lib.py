@@ -15,6 +15,13 @@ UB_CONV_K3S1P1, UB_CONV_K1, UB_CONV_K4S2P1, UB_DECONV_K2S2, UB_CONV_K4S2P1_S2D =
 UB_NORM_INSTANCE, UB_NORM_BATCH_TRAIN, UB_NORM_BATCH_EVAL, UB_NORM_NONE = 0, 1, 2, 3
 
 
+class NormBwdFuse(C.Structure):
+    """Mirror of ``ub_norm_bwd_fuse`` (include/ub_api.h)."""
+    _fields_ = [("y", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p),
+                ("rstd", C.c_void_p), ("slope", C.c_float), ("drop_p", C.c_float), ("drop_seed", C.c_uint32),
+                ("partial", C.c_void_p)]
+
+
 class ConvDesc(C.Structure):
     """Mirror of ``ub_conv_desc`` (include/ub_api.h)."""
     _fields_ = [(k, C.c_int) for k in ("kind", "n", "d", "h", "w", "c0", "c0p", "c1", "c1p", "co", "cop")]
@@ -38,6 +45,8 @@ SIGNATURES = {
     "ub_conv_num_tiles": (_I, [_DP]),
     "ub_conv_fwd": (_I, [_DP, _P, _P, _P, _P, _I, _F, _P, _P, _P]),
     "ub_conv_dgrad": (_I, [_DP, _P, _P, _P, _P, _P]),
+    "ub_conv_dgrad_fuse_records": (_I, [_DP]),
+    "ub_conv_dgrad_fused": (_I, [_DP, _P, _P, _P, _P, C.POINTER(NormBwdFuse), _P]),
     "ub_conv_wgrad_workspace_bytes": (_LL, [_DP]),
     "ub_conv_wgrad": (_I, [_DP, _P, _P, _P, _P, _P, _P]),
     "ub_pack_ncdhw": (_I, [_P, _I, _P, _I, _I, _LL, _I, _P, _P]),
@@ -46,7 +55,8 @@ SIGNATURES = {
     "ub_norm_finalize": (_I, [_P, _I, _I, _I, _I, _D, _P, _P, _F, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "ub_norm_act_fwd": (_I, [_P, _P, _P, _F, _F, _U32, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ub_norm_act_bwd_workspace_bytes": (_LL, [_I, _I]),
-    "ub_norm_act_bwd": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _F, _F, _U32, _I, _LL, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "ub_norm_act_bwd": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _F, _F, _U32, _I, _LL, _I, _I, _P, _P, _P, _P, _P, _P, _I,
+                             _P]),
     "ub_maxpool_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ub_colsum_workspace_bytes": (_LL, [_I]),
     "ub_colsum": (_I, [_P, _LL, _I, _I, _P, _P, _P]),

@@ -18,6 +18,7 @@
 // stays resident in shared memory for the CTA's lifetime.
 #pragma once
 #include "igemm_fwd.cuh"
+#include "pointwise.cuh"
 
 namespace ub {
 
@@ -32,6 +33,17 @@ struct MarchParams {
   int bias_n;
   float* stats;                     // [item][2][32] or nullptr
   int nsa;                          // A (plane, chunk) stages
+  // kNormBwd instantiation (dgrad of the conv that consumes a norm block's activations): the tensor
+  // written here is dA of that block; the epilogue also accumulates its norm-backward reductions
+  //   S1[n,c] = sum dz,  S2[n,c] = sum dz * xhat,  dz = dA * lrelu'(y*scale+shift) * dropout,
+  // into `stats` (same per-CTA record format), so the separate reduction pass over dA and y is not run.
+  const void* nb_y;                 // raw conv output of the producer block [N][D][H][W][32] bf16
+  const float* nb_scale;            // [N][32] gamma * rstd
+  const float* nb_shift;            // [N][32]
+  const float* nb_mean;             // [N][32]
+  const float* nb_rstd;             // [N][32]
+  float nb_slope, nb_drop_p;
+  uint32_t nb_drop_seed, nb_drop_thresh;
 };
 
 constexpr int kMarchPlaneBytes = 12288;   // 180 rows x 64 B, padded to a multiple of 1024
@@ -41,6 +53,7 @@ constexpr int kMarchRing = 5;       // TMEM accumulator ring: 5 x 96 columns
 constexpr int kMarchEpiWarps = 8;
 constexpr int kMarchThreads = (kMarchEpiWarps + 2) * 32;   // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
 
+template <bool kNormBwd>
 __global__ void __launch_bounds__(kMarchThreads, 1)
 igemm_march_kernel(const __grid_constant__ MarchParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -56,7 +69,7 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
   const uint32_t w_full = bar_base, a_full = w_full + 8, a_empty = a_full + 8 * P.nsa,
                  acc_full = a_empty + 8 * P.nsa, acc_empty = acc_full + 8 * kMarchRing;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (acc_empty + 8 * kMarchRing - base));
-  float* red = reinterpret_cast<float*>(sm + (((acc_empty + 8 * kMarchRing + 16 + 15) & ~15u) - base));  // [8][2][32] + bias[32], 16-B aligned
+  float* red = reinterpret_cast<float*>(sm + (((acc_empty + 8 * kMarchRing + 16 + 15) & ~15u) - base));  // [8][2][32] + bias[32] + consts[4][32], 16-B aligned
 
   // ---- work item: (n, h tile, w tile, d segment)
   int t = blockIdx.x;
@@ -161,18 +174,45 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
     const bool valid_e = odd ? valid_pair : valid_hw, valid_o = odd ? valid_hw : valid_pair;
     const bool do_stats = P.stats != nullptr;
     float* bias_s = red + kMarchEpiWarps * 2 * 32;
+    float* nbc = bias_s + 32;   // [scale | shift | rstd | -mean*rstd][32] of this CTA's sample
     if (threadIdx.x < 32)
       bias_s[threadIdx.x] = (P.bias != nullptr && threadIdx.x < P.bias_n) ? __ldg(P.bias + threadIdx.x) : 0.f;
+    if (kNormBwd && threadIdx.x >= 32 && threadIdx.x < 64) {
+      const int c = threadIdx.x - 32;
+      const float rs = P.nb_rstd[nb * 32 + c];
+      nbc[c] = P.nb_scale[nb * 32 + c];
+      nbc[32 + c] = P.nb_shift[nb * 32 + c];
+      nbc[64 + c] = rs;
+      nbc[96 + c] = -P.nb_mean[nb * 32 + c] * rs;
+    }
     named_bar_sync(1, kMarchEpiWarps * 32);
+    const bool has_drop = kNormBwd && P.nb_drop_p > 0.f;
+    const float nb_inv = has_drop ? 1.f / (1.f - P.nb_drop_p) : 1.f;
     float st_a[32], st_b[32];   // per-thread channel sums over this warp's planes; transposed once at the end
 #pragma unroll
     for (int j = 0; j < 32; ++j) { st_a[j] = 0.f; st_b[j] = 0.f; }
     __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(P.out);
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    // kNormBwd: the producer's raw output row of the NEXT plane of this warp group is prefetched into L2
+    // while the current one is processed (the HBM latency would otherwise sit in the middle of every
+    // plane); no registers are held across iterations for it
+    const size_t plane_vox = (size_t)P.H * P.W;
     for (int d = d_begin + grp; d < d_end; d += 2) {
       // newest plane this output needs
       const int pnew = d + 1 <= p_last ? d + 1 : p_last;
       const int pi = pnew - p_first;
+      const size_t vox_own = (((size_t)nb * P.D + d) * P.H + h) * P.W + w;
+      uint4 yv[4];
+      if (kNormBwd && valid_hw) {
+        const uint4* yp = reinterpret_cast<const uint4*>(P.nb_y) + vox_own * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) yv[j] = __ldg(yp + j);
+        if (d + 2 < d_end) {
+          const uint4* yn = yp + 2 * plane_vox * 4;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(yn));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(yn + 2));
+        }
+      }
       mbar_wait(acc_full + 8 * (pi % kMarchRing), (uint32_t)(pi / kMarchRing) & 1u);
       tc_fence_after();
       float v[32];
@@ -230,7 +270,7 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
           d_o[2] = odd ? make_uint4(pk[12], pk[13], pk[14], pk[15]) : make_uint4(rx[4], rx[5], rx[6], rx[7]);
         }
       }
-      if (do_stats && valid_hw) {
+      if (!kNormBwd && do_stats && valid_hw) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float lo = __uint_as_float(pk[j] << 16);
@@ -239,8 +279,47 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
           st_b[2 * j] = fmaf(lo, lo, st_b[2 * j]); st_b[2 * j + 1] = fmaf(hi, hi, st_b[2 * j + 1]);
         }
       }
+      if (kNormBwd && valid_hw) {
+        // dz from the ROUNDED gradient (what the apply pass will read back) and the forward's own fma.
+        // st_a accumulates sum dz, st_b accumulates sum dz * y; xhat = y * rstd - mean * rstd is applied
+        // once per thread after the loop.
+        const uint32_t* yw = reinterpret_cast<const uint32_t*>(yv);
+        const float4* sc4 = reinterpret_cast<const float4*>(nbc);
+        const float4* sh4 = reinterpret_cast<const float4*>(nbc + 32);
+#pragma unroll
+        for (int o8 = 0; o8 < 4; ++o8) {
+          float f[8];
+          if (has_drop) {
+            dropout_factors8((unsigned long long)vox_own * 32ull + o8 * 8, P.nb_drop_seed, P.nb_drop_thresh, nb_inv, f);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = 1.f;
+          }
+#pragma unroll
+          for (int k4 = 0; k4 < 2; ++k4) {
+            const float4 sc = sc4[o8 * 2 + k4], sh = sh4[o8 * 2 + k4];
+            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int c = o8 * 8 + k4 * 4 + k;
+              const uint32_t dw = pk[c >> 1], yy = yw[c >> 1];
+              const float da = __uint_as_float((c & 1) ? (dw & 0xFFFF0000u) : (dw << 16));
+              const float yf = __uint_as_float((c & 1) ? (yy & 0xFFFF0000u) : (yy << 16));
+              const float fk = f[k4 * 4 + k];
+              const float dz = da * (fmaf(yf, scv[k], shv[k]) > 0.f ? fk : fk * P.nb_slope);
+              st_a[c] += dz;
+              st_b[c] = fmaf(dz, yf, st_b[c]);
+            }
+          }
+        }
+      }
     }
-    if (do_stats) {
+    if (kNormBwd) {
+      // S2 = sum dz * xhat = rstd * sum dz*y - mean*rstd * sum dz
+#pragma unroll
+      for (int c = 0; c < 32; ++c) st_b[c] = fmaf(nbc[64 + c], st_b[c], nbc[96 + c] * st_a[c]);
+    }
+    if (do_stats || kNormBwd) {
       const float s_acc = warp_transpose_reduce32(st_a, lane);
       const float q_acc = warp_transpose_reduce32(st_b, lane);
       red[(warp * 2 + 0) * 32 + lane] = s_acc;

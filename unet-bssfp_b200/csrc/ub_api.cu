@@ -298,18 +298,29 @@ static void march_geometry(int n, int D, int H, int W, int* tiles_w, int* tiles_
   *nseg = cdiv(D, *seg_len);
 }
 
+static uint32_t drop_thresh(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
+
 static int launch_march(const void* src0, int c0p, const void* src1, int c1p, int n, int D, int H, int W,
                         const void* w_packed, const float* bias, int bias_n, void* out, float* stats,
-                        cudaStream_t st) {
+                        const ub_norm_bwd_fuse* fuse, cudaStream_t st) {
   MarchParams P;
   memset(&P, 0, sizeof(P));
+  if (fuse) {
+    if (!fuse->y || !fuse->scale || !fuse->shift || !fuse->mean || !fuse->rstd || !fuse->partial)
+      return fail(-1, "incomplete ub_norm_bwd_fuse");
+    if (fuse->drop_p < 0.f || fuse->drop_p >= 1.f) return fail(-1, "dropout p out of range");
+    P.nb_y = fuse->y; P.nb_scale = fuse->scale; P.nb_shift = fuse->shift; P.nb_mean = fuse->mean; P.nb_rstd = fuse->rstd;
+    P.nb_slope = fuse->slope; P.nb_drop_p = fuse->drop_p; P.nb_drop_seed = fuse->drop_seed;
+    P.nb_drop_thresh = drop_thresh(fuse->drop_p);
+    stats = fuse->partial;
+  }
   P.n_chunks_src0 = c0p / 32;
   P.n_chunks_total = (c0p + c1p) / 32;
   P.Nb = n; P.D = D; P.H = H; P.W = W;
   march_geometry(n, D, H, W, &P.tiles_w, &P.tiles_h, &P.nseg, &P.seg_len);
   P.out = out; P.bias = bias; P.bias_n = bias_n; P.stats = stats;
   const int wbytes = P.n_chunks_total * 9 * kMarchWTileBytes;
-  const int misc = 8 * 32 + 64 + (kMarchEpiWarps * 2 * 32 + 32) * 4 + 64 + 1024;
+  const int misc = 8 * 32 + 64 + (kMarchEpiWarps * 2 * 32 + 32 + 128) * 4 + 64 + 1024;
   P.nsa = (220 * 1024 - wbytes - misc) / kMarchPlaneBytes;
   if (P.nsa > 8) P.nsa = 8;
   if (P.nsa < 2) return fail(-2, "march smem plan: no room for the plane ring");
@@ -321,11 +332,14 @@ static int launch_march(const void* src0, int c0p, const void* src1, int c1p, in
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(igemm_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(igemm_march_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(igemm_march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) return fail(-3, "cudaFuncSetAttribute(igemm_march): %s", cudaGetErrorString(attr_err));
   const unsigned grid = (unsigned)(n * P.tiles_h * P.tiles_w * P.nseg);
-  igemm_march_kernel<<<grid, kMarchThreads, smem, st>>>(P);
+  if (fuse) igemm_march_kernel<true><<<grid, kMarchThreads, smem, st>>>(P);
+  else igemm_march_kernel<false><<<grid, kMarchThreads, smem, st>>>(P);
   UB_LAUNCH_CHECK();
   return 0;
 }
@@ -366,7 +380,7 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
   if (use_march(d, 0)) {
     if (act) return fail(-2, "fused activation is not available on the marching conv path");
     return launch_march(src0, d->c0p, src1, d->c1p, d->n, d->d, d->h, d->w, w_packed, bias, d->co, out,
-                        stats_partial, st);
+                        stats_partial, nullptr, st);
   }
 
   IgemmPlan pl;
@@ -491,9 +505,23 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
   return launch_igemm(pl, st);
 }
 
+extern "C" int ub_conv_dgrad_fuse_records(const ub_conv_desc* d) {
+  if (check_desc(d)) return -1;
+  if (!use_march(d, 1)) return 0;
+  int tw, th, ns, sl;
+  march_geometry(d->n, d->d, d->h, d->w, &tw, &th, &ns, &sl);
+  return d->n * th * tw * ns;
+}
+
 extern "C" int ub_conv_dgrad(const ub_conv_desc* d, const void* dy, const void* w_packed_dgrad, void* dsrc0,
                              void* dsrc1, void* stream) {
+  return ub_conv_dgrad_fused(d, dy, w_packed_dgrad, dsrc0, dsrc1, nullptr, stream);
+}
+
+extern "C" int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const void* w_packed_dgrad, void* dsrc0,
+                                   void* dsrc1, const ub_norm_bwd_fuse* fuse, void* stream) {
   if (int e = check_desc(d)) return e;
+  if (fuse && !use_march(d, 1)) return fail(-2, "fused norm-backward reduction is available on the marching dgrad path only");
   if (int e = ensure_encode()) return e;
   if (!dy || !w_packed_dgrad || !dsrc0) return fail(-1, "null pointer in ub_conv_dgrad");
   if (d->c1p && !dsrc1) return fail(-1, "second gradient destination missing");
@@ -503,7 +531,7 @@ extern "C" int ub_conv_dgrad(const ub_conv_desc* d, const void* dy, const void* 
   const int ntaps = ntaps_of(d->kind);
   const int ncols = d->c0p + d->c1p;
   if (use_march(d, 1))
-    return launch_march(dy, d->cop, nullptr, 0, d->n, d->d, d->h, d->w, w_packed_dgrad, nullptr, 0, dsrc0, nullptr, st);
+    return launch_march(dy, d->cop, nullptr, 0, d->n, d->d, d->h, d->w, w_packed_dgrad, nullptr, 0, dsrc0, nullptr, fuse, st);
 
   IgemmPlan pl;
   memset(&pl, 0, sizeof(pl));
@@ -859,8 +887,6 @@ extern "C" int ub_norm_finalize(const float* stats_partial, int tiles_per_sample
   return 0;
 }
 
-static uint32_t drop_thresh(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
-
 extern "C" int ub_norm_act_fwd(const void* y, const float* scale, const float* shift, float slope, float drop_p,
                                uint32_t drop_seed, int n, int d, int h, int w, int cp, void* a, void* pooled,
                                void* stream) {
@@ -904,7 +930,8 @@ extern "C" int ub_norm_act_bwd(const void* dA, const void* a, const void* y, int
                                const float* rstd, const float* scale, const float* shift, float slope, float drop_p,
                                uint32_t drop_seed,
                                int n, long long voxels, int cp, int c, void* workspace, void* dy, float* dgamma,
-                               float* dbeta, float* dbias, void* stream) {
+                               float* dbeta, float* dbias, const float* ext_partial, int ext_records_per_sample,
+                               void* stream) {
   if (!dA || !dy || cp % 8 || n <= 0 || n > 65535) return fail(-1, "bad arguments to ub_norm_act_bwd");
   if (!a && (mode == UB_NORM_NONE || !shift)) return fail(-1, "ub_norm_act_bwd needs the activations `a` or (y, scale, shift)");
   const int c8 = cp / 8;
@@ -928,11 +955,19 @@ extern "C" int ub_norm_act_bwd(const void* dA, const void* a, const void* y, int
     long long bps = bps_max;
     if (bps * threads * 4 > vps) bps = (vps + 4ll * threads - 1) / (4ll * threads);
     if (bps < 1) bps = 1;
-    norm_act_bwd_reduce_kernel<<<dim3((unsigned)bps, n), threads, 2 * threads * 8 * sizeof(float), st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(dA), reinterpret_cast<const __nv_bfloat16*>(a),
-        reinterpret_cast<const __nv_bfloat16*>(y), B, cp, (uint32_t)vps, part);
-    UB_LAUNCH_CHECK();
-    norm_bwd_finalize_kernel<<<cp / 32, dim3(32, 32), 0, st>>>(part, (int)bps, n, cp, c, (double)voxels, mode, scale, c1, c2,
+    const float* part_in = part;
+    if (ext_partial) {
+      // the reductions were accumulated by the producer of dA (ub_conv_dgrad_fused)
+      if (ext_records_per_sample <= 0) return fail(-1, "ext_records_per_sample must be positive");
+      part_in = ext_partial;
+      bps = ext_records_per_sample;
+    } else {
+      norm_act_bwd_reduce_kernel<<<dim3((unsigned)bps, n), threads, 2 * threads * 8 * sizeof(float), st>>>(
+          reinterpret_cast<const __nv_bfloat16*>(dA), reinterpret_cast<const __nv_bfloat16*>(a),
+          reinterpret_cast<const __nv_bfloat16*>(y), B, cp, (uint32_t)vps, part);
+      UB_LAUNCH_CHECK();
+    }
+    norm_bwd_finalize_kernel<<<cp / 32, dim3(32, 32), 0, st>>>(part_in, (int)bps, n, cp, c, (double)voxels, mode, scale, c1, c2,
                                                            dgamma, dbeta, dbias);
     UB_LAUNCH_CHECK();
   }

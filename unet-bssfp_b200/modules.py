@@ -110,14 +110,26 @@ def _block_forward(blk: _Block, cache: _PackedWeights, src0, src1, training, see
     return a, pooled, sv
 
 
-def _block_backward(blk: _Block, cache: _PackedWeights, sv: _Saved, dA, need_w, need_in, grads):
-    """Accumulates parameter grads into ``grads`` (dict id(param) -> tensor); returns (d_src0, d_src1)."""
+def _fusion_of(blk: _Block, sv: _Saved):
+    """Norm-backward fusion descriptor of a block whose dA a downstream dgrad is about to produce."""
+    if blk.norm is None or sv is None or sv.y is None or sv.y.shape[-1] != 32:
+        return None
+    return ops.NormBwdFusion(sv.y, sv.scale, sv.shift, sv.mean, sv.rstd, blk.slope, sv.drop_p, sv.seed)
+
+
+def _block_backward(blk: _Block, cache: _PackedWeights, sv: _Saved, dA, need_w, need_in, grads, partial=None,
+                    producer=None):
+    """Accumulates parameter grads into ``grads`` (dict id(param) -> tensor); returns
+    (d_src0, d_src1, partial_of_producer). ``partial``: this block's norm-backward reductions if the
+    dgrad that produced ``dA`` already accumulated them. ``producer`` = (block, saved) of the block
+    whose activations are this conv's src0: when the dgrad runs on the marching kernel its epilogue
+    accumulates the producer's reductions."""
     spec = blk.spec
     co = spec.co
     if blk.norm is not None:
         dy, dgamma, dbeta, dbias = ops.norm_act_bwd(dA, None, sv.y, sv.mode, sv.mean, sv.rstd, sv.scale, blk.slope,
                                                     sv.drop_p, sv.seed, co, want_param_grads=need_w,
-                                                    want_bias_grad=need_w, shift=sv.shift)
+                                                    want_bias_grad=need_w, shift=sv.shift, partial=partial)
         if need_w:
             grads[id(blk.norm.weight)] = dgamma
             grads[id(blk.norm.bias)] = dbeta
@@ -132,8 +144,13 @@ def _block_backward(blk: _Block, cache: _PackedWeights, sv: _Saved, dA, need_w, 
     if need_w:
         grads[id(blk.conv.weight)] = ops.conv_wgrad(spec, sv.src0, sv.src1, dy, tuple(blk.conv.weight.shape))
     if need_in:
-        return ops.conv_dgrad(spec, dy, cache.get(spec, blk.conv.weight, 1), sv.in_dhw)
-    return None, None
+        wd = cache.get(spec, blk.conv.weight, 1)
+        fuse = _fusion_of(*producer) if producer is not None else None
+        if fuse is not None and ops.dgrad_fuse_records(spec, dy.shape[0], *sv.in_dhw) > 0:
+            return ops.conv_dgrad(spec, dy, wd, sv.in_dhw, fuse=fuse)
+        d0, d1 = ops.conv_dgrad(spec, dy, wd, sv.in_dhw)
+        return d0, d1, None
+    return None, None, None
 
 
 class _InputPackCache:
@@ -324,7 +341,7 @@ class _ChainFunction(torch.autograd.Function):
             blk = chain.blocks[i]
             need_w = any(pneed[id(p)] for p in blk.params())
             need_in = i > 0 or need_x or need_y
-            d0, _ = _block_backward(blk, chain.cache, saved[i], dA, need_w, need_in, grads)
+            d0, _, _ = _block_backward(blk, chain.cache, saved[i], dA, need_w, need_in, grads)
             saved[i] = None
             dA = d0
         dx = ops.unpack_ncdhw(d0, ctx.cx, 0).to(ctx.in_dtype) if need_x else None
@@ -442,35 +459,39 @@ class _GeneratorFunction(torch.autograd.Function):
         need_x = ctx.needs_input_grad[0]
         grads = {}
 
-        def bwd(blk, dA, need_in=True):
+        def bwd(blk, dA, need_in=True, partial=None, producer=None):
+            """-> (d_src0, d_src1, partial of ``producer``)."""
             need_w = any(pneed[id(p)] for p in blk.params())
-            r = _block_backward(blk, cache, S[blk.name], dA, need_w, need_in, grads)
+            prod = (producer, S[producer.name]) if producer is not None else None
+            r = _block_backward(blk, cache, S[blk.name], dA, need_w, need_in, grads, partial=partial, producer=prod)
             S[blk.name] = None
             return r
 
         dA = ops.pack_ncdhw(dout.contiguous().float())
-        du, _ = bwd(net.final, dA)
+        du, _, _ = bwd(net.final, dA)
         nlev = len(net.enc)
         dskip = [None] * nlev
         for j in range(len(net.dec) - 1, -1, -1):      # upcat_1 first
             dc, c0, c1 = net.dec[j]
-            dt, _ = bwd(c1, du)
-            d_xe, d_up = bwd(c0, dt)
+            dt, _, part = bwd(c1, du, producer=c0)      # dt = dA of c0 (same resolution, chained)
+            d_xe, d_up, _ = bwd(c0, dt, partial=part)
             dskip[nlev - 2 - j] = d_xe
-            du, _ = bwd(dc, d_up)
+            du, _, _ = bwd(dc, d_up)
         dcur = du                                        # grad of x4 (bottom)
+        part_head = None
         for lvl in range(nlev - 1, -1, -1):
             c0, c1 = net.enc[lvl]
             if lvl != nlev - 1:
                 # dcur is the grad of the pooled tensor; route it onto the skip grad of x_lvl
                 xk = S[c1.name].a
                 dcur = ops.maxpool_bwd(xk, dcur, dskip[lvl])
-            dt, _ = bwd(c1, dcur)
+            dt, _, part = bwd(c1, dcur, producer=c0)
             first = lvl == 0
-            dcur, _ = bwd(c0, dt, need_in=(not first) or net.head is not None or need_x)
+            dcur, _, part_head = bwd(c0, dt, need_in=(not first) or net.head is not None or need_x, partial=part,
+                                     producer=net.head if (first and net.head is not None) else None)
         dx = None
         if net.head is not None:
-            dcur, _ = bwd(net.head, dcur, need_in=need_x)
+            dcur, _, _ = bwd(net.head, dcur, need_in=need_x, partial=part_head)
         if need_x:
             dx = ops.unpack_ncdhw(dcur, ctx.cx).to(ctx.in_dtype)
         ctx.S = None

@@ -113,8 +113,32 @@ def conv_fwd(spec: ConvSpec, src0, src1, w_packed, bias, act=0, slope=0.0, want_
     return out, stats
 
 
-def conv_dgrad(spec: ConvSpec, dy, w_packed_dgrad, in_dhw):
-    """dy (N,Do,Ho,Wo,cop) -> (dsrc0, dsrc1|None), each (N,d,h,w,c*p) bf16."""
+@dataclass
+class NormBwdFusion:
+    """Saved tensors of the block that PRODUCED a conv's input: lets that conv's dgrad epilogue
+    accumulate the block's norm-backward reductions (``ub_norm_bwd_fuse``)."""
+    y: torch.Tensor
+    scale: torch.Tensor
+    shift: torch.Tensor
+    mean: torch.Tensor
+    rstd: torch.Tensor
+    slope: float
+    drop_p: float
+    drop_seed: int
+
+
+def dgrad_fuse_records(spec: ConvSpec, n, d, h, w) -> int:
+    """Number of partial records ``conv_dgrad(..., fuse=)`` would emit; 0 when the fusion is unavailable."""
+    desc = spec.desc(n, d, h, w)
+    r = _lib.load().ub_conv_dgrad_fuse_records(C.byref(desc))
+    if r < 0:
+        _lib.check(-1, "ub_conv_dgrad_fuse_records")
+    return r
+
+
+def conv_dgrad(spec: ConvSpec, dy, w_packed_dgrad, in_dhw, fuse: NormBwdFusion | None = None):
+    """dy (N,Do,Ho,Wo,cop) -> (dsrc0, dsrc1|None), each (N,d,h,w,c*p) bf16.
+    With ``fuse`` -> (dsrc0, dsrc1, partial [records][2][32] fp32): norm-backward sums of the producer block."""
     _require_cuda(dy, w_packed_dgrad)
     lib = _lib.load()
     n = dy.shape[0]
@@ -122,8 +146,18 @@ def conv_dgrad(spec: ConvSpec, dy, w_packed_dgrad, in_dhw):
     desc = spec.desc(n, d, h, w)
     d0 = torch.empty((n, d, h, w, spec.c0p), dtype=torch.bfloat16, device=dy.device)
     d1 = torch.empty((n, d, h, w, spec.c1p), dtype=torch.bfloat16, device=dy.device) if spec.c1 else None
-    _lib.check(lib.ub_conv_dgrad(C.byref(desc), _p(dy), _p(w_packed_dgrad), _p(d0), _p(d1), _stream()), "ub_conv_dgrad")
-    return d0, d1
+    if fuse is None:
+        _lib.check(lib.ub_conv_dgrad(C.byref(desc), _p(dy), _p(w_packed_dgrad), _p(d0), _p(d1), _stream()), "ub_conv_dgrad")
+        return d0, d1
+    records = lib.ub_conv_dgrad_fuse_records(C.byref(desc))
+    if records <= 0:
+        raise RuntimeError("conv_dgrad: the norm-backward fusion is not available for this convolution")
+    partial = torch.empty((records, 2, 32), dtype=torch.float32, device=dy.device)
+    f = _lib.NormBwdFuse(fuse.y.data_ptr(), fuse.scale.data_ptr(), fuse.shift.data_ptr(), fuse.mean.data_ptr(),
+                         fuse.rstd.data_ptr(), fuse.slope, fuse.drop_p, fuse.drop_seed & 0xFFFFFFFF, partial.data_ptr())
+    _lib.check(lib.ub_conv_dgrad_fused(C.byref(desc), _p(dy), _p(w_packed_dgrad), _p(d0), _p(d1), C.byref(f), _stream()),
+               "ub_conv_dgrad_fused")
+    return d0, d1, partial
 
 
 def conv_wgrad(spec: ConvSpec, src0, src1, dy, weight_shape):
@@ -206,9 +240,10 @@ def norm_act_fwd(y, scale, shift, slope, drop_p=0.0, drop_seed=0, pool=False):
 
 
 def norm_act_bwd(dA, a, y, mode, mean, rstd, scale, slope, drop_p, drop_seed, c, want_param_grads=True,
-                 want_bias_grad=True, shift=None):
+                 want_bias_grad=True, shift=None, partial=None):
     """-> (dy, dgamma|None, dbeta|None, dbias|None). With ``shift`` (norm modes) the activation sign is
-    recomputed from ``y`` and ``a`` is not read (may be None)."""
+    recomputed from ``y`` and ``a`` is not read (may be None). ``partial``: reduction records already
+    accumulated by ``conv_dgrad(..., fuse=)`` -- the reduction pass is skipped."""
     lib = _lib.load()
     n, d, h, w, cp = dA.shape
     voxels = d * h * w
@@ -225,7 +260,8 @@ def norm_act_bwd(dA, a, y, mode, mean, rstd, scale, slope, drop_p, drop_seed, c,
             dbias = torch.empty(c, dtype=torch.float32, device=dev)
     _lib.check(lib.ub_norm_act_bwd(_p(dA), _p(a), _p(y), mode, _p(mean), _p(rstd), _p(scale), _p(shift), slope, drop_p,
                                    drop_seed & 0xFFFFFFFF, n, voxels, cp, c, _p(ws), _p(dy), _p(dgamma), _p(dbeta),
-                                   _p(dbias), _stream()), "ub_norm_act_bwd")
+                                   _p(dbias), _p(partial), 0 if partial is None else partial.shape[0] // n, _stream()),
+               "ub_norm_act_bwd")
     return dy, dgamma, dbeta, dbias
 
 
