@@ -34,7 +34,7 @@ enum {
   UB_CONV_K4S2P1 = 2,   /* nn.Conv3d(k=4,s=2,p=1): DownSampleConv in the PatchGAN, ref:model.py:50,72-82 */
   UB_DECONV_K2S2 = 3,   /* nn.ConvTranspose3d(k=2,s=2): monai UpSample "deconv" in UpCat */
   UB_CONV_K4S2P1_S2D = 4 /* UB_CONV_K4S2P1 whose source is the space-to-depth layout written by
-                            ub_pack_ncdhw_s2d ([n][d/2][h/2][w/2][(pd,ph,pw)][c0p]): the PatchGAN stem d1,
+                            ub_pack_ncdhw_s2d ([n][(pd,ph,pw)][d/2][h/2][w/2][c0p]): the PatchGAN stem d1,
                             ref:model.py:72-73,86. n,d,h,w / c0,c0p describe the ORIGINAL input; the
                             gradient written by ub_conv_dgrad is in the plain NDHWC layout */
 };
@@ -91,7 +91,8 @@ int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void* src1, con
  * torch.cat of ref:model.py:86 and Lightning's host tensor layout */
 int ub_pack_ncdhw(const float* a, int ca, const float* b, int cb, int n, long long voxels, int cp,
                   void* out, void* stream);
-/* same, but the destination is the space-to-depth layout [n][d/2][h/2][w/2][(pd,ph,pw)][cp] read by
+/* same, but the destination is the parity-planar space-to-depth layout
+ * [n][(pd,ph,pw)][d/2][h/2][w/2][cp] (eight dense half-resolution sub-volumes per sample) read by
  * UB_CONV_K4S2P1_S2D (the PatchGAN stem d1, ref:model.py:72-73,86); d, h, w must be even */
 int ub_pack_ncdhw_s2d(const float* a, int ca, const float* b, int cb, int n, int d, int h, int w, int cp,
                       void* out, void* stream);

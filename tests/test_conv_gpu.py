@@ -62,8 +62,8 @@ def _src(kind, x):
     t = to_internal(x)
     if kind == 4:
         n, d, h, w, cp = t.shape
-        t = t.view(n, d // 2, 2, h // 2, 2, w // 2, 2, cp).permute(0, 1, 3, 5, 2, 4, 6, 7).reshape(
-            n, d // 2, h // 2, w // 2, 8 * cp).contiguous()
+        t = t.view(n, d // 2, 2, h // 2, 2, w // 2, 2, cp).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(
+            n, 8, d // 2, h // 2, w // 2, cp).contiguous()
     return t
 
 

@@ -36,15 +36,15 @@ def test_pack_unpack_roundtrip(ca, cb, shape):
 
 @pytest.mark.parametrize("ca,cb,shape", [(24, 6, (2, 4, 6, 10)), (6, 6, (1, 8, 8, 8)), (24, 0, (1, 2, 4, 18))])
 def test_pack_space_to_depth(ca, cb, shape):
-    """s2d layout [n][d/2][h/2][w/2][(pd,ph,pw)][cp] == plain pack regrouped by parity (bit-exact)."""
+    """s2d layout [n][(pd,ph,pw)][d/2][h/2][w/2][cp] == plain pack regrouped by parity (bit-exact)."""
     ops = _ops()
     n, d, h, w = shape
     a = _rand((n, ca, d, h, w), 0)
     b = _rand((n, cb, d, h, w), 1) if cb else None
     plain = ops.pack_ncdhw(a, b)                                      # (n,d,h,w,32)
     s2d = ops.pack_ncdhw(a, b, s2d=True)
-    assert s2d.shape == (n, d // 2, h // 2, w // 2, 256)
-    want = plain.view(n, d // 2, 2, h // 2, 2, w // 2, 2, 32).permute(0, 1, 3, 5, 2, 4, 6, 7).reshape(s2d.shape)
+    assert s2d.shape == (n, 8, d // 2, h // 2, w // 2, 32)
+    want = plain.view(n, d // 2, 2, h // 2, 2, w // 2, 2, 32).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(s2d.shape)
     assert torch.equal(s2d, want)
 
 

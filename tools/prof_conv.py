@@ -10,6 +10,8 @@ dev = "cuda"
 spec = ops.ConvSpec(kind, c0, co, c1)
 g = torch.Generator(device=dev).manual_seed(0)
 s0 = torch.randn((n, d, h, w, spec.c0p), device=dev, generator=g).to(torch.bfloat16)
+if kind == 4:   # space-to-depth source layout
+    s0 = s0.view(n, 8, d // 2, h // 2, w // 2, spec.c0p)
 s1 = torch.randn((n, d, h, w, spec.c1p), device=dev, generator=g).to(torch.bfloat16) if c1 else None
 k = {0: 3, 1: 1, 2: 4, 3: 2, 4: 4}[kind]
 wshape = (c0 + c1, co, k, k, k) if kind == 3 else (co, c0 + c1, k, k, k)

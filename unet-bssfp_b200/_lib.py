@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libubssfp.so")
+# UB_LIB_PATH: load another build of the same ABI (A/B timing of kernel changes); default = the in-tree build
+LIB_PATH = os.environ.get("UB_LIB_PATH") or os.path.join(_HERE, "libubssfp.so")
 
 UB_CONV_K3S1P1, UB_CONV_K1, UB_CONV_K4S2P1, UB_DECONV_K2S2, UB_CONV_K4S2P1_S2D = 0, 1, 2, 3, 4
 UB_NORM_INSTANCE, UB_NORM_BATCH_TRAIN, UB_NORM_BATCH_EVAL, UB_NORM_NONE = 0, 1, 2, 3

@@ -61,8 +61,9 @@ struct IgemmParams {
   int n_atiles, bw, bh, n_in_planes, in_stride;
   // chunks_per_group > 0 ("group mode", space-to-depth sources): chunk ch belongs to group
   // g = ch / chunks_per_group (the input parity class); the stage holds ONE tile whose origin offset
-  // is atile_off[g] and the taps of that chunk are taps[g * ntaps + tp]. The weight K coordinate is
-  // (ch % chunks_per_group) * kc.
+  // is atile_off[g] and the taps of that chunk are taps[g * ntaps + tp]. The source is parity-planar
+  // ([N * groups][D][H][W][chunks_per_group * kc]): channel coordinate (ch % chunks_per_group) * kc,
+  // batch coordinate nb * groups + g. The weight K coordinate is (ch % chunks_per_group) * kc.
   int chunks_per_group;
   int atile_off[kMaxATiles][3];  // (w, h, d) added to in_stride * tile origin
   int ntaps;
@@ -73,6 +74,9 @@ struct IgemmParams {
   // feeds the output planes p-2 .. p of the tile with UMMAs of N = up to f * nt (their accumulators
   // are adjacent TMEM columns), so the A operand is read from shared memory once per f depth taps.
   int kd_fold;
+  int fold_nd;                   // depth taps folded (3: 3x3x3; 2: the stride-2 stem on its space-to-depth source)
+  int fold_row_step;             // weight-tensor rows between the depth-tap blocks j = 0 .. fold_nd-1 of a tile
+                                 // (block j holds depth tap fold_nd-1-j)
   int b_block_rows;              // rows of one weight block in the packed tensor (nt, or 3 * nt when folded)
   int td;
   int Nb, Do, Ho, Wo;            // tile space (output voxels before the optional scatter)
@@ -189,7 +193,7 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       const uint32_t a_bytes = (uint32_t)(P.n_atiles * P.n_in_planes * P.bh * P.bw * pitch);
-      const uint32_t b_bytes = (uint32_t)((P.kd_fold ? 3 : 1) * NT.nt * pitch);
+      const uint32_t b_bytes = (uint32_t)((P.kd_fold ? P.fold_nd : 1) * NT.nt * pitch);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
@@ -199,8 +203,9 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
           mbar_expect_tx(a_full + 8 * sa, a_bytes);
           const bool s1 = ch >= P.n_chunks_src0;
           const CUtensorMap* tm = &P.tm_src[s1 ? 1 : 0];
-          const int c0 = (s1 ? ch - P.n_chunks_src0 : ch) * P.kc;
           const int grp = P.chunks_per_group ? ch / P.chunks_per_group : 0;
+          const int c0 = P.chunks_per_group ? (ch % P.chunks_per_group) * P.kc : (s1 ? ch - P.n_chunks_src0 : ch) * P.kc;
+          const int nb5 = P.chunks_per_group ? T.nb * (P.n_chunks_total / P.chunks_per_group) + grp : T.nb;
           uint32_t dst = a_base + sa * P.a_stage_bytes;
           for (int at = 0; at < P.n_atiles; ++at) {
             const int oi = P.chunks_per_group ? grp : at + NT.tapset;
@@ -208,7 +213,7 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
             const int chh = T.h0 * P.in_stride + P.atile_off[oi][1];
             for (int p = 0; p < P.n_in_planes; ++p, dst += P.plane_stride) {
               const int cd = (T.d0 + p) * P.in_stride + P.atile_off[oi][2];
-              tma_load_5d(dst, tm, a_full + 8 * sa, c0, cw, chh, cd, T.nb);
+              tma_load_5d(dst, tm, a_full + 8 * sa, c0, cw, chh, cd, nb5);
             }
           }
           const int wk = (P.chunks_per_group ? ch % P.chunks_per_group : ch) * P.kc;
@@ -218,9 +223,10 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
             mbar_expect_tx(b_full + 8 * sb, b_bytes);
             const int brow = (taps[tp].wblock + NT.wblock_add) * P.b_block_rows + NT.n0;
             tma_load_2d(b_base + sb * P.b_stage_bytes, &P.tm_w, b_full + 8 * sb, wk, brow);
-            if (P.kd_fold) {   // the three depth-tap blocks of the folded tile (TMA boxes hold <= 256 rows)
-              tma_load_2d(b_base + sb * P.b_stage_bytes + NT.nt * pitch, &P.tm_w, b_full + 8 * sb, wk, brow + NT.nt);
-              tma_load_2d(b_base + sb * P.b_stage_bytes + 2 * NT.nt * pitch, &P.tm_w, b_full + 8 * sb, wk, brow + 2 * NT.nt);
+            if (P.kd_fold) {   // the other depth-tap blocks of the folded tile (TMA boxes hold <= 256 rows)
+              for (int j = 1; j < P.fold_nd; ++j)
+                tma_load_2d(b_base + sb * P.b_stage_bytes + j * NT.nt * pitch, &P.tm_w, b_full + 8 * sb, wk,
+                            brow + j * P.fold_row_step);
             }
             if (++sb == P.nsb) { sb = 0; pb ^= 1; }
           }
@@ -239,10 +245,40 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
     const uint32_t lbo_lo = 1u << 16;  // LBO field (16 bytes) lives in the low word
     const uint32_t plane16 = (uint32_t)P.plane_stride >> 4;
     const bool leader = elect_one();
+    // depth-tap folding constants
+    const int fold = P.kd_fold, ndm1 = P.fold_nd - 1;
+    const uint32_t kd_rows16 = (uint32_t)(NT.nt * pitch) >> 4;   // one depth-tap block of the weight tile
+    uint32_t idesc_blk[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) idesc_blk[i] = make_idesc_bf16(128, (i + 1) * NT.nt <= 256 ? (i + 1) * NT.nt : NT.nt, 0, 0);
     int sa = 0, sb = 0, slot = 0;
     uint32_t pa = 0, pb = 0, pacc = 0;
     for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
       const IgemmTileCoord T = igemm_tile(P, t);
+      const int n_pin = T.planes + ndm1;
+      // folded schedule of this tile: entry e = (halo plane p_in, UMMA group gi): accumulator column
+      // offset, A plane offset, weight block offset, instruction descriptor (N = 1..3 depth blocks)
+      uint32_t fs_d[12], fs_a[12], fs_b[12], fs_i[12], fs_valid = 0;
+      if (fold) {
+#pragma unroll
+        for (int p_in = 0; p_in < 6; ++p_in) {
+#pragma unroll
+          for (int gi = 0; gi < 2; ++gi) {
+            const int e = p_in * 2 + gi;
+            const int o_lo = p_in - ndm1 > 0 ? p_in - ndm1 : 0;
+            const int o_hi = p_in < T.planes - 1 ? p_in : T.planes - 1;
+            const int oa = o_lo + gi * fold;
+            const int ob = oa + fold - 1 < o_hi ? oa + fold - 1 : o_hi;
+            const bool v = p_in < n_pin && oa <= o_hi;
+            const int nb_ = ob - oa;
+            fs_d[e] = (uint32_t)(oa * ntc);
+            fs_a[e] = (uint32_t)p_in * plane16;
+            fs_b[e] = (uint32_t)(ndm1 - (p_in - oa)) * kd_rows16;
+            fs_i[e] = nb_ <= 0 ? idesc_blk[0] : (nb_ == 1 ? idesc_blk[1] : idesc_blk[2]);
+            fs_valid |= (v ? 1u : 0u) << e;
+          }
+        }
+      }
       mbar_wait(acc_empty + 8 * slot, pacc ^ 1);
       tc_fence_after();
       const uint32_t acc0 = tmem + slot * acc_cols;
@@ -255,28 +291,27 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
           mbar_wait(b_full + 8 * sb, pb);
           tc_fence_after();
           if (leader && P.kd_fold) {
-            const IgemmTap Tp = P.taps[tp];
+            const IgemmTap Tp = P.taps[tbase + tp];
             const uint32_t a_tap = lbo_lo | ((a_stage + Tp.row_off * pitch) >> 4);
             const uint32_t b_lo0 = lbo_lo | ((b_base + sb * P.b_stage_bytes) >> 4);
-            const uint32_t kd_rows16 = (uint32_t)(NT.nt * pitch) >> 4;   // one depth-tap block of the weight tile
-            const bool first = (ch | tp) == 0;
-            for (int p_in = 0; p_in < T.planes + 2; ++p_in) {
-              const int o_lo = p_in - 2 > 0 ? p_in - 2 : 0;
-              const int o_hi = p_in < T.planes - 1 ? p_in : T.planes - 1;
-              const uint32_t a_lo = a_tap + p_in * plane16;
-              if (!first) {
-                for (int oa = o_lo; oa <= o_hi; oa += P.kd_fold) {
-                  const int ob = oa + P.kd_fold - 1 < o_hi ? oa + P.kd_fold - 1 : o_hi;
-                  const uint32_t idesc_n = make_idesc_bf16(128, (ob - oa + 1) * NT.nt, 0, 0);
-                  const uint32_t b_lo = b_lo0 + (2 - (p_in - oa)) * kd_rows16;
-                  umma_bf16_lohi(acc0 + oa * ntc, a_lo, a_hi, b_lo, b_hi, idesc_n, 1u);
-                  umma_bf16_lohi(acc0 + oa * ntc, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc_n, 1u);
+            if ((ch | tp) != 0) {
+              // the per-tile schedule (fs_*) makes this a straight run of UMMAs: ~8 integer ops each
+#pragma unroll
+              for (int e = 0; e < 12; ++e) {
+                if ((fs_valid >> e) & 1u) {
+                  umma_bf16_lohi(acc0 + fs_d[e], a_tap + fs_a[e], a_hi, b_lo0 + fs_b[e], b_hi, fs_i[e], 1u);
+                  umma_bf16_lohi(acc0 + fs_d[e], a_tap + fs_a[e] + 2, a_hi, b_lo0 + fs_b[e] + 2, b_hi, fs_i[e], 1u);
                 }
-              } else {
-                // first tap of the tile: each output plane's first contribution (kd = 0) overwrites
+              }
+            } else {
+              // first tap of the tile: each output plane's first contribution (kd = 0) overwrites
+              for (int p_in = 0; p_in < n_pin; ++p_in) {
+                const int o_lo = p_in - ndm1 > 0 ? p_in - ndm1 : 0;
+                const int o_hi = p_in < T.planes - 1 ? p_in : T.planes - 1;
+                const uint32_t a_lo = a_tap + p_in * plane16;
                 for (int o = o_lo; o <= o_hi; ++o) {
                   const int kd = p_in - o;
-                  const uint32_t b_lo = b_lo0 + (2 - kd) * kd_rows16;
+                  const uint32_t b_lo = b_lo0 + (uint32_t)(ndm1 - kd) * kd_rows16;
                   umma_bf16_lohi(acc0 + o * ntc, a_lo, a_hi, b_lo, b_hi, idesc, (uint32_t)(kd != 0));
                   umma_bf16_lohi(acc0 + o * ntc, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
                 }

@@ -31,7 +31,8 @@ struct WgradParams {
   int dy_stride;                         // dY coordinate = tile coord * dy_stride + off
   int n_variants;
   int x_off[kMaxWgVariants][3];          // (w,h,d)
-  int x_coff[kMaxWgVariants];            // channel offset of the variant inside X (space-to-depth parity block)
+  int x_nmul, x_nadd[kMaxWgVariants];    // X batch coordinate = nb * x_nmul + x_nadd[variant] (parity-planar
+                                         // space-to-depth source: x_nmul = 8, x_nadd = parity of the variant)
   int dy_off[kMaxWgVariants][3];
   int ngroups, group_row_step;           // groups per variant (kh), rows between group starts
   int natoms;                            // useful atoms per group (kw), <= 4
@@ -104,8 +105,9 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
         mbar_wait(empty + 8 * st, ph ^ 1);
         mbar_expect_tx(full + 8 * st, bytes);
         const uint32_t xs = base + st * stage_bytes;
-        tma_load_5d(xs, tmx, full + 8 * st, c0 + P.x_coff[var], tw_i * 8 * P.x_stride + P.x_off[var][0],
-                    th_i * 16 * P.x_stride + P.x_off[var][1], d * P.x_stride + P.x_off[var][2], nb);
+        tma_load_5d(xs, tmx, full + 8 * st, c0, tw_i * 8 * P.x_stride + P.x_off[var][0],
+                    th_i * 16 * P.x_stride + P.x_off[var][1], d * P.x_stride + P.x_off[var][2],
+                    nb * P.x_nmul + P.x_nadd[var]);
         for (int b = 0; b < nboxes; ++b)
           tma_load_5d(xs + P.x_stage_bytes + b * 128 * dy_pitch, &P.tm_dy, full + 8 * st, n0 + b * P.ncb,
                       tw_i * 8 * P.dy_stride + P.dy_off[var][0], th_i * 16 * P.dy_stride + P.dy_off[var][1],

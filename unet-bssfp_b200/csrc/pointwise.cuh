@@ -122,8 +122,9 @@ __device__ __forceinline__ void norm_act_apply8(float (&x)[8], const NormActArgs
 // instruction writes one contiguous run of CP*2-byte voxel rows (no partial sectors on either side).
 // Two optional inputs a (ca channels) and b (cb channels) are concatenated: this is the torch.cat of
 // the PatchGAN input (ref: model.py:86) folded into the layout change.
-// S2D: the destination is the space-to-depth layout [N][D/2][H/2][W/2][(pd,ph,pw)][CP] that the
-// stride-2 PatchGAN stem reads with plain (unstrided) TMA boxes.
+// S2D: the destination is the parity-planar space-to-depth layout [N][(pd,ph,pw)][D/2][H/2][W/2][CP]
+// (eight dense half-resolution sub-volumes per sample) that the stride-2 PatchGAN stem reads with
+// plain, unstrided TMA boxes whose rows are contiguous in memory.
 template <int CP, bool S2D, int UNROLL>
 __global__ void __launch_bounds__(256)
 pack_ncdhw_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
@@ -155,8 +156,8 @@ pack_ncdhw_kernel(const float* __restrict__ a, int ca, const float* __restrict__
       const int w = (int)(v % W);
       const long long t = v / W;
       const int h = (int)(t % H), d = (int)(t / H);
-      const size_t q = (((size_t)n * (D >> 1) + (d >> 1)) * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
-      row = q * 8 + ((d & 1) * 4 + (h & 1) * 2 + (w & 1));
+      const size_t par = (size_t)n * 8 + ((d & 1) * 4 + (h & 1) * 2 + (w & 1));
+      row = ((par * (D >> 1) + (d >> 1)) * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
     } else {
       row = (size_t)n * V + v;
     }

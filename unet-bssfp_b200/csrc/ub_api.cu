@@ -221,13 +221,15 @@ static int finish_plan(IgemmPlan* pl, int nt_max) {
   const int pitch = P.kc * 2;
   P.plane_stride = align_up(P.bh * P.bw * pitch, 1024);
   P.a_stage_bytes = P.n_atiles * P.n_in_planes * P.plane_stride;
-  P.b_stage_bytes = align_up((P.kd_fold ? 3 : 1) * nt_max * pitch, 1024);
+  P.b_stage_bytes = align_up((P.kd_fold ? P.fold_nd : 1) * nt_max * pitch, 1024);
   const int misc = 8 * 80 + 64 + kFwdRedFloats * 4 + 1024;
   // A stages: two (the next chunk / next tile loads while this one is multiplied) when they fit.
   // B ring: as deep as the remaining budget allows (<= 16): a weight tile is consumed in td*2 MMAs,
   // far faster than one TMA round trip, so the ring must cover ~2k cycles of latency.
-  P.nsa = 2;
-  if (2 * P.a_stage_bytes + 4 * P.b_stage_bytes + misc > kSmemBudget) P.nsa = 1;
+  // Layers with few taps per K chunk (the space-to-depth stem: 4) consume an A stage faster than one TMA
+  // round trip: give them up to four stages.
+  P.nsa = P.ntaps * P.td <= 32 ? 4 : 2;
+  while (P.nsa > 1 && P.nsa * P.a_stage_bytes + 4 * P.b_stage_bytes + misc > kSmemBudget) --P.nsa;
   P.nsb = (kSmemBudget - P.nsa * P.a_stage_bytes - misc) / P.b_stage_bytes;
   if (P.nsb > 16) P.nsb = 16;
   if (P.nsb < 2) return fail(-2, "igemm smem plan: no room for the weight ring");
@@ -401,6 +403,8 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
   make_ntiles(P, d->cop, out, 0, nullptr);
   const int nt_max = d->cop < 128 ? d->cop : 128;
   P.kd_fold = use_kd_fold(d, 0);
+  P.fold_nd = 3;
+  P.fold_row_step = nt_max;
   P.b_block_rows = P.kd_fold ? 3 * d->cop : d->cop;
   if (int e = make_w_map(&P.tm_w, w_packed, ktot, (long long)ntaps * d->cop, 32, nt_max)) return e;
 
@@ -431,7 +435,14 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
     P.n_atiles = 1; P.bw = 9; P.bh = 17; P.n_in_planes = P.td + 1; P.in_stride = 1;
     P.chunks_per_group = d->c0p / 32;
     P.n_chunks_src0 = P.n_chunks_total = 8 * P.chunks_per_group;
-    P.ntaps = 8;
+    // single N tile of <= 128 columns: fold the two depth shifts of a parity group into one UMMA of
+    // N = 2 * nt (input plane p of the tile feeds the output planes p-1 and p); the two depth-tap
+    // blocks of a tile are 32 taps apart in the [tap][cop][cin] pack
+    const bool fold = d->cop <= 128;
+    P.kd_fold = fold ? 2 : 0;
+    P.fold_nd = 2;
+    P.fold_row_step = -32 * d->cop;
+    P.ntaps = fold ? 4 : 8;
     for (int pd = 0; pd < 2; ++pd)
       for (int ph = 0; ph < 2; ++ph)
         for (int pw = 0; pw < 2; ++pw) {
@@ -440,14 +451,14 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
           P.atile_off[g][1] = ph ? -1 : 0;
           P.atile_off[g][2] = pd ? -1 : 0;
           int t = 0;
-          for (int sd = 0; sd < 2; ++sd)
+          for (int sd = fold ? 1 : 0; sd < 2; ++sd)     // folded: the table entry names the sd = 1 tap (block j = 0)
             for (int sh = 0; sh < 2; ++sh)
               for (int sw = 0; sw < 2; ++sw, ++t) {
                 const int kd = 2 * sd + (1 - pd), kh = 2 * sh + (1 - ph), kw = 2 * sw + (1 - pw);
-                P.taps[g * 8 + t] = IgemmTap{0, (uint16_t)(sh * P.bw + sw), (uint16_t)sd, (uint16_t)((kd * 4 + kh) * 4 + kw)};
+                P.taps[g * P.ntaps + t] = IgemmTap{0, (uint16_t)(sh * P.bw + sw), (uint16_t)sd, (uint16_t)((kd * 4 + kh) * 4 + kw)};
               }
         }
-    if (int e = make_act_map(&P.tm_src[0], src0, 8 * d->c0p, d->w / 2, d->h / 2, d->d / 2, d->n, 32, P.bw, P.bh, 1)) return e;
+    if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w / 2, d->h / 2, d->d / 2, d->n * 8, 32, P.bw, P.bh, 1)) return e;
     if (int e = finish_plan(&pl, nt_max)) return e;
     return launch_igemm(pl, st);
   }
@@ -549,6 +560,8 @@ extern "C" int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const 
   // N tiles may have different widths; the weight box uses the widest, narrower tiles read extra rows
   // of the following tap block / pad rows (never used by their MMA: idesc N = nt)
   P.kd_fold = use_kd_fold(d, 1);
+  P.fold_nd = 3;
+  P.fold_row_step = nt_max;
   P.b_block_rows = P.kd_fold ? 3 * ncols : ncols;
   if (int e = make_w_map(&P.tm_w, w_packed_dgrad, d->cop, (long long)ntaps * ncols, 32, nt_max)) return e;
   bool uniform = true;
@@ -655,6 +668,7 @@ static int plan_wgrad(const ub_conv_desc* d, WgradPlan* pl) {
   P.ncb = P.nt < 64 ? P.nt : 64;
   P.Nb = d->n;
   P.x_stride = 1; P.dy_stride = 1;
+  P.x_nmul = d->kind == UB_CONV_K4S2P1_S2D ? 8 : 1;
   for (int i = 0; i < 64; ++i) pl->tapmap[i] = -1;
   if (d->kind == UB_CONV_K3S1P1) {
     P.bw = 10; P.bh = 18; P.Dt = od; P.Ht = oh; P.Wt = ow;
@@ -680,7 +694,7 @@ static int plan_wgrad(const ub_conv_desc* d, WgradPlan* pl) {
             // plain source: parity tile with element stride 2 (depth in input planes);
             // space-to-depth source: q-space coordinates, parity selects the channel block
             P.x_off[v][2] = s2d ? sd + (pd ? -1 : 0) : 2 * sd + (pd ? -1 : 0);
-            P.x_coff[v] = s2d ? ((pd * 2 + ph) * 2 + pw) * d->c0p : 0;
+            P.x_nadd[v] = s2d ? (pd * 2 + ph) * 2 + pw : 0;
             for (int sh = 0; sh < 2; ++sh)
               for (int sw = 0; sw < 2; ++sw) {
                 const int kd = 2 * sd + (1 - pd), kh = 2 * sh + (1 - ph), kw = 2 * sw + (1 - pw);
@@ -790,7 +804,7 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
   out_dims(d, &od, &oh, &ow);
   P.partial = reinterpret_cast<float*>(workspace);
   if (d->kind == UB_CONV_K4S2P1_S2D) {
-    if (int e = make_act_map(&P.tm_x[0], src0, 8 * d->c0p, d->w / 2, d->h / 2, d->d / 2, d->n, 32, P.bw, P.bh, 1)) return e;
+    if (int e = make_act_map(&P.tm_x[0], src0, d->c0p, d->w / 2, d->h / 2, d->d / 2, d->n * 8, 32, P.bw, P.bh, 1)) return e;
   } else {
     if (int e = make_act_map(&P.tm_x[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, P.x_stride)) return e;
   }

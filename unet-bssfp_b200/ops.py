@@ -66,9 +66,10 @@ class ConvSpec:
 
     def in_dims(self, src0):
         """(n, d, h, w) of the ORIGINAL input of this conv given its source tensor."""
-        n, d, h, w, _ = src0.shape
-        if self.kind == UB_CONV_K4S2P1_S2D:      # space-to-depth source (n, d/2, h/2, w/2, 8*c0p)
+        if self.kind == UB_CONV_K4S2P1_S2D:      # parity-planar space-to-depth source (n, 8, d/2, h/2, w/2, c0p)
+            n, _, d, h, w, _ = src0.shape
             return n, 2 * d, 2 * h, 2 * w
+        n, d, h, w, _ = src0.shape
         return n, d, h, w
 
     def out_dims(self, d, h, w):
@@ -179,8 +180,8 @@ def conv_wgrad(spec: ConvSpec, src0, src1, dy, weight_shape):
 # layout
 # ---------------------------------------------------------------------------------------------------
 def pack_ncdhw(a: torch.Tensor, b: torch.Tensor | None = None, s2d: bool = False) -> torch.Tensor:
-    """cat[a, b] NCDHW fp32 -> (N,D,H,W,Cp) bf16; ``s2d``: space-to-depth layout (N,D/2,H/2,W/2,8*Cp) with
-    channel order (pd, ph, pw, c) -- the input layout of the stride-2 PatchGAN stem."""
+    """cat[a, b] NCDHW fp32 -> (N,D,H,W,Cp) bf16; ``s2d``: parity-planar space-to-depth layout
+    (N, 8 = (pd,ph,pw), D/2, H/2, W/2, Cp) -- the input layout of the stride-2 PatchGAN stem."""
     _require_cuda(a, b)
     lib = _lib.load()
     a = a.contiguous().float()
@@ -191,7 +192,7 @@ def pack_ncdhw(a: torch.Tensor, b: torch.Tensor | None = None, s2d: bool = False
         cb = b.shape[1]
     cp = pad32(ca + cb)
     if s2d:
-        out = torch.empty((n, d // 2, h // 2, w // 2, 8 * cp), dtype=torch.bfloat16, device=a.device)
+        out = torch.empty((n, 8, d // 2, h // 2, w // 2, cp), dtype=torch.bfloat16, device=a.device)
         _lib.check(lib.ub_pack_ncdhw_s2d(_p(a), ca, _p(b), cb, n, d, h, w, cp, _p(out), _stream()), "ub_pack_ncdhw_s2d")
         return out
     out = torch.empty((n, d, h, w, cp), dtype=torch.bfloat16, device=a.device)
