@@ -96,6 +96,16 @@ int ub_pack_ncdhw(const float* a, int ca, const float* b, int cb, int n, long lo
  * UB_CONV_K4S2P1_S2D (the PatchGAN stem d1, ref:model.py:72-73,86); d, h, w must be even */
 int ub_pack_ncdhw_s2d(const float* a, int ca, const float* b, int cb, int n, int d, int h, int w, int cp,
                       void* out, void* stream);
+/* Sliding-window inference (ref:model.py:315-333, ref:data_module.py:168-183; torchio==0.19.6
+ * GridSampler / GridAggregator with patch_overlap 0). ub_pack_patches gathers n (<= 64) d x h x w patches of
+ * an NCDHW fp32 volume into one NDHWC bf16 batch: patch i starts at element offsets[i] (HOST array) of `a`,
+ * its element (c,z,y,x) is at + c*stride_c + z*stride_d + y*stride_h + x. ub_unpack_patch writes channels
+ * [c_begin, c_begin+c) of batch sample `sample` into the volume region at dst + dst_offset (same
+ * addressing); calling it in sampler order reproduces "the later patch wins". */
+int ub_pack_patches(const float* a, int ca, int n, const long long* offsets, int d, int h, int w,
+                    long long stride_c, long long stride_d, long long stride_h, int cp, void* out, void* stream);
+int ub_unpack_patch(const void* src, int cp, int c_begin, int c, int sample, int d, int h, int w, float* dst,
+                    long long dst_offset, long long stride_c, long long stride_d, long long stride_h, void* stream);
 /* NDHWC bf16 (cp channels) -> NCDHW fp32, channels [c_begin, c_begin + c) */
 int ub_unpack_ncdhw(const void* src, int cp, int c_begin, int c, int n, long long voxels, float* out,
                     void* stream);

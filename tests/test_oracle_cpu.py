@@ -119,3 +119,22 @@ def test_eval_matches_golden():
     np.testing.assert_allclose(diff.astype(np.float32), GOLD["eval_diff_rel"], rtol=1e-6, equal_nan=True)
     np.testing.assert_allclose(errs, GOLD["eval_errs_rel"], rtol=1e-12, equal_nan=True)
     assert np.isnan(errs[:, 0]).all() and np.isfinite(errs[:, 1:]).all()   # the 0/0 voxel poisons channel 0 only
+
+
+def test_grid_sampler_restatement_kat():
+    """torchio GridSampler (overlap 0) locations: SURVEY section 8d KAT and the host logic of the product."""
+    import importlib
+    from oracle import infer_oracle as I
+    locs = I.grid_locations((160, 192, 160), (64, 64, 64))
+    assert len(locs) == 27 and locs[0] == (0, 0, 0) and locs[-1] == (96, 128, 96)
+    assert locs == sorted(locs)
+    assert I.grid_locations((64, 64, 64), (64, 64, 64)) == [(0, 0, 0)]
+    assert I.grid_locations((96, 128, 128), (64, 64, 64)) == [(z, y, x) for z in (0, 32) for y in (0, 64) for x in (0, 64)]
+    inf = importlib.import_module("unet_bssfp_b200.inference")
+    for shape, patch in [((160, 192, 160), (64, 64, 64)), ((96, 128, 128), (64, 64, 64)), ((70, 64, 100), (32, 64, 48))]:
+        assert inf.grid_locations(shape, patch) == I.grid_locations(shape, patch)
+    # later patch wins
+    import torch
+    out = I.aggregate(torch.zeros((1, 4, 4, 6)), [torch.full((1, 4, 4, 4), 1.0), torch.full((1, 4, 4, 4), 2.0)],
+                      [(0, 0, 0), (0, 0, 2)])
+    assert out[0, 0, 0].tolist() == [1, 1, 2, 2, 2, 2]

@@ -9,3 +9,4 @@ __version__ = "0.1.0"
 from .modules import (BasicUNet, BCEWithLogitsLoss, Discriminator, DownSampleConv, Generator,  # noqa: E402,F401
                       L1Loss)
 from . import ops  # noqa: E402,F401
+from . import inference  # noqa: E402,F401

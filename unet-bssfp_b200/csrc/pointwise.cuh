@@ -165,6 +165,63 @@ pack_ncdhw_kernel(const float* __restrict__ a, int ca, const float* __restrict__
   }
 }
 
+// Patch gather (sliding-window inference): sample n of the output batch is the d x h x w sub-volume of an
+// NCDHW fp32 tensor that starts at element offset G.offset[n]; element (c, z, y, x) of it lives at
+// + c * stride_c + z * stride_d + y * stride_h + x. Replaces torchio's GridSampler patch extraction
+// (ref: data_module.py:168-183, model.py:315-321) with index arithmetic inside the layout pack.
+constexpr int kMaxPatchBatch = 64;
+struct PatchGeom {
+  long long offset[kMaxPatchBatch];
+  long long stride_c, stride_d, stride_h;
+  int d, h, w;
+};
+template <int CP, int UNROLL>
+__global__ void __launch_bounds__(256)
+pack_patches_kernel(const float* __restrict__ a, int ca, __nv_bfloat16* __restrict__ dst, PatchGeom G) {
+  constexpr int OCT = CP / 8;
+  constexpr int VPB = 256 / OCT;
+  const int n = blockIdx.y;
+  const int oct = threadIdx.x % OCT;
+  const uint32_t V = (uint32_t)G.d * G.h * G.w;
+  const uint32_t v0 = blockIdx.x * (VPB * UNROLL) + threadIdx.x / OCT;
+  const float* base = a + G.offset[n];
+  float g[UNROLL][8];
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    const uint32_t v = v0 + u * VPB;
+    const uint32_t x = v % G.w, t = v / G.w;
+    const uint32_t y = t % G.h, z = t / G.h;
+    const float* p = base + (size_t)z * G.stride_d + (size_t)y * G.stride_h + x;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = oct * 8 + k;
+      g[u][k] = (c < ca && v < V) ? __ldg(p + (size_t)c * G.stride_c) : 0.f;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    const uint32_t v = v0 + u * VPB;
+    if (v >= V) continue;
+    reinterpret_cast<bf16x8*>(dst + ((size_t)n * V + v) * CP)[oct] = pack8(g[u]);
+  }
+}
+
+// Patch scatter: channels [c_begin, c_begin + c) of sample `sample` of an NDHWC bf16 batch -> a d x h x w
+// region of an NCDHW fp32 volume (same addressing as PatchGeom, one region: offset[0]). Later patches
+// overwrite earlier ones when launched in sampler order: torchio GridAggregator.add_batch with
+// overlap 0 (ref: model.py:322).
+__global__ void unpack_patch_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int cp, int c_begin,
+                                    int c, int sample, PatchGeom G) {
+  const uint32_t V = (uint32_t)G.d * G.h * G.w;
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const uint32_t x = v % G.w, t = v / G.w;
+  const uint32_t y = t % G.h, z = t / G.h;
+  const __nv_bfloat16* s = src + ((size_t)sample * V + v) * cp + c_begin;
+  float* d = dst + G.offset[0] + (size_t)z * G.stride_d + (size_t)y * G.stride_h + x;
+  for (int k = 0; k < c; ++k) d[(size_t)k * G.stride_c] = __bfloat162float(s[k]);
+}
+
 // channels [c_begin, c_begin + c) of an NDHWC bf16 tensor -> NCDHW fp32
 __global__ void unpack_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int cp,
                                     int c_begin, int c, long long V, long long total) {

@@ -873,6 +873,42 @@ extern "C" int ub_pack_ncdhw_s2d(const float* a, int ca, const float* b, int cb,
   return launch_pack<true>(a, ca, b, cb, n, (long long)d * h * w, d, h, w, cp, out, (cudaStream_t)stream);
 }
 
+extern "C" int ub_pack_patches(const float* a, int ca, int n, const long long* offsets, int d, int h, int w,
+                               long long stride_c, long long stride_d, long long stride_h, int cp, void* out,
+                               void* stream) {
+  if (!a || !out || !offsets || ca <= 0 || n <= 0 || d <= 0 || h <= 0 || w <= 0) return fail(-1, "bad arguments to ub_pack_patches");
+  if (n > kMaxPatchBatch) return fail(-1, "ub_pack_patches: at most %d patches per call", kMaxPatchBatch);
+  if (ca > cp || (cp != 32 && cp != 64)) return fail(-1, "ub_pack_patches supports cp in {32, 64}, got ca=%d cp=%d", ca, cp);
+  PatchGeom G;
+  memset(&G, 0, sizeof(G));
+  for (int i = 0; i < n; ++i) G.offset[i] = offsets[i];
+  G.stride_c = stride_c; G.stride_d = stride_d; G.stride_h = stride_h; G.d = d; G.h = h; G.w = w;
+  const long long V = (long long)d * h * w;
+  constexpr int UNROLL = 4;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cp == 32) pack_patches_kernel<32, UNROLL><<<dim3((unsigned)((V + 64 * UNROLL - 1) / (64 * UNROLL)), n), 256, 0, st>>>(a, ca, o, G);
+  else pack_patches_kernel<64, UNROLL><<<dim3((unsigned)((V + 32 * UNROLL - 1) / (32 * UNROLL)), n), 256, 0, st>>>(a, ca, o, G);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ub_unpack_patch(const void* src, int cp, int c_begin, int c, int sample, int d, int h, int w, float* dst,
+                               long long dst_offset, long long stride_c, long long stride_d, long long stride_h,
+                               void* stream) {
+  if (!src || !dst || c <= 0 || c_begin < 0 || c_begin + c > cp || cp % 8 || sample < 0 || d <= 0 || h <= 0 || w <= 0)
+    return fail(-1, "bad arguments to ub_unpack_patch");
+  PatchGeom G;
+  memset(&G, 0, sizeof(G));
+  G.offset[0] = dst_offset;
+  G.stride_c = stride_c; G.stride_d = stride_d; G.stride_h = stride_h; G.d = d; G.h = h; G.w = w;
+  const long long V = (long long)d * h * w;
+  unpack_patch_kernel<<<(unsigned)((V + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), dst, cp, c_begin, c, sample, G);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int ub_unpack_ncdhw(const void* src, int cp, int c_begin, int c, int n, long long voxels, float* out,
                                void* stream) {
   if (!src || !out || c <= 0 || c_begin < 0 || c_begin + c > cp || cp % 8) return fail(-1, "bad arguments to ub_unpack_ncdhw");

@@ -1,0 +1,69 @@
+"""Whole-volume sliding-window inference and its evaluation, on device.
+
+Mirrors what ``predict_step`` / ``test_step`` of the reference do with torchio (ref:src/model.py:291-333,
+ref:src/data_module.py:168-183; torchio==0.19.6 ``GridSampler(subject, patch_size)`` with the default
+``patch_overlap = 0`` and ``GridAggregator`` in its default ``'crop'`` mode): the volume is covered by a
+grid of patches whose last patch per axis is shifted back to end at the border, every patch goes
+through the generator, and ``add_batch`` writes each prediction into the output volume in sampler
+order -- where patches overlap the later one wins.
+
+Here the sampler and aggregator are index arithmetic inside the layout kernels (``ub_pack_patches`` /
+``ub_unpack_patch``): no host round trip and no intermediate NCDHW patch tensors.
+``relative_error`` then runs the fused error-map + ROI reduction of ref:src/eval.py:154-166,217-258.
+"""
+from __future__ import annotations
+
+import itertools
+
+import torch
+
+from . import ops
+
+__all__ = ["grid_locations", "predict_volume", "relative_error"]
+
+
+def grid_locations(shape, patch):
+    """Patch origins of torchio's GridSampler for ``patch_overlap = 0``, in sampler order
+    (lexicographic in (axis0, axis1, axis2)): per axis ``range(0, size + 1 - patch, patch)`` plus a
+    last origin at ``size - patch`` when the grid does not end at the border."""
+    per_axis = []
+    for size, p in zip(shape, patch):
+        if p > size:
+            raise ValueError(f"patch size {p} larger than the volume ({size})")
+        idx = list(range(0, size + 1 - p, p))
+        if idx[-1] != size - p:
+            idx.append(size - p)
+        per_axis.append(idx)
+    return list(itertools.product(*per_axis))
+
+
+@torch.no_grad()
+def predict_volume(gen, volume: torch.Tensor, patch=64, batch: int = 8) -> torch.Tensor:
+    """``volume``: (C,D,H,W) or (1,C,D,H,W) fp32 CUDA tensor. Returns the aggregated prediction
+    (6,D,H,W) fp32 on the same device. ``gen`` is a ``unet_bssfp_b200.Generator`` (its train/eval mode is
+    respected, as in the reference where ``predict_step`` runs under ``model.eval()``)."""
+    vol = volume if volume.dim() == 4 else volume[0]
+    if not vol.is_cuda:
+        raise RuntimeError("predict_volume runs on CUDA tensors only (there is no CPU fallback)")
+    patch = (patch,) * 3 if isinstance(patch, int) else tuple(patch)
+    origins = grid_locations(tuple(vol.shape[1:]), patch)
+    out_c = gen.blocks["unet"].out_channels
+    out = torch.zeros((out_c,) + tuple(vol.shape[1:]), dtype=torch.float32, device=vol.device)
+    for i in range(0, len(origins), batch):
+        group = origins[i:i + batch]
+        a = ops.pack_patches(vol, group, patch)
+        y = gen.forward_packed(a)
+        for k, org in enumerate(group):          # sampler order: the later patch wins
+            ops.unpack_patch(y, k, out_c, out, org)
+    return out
+
+
+def relative_error(pred: torch.Tensor, target: torch.Tensor, mask=None, probseg=None, angular: bool = False):
+    """``pred`` / ``target``: (C,D,H,W) fp32 volumes (module layout). Returns ``(diff (D,H,W,C), errs [R][C] |
+    None)``: the map of ``do_calc_diff_maps`` (channel-last, as the reference stores NIfTI volumes) and the
+    per-ROI probseg-weighted means of ``do_calc_error_avg``."""
+    p = pred.permute(1, 2, 3, 0).contiguous().float()
+    t = target.permute(1, 2, 3, 0).contiguous().float()
+    diff, sums, norms = ops.relerr_map_reduce(p, t, mask, probseg, angular=angular)
+    errs = None if sums is None else sums / norms[:, None]
+    return diff, errs

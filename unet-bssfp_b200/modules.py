@@ -406,45 +406,52 @@ def _check_unet_dims(d, h, w):
                            "monai UpCat for odd sizes is not on the sm_100a path)")
 
 
+def _generator_run(net: _UNetGraph, a, need_bwd: bool):
+    """Packed input (N,D,H,W,32) bf16 -> packed output of ``final_conv`` (N,D,H,W,32) bf16 and the
+    saved-for-backward dict (or None). The one place that sequences the generator's kernels."""
+    training = net.training
+    head_training = net.head_mod.training if net.head_mod is not None else training
+    base_seed = _fresh_seed() if training else 0
+    cache = net.cache
+    S = {}          # block name -> saved
+    lid = [0]
+
+    def run(blk, s0, s1=None, pool=False, tr=training):
+        lid[0] += 1
+        a_, pooled, sv = _block_forward(blk, cache, s0, s1, tr, (base_seed + 7919 * lid[0]) & 0x7FFFFFFF,
+                                        pool=pool, save=need_bwd)
+        S[blk.name] = sv
+        return a_, pooled
+
+    if net.head is not None:
+        a, _ = run(net.head, a, tr=head_training)
+    skips = []
+    cur = a
+    for lvl, (c0, c1) in enumerate(net.enc):
+        t, _ = run(c0, cur)
+        last = lvl == len(net.enc) - 1
+        xk, pooled = run(c1, t, pool=not last)
+        skips.append(xk)
+        cur = xk if last else pooled
+    u = skips[-1]
+    for j, (dc, c0, c1) in enumerate(net.dec):
+        x_e = skips[-2 - j]
+        up, _ = run(dc, u)
+        t, _ = run(c0, x_e, up)
+        u, _ = run(c1, t)
+    yf, _ = run(net.final, u)
+    return yf, (S if need_bwd else None)
+
+
 class _GeneratorFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, net: _UNetGraph, grad_enabled, *params):
         need_bwd = grad_enabled and (x.requires_grad or any(p.requires_grad for p in params))
         _check_unet_dims(*x.shape[2:])
-        training = net.training
-        head_training = net.head_mod.training if net.head_mod is not None else training
-        base_seed = _fresh_seed() if training else 0
-        cache = net.cache
-        S = {}          # block name -> saved
-        lid = [0]
-
-        def run(blk, s0, s1=None, pool=False, tr=training):
-            lid[0] += 1
-            a, pooled, sv = _block_forward(blk, cache, s0, s1, tr, (base_seed + 7919 * lid[0]) & 0x7FFFFFFF,
-                                           pool=pool, save=need_bwd)
-            S[blk.name] = sv
-            return a, pooled
-
         a = net.input_pack.get(x)
-        if net.head is not None:
-            a, _ = run(net.head, a, tr=head_training)
-        skips = []
-        cur = a
-        for lvl, (c0, c1) in enumerate(net.enc):
-            t, _ = run(c0, cur)
-            last = lvl == len(net.enc) - 1
-            xk, pooled = run(c1, t, pool=not last)
-            skips.append(xk)
-            cur = xk if last else pooled
-        u = skips[-1]
-        for j, (dc, c0, c1) in enumerate(net.dec):
-            x_e = skips[-2 - j]
-            up, _ = run(dc, u)
-            t, _ = run(c0, x_e, up)
-            u, _ = run(c1, t)
-        yf, _ = run(net.final, u)
+        yf, S = _generator_run(net, a, need_bwd)
         out = ops.unpack_ncdhw(yf, net.unet.out_channels)
-        ctx.net, ctx.S = net, (S if need_bwd else None)
+        ctx.net, ctx.S = net, S
         ctx.cx = x.shape[1]
         ctx.in_dtype = x.dtype
         return out.to(x.dtype)
@@ -526,6 +533,14 @@ class Generator(nn.Module):
     def forward(self, x):
         net = self._net()
         return _GeneratorFunction.apply(x, net, torch.is_grad_enabled(), *net.params)
+
+    @torch.no_grad()
+    def forward_packed(self, a):
+        """Inference on an already packed batch: (N,D,H,W,32) bf16 NDHWC -> (N,D,H,W,32) bf16 whose first
+        6 channels are the prediction (no NCDHW round trip; used by ``inference.predict_volume``)."""
+        _check_unet_dims(*a.shape[1:4])
+        yf, _ = _generator_run(self._net(), a, need_bwd=False)
+        return yf
 
 
 class Discriminator(nn.Module):

@@ -18,6 +18,7 @@ from ._lib import (ConvDesc, UB_CONV_K1, UB_CONV_K3S1P1, UB_CONV_K4S2P1, UB_CONV
 
 __all__ = [
     "ConvSpec", "pad32", "pack_conv_weights", "conv_fwd", "conv_dgrad", "conv_wgrad", "pack_ncdhw", "unpack_ncdhw",
+    "pack_patches", "unpack_patch",
     "norm_finalize", "norm_act_fwd", "norm_act_bwd", "maxpool_bwd", "colsum", "l1_fwd", "l1_bwd", "bce_logits",
     "scale_by", "relerr_map_reduce",
 ]
@@ -198,6 +199,45 @@ def pack_ncdhw(a: torch.Tensor, b: torch.Tensor | None = None, s2d: bool = False
     out = torch.empty((n, d, h, w, cp), dtype=torch.bfloat16, device=a.device)
     _lib.check(lib.ub_pack_ncdhw(_p(a), ca, _p(b), cb, n, d * h * w, cp, _p(out), _stream()), "ub_pack_ncdhw")
     return out
+
+
+def pack_patches(volume: torch.Tensor, origins, patch) -> torch.Tensor:
+    """Gather ``len(origins)`` patches of an NCDHW fp32 volume (1,C,D,H,W) or (C,D,H,W) into one
+    (n, pd, ph, pw, Cp) bf16 batch. ``origins``: (z, y, x) starts; ``patch``: (pd, ph, pw)."""
+    _require_cuda(volume)
+    lib = _lib.load()
+    vol = volume if volume.dim() == 4 else volume[0]
+    if vol.dtype != torch.float32 or vol.stride(-1) != 1:
+        vol = vol.float().contiguous()
+    c, D, H, W = vol.shape
+    pd, ph, pw = patch
+    sc, sd, sh, _ = vol.stride()
+    n = len(origins)
+    offs = (C.c_longlong * n)(*[z * sd + y * sh + x for (z, y, x) in origins])
+    for (z, y, x) in origins:
+        if z < 0 or y < 0 or x < 0 or z + pd > D or y + ph > H or x + pw > W:
+            raise RuntimeError(f"patch at {(z, y, x)} of size {patch} leaves the volume {(D, H, W)}")
+    cp = pad32(c)
+    out = torch.empty((n, pd, ph, pw, cp), dtype=torch.bfloat16, device=vol.device)
+    _lib.check(lib.ub_pack_patches(_p(vol), c, n, offs, pd, ph, pw, sc, sd, sh, cp, _p(out), _stream()), "ub_pack_patches")
+    return out
+
+
+def unpack_patch(batch: torch.Tensor, sample: int, c: int, volume: torch.Tensor, origin, c_begin: int = 0):
+    """Write channels [c_begin, c_begin+c) of ``batch[sample]`` (NDHWC bf16) into the (c,D,H,W) fp32
+    ``volume`` at ``origin``; the later call wins where patches overlap."""
+    _require_cuda(batch, volume)
+    lib = _lib.load()
+    if volume.dtype != torch.float32 or volume.dim() != 4 or volume.stride(-1) != 1:
+        raise RuntimeError("unpack_patch writes into a (C,D,H,W) fp32 tensor with contiguous rows")
+    _, pd, ph, pw, cp = batch.shape
+    z, y, x = origin
+    sc, sd, sh, _ = volume.stride()
+    _, D, H, W = volume.shape
+    if z < 0 or y < 0 or x < 0 or z + pd > D or y + ph > H or x + pw > W or volume.shape[0] < c:
+        raise RuntimeError(f"patch at {origin} of size {(pd, ph, pw)} leaves the volume {(D, H, W)}")
+    _lib.check(lib.ub_unpack_patch(_p(batch), cp, c_begin, c, sample, pd, ph, pw, _p(volume), z * sd + y * sh + x, sc, sd,
+                                   sh, _stream()), "ub_unpack_patch")
 
 
 def unpack_ncdhw(x: torch.Tensor, c: int, c_begin: int = 0) -> torch.Tensor:
