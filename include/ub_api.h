@@ -163,6 +163,14 @@ int ub_relerr_map_reduce(const float* pred, const float* target, const unsigned 
                          const float* probseg, int c, int r, long long voxels, int angular, float* diff,
                          double* sums, double* norms, void* stream);
 
+/* ref:eval.py:73-116 (do_calc_scalar_maps): per-voxel symmetric 3x3 eigen-decomposition of the diffusion
+ * tensor (channel-last [voxels][6] = dxx,dxy,dxz,dyy,dyz,dzz, fp32) and the derived maps FA, MD, AD, RD
+ * ([voxels]), azimuth / inclination of the principal axis in degrees ([voxels]) and the FA-weighted RGB map
+ * ([voxels][3]). Any output may be NULL. Arithmetic in fp64 like the reference. The principal eigenvector is
+ * oriented with v_z >= 0 (LAPACK leaves the sign implementation-defined). */
+int ub_dti_scalar_maps(const float* tensor6, long long voxels, float* fa, float* md, float* ad, float* rd,
+                       float* azimuth, float* inclination, float* rgb, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

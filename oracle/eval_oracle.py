@@ -3,6 +3,8 @@
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this.
 
 * ``rel_error_map``   ref:src/eval.py:154-166 (do_calc_diff_maps; file I/O stripped)
+* ``dti_scalar_maps`` ref:src/eval.py:73-116 (do_calc_scalar_maps; the Python triple loop is batched through
+                      ``np.linalg.eigh(..., 'U')``, which runs the same LAPACK routine per matrix)
 * ``roi_error_avg``   ref:src/eval.py:217-258 (do_calc_error_avg; file-name parsing, pandas and NIfTI
                       I/O stripped -- the arithmetic of lines 238-249 is kept verbatim in meaning)
 
@@ -42,3 +44,32 @@ def roi_error_avg(diff, mask, probseg):
             norm = probseg[..., roi_idx].sum()
             errs[roi_idx, i] = segmented.sum() / norm
     return errs, diff_map
+
+
+def dti_scalar_maps(data, canonical_sign=False):
+    """ref:src/eval.py:73-116. data (..., 6) -> dict(fa, md, ad, rd, azimuth, inclination, rgb) in float64.
+    ``canonical_sign``: orient the principal eigenvector with v_z >= 0 (then v_y, then v_x) before taking
+    the angles -- LAPACK leaves the sign implementation-defined; the reference keeps whatever it returns."""
+    data = np.asarray(data, dtype=np.float64)
+    d = np.zeros(data.shape[:-1] + (3, 3))
+    d[..., 0, 0], d[..., 0, 1], d[..., 0, 2] = data[..., 0], data[..., 1], data[..., 2]
+    d[..., 1, 0], d[..., 1, 1], d[..., 1, 2] = data[..., 1], data[..., 3], data[..., 4]
+    d[..., 2, 0], d[..., 2, 1], d[..., 2, 2] = data[..., 2], data[..., 4], data[..., 5]
+    eigvals, eigvecs = np.linalg.eigh(d, "U")
+    ad = eigvals[..., 2]
+    rd = (eigvals[..., 0] + eigvals[..., 1]) / 2
+    md = eigvals.mean(-1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        var = np.sqrt(((eigvals - md[..., None]) ** 2).sum(-1))
+        norm = np.sqrt((eigvals ** 2).sum(-1))
+        fa = np.sqrt(1.5) * var / norm
+    v = eigvecs[..., :, 2].copy()
+    if canonical_sign:
+        flip = (v[..., 2] < 0) | ((v[..., 2] == 0) & ((v[..., 1] < 0) | ((v[..., 1] == 0) & (v[..., 0] < 0))))
+        v[flip] *= -1
+    azimuth = 180 / np.pi * np.arctan2(v[..., 1], v[..., 0])
+    azimuth = np.where(azimuth > 180, azimuth - 360, azimuth)
+    r = np.sqrt((v ** 2).sum(-1))
+    inclination = 180 / np.pi * np.arccos(np.clip(v[..., 2] / r, -1.0, 1.0))
+    rgb = fa[..., None] * np.abs(v)
+    return {"fa": fa, "md": md, "ad": ad, "rd": rd, "azimuth": azimuth, "inclination": inclination, "rgb": rgb}

@@ -72,3 +72,65 @@ def test_full_size_volume_properties():
     d_only, none = _run(pred, tgt, None, None, False)
     assert none is None
     np.testing.assert_array_equal(d_only, diff)
+
+
+def _synth_dti(shape, seed=0):
+    """SPD-ish diffusion tensors with a clear principal axis plus isotropic / degenerate / zero voxels."""
+    rng = np.random.default_rng(seed)
+    n = int(np.prod(shape))
+    q, _ = np.linalg.qr(rng.normal(size=(n, 3, 3)))
+    lam = np.sort(rng.uniform(0.1e-3, 3e-3, size=(n, 3)), axis=1)
+    lam[:, 2] *= rng.uniform(1.05, 3.0, size=n)
+    d = np.einsum("nij,nj,nkj->nik", q, lam, q)
+    t6 = np.stack([d[:, 0, 0], d[:, 0, 1], d[:, 0, 2], d[:, 1, 1], d[:, 1, 2], d[:, 2, 2]], -1).astype(np.float32)
+    t6[0] = 0.0                                   # zero tensor: FA = 0/0 = NaN, axis e_z
+    t6[1] = [2e-3, 0, 0, 2e-3, 0, 2e-3]           # isotropic: FA = 0
+    t6[2] = [1e-3, 0, 0, 2e-3, 0, 3e-3]           # already diagonal
+    t6[3] = [3e-3, 0, 0, 2e-3, 0, 1e-3]           # principal axis = x
+    return t6.reshape(tuple(shape) + (6,))
+
+
+def test_dti_scalar_maps_match_oracle():
+    """ub_dti_scalar_maps vs the NumPy/LAPACK oracle of ref:eval.py:73-116 (1e-4). Sign-free maps are
+    compared as is; azimuth / inclination against the oracle with the same principal-axis orientation
+    (v_z >= 0), since LAPACK's eigenvector sign is implementation-defined."""
+    from unet_bssfp_b200 import ops
+    t6 = _synth_dti((24, 20, 16))
+    got = {k: v.cpu().numpy() for k, v in ops.dti_scalar_maps(torch.from_numpy(t6).cuda()).items()}
+    ref = E.dti_scalar_maps(t6, canonical_sign=True)
+    for k in ("md", "ad", "rd"):
+        np.testing.assert_allclose(got[k], ref[k], rtol=1e-4, atol=1e-9)
+    flat_fa, ref_fa = got["fa"].reshape(-1), ref["fa"].reshape(-1)
+    assert np.isnan(flat_fa[0]) and np.isnan(ref_fa[0])                      # zero tensor: 0/0 kept
+    np.testing.assert_allclose(flat_fa[1:], ref_fa[1:], rtol=1e-4, atol=1e-6)
+    ok = np.ones(flat_fa.shape, bool)
+    ok[:3] = False                                                           # zero / isotropic / tie: axis not unique
+    np.testing.assert_allclose(got["rgb"].reshape(-1, 3)[ok], ref["rgb"].reshape(-1, 3)[ok], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(got["inclination"].reshape(-1)[ok], ref["inclination"].reshape(-1)[ok], rtol=1e-4, atol=2e-3)
+    da = np.abs(got["azimuth"].reshape(-1)[ok] - ref["azimuth"].reshape(-1)[ok])
+    da = np.minimum(da, 360 - da)                                            # +-180 is the same direction at v_z = 0
+    horizontal = ref["inclination"].reshape(-1)[ok] > 89.999
+    assert (da[~horizontal] < 2e-3).all()
+    assert (np.minimum(da[horizontal], np.abs(da[horizontal] - 180)) < 2e-3).all()
+    # against the raw (reference-sign) oracle: every voxel is either identical or the antipode
+    raw = E.dti_scalar_maps(t6)
+    inc_g, inc_r = got["inclination"].reshape(-1)[ok], raw["inclination"].reshape(-1)[ok]
+    assert (np.minimum(np.abs(inc_g - inc_r), np.abs(inc_g - (180 - inc_r))) < 2e-3).all()
+    # hand cases
+    assert abs(flat_fa[1]) < 1e-6 and abs(got["azimuth"].reshape(-1)[3]) < 1e-4 and abs(got["inclination"].reshape(-1)[3] - 90) < 1e-4
+    assert abs(got["ad"].reshape(-1)[2] - 3e-3) < 1e-9 and abs(got["inclination"].reshape(-1)[2]) < 1e-4
+
+
+def test_dti_scalar_maps_full_volume_invariants():
+    """160x192x160: MD = trace / 3, AD >= MD >= RD, 0 <= FA <= 1, rotation-free identities."""
+    from unet_bssfp_b200 import ops
+    t6 = _synth_dti((160, 192, 160), seed=1)
+    m = ops.dti_scalar_maps(torch.from_numpy(t6).cuda())
+    torch.cuda.synchronize()
+    tr = torch.from_numpy((t6[..., 0] + t6[..., 3] + t6[..., 5]) / 3).cuda()
+    assert ((m["md"] - tr).abs() <= 1e-6 * tr.abs() + 1e-10).all()
+    fa = m["fa"].reshape(-1)[1:]
+    assert (fa >= -1e-6).all() and (fa <= 1 + 1e-6).all()
+    assert (m["ad"] >= m["md"] - 1e-9).all() and (m["md"] >= m["rd"] - 1e-9).all()
+    assert (m["inclination"] >= 0).all() and (m["inclination"] <= 90.0001).all()
+    assert ((m["ad"] + 2 * m["rd"]) / 3 - m["md"]).abs().max().item() < 1e-8

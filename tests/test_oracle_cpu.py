@@ -138,3 +138,18 @@ def test_grid_sampler_restatement_kat():
     out = I.aggregate(torch.zeros((1, 4, 4, 6)), [torch.full((1, 4, 4, 4), 1.0), torch.full((1, 4, 4, 4), 2.0)],
                       [(0, 0, 0), (0, 0, 2)])
     assert out[0, 0, 0].tolist() == [1, 1, 2, 2, 2, 2]
+
+
+def test_dti_oracle_hand_cases():
+    """Known answers of the DTI scalar maps (ref:eval.py:73-116 formulas)."""
+    from oracle import eval_oracle as E
+    t = np.array([[3e-3, 0, 0, 2e-3, 0, 1e-3],        # diagonal, principal axis x
+                  [2e-3, 0, 0, 2e-3, 0, 2e-3],        # isotropic
+                  [1.0, 0, 0, 0.0, 0, 0.0]])          # stick along x: FA = 1
+    m = E.dti_scalar_maps(t)
+    assert np.allclose(m["ad"], [3e-3, 2e-3, 1.0]) and np.allclose(m["rd"], [1.5e-3, 2e-3, 0.0])
+    assert np.allclose(m["md"], [2e-3, 2e-3, 1 / 3])
+    lam = np.array([1e-3, 2e-3, 3e-3])
+    fa0 = np.sqrt(1.5) * np.sqrt(((lam - 2e-3) ** 2).sum()) / np.sqrt((lam ** 2).sum())
+    assert np.allclose(m["fa"], [fa0, 0.0, 1.0])
+    assert np.allclose(np.abs(m["inclination"][[0, 2]]), 90.0) and np.allclose(m["rgb"][2], [1.0, 0.0, 0.0])

@@ -68,6 +68,7 @@ SIGNATURES = {
     "ub_l1_bwd": (_I, [_P, _P, _P, _LL, _P, _P]),
     "ub_bce_logits": (_I, [_P, _P, _F, _I, _P, _P, _P]),
     "ub_scale": (_I, [_P, _P, _LL, _P, _P]),
+    "ub_dti_scalar_maps": (_I, [_P, _LL, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ub_relerr_map_reduce": (_I, [_P, _P, _P, _P, _I, _I, _LL, _I, _P, _P, _P, _P]),
 }
 

@@ -920,4 +920,84 @@ __global__ void relerr_kernel(const float* __restrict__ pred, const float* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// evaluation: DTI scalar maps from the 6 unique tensor components (dxx, dxy, dxz, dyy, dyz, dzz)
+//   ref: eval.py:73-116 (do_calc_scalar_maps: np.linalg.eigh per voxel in a Python triple loop)
+// One thread per voxel, fp64 cyclic Jacobi on the symmetric 3x3 (converged to machine precision in
+// <= 8 sweeps), eigenvalues ascending as LAPACK returns them:
+//   AD = l3, RD = (l1 + l2) / 2, MD = mean, FA = sqrt(1.5) * |l - MD| / |l|   (0/0 -> NaN as numpy)
+//   azimuth = atan2(v_y, v_x), inclination = acos(v_z / |v|) in degrees, RGB = FA * |v|,  v = principal axis.
+// The SIGN of an eigenvector is implementation-defined in LAPACK; here v is oriented with v_z >= 0
+// (then v_y >= 0, then v_x >= 0 on ties), so inclination lies in [0, 90].
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void jacobi_rotate(double (&A)[3][3], double (&V)[3][3], int p, int q) {
+  if (A[p][q] == 0.0) return;
+  const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+  const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+  const double c = 1.0 / sqrt(t * t + 1.0), s_ = t * c;
+  const double app = A[p][p], aqq = A[q][q], apq = A[p][q];
+  A[p][p] = app - t * apq;
+  A[q][q] = aqq + t * apq;
+  A[p][q] = A[q][p] = 0.0;
+  const int r = 3 - p - q;
+  const double arp = A[r][p], arq = A[r][q];
+  A[r][p] = A[p][r] = c * arp - s_ * arq;
+  A[r][q] = A[q][r] = s_ * arp + c * arq;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double vkp = V[k][p], vkq = V[k][q];
+    V[k][p] = c * vkp - s_ * vkq;
+    V[k][q] = s_ * vkp + c * vkq;
+  }
+}
+
+__global__ void dti_scalar_maps_kernel(const float* __restrict__ t6, long long nvox, float* __restrict__ fa,
+                                       float* __restrict__ md, float* __restrict__ ad, float* __restrict__ rd,
+                                       float* __restrict__ azimuth, float* __restrict__ inclination,
+                                       float* __restrict__ rgb) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvox) return;
+  const float* t = t6 + v * 6;
+  double A[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  A[0][0] = t[0]; A[0][1] = A[1][0] = t[1]; A[0][2] = A[2][0] = t[2];
+  A[1][1] = t[3]; A[1][2] = A[2][1] = t[4]; A[2][2] = t[5];
+  for (int sweep = 0; sweep < 8; ++sweep) {
+    const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    if (off == 0.0) break;
+    jacobi_rotate(A, V, 0, 1);
+    jacobi_rotate(A, V, 0, 2);
+    jacobi_rotate(A, V, 1, 2);
+  }
+  double l[3] = {A[0][0], A[1][1], A[2][2]};
+  int idx[3] = {0, 1, 2};
+  // ascending, stable
+  if (l[idx[1]] < l[idx[0]]) { const int s_ = idx[0]; idx[0] = idx[1]; idx[1] = s_; }
+  if (l[idx[2]] < l[idx[1]]) { const int s_ = idx[1]; idx[1] = idx[2]; idx[2] = s_; }
+  if (l[idx[1]] < l[idx[0]]) { const int s_ = idx[0]; idx[0] = idx[1]; idx[1] = s_; }
+  const double l1 = l[idx[0]], l2 = l[idx[1]], l3 = l[idx[2]];
+  double vx = V[0][idx[2]], vy = V[1][idx[2]], vz = V[2][idx[2]];
+  if (vz < 0.0 || (vz == 0.0 && (vy < 0.0 || (vy == 0.0 && vx < 0.0)))) { vx = -vx; vy = -vy; vz = -vz; }
+  const double mean = (l1 + l2 + l3) / 3.0;
+  const double var = sqrt((l1 - mean) * (l1 - mean) + (l2 - mean) * (l2 - mean) + (l3 - mean) * (l3 - mean));
+  const double nrm = sqrt(l1 * l1 + l2 * l2 + l3 * l3);
+  const double f = sqrt(1.5) * var / nrm;
+  const double r = sqrt(vx * vx + vy * vy + vz * vz);
+  const double kDeg = 57.29577951308232087680;
+  if (fa) fa[v] = (float)f;
+  if (md) md[v] = (float)mean;
+  if (ad) ad[v] = (float)l3;
+  if (rd) rd[v] = (float)((l1 + l2) * 0.5);
+  if (azimuth) azimuth[v] = (float)(kDeg * atan2(vy, vx));
+  if (inclination) {
+    double cz = vz / r;
+    cz = cz > 1.0 ? 1.0 : cz;
+    inclination[v] = (float)(kDeg * acos(cz));
+  }
+  if (rgb) {
+    rgb[v * 3 + 0] = (float)(f * fabs(vx));
+    rgb[v * 3 + 1] = (float)(f * fabs(vy));
+    rgb[v * 3 + 2] = (float)(f * fabs(vz));
+  }
+}
+
 }  // namespace ub

@@ -1112,3 +1112,12 @@ extern "C" int ub_relerr_map_reduce(const float* pred, const float* target, cons
   UB_LAUNCH_CHECK();
   return 0;
 }
+
+extern "C" int ub_dti_scalar_maps(const float* tensor6, long long voxels, float* fa, float* md, float* ad, float* rd,
+                                  float* azimuth, float* inclination, float* rgb, void* stream) {
+  if (!tensor6 || voxels <= 0) return fail(-1, "bad arguments to ub_dti_scalar_maps");
+  dti_scalar_maps_kernel<<<(unsigned)((voxels + 127) / 128), 128, 0, (cudaStream_t)stream>>>(tensor6, voxels, fa, md, ad, rd,
+                                                                                           azimuth, inclination, rgb);
+  UB_LAUNCH_CHECK();
+  return 0;
+}

@@ -20,7 +20,7 @@ __all__ = [
     "ConvSpec", "pad32", "pack_conv_weights", "conv_fwd", "conv_dgrad", "conv_wgrad", "pack_ncdhw", "unpack_ncdhw",
     "pack_patches", "unpack_patch",
     "norm_finalize", "norm_act_fwd", "norm_act_bwd", "maxpool_bwd", "colsum", "l1_fwd", "l1_bwd", "bce_logits",
-    "scale_by", "relerr_map_reduce",
+    "scale_by", "relerr_map_reduce", "dti_scalar_maps",
 ]
 
 
@@ -392,3 +392,20 @@ def relerr_map_reduce(pred, target, mask=None, probseg=None, angular=False, want
     _lib.check(lib.ub_relerr_map_reduce(_p(pred), _p(target), _p(mask), _p(probseg), c, r, voxels, int(angular),
                                         _p(diff), _p(sums), _p(norms), _stream()), "ub_relerr_map_reduce")
     return diff, sums, norms
+
+
+def dti_scalar_maps(tensor6: torch.Tensor):
+    """(..., 6) fp32 channel-last diffusion tensors -> dict of fp32 maps: fa, md, ad, rd, azimuth,
+    inclination (shape ...) and rgb (..., 3). ref:src/eval.py:73-116."""
+    _require_cuda(tensor6)
+    lib = _lib.load()
+    t = tensor6.contiguous().float()
+    if t.shape[-1] != 6:
+        raise RuntimeError("dti_scalar_maps expects the 6 unique tensor components in the last dimension")
+    shape = t.shape[:-1]
+    out = {k: torch.empty(shape, dtype=torch.float32, device=t.device) for k in ("fa", "md", "ad", "rd", "azimuth", "inclination")}
+    out["rgb"] = torch.empty(tuple(shape) + (3,), dtype=torch.float32, device=t.device)
+    _lib.check(lib.ub_dti_scalar_maps(_p(t), t.numel() // 6, _p(out["fa"]), _p(out["md"]), _p(out["ad"]), _p(out["rd"]),
+                                      _p(out["azimuth"]), _p(out["inclination"]), _p(out["rgb"]), _stream()),
+               "ub_dti_scalar_maps")
+    return out
