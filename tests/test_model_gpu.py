@@ -221,6 +221,47 @@ def test_full_step_runs_and_updates_both_networks():
     assert all(p.requires_grad for p in list(g.parameters()) + list(d.parameters()))
 
 
+@pytest.mark.parametrize("fused", [True, False])
+def test_updated_weights_are_used_after_optimizer_steps(fused):
+    """The bf16 operand copies of the weights must follow the fp32 Parameters through optimizer steps.
+    torch's fused AdamW writes parameters without bumping ``tensor._version`` (regression: the packed
+    weights stayed at their initial values): after two full steps the modules must agree with an oracle
+    that is loaded with the UPDATED state dict -- and disagree with the initial-weight output."""
+    strict_fp32()
+    O, og, od, g, d = _pair("bssfp")
+    from unet_bssfp_b200.train_step import GanTrainer
+    tr = GanTrainer(g, d, lr=2e-2, fused_optimizer=fused)
+    torch.manual_seed(3)
+    x = torch.rand(1, 24, 32, 32, 32, device=DEV)
+    y = torch.rand(1, 6, 32, 32, 32, device=DEV)
+    g.eval()
+    with torch.no_grad():
+        before = g(x).clone()
+        logit_before = d(x, y).clone()
+    g.train()
+    for _ in range(2):
+        tr.step(x, y)
+    og.load_state_dict(g.state_dict())
+    od.load_state_dict(d.state_dict())
+    g.eval(); og.eval(); d.eval(); od.eval()
+    with torch.no_grad():
+        after, ref = g(x), og(x)
+        logit_after, logit_ref = d(x, y), od(x, y)
+    assert rel_l2(after, ref) < 3e-2, rel_l2(after, ref)                     # follows the updated weights
+    assert rel_l2(after, before) > 10 * rel_l2(after, ref)                    # ... and they did change the output
+    assert rel_l2(logit_after, logit_ref) < 3e-2
+    assert rel_l2(logit_after, logit_before) > 5 * rel_l2(logit_after, logit_ref)
+    # writes behind torch's back need the explicit invalidation
+    import unet_bssfp_b200 as ub
+    with torch.no_grad():
+        w = g.blocks["unet"].final_conv.weight
+        w.data_ptr()
+        torch.cuda.current_stream().synchronize()
+        w.detach().view(-1)[:].mul_(0.0)                                      # in-place: bumps _version, no call needed
+        assert g(x).abs().max().item() <= g.blocks["unet"].final_conv.bias.abs().max().item() + 1e-6
+    ub.invalidate_packed_weights(g)
+
+
 def test_shape_errors():
     import unet_bssfp_b200 as ub
     g, d = ub.Generator("t1w").to(DEV), ub.Discriminator("t1w").to(DEV)

@@ -29,16 +29,58 @@ UNET_FEATURES = (32, 64, 128, 256, 512, 32)
 
 
 # ---------------------------------------------------------------------------------------------------
-# packed-weight cache: bf16 operand copies of the fp32 Parameters, refreshed when the optimiser
-# (in-place update => tensor._version bump) or load_state_dict changes them
+# packed-weight cache: bf16 operand copies of the fp32 Parameters, refreshed whenever the parameter may
+# have changed:
+#   * in-place autograd-visible writes (manual updates, load_state_dict, foreach optimizers) bump
+#     ``tensor._version``;
+#   * torch's FUSED optimizers (``AdamW(fused=True)``, what GanTrainer and Lightning's configure_optimizers
+#     would use on CUDA) write the parameters from a multi-tensor kernel WITHOUT bumping ``_version``, so
+#     a process-wide optimizer post-step hook stamps every parameter the optimizer owns with a new
+#     generation number;
+#   * ``.data`` / device moves change ``data_ptr``.
 # ---------------------------------------------------------------------------------------------------
+_param_generation = {}      # id(param) -> generation of the last optimizer step that owned it
+_generation_counter = [0]
+
+
+def _optimizer_post_step(optimizer, args, kwargs):
+    _generation_counter[0] += 1
+    g = _generation_counter[0]
+    for group in optimizer.param_groups:
+        for p in group["params"]:
+            _param_generation[id(p)] = g
+
+
+from torch.optim.optimizer import register_optimizer_step_post_hook as _register_post_step  # noqa: E402
+
+_register_post_step(_optimizer_post_step)
+
+
+def invalidate_packed_weights(module: nn.Module | None = None):
+    """Force a re-pack of the bf16 weight operands: of ``module``'s parameters, or of everything.
+    Needed only after writing parameter memory behind autograd's and torch.optim's back (a custom
+    kernel, ``cudaMemcpy`` into ``param.data_ptr()``)."""
+    _generation_counter[0] += 1
+    g = _generation_counter[0]
+    if module is None:
+        for k in list(_param_generation):
+            _param_generation[k] = g
+        _PackedWeights.global_floor = g
+    else:
+        for p in module.parameters():
+            _param_generation[id(p)] = g
+
+
 class _PackedWeights:
+    global_floor = 0
+
     def __init__(self):
         self._cache = {}
 
     def get(self, spec, weight, direction):
         key = (id(weight), direction)
-        ver = (weight._version, weight.data_ptr(), weight.device)
+        ver = (weight._version, weight.data_ptr(), weight.device,
+               max(_param_generation.get(id(weight), 0), _PackedWeights.global_floor))
         hit = self._cache.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
