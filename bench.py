@@ -156,9 +156,14 @@ def dominant_kernel_roofline(dev, batch, size, peaks, iters=5):
     ms = statistics.median(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
     flops = 2.0 * batch * size ** 3 * 27 * 96 * 32
     ach = flops / (ms * 1e-3) / 1e12
+    # DRAM traffic of this launch from the committed `ncu --set full` capture (profiles/r01m_march96_ncu_summary.txt):
+    # dram__bytes_read.sum 3.262 GB + dram__bytes_write.sum 1.055 GB; algorithmic bytes = both sources once +
+    # the output once = (32 + 64 + 32) ch * 2 B * 8 * 128^3 voxels = 4.295 GB
+    traffic = 3.262496e9 + 1.054787e9 if (batch, size) == (8, 128) else None
     return {"bound": "tensor", "kernel": "igemm_march_kernel[upcat_1.conv_0 fwd, cat[32|64]->32 k3, 8x128^3]", "achieved": ach,
             "peak": peaks["bf16_burst"], "peak_src": peaks["src"] + " (burst: kernel timed alone)", "unit": "TFLOP/s",
-            "frac": ach / peaks["bf16_burst"], "ms_per_launch": ms, "flops_per_launch": flops, "traffic": None}
+            "frac": ach / peaks["bf16_burst"], "ms_per_launch": ms, "flops_per_launch": flops, "traffic": traffic,
+            "traffic_unit": "bytes per launch (ncu dram read + write)", "algorithmic_bytes": 2.0 * batch * size ** 3 * 128}
 
 
 def main():
@@ -286,7 +291,7 @@ def main():
         flop_step = FLOP_PER_VOXEL[args.modality] * B * S ** 3
         roof["step_tflops"] = flop_step / (ms_step * 1e-3) / 1e12
         roof["step_frac_of_sustained_peak"] = roof["step_tflops"] / peaks["bf16_sustained"]
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported at N = 1 only (torchrun pins OMP_NUM_THREADS=1)
             v, ms, cores = cpu_reference_run(steps=2, warmup=1, size=64, modality=args.modality)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
                    "sample": f"full GAN step, batch 1 x 64^3 ({args.modality}), fp32 torch CPU oracle, 2 timed steps after 1 warm-up"}
