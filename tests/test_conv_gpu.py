@@ -40,6 +40,8 @@ CASES = [
     (0, 32, 0, 64, (1, 9, 24, 16)),      # dgrad on the marching kernel with K = 64
     (0, 64, 0, 32, (2, 11, 16, 24)),     # forward on the marching kernel with two K chunks of one source
     (0, 32, 64, 32, (1, 5, 16, 8)),      # skip concat [32 | 64] as two sources, split dgrad destinations
+    (0, 32, 64, 32, (2, 7, 32, 32)),     # marching kernel on CTA pairs (cta_group::2): 4 w tiles, 3 K chunks, two sources
+    (0, 64, 0, 32, (1, 12, 16, 16)),     # CTA pairs, two K chunks, two d segments
     (0, 128, 0, 256, (1, 4, 8, 8)),      # several N tiles, plane smaller than the 16x8 tile
     (0, 256, 256, 256, (1, 2, 4, 4)),
     (1, 24, 0, 24, (2, 4, 16, 8)),

@@ -24,7 +24,7 @@ namespace ub {
 
 struct MarchParams {
   CUtensorMap tm_src[2];
-  CUtensorMap tm_w;                 // [9 * 96][Kpad] bf16, box (32, 96)
+  CUtensorMap tm_w;                 // [9 * 96][Kpad] bf16, box (32, 96); pair mode: box (32, 48)
   int n_chunks_src0, n_chunks_total;
   int Nb, D, H, W;
   int tiles_w, tiles_h, nseg, seg_len;
@@ -53,7 +53,13 @@ constexpr int kMarchRing = 5;       // TMEM accumulator ring: 5 x 96 columns
 constexpr int kMarchEpiWarps = 8;
 constexpr int kMarchThreads = (kMarchEpiWarps + 2) * 32;   // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
 
-template <bool kNormBwd>
+// kPair: two CTAs of a cluster (cta_group::2) own two neighbouring 16x8 columns and march together; every
+// UMMA is M = 256 x N = 96 with the 96 weight rows split 48 / 48 between the two CTAs' shared memories,
+// so each SM reads 4 KB (A) + 1.5 KB (B) per instruction instead of 4 + 3 KB -- the shared-memory pipe is
+// what bounds the single-CTA kernel (ncu: 81 % l1tex data-pipe, 69 % tensor-pipe active). The leader
+// (rank 0) issues the MMAs and owns w_full / a_full / acc_empty; the peer's TMA loads and epilogue arrive
+// on them remotely; tcgen05.commit multicasts a_empty / acc_full to both CTAs.
+template <bool kNormBwd, bool kPair>
 __global__ void __launch_bounds__(kMarchThreads, 1)
 igemm_march_kernel(const __grid_constant__ MarchParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -61,9 +67,11 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = P.n_chunks_total;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  constexpr int kWTile = kPair ? kMarchWTileBytes / 2 : kMarchWTileBytes;   // this CTA's share of a weight tile
 
   const uint32_t w_base = base;
-  const uint32_t a_base = w_base + nch * 9 * kMarchWTileBytes;
+  const uint32_t a_base = w_base + nch * 9 * kWTile;
   const uint32_t bar_base = a_base + P.nsa * kMarchPlaneBytes;
   // barriers: w_full | a_full[nsa] | a_empty[nsa] | acc_full[ring] | acc_empty[ring]
   const uint32_t w_full = bar_base, a_full = w_full + 8, a_empty = a_full + 8 * P.nsa,
@@ -71,12 +79,14 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (acc_empty + 8 * kMarchRing - base));
   float* red = reinterpret_cast<float*>(sm + (((acc_empty + 8 * kMarchRing + 16 + 15) & ~15u) - base));  // [8][2][32] + bias[32] + consts[4][32], 16-B aligned
 
-  // ---- work item: (n, h tile, w tile, d segment)
-  int t = blockIdx.x;
+  // ---- work item: (n, h tile, w tile, d segment); a CTA pair takes the w tiles 2k and 2k+1
+  int t = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int seg = t % P.nseg; t /= P.nseg;
-  const int tw_i = t % P.tiles_w; t /= P.tiles_w;
+  const int tiles_wp = kPair ? P.tiles_w / 2 : P.tiles_w;
+  const int tw_i = kPair ? (t % tiles_wp) * 2 + (int)rank : t % tiles_wp; t /= tiles_wp;
   const int th_i = t % P.tiles_h; t /= P.tiles_h;
   const int nb = t;
+  const int item = ((nb * P.tiles_h + th_i) * P.tiles_w + tw_i) * P.nseg + seg;   // statistics record
   const int w0 = tw_i * 8, h0 = th_i * 16;
   const int d_begin = seg * P.seg_len;
   int d_end = d_begin + P.seg_len; if (d_end > P.D) d_end = P.D;
@@ -86,7 +96,10 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
     for (int i = 0; i < P.nsa; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
-    for (int i = 0; i < kMarchRing; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, kMarchEpiWarps); }
+    for (int i = 0; i < kMarchRing; ++i) {
+      mbar_init(acc_full + 8 * i, 1);
+      mbar_init(acc_empty + 8 * i, kPair ? 2 * kMarchEpiWarps : kMarchEpiWarps);
+    }
     fence_mbar_init();
   }
   if (warp == kMarchEpiWarps && lane == 0) {
@@ -94,73 +107,99 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
     if (nch > P.n_chunks_src0) tma_prefetch_desc(&P.tm_src[1]);
     tma_prefetch_desc(&P.tm_w);
   }
-  if (warp == kMarchEpiWarps + 1) tmem_alloc_rt(smem_u32(tmem_slot), 512);
+  if (warp == kMarchEpiWarps + 1) {
+    if (kPair) tmem_alloc_pair(smem_u32(tmem_slot), 512);
+    else tmem_alloc_rt(smem_u32(tmem_slot), 512);
+  }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // barriers that live in the leader CTA, as shared::cluster addresses usable from both CTAs
+  const uint32_t w_full_ld = kPair ? mapa_shared(w_full, 0) : w_full;
+  const uint32_t a_full_ld = kPair ? mapa_shared(a_full, 0) : a_full;
+  const uint32_t acc_empty_ld = kPair ? mapa_shared(acc_empty, 0) : acc_empty;
 
   if (warp == kMarchEpiWarps) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      mbar_expect_tx(w_full, (uint32_t)(nch * 9 * kMarchWTileBytes));
+      const uint32_t w_bytes = (uint32_t)(nch * 9 * kWTile);
+      if (rank == 0) mbar_expect_tx(w_full, kPair ? 2 * w_bytes : w_bytes);
       for (int c = 0; c < nch; ++c)
-        for (int tp = 0; tp < 9; ++tp)
-          tma_load_2d(w_base + (c * 9 + tp) * kMarchWTileBytes, &P.tm_w, w_full, c * 32, tp * 96);
+        for (int tp = 0; tp < 9; ++tp) {
+          if (kPair) tma_load_2d_pair(w_base + (c * 9 + tp) * kWTile, &P.tm_w, w_full_ld, c * 32, tp * 96 + (int)rank * 48);
+          else tma_load_2d(w_base + (c * 9 + tp) * kWTile, &P.tm_w, w_full, c * 32, tp * 96);
+        }
       int sa = 0;
       uint32_t pa = 0;
       for (int p = p_first; p <= p_last; ++p) {
         for (int c = 0; c < nch; ++c) {
           mbar_wait(a_empty + 8 * sa, pa ^ 1);
-          mbar_expect_tx(a_full + 8 * sa, 180 * 64);
+          if (rank == 0) mbar_expect_tx(a_full + 8 * sa, kPair ? 2 * 180 * 64 : 180 * 64);
           const bool s1 = c >= P.n_chunks_src0;
-          tma_load_5d(a_base + sa * kMarchPlaneBytes, &P.tm_src[s1 ? 1 : 0], a_full + 8 * sa,
-                      (s1 ? c - P.n_chunks_src0 : c) * 32, w0 - 1, h0 - 1, p, nb);
+          if (kPair)
+            tma_load_5d_pair(a_base + sa * kMarchPlaneBytes, &P.tm_src[s1 ? 1 : 0], a_full_ld + 8 * sa,
+                             (s1 ? c - P.n_chunks_src0 : c) * 32, w0 - 1, h0 - 1, p, nb);
+          else
+            tma_load_5d(a_base + sa * kMarchPlaneBytes, &P.tm_src[s1 ? 1 : 0], a_full + 8 * sa,
+                        (s1 ? c - P.n_chunks_src0 : c) * 32, w0 - 1, h0 - 1, p, nb);
           if (++sa == P.nsa) { sa = 0; pa ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == kMarchEpiWarps + 1) {
-    // =========================== MMA issuer ===========================
-    const uint32_t idesc = make_idesc_bf16(128, 96, 0, 0);
-    const uint32_t a_hi = (uint32_t)(make_smem_desc(0, 16, 10 * 64, SWZ_64B) >> 32);
-    const uint32_t b_hi = (uint32_t)(make_smem_desc(0, 16, 8 * 64, SWZ_64B) >> 32);
-    const uint32_t lbo_lo = 1u << 16;
-    const bool leader = elect_one();
-    mbar_wait(w_full, 0);
-    tc_fence_after();
-    int sa = 0;
-    uint32_t pa = 0;
-    int slot = 0;
-    uint32_t pacc = 0;
-    for (int p = p_first; p <= p_last; ++p) {
-      mbar_wait(acc_empty + 8 * slot, pacc ^ 1);
+    // =========================== MMA issuer (leader CTA only in pair mode) ===========================
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(kPair ? 256 : 128, 96, 0, 0);
+      const uint32_t a_hi = (uint32_t)(make_smem_desc(0, 16, 10 * 64, SWZ_64B) >> 32);
+      const uint32_t b_hi = (uint32_t)(make_smem_desc(0, 16, 8 * 64, SWZ_64B) >> 32);
+      const uint32_t lbo_lo = 1u << 16;
+      const bool leader = elect_one();
+      mbar_wait(w_full, 0);
       tc_fence_after();
-      const uint32_t acc = tmem + slot * 96;
-      for (int c = 0; c < nch; ++c) {
-        mbar_wait(a_full + 8 * sa, pa);
+      int sa = 0;
+      uint32_t pa = 0;
+      int slot = 0;
+      uint32_t pacc = 0;
+      for (int p = p_first; p <= p_last; ++p) {
+        mbar_wait(acc_empty + 8 * slot, pacc ^ 1);
         tc_fence_after();
+        const uint32_t acc = tmem + slot * 96;
+        for (int c = 0; c < nch; ++c) {
+          mbar_wait(a_full + 8 * sa, pa);
+          tc_fence_after();
+          if (leader) {
+            const uint32_t a_lo = lbo_lo | ((a_base + sa * kMarchPlaneBytes) >> 4);
+            const uint32_t b_lo = lbo_lo | ((w_base + c * 9 * kWTile) >> 4);
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                const uint32_t ao = (uint32_t)((kh * 10 + kw) * 64) >> 4;
+                const uint32_t bo = (uint32_t)((kh * 3 + kw) * kWTile) >> 4;
+                if (kPair) {
+                  umma_bf16_lohi_pair(acc, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc, (uint32_t)((c | kh | kw) != 0));
+                  umma_bf16_lohi_pair(acc, a_lo + ao + 2, a_hi, b_lo + bo + 2, b_hi, idesc, 1u);
+                } else {
+                  umma_bf16_lohi(acc, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc, (uint32_t)((c | kh | kw) != 0));
+                  umma_bf16_lohi(acc, a_lo + ao + 2, a_hi, b_lo + bo + 2, b_hi, idesc, 1u);
+                }
+              }
+            if (kPair) umma_commit_pair(a_empty + 8 * sa);
+            else umma_commit(a_empty + 8 * sa);
+          }
+          __syncwarp();
+          if (++sa == P.nsa) { sa = 0; pa ^= 1; }
+        }
         if (leader) {
-          const uint32_t a_lo = lbo_lo | ((a_base + sa * kMarchPlaneBytes) >> 4);
-          const uint32_t b_lo = lbo_lo | ((w_base + c * 9 * kMarchWTileBytes) >> 4);
-#pragma unroll
-          for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-              const uint32_t ao = (uint32_t)((kh * 10 + kw) * 64) >> 4;
-              const uint32_t bo = (uint32_t)((kh * 3 + kw) * kMarchWTileBytes) >> 4;
-              umma_bf16_lohi(acc, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc, (uint32_t)((c | kh | kw) != 0));
-              umma_bf16_lohi(acc, a_lo + ao + 2, a_hi, b_lo + bo + 2, b_hi, idesc, 1u);
-            }
-          umma_commit(a_empty + 8 * sa);
+          if (kPair) umma_commit_pair(acc_full + 8 * slot);
+          else umma_commit(acc_full + 8 * slot);
         }
         __syncwarp();
-        if (++sa == P.nsa) { sa = 0; pa ^= 1; }
+        if (++slot == kMarchRing) { slot = 0; pacc ^= 1; }
       }
-      if (leader) umma_commit(acc_full + 8 * slot);
-      __syncwarp();
-      if (++slot == kMarchRing) { slot = 0; pacc ^= 1; }
     }
   } else {
     // =========================== epilogue (warps 0-7) ===========================
@@ -236,8 +275,14 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(acc_empty + 8 * ((d - p_first) % kMarchRing));
-        if (d - 1 >= p_first) mbar_arrive_n(acc_empty + 8 * ((d - 1 - p_first) % kMarchRing), d == d_begin ? 2u : 1u);
+        if (kPair) {
+          mbar_arrive_cluster(acc_empty_ld + 8 * ((d - p_first) % kMarchRing), 1u);
+          if (d - 1 >= p_first)
+            mbar_arrive_cluster(acc_empty_ld + 8 * ((d - 1 - p_first) % kMarchRing), d == d_begin ? 2u : 1u);
+        } else {
+          mbar_arrive(acc_empty + 8 * ((d - p_first) % kMarchRing));
+          if (d - 1 >= p_first) mbar_arrive_n(acc_empty + 8 * ((d - 1 - p_first) % kMarchRing), d == d_begin ? 2u : 1u);
+        }
       }
       uint32_t pk[16];
       const float4* b4 = reinterpret_cast<const float4*>(bias_s);
@@ -329,7 +374,7 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
         float s = 0.f, qq = 0.f;
 #pragma unroll
         for (int wq = 0; wq < kMarchEpiWarps; ++wq) { s += red[(wq * 2 + 0) * 32 + lane]; qq += red[(wq * 2 + 1) * 32 + lane]; }
-        float* st = P.stats + (size_t)blockIdx.x * 64;
+        float* st = P.stats + (size_t)item * 64;
         st[lane] = s;
         st[32 + lane] = qq;
       }
@@ -337,7 +382,11 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kMarchEpiWarps + 1) tmem_dealloc_rt(tmem, 512);
+  if (kPair) cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the other may still signal it
+  if (warp == kMarchEpiWarps + 1) {
+    if (kPair) tmem_dealloc_pair(tmem, 512);
+    else tmem_dealloc_rt(tmem, 512);
+  }
 }
 
 }  // namespace ub

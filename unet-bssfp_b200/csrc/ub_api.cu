@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <atomic>
 #include "../../include/ub_api.h"
@@ -321,7 +322,13 @@ static int launch_march(const void* src0, int c0p, const void* src1, int c1p, in
   P.Nb = n; P.D = D; P.H = H; P.W = W;
   march_geometry(n, D, H, W, &P.tiles_w, &P.tiles_h, &P.nseg, &P.seg_len);
   P.out = out; P.bias = bias; P.bias_n = bias_n; P.stats = stats;
-  const int wbytes = P.n_chunks_total * 9 * kMarchWTileBytes;
+  // CTA pairs (cta_group::2) whenever the w tiles pair up; UB_MARCH_PAIR=0 forces the single-CTA kernel
+  static const bool pair_enabled = !(getenv("UB_MARCH_PAIR") && atoi(getenv("UB_MARCH_PAIR")) == 0);
+  // (a plane must be long enough to hide the cross-CTA accumulator hand-off: measured on B200 at 8x128^3,
+  // 1 K chunk 854 vs 1183 TFLOP/s single-CTA, 2 chunks 1324 vs 1330, 3 chunks 1538 vs 1360)
+  static const int pair_min_chunks = getenv("UB_MARCH_PAIR_MIN_CHUNKS") ? atoi(getenv("UB_MARCH_PAIR_MIN_CHUNKS")) : 3;
+  const bool pair = pair_enabled && (P.tiles_w % 2 == 0) && P.n_chunks_total >= pair_min_chunks;
+  const int wbytes = P.n_chunks_total * 9 * (pair ? kMarchWTileBytes / 2 : kMarchWTileBytes);
   const int misc = 8 * 32 + 64 + (kMarchEpiWarps * 2 * 32 + 32 + 128) * 4 + 64 + 1024;
   P.nsa = (220 * 1024 - wbytes - misc) / kMarchPlaneBytes;
   if (P.nsa > 8) P.nsa = 8;
@@ -330,18 +337,38 @@ static int launch_march(const void* src0, int c0p, const void* src1, int c1p, in
   if (int e = make_act_map(&P.tm_src[0], src0, c0p, W, H, D, n, 32, 10, 18, 1)) return e;
   if (c1p)
     if (int e = make_act_map(&P.tm_src[1], src1, c1p, W, H, D, n, 32, 10, 18, 1)) return e;
-  if (int e = make_w_map(&P.tm_w, w_packed, c0p + c1p, 9 * 96, 32, 96)) return e;
+  if (int e = make_w_map(&P.tm_w, w_packed, c0p + c1p, 9 * 96, 32, pair ? 48 : 96)) return e;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(igemm_march_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(igemm_march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    const void* fns[4] = {(const void*)igemm_march_kernel<false, false>, (const void*)igemm_march_kernel<true, false>,
+                          (const void*)igemm_march_kernel<false, true>, (const void*)igemm_march_kernel<true, true>};
+    for (int i = 0; i < 4 && attr_err == cudaSuccess; ++i)
+      attr_err = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) return fail(-3, "cudaFuncSetAttribute(igemm_march): %s", cudaGetErrorString(attr_err));
   const unsigned grid = (unsigned)(n * P.tiles_h * P.tiles_w * P.nseg);
-  if (fuse) igemm_march_kernel<true><<<grid, kMarchThreads, smem, st>>>(P);
-  else igemm_march_kernel<false><<<grid, kMarchThreads, smem, st>>>(P);
+  if (pair) {
+    // cluster of two CTAs along x: blocks (2k, 2k+1) take the w tiles (2j, 2j+1) of one column pair
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(kMarchThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = fuse ? cudaLaunchKernelEx(&cfg, igemm_march_kernel<true, true>, P)
+                          : cudaLaunchKernelEx(&cfg, igemm_march_kernel<false, true>, P);
+    if (le != cudaSuccess) return fail(-3, "cluster launch of igemm_march failed: %s", cudaGetErrorString(le));
+  } else if (fuse) {
+    igemm_march_kernel<true, false><<<grid, kMarchThreads, smem, st>>>(P);
+  } else {
+    igemm_march_kernel<false, false><<<grid, kMarchThreads, smem, st>>>(P);
+  }
   UB_LAUNCH_CHECK();
   return 0;
 }
