@@ -763,17 +763,20 @@ static int plan_wgrad(const ub_conv_desc* d, WgradPlan* pl) {
 // The marching wgrad kernel works on (32 ci x 32 co) blocks; it serves the 3x3x3 layers whose planes
 // fill the 16x8 voxel tile reasonably (the deep, tiny-plane layers stay on the generic kernel).
 static bool use_wgrad_march(const ub_conv_desc* d) {
+  if (d->kind == UB_CONV_K4S2P1_S2D)      // the stem: 2x2x2-tap conv per input parity on the half-resolution grid
+    return d->h >= 32 && d->w >= 16 && (long long)d->c0p * d->cop <= 64 * 64;
   return d->kind == UB_CONV_K3S1P1 && d->h >= 16 && d->w >= 8 && (long long)(d->c0p + d->c1p) * d->cop <= 128 * 256;
 }
 static int wgrad_march_splits(const ub_conv_desc* d) {
-  const int cols = (d->c0p + d->c1p) / 32 * (d->cop / 32);
+  int cols = (d->c0p + d->c1p) / 32 * (d->cop / 32);
+  if (d->kind == UB_CONV_K4S2P1_S2D) cols *= 8;
   int ns = sm_count() / cols;
   return ns < 1 ? 1 : ns;
 }
 
 extern "C" long long ub_conv_wgrad_workspace_bytes(const ub_conv_desc* d) {
   if (check_desc(d)) return -1;
-  if (use_wgrad_march(d)) return (long long)wgrad_march_splits(d) * 27 * (d->c0p + d->c1p) * d->cop * 4;
+  if (use_wgrad_march(d)) return (long long)wgrad_march_splits(d) * ntaps_of(d->kind) * (d->c0p + d->c1p) * d->cop * 4;
   WgradPlan pl;
   if (plan_wgrad(d, &pl)) return -1;
   return (long long)pl.grid.x * pl.ntap_lin * pl.P.ci_total * pl.P.co_total * 4;
@@ -787,39 +790,50 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
   if (d->c1p && !src1) return fail(-1, "second source missing");
   cudaStream_t st = (cudaStream_t)stream;
   if (use_wgrad_march(d)) {
+    const bool stem = d->kind == UB_CONV_K4S2P1_S2D;
+    const int kt = stem ? 2 : 3;
+    // the grid the reduction runs over: the dY grid (stem: half resolution)
+    const int gd = stem ? d->d / 2 : d->d, gh = stem ? d->h / 2 : d->h, gw = stem ? d->w / 2 : d->w;
+    const int ntap = ntaps_of(d->kind);
     WgradMarchParams M;
     memset(&M, 0, sizeof(M));
     M.n_chunks_src0 = d->c0p / 32;
     M.n_chunks_total = (d->c0p + d->c1p) / 32;
-    M.Nb = d->n; M.D = d->d; M.H = d->h; M.W = d->w;
-    march_geometry(d->n, d->d, d->h, d->w, &M.tiles_w, &M.tiles_h, &M.nseg, &M.seg_len);
+    M.Nb = d->n; M.D = gd; M.H = gh; M.W = gw;
+    march_geometry(d->n, gd, gh, gw, &M.tiles_w, &M.tiles_h, &M.nseg, &M.seg_len);
     M.ci_total = d->c0p + d->c1p;
     M.co_total = d->cop;
     M.n_cotiles = d->cop / 32;
+    M.ntaps = ntap;
     M.partial = reinterpret_cast<float*>(workspace);
-    if (int e = make_act_map(&M.tm_x[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, 10, 18, 1)) return e;
+    const int bw = 8 + kt - 1, bh = 16 + kt - 1;
+    if (int e = make_act_map(&M.tm_x[0], src0, d->c0p, gw, gh, gd, stem ? d->n * 8 : d->n, 32, bw, bh, 1)) return e;
     if (d->c1p)
-      if (int e = make_act_map(&M.tm_x[1], src1, d->c1p, d->w, d->h, d->d, d->n, 32, 10, 18, 1)) return e;
-    if (int e = make_act_map(&M.tm_dy, dy, d->cop, d->w, d->h, d->d, d->n, 32, 8, 16, 1)) return e;
+      if (int e = make_act_map(&M.tm_x[1], src1, d->c1p, gw, gh, gd, d->n, 32, bw, bh, 1)) return e;
+    if (int e = make_act_map(&M.tm_dy, dy, d->cop, gw, gh, gd, d->n, 32, 8, 16, 1)) return e;
     static std::once_flag once_m;
     static cudaError_t attr_err_m = cudaSuccess;
     std::call_once(once_m, [] {
-      attr_err_m = cudaFuncSetAttribute(wgrad_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      attr_err_m = cudaFuncSetAttribute(wgrad_march_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (attr_err_m == cudaSuccess)
+        attr_err_m = cudaFuncSetAttribute(wgrad_march_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err_m != cudaSuccess) return fail(-3, "cudaFuncSetAttribute(wgrad_march): %s", cudaGetErrorString(attr_err_m));
     const int nsplit = wgrad_march_splits(d);
-    const int smem = kWmXStages * kWmXBytes + (kWmYSlots + 2) * kWmYBytes + 8 * 32 + 64 + 1024;
-    wgrad_march_kernel<<<dim3((unsigned)nsplit, (unsigned)(M.n_chunks_total * M.n_cotiles)), kIgemmThreads, smem, st>>>(M);
+    const int smem = kWmXStages * kWmXBytes + (kWmYSlots + kt - 1) * kWmYBytes + 8 * 32 + 64 + 1024;
+    const dim3 grid((unsigned)nsplit, (unsigned)(M.n_chunks_total * M.n_cotiles * (stem ? 8 : 1)));
+    if (stem) wgrad_march_kernel<2><<<grid, kIgemmThreads, smem, st>>>(M);
+    else wgrad_march_kernel<3><<<grid, kIgemmThreads, smem, st>>>(M);
     UB_LAUNCH_CHECK();
     WgradReduceArgs R;
     memset(&R, 0, sizeof(R));
     const int ci = d->c0 + d->c1;
-    R.nsplit = nsplit; R.ntap = 27; R.ci_total = M.ci_total; R.co_total = d->cop; R.ci = ci; R.co = d->co;
-    R.stride_ci = 27; R.stride_co = (long long)ci * 27; R.dst_tap_stride = 1;
+    R.nsplit = nsplit; R.ntap = ntap; R.ci_total = M.ci_total; R.co_total = d->cop; R.ci = ci; R.co = d->co;
+    R.stride_ci = ntap; R.stride_co = (long long)ci * ntap; R.dst_tap_stride = 1;
     R.split_pad = d->c1p ? d->c0p : 0;
     R.split_real = d->c1p ? d->c0 : 0;
-    for (int i = 0; i < 64; ++i) R.tapmap[i] = i < 27 ? i : -1;
-    const long long per_split = 27ll * R.ci_total * d->cop;
+    for (int i = 0; i < 64; ++i) R.tapmap[i] = i < ntap ? i : -1;
+    const long long per_split = (long long)ntap * R.ci_total * d->cop;
     wgrad_reduce_kernel<<<(unsigned)((per_split + 255) / 256), 256, 0, st>>>(M.partial, dw, R);
     UB_LAUNCH_CHECK();
     return 0;

@@ -1,56 +1,70 @@
-// Marching-plane weight gradient for the 3x3x3 convs, one (32 input channels x 32 output channels)
-// block per CTA column: dW[kd,kh,kw][ci][co] = sum_v X[v + (kd,kh,kw) - 1][ci] * dY[v][co].
+// Marching-plane weight gradient, one (32 input channels x 32 output channels) block per CTA column:
+//   KT = 3: 3x3x3 s1 p1 convs            dW[kd,kh,kw][ci][co] = sum_v X[v + (kd,kh,kw) - 1][ci] * dY[v][co]
+//   KT = 2: the 4x4x4 s2 p1 PatchGAN stem on its parity-planar space-to-depth source: for input parity
+//           (pd,ph,pw) the conv is a 2x2x2-tap conv on the half-resolution grid,
+//           dW[2s+1-p][ci][co] = sum_o X2[o + s + (p ? -1 : 0)][parity p][ci] * dY[o][co],   s in {0,1}^3.
 //
-// igemm_wgrad_kernel handles one kd per CTA with N = C_out = 32 (smem-bound UMMA, X planes loaded three
-// times). Here the depth taps are folded into N by shifting dY instead of X: for one X plane p,
+// igemm_wgrad_kernel handles one depth tap per CTA with N = 32 (smem-bound UMMA, X planes re-loaded per
+// tap). Here the depth taps are folded into N by shifting dY instead of X: for one X plane p,
 //
-//     D[kh][(kw, ci)][(j, co)] += sum_{h,w} X[p, h+kh-1, w+kw-1, ci] * dY[p - 1 + j, h, w, co],   kd = 2 - j
+//     D[kh][(kw, ci)][(j, co)] += sum_{h,w} X[p, h+kh, w+kw, ci] * dY[p + doff + j, h, w, co],   depth tap = KT-1-j
 //
-// so ONE UMMA (M = 128 = 4 kw-atoms x 32 ci, N = 96 = 3 dY planes x 32 co, K = 16 voxels) covers nine
-// taps. Both operands are MN-major views of the tiles exactly as TMA delivered them:
+// so ONE UMMA (M = 128 = 4 kw-atoms x 32 ci, N = KT*32 = KT dY planes x 32 co, K = 16 voxels) covers
+// KT*KT taps. Both operands are MN-major views of the tiles exactly as TMA delivered them:
 //   A atoms (kw) are one halo row apart (LBO = 64 B), B atoms (j) are one dY plane apart
-//   (LBO = 8 KB): the dY planes live in a ring whose first two slots are mirrored behind the last so
-//   that three consecutive planes are always contiguous. Planes -1 and D are out-of-bounds TMA loads
-//   (zero fill) -- the conv padding in depth.
-// A CTA marches along d through its share of (n, h-tile, w-tile, d-segment) items and keeps the three
-// kh accumulators (3 x 96 TMEM columns) for its whole lifetime (split-K over CTAs), then writes one
-// fp32 partial record [27][32 ci][32 co]; wgrad_reduce_kernel sums the records in a fixed order.
+//   (LBO = 8 KB): the dY planes live in a ring whose first KT-1 slots are mirrored behind the last so
+//   that KT consecutive planes are always contiguous. Out-of-range dY planes are out-of-bounds TMA
+//   loads (zero fill) -- the conv padding in depth.
+// A CTA marches along d through its share of (n, h-tile, w-tile, d-segment) items and keeps the KT
+// kh accumulators (KT x KT*32 TMEM columns) for its whole lifetime (split-K over CTAs), then writes one
+// fp32 partial record; wgrad_reduce_kernel sums the records in a fixed order.
 #pragma once
 #include "igemm_fwd.cuh"
 
 namespace ub {
 
 struct WgradMarchParams {
-  CUtensorMap tm_x[2];      // box (32, 10, 18, 1, 1)
+  CUtensorMap tm_x[2];      // box (32, 8+KT-1, 16+KT-1, 1, 1)
   CUtensorMap tm_dy;        // box (32, 8, 16, 1, 1)
   int n_chunks_src0, n_chunks_total;
-  int Nb, D, H, W;
+  int Nb, D, H, W;          // the dY grid (KT = 2: the half-resolution output grid)
   int tiles_w, tiles_h, nseg, seg_len;
   int ci_total;             // padded input channels (partial pitch)
   int co_total, n_cotiles;  // padded output channels, co_total / 32
-  float* partial;           // [gridDim.x][27][ci_total][co_total]
+  int ntaps;                // taps of the partial record (27 / 64)
+  float* partial;           // [gridDim.x][ntaps][ci_total][co_total]
 };
 
 constexpr int kWmXStages = 4, kWmXBytes = 12288;
-constexpr int kWmYSlots = 8, kWmYBytes = 8192;   // + 2 mirror slots
+constexpr int kWmYSlots = 8, kWmYBytes = 8192;   // + KT-1 mirror slots
 
+template <int KT>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
+  constexpr int BW = 8 + KT - 1, BH = 16 + KT - 1;     // halo box
+  constexpr int NN = KT * 32;                          // UMMA N
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t x_base = base;
   const uint32_t y_base = x_base + kWmXStages * kWmXBytes;
-  const uint32_t bar_base = y_base + (kWmYSlots + 2) * kWmYBytes;
+  const uint32_t bar_base = y_base + (kWmYSlots + KT - 1) * kWmYBytes;
   const uint32_t x_full = bar_base, x_empty = x_full + 8 * kWmXStages, y_full = x_empty + 8 * kWmXStages,
                  y_empty = y_full + 8 * kWmYSlots, acc_full = y_empty + 8 * kWmYSlots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (acc_full + 8 - base));
 
-  const int chunk = blockIdx.y / P.n_cotiles;
-  const int cot = blockIdx.y - chunk * P.n_cotiles;
+  // blockIdx.y = ((parity) * chunks + chunk) * cotiles + cot   (parity only for KT = 2)
+  int by = blockIdx.y;
+  const int cot = by % P.n_cotiles; by /= P.n_cotiles;
+  const int chunk = by % P.n_chunks_total; by /= P.n_chunks_total;
+  const int parity = KT == 2 ? by : 0;
+  const int pd = (parity >> 2) & 1, ph = (parity >> 1) & 1, pw = parity & 1;
   const bool s1 = chunk >= P.n_chunks_src0;
   const int c0 = (s1 ? chunk - P.n_chunks_src0 : chunk) * 32;
+  // X tile origin relative to the dY tile origin, and the dY plane paired with atom j of X plane p: p + doff + j
+  const int xoff_w = KT == 3 ? -1 : (pw ? -1 : 0), xoff_h = KT == 3 ? -1 : (ph ? -1 : 0);
+  const int doff = KT == 3 ? -1 : pd - 1;
   // contiguous range of items for this CTA
   const int items = P.Nb * P.tiles_h * P.tiles_w * P.nseg;
   const int per = (items + gridDim.x - 1) / gridDim.x;
@@ -81,7 +95,7 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
       int ys = 0; uint32_t yp = 0;    // dY ring
       auto load_dy = [&](int q, int nb, int h0, int w0) {
         mbar_wait(y_empty + 8 * ys, yp ^ 1);
-        const bool mirror = ys < 2;
+        const bool mirror = ys < KT - 1;
         mbar_expect_tx(y_full + 8 * ys, mirror ? 2 * kWmYBytes : kWmYBytes);
         tma_load_5d(y_base + ys * kWmYBytes, &P.tm_dy, y_full + 8 * ys, cot * 32, w0, h0, q, nb);
         if (mirror) tma_load_5d(y_base + (kWmYSlots + ys) * kWmYBytes, &P.tm_dy, y_full + 8 * ys, cot * 32, w0, h0, q, nb);
@@ -95,15 +109,16 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
         const int nb = t;
         const int d0 = seg * P.seg_len;
         int d1 = d0 + P.seg_len; if (d1 > P.D) d1 = P.D;
-        // the item owns X planes [d0, d1) and pairs each with dY planes p-1, p, p+1; planes -1 and D
-        // are out-of-bounds TMA coordinates (zero fill = the conv padding in depth)
-        load_dy(d0 - 1, nb, h0, w0);
-        load_dy(d0, nb, h0, w0);
+        // the item owns X planes [d0, d1) and pairs each with the dY planes p+doff .. p+doff+KT-1; planes
+        // outside [0, D) are out-of-bounds TMA coordinates (zero fill = the conv padding in depth)
+#pragma unroll
+        for (int j = 0; j < KT - 1; ++j) load_dy(d0 + doff + j, nb, h0, w0);
         for (int p = d0; p < d1; ++p) {
-          load_dy(p + 1, nb, h0, w0);
+          load_dy(p + doff + KT - 1, nb, h0, w0);
           mbar_wait(x_empty + 8 * xs, xp ^ 1);
-          mbar_expect_tx(x_full + 8 * xs, 180 * 64);
-          tma_load_5d(x_base + xs * kWmXBytes, tmx, x_full + 8 * xs, c0, w0 - 1, h0 - 1, p, nb);
+          mbar_expect_tx(x_full + 8 * xs, BW * BH * 64);
+          tma_load_5d(x_base + xs * kWmXBytes, tmx, x_full + 8 * xs, c0, w0 + xoff_w, h0 + xoff_h, p,
+                      KT == 2 ? nb * 8 + parity : nb);
           if (++xs == kWmXStages) { xs = 0; xp ^= 1; }
         }
       }
@@ -111,33 +126,33 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
     __syncwarp();
   } else if (warp == 5) {
     // =========================== MMA issuer ===========================
-    const uint32_t idesc = make_idesc_bf16(128, 96, 1, 1);
-    const uint64_t a_desc0 = make_smem_desc(0, /*lbo: next kw atom = next halo row*/ 64, /*sbo: next h row*/ 10 * 64, SWZ_64B);
+    const uint32_t idesc = make_idesc_bf16(128, NN, 1, 1);
+    const uint64_t a_desc0 = make_smem_desc(0, /*lbo: next kw atom = next halo row*/ 64, /*sbo: next h row*/ BW * 64, SWZ_64B);
     const uint64_t b_desc0 = make_smem_desc(0, /*lbo: next dY plane*/ kWmYBytes, /*sbo: next 8 voxel rows*/ 8 * 64, SWZ_64B);
     const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
     const uint32_t a_lo0 = (uint32_t)a_desc0, b_lo0 = (uint32_t)b_desc0;
     const bool leader = elect_one();
     int xs = 0; uint32_t xp = 0;
-    int ys = 0; uint32_t yp = 0;       // slot / phase of the OLDEST of the three live dY planes
+    int ys = 0; uint32_t yp = 0;       // slot / phase of the OLDEST of the KT live dY planes
     uint32_t first = 1;
     for (int it = i_begin; it < i_end; ++it) {
       const int seg = it % P.nseg;
       const int d0 = seg * P.seg_len;
       int d1 = d0 + P.seg_len; if (d1 > P.D) d1 = P.D;
-      // the first two dY planes of the item
+      // the first KT-1 dY planes of the item
       {
-        int s = ys; uint32_t ph = yp;
-        for (int k = 0; k < 2; ++k) {
-          mbar_wait(y_full + 8 * s, ph);
-          if (++s == kWmYSlots) { s = 0; ph ^= 1; }
+        int s = ys; uint32_t ph_ = yp;
+        for (int k = 0; k < KT - 1; ++k) {
+          mbar_wait(y_full + 8 * s, ph_);
+          if (++s == kWmYSlots) { s = 0; ph_ ^= 1; }
         }
       }
       for (int p = d0; p < d1; ++p) {
-        // newest plane (oldest + 2)
+        // newest plane (oldest + KT-1)
         {
-          int s = ys + 2; uint32_t ph = yp;
-          if (s >= kWmYSlots) { s -= kWmYSlots; ph ^= 1; }
-          mbar_wait(y_full + 8 * s, ph);
+          int s = ys + KT - 1; uint32_t ph_ = yp;
+          if (s >= kWmYSlots) { s -= kWmYSlots; ph_ ^= 1; }
+          mbar_wait(y_full + 8 * s, ph_);
         }
         mbar_wait(x_full + 8 * xs, xp);
         tc_fence_after();
@@ -146,24 +161,25 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
           const uint32_t a_lo = a_lo0 + ((x_base + xs * kWmXBytes) >> 4);
           const uint32_t b_lo = b_lo0 + ((y_base + ys * kWmYBytes) >> 4);
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh)
+          for (int kh = 0; kh < KT; ++kh)
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
-              umma_bf16_lohi(tmem + kh * 96, a_lo + (uint32_t)((kh * 10 + ks * 20) * 64 >> 4), a_hi,
+              umma_bf16_lohi(tmem + kh * NN, a_lo + (uint32_t)((kh * BW + ks * 2 * BW) * 64 >> 4), a_hi,
                              b_lo + (uint32_t)(ks * 16 * 64 >> 4), b_hi, idesc, (ks == 0 ? (first ^ 1u) : 1u));
           umma_commit(x_empty + 8 * xs);
           umma_commit(y_empty + 8 * ys);           // the oldest plane is dead after this step
-          if (last) {                              // ... and so are the other two at the end of an item
-            int s = ys + 1; if (s >= kWmYSlots) s -= kWmYSlots;
-            umma_commit(y_empty + 8 * s);
-            s = ys + 2; if (s >= kWmYSlots) s -= kWmYSlots;
-            umma_commit(y_empty + 8 * s);
+          if (last) {                              // ... and so are the others at the end of an item
+#pragma unroll
+            for (int k = 1; k < KT; ++k) {
+              int s = ys + k; if (s >= kWmYSlots) s -= kWmYSlots;
+              umma_commit(y_empty + 8 * s);
+            }
           }
         }
         __syncwarp();
         first = 0;
         if (++xs == kWmXStages) { xs = 0; xp ^= 1; }
-        const int adv = last ? 3 : 1;
+        const int adv = last ? KT : 1;
         ys += adv;
         if (ys >= kWmYSlots) { ys -= kWmYSlots; yp ^= 1; }
       }
@@ -176,16 +192,18 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
     tc_fence_after();
     const bool any = i_end > i_begin;
     const size_t tap_elems = (size_t)P.ci_total * P.co_total;
-    float* outb = P.partial + (size_t)blockIdx.x * 27 * tap_elems;
-    for (int kh = 0; kh < 3; ++kh) {
+    float* outb = P.partial + (size_t)blockIdx.x * P.ntaps * tap_elems;
+    for (int kh = 0; kh < KT; ++kh) {
 #pragma unroll 1
-      for (int j = 0; j < 3; ++j) {
+      for (int j = 0; j < KT; ++j) {
         uint32_t rr[32];
-        tmem_ld_32x32b_x32(tmem + ((uint32_t)(warp * 32) << 16) + kh * 96 + j * 32, rr);
+        tmem_ld_32x32b_x32(tmem + ((uint32_t)(warp * 32) << 16) + kh * NN + j * 32, rr);
         tmem_ld_wait();
-        if (warp < 3) {   // warp = kw atom (the 4th atom is unused), lane = ci
-          const int kd = 2 - j;
-          float4* d4 = reinterpret_cast<float4*>(outb + (size_t)((kd * 3 + kh) * 3 + warp) * tap_elems +
+        if (warp < KT) {   // warp = kw atom (the other atoms are unused), lane = ci
+          int tap;
+          if (KT == 3) tap = ((2 - j) * 3 + kh) * 3 + warp;
+          else tap = ((2 * (1 - j) + 1 - pd) * 4 + (2 * kh + 1 - ph)) * 4 + (2 * warp + 1 - pw);
+          float4* d4 = reinterpret_cast<float4*>(outb + (size_t)tap * tap_elems +
                                                  (size_t)(chunk * 32 + lane) * P.co_total + cot * 32);
 #pragma unroll
           for (int q = 0; q < 8; ++q)
