@@ -435,12 +435,12 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
             uint4* de = reinterpret_cast<uint4*>(be) + (odd ? 1 : 0);
             uint4* d_o = reinterpret_cast<uint4*>(be + row_step) + (odd ? 1 : 0);
             if (valid_e) {
-              de[0] = odd ? make_uint4(rx[0], rx[1], rx[2], rx[3]) : make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              if (full32) de[2] = odd ? make_uint4(rx[4], rx[5], rx[6], rx[7]) : make_uint4(pk[8], pk[9], pk[10], pk[11]);
+              __stcs(de + 0, odd ? make_uint4(rx[0], rx[1], rx[2], rx[3]) : make_uint4(pk[0], pk[1], pk[2], pk[3]));
+              if (full32) __stcs(de + 2, odd ? make_uint4(rx[4], rx[5], rx[6], rx[7]) : make_uint4(pk[8], pk[9], pk[10], pk[11]));
             }
             if (valid_o) {
-              d_o[0] = odd ? make_uint4(pk[4], pk[5], pk[6], pk[7]) : make_uint4(rx[0], rx[1], rx[2], rx[3]);
-              if (full32) d_o[2] = odd ? make_uint4(pk[12], pk[13], pk[14], pk[15]) : make_uint4(rx[4], rx[5], rx[6], rx[7]);
+              __stcs(d_o + 0, odd ? make_uint4(pk[4], pk[5], pk[6], pk[7]) : make_uint4(rx[0], rx[1], rx[2], rx[3]));
+              if (full32) __stcs(d_o + 2, odd ? make_uint4(pk[12], pk[13], pk[14], pk[15]) : make_uint4(rx[4], rx[5], rx[6], rx[7]));
             }
           }
           if (do_stats && valid_hw) {

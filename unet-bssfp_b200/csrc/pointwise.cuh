@@ -18,6 +18,18 @@ struct alignas(16) bf16x8 {
   __nv_bfloat162 v[4];
 };
 
+// streaming 16-byte accesses (ld.global.cs / st.global.cs): every pass touches each byte once and the
+// tensors are far larger than L2, so they should not displace what little is re-used
+__device__ __forceinline__ bf16x8 ld_stream(const bf16x8* p) {
+  const uint4 v = __ldcs(reinterpret_cast<const uint4*>(p));
+  bf16x8 r;
+  *reinterpret_cast<uint4*>(&r) = v;
+  return r;
+}
+__device__ __forceinline__ void st_stream(bf16x8* p, const bf16x8& v) {
+  __stcs(reinterpret_cast<uint4*>(p), *reinterpret_cast<const uint4*>(&v));
+}
+
 __device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -161,7 +173,7 @@ pack_ncdhw_kernel(const float* __restrict__ a, int ca, const float* __restrict__
     } else {
       row = (size_t)n * V + v;
     }
-    reinterpret_cast<bf16x8*>(dst + row * CP)[oct] = pack8(g[u]);
+    st_stream(reinterpret_cast<bf16x8*>(dst + row * CP) + oct, pack8(g[u]));
   }
 }
 
@@ -337,7 +349,7 @@ norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restri
 #pragma unroll
   for (int u = 0; u < UNROLL; ++u) {
     const uint32_t idx = i0 + u * 256u;
-    if (idx < vps) in[u] = yv[idx];
+    if (idx < vps) in[u] = ld_stream(yv + idx);
   }
 #pragma unroll
   for (int u = 0; u < UNROLL; ++u) {
@@ -365,7 +377,7 @@ norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restri
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = lrelu(x[k], A.slope, slope_le1);
-    av[idx] = pack8(x);
+    st_stream(av + idx, pack8(x));
   }
 }
 
@@ -394,16 +406,16 @@ __global__ void norm_act_pool_fwd_kernel(const __nv_bfloat16* __restrict__ y, __
     const size_t vox = (((size_t)n * D + d) * H + h) * W + w;
     const size_t e = vox * c8 + (c0 >> 3);
     float x[8];
-    unpack8(reinterpret_cast<const bf16x8*>(y)[e], x);
+    unpack8(ld_stream(reinterpret_cast<const bf16x8*>(y) + e), x);
     norm_act_apply8(x, A, n, Cp, c0, (unsigned long long)e * 8ull);
     const bf16x8 pk = pack8(x);
-    reinterpret_cast<bf16x8*>(a)[e] = pk;
+    st_stream(reinterpret_cast<bf16x8*>(a) + e, pk);
     float xr[8];
     unpack8(pk, xr);  // max over the stored (rounded) values
 #pragma unroll
     for (int k = 0; k < 8; ++k) m[k] = xr[k] > m[k] ? xr[k] : m[k];
   }
-  reinterpret_cast<bf16x8*>(pooled)[i] = pack8(m);
+  st_stream(reinterpret_cast<bf16x8*>(pooled) + i, pack8(m));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -493,8 +505,8 @@ norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bflo
     for (int u = 0; u < 4; ++u) {
       const uint32_t idx = i + u * stride;
       if (idx < vps) {
-        d_[u] = dAv[idx];
-        y_[u] = yv[idx];
+        d_[u] = ld_stream(dAv + idx);
+        y_[u] = ld_stream(yv + idx);
         if (!from_y) a_[u] = av[idx];
       }
     }
@@ -613,9 +625,9 @@ norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloa
   for (int u = 0; u < UNROLL; ++u) {
     const uint32_t idx = i0 + u * 256u;
     if (idx < vps) {
-      d_[u] = dAv[idx];
-      if (!from_y) a_[u] = av[idx];
-      if (has_norm) y_[u] = yv[idx];
+      d_[u] = ld_stream(dAv + idx);
+      if (!from_y) a_[u] = ld_stream(av + idx);
+      if (has_norm) y_[u] = ld_stream(yv + idx);
     }
   }
 #pragma unroll
@@ -630,7 +642,7 @@ norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloa
 #pragma unroll
       for (int k = 0; k < 8; ++k) dz[k] = fmaf(ka[k], dz[k], fmaf(kc[k], yy[k], kb[k]));
     }
-    dyv[idx] = pack8(dz);
+    st_stream(dyv + idx, pack8(dz));
   }
 }
 
@@ -654,7 +666,7 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __
   const int hy = (int)(pv % Hp);
   const int dz = (int)(pv / Hp);
   float g[8];
-  unpack8(reinterpret_cast<const bf16x8*>(dP)[i], g);
+  unpack8(ld_stream(reinterpret_cast<const bf16x8*>(dP) + i), g);
   float best[8];
   int arg[8];
 #pragma unroll
@@ -665,7 +677,7 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __
     const int d = 2 * dz + (j >> 2), h = 2 * hy + ((j >> 1) & 1), w = 2 * wx + (j & 1);
     e[j] = ((((size_t)n * D + d) * H + h) * W + w) * c8 + cidx;
     float x[8];
-    unpack8(reinterpret_cast<const bf16x8*>(a)[e[j]], x);
+    unpack8(ld_stream(reinterpret_cast<const bf16x8*>(a) + e[j]), x);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       if (x[k] > best[k]) { best[k] = x[k]; arg[k] = j; }
@@ -673,10 +685,10 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float o[8];
-    if (accumulate) unpack8(reinterpret_cast<const bf16x8*>(dA)[e[j]], o);
+    if (accumulate) unpack8(ld_stream(reinterpret_cast<const bf16x8*>(dA) + e[j]), o);
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = (accumulate ? o[k] : 0.f) + (arg[k] == j ? g[k] : 0.f);
-    reinterpret_cast<bf16x8*>(dA)[e[j]] = pack8(o);
+    st_stream(reinterpret_cast<bf16x8*>(dA) + e[j], pack8(o));
   }
 }
 
@@ -696,7 +708,7 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long lon
   if (vlane < lanes_v)
     for (long long r = (long long)blockIdx.x * lanes_v + vlane; r < rows; r += (long long)gridDim.x * lanes_v) {
       float v[8];
-      unpack8(reinterpret_cast<const bf16x8*>(x)[(size_t)r * c8 + cidx], v);
+      unpack8(ld_stream(reinterpret_cast<const bf16x8*>(x) + (size_t)r * c8 + cidx), v);
 #pragma unroll
       for (int k = 0; k < 8; ++k) s[k] += v[k];
     }
