@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- G+D train-step voxels/s of the sm_100a hot path (BASELINE.json metric).
 
-    python bench.py --gpus 1 --steps 5 --warmup 3
+    python bench.py --gpus 1 --steps 20 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference          # the reference arithmetic (oracle) on the host cores
@@ -169,7 +169,7 @@ def dominant_kernel_roofline(dev, batch, size, peaks, iters=5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="per-GPU batch (BASELINE config 2: 8)")
