@@ -189,3 +189,68 @@ def test_dgrad_fused_norm_backward_reduction(mode, drop_p, co, shape):
     assert rel_l2(got[0].float(), ref[0].float()) < 1e-3
     # a conv whose source has 64 channels has no fused path
     assert ops.dgrad_fuse_records(ops.ConvSpec(0, 64, 64), n, d, h, w) == 0
+
+
+@pytest.mark.parametrize("kind,c0,c1,co,shape", [
+    (0, 24, 0, 32, (1, 6, 20, 12)),      # marching kernel, ragged h / w tiles (lane-pair stores at the border)
+    (0, 64, 0, 64, (1, 5, 18, 10)),      # generic folded kernel, ragged d / h / w
+    (0, 32, 64, 32, (1, 5, 20, 12)),     # two sources; dgrad with split destinations
+    (3, 64, 0, 64, (1, 3, 6, 5)),        # transposed conv: scatter stores with stride 2
+    (2, 32, 0, 64, (1, 6, 10, 12)),      # stride-2 conv: parity-class scatter in dgrad
+    (4, 30, 0, 32, (1, 6, 36, 20)),      # stem on the space-to-depth source
+])
+def test_no_out_of_bounds_writes(kind, c0, c1, co, shape):
+    """Guard bands around every output of the C ABI calls stay untouched (compute-sanitizer is not
+    available on the pool): outputs live in the middle of NaN-filled arenas."""
+    import ctypes as C
+    from unet_bssfp_b200 import _lib
+    ops = _ops()
+    lib = _lib.load()
+    x, wt, b = _make(kind, c0, c1, co, shape, seed=3)
+    spec = ops.ConvSpec(kind, c0, co, c1)
+    n, d, h, w = shape
+    od, oh, ow = spec.out_dims(d, h, w)
+    desc = spec.desc(n, d, h, w)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    GUARD = 4096
+
+    def arena(numel, dtype):
+        buf = torch.full((numel + 2 * GUARD,), float("nan"), dtype=dtype, device="cuda")
+        return buf, buf[GUARD:GUARD + numel]
+
+    def intact(buf):
+        return bool(torch.isnan(buf[:GUARD]).all() and torch.isnan(buf[-GUARD:]).all())
+
+    s0 = _src(kind, x[:, :c0])
+    s1 = to_internal(x[:, c0:]) if c1 else None
+    # forward (+ statistics)
+    wf = ops.pack_conv_weights(spec, wt, 0)
+    ybuf, y = arena(n * od * oh * ow * spec.cop, torch.bfloat16)
+    tiles = lib.ub_conv_num_tiles(C.byref(desc))
+    sbuf, stats = arena(tiles * 2 * spec.cop, torch.float32)
+    want_stats = kind != 3
+    _lib.check(lib.ub_conv_fwd(C.byref(desc), P(s0), P(s1), P(wf), P(b), 0, 0.0, P(y), P(stats) if want_stats else None, st))
+    torch.cuda.synchronize()
+    assert intact(ybuf) and intact(sbuf)
+    assert not torch.isnan(y.float()).any()
+    if want_stats:
+        assert not torch.isnan(stats).any()          # every tile wrote its record
+    # dgrad
+    wd = ops.pack_conv_weights(spec, wt, 1)
+    dy = torch.randn((n, od, oh, ow, spec.cop), device="cuda").to(torch.bfloat16)
+    d0buf, d0 = arena(n * d * h * w * spec.c0p, torch.bfloat16)
+    d1buf, d1 = arena(n * d * h * w * max(spec.c1p, 1), torch.bfloat16)
+    _lib.check(lib.ub_conv_dgrad(C.byref(desc), P(dy), P(wd), P(d0), P(d1) if c1 else None, st))
+    torch.cuda.synchronize()
+    assert intact(d0buf) and intact(d1buf) and not torch.isnan(d0.float()).any()
+    if c1:
+        assert not torch.isnan(d1.float()).any()
+    # wgrad
+    nbytes = lib.ub_conv_wgrad_workspace_bytes(C.byref(desc))
+    wsbuf, ws = arena(nbytes // 4, torch.float32)
+    dwbuf, dw = arena(wt.numel(), torch.float32)
+    dw.zero_()
+    _lib.check(lib.ub_conv_wgrad(C.byref(desc), P(s0), P(s1), P(dy), P(ws), P(dw), st))
+    torch.cuda.synchronize()
+    assert intact(wsbuf) and intact(dwbuf) and not torch.isnan(dw).any()
