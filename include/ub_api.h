@@ -106,9 +106,25 @@ int ub_pack_patches(const float* a, int ca, int n, const long long* offsets, int
                     long long stride_c, long long stride_d, long long stride_h, int cp, void* out, void* stream);
 int ub_unpack_patch(const void* src, int cp, int c_begin, int c, int sample, int d, int h, int w, float* dst,
                     long long dst_offset, long long stride_c, long long stride_d, long long stride_h, void* stream);
+/* the same aggregation for an NCDHW fp32 patch [c][d][h][w] (the output of ub_conv1x1_to_ncdhw) */
+int ub_paste_patch(const float* src, int c, int d, int h, int w, float* dst, long long dst_offset,
+                   long long stride_c, long long stride_d, long long stride_h, void* stream);
 /* NDHWC bf16 (cp channels) -> NCDHW fp32, channels [c_begin, c_begin + c) */
 int ub_unpack_ncdhw(const void* src, int cp, int c_begin, int c, int n, long long voxels, float* out,
                     void* stream);
+
+/* ---- output head: 1x1x1 conv to <= 8 channels fused with the layout change ------------------------- */
+/* monai BasicUNet.final_conv = nn.Conv3d(32, 6, 1) (ref:model.py:22-28) followed by the module boundary:
+ * out (NCDHW fp32 [n][co][voxels]) = W u + b straight from the NDHWC bf16 activations u (cp = 32), instead of a
+ * padded 32-channel bf16 tensor + unpack. w [co][ci] / bias [co] are the fp32 parameters (device pointers).
+ * workspace: ub_conv1x1_workspace_bytes() bytes. */
+long long ub_conv1x1_workspace_bytes(void);
+int ub_conv1x1_to_ncdhw(const void* u, int cp, const float* w, int ci, const float* bias, int co, int n,
+                        long long voxels, void* workspace, float* out, void* stream);
+/* its backward in ONE pass over dout (NCDHW fp32) and u: du = W^T dout (NDHWC bf16, may be NULL),
+ * dw [co][ci] = sum dout (x) u and db [co] = sum dout (fp32, may be NULL; u may be NULL when both are) */
+int ub_conv1x1_from_ncdhw_bwd(const float* dout, int co, const void* u, int cp, const float* w, int ci, int n,
+                              long long voxels, void* workspace, void* du, float* dw, float* db, void* stream);
 
 /* ---- normalisation + dropout + activation --------------------------------------------------- */
 enum { UB_NORM_INSTANCE = 0, UB_NORM_BATCH_TRAIN = 1, UB_NORM_BATCH_EVAL = 2, UB_NORM_NONE = 3 };

@@ -172,3 +172,28 @@ def test_l1_and_bce_losses():
         (lb2 * 0.5).backward()
         assert abs(lb.item() - lb2.item()) < 1e-5 * abs(lb2.item())
         assert torch.allclose(z.grad, z2.grad, rtol=1e-4, atol=1e-8)
+
+
+@pytest.mark.parametrize("co,ci,shape", [(6, 32, (2, 4, 6, 10)), (1, 32, (1, 3, 5, 7)), (8, 24, (1, 4, 4, 8))])
+def test_output_head_conv1x1_fused(co, ci, shape):
+    """ub_conv1x1_to_ncdhw / ub_conv1x1_from_ncdhw_bwd vs F.conv3d(k=1) + autograd on the bf16-rounded input
+    (fp32 weights, fp32 math): forward exact to fp32 rounding, du to bf16 rounding, dW / db to 1e-4."""
+    strict_fp32()
+    ops = _ops()
+    n, d, h, w = shape
+    u = bf16_round(_rand((n, ci, d, h, w), 0))
+    wt = _rand((co, ci, 1, 1, 1), 1) * 0.3
+    b = _rand((co,), 2)
+    out = ops.conv1x1_to_ncdhw(to_internal(u), wt, b)
+    ur, wr, br = u.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.conv3d(ur, wr, br)
+    assert out.shape == ref.shape and rel_to_max(out, ref) < 1e-5
+    g = _rand(ref.shape, 3)
+    ref.backward(g)
+    du, dw, db = ops.conv1x1_from_ncdhw_bwd(g, to_internal(u), wt)
+    assert rel_to_max(from_internal(du, ci), ur.grad) < 6e-3
+    if ci < 32:
+        assert du[..., ci:].abs().max().item() == 0.0
+    assert rel_to_max(dw, wr.grad) < 1e-4 and rel_to_max(db, br.grad) < 1e-4
+    du2, dw2, db2 = ops.conv1x1_from_ncdhw_bwd(g, to_internal(u), wt, need_input=True, need_params=False)
+    assert torch.equal(du2, du) and dw2 is None and db2 is None

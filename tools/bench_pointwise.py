@@ -90,3 +90,10 @@ if len(sys.argv) > 4:
     o2 = torch.empty_like(y)
     timeit("  unskewed raw norm_act_bwd from y p=0.05", lambda: raw_bwd(dA, y, o2), elems * 10)
     timeit("  unskewed raw norm_act_fwd p=0.05", lambda: raw_fwd(y, o2), elems * 4)
+if CP == 32 and len(sys.argv) <= 4:
+    wt = torch.randn((6, 32, 1, 1, 1), device=dev) * 0.1
+    bb = torch.randn((6,), device=dev)
+    go = torch.randn((N, 6, S, S, S), device=dev)
+    timeit("conv1x1_to_ncdhw (88 B/vox)", lambda: ops.conv1x1_to_ncdhw(y, wt, bb), elems // 32 * 88)
+    timeit("conv1x1_from_ncdhw_bwd all (152 B/vox)", lambda: ops.conv1x1_from_ncdhw_bwd(go, y, wt), elems // 32 * 152)
+    timeit("conv1x1_from_ncdhw_bwd du only (88 B/vox)", lambda: ops.conv1x1_from_ncdhw_bwd(go, y, wt, need_params=False), elems // 32 * 88)

@@ -84,7 +84,7 @@ def l_generic(out, *a, **k):
 wrap("conv_fwd", l_conv_fwd)
 wrap("conv_dgrad", l_conv_dgrad)
 wrap("conv_wgrad", l_conv_wgrad)
-for nm in ("pack_ncdhw", "unpack_ncdhw", "norm_finalize", "norm_act_fwd", "norm_act_bwd", "maxpool_bwd", "colsum",
+for nm in ("conv1x1_to_ncdhw", "conv1x1_from_ncdhw_bwd", "pack_ncdhw", "unpack_ncdhw", "norm_finalize", "norm_act_fwd", "norm_act_bwd", "maxpool_bwd", "colsum",
            "l1_fwd", "l1_bwd", "bce_logits", "scale_by", "pack_conv_weights"):
     wrap(nm, l_generic)
 

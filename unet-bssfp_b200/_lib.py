@@ -54,7 +54,11 @@ SIGNATURES = {
     "ub_pack_ncdhw_s2d": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "ub_pack_patches": (_I, [_P, _I, _I, C.POINTER(C.c_longlong), _I, _I, _I, _LL, _LL, _LL, _I, _P, _P]),
     "ub_unpack_patch": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _LL, _LL, _LL, _LL, _P]),
+    "ub_paste_patch": (_I, [_P, _I, _I, _I, _I, _P, _LL, _LL, _LL, _LL, _P]),
     "ub_unpack_ncdhw": (_I, [_P, _I, _I, _I, _I, _LL, _P, _P]),
+    "ub_conv1x1_workspace_bytes": (_LL, []),
+    "ub_conv1x1_to_ncdhw": (_I, [_P, _I, _P, _I, _P, _I, _I, _LL, _P, _P, _P]),
+    "ub_conv1x1_from_ncdhw_bwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _LL, _P, _P, _P, _P, _P]),
     "ub_norm_finalize": (_I, [_P, _I, _I, _I, _I, _D, _P, _P, _F, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "ub_norm_act_fwd": (_I, [_P, _P, _P, _F, _F, _U32, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ub_norm_act_bwd_workspace_bytes": (_LL, [_I, _I]),

@@ -234,6 +234,17 @@ __global__ void unpack_patch_kernel(const __nv_bfloat16* __restrict__ src, float
   for (int k = 0; k < c; ++k) d[(size_t)k * G.stride_c] = __bfloat162float(s[k]);
 }
 
+// Same for an NCDHW fp32 patch (c, d, h, w contiguous), e.g. the output of the fused generator head.
+__global__ void paste_patch_kernel(const float* __restrict__ src, float* __restrict__ dst, int c, PatchGeom G) {
+  const uint32_t V = (uint32_t)G.d * G.h * G.w;
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const uint32_t x = v % G.w, t = v / G.w;
+  const uint32_t y = t % G.h, z = t / G.h;
+  float* d = dst + G.offset[0] + (size_t)z * G.stride_d + (size_t)y * G.stride_h + x;
+  for (int k = 0; k < c; ++k) d[(size_t)k * G.stride_c] = __ldcs(src + (size_t)k * V + v);
+}
+
 // channels [c_begin, c_begin + c) of an NDHWC bf16 tensor -> NCDHW fp32
 __global__ void unpack_ncdhw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int cp,
                                     int c_begin, int c, long long V, long long total) {
@@ -930,6 +941,188 @@ __global__ void relerr_kernel(const float* __restrict__ pred, const float* __res
       if ((threadIdx.x & 31) == 0) atomicAdd(sums + r * C + c, s);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Output head of the generator: 1x1x1 conv to <= 8 channels fused with the layout change
+//   ref: monai BasicUNet.final_conv (nn.Conv3d(32, 6, 1)), ref:model.py:22-28; output NCDHW fp32.
+// The tensor-core path would write a 32-channel padded bf16 tensor and unpack it (192 B/voxel of traffic
+// for 24 B of result); this is a matvec of 6 x 32 per voxel, done on the CUDA cores at HBM speed.
+// thread = (voxel, octet of input channels): 16-byte coalesced loads, partial dot products over the 8
+// channels, two xor-shuffles across the 4 octet lanes, lane `oct` stores outputs oct and oct + 4.
+// ------------------------------------------------------------------------------------------------
+constexpr int kC1MaxCo = 8;
+struct Conv1x1Weights {
+  float w[kC1MaxCo][32];   // [co][ci], zero padded
+  float b[kC1MaxCo];
+};
+
+template <int CO>
+__global__ void __launch_bounds__(256)
+conv1x1_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ u, float* __restrict__ out, const Conv1x1Weights* __restrict__ Wg,
+                        uint32_t V) {
+  // grid = (blocks, N): each block strides over the voxels of one sample; weights live in registers
+  const int n = blockIdx.y;
+  const int oct = threadIdx.x & 3;
+  float wr[CO][8], br[CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+    br[c] = Wg->b[c];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wr[c][k] = Wg->w[c][oct * 8 + k];
+  }
+  const bf16x8* up = reinterpret_cast<const bf16x8*>(u + (size_t)n * V * 32);
+  float* op = out + (size_t)n * CO * V;
+  constexpr int UNR = 4;             // independent 16-byte loads in flight per thread
+  const uint32_t vstep = gridDim.x * (64 * UNR);
+  // all lanes of a warp run the same number of iterations (the shuffles below need the full warp)
+  for (uint32_t vb = blockIdx.x * (64 * UNR); vb < V; vb += vstep) {
+    bf16x8 raw[UNR];
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) {
+      const uint32_t v = vb + q * 64 + (threadIdx.x >> 2);
+      if (v < V) raw[q] = ld_stream(up + (size_t)v * 4 + oct);
+    }
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) {
+      const uint32_t v = vb + q * 64 + (threadIdx.x >> 2);
+      const bool ok = v < V;
+      float x[8];
+      unpack8(raw[q], x);
+      float mine0 = 0.f, mine1 = 0.f;   // outputs oct and oct + 4
+#pragma unroll
+      for (int c = 0; c < CO; ++c) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a = fmaf(ok ? x[k] : 0.f, wr[c][k], a);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        if ((c & 3) == oct) { if (c < 4) mine0 = a + br[c]; else mine1 = a + br[c]; }
+      }
+      if (ok) {
+        if (oct < CO) __stcs(op + (size_t)oct * V + v, mine0);
+        if (oct + 4 < CO) __stcs(op + (size_t)(oct + 4) * V + v, mine1);
+      }
+    }
+  }
+}
+
+// Backward of the above in one pass over dout (NCDHW fp32) and u (NDHWC bf16, 32 channels):
+//   du[v][ci] = sum_co dout[co][v] * W[co][ci]          (bf16, may be skipped)
+//   dW[co][ci] = sum_v dout[co][v] * u[v][ci],  db[co] = sum_v dout[co][v]     (per-block partials)
+// thread = (voxel, octet of ci); grid = (blocks, N); part: [blocks * N][kC1MaxCo][33] floats (column 32 =
+// bias gradient).
+template <int CO>
+__global__ void __launch_bounds__(256, 2)
+conv1x1_from_ncdhw_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ u,
+                              __nv_bfloat16* __restrict__ du, const Conv1x1Weights* __restrict__ Wg, uint32_t V,
+                              int want_w, float* __restrict__ part) {
+  __shared__ float red[8][CO][33];
+  const int n = blockIdx.y;
+  const int oct = threadIdx.x & 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float wr[CO][8];
+#pragma unroll
+  for (int c = 0; c < CO; ++c)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wr[c][k] = Wg->w[c][oct * 8 + k];
+  float gw[CO][8], gb[CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+    gb[c] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gw[c][k] = 0.f;
+  }
+  const float* gp = dout + (size_t)n * CO * V;
+  const bf16x8* up = reinterpret_cast<const bf16x8*>(u) + (size_t)n * V * 4;
+  bf16x8* dup = reinterpret_cast<bf16x8*>(du) + (size_t)n * V * 4;
+  constexpr int UNR = 2;
+  const uint32_t vstep = gridDim.x * (64 * UNR);
+  for (uint32_t vb = blockIdx.x * (64 * UNR) + (threadIdx.x >> 2); vb < V; vb += vstep) {
+    float g[UNR][CO];
+    bf16x8 ux[UNR];
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) {
+      const uint32_t v = vb + q * 64;
+      if (v < V) {
+#pragma unroll
+        for (int c = 0; c < CO; ++c) g[q][c] = __ldcs(gp + (size_t)c * V + v);
+        if (want_w) ux[q] = ld_stream(up + (size_t)v * 4 + oct);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) {
+      const uint32_t v = vb + q * 64;
+      if (v >= V) continue;
+      if (du != nullptr) {
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float a = 0.f;
+#pragma unroll
+          for (int c = 0; c < CO; ++c) a = fmaf(g[q][c], wr[c][k], a);
+          o[k] = a;
+        }
+        st_stream(dup + (size_t)v * 4 + oct, pack8(o));
+      }
+      if (want_w) {
+        float x[8];
+        unpack8(ux[q], x);
+#pragma unroll
+        for (int c = 0; c < CO; ++c) {
+          gb[c] += g[q][c];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) gw[c][k] = fmaf(g[q][c], x[k], gw[c][k]);
+        }
+      }
+    }
+  }
+  if (!want_w) return;
+  // reduce over the 8 voxel lanes that share an octet (xor 4, 8, 16), then over the 8 warps through smem
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float a = gw[c][k];
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      a += __shfl_xor_sync(0xffffffffu, a, 8);
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      gw[c][k] = a;
+    }
+    float bsum = gb[c];
+    bsum += __shfl_xor_sync(0xffffffffu, bsum, 4);
+    bsum += __shfl_xor_sync(0xffffffffu, bsum, 8);
+    bsum += __shfl_xor_sync(0xffffffffu, bsum, 16);
+    gb[c] = bsum;
+  }
+  if (lane < 4) {
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[warp][c][lane * 8 + k] = gw[c][k];
+      if (lane == 0) red[warp][c][32] = gb[c];   // every octet lane saw the same dout values
+    }
+  }
+  __syncthreads();
+  float* pb = part + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * kC1MaxCo * 33;
+  for (int i = threadIdx.x; i < CO * 33; i += blockDim.x) {
+    float a = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) a += red[wq][i / 33][i % 33];
+    pb[i] = a;
+  }
+}
+// sums the block partials in fp64: dw [co][ci], db [co]
+__global__ void conv1x1_bwd_finish_kernel(const float* __restrict__ part, int nblocks, int co, int ci, float* __restrict__ dw,
+                                          float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kC1MaxCo * 33) return;
+  const int c = i / 33, k = i % 33;
+  if (c >= co) return;
+  double a = 0.0;
+  for (int b = 0; b < nblocks; ++b) a += (double)part[(size_t)b * kC1MaxCo * 33 + i];
+  if (k == 32) { if (db) db[c] = (float)a; }
+  else if (k < ci && dw) dw[c * ci + k] = (float)a;
 }
 
 // ------------------------------------------------------------------------------------------------

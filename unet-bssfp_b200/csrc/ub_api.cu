@@ -950,6 +950,19 @@ extern "C" int ub_unpack_patch(const void* src, int cp, int c_begin, int c, int 
   return 0;
 }
 
+extern "C" int ub_paste_patch(const float* src, int c, int d, int h, int w, float* dst, long long dst_offset,
+                              long long stride_c, long long stride_d, long long stride_h, void* stream) {
+  if (!src || !dst || c <= 0 || d <= 0 || h <= 0 || w <= 0) return fail(-1, "bad arguments to ub_paste_patch");
+  PatchGeom G;
+  memset(&G, 0, sizeof(G));
+  G.offset[0] = dst_offset;
+  G.stride_c = stride_c; G.stride_d = stride_d; G.stride_h = stride_h; G.d = d; G.h = h; G.w = w;
+  const long long V = (long long)d * h * w;
+  paste_patch_kernel<<<(unsigned)((V + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, c, G);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int ub_unpack_ncdhw(const void* src, int cp, int c_begin, int c, int n, long long voxels, float* out,
                                void* stream) {
   if (!src || !out || c <= 0 || c_begin < 0 || c_begin + c > cp || cp % 8) return fail(-1, "bad arguments to ub_unpack_ncdhw");
@@ -1160,5 +1173,86 @@ extern "C" int ub_dti_scalar_maps(const float* tensor6, long long voxels, float*
   dti_scalar_maps_kernel<<<(unsigned)((voxels + 127) / 128), 128, 0, (cudaStream_t)stream>>>(tensor6, voxels, fa, md, ad, rd,
                                                                                            azimuth, inclination, rgb);
   UB_LAUNCH_CHECK();
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------
+// output head: 1x1x1 conv fused with the layout change (ref: BasicUNet.final_conv)
+// --------------------------------------------------------------------------------------------------
+static const int kC1BwdBlocks = 1184;
+static int fill_conv1x1_weights(const float* w, int ci, const float* bias, int co, void* table_dev, cudaStream_t st);
+
+extern "C" long long ub_conv1x1_workspace_bytes(void) {
+  // [Conv1x1Weights table | block partials of the backward]
+  return (long long)sizeof(Conv1x1Weights) + (long long)kC1BwdBlocks * kC1MaxCo * 33 * 4;
+}
+
+// w / bias are DEVICE pointers (the fp32 Parameters); the zero-padded table is built on the device
+__global__ void conv1x1_table_kernel(const float* __restrict__ w, int ci, const float* __restrict__ bias, int co,
+                                     Conv1x1Weights* __restrict__ T) {
+  for (int i = threadIdx.x; i < kC1MaxCo * 32; i += blockDim.x) {
+    const int c = i / 32, k = i % 32;
+    T->w[c][k] = (c < co && k < ci) ? w[c * ci + k] : 0.f;
+  }
+  if (threadIdx.x < kC1MaxCo) T->b[threadIdx.x] = (bias != nullptr && (int)threadIdx.x < co) ? bias[threadIdx.x] : 0.f;
+}
+static int fill_conv1x1_weights(const float* w, int ci, const float* bias, int co, void* table_dev, cudaStream_t st) {
+  conv1x1_table_kernel<<<1, 256, 0, st>>>(w, ci, bias, co, reinterpret_cast<Conv1x1Weights*>(table_dev));
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ub_conv1x1_to_ncdhw(const void* u, int cp, const float* w, int ci, const float* bias, int co, int n,
+                                   long long voxels, void* workspace, float* out, void* stream) {
+  if (!u || !w || !out || !workspace || n <= 0 || n > 65535 || voxels <= 0) return fail(-1, "bad arguments to ub_conv1x1_to_ncdhw");
+  if (cp != 32 || ci <= 0 || ci > 32 || co <= 0 || co > kC1MaxCo)
+    return fail(-2, "ub_conv1x1_to_ncdhw supports cp = 32, ci <= 32, co <= %d (got cp=%d ci=%d co=%d)", kC1MaxCo, cp, ci, co);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = fill_conv1x1_weights(w, ci, bias, co, workspace, st)) return e;
+  if (voxels >= (1ll << 31)) return fail(-2, "ub_conv1x1_to_ncdhw: sample too large");
+  long long blocks = (voxels + 255) / 256;
+  const long long cap = (8ll * sm_count() + n - 1) / n;
+  if (blocks > cap) blocks = cap;
+  const dim3 grid((unsigned)blocks, n);
+  const __nv_bfloat16* up = reinterpret_cast<const __nv_bfloat16*>(u);
+  const Conv1x1Weights* T = reinterpret_cast<const Conv1x1Weights*>(workspace);
+  switch (co) {
+#define UB_C1_FWD(C_) case C_: conv1x1_to_ncdhw_kernel<C_><<<grid, 256, 0, st>>>(up, out, T, (uint32_t)voxels); break;
+    UB_C1_FWD(1) UB_C1_FWD(2) UB_C1_FWD(3) UB_C1_FWD(4) UB_C1_FWD(5) UB_C1_FWD(6) UB_C1_FWD(7) UB_C1_FWD(8)
+#undef UB_C1_FWD
+  }
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ub_conv1x1_from_ncdhw_bwd(const float* dout, int co, const void* u, int cp, const float* w, int ci, int n,
+                                         long long voxels, void* workspace, void* du, float* dw, float* db, void* stream) {
+  if (!dout || !w || !workspace || n <= 0 || voxels <= 0) return fail(-1, "bad arguments to ub_conv1x1_from_ncdhw_bwd");
+  if ((dw || db) && !u) return fail(-1, "ub_conv1x1_from_ncdhw_bwd: weight / bias gradients need the forward input u");
+  if (cp != 32 || ci <= 0 || ci > 32 || co <= 0 || co > kC1MaxCo)
+    return fail(-2, "ub_conv1x1_from_ncdhw_bwd supports cp = 32, ci <= 32, co <= %d", kC1MaxCo);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = fill_conv1x1_weights(w, ci, nullptr, co, workspace, st)) return e;
+  float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + sizeof(Conv1x1Weights));
+  const int want_w = (dw || db) ? 1 : 0;
+  if (voxels >= (1ll << 31) || n > 65535) return fail(-2, "ub_conv1x1_from_ncdhw_bwd: sample too large");
+  long long blocks = (voxels + 127) / 128;
+  long long cap = kC1BwdBlocks / n;
+  if (cap < 1) cap = 1;
+  if (blocks > cap) blocks = cap;
+  const dim3 grid((unsigned)blocks, n);
+  const __nv_bfloat16* up = reinterpret_cast<const __nv_bfloat16*>(u);
+  __nv_bfloat16* dup = reinterpret_cast<__nv_bfloat16*>(du);
+  const Conv1x1Weights* T = reinterpret_cast<const Conv1x1Weights*>(workspace);
+  switch (co) {
+#define UB_C1_BWD(C_) case C_: conv1x1_from_ncdhw_bwd_kernel<C_><<<grid, 256, 0, st>>>(dout, up, dup, T, (uint32_t)voxels, want_w, part); break;
+    UB_C1_BWD(1) UB_C1_BWD(2) UB_C1_BWD(3) UB_C1_BWD(4) UB_C1_BWD(5) UB_C1_BWD(6) UB_C1_BWD(7) UB_C1_BWD(8)
+#undef UB_C1_BWD
+  }
+  UB_LAUNCH_CHECK();
+  if (want_w) {
+    conv1x1_bwd_finish_kernel<<<(kC1MaxCo * 33 + 127) / 128, 128, 0, st>>>(part, (int)(blocks * n), co, ci, dw, db);
+    UB_LAUNCH_CHECK();
+  }
   return 0;
 }

@@ -8,7 +8,7 @@ through the generator, and ``add_batch`` writes each prediction into the output 
 order -- where patches overlap the later one wins.
 
 Here the sampler and aggregator are index arithmetic inside the layout kernels (``ub_pack_patches`` /
-``ub_unpack_patch``): no host round trip and no intermediate NCDHW patch tensors.
+``ub_paste_patch``): no host round trip and no intermediate NCDHW patch tensors.
 ``relative_error`` then runs the fused error-map + ROI reduction of ref:src/eval.py:154-166,217-258.
 """
 from __future__ import annotations
@@ -52,9 +52,9 @@ def predict_volume(gen, volume: torch.Tensor, patch=64, batch: int = 8) -> torch
     for i in range(0, len(origins), batch):
         group = origins[i:i + batch]
         a = ops.pack_patches(vol, group, patch)
-        y = gen.forward_packed(a)
+        y = gen.forward_packed(a)                # (n, 6, pd, ph, pw) fp32
         for k, org in enumerate(group):          # sampler order: the later patch wins
-            ops.unpack_patch(y, k, out_c, out, org)
+            ops.paste_patch(y[k], out, org)
     return out
 
 

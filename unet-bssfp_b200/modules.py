@@ -448,9 +448,16 @@ def _check_unet_dims(d, h, w):
                            "monai UpCat for odd sizes is not on the sm_100a path)")
 
 
-def _generator_run(net: _UNetGraph, a, need_bwd: bool):
-    """Packed input (N,D,H,W,32) bf16 -> packed output of ``final_conv`` (N,D,H,W,32) bf16 and the
-    saved-for-backward dict (or None). The one place that sequences the generator's kernels."""
+def _final_is_fusable(net: "_UNetGraph") -> bool:
+    sp = net.final.spec
+    return sp.c0p == 32 and sp.c0 <= 32 and sp.co <= 8
+
+
+def _generator_run(net: _UNetGraph, a, need_bwd: bool, ncdhw_out: bool = False):
+    """Packed input (N,D,H,W,32) bf16 -> output of ``final_conv`` and the saved-for-backward dict (or
+    None). ``ncdhw_out``: the output head runs fused with the layout change and returns (N,6,D,H,W) fp32
+    (module boundary); otherwise the packed (N,D,H,W,32) bf16 tensor (inference keeps it packed). The one
+    place that sequences the generator's kernels."""
     training = net.training
     head_training = net.head_mod.training if net.head_mod is not None else training
     base_seed = _fresh_seed() if training else 0
@@ -481,7 +488,16 @@ def _generator_run(net: _UNetGraph, a, need_bwd: bool):
         up, _ = run(dc, u)
         t, _ = run(c0, x_e, up)
         u, _ = run(c1, t)
+    if ncdhw_out and _final_is_fusable(net):
+        out = ops.conv1x1_to_ncdhw(u, net.final.conv.weight, net.final.conv.bias)
+        if need_bwd:
+            sv = _Saved()
+            sv.src0 = u
+            S[net.final.name] = sv
+        return out, (S if need_bwd else None)
     yf, _ = run(net.final, u)
+    if ncdhw_out:
+        yf = ops.unpack_ncdhw(yf, net.unet.out_channels)
     return yf, (S if need_bwd else None)
 
 
@@ -491,8 +507,7 @@ class _GeneratorFunction(torch.autograd.Function):
         need_bwd = grad_enabled and (x.requires_grad or any(p.requires_grad for p in params))
         _check_unet_dims(*x.shape[2:])
         a = net.input_pack.get(x)
-        yf, S = _generator_run(net, a, need_bwd)
-        out = ops.unpack_ncdhw(yf, net.unet.out_channels)
+        out, S = _generator_run(net, a, need_bwd, ncdhw_out=True)
         ctx.net, ctx.S = net, S
         ctx.cx = x.shape[1]
         ctx.in_dtype = x.dtype
@@ -516,8 +531,17 @@ class _GeneratorFunction(torch.autograd.Function):
             S[blk.name] = None
             return r
 
-        dA = ops.pack_ncdhw(dout.contiguous().float())
-        du, _, _ = bwd(net.final, dA)
+        if _final_is_fusable(net):
+            # output head: dgrad, wgrad and bias gradient in one pass over dout (NCDHW) and the saved input
+            fw, fb = net.final.conv.weight, net.final.conv.bias
+            need_w = pneed[id(fw)] or pneed[id(fb)]
+            du, dw_, db_ = ops.conv1x1_from_ncdhw_bwd(dout, S[net.final.name].src0, fw, need_input=True, need_params=need_w)
+            if need_w:
+                grads[id(fw)], grads[id(fb)] = dw_, db_
+            S[net.final.name] = None
+        else:
+            dA = ops.pack_ncdhw(dout.contiguous().float())
+            du, _, _ = bwd(net.final, dA)
         nlev = len(net.enc)
         dskip = [None] * nlev
         for j in range(len(net.dec) - 1, -1, -1):      # upcat_1 first
@@ -578,11 +602,11 @@ class Generator(nn.Module):
 
     @torch.no_grad()
     def forward_packed(self, a):
-        """Inference on an already packed batch: (N,D,H,W,32) bf16 NDHWC -> (N,D,H,W,32) bf16 whose first
-        6 channels are the prediction (no NCDHW round trip; used by ``inference.predict_volume``)."""
+        """Inference on an already packed batch: (N,D,H,W,32) bf16 NDHWC -> (N,6,D,H,W) fp32, the same
+        arithmetic as ``forward`` without packing the input (used by ``inference.predict_volume``)."""
         _check_unet_dims(*a.shape[1:4])
-        yf, _ = _generator_run(self._net(), a, need_bwd=False)
-        return yf
+        out, _ = _generator_run(self._net(), a, need_bwd=False, ncdhw_out=True)
+        return out
 
 
 class Discriminator(nn.Module):

@@ -17,8 +17,8 @@ from ._lib import (ConvDesc, UB_CONV_K1, UB_CONV_K3S1P1, UB_CONV_K4S2P1, UB_CONV
                    UB_NORM_BATCH_EVAL, UB_NORM_BATCH_TRAIN, UB_NORM_INSTANCE, UB_NORM_NONE)
 
 __all__ = [
-    "ConvSpec", "pad32", "pack_conv_weights", "conv_fwd", "conv_dgrad", "conv_wgrad", "pack_ncdhw", "unpack_ncdhw",
-    "pack_patches", "unpack_patch",
+    "ConvSpec", "pad32", "pack_conv_weights", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv1x1_to_ncdhw", "conv1x1_from_ncdhw_bwd", "pack_ncdhw", "unpack_ncdhw",
+    "pack_patches", "unpack_patch", "paste_patch",
     "norm_finalize", "norm_act_fwd", "norm_act_bwd", "maxpool_bwd", "colsum", "l1_fwd", "l1_bwd", "bce_logits",
     "scale_by", "relerr_map_reduce", "dti_scalar_maps",
 ]
@@ -177,6 +177,37 @@ def conv_wgrad(spec: ConvSpec, src0, src1, dy, weight_shape):
     return dw
 
 
+def conv1x1_to_ncdhw(u, weight, bias):
+    """Generator output head: u (N,D,H,W,32) bf16, weight (co, ci, 1,1,1) fp32, bias (co) -> (N,co,D,H,W) fp32."""
+    _require_cuda(u, weight, bias)
+    lib = _lib.load()
+    n, d, h, w, cp = u.shape
+    co, ci = weight.shape[0], weight.shape[1]
+    ws = torch.empty(lib.ub_conv1x1_workspace_bytes() // 4, dtype=torch.float32, device=u.device)
+    out = torch.empty((n, co, d, h, w), dtype=torch.float32, device=u.device)
+    wt = weight.detach().contiguous().float()
+    _lib.check(lib.ub_conv1x1_to_ncdhw(_p(u), cp, _p(wt), ci, _p(bias), co, n, d * h * w, _p(ws), _p(out), _stream()),
+               "ub_conv1x1_to_ncdhw")
+    return out
+
+
+def conv1x1_from_ncdhw_bwd(dout, u, weight, need_input=True, need_params=True):
+    """Backward of ``conv1x1_to_ncdhw`` in one pass: -> (du (N,D,H,W,32) bf16 | None, dweight | None, dbias | None)."""
+    _require_cuda(dout, u, weight)
+    lib = _lib.load()
+    n, d, h, w, cp = u.shape
+    co, ci = weight.shape[0], weight.shape[1]
+    dout = dout.contiguous().float()
+    ws = torch.empty(lib.ub_conv1x1_workspace_bytes() // 4, dtype=torch.float32, device=u.device)
+    du = torch.empty_like(u) if need_input else None
+    dw = torch.empty(tuple(weight.shape), dtype=torch.float32, device=u.device) if need_params else None
+    db = torch.empty(co, dtype=torch.float32, device=u.device) if need_params else None
+    wt = weight.detach().contiguous().float()
+    _lib.check(lib.ub_conv1x1_from_ncdhw_bwd(_p(dout), co, _p(u), cp, _p(wt), ci, n, d * h * w, _p(ws), _p(du), _p(dw),
+                                             _p(db), _stream()), "ub_conv1x1_from_ncdhw_bwd")
+    return du, dw, db
+
+
 # ---------------------------------------------------------------------------------------------------
 # layout
 # ---------------------------------------------------------------------------------------------------
@@ -238,6 +269,24 @@ def unpack_patch(batch: torch.Tensor, sample: int, c: int, volume: torch.Tensor,
         raise RuntimeError(f"patch at {origin} of size {(pd, ph, pw)} leaves the volume {(D, H, W)}")
     _lib.check(lib.ub_unpack_patch(_p(batch), cp, c_begin, c, sample, pd, ph, pw, _p(volume), z * sd + y * sh + x, sc, sd,
                                    sh, _stream()), "ub_unpack_patch")
+
+
+def paste_patch(patch: torch.Tensor, volume: torch.Tensor, origin):
+    """Write an NCDHW fp32 patch (c, pd, ph, pw) into the (c, D, H, W) fp32 ``volume`` at ``origin`` (later wins)."""
+    _require_cuda(patch, volume)
+    lib = _lib.load()
+    if patch.dtype != torch.float32 or not patch.is_contiguous():
+        patch = patch.float().contiguous()
+    if volume.dtype != torch.float32 or volume.dim() != 4 or volume.stride(-1) != 1:
+        raise RuntimeError("paste_patch writes into a (C,D,H,W) fp32 tensor with contiguous rows")
+    c, pd, ph, pw = patch.shape
+    z, y, x = origin
+    sc, sd, sh, _ = volume.stride()
+    _, D, H, W = volume.shape
+    if z < 0 or y < 0 or x < 0 or z + pd > D or y + ph > H or x + pw > W or volume.shape[0] < c:
+        raise RuntimeError(f"patch at {origin} of size {(pd, ph, pw)} leaves the volume {(D, H, W)}")
+    _lib.check(lib.ub_paste_patch(_p(patch), c, pd, ph, pw, _p(volume), z * sd + y * sh + x, sc, sd, sh, _stream()),
+               "ub_paste_patch")
 
 
 def unpack_ncdhw(x: torch.Tensor, c: int, c_begin: int = 0) -> torch.Tensor:
