@@ -12,8 +12,9 @@
 // tile, 18x10 rows), multiplied by the 9 (kh, kw) weight tiles of N = 96 rows (18 UMMAs per 32-channel
 // chunk instead of 54), and lands in one of four TMEM accumulators. The epilogue warps, one plane
 // behind, add the three 32-column slices that belong to output plane d -- same thread, three TMEM
-// loads, no cross-lane traffic -- while the MMA thread already works on the next plane (TMEM ring of
-// 5 x 96 columns). Eight epilogue warps (two per TMEM lane quarter) take alternate output planes.
+// loads, no cross-lane traffic -- while the MMA thread already works on the next planes (TMEM ring of
+// 5 x 96 columns). Eight epilogue warps (two per TMEM lane quarter, 16 output channels each) read every
+// accumulator once, as soon as it completes, and roll the partial output planes through registers.
 // The full weight set (9 x 96 x C_in bf16, <= 162 KB for the 96->32 skip-concat conv)
 // stays resident in shared memory for the CTA's lifetime.
 #pragma once
@@ -98,7 +99,7 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
     for (int i = 0; i < P.nsa; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < kMarchRing; ++i) {
       mbar_init(acc_full + 8 * i, 1);
-      mbar_init(acc_empty + 8 * i, kPair ? 2 * kMarchEpiWarps : kMarchEpiWarps);
+      mbar_init(acc_empty + 8 * i, kPair ? 2 * kMarchEpiWarps : kMarchEpiWarps);   // one arrival per epilogue warp and plane
     }
     fence_mbar_init();
   }
@@ -203,14 +204,15 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
     }
   } else {
     // =========================== epilogue (warps 0-7) ===========================
-    // warp w reads TMEM lanes 32*(w%4)..+31; group w/4 takes the output planes d_begin + group, +2, ...
-    const int q = warp & 3, grp = warp >> 2;
+    // warp w reads TMEM lanes 32*(w%4)..+31 (accumulator rows); warp group w/4 takes the output channels
+    // [16*(w/4), +16). Every input plane's accumulator is read ONCE, right when it completes, and handed
+    // back to the MMA thread immediately: its three depth slices are contributions to the output planes
+    // p+1 (kd=0), p (kd=1), p-1 (kd=2), which roll through two register sets (ra: plane p-1 so far,
+    // rb: plane p so far). The MMA thread can therefore run ring-1 planes ahead of the epilogue.
+    const int q = warp & 3, half = warp >> 2;
     const int r = q * 32 + lane;
     const int h = h0 + (r >> 3), w = w0 + (r & 7);
     const bool valid_hw = (h < P.H) && (w < P.W);
-    const bool valid_pair = (h < P.H) && ((w ^ 1) < P.W);
-    const bool odd = (lane & 1) != 0;
-    const bool valid_e = odd ? valid_pair : valid_hw, valid_o = odd ? valid_hw : valid_pair;
     const bool do_stats = P.stats != nullptr;
     float* bias_s = red + kMarchEpiWarps * 2 * 32;
     float* nbc = bias_s + 32;   // [scale | shift | rstd | -mean*rstd][32] of this CTA's sample
@@ -227,97 +229,34 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
     named_bar_sync(1, kMarchEpiWarps * 32);
     const bool has_drop = kNormBwd && P.nb_drop_p > 0.f;
     const float nb_inv = has_drop ? 1.f / (1.f - P.nb_drop_p) : 1.f;
-    float st_a[32], st_b[32];   // per-thread channel sums over this warp's planes; transposed once at the end
+    const int cb = half * 16;           // first channel of this thread
+    float bias_r[16];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { st_a[j] = 0.f; st_b[j] = 0.f; }
+    for (int j = 0; j < 16; ++j) bias_r[j] = bias_s[cb + j];
+    float st_a[16], st_b[16];           // per-thread channel sums over the CTA's planes; transposed once at the end
+    float ra[16], rb[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { st_a[j] = 0.f; st_b[j] = 0.f; ra[j] = 0.f; rb[j] = 0.f; }
     __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(P.out);
-    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-    // kNormBwd: the producer's raw output row of the NEXT plane of this warp group is prefetched into L2
-    // while the current one is processed (the HBM latency would otherwise sit in the middle of every
-    // plane); no registers are held across iterations for it
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cb;
     const size_t plane_vox = (size_t)P.H * P.W;
-    for (int d = d_begin + grp; d < d_end; d += 2) {
-      // newest plane this output needs
-      const int pnew = d + 1 <= p_last ? d + 1 : p_last;
-      const int pi = pnew - p_first;
-      const size_t vox_own = (((size_t)nb * P.D + d) * P.H + h) * P.W + w;
-      uint4 yv[4];
-      if (kNormBwd && valid_hw) {
-        const uint4* yp = reinterpret_cast<const uint4*>(P.nb_y) + vox_own * 4;
+    const size_t vox0 = (((size_t)nb * P.D) * P.H + h) * P.W + w;     // voxel of plane 0
+
+    // finish output plane d from `fin` (all three depth contributions summed): bias, bf16, store, statistics
+    auto finish_plane = [&](int d, const float (&fin)[16], const uint4 (&yv)[2]) {
+      uint32_t pk[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) yv[j] = __ldg(yp + j);
-        if (d + 2 < d_end) {
-          const uint4* yn = yp + 2 * plane_vox * 4;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(yn));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(yn + 2));
-        }
-      }
-      mbar_wait(acc_full + 8 * (pi % kMarchRing), (uint32_t)(pi / kMarchRing) & 1u);
-      tc_fence_after();
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = 0.f;
-#pragma unroll
-      for (int kd = 0; kd < 3; ++kd) {
-        const int p = d + kd - 1;
-        if (p >= 0 && p < P.D) {            // uniform over the CTA
-          uint32_t rr[32];
-          tmem_ld_32x32b_x32(lane_base + (uint32_t)(((p - p_first) % kMarchRing) * 96 + kd * 32), rr);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(rr[j]);
-        }
-      }
-      // Accumulator of input plane p is read by the outputs p-1, p, p+1, i.e. twice by one warp group
-      // and once by the other. Each group arrives after ITS last read: on plane d (read only now by
-      // this group) and on plane d-1 (read before at d-2). The first output plane of a segment also
-      // arrives for the other group, which never touches plane d_begin-1.
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (kPair) {
-          mbar_arrive_cluster(acc_empty_ld + 8 * ((d - p_first) % kMarchRing), 1u);
-          if (d - 1 >= p_first)
-            mbar_arrive_cluster(acc_empty_ld + 8 * ((d - 1 - p_first) % kMarchRing), d == d_begin ? 2u : 1u);
-        } else {
-          mbar_arrive(acc_empty + 8 * ((d - p_first) % kMarchRing));
-          if (d - 1 >= p_first) mbar_arrive_n(acc_empty + 8 * ((d - 1 - p_first) % kMarchRing), d == d_begin ? 2u : 1u);
-        }
-      }
-      uint32_t pk[16];
-      const float4* b4 = reinterpret_cast<const float4*>(bias_s);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 bv = b4[j];
-        pk[2 * j] = pack_bf16x2(v[4 * j + 0] + bv.x, v[4 * j + 1] + bv.y);
-        pk[2 * j + 1] = pack_bf16x2(v[4 * j + 2] + bv.z, v[4 * j + 3] + bv.w);
-      }
-      {
-        // lane pairs exchange half rows so that every store instruction writes whole 32-byte sectors
-        // (see igemm_fwd.cuh)
-        uint32_t sx[8], rx[8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          sx[j] = odd ? pk[j] : pk[4 + j];
-          sx[4 + j] = odd ? pk[8 + j] : pk[12 + j];
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) rx[j] = __shfl_xor_sync(0xffffffffu, sx[j], 1);
-        const size_t vox_e = (((size_t)nb * P.D + d) * P.H + h) * P.W + (w & ~1);
-        uint4* de = reinterpret_cast<uint4*>(outp + vox_e * 32) + (odd ? 1 : 0);
-        uint4* d_o = de + 4;
-        if (valid_e) {
-          __stcs(de + 0, odd ? make_uint4(rx[0], rx[1], rx[2], rx[3]) : make_uint4(pk[0], pk[1], pk[2], pk[3]));
-          __stcs(de + 2, odd ? make_uint4(rx[4], rx[5], rx[6], rx[7]) : make_uint4(pk[8], pk[9], pk[10], pk[11]));
-        }
-        if (valid_o) {
-          __stcs(d_o + 0, odd ? make_uint4(pk[4], pk[5], pk[6], pk[7]) : make_uint4(rx[0], rx[1], rx[2], rx[3]));
-          __stcs(d_o + 2, odd ? make_uint4(pk[12], pk[13], pk[14], pk[15]) : make_uint4(rx[4], rx[5], rx[6], rx[7]));
-        }
+      for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(fin[2 * j] + bias_r[2 * j], fin[2 * j + 1] + bias_r[2 * j + 1]);
+      const size_t vox = vox0 + (size_t)d * plane_vox;
+      if (valid_hw) {
+        // 16 channels = 32 bytes = one whole sector of this voxel row
+        uint4* dst = reinterpret_cast<uint4*>(outp + vox * 32 + cb);
+        __stcs(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        __stcs(dst + 1, make_uint4(pk[4], pk[5], pk[6], pk[7]));
       }
       if (!kNormBwd && do_stats && valid_hw) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
           const float lo = __uint_as_float(pk[j] << 16);
           const float hi = __uint_as_float(pk[j] & 0xFFFF0000u);
           st_a[2 * j] += lo; st_a[2 * j + 1] += hi;
@@ -329,51 +268,100 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
         // st_a accumulates sum dz, st_b accumulates sum dz * y; xhat = y * rstd - mean * rstd is applied
         // once per thread after the loop.
         const uint32_t* yw = reinterpret_cast<const uint32_t*>(yv);
-        const float4* sc4 = reinterpret_cast<const float4*>(nbc);
-        const float4* sh4 = reinterpret_cast<const float4*>(nbc + 32);
 #pragma unroll
-        for (int o8 = 0; o8 < 4; ++o8) {
+        for (int o8 = 0; o8 < 2; ++o8) {
           float f[8];
           if (has_drop) {
-            dropout_factors8((unsigned long long)vox_own * 32ull + o8 * 8, P.nb_drop_seed, P.nb_drop_thresh, nb_inv, f);
+            dropout_factors8((unsigned long long)vox * 32ull + cb + o8 * 8, P.nb_drop_seed, P.nb_drop_thresh, nb_inv, f);
           } else {
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[k] = 1.f;
           }
 #pragma unroll
-          for (int k4 = 0; k4 < 2; ++k4) {
-            const float4 sc = sc4[o8 * 2 + k4], sh = sh4[o8 * 2 + k4];
-            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int c = o8 * 8 + k4 * 4 + k;
-              const uint32_t dw = pk[c >> 1], yy = yw[c >> 1];
-              const float da = __uint_as_float((c & 1) ? (dw & 0xFFFF0000u) : (dw << 16));
-              const float yf = __uint_as_float((c & 1) ? (yy & 0xFFFF0000u) : (yy << 16));
-              const float fk = f[k4 * 4 + k];
-              const float dz = da * (fmaf(yf, scv[k], shv[k]) > 0.f ? fk : fk * P.nb_slope);
-              st_a[c] += dz;
-              st_b[c] = fmaf(dz, yf, st_b[c]);
-            }
+          for (int k = 0; k < 8; ++k) {
+            const int c = o8 * 8 + k;
+            const uint32_t dw = pk[c >> 1], yy = yw[c >> 1];
+            const float da = __uint_as_float((c & 1) ? (dw & 0xFFFF0000u) : (dw << 16));
+            const float yf = __uint_as_float((c & 1) ? (yy & 0xFFFF0000u) : (yy << 16));
+            const float dz = da * (fmaf(yf, nbc[cb + c], nbc[32 + cb + c]) > 0.f ? f[k] : f[k] * P.nb_slope);
+            st_a[c] += dz;
+            st_b[c] = fmaf(dz, yf, st_b[c]);
           }
         }
       }
+    };
+
+    for (int p = p_first; p <= p_last; ++p) {
+      const int pi = p - p_first;
+      const int slot = pi % kMarchRing;
+      // the output plane this step completes is p-1: fetch its producer-block row early (kNormBwd)
+      const int dfin = p - 1;
+      const bool fin_ok = dfin >= d_begin && dfin < d_end;
+      uint4 yv[2];
+      if (kNormBwd && valid_hw && fin_ok) {
+        const uint4* yp = reinterpret_cast<const uint4*>(P.nb_y) + (vox0 + (size_t)dfin * plane_vox) * 4 + half * 2;
+        yv[0] = __ldg(yp);
+        yv[1] = __ldg(yp + 1);
+        if (dfin + 1 < d_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + plane_vox * 4));
+      }
+      mbar_wait(acc_full + 8 * slot, (uint32_t)(pi / kMarchRing) & 1u);
+      tc_fence_after();
+      uint32_t v0[16], v1[16], v2[16];
+      const uint32_t ta = lane_base + (uint32_t)(slot * 96);
+      tmem_ld_32x32b_x16(ta, v0);           // kd = 0 -> output plane p+1
+      tmem_ld_32x32b_x16(ta + 32, v1);      // kd = 1 -> output plane p
+      tmem_ld_32x32b_x16(ta + 64, v2);      // kd = 2 -> output plane p-1
+      tmem_ld_wait();
+      // the accumulator is in registers: hand the slot back before doing anything else
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(acc_empty_ld + 8 * slot, 1u);
+        else mbar_arrive(acc_empty + 8 * slot);
+      }
+      float fin[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        fin[j] = ra[j] + __uint_as_float(v2[j]);
+        ra[j] = rb[j] + __uint_as_float(v1[j]);
+        rb[j] = __uint_as_float(v0[j]);
+      }
+      if (fin_ok) finish_plane(dfin, fin, yv);
+    }
+    // the last output plane of the volume has no plane behind it: ra already holds its full sum
+    if (p_last == d_end - 1) {
+      uint4 yv[2];
+      if (kNormBwd && valid_hw) {
+        const uint4* yp = reinterpret_cast<const uint4*>(P.nb_y) + (vox0 + (size_t)p_last * plane_vox) * 4 + half * 2;
+        yv[0] = __ldg(yp);
+        yv[1] = __ldg(yp + 1);
+      }
+      finish_plane(p_last, ra, yv);
     }
     if (kNormBwd) {
       // S2 = sum dz * xhat = rstd * sum dz*y - mean*rstd * sum dz
 #pragma unroll
-      for (int c = 0; c < 32; ++c) st_b[c] = fmaf(nbc[64 + c], st_b[c], nbc[96 + c] * st_a[c]);
+      for (int c = 0; c < 16; ++c) st_b[c] = fmaf(nbc[64 + cb + c], st_b[c], nbc[96 + cb + c] * st_a[c]);
     }
     if (do_stats || kNormBwd) {
-      const float s_acc = warp_transpose_reduce32(st_a, lane);
-      const float q_acc = warp_transpose_reduce32(st_b, lane);
-      red[(warp * 2 + 0) * 32 + lane] = s_acc;
-      red[(warp * 2 + 1) * 32 + lane] = q_acc;
+      float ta_[32], tb_[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { ta_[j] = j < 16 ? st_a[j] : 0.f; tb_[j] = j < 16 ? st_b[j] : 0.f; }
+      const float s_acc = warp_transpose_reduce32(ta_, lane);   // lane l < 16: total of channel cb + l
+      const float q_acc = warp_transpose_reduce32(tb_, lane);
+      if (lane < 16) {
+        red[(warp * 2 + 0) * 32 + lane] = s_acc;
+        red[(warp * 2 + 1) * 32 + lane] = q_acc;
+      }
       named_bar_sync(1, kMarchEpiWarps * 32);
       if (threadIdx.x < 32) {
+        const int hh = lane >> 4, cl = lane & 15;     // channel lane = hh * 16 + cl, summed over the 4 lane quarters
         float s = 0.f, qq = 0.f;
 #pragma unroll
-        for (int wq = 0; wq < kMarchEpiWarps; ++wq) { s += red[(wq * 2 + 0) * 32 + lane]; qq += red[(wq * 2 + 1) * 32 + lane]; }
+        for (int wq = 0; wq < 4; ++wq) {
+          s += red[((hh * 4 + wq) * 2 + 0) * 32 + cl];
+          qq += red[((hh * 4 + wq) * 2 + 1) * 32 + cl];
+        }
         float* st = P.stats + (size_t)item * 64;
         st[lane] = s;
         st[32 + lane] = qq;

@@ -324,9 +324,9 @@ static int launch_march(const void* src0, int c0p, const void* src1, int c1p, in
   P.out = out; P.bias = bias; P.bias_n = bias_n; P.stats = stats;
   // CTA pairs (cta_group::2) whenever the w tiles pair up; UB_MARCH_PAIR=0 forces the single-CTA kernel
   static const bool pair_enabled = !(getenv("UB_MARCH_PAIR") && atoi(getenv("UB_MARCH_PAIR")) == 0);
-  // (a plane must be long enough to hide the cross-CTA accumulator hand-off: measured on B200 at 8x128^3,
-  // 1 K chunk 854 vs 1183 TFLOP/s single-CTA, 2 chunks 1324 vs 1330, 3 chunks 1538 vs 1360)
-  static const int pair_min_chunks = getenv("UB_MARCH_PAIR_MIN_CHUNKS") ? atoi(getenv("UB_MARCH_PAIR_MIN_CHUNKS")) : 3;
+  // (a plane must be long enough to amortise the cross-CTA barrier traffic: measured on B200 at 8x128^3,
+  // 1 K chunk 805 vs 1200 TFLOP/s single-CTA, 2 chunks 1374 vs 1330, 3 chunks 1576 vs 1360)
+  static const int pair_min_chunks = getenv("UB_MARCH_PAIR_MIN_CHUNKS") ? atoi(getenv("UB_MARCH_PAIR_MIN_CHUNKS")) : 2;
   const bool pair = pair_enabled && (P.tiles_w % 2 == 0) && P.n_chunks_total >= pair_min_chunks;
   const int wbytes = P.n_chunks_total * 9 * (pair ? kMarchWTileBytes / 2 : kMarchWTileBytes);
   const int misc = 8 * 32 + 64 + (kMarchEpiWarps * 2 * 32 + 32 + 128) * 4 + 64 + 1024;
