@@ -99,7 +99,9 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
     for (int i = 0; i < P.nsa; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < kMarchRing; ++i) {
       mbar_init(acc_full + 8 * i, 1);
-      mbar_init(acc_empty + 8 * i, kPair ? 2 * kMarchEpiWarps : kMarchEpiWarps);   // one arrival per epilogue warp and plane
+      // single CTA: one arrival per epilogue warp and plane; pair: ONE arrival per CTA and plane (the eight
+      // warps meet at a named barrier first -- remote mbarrier arrivals are expensive)
+      mbar_init(acc_empty + 8 * i, kPair ? 2 : kMarchEpiWarps);
     }
     fence_mbar_init();
   }
@@ -314,10 +316,12 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
       tmem_ld_wait();
       // the accumulator is in registers: hand the slot back before doing anything else
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (kPair) mbar_arrive_cluster(acc_empty_ld + 8 * slot, 1u);
-        else mbar_arrive(acc_empty + 8 * slot);
+      if (kPair) {
+        named_bar_sync(2, kMarchEpiWarps * 32);
+        if (threadIdx.x == 0) mbar_arrive_cluster(acc_empty_ld + 8 * slot, 1u);
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + 8 * slot);
       }
       float fin[16];
 #pragma unroll

@@ -152,6 +152,54 @@ def _block_forward(blk: _Block, cache: _PackedWeights, src0, src1, training, see
     return a, pooled, sv
 
 
+# ---------------------------------------------------------------------------------------------------
+# weight gradients on a side stream. In the backward pass the chain  norm/act backward -> dgrad -> norm/act
+# backward -> ...  is strictly sequential, while the weight gradient of a block only needs that block's dy.
+# The wgrad kernels are tensor / shared-memory bound and leave HBM idle; the norm/activation backward
+# passes are HBM bound and use neither shared memory nor TMEM, so their thread blocks co-reside with the
+# wgrad CTAs on the same SMs. (wgrad and dgrad cannot co-reside -- both want the whole TMEM -- and simply
+# interleave.) UB_WGRAD_STREAM=0 keeps everything on one stream.
+# ---------------------------------------------------------------------------------------------------
+import os as _os
+
+_WGRAD_SIDE = _os.environ.get("UB_WGRAD_STREAM", "1") != "0"
+_side_streams = {}
+
+
+def _side_stream(device):
+    st = _side_streams.get(device)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _side_streams[device] = st
+    return st
+
+
+def _wgrad_async(spec, src0, src1, dy, weight_shape, ready=None):
+    """conv_wgrad on the side stream, ordered after ``ready`` (an event recorded once dy was complete; default:
+    everything enqueued so far on the current stream). The caller joins with ``_join_side_stream`` before
+    the gradients leave the backward function."""
+    if not _WGRAD_SIDE:
+        return ops.conv_wgrad(spec, src0, src1, dy, weight_shape)
+    main = torch.cuda.current_stream()
+    side = _side_stream(dy.device)
+    if ready is not None:
+        side.wait_event(ready)
+    else:
+        side.wait_stream(main)
+    with torch.cuda.stream(side):
+        dw = ops.conv_wgrad(spec, src0, src1, dy, weight_shape)
+    for t in (src0, src1, dy):
+        if t is not None:
+            t.record_stream(side)          # the caching allocator must not recycle them under the side stream
+    dw.record_stream(main)
+    return dw
+
+
+def _join_side_stream(device):
+    if _WGRAD_SIDE and device in _side_streams:
+        torch.cuda.current_stream().wait_stream(_side_streams[device])
+
+
 def _fusion_of(blk: _Block, sv: _Saved):
     """Norm-backward fusion descriptor of a block whose dA a downstream dgrad is about to produce."""
     if blk.norm is None or sv is None or sv.y is None or sv.y.shape[-1] != 32:
@@ -183,16 +231,24 @@ def _block_backward(blk: _Block, cache: _PackedWeights, sv: _Saved, dA, need_w, 
             dy = dA
         if need_w:
             grads[id(blk.conv.bias)] = ops.colsum(dy, co)
-    if need_w:
-        grads[id(blk.conv.weight)] = ops.conv_wgrad(spec, sv.src0, sv.src1, dy, tuple(blk.conv.weight.shape))
+    # The dgrad (the critical chain) is enqueued FIRST; the wgrad goes to the side stream afterwards, ordered
+    # only after dy: it then fills the SMs while the next block's memory-bound norm/activation backward runs.
+    dy_ready = None
+    if need_w and need_in and _WGRAD_SIDE:
+        dy_ready = torch.cuda.Event()
+        dy_ready.record()
+    result = (None, None, None)
     if need_in:
         wd = cache.get(spec, blk.conv.weight, 1)
         fuse = _fusion_of(*producer) if producer is not None else None
         if fuse is not None and ops.dgrad_fuse_records(spec, dy.shape[0], *sv.in_dhw) > 0:
-            return ops.conv_dgrad(spec, dy, wd, sv.in_dhw, fuse=fuse)
-        d0, d1 = ops.conv_dgrad(spec, dy, wd, sv.in_dhw)
-        return d0, d1, None
-    return None, None, None
+            result = ops.conv_dgrad(spec, dy, wd, sv.in_dhw, fuse=fuse)
+        else:
+            d0, d1 = ops.conv_dgrad(spec, dy, wd, sv.in_dhw)
+            result = (d0, d1, None)
+    if need_w:
+        grads[id(blk.conv.weight)] = _wgrad_async(spec, sv.src0, sv.src1, dy, tuple(blk.conv.weight.shape), ready=dy_ready)
+    return result
 
 
 class _InputPackCache:
@@ -388,6 +444,7 @@ class _ChainFunction(torch.autograd.Function):
             dA = d0
         dx = ops.unpack_ncdhw(d0, ctx.cx, 0).to(ctx.in_dtype) if need_x else None
         dy = ops.unpack_ncdhw(d0, ctx.cy, ctx.cx).to(ctx.in_dtype) if need_y else None
+        _join_side_stream(dout.device)
         ctx.saved = None
         pg = [grads.get(id(p)) if pneed[id(p)] else None for p in chain.params]
         return (dx, dy, None, None, *pg)
@@ -567,6 +624,7 @@ class _GeneratorFunction(torch.autograd.Function):
             dcur, _, _ = bwd(net.head, dcur, need_in=need_x, partial=part_head)
         if need_x:
             dx = ops.unpack_ncdhw(dcur, ctx.cx).to(ctx.in_dtype)
+        _join_side_stream(dout.device)
         ctx.S = None
         pg = [grads.get(id(p)) if pneed[id(p)] else None for p in net.params]
         return (dx, None, None, *pg)
