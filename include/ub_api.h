@@ -187,6 +187,31 @@ int ub_relerr_map_reduce(const float* pred, const float* target, const unsigned 
 int ub_dti_scalar_maps(const float* tensor6, long long voxels, float* fa, float* md, float* ad, float* rd,
                        float* azimuth, float* inclination, float* rgb, void* stream);
 
+/* ---- optimiser ------------------------------------------------------------------ */
+/* torch.optim.AdamW (ref:src/model.py:144,164,359-361: lr 1e-3, betas (0.9, 0.999), eps 1e-8, weight decay 0.01)
+ * over `count` parameter tensors in as few launches as the pointer table allows. `tensors` is a HOST array;
+ * p / g / m / v are device pointers to fp32 arrays of numel elements (parameter, gradient, exp_avg, exp_avg_sq),
+ * updated in place. step >= 1 is the number of this update (bias corrections 1 - beta^step, computed on the
+ * host). grad_scale multiplies the gradient first (1 / world_size after a SUM all-reduce; otherwise 1). */
+typedef struct {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  long long numel;
+} ub_adamw_tensor;
+int ub_adamw_step(const ub_adamw_tensor* tensors, int count, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, long long step, float grad_scale, void* stream);
+
+/* ---- prediction volume -> NIfTI storage order ------------------------------------- */
+/* ref:src/model.py:335-357 (save_predicitions: np.moveaxis(volume, 0, -1) -> Nifti1Image) followed by
+ * ref:src/eval.py:39-47 (do_invert_dwi_tensor_norm: v * |max - min| + min in float64, stored as the header's
+ * float32). src: one volume in module layout [c][x][y][z] fp32 (z fastest); dst: the data block of a NIfTI-1
+ * file holding the channel-last array (x, y, z, c), i.e. [c][z][y][x] with x fastest. scale = 1, offset = 0
+ * gives the plain layout change. */
+int ub_denorm_to_nifti(const float* src, int c, int x, int y, int z, double scale, double offset, float* dst,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,10 +7,14 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline leg
                       ``np.linalg.eigh(..., 'U')``, which runs the same LAPACK routine per matrix)
 * ``roi_error_avg``   ref:src/eval.py:217-258 (do_calc_error_avg; file-name parsing, pandas and NIfTI
                       I/O stripped -- the arithmetic of lines 238-249 is kept verbatim in meaning)
+* ``invert_dwi_tensor_norm`` ref:src/eval.py:39-47 (do_invert_dwi_tensor_norm; min-max de-normalisation)
 
-PARITY PIN: the reference has no tests or golden vectors for these functions (SURVEY.md section 4);
-pinned by hand-checkable cases in tests/test_oracle_cpu.py (zeros -> inf -> 0, NaN kept, angular
-wrap-around) and the committed goldens generated from THIS file (tests/golden/make_golden.py).
+PARITY PIN: the reference has no tests or golden vectors of its own for these functions (SURVEY.md
+section 4). Pinned by (1) ``tests/golden/golden_ref_v1.npz``: outputs of the reference's OWN
+``do_calc_diff_maps / do_calc_error_avg / do_calc_scalar_maps / do_invert_dwi_tensor_norm``, executed
+unmodified from /root/reference/src/eval.py by ``tests/golden/make_golden_ref.py`` (nibabel replaced by an
+in-memory image store), checked in ``tests/test_reference_golden_cpu.py``; (2) hand-checkable cases in
+tests/test_oracle_cpu.py (zeros -> inf -> 0, NaN kept, angular wrap-around).
 """
 import numpy as np
 
@@ -44,6 +48,14 @@ def roi_error_avg(diff, mask, probseg):
             norm = probseg[..., roi_idx].sum()
             errs[roi_idx, i] = segmented.sum() / norm
     return errs, diff_map
+
+
+def invert_dwi_tensor_norm(data, min_v, max_v):
+    """ref:src/eval.py:39-47: data * |max - min| + min per channel, float64 like get_fdata()."""
+    data = np.array(data, dtype=np.float64)
+    for i in range(data.shape[-1]):
+        data[..., i] = (data[..., i] * np.abs(max_v - min_v)) + min_v
+    return data
 
 
 def dti_scalar_maps(data, canonical_sign=False):

@@ -221,16 +221,16 @@ def test_full_step_runs_and_updates_both_networks():
     assert all(p.requires_grad for p in list(g.parameters()) + list(d.parameters()))
 
 
-@pytest.mark.parametrize("fused", [True, False])
-def test_updated_weights_are_used_after_optimizer_steps(fused):
+@pytest.mark.parametrize("optimizer", ["ub", "torch_fused", "torch"])
+def test_updated_weights_are_used_after_optimizer_steps(optimizer):
     """The bf16 operand copies of the weights must follow the fp32 Parameters through optimizer steps.
-    torch's fused AdamW writes parameters without bumping ``tensor._version`` (regression: the packed
+    torch's fused AdamW and this package's FusedAdamW kernel write parameters without bumping ``tensor._version`` (regression: the packed
     weights stayed at their initial values): after two full steps the modules must agree with an oracle
     that is loaded with the UPDATED state dict -- and disagree with the initial-weight output."""
     strict_fp32()
     O, og, od, g, d = _pair("bssfp")
     from unet_bssfp_b200.train_step import GanTrainer
-    tr = GanTrainer(g, d, lr=2e-2, fused_optimizer=fused)
+    tr = GanTrainer(g, d, lr=2e-2, optimizer=optimizer)
     torch.manual_seed(3)
     x = torch.rand(1, 24, 32, 32, 32, device=DEV)
     y = torch.rand(1, 6, 32, 32, 32, device=DEV)

@@ -1,0 +1,158 @@
+"""GPU parity of the sm_100a path against golden vectors produced by the REFERENCE'S OWN CODE
+(tests/golden/golden_ref_v1.npz, written by tests/golden/make_golden_ref.py from /root/reference/src/model.py and
+eval.py run unmodified; see that script for what its stand-ins replace). Nothing here reads /root/reference.
+
+Tolerances: bf16 end-to-end bar of tests/test_model_gpu.py (forward rel-L2 <= 2e-2 through 24 stacked bf16
+layers), losses within 3 %, evaluation maps 1e-4 (north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.golden.make_golden_ref import state_checksum, synth_batch
+from tests.util import rel_l2
+
+pytestmark = pytest.mark.gpu
+REF = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_ref_v1.npz"))
+DEV = "cuda"
+
+
+def _fresh(mod):
+    import unet_bssfp_b200 as ub
+    torch.manual_seed(0)
+    g, d = ub.Generator(mod), ub.Discriminator(mod)
+    if abs(state_checksum(g) - float(REF[f"{mod}_g_checksum"])) > 1e-9 * float(REF[f"{mod}_g_checksum"]):
+        pytest.skip("default torch init differs from the torch version that generated the goldens")
+    assert abs(state_checksum(d) - float(REF[f"{mod}_d_checksum"])) <= 1e-9 * float(REF[f"{mod}_d_checksum"])
+    g.blocks["unet"].dropout = 0.0
+    return g.to(DEV), d.to(DEV)
+
+
+@pytest.mark.parametrize("mod", ["bssfp", "t1w"])
+def test_networks_match_reference_outputs(mod):
+    g, d = _fresh(mod)
+    assert list(g.state_dict().keys()) == list(REF[f"{mod}_g_keys"])
+    assert list(d.state_dict().keys()) == list(REF[f"{mod}_d_keys"])
+    xb, yb = synth_batch(24 if mod == "bssfp" else 6)
+    xb, yb = xb.to(DEV), yb.to(DEV)
+    g.eval()
+    with torch.no_grad():
+        got = g(xb[:1]).cpu()
+    assert rel_l2(got, torch.from_numpy(REF[f"{mod}_g_eval_32"])) < 2e-2
+    for mode, key in (("train", "d_train_32_b2"), ("eval", "d_eval_32_b2")):
+        getattr(d, mode)()
+        with torch.no_grad():
+            logits = d(xb, yb).cpu().numpy()
+        ref = REF[f"{mod}_{key}"]
+        assert np.abs(logits - ref).max() < 3e-2 * max(1.0, np.abs(ref).max()), (mode, logits.ravel(), ref.ravel())
+    # _gen_step / _discr_step of the reference's LightningModule, train mode, dropout 0, fresh weights
+    from unet_bssfp_b200.train_step import GanTrainer
+    g, d = _fresh(mod)
+    g.train(); d.train()
+    tr = GanTrainer(g, d)
+    with torch.no_grad():
+        gl, y_hat = tr.gen_loss(xb, yb)
+        dl = tr.discr_loss(xb, yb)
+        recon = tr.recon_loss(y_hat, yb)
+    assert abs(gl.item() / float(REF[f"{mod}_gen_loss"]) - 1) < 0.03
+    assert abs(dl.item() - float(REF[f"{mod}_discr_loss"])) < 0.03
+    assert abs(recon.item() / float(REF[f"{mod}_gen_loss_recon"]) - 1) < 0.02
+
+
+def test_phase_gradients_match_reference():
+    """Weight gradients of the G phase (D frozen) and the D phase against the reference's manual_backward."""
+    from unet_bssfp_b200.train_step import GanTrainer
+    g, d = _fresh("bssfp")
+    g.train(); d.train()
+    tr = GanTrainer(g, d)
+    xb, yb = synth_batch(24)
+    xb, yb = xb.to(DEV), yb.to(DEV)
+    for p in d.parameters():
+        p.requires_grad_(False)
+    gl, _ = tr.gen_loss(xb, yb)
+    gl.backward()
+    assert all(p.grad is None for p in d.parameters())
+    gp = dict(g.named_parameters(remove_duplicate=False))
+    errs = {}
+    for k in [k for k in REF.files if k.startswith("bssfp_ggrad::")]:
+        errs[k] = rel_l2(gp[k.split("::")[1]].grad.cpu(), torch.from_numpy(REF[k]))
+    # bf16 through LeakyReLU / max-pool sign flips: per-tensor errors of a few 1e-2 .. 1e-1 are what stock bf16
+    # autocast shows too (tests/test_model_gpu.py measures that yardstick); here a fixed bar on the goldens
+    assert max(errs.values()) < 0.35 and float(np.median(list(errs.values()))) < 0.15, errs
+    for p in d.parameters():
+        p.requires_grad_(True)
+    g.zero_grad(set_to_none=True)
+    for p in g.parameters():
+        p.requires_grad_(False)
+    dl = tr.discr_loss(xb, yb)
+    dl.backward()
+    assert all(p.grad is None for p in g.parameters())
+    dp = dict(d.named_parameters(remove_duplicate=False))
+    errs = {}
+    for k in [k for k in REF.files if k.startswith("bssfp_dgrad::")]:
+        errs[k] = rel_l2(dp[k.split("::")[1]].grad.cpu(), torch.from_numpy(REF[k]))
+    assert max(errs.values()) < 0.35 and float(np.median(list(errs.values()))) < 0.15, errs
+
+
+def test_three_training_steps_track_the_reference():
+    """GanTrainer.step x 3 (our AdamW kernel, both phases) against three reference training_step calls."""
+    from unet_bssfp_b200.train_step import GanTrainer
+    g, d = _fresh("bssfp")
+    g.train(); d.train()
+    tr = GanTrainer(g, d)
+    xb, yb = synth_batch(24)
+    xb, yb = xb.to(DEV), yb.to(DEV)
+    gls, dls = [], []
+    for _ in range(3):
+        gl, dl = tr.step(xb, yb)
+        gls.append(float(gl)); dls.append(float(dl))
+    # AdamW's first updates are +-lr per weight whatever the gradient magnitude, so bf16 sign noise moves the
+    # trajectory; the losses still follow the reference's closely on three steps
+    np.testing.assert_allclose(gls, REF["bssfp_train3_gen_loss"], rtol=0.05)
+    np.testing.assert_allclose(dls, REF["bssfp_train3_discr_loss"], rtol=0.15, atol=0.05)
+    assert int(d.d2.bn.num_batches_tracked) == int(REF["bssfp_train3_num_batches_tracked_d2"])
+    np.testing.assert_allclose(g.blocks["bssfp"].bn.running_var.cpu().numpy(), REF["bssfp_train3_head_running_var"],
+                               rtol=2e-2)
+
+
+def test_eval_kernels_match_reference_outputs():
+    from unet_bssfp_b200 import ops
+    pred, tgt = torch.from_numpy(REF["eval_pred"]).to(DEV), torch.from_numpy(REF["eval_target"]).to(DEV)
+    mask, probseg = torch.from_numpy(REF["eval_mask"]).to(DEV), torch.from_numpy(REF["eval_probseg"]).to(DEV)
+    diff, sums, norms = ops.relerr_map_reduce(pred, tgt, mask, probseg, angular=False)
+    np.testing.assert_allclose(diff.cpu().numpy(), REF["eval_diff_rel"], rtol=1e-4, atol=1e-6, equal_nan=True)
+    np.testing.assert_allclose((sums / norms[:, None]).cpu().numpy(), REF["eval_errs_rel"], rtol=1e-4, equal_nan=True)
+    ap = torch.from_numpy(REF["eval_ang_pred"][..., None].copy()).to(DEV)
+    at = torch.from_numpy(REF["eval_ang_target"][..., None].copy()).to(DEV)
+    diff, sums, norms = ops.relerr_map_reduce(ap, at, mask, probseg, angular=True)
+    np.testing.assert_allclose(diff.cpu().numpy()[..., 0], REF["eval_diff_ang"], rtol=1e-4, atol=2e-4)
+    np.testing.assert_allclose((sums / norms[:, None]).cpu().numpy(), REF["eval_errs_ang"], rtol=1e-4)
+
+
+def test_dti_maps_match_reference_outputs():
+    """ub_dti_scalar_maps against the reference's own per-voxel np.linalg.eigh loop (ref:src/eval.py:73-135).
+    Sign-free maps at 1e-4; the angles up to the antipode LAPACK's implementation-defined sign allows."""
+    from unet_bssfp_b200 import ops
+    got = {k: v.cpu().numpy() for k, v in ops.dti_scalar_maps(torch.from_numpy(REF["dti_tensor6"]).to(DEV)).items()}
+    for k in ("fa", "md", "ad", "rd", "rgb"):
+        np.testing.assert_allclose(got[k], REF[f"dti_{k}"], rtol=1e-4, atol=1e-7, err_msg=k)
+    inc, az = got["inclination"], got["azimuth"]
+    same = (np.abs(inc - REF["dti_inclination"]) < 2e-3)
+    anti = (np.abs(inc - (180 - REF["dti_inclination"])) < 2e-3)
+    assert (same | anti).all()
+    daz = np.abs(az - REF["dti_azimuth"])
+    daz = np.minimum(daz, 360 - daz)
+    assert ((daz < 2e-3) | (np.abs(daz - 180) < 2e-3)).all()
+    assert ((daz < 2e-3) == same)[~(same & anti)].all()        # azimuth flips exactly where the axis is the antipode
+
+
+def test_denormalised_volume_matches_reference_output():
+    """ub_denorm_to_nifti (N4) against do_invert_dwi_tensor_norm run on the reference (stored as float32)."""
+    from unet_bssfp_b200 import nifti
+    pred = REF["eval_pred"]                                       # (X,Y,Z,C) channel-last as the reference stores it
+    vol = torch.from_numpy(np.moveaxis(pred, -1, 0).copy()).to(DEV)   # module layout (C,X,Y,Z)
+    lo, hi = REF["denorm_minmax"]
+    block = nifti.volume_to_nifti_order(vol, (lo, hi)).cpu().numpy()  # (C,Z,Y,X)
+    got = block.transpose(3, 2, 1, 0)                             # logical (X,Y,Z,C)
+    np.testing.assert_array_equal(got, REF["denorm_out"].astype(np.float32))   # bit-exact after the float32 store

@@ -10,3 +10,5 @@ from .modules import (BasicUNet, BCEWithLogitsLoss, Discriminator, DownSampleCon
                       L1Loss, invalidate_packed_weights)
 from . import ops  # noqa: E402,F401
 from . import inference  # noqa: E402,F401
+from . import nifti  # noqa: E402,F401
+from .optim import FusedAdamW  # noqa: E402,F401

@@ -23,6 +23,11 @@ class NormBwdFuse(C.Structure):
                 ("partial", C.c_void_p)]
 
 
+class AdamWTensor(C.Structure):
+    """Mirror of ``ub_adamw_tensor`` (include/ub_api.h)."""
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("numel", C.c_longlong)]
+
+
 class ConvDesc(C.Structure):
     """Mirror of ``ub_conv_desc`` (include/ub_api.h)."""
     _fields_ = [(k, C.c_int) for k in ("kind", "n", "d", "h", "w", "c0", "c0p", "c1", "c1p", "co", "cop")]
@@ -74,6 +79,8 @@ SIGNATURES = {
     "ub_scale": (_I, [_P, _P, _LL, _P, _P]),
     "ub_dti_scalar_maps": (_I, [_P, _LL, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ub_relerr_map_reduce": (_I, [_P, _P, _P, _P, _I, _I, _LL, _I, _P, _P, _P, _P]),
+    "ub_adamw_step": (_I, [C.POINTER(AdamWTensor), _I, _F, _F, _F, _F, _F, _LL, _F, _P]),
+    "ub_denorm_to_nifti": (_I, [_P, _I, _I, _I, _I, _D, _D, _P, _P]),
 }
 
 _lib = None

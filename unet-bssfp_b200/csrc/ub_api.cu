@@ -12,6 +12,7 @@
 #include "igemm_march.cuh"
 #include "wgrad_march.cuh"
 #include "pointwise.cuh"
+#include "optim_io.cuh"
 
 using namespace ub;
 
@@ -1254,5 +1255,53 @@ extern "C" int ub_conv1x1_from_ncdhw_bwd(const float* dout, int co, const void* 
     conv1x1_bwd_finish_kernel<<<(kC1MaxCo * 33 + 127) / 128, 128, 0, st>>>(part, (int)(blocks * n), co, ci, dw, db);
     UB_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------
+// N3: multi-tensor AdamW (ref:src/model.py:359-361); N4: de-normalised volume in NIfTI storage order
+// --------------------------------------------------------------------------------------------------
+extern "C" int ub_adamw_step(const ub_adamw_tensor* tensors, int count, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, long long step, float grad_scale, void* stream) {
+  if (count < 0 || (count > 0 && !tensors) || step < 1) return fail(-1, "bad arguments to ub_adamw_step");
+  if (!(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f && lr >= 0.f))
+    return fail(-1, "ub_adamw_step: invalid hyper-parameters");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  AdamWBatch B;
+  B.lr = lr; B.beta1 = beta1; B.beta2 = beta2; B.eps = eps;
+  B.decay_mul = (float)(1.0 - (double)lr * (double)weight_decay);
+  B.step_size = (float)((double)lr / bc1);
+  B.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  B.grad_scale = grad_scale;
+  cudaStream_t st = (cudaStream_t)stream;
+  int i = 0;
+  while (i < count) {
+    B.count = 0;
+    B.block_begin[0] = 0;
+    while (i < count && B.count < kAdamWMaxTensors) {
+      const ub_adamw_tensor& t = tensors[i++];
+      if (t.numel == 0) continue;
+      if (!t.p || !t.g || !t.m || !t.v || t.numel < 0 || t.numel >= (1ll << 31))
+        return fail(-1, "ub_adamw_step: tensor %d has a null pointer or an unsupported size", i - 1);
+      const int k = B.count++;
+      B.p[k] = t.p; B.g[k] = t.g; B.m[k] = t.m; B.v[k] = t.v;
+      B.numel[k] = (int)t.numel;
+      B.block_begin[k + 1] = B.block_begin[k] + (int)((t.numel + kAdamWChunk - 1) / kAdamWChunk);
+    }
+    if (B.count == 0) break;
+    adamw_multi_kernel<<<(unsigned)B.block_begin[B.count], 256, 0, st>>>(B);
+    UB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int ub_denorm_to_nifti(const float* src, int c, int x, int y, int z, double scale, double offset, float* dst,
+                                  void* stream) {
+  if (!src || !dst || c <= 0 || x <= 0 || y <= 0 || z <= 0) return fail(-1, "bad arguments to ub_denorm_to_nifti");
+  if ((long long)c * y > 65535) return fail(-2, "ub_denorm_to_nifti: channels x Y must not exceed 65535");
+  const dim3 grid((unsigned)((z + 31) / 32), (unsigned)((x + 31) / 32), (unsigned)(c * y));
+  denorm_to_nifti_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, dst, x, y, z, scale, offset);
+  UB_LAUNCH_CHECK();
   return 0;
 }

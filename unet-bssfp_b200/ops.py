@@ -20,7 +20,7 @@ __all__ = [
     "ConvSpec", "pad32", "pack_conv_weights", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv1x1_to_ncdhw", "conv1x1_from_ncdhw_bwd", "pack_ncdhw", "unpack_ncdhw",
     "pack_patches", "unpack_patch", "paste_patch",
     "norm_finalize", "norm_act_fwd", "norm_act_bwd", "maxpool_bwd", "colsum", "l1_fwd", "l1_bwd", "bce_logits",
-    "scale_by", "relerr_map_reduce", "dti_scalar_maps",
+    "scale_by", "relerr_map_reduce", "dti_scalar_maps", "denorm_to_nifti",
 ]
 
 
@@ -457,4 +457,18 @@ def dti_scalar_maps(tensor6: torch.Tensor):
     _lib.check(lib.ub_dti_scalar_maps(_p(t), t.numel() // 6, _p(out["fa"]), _p(out["md"]), _p(out["ad"]), _p(out["rd"]),
                                       _p(out["azimuth"]), _p(out["inclination"]), _p(out["rgb"]), _stream()),
                "ub_dti_scalar_maps")
+    return out
+
+
+def denorm_to_nifti(volume: torch.Tensor, scale: float = 1.0, offset: float = 0.0):
+    """(C,X,Y,Z) fp32 -> (C,Z,Y,X) fp32 = NIfTI storage order of the channel-last array, values
+    ``v * scale + offset`` evaluated in fp64 (ref:src/eval.py:39-47, ref:src/model.py:344-346)."""
+    _require_cuda(volume)
+    if volume.dim() != 4:
+        raise RuntimeError("denorm_to_nifti expects one (C,X,Y,Z) volume")
+    v = volume.contiguous().float()
+    c, x, y, z = v.shape
+    out = torch.empty((c, z, y, x), dtype=torch.float32, device=v.device)
+    _lib.check(_lib.load().ub_denorm_to_nifti(_p(v), c, x, y, z, float(scale), float(offset), _p(out), _stream()),
+               "ub_denorm_to_nifti")
     return out

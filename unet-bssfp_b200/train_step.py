@@ -12,6 +12,7 @@ import torch
 import torch.distributed as dist
 
 from .modules import BCEWithLogitsLoss, L1Loss
+from .optim import FusedAdamW
 
 RECON_FACTOR = 1e2   # ref:src/model.py:147
 N_RECON_TERMS = 2    # ref:src/model.py:138 (L1, Perceptual)
@@ -53,12 +54,20 @@ class GradAllReducer:
 class GanTrainer:
     """Holds the two networks, their AdamW optimisers (ref:src/model.py:359-361) and the loss modules."""
 
-    def __init__(self, gen, discr, lr=1e-3, fused_optimizer=True):
+    def __init__(self, gen, discr, lr=1e-3, optimizer="ub", fused_optimizer=None):
+        """``optimizer``: "ub" = ``FusedAdamW`` on the sm_100a multi-tensor kernel (default), "torch_fused" /
+        "torch" = ``torch.optim.AdamW`` with / without ``fused=True`` (what Lightning would build from the
+        reference's ``configure_optimizers``; kept for A/B and for the weight-cache regression tests)."""
         self.gen, self.discr = gen, discr
-        cuda = next(gen.parameters()).is_cuda
-        kw = {"fused": True} if (fused_optimizer and cuda) else {}
-        self.opt_g = torch.optim.AdamW(gen.parameters(), lr=lr, **kw)
-        self.opt_d = torch.optim.AdamW(discr.parameters(), lr=lr, **kw)
+        if fused_optimizer is not None:            # older spelling
+            optimizer = "torch_fused" if fused_optimizer else "torch"
+        if optimizer == "ub":
+            self.opt_g = FusedAdamW(gen.parameters(), lr=lr)
+            self.opt_d = FusedAdamW(discr.parameters(), lr=lr)
+        else:
+            kw = {"fused": True} if optimizer == "torch_fused" else {}
+            self.opt_g = torch.optim.AdamW(gen.parameters(), lr=lr, **kw)
+            self.opt_d = torch.optim.AdamW(discr.parameters(), lr=lr, **kw)
         self.l1 = L1Loss()
         self.bce = BCEWithLogitsLoss()
         self.reduce_g = GradAllReducer(gen)
