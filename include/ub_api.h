@@ -192,7 +192,7 @@ int ub_dti_scalar_maps(const float* tensor6, long long voxels, float* fa, float*
  * over `count` parameter tensors in as few launches as the pointer table allows. `tensors` is a HOST array;
  * p / g / m / v are device pointers to fp32 arrays of numel elements (parameter, gradient, exp_avg, exp_avg_sq),
  * updated in place. step >= 1 is the number of this update (bias corrections 1 - beta^step, computed on the
- * host). grad_scale multiplies the gradient first (1 / world_size after a SUM all-reduce; otherwise 1). */
+ * host; the hyper-parameters are doubles because torch derives 1 - beta from Python floats). grad_scale multiplies the gradient first (1 / world_size after a SUM all-reduce; otherwise 1). */
 typedef struct {
   float* p;
   const float* g;
@@ -200,8 +200,8 @@ typedef struct {
   float* v;
   long long numel;
 } ub_adamw_tensor;
-int ub_adamw_step(const ub_adamw_tensor* tensors, int count, float lr, float beta1, float beta2, float eps,
-                  float weight_decay, long long step, float grad_scale, void* stream);
+int ub_adamw_step(const ub_adamw_tensor* tensors, int count, double lr, double beta1, double beta2, double eps,
+                  double weight_decay, long long step, float grad_scale, void* stream);
 
 /* ---- prediction volume -> NIfTI storage order ------------------------------------- */
 /* ref:src/model.py:335-357 (save_predicitions: np.moveaxis(volume, 0, -1) -> Nifti1Image) followed by
@@ -211,6 +211,45 @@ int ub_adamw_step(const ub_adamw_tensor* tensors, int count, float lr, float bet
  * gives the plain layout change. */
 int ub_denorm_to_nifti(const float* src, int c, int x, int y, int z, double scale, double offset, float* dst,
                        void* stream);
+
+/* ---- fp32 mode ------------------------------------------------------------------------------------ */
+/* north_star: "agree within 1e-2 relative (bf16) or 1e-5 (fp32 mode)". The same operators on the CUDA cores
+ * (fp32 products, fp64 sums), tensors in the reference's own NCDHW fp32 layout with REAL channel counts and
+ * torch weight layouts ([co][ci][k][k][k]; [ci][co][2][2][2] for the transposed conv). A verification path for
+ * small volumes: no tensor cores, no roofline claim. */
+typedef struct {
+  int n, c0, c1, co;   /* batch; channels of source 0 / source 1 (skip concat [src0, src1], c1 = 0: none); output channels */
+  int d, h, w;         /* input spatial size */
+  int k, stride, pad;  /* (1,1,0), (3,1,1) or (4,2,1): the three Conv3d shapes of ref:model.py */
+} ub_f32_conv_desc;
+int ub_f32_conv_fwd(const ub_f32_conv_desc* d, const float* src0, const float* src1, const float* w, const float* bias,
+                    float* out, void* stream);
+int ub_f32_conv_dgrad(const ub_f32_conv_desc* d, const float* dout, const float* w, float* dsrc0, float* dsrc1,
+                      void* stream);
+/* dw and / or dbias may be NULL */
+int ub_f32_conv_wgrad(const ub_f32_conv_desc* d, const float* src0, const float* src1, const float* dout, float* dw,
+                      float* dbias, void* stream);
+/* ConvTranspose3d(kernel 2, stride 2); d, h, w = INPUT spatial size */
+int ub_f32_deconv2_fwd(int n, int ci, int co, int d, int h, int w, const float* src, const float* wt, const float* bias,
+                       float* out, void* stream);
+int ub_f32_deconv2_dgrad(int n, int ci, int co, int d, int h, int w, const float* dout, const float* wt, float* dsrc,
+                         void* stream);
+int ub_f32_deconv2_wgrad(int n, int ci, int co, int d, int h, int w, const float* src, const float* dout, float* dw,
+                         float* dbias, void* stream);
+/* statistics straight from y [n][c][voxels] (two passes, fp64); mode = UB_NORM_INSTANCE / BATCH_TRAIN / BATCH_EVAL;
+ * scale / shift / mean / rstd: [n][c] */
+int ub_f32_norm_stats(const float* y, int n, int c, long long voxels, int mode, const float* gamma, const float* beta,
+                      float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                      float* mean, float* rstd, void* stream);
+/* a = LeakyReLU(Dropout(y * scale + shift)) (scale NULL: no norm); pooled (may be NULL) = MaxPool3d(2)(a) */
+int ub_f32_norm_act_fwd(const float* y, const float* scale, const float* shift, float slope, float drop_p,
+                        uint32_t drop_seed, int n, int c, int d, int h, int w, float* a, float* pooled, void* stream);
+/* backward of the block above, including the max-pool routing: dA (gradient of a) and dP (gradient of pooled) may
+ * each be NULL (not both). mode UB_NORM_NONE: activation backward only. c1c2: workspace of 2*n*c floats. */
+int ub_f32_norm_act_bwd(const float* dA, const float* dP, const float* a, const float* y, int mode, const float* mean,
+                        const float* rstd, const float* scale, const float* shift, float slope, float drop_p,
+                        uint32_t drop_seed, int n, int c, int d, int h, int w, float* c1c2, float* dy, float* dgamma,
+                        float* dbeta, void* stream);
 
 #ifdef __cplusplus
 }

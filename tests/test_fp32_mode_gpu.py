@@ -1,0 +1,227 @@
+"""GPU parity of the fp32 mode (``precision = "fp32"``: CUDA-core kernels, NCDHW fp32) at the north_star's fp32
+tolerance: outputs and gradients within 1e-5 relative of the reference arithmetic.
+
+Truth is the torch.nn oracle evaluated in FLOAT64 on the same weights and inputs; stock fp32 PyTorch (cuDNN with
+TF32 off) is measured beside it as the yardstick. Also checked against the goldens the reference's own code
+produced on CPU (tests/golden/golden_ref_v1.npz)."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.golden.make_golden_ref import state_checksum, synth_batch
+from tests.util import rel_l2, rel_to_max, strict_fp32
+
+pytestmark = pytest.mark.gpu
+REF = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_ref_v1.npz"))
+DEV = "cuda"
+TOL = 1e-5
+
+
+def _pair(mod, seed=0):
+    import unet_bssfp_b200 as ub
+    from oracle import model_oracle as O
+    torch.manual_seed(seed)
+    og, od = O.Generator(mod).to(DEV), O.Discriminator(mod).to(DEV)
+    g, d = ub.Generator(mod).to(DEV), ub.Discriminator(mod).to(DEV)
+    g.load_state_dict(og.state_dict())
+    d.load_state_dict(od.state_dict())
+    ub.set_precision(g, "fp32")
+    ub.set_precision(d, "fp32")
+    for m in og.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    g.blocks["unet"].dropout = 0.0
+    g._graph = None
+    return O, og, od, g, d
+
+
+@pytest.mark.parametrize("k,s,p,c0,c1,co,shape", [(3, 1, 1, 5, 3, 7, (2, 6, 9, 10)), (1, 1, 0, 6, 0, 24, (1, 4, 5, 6)),
+                                                  (4, 2, 1, 3, 2, 8, (2, 8, 6, 10)), (3, 1, 1, 40, 0, 33, (1, 4, 4, 4))])
+def test_conv_block_matches_torch_fp64(k, s, p, c0, c1, co, shape):
+    """conv(cat[src0, src1]) forward, dgrad (both sources), wgrad, bias gradient."""
+    from unet_bssfp_b200 import fp32_mode as F, ops
+    from unet_bssfp_b200._lib import UB_CONV_K1, UB_CONV_K3S1P1, UB_CONV_K4S2P1
+    from unet_bssfp_b200.modules import _Block
+    kind = {3: UB_CONV_K3S1P1, 1: UB_CONV_K1, 4: UB_CONV_K4S2P1}[k]
+    n, d, h, w = shape
+    torch.manual_seed(0)
+    conv = torch.nn.Conv3d(c0 + c1, co, k, s, p).to(DEV)
+    blk = _Block("t", ops.ConvSpec(kind, c0, co, c1), conv)
+    a = torch.randn(n, c0, d, h, w, device=DEV, requires_grad=True)
+    b = torch.randn(n, c1, d, h, w, device=DEV, requires_grad=True) if c1 else None
+    out, _ = F.run_block(blk, a, b, False, 0)
+    c64 = copy.deepcopy(conv).double()
+    a64 = a.detach().double().requires_grad_(True)
+    b64 = b.detach().double().requires_grad_(True) if c1 else None
+    ref = c64(torch.cat([a64, b64], 1) if c1 else a64)
+    assert rel_to_max(out.double(), ref) < TOL
+    dy = torch.randn_like(out)
+    out.backward(dy)
+    ref.backward(dy.double())
+    assert rel_to_max(a.grad.double(), a64.grad) < TOL
+    if c1:
+        assert rel_to_max(b.grad.double(), b64.grad) < TOL
+    assert rel_to_max(conv.weight.grad.double(), c64.weight.grad) < TOL
+    assert rel_to_max(conv.bias.grad.double(), c64.bias.grad) < TOL
+
+
+def test_deconv_block_matches_torch_fp64():
+    from unet_bssfp_b200 import fp32_mode as F, ops
+    from unet_bssfp_b200._lib import UB_DECONV_K2S2
+    from unet_bssfp_b200.modules import _Block
+    torch.manual_seed(0)
+    dc = torch.nn.ConvTranspose3d(12, 5, kernel_size=2, stride=2).to(DEV)
+    blk = _Block("t", ops.ConvSpec(UB_DECONV_K2S2, 12, 5), dc)
+    x = torch.randn(2, 12, 3, 4, 5, device=DEV, requires_grad=True)
+    out, _ = F.run_block(blk, x, None, False, 0)
+    d64 = copy.deepcopy(dc).double()
+    x64 = x.detach().double().requires_grad_(True)
+    ref = d64(x64)
+    assert out.shape == ref.shape and rel_to_max(out.double(), ref) < TOL
+    dy = torch.randn_like(out)
+    out.backward(dy); ref.backward(dy.double())
+    assert rel_to_max(x.grad.double(), x64.grad) < TOL
+    assert rel_to_max(dc.weight.grad.double(), d64.weight.grad) < TOL
+    assert rel_to_max(dc.bias.grad.double(), d64.bias.grad) < TOL
+
+
+@pytest.mark.parametrize("mod,shape", [("bssfp", (1, 32, 32, 32)), ("t1w", (2, 32, 16, 48))])
+def test_generator_fp32_mode_forward_backward(mod, shape):
+    strict_fp32()
+    O, og, od, g, d = _pair(mod)
+    og.train(); g.train()
+    n, dd, hh, ww = shape
+    torch.manual_seed(1234)
+    x = torch.rand(n, O.in_channels_of(mod), dd, hh, ww, device=DEV)
+    o64 = copy.deepcopy(og).double()
+    ref = o64(x.double())
+    dY = torch.randn_like(ref)
+    ref.backward(dY)
+    got = g(x)
+    got.backward(dY.float())
+    y32 = og(x)
+    y32.backward(dY.float())
+    assert got.dtype == torch.float32 and got.shape == ref.shape
+    e, ey = rel_to_max(got.double(), ref), rel_to_max(y32.double(), ref)
+    assert e < TOL, (e, ey)
+    worst = 0.0
+    for (n1, p64), (n2, p), (_, p32) in zip(o64.named_parameters(), g.named_parameters(), og.named_parameters()):
+        assert n1 == n2 and (p64.grad is None) == (p.grad is None), n1
+        if p64.grad is None:
+            continue
+        if n1.endswith("conv.bias") and "final_conv" not in n1 and "deconv" not in n1:
+            # bias feeding a batch-statistics norm: analytically zero gradient; compare absolutely
+            assert p.grad.abs().max().item() <= 1e-2 + p64.grad.abs().max().item()
+            continue
+        e = rel_l2(p.grad.double(), p64.grad)
+        worst = max(worst, e)
+        assert e < 5 * TOL, (n1, e, rel_l2(p32.grad.double(), p64.grad))
+    flat = lambda net: torch.cat([p.grad.double().flatten() for n_, p in net.named_parameters() if p.grad is not None and p.ndim > 1])
+    assert rel_l2(flat(g), flat(o64)) < TOL
+    # BatchNorm running statistics of the head
+    hd = "bssfp" if mod == "bssfp" else "t1w"
+    assert rel_l2(g.blocks[hd].bn.running_var.double(), o64.blocks[hd].bn.running_var) < 1e-6
+    assert int(g.blocks[hd].bn.num_batches_tracked) == int(o64.blocks[hd].bn.num_batches_tracked)
+
+
+def test_discriminator_fp32_mode_forward_backward():
+    strict_fp32()
+    O, og, od, g, d = _pair("bssfp")
+    od.train(); d.train()
+    torch.manual_seed(1234)
+    x = torch.rand(2, 24, 64, 32, 32, device=DEV)
+    y = torch.rand(2, 6, 64, 32, 32, device=DEV)
+    o64 = copy.deepcopy(od).double()
+    y64 = y.double().requires_grad_(True)
+    yp = y.clone().requires_grad_(True)
+    ref, got = o64(x.double(), y64), d(x, yp)
+    assert got.shape == ref.shape == (2, 1, 2, 1, 1)
+    assert rel_to_max(got.double(), ref) < TOL
+    dl = torch.randn_like(ref)
+    ref.backward(dl); got.backward(dl.float())
+    assert rel_l2(yp.grad.double(), y64.grad) < 5 * TOL
+    for (n1, p64), (n2, p) in zip(o64.named_parameters(), d.named_parameters()):
+        assert (p64.grad is None) == (p.grad is None), n1
+        if p64.grad is None or (n1.endswith("conv.bias") and not n1.startswith("d1")):
+            continue
+        assert rel_l2(p.grad.double(), p64.grad) < 5 * TOL, n1
+    d.eval(); o64.eval()
+    with torch.no_grad():
+        assert rel_to_max(d(x, y).double(), o64(x.double(), y.double())) < TOL     # running statistics path
+
+
+def test_fp32_mode_matches_reference_goldens():
+    """Against what the reference's own code computed (CPU, fp32): eval output, G-phase weight gradients."""
+    import unet_bssfp_b200 as ub
+    from unet_bssfp_b200.train_step import GanTrainer
+    torch.manual_seed(0)
+    g, d = ub.Generator("bssfp"), ub.Discriminator("bssfp")
+    if abs(state_checksum(g) - float(REF["bssfp_g_checksum"])) > 1e-9 * float(REF["bssfp_g_checksum"]):
+        pytest.skip("default torch init differs from the torch version that generated the goldens")
+    g, d = ub.set_precision(g.to(DEV), "fp32"), ub.set_precision(d.to(DEV), "fp32")
+    g.blocks["unet"].dropout = 0.0
+    xb, yb = synth_batch(24)
+    xb, yb = xb.to(DEV), yb.to(DEV)
+    g.eval()
+    with torch.no_grad():
+        got = g(xb[:1]).cpu()
+    assert rel_to_max(got, torch.from_numpy(REF["bssfp_g_eval_32"])) < TOL
+    g.train(); d.train()
+    tr = GanTrainer(g, d)
+    for p in d.parameters():
+        p.requires_grad_(False)
+    gl, _ = tr.gen_loss(xb, yb)
+    assert abs(gl.item() / float(REF["bssfp_gen_loss"]) - 1) < 1e-5
+    gl.backward()
+    gp = dict(g.named_parameters(remove_duplicate=False))
+    for k in [k for k in REF.files if k.startswith("bssfp_ggrad::")]:
+        e = rel_l2(gp[k.split("::")[1]].grad.cpu(), torch.from_numpy(REF[k]))
+        assert e < 1e-4, (k, e)                     # the golden itself is fp32 CPU arithmetic
+    for p in d.parameters():
+        p.requires_grad_(True)
+    g.zero_grad(set_to_none=True)
+    with torch.no_grad():
+        dl = tr.discr_loss(xb, yb)
+    assert abs(dl.item() - float(REF["bssfp_discr_loss"])) < 1e-5
+
+
+def test_fp32_mode_three_training_steps_follow_the_reference():
+    import unet_bssfp_b200 as ub
+    from unet_bssfp_b200.train_step import GanTrainer
+    torch.manual_seed(0)
+    g, d = ub.Generator("bssfp"), ub.Discriminator("bssfp")
+    if abs(state_checksum(g) - float(REF["bssfp_g_checksum"])) > 1e-9 * float(REF["bssfp_g_checksum"]):
+        pytest.skip("default torch init differs from the torch version that generated the goldens")
+    g, d = ub.set_precision(g.to(DEV), "fp32"), ub.set_precision(d.to(DEV), "fp32")
+    g.blocks["unet"].dropout = 0.0
+    g.train(); d.train()
+    tr = GanTrainer(g, d)
+    xb, yb = synth_batch(24)
+    xb, yb = xb.to(DEV), yb.to(DEV)
+    gls, dls = [], []
+    for _ in range(3):
+        gl, dl = tr.step(xb, yb)
+        gls.append(float(gl)); dls.append(float(dl))
+    np.testing.assert_allclose(gls, REF["bssfp_train3_gen_loss"], rtol=2e-3)
+    np.testing.assert_allclose(dls, REF["bssfp_train3_discr_loss"], rtol=2e-3, atol=1e-4)
+    assert abs(state_checksum(g.cpu()) / float(REF["bssfp_train3_gen_checksum"]) - 1) < 1e-4
+    assert abs(state_checksum(d.cpu()) / float(REF["bssfp_train3_discr_checksum"]) - 1) < 1e-4
+
+
+def test_fp32_mode_dropout_and_errors():
+    import unet_bssfp_b200 as ub
+    g = ub.set_precision(ub.Generator("t1w").to(DEV), "fp32")
+    g.train()
+    x = torch.rand(1, 6, 16, 16, 16, device=DEV)
+    with torch.no_grad():
+        torch.manual_seed(3); a = g(x)
+        torch.manual_seed(3); b = g(x)
+        torch.manual_seed(4); c = g(x)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    with pytest.raises(RuntimeError, match="divisible by 16"):
+        g(torch.rand(1, 6, 24, 16, 16, device=DEV))
+    with pytest.raises(ValueError):
+        ub.set_precision(g, "fp16")

@@ -7,7 +7,7 @@ relative-error reduction, all running on hand-written CUDA through ``libubssfp.s
 __version__ = "0.1.0"
 
 from .modules import (BasicUNet, BCEWithLogitsLoss, Discriminator, DownSampleConv, Generator,  # noqa: E402,F401
-                      L1Loss, invalidate_packed_weights)
+                      L1Loss, invalidate_packed_weights, set_precision)
 from . import ops  # noqa: E402,F401
 from . import inference  # noqa: E402,F401
 from . import nifti  # noqa: E402,F401

@@ -28,6 +28,11 @@ class AdamWTensor(C.Structure):
     _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("numel", C.c_longlong)]
 
 
+class F32ConvDesc(C.Structure):
+    """Mirror of ``ub_f32_conv_desc`` (include/ub_api.h)."""
+    _fields_ = [(k, C.c_int) for k in ("n", "c0", "c1", "co", "d", "h", "w", "k", "stride", "pad")]
+
+
 class ConvDesc(C.Structure):
     """Mirror of ``ub_conv_desc`` (include/ub_api.h)."""
     _fields_ = [(k, C.c_int) for k in ("kind", "n", "d", "h", "w", "c0", "c0p", "c1", "c1p", "co", "cop")]
@@ -79,8 +84,17 @@ SIGNATURES = {
     "ub_scale": (_I, [_P, _P, _LL, _P, _P]),
     "ub_dti_scalar_maps": (_I, [_P, _LL, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ub_relerr_map_reduce": (_I, [_P, _P, _P, _P, _I, _I, _LL, _I, _P, _P, _P, _P]),
-    "ub_adamw_step": (_I, [C.POINTER(AdamWTensor), _I, _F, _F, _F, _F, _F, _LL, _F, _P]),
+    "ub_adamw_step": (_I, [C.POINTER(AdamWTensor), _I, _D, _D, _D, _D, _D, _LL, _F, _P]),
     "ub_denorm_to_nifti": (_I, [_P, _I, _I, _I, _I, _D, _D, _P, _P]),
+    "ub_f32_conv_fwd": (_I, [C.POINTER(F32ConvDesc), _P, _P, _P, _P, _P, _P]),
+    "ub_f32_conv_dgrad": (_I, [C.POINTER(F32ConvDesc), _P, _P, _P, _P, _P]),
+    "ub_f32_conv_wgrad": (_I, [C.POINTER(F32ConvDesc), _P, _P, _P, _P, _P, _P]),
+    "ub_f32_deconv2_fwd": (_I, [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "ub_f32_deconv2_dgrad": (_I, [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "ub_f32_deconv2_wgrad": (_I, [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "ub_f32_norm_stats": (_I, [_P, _I, _I, _LL, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "ub_f32_norm_act_fwd": (_I, [_P, _P, _P, _F, _F, _U32, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "ub_f32_norm_act_bwd": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _F, _F, _U32, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

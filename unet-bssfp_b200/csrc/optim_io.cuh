@@ -28,15 +28,18 @@ struct AdamWBatch {
   int numel[kAdamWMaxTensors];
   int block_begin[kAdamWMaxTensors + 1];   // prefix of chunks per tensor
   int count;
-  float lr, beta1, beta2, eps, decay_mul /* 1 - lr * wd */, step_size /* lr / bc1 */, inv_bc2_sqrt, grad_scale;
+  // all derived on the host in double and rounded once (what torch does with its Python-float hyper-parameters)
+  float beta2, one_minus_beta1, one_minus_beta2, eps, decay_mul /* 1 - lr * wd */, step_size /* lr / bc1 */, bc2_sqrt,
+      grad_scale;
 };
 
 __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, const AdamWBatch& B) {
   g *= B.grad_scale;
   p *= B.decay_mul;
-  m = m + (1.f - B.beta1) * (g - m);                       // lerp_
-  v = B.beta2 * v + (1.f - B.beta2) * g * g;
-  const float denom = sqrtf(v) * B.inv_bc2_sqrt + B.eps;
+  m = m + B.one_minus_beta1 * (g - m);                     // lerp_(g, 1 - b1), weight < 0.5 branch
+  v = B.beta2 * v;                                         // mul_(b2), rounded, then addcmul_(g, g, 1 - b2)
+  v = v + B.one_minus_beta2 * g * g;
+  const float denom = sqrtf(v) / B.bc2_sqrt + B.eps;
   p -= B.step_size * (m / denom);
 }
 

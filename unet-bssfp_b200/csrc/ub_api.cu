@@ -13,6 +13,7 @@
 #include "wgrad_march.cuh"
 #include "pointwise.cuh"
 #include "optim_io.cuh"
+#include "fp32_path.cuh"
 
 using namespace ub;
 
@@ -1261,18 +1262,19 @@ extern "C" int ub_conv1x1_from_ncdhw_bwd(const float* dout, int co, const void* 
 // --------------------------------------------------------------------------------------------------
 // N3: multi-tensor AdamW (ref:src/model.py:359-361); N4: de-normalised volume in NIfTI storage order
 // --------------------------------------------------------------------------------------------------
-extern "C" int ub_adamw_step(const ub_adamw_tensor* tensors, int count, float lr, float beta1, float beta2, float eps,
-                             float weight_decay, long long step, float grad_scale, void* stream) {
+extern "C" int ub_adamw_step(const ub_adamw_tensor* tensors, int count, double lr, double beta1, double beta2, double eps,
+                             double weight_decay, long long step, float grad_scale, void* stream) {
   if (count < 0 || (count > 0 && !tensors) || step < 1) return fail(-1, "bad arguments to ub_adamw_step");
-  if (!(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f && lr >= 0.f))
+  if (!(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0 && lr >= 0.0))
     return fail(-1, "ub_adamw_step: invalid hyper-parameters");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
   AdamWBatch B;
-  B.lr = lr; B.beta1 = beta1; B.beta2 = beta2; B.eps = eps;
-  B.decay_mul = (float)(1.0 - (double)lr * (double)weight_decay);
-  B.step_size = (float)((double)lr / bc1);
-  B.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  B.beta2 = (float)beta2; B.one_minus_beta1 = (float)(1.0 - beta1); B.one_minus_beta2 = (float)(1.0 - beta2);
+  B.eps = (float)eps;
+  B.decay_mul = (float)(1.0 - lr * weight_decay);
+  B.step_size = (float)(lr / bc1);
+  B.bc2_sqrt = (float)sqrt(bc2);
   B.grad_scale = grad_scale;
   cudaStream_t st = (cudaStream_t)stream;
   int i = 0;
@@ -1302,6 +1304,167 @@ extern "C" int ub_denorm_to_nifti(const float* src, int c, int x, int y, int z, 
   if ((long long)c * y > 65535) return fail(-2, "ub_denorm_to_nifti: channels x Y must not exceed 65535");
   const dim3 grid((unsigned)((z + 31) / 32), (unsigned)((x + 31) / 32), (unsigned)(c * y));
   denorm_to_nifti_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, dst, x, y, z, scale, offset);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------
+// fp32 mode (CUDA-core kernels, NCDHW fp32 tensors): verification path, 1e-5 against the reference
+// --------------------------------------------------------------------------------------------------
+static int f32_geom(const ub_f32_conv_desc* d, f32::ConvGeom* G) {
+  if (!d) return fail(-1, "null fp32 conv descriptor");
+  if (d->n <= 0 || d->c0 <= 0 || d->c1 < 0 || d->co <= 0 || d->d <= 0 || d->h <= 0 || d->w <= 0)
+    return fail(-1, "fp32 conv: non-positive size");
+  if (!((d->k == 1 && d->stride == 1 && d->pad == 0) || (d->k == 3 && d->stride == 1 && d->pad == 1) ||
+        (d->k == 4 && d->stride == 2 && d->pad == 1)))
+    return fail(-2, "fp32 conv supports (k,s,p) = (1,1,0), (3,1,1), (4,2,1); got (%d,%d,%d)", d->k, d->stride, d->pad);
+  G->n = d->n; G->c0 = d->c0; G->c1 = d->c1; G->co = d->co; G->d = d->d; G->h = d->h; G->w = d->w;
+  G->k = d->k; G->s = d->stride; G->p = d->pad;
+  G->od = (d->d + 2 * d->pad - d->k) / d->stride + 1;
+  G->oh = (d->h + 2 * d->pad - d->k) / d->stride + 1;
+  G->ow = (d->w + 2 * d->pad - d->k) / d->stride + 1;
+  if (G->od <= 0 || G->oh <= 0 || G->ow <= 0) return fail(-2, "fp32 conv: input smaller than the kernel");
+  return 0;
+}
+static unsigned f32_blocks(long long total) { return (unsigned)((total + 255) / 256); }
+#define UB_F32_TOTAL_CHECK(t) if ((t) <= 0 || (t) >= (1ll << 39)) return fail(-2, "fp32 path: tensor too large")
+
+extern "C" int ub_f32_conv_fwd(const ub_f32_conv_desc* d, const float* src0, const float* src1, const float* w,
+                               const float* bias, float* out, void* stream) {
+  f32::ConvGeom G;
+  if (int e = f32_geom(d, &G)) return e;
+  if (!src0 || !w || !out || (G.c1 > 0 && !src1)) return fail(-1, "bad arguments to ub_f32_conv_fwd");
+  const long long total = (long long)G.n * G.co * G.od * G.oh * G.ow;
+  UB_F32_TOTAL_CHECK(total);
+  f32::conv_fwd_kernel<<<f32_blocks(total), 256, 0, (cudaStream_t)stream>>>(src0, src1, w, bias, out, G, total);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ub_f32_conv_dgrad(const ub_f32_conv_desc* d, const float* dout, const float* w, float* dsrc0, float* dsrc1,
+                                 void* stream) {
+  f32::ConvGeom G;
+  if (int e = f32_geom(d, &G)) return e;
+  if (!dout || !w || !dsrc0 || (G.c1 > 0 && !dsrc1)) return fail(-1, "bad arguments to ub_f32_conv_dgrad");
+  const long long total = (long long)G.n * (G.c0 + G.c1) * G.d * G.h * G.w;
+  UB_F32_TOTAL_CHECK(total);
+  f32::conv_dgrad_kernel<<<f32_blocks(total), 256, 0, (cudaStream_t)stream>>>(dout, w, dsrc0, dsrc1, G, total);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ub_f32_conv_wgrad(const ub_f32_conv_desc* d, const float* src0, const float* src1, const float* dout,
+                                 float* dw, float* dbias, void* stream) {
+  f32::ConvGeom G;
+  if (int e = f32_geom(d, &G)) return e;
+  if (!dout || (dw && (!src0 || (G.c1 > 0 && !src1)))) return fail(-1, "bad arguments to ub_f32_conv_wgrad");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dw) {
+    const dim3 grid((unsigned)(G.co * (G.c0 + G.c1)), (unsigned)G.k);
+    if (G.k == 1) f32::conv_wgrad_kernel<1><<<grid, 128, 0, st>>>(src0, src1, dout, dw, G);
+    else if (G.k == 3) f32::conv_wgrad_kernel<3><<<grid, 128, 0, st>>>(src0, src1, dout, dw, G);
+    else f32::conv_wgrad_kernel<4><<<grid, 128, 0, st>>>(src0, src1, dout, dw, G);
+    UB_LAUNCH_CHECK();
+  }
+  if (dbias) {
+    f32::channel_sum_kernel<<<(unsigned)G.co, 256, 0, st>>>(dout, G.n, G.co, (long long)G.od * G.oh * G.ow, dbias);
+    UB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int ub_f32_deconv2_fwd(int n, int ci, int co, int d, int h, int w, const float* src, const float* wt,
+                                  const float* bias, float* out, void* stream) {
+  if (!src || !wt || !out || n <= 0 || ci <= 0 || co <= 0 || d <= 0 || h <= 0 || w <= 0) return fail(-1, "bad arguments to ub_f32_deconv2_fwd");
+  const long long total = (long long)n * co * 8 * d * h * w;
+  UB_F32_TOTAL_CHECK(total);
+  f32::deconv2_fwd_kernel<<<f32_blocks(total), 256, 0, (cudaStream_t)stream>>>(src, wt, bias, out, n, ci, co, d, h, w, total);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ub_f32_deconv2_dgrad(int n, int ci, int co, int d, int h, int w, const float* dout, const float* wt,
+                                    float* dsrc, void* stream) {
+  if (!dout || !wt || !dsrc || n <= 0 || ci <= 0 || co <= 0 || d <= 0 || h <= 0 || w <= 0) return fail(-1, "bad arguments to ub_f32_deconv2_dgrad");
+  const long long total = (long long)n * ci * d * h * w;
+  UB_F32_TOTAL_CHECK(total);
+  f32::deconv2_dgrad_kernel<<<f32_blocks(total), 256, 0, (cudaStream_t)stream>>>(dout, wt, dsrc, n, ci, co, d, h, w, total);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ub_f32_deconv2_wgrad(int n, int ci, int co, int d, int h, int w, const float* src, const float* dout,
+                                    float* dw, float* dbias, void* stream) {
+  if (!dout || (dw && !src) || n <= 0 || ci <= 0 || co <= 0 || d <= 0 || h <= 0 || w <= 0) return fail(-1, "bad arguments to ub_f32_deconv2_wgrad");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dw) {
+    f32::deconv2_wgrad_kernel<<<(unsigned)(ci * co), 128, 0, st>>>(src, dout, dw, n, ci, co, d, h, w);
+    UB_LAUNCH_CHECK();
+  }
+  if (dbias) {
+    f32::channel_sum_kernel<<<(unsigned)co, 256, 0, st>>>(dout, n, co, (long long)8 * d * h * w, dbias);
+    UB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int ub_f32_norm_stats(const float* y, int n, int c, long long voxels, int mode, const float* gamma,
+                                 const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                                 float* scale, float* shift, float* mean, float* rstd, void* stream) {
+  if (!y || !scale || !shift || !mean || !rstd || n <= 0 || c <= 0 || voxels <= 0 || mode < 0 || mode > 2)
+    return fail(-1, "bad arguments to ub_f32_norm_stats");
+  if (mode == UB_NORM_BATCH_EVAL && (!running_mean || !running_var)) return fail(-1, "eval BatchNorm needs running statistics");
+  f32::norm_stats_kernel<<<(unsigned)c, 256, 0, (cudaStream_t)stream>>>(y, n, c, voxels, mode, gamma, beta, eps, momentum,
+                                                                        running_mean, running_var, scale, shift, mean, rstd);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+static uint32_t f32_drop_thresh(float p) {
+  double t = (double)p * 4294967296.0;
+  return t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+}
+
+extern "C" int ub_f32_norm_act_fwd(const float* y, const float* scale, const float* shift, float slope, float drop_p,
+                                   uint32_t drop_seed, int n, int c, int d, int h, int w, float* a, float* pooled,
+                                   void* stream) {
+  if (!y || !a || n <= 0 || c <= 0 || d <= 0 || h <= 0 || w <= 0 || drop_p < 0.f || drop_p >= 1.f || (scale && !shift))
+    return fail(-1, "bad arguments to ub_f32_norm_act_fwd");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long vol = (long long)d * h * w, total = (long long)n * c * vol;
+  UB_F32_TOTAL_CHECK(total);
+  f32::norm_act_fwd_kernel<<<f32_blocks(total), 256, 0, st>>>(y, scale, shift, slope, drop_p, drop_seed,
+                                                              f32_drop_thresh(drop_p), vol, total, a);
+  UB_LAUNCH_CHECK();
+  if (pooled) {
+    const long long pt = (long long)n * c * (d / 2) * (h / 2) * (w / 2);
+    if (pt <= 0) return fail(-2, "MaxPool3d(2) needs every spatial size >= 2");
+    f32::maxpool_fwd_kernel<<<f32_blocks(pt), 256, 0, st>>>(a, pooled, d, h, w, pt);
+    UB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int ub_f32_norm_act_bwd(const float* dA, const float* dP, const float* a, const float* y, int mode,
+                                   const float* mean, const float* rstd, const float* scale, const float* shift,
+                                   float slope, float drop_p, uint32_t drop_seed, int n, int c, int d, int h, int w,
+                                   float* c1c2, float* dy, float* dgamma, float* dbeta, void* stream) {
+  if ((!dA && !dP) || !dy || n <= 0 || c <= 0 || d <= 0 || h <= 0 || w <= 0) return fail(-1, "bad arguments to ub_f32_norm_act_bwd");
+  const bool has_norm = mode != UB_NORM_NONE;
+  if (has_norm && (!y || !mean || !rstd || !scale || !shift || !c1c2)) return fail(-1, "ub_f32_norm_act_bwd: norm modes need y, statistics and the c1c2 workspace");
+  if ((dP || (!has_norm && slope != 1.f)) && !a) return fail(-1, "ub_f32_norm_act_bwd: the activations a are required");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long vol = (long long)d * h * w, total = (long long)n * c * vol;
+  UB_F32_TOTAL_CHECK(total);
+  f32::act_bwd_kernel<<<f32_blocks(total), 256, 0, st>>>(dA, dP, a, y, has_norm ? scale : nullptr, shift, slope, drop_p,
+                                                         drop_seed, f32_drop_thresh(drop_p), d, h, w, total, dy);
+  UB_LAUNCH_CHECK();
+  if (!has_norm) return 0;
+  float* c1 = c1c2;
+  float* c2 = c1c2 + (size_t)n * c;
+  f32::norm_bwd_reduce_kernel<<<(unsigned)c, 256, 0, st>>>(dy, y, mean, rstd, n, c, vol, mode, c1, c2, dgamma, dbeta);
+  UB_LAUNCH_CHECK();
+  f32::norm_bwd_apply_kernel<<<f32_blocks(total), 256, 0, st>>>(dy, y, mean, rstd, scale, c1, c2, vol, total);
   UB_LAUNCH_CHECK();
   return 0;
 }

@@ -27,6 +27,33 @@ from ._lib import (UB_CONV_K1, UB_CONV_K3S1P1, UB_CONV_K4S2P1, UB_CONV_K4S2P1_S2
 
 UNET_FEATURES = (32, 64, 128, 256, 512, 32)
 
+# ---------------------------------------------------------------------------------------------------
+# precision: "bf16" = the tcgen05 tensor-core path (default, the throughput path); "fp32" = the CUDA-core
+# verification path of fp32_mode.py (1e-5 against the reference, small volumes). Per module
+# (``module.precision`` / ``set_precision``) with the process default from UB_PRECISION.
+# ---------------------------------------------------------------------------------------------------
+import os as _os_env
+
+_DEFAULT_PRECISION = _os_env.environ.get("UB_PRECISION", "bf16")
+_PRECISIONS = ("bf16", "fp32")
+
+
+def _precision_of(module) -> str:
+    p = getattr(module, "precision", None) or _DEFAULT_PRECISION
+    if p not in _PRECISIONS:
+        raise ValueError(f"precision must be one of {_PRECISIONS}, got {p!r}")
+    return p
+
+
+def set_precision(module: nn.Module, precision: str):
+    """Select the arithmetic of every hot-path module inside ``module``: "bf16" or "fp32"."""
+    if precision not in _PRECISIONS:
+        raise ValueError(f"precision must be one of {_PRECISIONS}, got {precision!r}")
+    for m in module.modules():
+        if isinstance(m, (Generator, Discriminator, DownSampleConv, BasicUNet)):
+            m.precision = precision
+    return module
+
 
 # ---------------------------------------------------------------------------------------------------
 # packed-weight cache: bf16 operand copies of the fp32 Parameters, refreshed whenever the parameter may
@@ -312,6 +339,9 @@ class DownSampleConv(nn.Module):
 
     def forward(self, x):
         blk = self._block()
+        if _precision_of(self) == "fp32":
+            from . import fp32_mode
+            return fp32_mode.chain_forward(_Chain([blk], self._cache, self, blk.spec.co), x)
         params = blk.params()
         return _ChainFunction.apply(x, None, _Chain([blk], self._cache, self, blk.spec.co), torch.is_grad_enabled(),
                                     *params)
@@ -385,6 +415,10 @@ class BasicUNet(nn.Module):
 
     def forward(self, x):
         net = _UNetGraph(None, self, self._cache)
+        if _precision_of(self) == "fp32":
+            from . import fp32_mode
+            _check_unet_dims(*x.shape[2:])
+            return fp32_mode.generator_forward(net, x, _fresh_seed)
         return _GeneratorFunction.apply(x, net, torch.is_grad_enabled(), *net.params)
 
 
@@ -656,6 +690,10 @@ class Generator(nn.Module):
 
     def forward(self, x):
         net = self._net()
+        if _precision_of(self) == "fp32":
+            from . import fp32_mode
+            _check_unet_dims(*x.shape[2:])
+            return fp32_mode.generator_forward(net, x, _fresh_seed)
         return _GeneratorFunction.apply(x, net, torch.is_grad_enabled(), *net.params)
 
     @torch.no_grad()
@@ -702,6 +740,9 @@ class Discriminator(nn.Module):
         if d % 32 or h % 32 or w % 32:
             raise RuntimeError(f"PatchGAN input size ({d},{h},{w}) must be divisible by 32")
         chain = self._net()
+        if _precision_of(self) == "fp32":
+            from . import fp32_mode
+            return fp32_mode.chain_forward(chain, x, y)
         return _ChainFunction.apply(x, y, chain, torch.is_grad_enabled(), *chain.params)
 
 
