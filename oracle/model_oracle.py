@@ -18,13 +18,16 @@ What is restated, and from where (``/root/reference`` is cited as ``ref:``):
   InstanceNorm3d(affine=True), bias=True, dropout=0.05 (element-wise nn.Dropout), upsample="deconv".
 * ``gan_step``                  ref:src/model.py:170-193 and 259-281 (training_step semantics)
 
-PARITY PIN: the reference ships no tests / golden vectors for this path and
-the reference file itself cannot be imported here (monai, lightning, torchio, nibabel missing).
-The restatement is pinned by the structural known answers the survey measured on the reference's
-module tree: parameter counts (G 22 646 182, D 11 230 593), the 110 / 46 state-dict keys and their
-shapes, output shapes, plus committed golden vectors under ``tests/golden``
-generated from THIS oracle by ``tests/golden/make_golden.py``.  Status: "parity unpinned by the
-reference; pinned by structural KATs + self-generated goldens".
+PARITY PIN: the reference ships no tests / golden vectors of its own for this path.
+The restatement is pinned by OUTPUTS OF THE REFERENCE ITSELF run in the build container:
+``tests/golden/make_golden_ref.py`` imports /root/reference/src/model.py unmodified (stand-ins for the absent
+monai / lightning / torchio / nibabel packages; ``monai.networks.nets.BasicUNet`` is the restatement below) and
+records module trees, initialisation checksums, forward values, ``_gen_step`` / ``_discr_step`` losses, phase
+gradients under ``toggle_optimizer`` and three whole ``training_step`` calls into
+``tests/golden/golden_ref_v1.npz``; ``tests/test_reference_golden_cpu.py`` checks this module against them.
+Status: pinned by the reference for everything in model.py; the BasicUNet internals (third-party monai 1.3.0,
+absent here) remain a restatement pinned by the structural known answers of SURVEY.md Appendix A
+(22 645 318 U-Net parameters; key names and shapes of the published monai 1.3.0 source).
 """
 from __future__ import annotations
 

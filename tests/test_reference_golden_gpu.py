@@ -60,6 +60,27 @@ def test_networks_match_reference_outputs(mod):
     assert abs(recon.item() / float(REF[f"{mod}_gen_loss_recon"]) - 1) < 0.02
 
 
+def _autocast_yardstick(mod, xb, yb, phase):
+    """Gradients of the torch.nn oracle under torch.autocast(bf16) (cuDNN) on the same weights: what stock bf16
+    PyTorch makes of the same quantity. With the L1 sign gradient at random initialisation the weight gradients are
+    ill-conditioned (a bf16 perturbation of y_hat flips sign(y_hat - y) on a few per cent of the voxels), so the
+    bar is relative to this yardstick, as in tests/test_model_gpu.py."""
+    from oracle import model_oracle as O
+    torch.manual_seed(0)
+    og, od = O.Generator(mod).to(DEV), O.Discriminator(mod).to(DEV)
+    for m in og.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    og.train(); od.train()
+    frozen, live = (od, og) if phase == "gen" else (og, od)
+    for p in frozen.parameters():
+        p.requires_grad_(False)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = O.gen_loss(og, od, xb, yb)[0] if phase == "gen" else O.discr_loss(og, od, xb, yb)
+    loss.float().backward()
+    return dict(live.named_parameters(remove_duplicate=False))
+
+
 def test_phase_gradients_match_reference():
     """Weight gradients of the G phase (D frozen) and the D phase against the reference's manual_backward."""
     from unet_bssfp_b200.train_step import GanTrainer
@@ -74,12 +95,17 @@ def test_phase_gradients_match_reference():
     gl.backward()
     assert all(p.grad is None for p in d.parameters())
     gp = dict(g.named_parameters(remove_duplicate=False))
-    errs = {}
+    yard = _autocast_yardstick("bssfp", xb, yb, "gen")
+    ours, theirs = [], []
     for k in [k for k in REF.files if k.startswith("bssfp_ggrad::")]:
-        errs[k] = rel_l2(gp[k.split("::")[1]].grad.cpu(), torch.from_numpy(REF[k]))
-    # bf16 through LeakyReLU / max-pool sign flips: per-tensor errors of a few 1e-2 .. 1e-1 are what stock bf16
-    # autocast shows too (tests/test_model_gpu.py measures that yardstick); here a fixed bar on the goldens
-    assert max(errs.values()) < 0.35 and float(np.median(list(errs.values()))) < 0.15, errs
+        name, ref = k.split("::")[1], torch.from_numpy(REF[k])
+        if name.endswith("conv.bias") and "final_conv" not in name and "deconv" not in name:
+            continue                                  # analytically zero (bias in front of a batch-statistics norm)
+        e, ey = rel_l2(gp[name].grad.cpu(), ref), rel_l2(yard[name].grad.float().cpu(), ref)
+        ours.append(e); theirs.append(ey)
+        # yardstick errors above 0.5 mean the quantity is rounding noise in bf16 whoever computes it: sanity only
+        assert e < (1.25 * ey + 2e-2 if ey < 0.5 else 2.0), (name, e, ey)
+    assert float(np.median(ours)) < 1.25 * float(np.median(theirs)) + 2e-2, (ours, theirs)
     for p in d.parameters():
         p.requires_grad_(True)
     g.zero_grad(set_to_none=True)
@@ -89,10 +115,13 @@ def test_phase_gradients_match_reference():
     dl.backward()
     assert all(p.grad is None for p in g.parameters())
     dp = dict(d.named_parameters(remove_duplicate=False))
-    errs = {}
+    yard = _autocast_yardstick("bssfp", xb, yb, "discr")
     for k in [k for k in REF.files if k.startswith("bssfp_dgrad::")]:
-        errs[k] = rel_l2(dp[k.split("::")[1]].grad.cpu(), torch.from_numpy(REF[k]))
-    assert max(errs.values()) < 0.35 and float(np.median(list(errs.values()))) < 0.15, errs
+        name, ref = k.split("::")[1], torch.from_numpy(REF[k])
+        if name.endswith("conv.bias") and not name.startswith("d1"):
+            continue
+        e, ey = rel_l2(dp[name].grad.cpu(), ref), rel_l2(yard[name].grad.float().cpu(), ref)
+        assert e < (1.25 * ey + 2e-2 if ey < 0.5 else 2.0), (name, e, ey)
 
 
 def test_three_training_steps_track_the_reference():
