@@ -135,6 +135,13 @@ int ub_norm_finalize(const float* stats_partial, int tiles_per_sample, int n, in
                      double voxels_per_sample, const float* gamma, const float* beta, float eps, int mode,
                      float momentum, float* running_mean, float* running_var, float* scale, float* shift,
                      float* mean, float* rstd, void* stream);
+/* BatchNorm running statistics from the batch statistics a UB_NORM_BATCH_TRAIN finalize saved (mean / rstd: the
+ * first c entries of its outputs) when it was called with running_mean = running_var = NULL:
+ * running = (1 - momentum) * running + momentum * {mean, unbiased variance}; count = n * voxels. Decouples the
+ * update from the forward pass so that independent passes can run on different streams and still update in the
+ * reference's order (ref:src/model.py:184-186: fake branch, then real branch). */
+int ub_bn_running_update(const float* mean, const float* rstd, int c, double count, float eps, float momentum,
+                         float* running_mean, float* running_var, void* stream);
 /* a = LeakyReLU_slope(Dropout_p(y * scale + shift)); pooled (may be NULL) = MaxPool3d(2)(a).
  * scale == NULL: no normalisation. ref: monai ADN "NDA" + Down.max_pooling */
 int ub_norm_act_fwd(const void* y, const float* scale, const float* shift, float slope, float drop_p,

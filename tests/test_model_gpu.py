@@ -269,3 +269,71 @@ def test_shape_errors():
         g(torch.rand(1, 6, 24, 32, 32, device=DEV))
     with pytest.raises(RuntimeError, match="divisible by 32"):
         d(torch.rand(1, 6, 48, 32, 32, device=DEV), torch.rand(1, 6, 48, 32, 32, device=DEV))
+
+
+def test_discriminator_phase_on_two_streams_equals_one_stream():
+    """GanTrainer.discr_loss runs the real-sample pass on a second stream (deferred BatchNorm running-statistics
+    updates keep the reference's order): loss, every gradient and the running statistics must equal the
+    single-stream evaluation."""
+    import unet_bssfp_b200 as ub
+    from unet_bssfp_b200.train_step import GanTrainer
+    O, og, od, g, d = _pair("bssfp")
+    _no_dropout(og, g)
+    g2, d2 = ub.Generator("bssfp").to(DEV), ub.Discriminator("bssfp").to(DEV)
+    g2.load_state_dict(g.state_dict()); d2.load_state_dict(d.state_dict())
+    g2.blocks["unet"].dropout = 0.0
+    ta, tb = GanTrainer(g, d), GanTrainer(g2, d2)
+    ta.overlap_real_branch, tb.overlap_real_branch = True, False
+    torch.manual_seed(3)
+    x = torch.rand(2, 24, 64, 32, 32, device=DEV)
+    y = torch.rand(2, 6, 64, 32, 32, device=DEV)
+    for net in (g, g2):
+        for p in net.parameters():
+            p.requires_grad_(False)
+    for _ in range(2):
+        la, lb = ta.discr_loss(x, y), tb.discr_loss(x, y)
+        la.backward(); lb.backward()
+        torch.cuda.synchronize()
+    assert ta._branch_stream is not None and tb._branch_stream is None
+    assert torch.equal(la, lb)
+    for (n1, p1), (n2, p2) in zip(d.named_parameters(), d2.named_parameters()):
+        assert (p1.grad is None) == (p2.grad is None), n1
+        if p1.grad is not None:
+            assert torch.equal(p1.grad, p2.grad), n1
+    for m1, m2 in zip(d.modules(), d2.modules()):
+        if isinstance(m1, torch.nn.BatchNorm3d):
+            assert int(m1.num_batches_tracked) == int(m2.num_batches_tracked) == 4
+            torch.testing.assert_close(m1.running_mean, m2.running_mean, rtol=1e-6, atol=1e-7)
+            torch.testing.assert_close(m1.running_var, m2.running_var, rtol=1e-5, atol=1e-7)
+    # and both follow the oracle's running statistics (fake pass first, then the real pass)
+    od.train(); og.train()
+    for _ in range(2):
+        O.discr_loss(og, od, x, y)
+    assert rel_l2(d.d2.bn.running_mean, od.d2.bn.running_mean) < 2e-2
+    assert rel_l2(d.d3.bn.running_var, od.d3.bn.running_var) < 2e-2
+
+
+def test_config4_full_size_t1w_batch16():
+    """BASELINE config 4 at full size (t1w: 6 input channels, batch 16, 128^3). Size-independent properties:
+    samples are independent in eval mode (InstanceNorm per sample, BatchNorm on running statistics), so a slice of
+    the batch output equals the output of the sliced batch; one full optimisation step runs and stays finite."""
+    import unet_bssfp_b200 as ub
+    from unet_bssfp_b200.train_step import GanTrainer
+    torch.manual_seed(0)
+    g, d = ub.Generator("t1w").to(DEV), ub.Discriminator("t1w").to(DEV)
+    torch.manual_seed(7)
+    x = torch.rand(16, 6, 128, 128, 128, device=DEV)
+    y = torch.rand(16, 6, 128, 128, 128, device=DEV)
+    g.eval()
+    with torch.no_grad():
+        full = g(x)
+        part = g(x[5:7])
+    assert full.shape == (16, 6, 128, 128, 128)
+    assert rel_l2(full[5:7], part) < 1e-6
+    del full, part
+    g.train()
+    tr = GanTrainer(g, d)
+    gl, dl = tr.step(x, y)
+    torch.cuda.synchronize()
+    assert torch.isfinite(gl) and torch.isfinite(dl)
+    assert 0.3 < float(dl) < 1.5                       # (BCE(real, 1) + BCE(fake, 0)) / 2 near ln 2 at initialisation

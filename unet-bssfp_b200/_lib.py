@@ -70,6 +70,7 @@ SIGNATURES = {
     "ub_conv1x1_to_ncdhw": (_I, [_P, _I, _P, _I, _P, _I, _I, _LL, _P, _P, _P]),
     "ub_conv1x1_from_ncdhw_bwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _LL, _P, _P, _P, _P, _P]),
     "ub_norm_finalize": (_I, [_P, _I, _I, _I, _I, _D, _P, _P, _F, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "ub_bn_running_update": (_I, [_P, _P, _I, _D, _F, _F, _P, _P, _P]),
     "ub_norm_act_fwd": (_I, [_P, _P, _P, _F, _F, _U32, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ub_norm_act_bwd_workspace_bytes": (_LL, [_I, _I]),
     "ub_norm_act_bwd": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _F, _F, _U32, _I, _LL, _I, _I, _P, _P, _P, _P, _P, _P, _I,

@@ -123,4 +123,22 @@ __global__ void __launch_bounds__(256) denorm_to_nifti_kernel(const float* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// BatchNorm running-statistics update from saved batch statistics (ub_norm_finalize run without running
+// buffers): running = (1 - momentum) * running + momentum * {mean, unbiased variance}. Lets two forward passes
+// of one network run on different streams and still apply their updates in the reference's order.
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_running_update_kernel(const float* __restrict__ mean, const float* __restrict__ rstd, int c, double count,
+                                         float eps, float momentum, float* __restrict__ running_mean,
+                                         float* __restrict__ running_var) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const double r = (double)rstd[i];
+  double var = 1.0 / (r * r) - (double)eps;            // biased batch variance
+  if (var < 0.0) var = 0.0;
+  const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+  running_mean[i] = (float)((1.0 - momentum) * running_mean[i] + momentum * (double)mean[i]);
+  running_var[i] = (float)((1.0 - momentum) * running_var[i] + momentum * unbiased);
+}
+
 }  // namespace ub

@@ -60,7 +60,16 @@ static int ensure_encode() {
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess)
       g_encode = (EncodeTiledFn)fn;
   });
-  return g_encode ? 0 : fail(-3, "cuTensorMapEncodeTiled unavailable (no CUDA driver / no GPU)");
+  if (!g_encode) return fail(-3, "cuTensorMapEncodeTiled unavailable (no CUDA driver / no GPU)");
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs a context current on the calling thread. A host thread that
+  // has not issued a runtime call yet (a user's worker thread) has none: bind the primary context once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaError_t e = cudaFree(0);
+    if (e != cudaSuccess) return fail(-3, "no CUDA context on this thread: %s", cudaGetErrorString(e));
+    ctx_bound = true;
+  }
+  return 0;
 }
 static CUtensorMapSwizzle swz_for_bytes(int b) {
   return b == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : b == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -1295,6 +1304,15 @@ extern "C" int ub_adamw_step(const ub_adamw_tensor* tensors, int count, double l
     adamw_multi_kernel<<<(unsigned)B.block_begin[B.count], 256, 0, st>>>(B);
     UB_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+extern "C" int ub_bn_running_update(const float* mean, const float* rstd, int c, double count, float eps, float momentum,
+                                    float* running_mean, float* running_var, void* stream) {
+  if (!mean || !rstd || !running_mean || !running_var || c <= 0 || count <= 0.0) return fail(-1, "bad arguments to ub_bn_running_update");
+  bn_running_update_kernel<<<(unsigned)((c + 127) / 128), 128, 0, (cudaStream_t)stream>>>(mean, rstd, c, count, eps, momentum,
+                                                                                      running_mean, running_var);
+  UB_LAUNCH_CHECK();
   return 0;
 }
 

@@ -139,6 +139,53 @@ class _Block:
         return ps
 
 
+# ---------------------------------------------------------------------------------------------------
+# deferred BatchNorm running-statistics updates: inside ``defer_bn_running_stats(log)`` a training-mode BatchNorm
+# block computes its batch statistics without touching running_mean / running_var and appends what the update
+# needs to ``log``; ``apply_deferred_bn(log)`` performs the updates later, in log order. GanTrainer uses it to run
+# the discriminator's real-sample pass on a second stream while keeping the reference's update order.
+# ---------------------------------------------------------------------------------------------------
+import contextlib as _contextlib
+import threading as _threading
+
+_bn_defer = _threading.local()
+
+
+@_contextlib.contextmanager
+def defer_bn_running_stats(log: list):
+    prev = getattr(_bn_defer, "log", None)
+    _bn_defer.log = log
+    try:
+        yield log
+    finally:
+        _bn_defer.log = prev
+
+
+def apply_deferred_bn(log: list):
+    for nm, mean, rstd, c, count, momentum in log:
+        ops.bn_running_update(mean, rstd, c, count, nm.eps, momentum, nm.running_mean, nm.running_var)
+        if nm.num_batches_tracked is not None:
+            nm.num_batches_tracked.add_(1)
+    log.clear()
+
+
+def prepack_weights(module: nn.Module):
+    """Refresh the packed bf16 weight operands of a Discriminator / Generator now, on the current stream (they are
+    otherwise packed lazily by the first forward / backward that needs them)."""
+    if isinstance(module, Discriminator):
+        chain = module._net()
+        for blk in chain.blocks:
+            chain.cache.get(blk.spec, blk.conv.weight, 0)
+            chain.cache.get(blk.spec, blk.conv.weight, 1)
+    elif isinstance(module, Generator):
+        net = module._net()
+        for blk in net.blocks:
+            if blk is net.final and _final_is_fusable(net):
+                continue
+            net.cache.get(blk.spec, blk.conv.weight, 0)
+            net.cache.get(blk.spec, blk.conv.weight, 1)
+
+
 class _Saved:
     __slots__ = ("src0", "src1", "y", "a", "mean", "rstd", "scale", "shift", "seed", "mode", "in_dhw", "drop_p")
 
@@ -166,11 +213,16 @@ def _block_forward(blk: _Block, cache: _PackedWeights, src0, src1, training, see
     else:
         mode = UB_NORM_BATCH_TRAIN if (training or not nm.track_running_stats) else UB_NORM_BATCH_EVAL
         rm, rv = nm.running_mean, nm.running_var
-        if mode == UB_NORM_BATCH_TRAIN and nm.num_batches_tracked is not None:
-            nm.num_batches_tracked.add_(1)
     momentum = getattr(nm, "momentum", 0.1) or 0.1
+    defer = getattr(_bn_defer, "log", None) if (mode == UB_NORM_BATCH_TRAIN and rm is not None) else None
+    if defer is not None:
+        rm = rv = None
+    elif mode == UB_NORM_BATCH_TRAIN and nm.num_batches_tracked is not None:
+        nm.num_batches_tracked.add_(1)
     scale, shift, mean, rstd = ops.norm_finalize(stats, n, od * oh * ow, spec.cop, spec.co, nm.weight, nm.bias,
                                                  nm.eps, mode, momentum, rm, rv)
+    if defer is not None:
+        defer.append((nm, mean, rstd, spec.co, float(n) * od * oh * ow, momentum))
     drop_p = blk.drop_p if training else 0.0
     a, pooled = ops.norm_act_fwd(y, scale, shift, blk.slope, drop_p, seed, pool=pool)
     if save:

@@ -19,7 +19,7 @@ from ._lib import (ConvDesc, UB_CONV_K1, UB_CONV_K3S1P1, UB_CONV_K4S2P1, UB_CONV
 __all__ = [
     "ConvSpec", "pad32", "pack_conv_weights", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv1x1_to_ncdhw", "conv1x1_from_ncdhw_bwd", "pack_ncdhw", "unpack_ncdhw",
     "pack_patches", "unpack_patch", "paste_patch",
-    "norm_finalize", "norm_act_fwd", "norm_act_bwd", "maxpool_bwd", "colsum", "l1_fwd", "l1_bwd", "bce_logits",
+    "norm_finalize", "bn_running_update", "norm_act_fwd", "norm_act_bwd", "maxpool_bwd", "colsum", "l1_fwd", "l1_bwd", "bce_logits",
     "scale_by", "relerr_map_reduce", "dti_scalar_maps", "denorm_to_nifti",
 ]
 
@@ -316,6 +316,12 @@ def norm_finalize(stats, n, voxels, cp, c, gamma, beta, eps, mode, momentum=0.1,
                                     mode, momentum, _p(running_mean), _p(running_var), _p(scale), _p(shift), _p(mean),
                                     _p(rstd), _stream()), "ub_norm_finalize")
     return scale, shift, mean, rstd
+
+
+def bn_running_update(mean, rstd, c, count, eps, momentum, running_mean, running_var):
+    """Deferred BatchNorm running-statistics update from saved batch statistics (``norm_finalize`` without buffers)."""
+    _lib.check(_lib.load().ub_bn_running_update(_p(mean), _p(rstd), c, float(count), eps, momentum, _p(running_mean),
+                                                _p(running_var), _stream()), "ub_bn_running_update")
 
 
 def norm_act_fwd(y, scale, shift, slope, drop_p=0.0, drop_seed=0, pool=False):
