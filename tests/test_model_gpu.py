@@ -329,7 +329,10 @@ def test_config4_full_size_t1w_batch16():
         full = g(x)
         part = g(x[5:7])
     assert full.shape == (16, 6, 128, 128, 128)
-    assert rel_l2(full[5:7], part) < 1e-6
+    # not bitwise: the launch geometry (depth segments per CTA, split-K) depends on the batch size, so fp32 sums
+    # associate differently and a few bf16 roundings flip per layer (measured 4.5e-3 after 24 layers); leaking
+    # statistics or data between samples would show as an O(1) error
+    assert rel_l2(full[5:7], part) < 1e-2
     del full, part
     g.train()
     tr = GanTrainer(g, d)
