@@ -48,7 +48,7 @@ __device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
 // Counter-based dropout mask (replaces torch's Philox stream, which cannot be reproduced bit-exactly;
 // ref: monai ADN "D" = nn.Dropout(p), element-wise). Eight consecutive elements (one 16-byte vector)
 // share one counter = the vector index; two rounds of 32x32->64-bit multiply-fold (a "mum" hash) give
-// 128 bits = eight 16-bit uniforms, compared against round(p * 65536).
+// 128 bits = eight 16-bit lanes, of which 15 bits each are compared against round(p * 32768).
 __device__ __forceinline__ uint32_t mulfold(uint32_t a, uint32_t b) {
   const unsigned long long m = (unsigned long long)a * b;
   return (uint32_t)m ^ (uint32_t)(m >> 32);
@@ -65,29 +65,47 @@ __device__ __forceinline__ void dropout_bits8(unsigned long long e0, uint32_t se
   u[2] = (uint32_t)p1 ^ (q >> 13 | q << 19);
   u[3] = (uint32_t)(p1 >> 32) ^ (q >> 21 | q << 11);
 }
-// keep mask for the 8 consecutive elements starting at element index e0 (multiple of 8)
-__device__ __forceinline__ uint32_t dropout_keep8(unsigned long long e0, uint32_t seed, uint32_t thresh16) {
+// Keep decision per element: its 15-bit uniform (low 15 bits of its 16-bit lane) >= t15 = round(p * 32768).
+// `thresh` carries t15 in BOTH 16-bit lanes. Lane-wise compare without unpacking: setting bit 15 of every lane
+// before subtracting the threshold confines the borrow to the lane and leaves bit 15 = (u15 >= t15); PRMT's
+// sign-replication mode spreads that bit over the lane. One mask word per packed bf16x2 word: 0xFFFF keeps,
+// 0 drops -- applied with a single AND on the packed data (4 integer ops per 2 elements).
+__device__ __forceinline__ void dropout_maskw(unsigned long long e0, uint32_t seed, uint32_t thresh, uint32_t (&mw)[4]) {
   uint32_t u[4];
   dropout_bits8(e0, seed, u);
-  uint32_t m = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    m |= ((u[i] & 0xFFFFu) >= thresh16 ? 1u : 0u) << (2 * i);
-    m |= ((u[i] >> 16) >= thresh16 ? 1u : 0u) << (2 * i + 1);
+    const uint32_t d = ((u[i] & 0x7FFF7FFFu) | 0x80008000u) - thresh;
+    // prmt, generic mode: selector nibble = byte index | 8 -> replicate that byte's sign over the target byte
+    // (inline PTX: __byte_perm documents only the three index bits of each nibble)
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(mw[i]) : "r"(d), "r"(0u), "r"(0xBB99u));
   }
+}
+__device__ __forceinline__ void apply_maskw(bf16x8& v, const uint32_t (&mw)[4]) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w[i] &= mw[i];
+}
+// keep mask for the 8 consecutive elements starting at element index e0 (multiple of 8), bit i = element i
+__device__ __forceinline__ uint32_t dropout_keep8(unsigned long long e0, uint32_t seed, uint32_t thresh) {
+  uint32_t mw[4];
+  dropout_maskw(e0, seed, thresh, mw);
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) m |= ((mw[i] & 1u) | ((mw[i] >> 15) & 2u)) << (2 * i);
   return m;
 }
 
 struct NormActArgs;
-// Same mask as dropout_keep8, delivered as per-element factors f[i] = keep ? inv : 0 (no bit packing).
-__device__ __forceinline__ void dropout_factors8(unsigned long long e0, uint32_t seed, uint32_t thresh16, float inv,
+// Same mask as dropout_maskw, delivered as per-element factors f[i] = keep ? inv : 0.
+__device__ __forceinline__ void dropout_factors8(unsigned long long e0, uint32_t seed, uint32_t thresh, float inv,
                                                  float (&f)[8]) {
-  uint32_t u[4];
-  dropout_bits8(e0, seed, u);
+  uint32_t mw[4];
+  dropout_maskw(e0, seed, thresh, mw);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    f[2 * i] = (u[i] & 0xFFFFu) >= thresh16 ? inv : 0.f;
-    f[2 * i + 1] = (u[i] >> 16) >= thresh16 ? inv : 0.f;
+    f[2 * i] = (mw[i] & 0xFFFFu) ? inv : 0.f;
+    f[2 * i + 1] = (mw[i] >> 16) ? inv : 0.f;
   }
 }
 // LeakyReLU for slope <= 1 is max(x, slope * x); the general form keeps the select.
@@ -102,7 +120,7 @@ struct NormActArgs {
   float slope;          // LeakyReLU negative slope (1.0f = no activation)
   float drop_p;         // 0 = no dropout
   uint32_t drop_seed;
-  uint32_t drop_thresh; // round(p * 65536)
+  uint32_t drop_thresh; // round(p * 32768) in both 16-bit lanes
 };
 
 __device__ __forceinline__ void norm_act_apply8(float (&x)[8], const NormActArgs& A, int n, int Cp, int c0,
@@ -117,10 +135,10 @@ __device__ __forceinline__ void norm_act_apply8(float (&x)[8], const NormActArgs
     x[6] = fmaf(x[6], s1.z, h1.z); x[7] = fmaf(x[7], s1.w, h1.w);
   }
   if (A.drop_p > 0.f) {
-    const uint32_t keep = dropout_keep8(e0, A.drop_seed, A.drop_thresh);
-    const float inv = 1.f / (1.f - A.drop_p);
+    float f[8];
+    dropout_factors8(e0, A.drop_seed, A.drop_thresh, 1.f / (1.f - A.drop_p), f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = (keep >> i) & 1u ? x[i] * inv : 0.f;
+    for (int i = 0; i < 8; ++i) x[i] *= f[i];
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) x[i] = x[i] > 0.f ? x[i] : x[i] * A.slope;
@@ -347,6 +365,7 @@ norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restri
   const bool has_drop = A.drop_p > 0.f;
   const bool slope_le1 = A.slope <= 1.f;
   const float inv = has_drop ? 1.f / (1.f - A.drop_p) : 1.f;
+  const float slope_inv = A.slope * inv;
   float sc[8], sh[8];
   if (FIXED) {
     const int c0 = (int)(threadIdx.x % c8) * 8;
@@ -380,15 +399,20 @@ norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restri
 #pragma unroll
       for (int k = 0; k < 8; ++k) x[k] = fmaf(x[k], sc[k], sh[k]);
     }
-    if (has_drop) {
-      float f[8];
-      dropout_factors8((unsigned long long)(base + idx) * 8ull, A.drop_seed, A.drop_thresh, inv, f);
+    // dropout: the kept value is lrelu(x / (1-p)) = max(x * inv, x * slope * inv) (slope <= 1); dropped lanes
+    // are cleared on the packed words
 #pragma unroll
-      for (int k = 0; k < 8; ++k) x[k] *= f[k];
+    for (int k = 0; k < 8; ++k) {
+      const float hi = x[k] * inv, lo = x[k] * slope_inv;
+      x[k] = slope_le1 ? fmaxf(hi, lo) : (x[k] > 0.f ? hi : lo);
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) x[k] = lrelu(x[k], A.slope, slope_le1);
-    st_stream(av + idx, pack8(x));
+    bf16x8 o = pack8(x);
+    if (has_drop) {
+      uint32_t mw[4];
+      dropout_maskw((unsigned long long)(base + idx) * 8ull, A.drop_seed, A.drop_thresh, mw);
+      apply_maskw(o, mw);
+    }
+    st_stream(av + idx, o);
   }
 }
 
@@ -450,16 +474,19 @@ struct NormBwdArgs {
 __device__ __forceinline__ void dz1_8(const bf16x8& da8, const bf16x8& a8, const NormBwdArgs& B,
                                       unsigned long long e0, float (&dz)[8]) {
   float da[8], av[8];
-  unpack8(da8, da);
+  bf16x8 dm = da8;
+  float inv = 1.f;
+  if (B.drop_p > 0.f) {
+    uint32_t mw[4];
+    dropout_maskw(e0, B.drop_seed, B.drop_thresh, mw);
+    apply_maskw(dm, mw);
+    inv = 1.f / (1.f - B.drop_p);
+  }
+  const float sinv = B.slope * inv;
+  unpack8(dm, da);
   unpack8(a8, av);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) dz[i] = da[i] * (av[i] > 0.f ? 1.f : B.slope);
-  if (B.drop_p > 0.f) {
-    float f[8];
-    dropout_factors8(e0, B.drop_seed, B.drop_thresh, 1.f / (1.f - B.drop_p), f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) dz[i] *= f[i];
-  }
+  for (int i = 0; i < 8; ++i) dz[i] = da[i] * (av[i] > 0.f ? inv : sinv);
 }
 
 // Same with the activation sign recomputed from the raw conv output y (no read of `a`).
@@ -467,15 +494,18 @@ __device__ __forceinline__ void dz1_from_y8(const bf16x8& da8, const float (&yy)
                                             const float (&sh)[8], const NormBwdArgs& B, unsigned long long e0,
                                             float (&dz)[8]) {
   float da[8];
-  unpack8(da8, da);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) dz[i] = da[i] * (fmaf(yy[i], sc[i], sh[i]) > 0.f ? 1.f : B.slope);
+  bf16x8 dm = da8;
+  float inv = 1.f;
   if (B.drop_p > 0.f) {
-    float f[8];
-    dropout_factors8(e0, B.drop_seed, B.drop_thresh, 1.f / (1.f - B.drop_p), f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) dz[i] *= f[i];
+    uint32_t mw[4];
+    dropout_maskw(e0, B.drop_seed, B.drop_thresh, mw);
+    apply_maskw(dm, mw);
+    inv = 1.f / (1.f - B.drop_p);
   }
+  const float sinv = B.slope * inv;
+  unpack8(dm, da);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dz[i] = da[i] * (fmaf(yy[i], sc[i], sh[i]) > 0.f ? inv : sinv);
 }
 
 // grid = (blocks_per_sample, N); each block strides over the vectors of one sample; partial sums are

@@ -312,7 +312,12 @@ static void march_geometry(int n, int D, int H, int W, int* tiles_w, int* tiles_
   *nseg = cdiv(D, *seg_len);
 }
 
-static uint32_t drop_thresh(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
+// 15-bit keep threshold round(p * 32768), replicated into both 16-bit lanes (pointwise.cuh: dropout_maskw)
+static uint32_t drop_thresh(float p) {
+  uint32_t t = (uint32_t)(p * 32768.0f + 0.5f);
+  if (t > 32767u) t = 32767u;
+  return t * 0x00010001u;
+}
 
 static int launch_march(const void* src0, int c0p, const void* src1, int c1p, int n, int D, int H, int W,
                         const void* w_packed, const float* bias, int bias_n, void* out, float* stats,
