@@ -81,3 +81,29 @@ def test_config5_geometry_and_eval():
     ref_errs, _ = E.roi_error_avg(ref, mask, probseg)
     np.testing.assert_allclose(diff.cpu().numpy(), ref, rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(errs.cpu().numpy(), ref_errs, rtol=1e-4)
+
+
+def test_graph_replay_equals_eager_and_follows_weight_updates():
+    """predict_volume with the CUDA-graph replay of the generator forward is bit-identical to eager launches,
+    pads a short last batch, and re-captures when the weights change."""
+    import unet_bssfp_b200 as ub
+    torch.manual_seed(0)
+    g = ub.Generator("t1w").to(DEV).eval()
+    torch.manual_seed(3)
+    vol = torch.rand((6, 48, 80, 40), device=DEV)                     # 12 patches of 32^3: batches of 5, 5, 2
+    eager = ub.inference.predict_volume(g, vol, patch=32, batch=5, use_graph=False)
+    graph = ub.inference.predict_volume(g, vol, patch=32, batch=5, use_graph=True)
+    assert torch.equal(eager, graph)
+    again = ub.inference.predict_volume(g, vol, patch=32, batch=5, use_graph=True)      # replay of the cached graph
+    assert torch.equal(eager, again) and len(g._infer_graphs) == 1
+    first = next(iter(g._infer_graphs.values()))
+    with torch.no_grad():
+        g.blocks["unet"].final_conv.bias.add_(0.5)                     # in-place update: the cached graph is stale
+    moved = ub.inference.predict_volume(g, vol, patch=32, batch=5, use_graph=True)
+    assert next(iter(g._infer_graphs.values())) is not first
+    assert torch.equal(moved, ub.inference.predict_volume(g, vol, patch=32, batch=5, use_graph=False))
+    assert (moved - eager - 0.5).abs().max().item() < 1e-5
+    g.train()                                                          # train mode (dropout, batch statistics): eager path
+    torch.manual_seed(1); a = ub.inference.predict_volume(g, vol, patch=32, batch=5)
+    torch.manual_seed(1); b = ub.inference.predict_volume(g, vol, patch=32, batch=5, use_graph=False)
+    assert torch.equal(a, b)

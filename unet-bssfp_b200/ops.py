@@ -232,9 +232,10 @@ def pack_ncdhw(a: torch.Tensor, b: torch.Tensor | None = None, s2d: bool = False
     return out
 
 
-def pack_patches(volume: torch.Tensor, origins, patch) -> torch.Tensor:
+def pack_patches(volume: torch.Tensor, origins, patch, out: torch.Tensor | None = None) -> torch.Tensor:
     """Gather ``len(origins)`` patches of an NCDHW fp32 volume (1,C,D,H,W) or (C,D,H,W) into one
-    (n, pd, ph, pw, Cp) bf16 batch. ``origins``: (z, y, x) starts; ``patch``: (pd, ph, pw)."""
+    (n, pd, ph, pw, Cp) bf16 batch. ``origins``: (z, y, x) starts; ``patch``: (pd, ph, pw). ``out``: write into the
+    first ``len(origins)`` samples of this existing batch tensor (the static input of a captured CUDA graph)."""
     _require_cuda(volume)
     lib = _lib.load()
     vol = volume if volume.dim() == 4 else volume[0]
@@ -249,7 +250,11 @@ def pack_patches(volume: torch.Tensor, origins, patch) -> torch.Tensor:
         if z < 0 or y < 0 or x < 0 or z + pd > D or y + ph > H or x + pw > W:
             raise RuntimeError(f"patch at {(z, y, x)} of size {patch} leaves the volume {(D, H, W)}")
     cp = pad32(c)
-    out = torch.empty((n, pd, ph, pw, cp), dtype=torch.bfloat16, device=vol.device)
+    if out is None:
+        out = torch.empty((n, pd, ph, pw, cp), dtype=torch.bfloat16, device=vol.device)
+    elif (out.dtype != torch.bfloat16 or not out.is_contiguous() or out.shape[0] < n
+          or tuple(out.shape[1:]) != (pd, ph, pw, cp)):
+        raise RuntimeError("pack_patches: `out` must be a contiguous (>= n, pd, ph, pw, Cp) bf16 tensor")
     _lib.check(lib.ub_pack_patches(_p(vol), c, n, offs, pd, ph, pw, sc, sd, sh, cp, _p(out), _stream()), "ub_pack_patches")
     return out
 
