@@ -77,11 +77,15 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
+                try:
+                    pw.append(float(r[2]))
+                except Exception:
+                    pass
                 for k, nme in enumerate(names):
                     if r[3 + k].lower().startswith("active"):
                         reasons.add(nme)
@@ -89,7 +93,9 @@ class ClockSampler:
                 pass
         # median under load: ignore idle samples far below the busiest
         hot = [v for v in sm if v >= 0.5 * max(sm)] if sm else []
+        hot_pw = [p for p, v in zip(pw, sm) if v >= 0.5 * max(sm)] if (sm and len(pw) == len(sm)) else pw
         return {"sm_mhz": statistics.median(hot) if hot else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w": statistics.median(hot_pw) if hot_pw else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 

@@ -345,6 +345,78 @@ __global__ void stats_finalize_kernel(const float* __restrict__ partial, int til
   }
 }
 
+// BatchNorm (training) statistics over MANY tile partials (the full-resolution input head: 32 768 records) in two
+// stages, so the reduction is not one thread block reading 8 MB. Stage 1, grid = (Cp/32, N), block = (32, 32): the
+// fp64 sums of sample n go, as raw bits, into the four per-(n, c) output slots (scale | shift hold sum, mean | rstd
+// hold sumsq) -- scratch that stage 2 overwrites. Stage 2, grid = (Cp/32), block = 32: channel c adds its N pairs in
+// order and writes the final values to every row.
+__global__ void bn_stats_stage1_kernel(const float* __restrict__ partial, int tiles_per_sample, int Cp,
+                                       float* __restrict__ scale, float* __restrict__ shift,
+                                       float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  __shared__ double sh_s[32][32], sh_q[32][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int n = blockIdx.y;
+  const int t0 = n * tiles_per_sample, t1 = t0 + tiles_per_sample;
+  double s = 0.0, q = 0.0;
+  float fs[4], fq[4];
+  int t = t0 + threadIdx.y;
+  for (; t + 96 < t1; t += 128) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      fs[u] = partial[((size_t)(t + 32 * u) * 2 + 0) * Cp + c];
+      fq[u] = partial[((size_t)(t + 32 * u) * 2 + 1) * Cp + c];
+    }
+    s += ((double)fs[0] + (double)fs[1]) + ((double)fs[2] + (double)fs[3]);
+    q += ((double)fq[0] + (double)fq[1]) + ((double)fq[2] + (double)fq[3]);
+  }
+  for (; t < t1; t += 32) {
+    s += (double)partial[((size_t)t * 2 + 0) * Cp + c];
+    q += (double)partial[((size_t)t * 2 + 1) * Cp + c];
+  }
+  sh_s[threadIdx.y][threadIdx.x] = s;
+  sh_q[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y != 0) return;
+  for (int k = 1; k < 32; ++k) { s += sh_s[k][threadIdx.x]; q += sh_q[k][threadIdx.x]; }
+  const size_t o = (size_t)n * Cp + c;
+  const unsigned long long sb = (unsigned long long)__double_as_longlong(s), qb = (unsigned long long)__double_as_longlong(q);
+  scale[o] = __uint_as_float((uint32_t)sb); shift[o] = __uint_as_float((uint32_t)(sb >> 32));
+  mean_out[o] = __uint_as_float((uint32_t)qb); rstd_out[o] = __uint_as_float((uint32_t)(qb >> 32));
+}
+__global__ void bn_stats_stage2_kernel(int Nb, int Cp, int C, double count_per_sample, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, float momentum,
+                                       float* __restrict__ running_mean, float* __restrict__ running_var,
+                                       float* __restrict__ scale, float* __restrict__ shift,
+                                       float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s = 0.0, q = 0.0;
+  for (int n = 0; n < Nb; ++n) {
+    const size_t o = (size_t)n * Cp + c;
+    const unsigned long long sb = (unsigned long long)__float_as_uint(scale[o]) | ((unsigned long long)__float_as_uint(shift[o]) << 32);
+    const unsigned long long qb = (unsigned long long)__float_as_uint(mean_out[o]) | ((unsigned long long)__float_as_uint(rstd_out[o]) << 32);
+    s += __longlong_as_double((long long)sb);
+    q += __longlong_as_double((long long)qb);
+  }
+  const double cnt = count_per_sample * Nb;
+  const double mean = s / cnt;
+  double var = q / cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  if (c < C && running_mean != nullptr) {
+    const double unbiased = cnt > 1.0 ? var * cnt / (cnt - 1.0) : var;
+    running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+    running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+  }
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  const float g = c < C ? gamma[c] : 0.f, b = c < C ? beta[c] : 0.f;
+  for (int n = 0; n < Nb; ++n) {
+    const size_t o = (size_t)n * Cp + c;
+    scale[o] = (float)(g * rstd);
+    shift[o] = (float)(b - mean * g * rstd);
+    mean_out[o] = (float)mean;
+    rstd_out[o] = (float)rstd;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward: a = LeakyReLU(Dropout(y * scale + shift)); optional fused MaxPool3d(2)
 // ------------------------------------------------------------------------------------------------
@@ -586,44 +658,55 @@ norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bflo
 }
 
 // Reduce block partials -> c1, c2 per (n,c) and accumulate dgamma / dbeta (/ bias grad in eval-BN).
-// mode as in stats_finalize. grid = (Cp/32), block = (32 channels, 32 lanes over the partial blocks).
-__global__ void norm_bwd_finalize_kernel(const float* __restrict__ part, int blocks_per_sample, int Nb, int Cp, int C,
-                                         double count_per_sample, int mode, const float* __restrict__ xscale,
-                                         float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
-                                         float* __restrict__ dbeta, float* __restrict__ dbias) {
-  __shared__ double sh1[32][33], sh2[32][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
+// mode as in stats_finalize. grid = (Cp/32); block = (32 lanes over the partial records, 32 channels): one WARP per
+// channel, so the per-sample sums are a shuffle tree (fixed order: deterministic) and the sample loop needs no block
+// barrier -- this kernel sits on the critical path of every norm backward (~36 launches per step).
+__global__ void __launch_bounds__(1024)
+norm_bwd_finalize_kernel(const float* __restrict__ part, int blocks_per_sample, int Nb, int Cp, int C,
+                         double count_per_sample, int mode, const float* __restrict__ xscale, float* __restrict__ c1,
+                         float* __restrict__ c2, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                         float* __restrict__ dbias) {
+  const int lane = threadIdx.x;
+  const int c = blockIdx.x * 32 + threadIdx.y;
   double tot1 = 0.0, tot2 = 0.0;
   for (int n = 0; n < Nb; ++n) {
+    const float* p0 = part + ((size_t)n * blocks_per_sample * 2) * Cp + c;
+    float f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};
     double s1 = 0.0, s2 = 0.0;
-    for (int b = threadIdx.y; b < blocks_per_sample; b += 32) {
-      const float* p = part + ((size_t)(n * blocks_per_sample + b) * 2) * Cp;
-      s1 += (double)p[c];
-      s2 += (double)p[Cp + c];
-    }
-    sh1[threadIdx.y][threadIdx.x] = s1;
-    sh2[threadIdx.y][threadIdx.x] = s2;
-    __syncthreads();
-    if (threadIdx.y == 0) {
-      for (int k = 1; k < 32; ++k) { s1 += sh1[k][threadIdx.x]; s2 += sh2[k][threadIdx.x]; }
-      tot1 += s1;
-      tot2 += s2;
-      if (mode == 0) {
-        c1[(size_t)n * Cp + c] = (float)(s1 / count_per_sample);
-        c2[(size_t)n * Cp + c] = (float)(s2 / count_per_sample);
+    int b = lane;
+    for (; b + 96 < blocks_per_sample; b += 128) {          // four independent loads in flight per thread
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        f1[u] = p0[(size_t)(b + 32 * u) * 2 * Cp];
+        f2[u] = p0[(size_t)(b + 32 * u) * 2 * Cp + Cp];
       }
+      s1 += ((double)f1[0] + (double)f1[1]) + ((double)f1[2] + (double)f1[3]);
+      s2 += ((double)f2[0] + (double)f2[1]) + ((double)f2[2] + (double)f2[3]);
     }
-    __syncthreads();
+    for (; b < blocks_per_sample; b += 32) {
+      s1 += (double)p0[(size_t)b * 2 * Cp];
+      s2 += (double)p0[(size_t)b * 2 * Cp + Cp];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    tot1 += s1;
+    tot2 += s2;
+    if (mode == 0 && lane == 0) {
+      c1[(size_t)n * Cp + c] = (float)(s1 / count_per_sample);
+      c2[(size_t)n * Cp + c] = (float)(s2 / count_per_sample);
+    }
   }
-  if (threadIdx.y != 0) return;
   if (mode != 0) {
     const double cnt = count_per_sample * Nb;
-    for (int n = 0; n < Nb; ++n) {
+    for (int n = lane; n < Nb; n += 32) {
       c1[(size_t)n * Cp + c] = mode == 1 ? (float)(tot1 / cnt) : 0.f;
       c2[(size_t)n * Cp + c] = mode == 1 ? (float)(tot2 / cnt) : 0.f;
     }
   }
-  if (c < C) {
+  if (lane == 0 && c < C) {
     if (dgamma) dgamma[c] = (float)tot2;
     if (dbeta) dbeta[c] = (float)tot1;
     // conv bias feeding a batch-statistics norm has an analytically zero gradient; with running
@@ -763,13 +846,16 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long lon
     part[(size_t)blockIdx.x * Cp + c] = t;
   }
 }
+// grid = ceil(C / 8), block = (32 lanes over the block partials, 8 channels): one warp per channel, shuffle tree
 __global__ void colsum_finish_kernel(const float* __restrict__ part, int nblocks, int Cp, int C,
                                      float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * blockDim.y + threadIdx.y;
   if (c >= C) return;
   double t = 0.0;
-  for (int b = 0; b < nblocks; ++b) t += (double)part[(size_t)b * Cp + c];
-  out[c] = (float)t;
+  for (int b = threadIdx.x; b < nblocks; b += 32) t += (double)part[(size_t)b * Cp + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (threadIdx.x == 0) out[c] = (float)t;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -830,6 +916,26 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
   if (co >= A.co || cir < 0 || A.tapmap[tap] < 0) return;
   float s = 0.f;
   for (int k = 0; k < A.nsplit; ++k) s += part[(size_t)k * per_split + i];
+  grad[(size_t)cir * A.stride_ci + (size_t)co * A.stride_co + (size_t)A.tapmap[tap] * A.dst_tap_stride] = s;
+}
+// Same reduction for SMALL outputs with many splits (the 32-channel layers: 27.6 k outputs x 148 splits): eight lanes
+// share one output and stride over the splits, so the serial chain is 8x shorter; shuffle tree, fixed order.
+__global__ void wgrad_reduce_wide_kernel(const float* __restrict__ part, float* __restrict__ grad, WgradReduceArgs A) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_split = (long long)A.ntap * A.ci_total * A.co_total;
+  const long long i = t >> 3;
+  const int sub = (int)(t & 7);
+  float s = 0.f;
+  if (i < per_split)
+    for (int k = sub; k < A.nsplit; k += 8) s += part[(size_t)k * per_split + i];
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (i >= per_split || sub != 0) return;
+  const int co = (int)(i % A.co_total);
+  const int ci = (int)((i / A.co_total) % A.ci_total);
+  const int tap = (int)(i / ((long long)A.co_total * A.ci_total));
+  const int cir = concat_real_index(ci, A.split_pad, A.split_real, A.ci);
+  if (co >= A.co || cir < 0 || A.tapmap[tap] < 0) return;
   grad[(size_t)cir * A.stride_ci + (size_t)co * A.stride_co + (size_t)A.tapmap[tap] * A.dst_tap_stride] = s;
 }
 
@@ -1142,15 +1248,18 @@ conv1x1_from_ncdhw_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat1
     pb[i] = a;
   }
 }
-// sums the block partials in fp64: dw [co][ci], db [co]
+// sums the block partials in fp64: dw [co][ci], db [co]. block = (32 lanes over the partials, 4 outputs)
 __global__ void conv1x1_bwd_finish_kernel(const float* __restrict__ part, int nblocks, int co, int ci, float* __restrict__ dw,
                                           float* __restrict__ db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * blockDim.y + threadIdx.y;
   if (i >= kC1MaxCo * 33) return;
   const int c = i / 33, k = i % 33;
   if (c >= co) return;
   double a = 0.0;
-  for (int b = 0; b < nblocks; ++b) a += (double)part[(size_t)b * kC1MaxCo * 33 + i];
+  for (int b = threadIdx.x; b < nblocks; b += 32) a += (double)part[(size_t)b * kC1MaxCo * 33 + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (threadIdx.x != 0) return;
   if (k == 32) { if (db) db[c] = (float)a; }
   else if (k < ci && dw) dw[c * ci + k] = (float)a;
 }

@@ -850,7 +850,10 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
     R.split_real = d->c1p ? d->c0 : 0;
     for (int i = 0; i < 64; ++i) R.tapmap[i] = i < ntap ? i : -1;
     const long long per_split = (long long)ntap * R.ci_total * d->cop;
-    wgrad_reduce_kernel<<<(unsigned)((per_split + 255) / 256), 256, 0, st>>>(M.partial, dw, R);
+    if (per_split <= 65536 && nsplit >= 32)
+      wgrad_reduce_wide_kernel<<<(unsigned)((per_split * 8 + 255) / 256), 256, 0, st>>>(M.partial, dw, R);
+    else
+      wgrad_reduce_kernel<<<(unsigned)((per_split + 255) / 256), 256, 0, st>>>(M.partial, dw, R);
     UB_LAUNCH_CHECK();
     return 0;
   }
@@ -891,7 +894,10 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
   R.split_real = d->c1p ? d->c0 : 0;
   for (int i = 0; i < 64; ++i) R.tapmap[i] = i < pl.ntap_lin ? pl.tapmap[i] : -1;
   const long long per_split = (long long)R.ntap * R.ci_total * R.co_total;
-  wgrad_reduce_kernel<<<(unsigned)((per_split + 255) / 256), 256, 0, st>>>(P.partial, dw, R);
+  if (per_split <= 65536 && R.nsplit >= 32)
+    wgrad_reduce_wide_kernel<<<(unsigned)((per_split * 8 + 255) / 256), 256, 0, st>>>(P.partial, dw, R);
+  else
+    wgrad_reduce_kernel<<<(unsigned)((per_split + 255) / 256), 256, 0, st>>>(P.partial, dw, R);
   UB_LAUNCH_CHECK();
   return 0;
 }
@@ -1000,6 +1006,16 @@ extern "C" int ub_norm_finalize(const float* stats_partial, int tiles_per_sample
   if ((mode != 2 && !stats_partial) || !gamma || !beta || !scale || !shift || !mean || !rstd || cp % 32)
     return fail(-1, "bad arguments to ub_norm_finalize");
   if (mode == 2 && (!running_mean || !running_var)) return fail(-1, "eval BatchNorm needs running statistics");
+  if (mode == UB_NORM_BATCH_TRAIN && n > 1 && (long long)tiles_per_sample * n >= 2048) {
+    // many tile partials (the full-resolution input head): per-sample sums first, then one small combine
+    bn_stats_stage1_kernel<<<dim3(cp / 32, n), dim3(32, 32), 0, (cudaStream_t)stream>>>(stats_partial, tiles_per_sample, cp,
+                                                                                      scale, shift, mean, rstd);
+    UB_LAUNCH_CHECK();
+    bn_stats_stage2_kernel<<<cp / 32, 32, 0, (cudaStream_t)stream>>>(n, cp, c, voxels_per_sample, gamma, beta, eps, momentum,
+                                                                    running_mean, running_var, scale, shift, mean, rstd);
+    UB_LAUNCH_CHECK();
+    return 0;
+  }
   stats_finalize_kernel<<<dim3(cp / 32, mode == UB_NORM_INSTANCE ? n : 1), dim3(32, 32), 0, (cudaStream_t)stream>>>(
       stats_partial, tiles_per_sample, n, cp, c, voxels_per_sample, gamma, beta, eps, mode, momentum, running_mean,
       running_var, scale, shift, mean, rstd);
@@ -1121,7 +1137,7 @@ extern "C" int ub_colsum(const void* x, long long rows, int cp, int c, void* wor
   colsum_bf16_kernel<<<kColsumBlocks, threads, threads * 8 * sizeof(float), st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), rows, cp, reinterpret_cast<float*>(workspace));
   UB_LAUNCH_CHECK();
-  colsum_finish_kernel<<<(c + 63) / 64, 64, 0, st>>>(reinterpret_cast<const float*>(workspace), kColsumBlocks, cp, c, out);
+  colsum_finish_kernel<<<(c + 7) / 8, dim3(32, 8), 0, st>>>(reinterpret_cast<const float*>(workspace), kColsumBlocks, cp, c, out);
   UB_LAUNCH_CHECK();
   return 0;
 }
@@ -1267,7 +1283,7 @@ extern "C" int ub_conv1x1_from_ncdhw_bwd(const float* dout, int co, const void* 
   }
   UB_LAUNCH_CHECK();
   if (want_w) {
-    conv1x1_bwd_finish_kernel<<<(kC1MaxCo * 33 + 127) / 128, 128, 0, st>>>(part, (int)(blocks * n), co, ci, dw, db);
+    conv1x1_bwd_finish_kernel<<<(kC1MaxCo * 33 + 3) / 4, dim3(32, 4), 0, st>>>(part, (int)(blocks * n), co, ci, dw, db);
     UB_LAUNCH_CHECK();
   }
   return 0;
