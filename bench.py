@@ -162,10 +162,10 @@ def dominant_kernel_roofline(dev, batch, size, peaks, iters=5):
     ms = statistics.median(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
     flops = 2.0 * batch * size ** 3 * 27 * 96 * 32
     ach = flops / (ms * 1e-3) / 1e12
-    # DRAM traffic of this launch from the committed `ncu --set full` capture (profiles/r01m_march96_ncu_summary.txt):
-    # dram__bytes_read.sum 3.262 GB + dram__bytes_write.sum 1.055 GB; algorithmic bytes = both sources once +
-    # the output once = (32 + 64 + 32) ch * 2 B * 8 * 128^3 voxels = 4.295 GB
-    traffic = 3.262496e9 + 1.054787e9 if (batch, size) == (8, 128) else None
+    # DRAM traffic of this launch from the committed `ncu --set full` capture of the CTA-pair kernel
+    # (profiles/r01w_march96_pair_ncu_summary.txt): dram__bytes_read.sum 3.267 GB + dram__bytes_write.sum 1.053 GB;
+    # algorithmic bytes = both sources once + the output once = (32 + 64 + 32) ch * 2 B * 8 * 128^3 voxels = 4.295 GB
+    traffic = 3.267318e9 + 1.052962e9 if (batch, size) == (8, 128) else None
     return {"bound": "tensor", "kernel": "igemm_march_kernel[upcat_1.conv_0 fwd, cat[32|64]->32 k3, 8x128^3]", "achieved": ach,
             "peak": peaks["bf16_burst"], "peak_src": peaks["src"] + " (burst: kernel timed alone)", "unit": "TFLOP/s",
             "frac": ach / peaks["bf16_burst"], "ms_per_launch": ms, "flops_per_launch": flops, "traffic": traffic,
