@@ -156,8 +156,11 @@ def test_goldens_regenerate_from_the_reference():
     """Where the reference is mounted (the build container), re-run its eval functions and compare with the
     committed file, so the fixture cannot drift from the script that claims to have produced it."""
     from tests.golden import make_golden_ref as M
-    _, ref_eval = M.load_reference()
-    out = {}
-    M.eval_goldens(ref_eval, out)
+    try:
+        _, ref_eval = M.load_reference()
+        out = {}
+        M.eval_goldens(ref_eval, out)
+    finally:
+        M.unload_stubs()
     for k in ("eval_diff_rel", "eval_errs_rel", "eval_diff_ang", "denorm_out", "dti_fa", "dti_azimuth", "dti_rgb"):
         np.testing.assert_array_equal(out[k], REF[k], err_msg=k)
