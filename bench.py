@@ -206,10 +206,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     import unet_bssfp_b200 as ub
-    from unet_bssfp_b200 import _lib
+    from unet_bssfp_b200 import _lib, hostmem
     from unet_bssfp_b200.train_step import GanTrainer
     lib = _lib.load()
     peaks = load_peaks()
+    # one process per GPU: stage the pinned input batch on the NUMA node of this rank's GPU (before allocating it)
+    numa_cpus = hostmem.bind_to_gpu(local) if (world > 1 and os.environ.get("UB_BIND_NUMA", "1") != "0") else None
 
     torch.manual_seed(0)  # same initial weights on every rank (DDP would broadcast rank 0's)
     gen = ub.Generator(args.modality).to(dev)
@@ -294,7 +296,8 @@ def main():
         ms_e_step = ms_e.item() / args.steps
         e2e = {"value": voxels_per_step / (ms_e_step * 1e-3), "unit": UNIT, "ms_per_step": ms_e_step,
                "h2d_bytes_per_step": int((x_host.numel() + y_host.numel()) * 4), "d2h_bytes_per_step": 8,
-               "how": "pinned host batch -> double-buffered H2D on a copy stream -> GanTrainer.step -> losses D2H"}
+               "how": "pinned host batch -> double-buffered H2D on a copy stream -> GanTrainer.step -> losses D2H",
+               "numa_bound_cpus": len(numa_cpus) if numa_cpus else None}
 
     roof = cpu = None
     if rank == 0:

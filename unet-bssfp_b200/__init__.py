@@ -11,4 +11,5 @@ from .modules import (BasicUNet, BCEWithLogitsLoss, Discriminator, DownSampleCon
 from . import ops  # noqa: E402,F401
 from . import inference  # noqa: E402,F401
 from . import nifti  # noqa: E402,F401
+from . import hostmem  # noqa: E402,F401
 from .optim import FusedAdamW  # noqa: E402,F401
