@@ -164,3 +164,26 @@ def test_goldens_regenerate_from_the_reference():
         M.unload_stubs()
     for k in ("eval_diff_rel", "eval_errs_rel", "eval_diff_ang", "denorm_out", "dti_fa", "dti_azimuth", "dti_rgb"):
         np.testing.assert_array_equal(out[k], REF[k], err_msg=k)
+
+
+def test_config1_full_size_matches_the_reference():
+    """BASELINE config 1 exactly (G fwd + bwd, one 64^3 bSSFP patch, batch 1, fp32 CPU) against the reference's run."""
+    g, _, ok = _same_init("bssfp")
+    if not ok:
+        pytest.skip("default torch init differs from the torch version that generated the goldens")
+    zero_dropout(g)
+    g.train()
+    x, y = synth_batch(24, b=1, s=64, seed=4321)
+    y_hat = g(x)
+    loss = torch.nn.functional.l1_loss(y_hat, y)
+    loss.backward()
+    assert abs(loss.item() - float(REF["cfg1_loss"])) < 1e-6
+    np.testing.assert_allclose(y_hat.detach()[0, :, ::21, ::21, ::21].numpy(), REF["cfg1_out_probe"], rtol=1e-4, atol=1e-5)
+    names = [k for k, p in g.named_parameters() if p.grad is not None]
+    assert names == list(REF["cfg1_grad_names"])
+    norms = np.array([p.grad.double().norm().item() for k, p in g.named_parameters() if p.grad is not None])
+    # conv biases in front of a batch-statistics norm: analytically zero gradients, rounding noise on both sides
+    big = np.array([not (k.endswith("conv.bias") and "final_conv" not in k and "deconv" not in k) for k in names])
+    np.testing.assert_allclose(norms[big], REF["cfg1_grad_norms"][big], rtol=2e-3)
+    np.testing.assert_allclose(g.blocks["unet"].final_conv.weight.grad.numpy(), REF["cfg1_grad_final_conv_weight"],
+                               rtol=1e-3, atol=1e-7)

@@ -185,3 +185,40 @@ def test_denormalised_volume_matches_reference_output():
     block = nifti.volume_to_nifti_order(vol, (lo, hi)).cpu().numpy()  # (C,Z,Y,X)
     got = block.transpose(3, 2, 1, 0)                             # logical (X,Y,Z,C)
     np.testing.assert_array_equal(got, REF["denorm_out"].astype(np.float32))   # bit-exact after the float32 store
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_config1_full_size_against_the_reference(precision):
+    """BASELINE config 1 (G fwd + bwd, one 64^3 bSSFP patch, batch 1) against the reference's own fp32 CPU run:
+    fp32 mode at the fp32 bar, the bf16 tensor-core path at the bf16 bar."""
+    import unet_bssfp_b200 as ub
+    g, _ = _fresh("bssfp")
+    ub.set_precision(g, precision)
+    g.train()
+    x, y = synth_batch(24, b=1, s=64, seed=4321)
+    x, y = x.to(DEV), y.to(DEV)
+    y_hat = g(x)
+    loss = ub.L1Loss()(y_hat, y)
+    loss.backward()
+    probe = y_hat.detach()[0, :, ::21, ::21, ::21].cpu().numpy()
+    ms = REF["cfg1_out_mean_std"]
+    names = [k for k, p in g.named_parameters() if p.grad is not None]
+    assert names == list(REF["cfg1_grad_names"])
+    norms = np.array([p.grad.double().norm().item() for k, p in g.named_parameters() if p.grad is not None])
+    # conv biases in front of a batch-statistics norm: analytically zero gradients, rounding noise on both sides
+    big = np.array([not (k.endswith("conv.bias") and "final_conv" not in k and "deconv" not in k) for k in names])
+    fcw = g.blocks["unet"].final_conv.weight.grad.cpu()
+    if precision == "fp32":
+        assert abs(loss.item() - float(REF["cfg1_loss"])) < 1e-5 * float(REF["cfg1_loss"]) + 1e-6
+        np.testing.assert_allclose(probe, REF["cfg1_out_probe"], rtol=1e-4, atol=1e-5)
+        assert abs(y_hat.double().mean().item() - ms[0]) < 1e-5 and abs(y_hat.double().std().item() - ms[1]) < 1e-5
+        np.testing.assert_allclose(norms[big], REF["cfg1_grad_norms"][big], rtol=5e-3)
+        assert rel_l2(fcw, torch.from_numpy(REF["cfg1_grad_final_conv_weight"])) < 1e-3
+    else:
+        assert abs(loss.item() / float(REF["cfg1_loss"]) - 1) < 1e-2
+        assert np.abs(probe - REF["cfg1_out_probe"]).max() < 3e-2 * np.abs(REF["cfg1_out_probe"]).max()
+        assert abs(y_hat.double().std().item() / ms[1] - 1) < 1e-2
+        # gradient norms: the L1 sign gradient at random initialisation is ill-conditioned in bf16 (see
+        # test_phase_gradients_match_reference); the overall scale must still be right
+        ratio = norms[big] / REF["cfg1_grad_norms"][big]
+        assert 0.5 < float(np.median(ratio)) < 2.0, float(np.median(ratio))
