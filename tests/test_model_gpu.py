@@ -340,3 +340,28 @@ def test_config4_full_size_t1w_batch16():
     torch.cuda.synchronize()
     assert torch.isfinite(gl) and torch.isfinite(dl)
     assert 0.3 < float(dl) < 1.5                       # (BCE(real, 1) + BCE(fake, 0)) / 2 near ln 2 at initialisation
+
+
+def test_config2_full_size_properties():
+    """BASELINE config 2 at full size (bssfp, batch 8, 128^3): size-independent properties. Eval-mode samples are
+    independent (generator: InstanceNorm; discriminator: running statistics); the fused L1 / BCE losses equal their
+    definitions on the full tensors; the discriminator's logits of a permuted batch are the permuted logits."""
+    import unet_bssfp_b200 as ub
+    torch.manual_seed(0)
+    g, d = ub.Generator("bssfp").to(DEV).eval(), ub.Discriminator("bssfp").to(DEV).eval()
+    torch.manual_seed(11)
+    x = torch.rand(8, 24, 128, 128, 128, device=DEV)
+    y = torch.rand(8, 6, 128, 128, 128, device=DEV)
+    with torch.no_grad():
+        y_hat = g(x)
+        assert y_hat.shape == (8, 6, 128, 128, 128) and torch.isfinite(y_hat).all()
+        assert rel_l2(y_hat[2:3], g(x[2:3])) < 1e-2                    # bf16 noise level, see the config-4 test
+        logits = d(x, y_hat)
+        assert logits.shape == (8, 1, 4, 4, 4)
+        perm = torch.tensor([3, 0, 7, 1, 6, 2, 5, 4], device=DEV)
+        assert rel_l2(d(x[perm], y_hat[perm]), logits[perm]) < 1e-2
+        l1 = ub.L1Loss()(y_hat, y)
+        assert abs(l1.item() - (y_hat - y).abs().mean().item()) < 1e-6 * max(1.0, l1.item())
+        bce = ub.BCEWithLogitsLoss()(logits, torch.ones_like(logits))
+        ref = torch.nn.functional.binary_cross_entropy_with_logits(logits, torch.ones_like(logits))
+        assert abs(bce.item() - ref.item()) < 1e-6
