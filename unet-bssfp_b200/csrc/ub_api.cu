@@ -394,6 +394,22 @@ static int launch_march(const void* src0, int c0p, const void* src1, int c1p, in
 static inline int k4_parity(int k) { return (k & 1) ? 0 : 1; }
 static inline int k4_shift(int k) { return k >> 1; }
 
+// Planes per tile of the generic 3x3x3 / 1x1x1 kernel. Four planes amortise the depth halo and the weight stream
+// best, but with an N tile of nt columns they need 4 * nt TMEM columns per accumulator set: above 256 the
+// accumulators cannot be double-buffered and the epilogue of every tile is exposed. Measured on B200 (8 x 128^3
+// step shapes, profiles/r01w_td2.txt): two-plane tiles (double-buffered) win whenever the layer has ONE N tile --
+// 128 -> 128 @32^3 forward 0.194 -> 0.153 ms, 128+128 -> 128 0.352 -> 0.290, the 32 -> 96-column dgrad of
+// upcat_1.conv_0 2.50 -> 2.42 -- and lose with several N tiles, where every tile re-streams the weights of its N
+// tile (256 -> 256 @16^3 0.103 -> 0.124), except at the 8^3 level, where they double the number of tiles of an
+// underfilled grid (512 -> 512 @8^3 0.177 -> 0.120).
+static int planes_per_tile(int depth, int nt_max, int n_ntiles) {
+  static const bool td2 = !(getenv("UB_TD2") && atoi(getenv("UB_TD2")) == 0);
+  int td = depth < 4 ? depth : 4;
+  const int cols = (nt_max + 31) / 32 * 32;
+  if (td2 && td == 4 && 2 * 4 * cols > 512 && 2 * 2 * cols <= 512 && (n_ntiles == 1 || depth <= 8)) td = 2;
+  return td;
+}
+
 extern "C" int ub_conv_num_tiles(const ub_conv_desc* d) {
   if (check_desc(d)) return -1;
   int od, oh, ow;
@@ -405,6 +421,8 @@ extern "C" int ub_conv_num_tiles(const ub_conv_desc* d) {
   }
   int td = 4;
   int Dt = od, Ht = oh, Wt = ow;
+  if (d->kind == UB_CONV_K3S1P1 || d->kind == UB_CONV_K1)
+    td = planes_per_tile(d->d, d->cop < 128 ? d->cop : 128, cdiv(d->cop, 128));
   if (d->kind == UB_CONV_K4S2P1) td = 1;
   if (d->kind == UB_DECONV_K2S2) { Dt = d->d; Ht = d->h; Wt = d->w; }
   if (td > Dt) td = Dt;
@@ -453,7 +471,7 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
 
   if (d->kind == UB_CONV_K3S1P1 || d->kind == UB_CONV_K1) {
     const int k = d->kind == UB_CONV_K3S1P1 ? 3 : 1;
-    P.td = d->d < 4 ? d->d : 4;
+    P.td = planes_per_tile(d->d, nt_max, P.n_ntiles);
     P.Do = od; P.Ho = oh; P.Wo = ow;
     P.n_atiles = 1; P.bw = 8 + k - 1; P.bh = 16 + k - 1; P.n_in_planes = P.td + k - 1; P.in_stride = 1;
     P.atile_off[0][0] = P.atile_off[0][1] = P.atile_off[0][2] = -(k / 2);
@@ -613,7 +631,7 @@ extern "C" int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const 
 
   if (d->kind == UB_CONV_K3S1P1 || d->kind == UB_CONV_K1) {
     const int k = d->kind == UB_CONV_K3S1P1 ? 3 : 1;
-    P.td = d->d < 4 ? d->d : 4;
+    P.td = planes_per_tile(d->d, nt_max, P.n_ntiles);
     P.Do = d->d; P.Ho = d->h; P.Wo = d->w;
     P.n_atiles = 1; P.bw = 8 + k - 1; P.bh = 16 + k - 1; P.n_in_planes = P.td + k - 1; P.in_stride = 1;
     P.atile_off[0][0] = P.atile_off[0][1] = P.atile_off[0][2] = -(k / 2);
