@@ -658,23 +658,25 @@ norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bflo
 }
 
 // Reduce block partials -> c1, c2 per (n,c) and accumulate dgamma / dbeta (/ bias grad in eval-BN).
-// mode as in stats_finalize. grid = (Cp/32); block = (32 lanes over the partial records, 32 channels): one WARP per
-// channel, so the per-sample sums are a shuffle tree (fixed order: deterministic) and the sample loop needs no block
-// barrier -- this kernel sits on the critical path of every norm backward (~36 launches per step).
+// mode as in stats_finalize. grid = (Cp/32), block = (32 channels, 32 lanes over the partial records): coalesced
+// 128-byte rows, four loads in flight per thread, ONE block barrier per sample (the lane sums of sample n go to
+// shared-memory buffer n & 1, which row 0 folds while the other rows already load sample n + 1). Fixed summation
+// order: deterministic. This kernel sits on the critical path of every norm backward (~31 launches per step).
 __global__ void __launch_bounds__(1024)
 norm_bwd_finalize_kernel(const float* __restrict__ part, int blocks_per_sample, int Nb, int Cp, int C,
                          double count_per_sample, int mode, const float* __restrict__ xscale, float* __restrict__ c1,
                          float* __restrict__ c2, float* __restrict__ dgamma, float* __restrict__ dbeta,
                          float* __restrict__ dbias) {
-  const int lane = threadIdx.x;
-  const int c = blockIdx.x * 32 + threadIdx.y;
+  __shared__ double sh1[2][32][33], sh2[2][32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int lane = threadIdx.y;
   double tot1 = 0.0, tot2 = 0.0;
   for (int n = 0; n < Nb; ++n) {
     const float* p0 = part + ((size_t)n * blocks_per_sample * 2) * Cp + c;
-    float f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};
     double s1 = 0.0, s2 = 0.0;
     int b = lane;
-    for (; b + 96 < blocks_per_sample; b += 128) {          // four independent loads in flight per thread
+    for (; b + 96 < blocks_per_sample; b += 128) {
+      float f1[4], f2[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         f1[u] = p0[(size_t)(b + 32 * u) * 2 * Cp];
@@ -687,26 +689,28 @@ norm_bwd_finalize_kernel(const float* __restrict__ part, int blocks_per_sample, 
       s1 += (double)p0[(size_t)b * 2 * Cp];
       s2 += (double)p0[(size_t)b * 2 * Cp + Cp];
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    tot1 += s1;
-    tot2 += s2;
-    if (mode == 0 && lane == 0) {
-      c1[(size_t)n * Cp + c] = (float)(s1 / count_per_sample);
-      c2[(size_t)n * Cp + c] = (float)(s2 / count_per_sample);
+    sh1[n & 1][lane][threadIdx.x] = s1;
+    sh2[n & 1][lane][threadIdx.x] = s2;
+    __syncthreads();
+    if (lane == 0) {
+      for (int k = 1; k < 32; ++k) { s1 += sh1[n & 1][k][threadIdx.x]; s2 += sh2[n & 1][k][threadIdx.x]; }
+      tot1 += s1;
+      tot2 += s2;
+      if (mode == 0) {
+        c1[(size_t)n * Cp + c] = (float)(s1 / count_per_sample);
+        c2[(size_t)n * Cp + c] = (float)(s2 / count_per_sample);
+      }
     }
   }
+  if (lane != 0) return;
   if (mode != 0) {
     const double cnt = count_per_sample * Nb;
-    for (int n = lane; n < Nb; n += 32) {
+    for (int n = 0; n < Nb; ++n) {
       c1[(size_t)n * Cp + c] = mode == 1 ? (float)(tot1 / cnt) : 0.f;
       c2[(size_t)n * Cp + c] = mode == 1 ? (float)(tot2 / cnt) : 0.f;
     }
   }
-  if (lane == 0 && c < C) {
+  if (c < C) {
     if (dgamma) dgamma[c] = (float)tot2;
     if (dbeta) dbeta[c] = (float)tot1;
     // conv bias feeding a batch-statistics norm has an analytically zero gradient; with running
