@@ -12,7 +12,8 @@
 #include <cstring>
 #include <vector>
 #include <cmath>
-#include "../unet-bssfp_b200/csrc/sm100_ptx.cuh"
+#include <cuda_fp16.h>
+#include "../unet_bssfp_b200/csrc/sm100_ptx.cuh"
 
 using namespace ub;
 
@@ -357,6 +358,105 @@ static int case_tma_stride(const char* name) {
   return bad ? 1 : 0;
 }
 
+// ----- mixed operand formats (kind::f16 with a_format != b_format): A fp16 x B bf16 and the other combinations.
+//       fmt: 0 = fp16, 1 = bf16 (instruction-descriptor encoding). Values are multiples of 0.25 in [-3, 3]:
+//       exact in both formats, and a wrong interpretation of the bits changes them by orders of magnitude.
+static std::vector<uint16_t> rand_16(size_t n, int fmt) {
+  std::vector<uint16_t> v(n);
+  for (size_t i = 0; i < n; ++i) {
+    const float f = 0.25f * rnd_int(-12, 12);
+    if (fmt == 0) { __half h = __float2half(f); v[i] = *reinterpret_cast<uint16_t*>(&h); }
+    else { __nv_bfloat16 b = __float2bfloat16(f); v[i] = *reinterpret_cast<uint16_t*>(&b); }
+  }
+  return v;
+}
+static float dec16(uint16_t x, int fmt) {
+  if (fmt == 0) { __half h = *reinterpret_cast<__half*>(&x); return __half2float(h); }
+  __nv_bfloat16 b = *reinterpret_cast<__nv_bfloat16*>(&x); return __bfloat162float(b);
+}
+static uint32_t idesc_fmt(uint32_t M, uint32_t N, int afmt, int bfmt, uint32_t a_mn, uint32_t b_mn) {
+  uint32_t d = make_idesc_bf16(M, N, a_mn, b_mn);
+  d &= ~((7u << 7) | (7u << 10));
+  d |= (uint32_t)afmt << 7;
+  d |= (uint32_t)bfmt << 10;
+  return d;
+}
+static int case_kmajor_mixed(const char* name, int kc, int N, int K, int afmt, int bfmt) {
+  const int sw = kc * 2;
+  auto A = rand_16((size_t)128 * K, afmt), B = rand_16((size_t)N * K, bfmt);
+  auto dA = to_dev(A); auto dB = to_dev(B);
+  Case cs; cs.ncols = (N + 31) / 32 * 32;
+  uint64_t dimsA[2] = {(uint64_t)K, 128}, strA[1] = {(uint64_t)K};
+  uint64_t dimsB[2] = {(uint64_t)K, (uint64_t)N}, strB[1] = {(uint64_t)K};
+  uint32_t boxA[2] = {(uint32_t)kc, 128}, boxB[2] = {(uint32_t)kc, (uint32_t)N};
+  cs.maps.m[0] = make_map(dA, 2, dimsA, strA, boxA, nullptr, sw);
+  cs.maps.m[1] = make_map(dB, 2, dimsB, strB, boxB, nullptr, sw);
+  const int nchunk = K / kc;
+  const uint32_t a_bytes = 128 * sw, b_bytes = N * sw;
+  const uint32_t b_base = ((nchunk * a_bytes) + 1023) & ~1023u;
+  for (int c = 0; c < nchunk; ++c) {
+    cs.tmas.push_back({0, 2, c * a_bytes, a_bytes, {c * kc, 0, 0, 0, 0}});
+    cs.tmas.push_back({1, 2, b_base + c * b_bytes, b_bytes, {c * kc, 0, 0, 0, 0}});
+  }
+  const uint32_t idesc = idesc_fmt(128, N, afmt, bfmt, 0, 0);
+  int first = 1;
+  for (int c = 0; c < nchunk; ++c)
+    for (int k = 0; k < kc / 16; ++k) {
+      MmaOp o{};
+      o.adesc = make_smem_desc(c * a_bytes + k * 32, 16, 8 * sw, swz_desc(sw));
+      o.bdesc = make_smem_desc(b_base + c * b_bytes + k * 32, 16, 8 * sw, swz_desc(sw));
+      o.idesc = idesc; o.accumulate = first ? 0 : 1; first = 0; o.tmem_col = 0;
+      cs.mmas.push_back(o);
+    }
+  std::vector<float> ref((size_t)128 * N, 0.f), out;
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < N; ++n) {
+      float s = 0;
+      for (int k = 0; k < K; ++k) s += dec16(A[(size_t)m * K + k], afmt) * dec16(B[(size_t)n * K + k], bfmt);
+      ref[(size_t)m * N + n] = s;
+    }
+  run_case(name, cs, out);
+  int r = report(name, out, ref, 128, N, cs.ncols);
+  cudaFree(dA); cudaFree(dB);
+  return r;
+}
+// MN-major mixed (the wgrad operand arrangement: A = activations fp16, B = gradients bf16), no halo: plain
+// D[c][n] = sum_v X[v][c] * dY[v][n] over 128 voxels; rows 0..63 of D (atom 0) are compared
+static int case_mnmajor_mixed(const char* name, int afmt, int bfmt) {
+  const int C = 64, N = 32, V = 128;
+  const int swA = C * 2, swB = N * 2;
+  auto X = rand_16((size_t)V * C, afmt), dY = rand_16((size_t)V * N, bfmt);
+  auto dX = to_dev(X); auto dD = to_dev(dY);
+  Case cs; cs.ncols = 32;
+  uint64_t dimsX[2] = {(uint64_t)C, (uint64_t)V}, strX[1] = {(uint64_t)C};
+  uint64_t dimsY[2] = {(uint64_t)N, (uint64_t)V}, strY[1] = {(uint64_t)N};
+  uint32_t boxX[2] = {(uint32_t)C, (uint32_t)V}, boxY[2] = {(uint32_t)N, (uint32_t)V};
+  cs.maps.m[0] = make_map(dX, 2, dimsX, strX, boxX, nullptr, swA);
+  cs.maps.m[1] = make_map(dD, 2, dimsY, strY, boxY, nullptr, swB);
+  const uint32_t a_bytes = V * swA, b_base = (a_bytes + 1023) & ~1023u;
+  cs.tmas.push_back({0, 2, 0, a_bytes, {0, 0, 0, 0, 0}});
+  cs.tmas.push_back({1, 2, b_base, (uint32_t)(V * swB), {0, 0, 0, 0, 0}});
+  const uint32_t idesc = idesc_fmt(128, N, afmt, bfmt, 1, 1);   // atom 0 = the 64 channels; atom 1 (one voxel row later) is not compared
+  for (int ks = 0; ks < V / 16; ++ks) {
+    MmaOp o{};
+    o.adesc = make_smem_desc(ks * 16 * swA, /*lbo=*/swA, /*sbo=*/8 * swA, swz_desc(swA));
+    o.bdesc = make_smem_desc(b_base + ks * 16 * swB, /*lbo=*/swB, /*sbo=*/8 * swB, swz_desc(swB));
+    o.idesc = idesc; o.accumulate = ks ? 1 : 0;
+    cs.mmas.push_back(o);
+  }
+  std::vector<float> ref((size_t)64 * N, 0.f), out;
+  for (int c = 0; c < C; ++c)
+    for (int n = 0; n < N; ++n) {
+      float s = 0;
+      for (int v = 0; v < V; ++v) s += dec16(X[(size_t)v * C + c], afmt) * dec16(dY[(size_t)v * N + n], bfmt);
+      ref[(size_t)c * N + n] = s;
+    }
+  run_case(name, cs, out);
+  int r = report(name, out, ref, 64, N, cs.ncols);
+  cudaFree(dX); cudaFree(dD);
+  return r;
+}
+
 int main(int argc, char** argv) {
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
@@ -378,6 +478,11 @@ int main(int argc, char** argv) {
   RUN("W2", case_wgrad("W2 wgrad sw64  C32 N32 kh0 (4 atoms)", 32, 32, 0, 8, 8));
   RUN("W3", case_wgrad("W3 wgrad sw128 C64 N64 kh2 edge", 64, 64, 2, 0, 0));
   RUN("T1", case_tma_stride("T1 tma elementStrides=2"));
+  RUN("M0", case_kmajor_mixed("M0 kmajor A bf16 x B bf16 (control)", 32, 96, 64, 1, 1));
+  RUN("M1", case_kmajor_mixed("M1 kmajor A fp16 x B bf16", 32, 96, 64, 0, 1));
+  RUN("M2", case_kmajor_mixed("M2 kmajor A bf16 x B fp16", 32, 96, 64, 1, 0));
+  RUN("M3", case_kmajor_mixed("M3 kmajor A fp16 x B fp16", 32, 96, 64, 0, 0));
+  RUN("M4", case_mnmajor_mixed("M4 mn-major A fp16 x B bf16", 0, 1));
   printf("probe done: %d failing case(s)\n", fails);
   return fails ? 1 : 0;
 }

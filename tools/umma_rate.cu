@@ -9,7 +9,7 @@
 #include <cstdint>
 #include <cuda.h>
 #include <cuda_runtime.h>
-#include "../unet-bssfp_b200/csrc/sm100_ptx.cuh"
+#include "../unet_bssfp_b200/csrc/sm100_ptx.cuh"
 
 using namespace ub;
 
