@@ -9,7 +9,10 @@
  *   - every entry returns 0 on success, <0 on error; ub_last_error() gives the thread-local message;
  *   - the caller owns ALL device memory (activations, workspaces, outputs);
  *   - all work is enqueued on the caller's cudaStream_t (passed as void*); no internal sync;
- *   - activations are NDHWC bf16 with the channel count padded to a multiple of 32 ("cp");
+ *   - activations and gradients are NDHWC bf16 with the channel count padded to a multiple of 32 ("cp");
+ *     the RAW output y of a conv that feeds a normalisation (ub_conv_fwd with stats_partial != NULL) is
+ *     NDHWC IEEE fp16 -- it is never a tensor-core operand, only the input of the norm/activation kernels
+ *     and of the deferred-activation operand transforms -- so activations are rounded to bf16 once;
  *     tensors at the module boundary are NCDHW fp32 as in the reference;
  *   - there is no CPU fallback and no cuDNN dispatch: an unsupported shape is an error.
  */
@@ -51,13 +54,42 @@ typedef struct {
 long long ub_packed_weight_elems(const ub_conv_desc* d, int dir);
 /* torch-layout fp32 weights ([co][ci][k..] or [ci][co][2][2][2] for the transposed conv) -> packed bf16 */
 int ub_pack_conv_weights(const ub_conv_desc* d, int dir, const float* w, void* packed, void* stream);
+/* the same for `count` weights in as few launches as the pointer table allows (`items` is a HOST array; only kind
+ * and the channel fields of desc are used). The modules re-pack every weight of a network at the start of each
+ * forward / backward pass from the live fp32 Parameters (~25 us for the generator), so no cached operand copy can
+ * go stale behind an out-of-band write to parameter memory. */
+typedef struct {
+  ub_conv_desc desc;
+  int dir;
+  const float* w;
+  void* packed;
+} ub_weight_pack_item;
+int ub_pack_conv_weights_multi(const ub_weight_pack_item* items, int count, void* stream);
 
 /* number of output tiles of the forward launch == rows of the statistics partial buffer */
 int ub_conv_num_tiles(const ub_conv_desc* d);
-/* y = conv(cat[src0, src1]) + bias; optional LeakyReLU; optional per-tile sum / sumsq partials
- * stats_partial: [ub_conv_num_tiles][2][cop] floats or NULL */
+/* A DEFERRED ACTIVATION: the activations a = LeakyReLU_slope(Dropout_p(y * scale + shift)) of a
+ * conv -> norm -> dropout -> LeakyReLU block (monai Convolution -> ADN("NDA"), ref:model.py:22-28), given by the
+ * block's raw conv output y (NDHWC fp16, 32 padded channels) and these constants instead of a materialised
+ * tensor. Consumers that accept one apply it on their operand path (in shared memory between the TMA arrival
+ * and the tcgen05.mma for the convolutions, in registers for the memory-bound kernels), so the tensor `a` is
+ * never written to or read from HBM. All consumers evaluate the same function bit for bit. */
+typedef struct {
+  const float* scale;      /* [n][32] gamma * rstd   (ub_norm_finalize) */
+  const float* shift;      /* [n][32] */
+  float slope, drop_p;
+  uint32_t drop_seed;
+} ub_deferred_act;
+/* 1 when source 0 of this convolution may be a deferred activation in ub_conv_fwd AND ub_conv_wgrad (3x3x3 convs
+ * with 32 output channels and a 32-channel source 0: the full-resolution layers), else 0 */
+int ub_conv_deferred_src0_ok(const ub_conv_desc* d);
+/* out = conv(cat[src0, src1]) + bias; optional LeakyReLU; optional per-tile sum / sumsq partials
+ * stats_partial: [ub_conv_num_tiles][2][cop] floats or NULL. With stats_partial the output is the raw input y of
+ * a normalisation and is written as fp16 (statistics from the fp32 accumulators); otherwise bf16.
+ * src0_act != NULL: src0 points at the producer's y (fp16) and is a deferred activation. */
 int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* src1, const void* w_packed,
-                const float* bias, int act, float slope, void* out, float* stats_partial, void* stream);
+                const float* bias, int act, float slope, void* out, float* stats_partial,
+                const ub_deferred_act* src0_act, void* stream);
 /* d src = conv_transpose(dy); dsrc1 may be NULL when the op has one source */
 int ub_conv_dgrad(const ub_conv_desc* d, const void* dy, const void* w_packed_dgrad, void* dsrc0,
                   void* dsrc1, void* stream);
@@ -69,7 +101,7 @@ int ub_conv_dgrad(const ub_conv_desc* d, const void* dy, const void* w_packed_dg
  * reduction pass over dA and y is skipped. Available where ub_conv_dgrad_fuse_records() > 0 (3x3x3
  * convs with one 32-channel source, i.e. the full-resolution layers). */
 typedef struct {
-  const void* y;           /* producer's raw conv output, NDHWC bf16, 32 channels */
+  const void* y;           /* producer's raw conv output, NDHWC fp16, 32 channels */
   const float* scale;      /* [n][32] gamma * rstd          (ub_norm_finalize) */
   const float* shift;      /* [n][32] */
   const float* mean;       /* [n][32] */
@@ -83,8 +115,9 @@ int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const void* w_pac
                         void* dsrc1, const ub_norm_bwd_fuse* fuse, void* stream);
 /* dw (fp32, torch layout) = sum_voxels src (x) dy; workspace holds the split-K partials */
 long long ub_conv_wgrad_workspace_bytes(const ub_conv_desc* d);
+/* src0_act != NULL: src0 points at the producer's y (fp16) and is a deferred activation (ub_conv_deferred_src0_ok) */
 int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void* src1, const void* dy,
-                  void* workspace, float* dw, void* stream);
+                  void* workspace, float* dw, const ub_deferred_act* src0_act, void* stream);
 
 /* ---- layout at the module boundary --------------------------------------------------------- */
 /* cat[a (ca ch), b (cb ch)] NCDHW fp32 -> NDHWC bf16 with cp channels (b may be NULL); replaces the
@@ -119,12 +152,14 @@ int ub_unpack_ncdhw(const void* src, int cp, int c_begin, int c, int n, long lon
  * padded 32-channel bf16 tensor + unpack. w [co][ci] / bias [co] are the fp32 parameters (device pointers).
  * workspace: ub_conv1x1_workspace_bytes() bytes. */
 long long ub_conv1x1_workspace_bytes(void);
+/* u_act != NULL (both calls): u points at the last block's y (fp16) and is a deferred activation */
 int ub_conv1x1_to_ncdhw(const void* u, int cp, const float* w, int ci, const float* bias, int co, int n,
-                        long long voxels, void* workspace, float* out, void* stream);
+                        long long voxels, void* workspace, float* out, const ub_deferred_act* u_act, void* stream);
 /* its backward in ONE pass over dout (NCDHW fp32) and u: du = W^T dout (NDHWC bf16, may be NULL),
  * dw [co][ci] = sum dout (x) u and db [co] = sum dout (fp32, may be NULL; u may be NULL when both are) */
 int ub_conv1x1_from_ncdhw_bwd(const float* dout, int co, const void* u, int cp, const float* w, int ci, int n,
-                              long long voxels, void* workspace, void* du, float* dw, float* db, void* stream);
+                              long long voxels, void* workspace, void* du, float* dw, float* db,
+                              const ub_deferred_act* u_act, void* stream);
 
 /* ---- normalisation + dropout + activation --------------------------------------------------- */
 enum { UB_NORM_INSTANCE = 0, UB_NORM_BATCH_TRAIN = 1, UB_NORM_BATCH_EVAL = 2, UB_NORM_NONE = 3 };
@@ -142,8 +177,9 @@ int ub_norm_finalize(const float* stats_partial, int tiles_per_sample, int n, in
  * reference's order (ref:src/model.py:184-186: fake branch, then real branch). */
 int ub_bn_running_update(const float* mean, const float* rstd, int c, double count, float eps, float momentum,
                          float* running_mean, float* running_var, void* stream);
-/* a = LeakyReLU_slope(Dropout_p(y * scale + shift)); pooled (may be NULL) = MaxPool3d(2)(a).
- * scale == NULL: no normalisation. ref: monai ADN "NDA" + Down.max_pooling */
+/* a = LeakyReLU_slope(Dropout_p(y * scale + shift)); pooled (may be NULL) = MaxPool3d(2)(a). y is fp16, a and
+ * pooled bf16. scale == NULL: no normalisation. a may be NULL when pooled is given (the activations stay
+ * deferred, only the pooled tensor is materialised). ref: monai ADN "NDA" + Down.max_pooling */
 int ub_norm_act_fwd(const void* y, const float* scale, const float* shift, float slope, float drop_p,
                     uint32_t drop_seed, int n, int d, int h, int w, int cp, void* a, void* pooled,
                     void* stream);
@@ -159,9 +195,10 @@ int ub_norm_act_bwd(const void* dA, const void* a, const void* y, int mode, cons
                     float* dbeta, float* dbias, const float* ext_partial, int ext_records_per_sample, void* stream);
 /* ext_partial != NULL: per-sample partial records [n * ext_records_per_sample][2][cp] produced by
  * ub_conv_dgrad_fused replace the reduction pass. */
-/* MaxPool3d(2) backward; accumulate != 0 adds onto the gradient already in dA (skip path) */
+/* MaxPool3d(2) backward; accumulate != 0 adds onto the gradient already in dA (skip path).
+ * a_act != NULL: `a` points at the block's y (fp16) and is a deferred activation */
 int ub_maxpool_bwd(const void* a, const void* dP, void* dA, int accumulate, int n, int d, int h, int w,
-                   int cp, void* stream);
+                   int cp, const ub_deferred_act* a_act, void* stream);
 /* out[c] = sum over rows of x[rows][cp] (bias gradients of convs without a following norm) */
 long long ub_colsum_workspace_bytes(int cp);
 int ub_colsum(const void* x, long long rows, int cp, int c, void* workspace, float* out, void* stream);

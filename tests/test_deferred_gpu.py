@@ -1,0 +1,188 @@
+"""Deferred activations: norm + dropout + LeakyReLU applied on the CONSUMER's operand path (VERDICT r1 item 1;
+reference semantics: monai Convolution -> ADN("NDA") instantiated at ref:src/model.py:22-28).
+
+A conv -> norm block keeps only its raw fp16 output y and per-(n, c) constants; the consumers -- the marching
+forward conv (shared-memory operand transform between TMA arrival and tcgen05.mma), the marching weight gradient,
+the pooling forward / backward passes and the fused 1x1x1 output head -- evaluate the activations themselves with
+ONE shared device function. So every consumer must give the SAME BITS as when it is fed the materialised tensor
+``ub_norm_act_fwd`` writes: that is what these tests assert, op by op and for the whole generator; the materialised
+path itself is checked against torch in test_pointwise_gpu.py / test_conv_gpu.py / test_model_gpu.py.
+"""
+import pytest
+import torch
+
+from tests.util import no_dropout, rel_l2, to_internal
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ops():
+    import unet_bssfp_b200 as ub
+    return ub.ops
+
+
+def _producer(n, d, h, w, c=32, seed=0, drop_p=0.0, slope=0.1):
+    """A producer block's saved state: y (fp16, c real channels of 32), scale / shift [n][32], and both forms of its
+    activations (deferred, materialised)."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    y = to_internal(torch.randn((n, c, d, h, w), device=DEV, generator=g) * 1.5 + 0.25, dtype=torch.float16)
+    scale = torch.zeros((n, 32), device=DEV)
+    shift = torch.zeros((n, 32), device=DEV)
+    scale[:, :c] = torch.rand((n, c), device=DEV, generator=g) + 0.5
+    shift[:, :c] = torch.randn((n, c), device=DEV, generator=g) * 0.3
+    seed_d = 4711 + seed
+    a, _ = ops.norm_act_fwd(y, scale, shift, slope, drop_p, seed_d)
+    return ops.DeferredAct(y, scale, shift, slope, drop_p, seed_d), a
+
+
+CONV_CASES = [
+    # c0, c1, co, (n, d, h, w)
+    (32, 0, 32, (2, 9, 32, 16)),      # one K chunk, single-CTA marching kernel, several d segments
+    (32, 0, 32, (1, 6, 20, 12)),      # ragged h / w tiles: halo rows outside the volume must stay zero AFTER activation
+    (24, 0, 32, (1, 5, 16, 8)),       # 24 real channels (the input head's output): padded channels stay inert
+    (32, 64, 32, (2, 7, 32, 32)),     # skip concat [deferred | plain], CTA-pair kernel (two w tiles per cluster)
+    (32, 64, 32, (1, 4, 16, 24)),     # skip concat, odd number of w tiles: single-CTA kernel with three chunks
+    (32, 32, 32, (1, 5, 16, 16)),     # two chunks
+]
+
+
+@pytest.mark.parametrize("drop_p", [0.0, 0.05])
+@pytest.mark.parametrize("c0,c1,co,shape", CONV_CASES)
+def test_conv_forward_on_deferred_source_is_bit_identical(c0, c1, co, shape, drop_p):
+    ops = _ops()
+    n, d, h, w = shape
+    spec = ops.ConvSpec(0, c0, co, c1)
+    assert ops.deferred_src0_ok(spec, n, d, h, w)
+    lazy, a = _producer(n, d, h, w, c=c0, seed=1, drop_p=drop_p)
+    g = torch.Generator(device=DEV).manual_seed(2)
+    s1 = to_internal(torch.randn((n, c1, d, h, w), device=DEV, generator=g)) if c1 else None
+    wt = torch.randn((co, c0 + c1, 3, 3, 3), device=DEV, generator=g) / ((c0 + c1) * 27) ** 0.5
+    b = torch.randn((co,), device=DEV, generator=g)
+    wpk = ops.pack_conv_weights(spec, wt, 0)
+    ref, ref_stats = ops.conv_fwd(spec, a, s1, wpk, b, want_stats=True)
+    got, got_stats = ops.conv_fwd(spec, lazy, s1, wpk, b, want_stats=True)
+    torch.cuda.synchronize()
+    assert got.dtype == torch.float16
+    assert torch.equal(got, ref)
+    assert torch.equal(got_stats, ref_stats)
+    # and without statistics (bf16 output)
+    ref2, _ = ops.conv_fwd(spec, a, s1, wpk, b)
+    got2, _ = ops.conv_fwd(spec, lazy, s1, wpk, b)
+    assert got2.dtype == torch.bfloat16 and torch.equal(got2, ref2)
+
+
+@pytest.mark.parametrize("drop_p", [0.0, 0.05])
+@pytest.mark.parametrize("c0,c1,co,shape", CONV_CASES)
+def test_conv_wgrad_on_deferred_source_is_bit_identical(c0, c1, co, shape, drop_p):
+    ops = _ops()
+    n, d, h, w = shape
+    spec = ops.ConvSpec(0, c0, co, c1)
+    lazy, a = _producer(n, d, h, w, c=c0, seed=3, drop_p=drop_p)
+    g = torch.Generator(device=DEV).manual_seed(4)
+    s1 = to_internal(torch.randn((n, c1, d, h, w), device=DEV, generator=g)) if c1 else None
+    dy = to_internal(torch.randn((n, co, d, h, w), device=DEV, generator=g))
+    shape_w = (co, c0 + c1, 3, 3, 3)
+    ref = ops.conv_wgrad(spec, a, s1, dy, shape_w)
+    got = ops.conv_wgrad(spec, lazy, s1, dy, shape_w)
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref)
+
+
+def test_deferred_source_is_refused_where_unsupported():
+    ops = _ops()
+    lazy, a = _producer(1, 4, 16, 8, seed=5)
+    spec = ops.ConvSpec(0, 32, 64)                      # 64 output channels: generic kernel, no operand transform
+    assert not ops.deferred_src0_ok(spec, 1, 4, 16, 8)
+    wpk = ops.pack_conv_weights(spec, torch.randn((64, 32, 3, 3, 3), device=DEV), 0)
+    with pytest.raises(RuntimeError, match="deferred"):
+        ops.conv_fwd(spec, lazy, None, wpk, None)
+    with pytest.raises(RuntimeError, match="deferred"):
+        ops.conv_wgrad(spec, lazy, None, to_internal(torch.randn((1, 64, 4, 16, 8), device=DEV)), (64, 32, 3, 3, 3))
+
+
+@pytest.mark.parametrize("drop_p", [0.0, 0.05])
+@pytest.mark.parametrize("shape", [(2, 4, 16, 8), (1, 6, 10, 12)])
+def test_pooling_passes_on_deferred_activations(shape, drop_p):
+    ops = _ops()
+    n, d, h, w = shape
+    lazy, a = _producer(n, d, h, w, seed=6, drop_p=drop_p)
+    a2, pooled = ops.norm_act_fwd(lazy.y, lazy.scale, lazy.shift, lazy.slope, drop_p, lazy.drop_seed, pool=True)
+    none, pooled_only = ops.norm_act_fwd(lazy.y, lazy.scale, lazy.shift, lazy.slope, drop_p, lazy.drop_seed, pool=True,
+                                         materialize=False)
+    assert none is None and torch.equal(a2, a) and torch.equal(pooled_only, pooled)
+    g = torch.Generator(device=DEV).manual_seed(7)
+    dP = to_internal(torch.randn((n, 32, d // 2, h // 2, w // 2), device=DEV, generator=g))
+    base = to_internal(torch.randn((n, 32, d, h, w), device=DEV, generator=g))
+    assert torch.equal(ops.maxpool_bwd(lazy, dP), ops.maxpool_bwd(a, dP))
+    assert torch.equal(ops.maxpool_bwd(lazy, dP, base.clone()), ops.maxpool_bwd(a, dP, base.clone()))
+
+
+@pytest.mark.parametrize("drop_p", [0.0, 0.05])
+def test_output_head_on_deferred_activations(drop_p):
+    ops = _ops()
+    n, d, h, w = 2, 4, 6, 10
+    lazy, a = _producer(n, d, h, w, seed=8, drop_p=drop_p)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    wt = torch.randn((6, 32, 1, 1, 1), device=DEV, generator=g) * 0.3
+    b = torch.randn((6,), device=DEV, generator=g)
+    assert torch.equal(ops.conv1x1_to_ncdhw(lazy, wt, b), ops.conv1x1_to_ncdhw(a, wt, b))
+    go = torch.randn((n, 6, d, h, w), device=DEV, generator=g)
+    du, dw, db = ops.conv1x1_from_ncdhw_bwd(go, lazy, wt)
+    du2, dw2, db2 = ops.conv1x1_from_ncdhw_bwd(go, a, wt)
+    assert torch.equal(du, du2) and torch.equal(dw, dw2) and torch.equal(db, db2)
+
+
+@pytest.mark.parametrize("mod,shape,train", [("bssfp", (1, 32, 32, 32), False), ("t1w", (2, 32, 48, 32), True),
+                                            ("bssfp", (1, 64, 64, 64), True)])
+def test_generator_with_and_without_deferral_is_bit_identical(mod, shape, train, monkeypatch):
+    """The whole generator, forward and backward (dropout active in train mode: the mask is a counter hash, identical
+    in both runs for the same seed): outputs, input gradient and every parameter gradient agree bit for bit between
+    the deferred path and the materialising path; the deferred run launches no norm_act_fwd for the 32-channel
+    full-resolution blocks and allocates none of their activation tensors."""
+    import unet_bssfp_b200 as ub
+    from unet_bssfp_b200 import modules
+    n, d, h, w = shape
+    cin = 24 if mod == "bssfp" else 6
+    torch.manual_seed(0)
+    g = ub.Generator(mod).to(DEV)
+    g.train(train)
+    torch.manual_seed(5)
+    x = torch.rand(n, cin, d, h, w, device=DEV)
+    dY = torch.randn(n, 6, d, h, w, device=DEV)
+
+    def run(defer):
+        monkeypatch.setattr(modules, "_DEFER", defer)
+        g._net()._defer_plans.clear()
+        plan = g._net().defer_plan(n, d, h, w, True)
+        for p in g.parameters():
+            p.grad = None
+        xr = x.clone().requires_grad_(True)
+        torch.manual_seed(77)                       # the dropout seeds come from the host RNG
+        out = g(xr)
+        out.backward(dY)
+        torch.cuda.synchronize()
+        return plan, out.detach(), xr.grad, {k: p.grad.clone() for k, p in g.named_parameters() if p.grad is not None}
+
+    plan1, out1, dx1, gr1 = run(True)
+    plan0, out0, dx0, gr0 = run(False)
+    assert plan0 == set()
+    assert plan1 == {"head", "conv_0.conv_0", "conv_0.conv_1", "upcat_1.conv_0", "upcat_1.conv_1"}
+    assert torch.equal(out1, out0)
+    assert torch.equal(dx1, dx0)
+    assert gr1.keys() == gr0.keys() and len(gr1) > 80
+    for k in gr1:
+        assert torch.equal(gr1[k], gr0[k]), k
+
+
+def test_inference_path_defers_too():
+    """``forward_packed`` (sliding-window inference) takes the same deferred path and agrees with ``forward``."""
+    import unet_bssfp_b200 as ub
+    torch.manual_seed(0)
+    g = ub.Generator("bssfp").to(DEV).eval()
+    x = torch.rand(2, 24, 32, 32, 32, device=DEV)
+    with torch.no_grad():
+        ref = g(x)
+        got = g.forward_packed(ub.ops.pack_ncdhw(x))
+    assert torch.equal(got, ref)

@@ -12,7 +12,7 @@ import pytest
 import torch
 
 from tests.golden.make_golden_ref import state_checksum, synth_batch
-from tests.util import rel_l2, rel_to_max, strict_fp32
+from tests.util import no_dropout, rel_l2, rel_to_max, strict_fp32
 
 pytestmark = pytest.mark.gpu
 REF = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_ref_v1.npz"))
@@ -30,11 +30,7 @@ def _pair(mod, seed=0):
     d.load_state_dict(od.state_dict())
     ub.set_precision(g, "fp32")
     ub.set_precision(d, "fp32")
-    for m in og.modules():
-        if isinstance(m, torch.nn.Dropout):
-            m.p = 0.0
-    g.blocks["unet"].dropout = 0.0
-    g._graph = None
+    no_dropout(og, g)
     return O, og, od, g, d
 
 
@@ -165,7 +161,7 @@ def test_fp32_mode_matches_reference_goldens():
     if abs(state_checksum(g) - float(REF["bssfp_g_checksum"])) > 1e-9 * float(REF["bssfp_g_checksum"]):
         pytest.skip("default torch init differs from the torch version that generated the goldens")
     g, d = ub.set_precision(g.to(DEV), "fp32"), ub.set_precision(d.to(DEV), "fp32")
-    g.blocks["unet"].dropout = 0.0
+    no_dropout(g)
     xb, yb = synth_batch(24)
     xb, yb = xb.to(DEV), yb.to(DEV)
     g.eval()
@@ -204,7 +200,7 @@ def test_fp32_mode_three_training_steps_follow_the_reference():
     if abs(state_checksum(g) - float(REF["bssfp_g_checksum"])) > 1e-9 * float(REF["bssfp_g_checksum"]):
         pytest.skip("default torch init differs from the torch version that generated the goldens")
     g, d = ub.set_precision(g.to(DEV), "fp32"), ub.set_precision(d.to(DEV), "fp32")
-    g.blocks["unet"].dropout = 0.0
+    no_dropout(g)
     g.train(); d.train()
     tr = GanTrainer(g, d)
     xb, yb = synth_batch(24)

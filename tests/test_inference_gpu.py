@@ -85,7 +85,8 @@ def test_config5_geometry_and_eval():
 
 def test_graph_replay_equals_eager_and_follows_weight_updates():
     """predict_volume with the CUDA-graph replay of the generator forward is bit-identical to eager launches,
-    pads a short last batch, and re-captures when the weights change."""
+    pads a short last batch, and FOLLOWS weight updates without a re-capture: the captured forward re-packs its
+    bf16 weight operands from the live parameter memory on every replay."""
     import unet_bssfp_b200 as ub
     torch.manual_seed(0)
     g = ub.Generator("t1w").to(DEV).eval()
@@ -98,11 +99,17 @@ def test_graph_replay_equals_eager_and_follows_weight_updates():
     assert torch.equal(eager, again) and len(g._infer_graphs) == 1
     first = next(iter(g._infer_graphs.values()))
     with torch.no_grad():
-        g.blocks["unet"].final_conv.bias.add_(0.5)                     # in-place update: the cached graph is stale
+        g.blocks["unet"].final_conv.bias.add_(0.5)                     # in-place update of a parameter the graph reads
     moved = ub.inference.predict_volume(g, vol, patch=32, batch=5, use_graph=True)
-    assert next(iter(g._infer_graphs.values())) is not first
+    assert next(iter(g._infer_graphs.values())) is first                # same captured graph ...
     assert torch.equal(moved, ub.inference.predict_volume(g, vol, patch=32, batch=5, use_graph=False))
-    assert (moved - eager - 0.5).abs().max().item() < 1e-5
+    assert (moved - eager - 0.5).abs().max().item() < 1e-5              # ... and it saw the new bias
+    with torch.no_grad():
+        g.blocks["unet"].conv_0.conv_1.conv.weight.data.mul_(0.5)       # a conv weight, written out of band
+    scaled = ub.inference.predict_volume(g, vol, patch=32, batch=5, use_graph=True)
+    assert next(iter(g._infer_graphs.values())) is first
+    assert torch.equal(scaled, ub.inference.predict_volume(g, vol, patch=32, batch=5, use_graph=False))
+    assert not torch.equal(scaled, moved)
     g.train()                                                          # train mode (dropout, batch statistics): eager path
     torch.manual_seed(1); a = ub.inference.predict_volume(g, vol, patch=32, batch=5)
     torch.manual_seed(1); b = ub.inference.predict_volume(g, vol, patch=32, batch=5, use_graph=False)

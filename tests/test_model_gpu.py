@@ -16,7 +16,7 @@ import pytest
 import torch
 
 from tests.golden.make_golden import state_checksum
-from tests.util import rel_l2, strict_fp32
+from tests.util import no_dropout, rel_l2, strict_fp32
 
 pytestmark = pytest.mark.gpu
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz"))
@@ -35,11 +35,7 @@ def _pair(mod, seed=0):
 
 
 def _no_dropout(og, g):
-    for m in og.modules():
-        if isinstance(m, torch.nn.Dropout):
-            m.p = 0.0
-    g.blocks["unet"].dropout = 0.0
-    g._graph = None
+    no_dropout(og, g)
 
 
 @pytest.mark.parametrize("mod,shape", [("bssfp", (1, 32, 32, 32)), ("t1w", (2, 32, 48, 32)), ("bssfp", (1, 64, 64, 64))])
@@ -251,15 +247,49 @@ def test_updated_weights_are_used_after_optimizer_steps(optimizer):
     assert rel_l2(after, before) > 10 * rel_l2(after, ref)                    # ... and they did change the output
     assert rel_l2(logit_after, logit_ref) < 3e-2
     assert rel_l2(logit_after, logit_before) > 5 * rel_l2(logit_after, logit_ref)
-    # writes behind torch's back need the explicit invalidation
-    import unet_bssfp_b200 as ub
     with torch.no_grad():
         w = g.blocks["unet"].final_conv.weight
-        w.data_ptr()
-        torch.cuda.current_stream().synchronize()
-        w.detach().view(-1)[:].mul_(0.0)                                      # in-place: bumps _version, no call needed
+        w.detach().view(-1)[:].mul_(0.0)
         assert g(x).abs().max().item() <= g.blocks["unet"].final_conv.bias.abs().max().item() + 1e-6
-    ub.invalidate_packed_weights(g)
+
+
+def test_out_of_band_weight_writes_are_seen():
+    """writes through ``.data`` change neither ``_version`` nor ``data_ptr`` nor any optimizer
+    stamp. The bf16 weight operands are re-packed from the live parameter memory on every pass, so such writes --
+    re-initialisation after a first forward, EMA swaps, a foreign kernel -- take effect, in forward AND backward,
+    exactly as with the reference, which reads its fp32 weights afresh in every call."""
+    O, og, od, g, d = _pair("bssfp", seed=5)
+    no_dropout(og, g)
+    torch.manual_seed(11)
+    x = torch.rand(1, 24, 32, 32, 32, device=DEV)
+    y = torch.rand(1, 6, 32, 32, 32, device=DEV)
+    g.eval(); og.eval(); d.eval(); od.eval()
+    with torch.no_grad():
+        g(x); d(x, y)                                   # first forward: operands packed once
+    # out-of-band writes: a 3x3x3 conv (marching kernel), a deep conv (generic kernel), a transposed conv, the stem
+    torch.manual_seed(12)
+    touched_g = [g.blocks["unet"].conv_0.conv_1.conv.weight, g.blocks["unet"].down_3.convs.conv_0.conv.weight,
+                 g.blocks["unet"].upcat_2.upsample.deconv.weight]
+    touched_d = [d.d1["bssfp"].conv.weight, d.d3.conv.weight]
+    for w in touched_g + touched_d:
+        v0, p0 = w._version, w.data_ptr()
+        w.data.normal_(0.0, 0.05)
+        assert w._version == v0 and w.data_ptr() == p0     # nothing a version-keyed cache could have noticed
+    og.load_state_dict(g.state_dict()); od.load_state_dict(d.state_dict())
+    with torch.no_grad():
+        e_g = rel_l2(g(x), og(x))
+        e_d = rel_l2(d(x, y), od(x, y))
+    assert e_g < 3e-2 and e_d < 3e-2, (e_g, e_d)
+    # backward (dgrad operand copies) after another out-of-band write
+    g.train(); og.train()
+    w = g.blocks["unet"].upcat_1.convs.conv_1.conv.weight
+    w.data.mul_(-1.5)
+    og.load_state_dict(g.state_dict())
+    xg = x.clone().requires_grad_(True)
+    xo = x.clone().requires_grad_(True)
+    g(xg).square().mean().backward()
+    og(xo).square().mean().backward()
+    assert rel_l2(xg.grad, xo.grad) < 0.1, rel_l2(xg.grad, xo.grad)
 
 
 def test_shape_errors():
@@ -281,7 +311,7 @@ def test_discriminator_phase_on_two_streams_equals_one_stream():
     _no_dropout(og, g)
     g2, d2 = ub.Generator("bssfp").to(DEV), ub.Discriminator("bssfp").to(DEV)
     g2.load_state_dict(g.state_dict()); d2.load_state_dict(d.state_dict())
-    g2.blocks["unet"].dropout = 0.0
+    no_dropout(g2)
     ta, tb = GanTrainer(g, d), GanTrainer(g2, d2)
     ta.overlap_real_branch, tb.overlap_real_branch = True, False
     torch.manual_seed(3)

@@ -67,7 +67,7 @@ def test_norm_act_forward_backward(mode, c, shape, pool):
     spec = ops.ConvSpec(_lib.UB_CONV_K1, c, c)
     eye = torch.eye(c, device="cuda").view(c, c, 1, 1, 1)
     yi, stats = ops.conv_fwd(spec, to_internal(y), None, ops.pack_conv_weights(spec, eye, 0), None, want_stats=True)
-    assert torch.equal(from_internal(yi, c), y)
+    assert yi.dtype == torch.float16 and (from_internal(yi, c) - y).abs().max().item() < 1e-6   # y is stored as fp16
     imode = {"instance": _lib.UB_NORM_INSTANCE, "batch_train": _lib.UB_NORM_BATCH_TRAIN, "batch_eval": _lib.UB_NORM_BATCH_EVAL}[mode]
     rm2, rv2 = rm.clone(), rv.clone()
     scale, shift, mean, rstd = ops.norm_finalize(stats, n, d * h * w, cp, c, gamma, beta, 1e-5, imode, 0.1, rm2, rv2)
@@ -126,7 +126,7 @@ def test_dropout_statistics_and_backward_mask():
     ops = _ops()
     from unet_bssfp_b200 import _lib
     n, c, d, h, w = 2, 32, 16, 16, 16
-    y = to_internal(torch.ones((n, c, d, h, w), device="cuda"))
+    y = to_internal(torch.ones((n, c, d, h, w), device="cuda"), dtype=torch.float16)
     p = 0.05
     a, _ = ops.norm_act_fwd(y, None, None, 0.1, drop_p=p, drop_seed=1234)
     af = a.float()

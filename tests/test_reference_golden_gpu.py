@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from tests.golden.make_golden_ref import state_checksum, synth_batch
-from tests.util import rel_l2
+from tests.util import no_dropout, rel_l2
 
 pytestmark = pytest.mark.gpu
 REF = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_ref_v1.npz"))
@@ -25,7 +25,7 @@ def _fresh(mod):
     if abs(state_checksum(g) - float(REF[f"{mod}_g_checksum"])) > 1e-9 * float(REF[f"{mod}_g_checksum"]):
         pytest.skip("default torch init differs from the torch version that generated the goldens")
     assert abs(state_checksum(d) - float(REF[f"{mod}_d_checksum"])) <= 1e-9 * float(REF[f"{mod}_d_checksum"])
-    g.blocks["unet"].dropout = 0.0
+    no_dropout(g)
     return g.to(DEV), d.to(DEV)
 
 

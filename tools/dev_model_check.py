@@ -42,8 +42,9 @@ print(f"G eval fwd: rel-L2 vs fp32 {rl2(po, ro):.3e}  vs fp64 {rl2(po, ro64):.3e
 # ---- G train-mode (dropout 0) forward + backward
 for m in og.modules():
     if isinstance(m, torch.nn.Dropout): m.p = 0.0
-g.blocks["unet"].dropout = 0.0
-g._graph = None
+for m in g.modules():
+    if isinstance(m, torch.nn.Dropout):
+        m.p = 0.0
 og.train(); g.train()
 dY = torch.randn_like(ro)
 ro = og(x); ro.backward(dY)

@@ -23,6 +23,12 @@ class NormBwdFuse(C.Structure):
                 ("partial", C.c_void_p)]
 
 
+class DeferredAct(C.Structure):
+    """Mirror of ``ub_deferred_act`` (include/ub_api.h)."""
+    _fields_ = [("scale", C.c_void_p), ("shift", C.c_void_p), ("slope", C.c_float), ("drop_p", C.c_float),
+                ("drop_seed", C.c_uint32)]
+
+
 class AdamWTensor(C.Structure):
     """Mirror of ``ub_adamw_tensor`` (include/ub_api.h)."""
     _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("numel", C.c_longlong)]
@@ -38,6 +44,11 @@ class ConvDesc(C.Structure):
     _fields_ = [(k, C.c_int) for k in ("kind", "n", "d", "h", "w", "c0", "c0p", "c1", "c1p", "co", "cop")]
 
 
+class WeightPackItem(C.Structure):
+    """Mirror of ``ub_weight_pack_item`` (include/ub_api.h)."""
+    _fields_ = [("desc", ConvDesc), ("dir", C.c_int), ("w", C.c_void_p), ("packed", C.c_void_p)]
+
+
 _P = C.c_void_p
 _F = C.c_float
 _I = C.c_int
@@ -45,6 +56,7 @@ _LL = C.c_longlong
 _U32 = C.c_uint32
 _D = C.c_double
 _DP = C.POINTER(ConvDesc)
+_AP = C.POINTER(DeferredAct)
 
 # name -> (restype, argtypes); every symbol of include/ub_api.h
 SIGNATURES = {
@@ -53,13 +65,15 @@ SIGNATURES = {
     "ub_launch_count": (_LL, []),
     "ub_packed_weight_elems": (_LL, [_DP, _I]),
     "ub_pack_conv_weights": (_I, [_DP, _I, _P, _P, _P]),
+    "ub_pack_conv_weights_multi": (_I, [C.POINTER(WeightPackItem), _I, _P]),
     "ub_conv_num_tiles": (_I, [_DP]),
-    "ub_conv_fwd": (_I, [_DP, _P, _P, _P, _P, _I, _F, _P, _P, _P]),
+    "ub_conv_deferred_src0_ok": (_I, [_DP]),
+    "ub_conv_fwd": (_I, [_DP, _P, _P, _P, _P, _I, _F, _P, _P, _AP, _P]),
     "ub_conv_dgrad": (_I, [_DP, _P, _P, _P, _P, _P]),
     "ub_conv_dgrad_fuse_records": (_I, [_DP]),
     "ub_conv_dgrad_fused": (_I, [_DP, _P, _P, _P, _P, C.POINTER(NormBwdFuse), _P]),
     "ub_conv_wgrad_workspace_bytes": (_LL, [_DP]),
-    "ub_conv_wgrad": (_I, [_DP, _P, _P, _P, _P, _P, _P]),
+    "ub_conv_wgrad": (_I, [_DP, _P, _P, _P, _P, _P, _AP, _P]),
     "ub_pack_ncdhw": (_I, [_P, _I, _P, _I, _I, _LL, _I, _P, _P]),
     "ub_pack_ncdhw_s2d": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "ub_pack_patches": (_I, [_P, _I, _I, C.POINTER(C.c_longlong), _I, _I, _I, _LL, _LL, _LL, _I, _P, _P]),
@@ -67,15 +81,15 @@ SIGNATURES = {
     "ub_paste_patch": (_I, [_P, _I, _I, _I, _I, _P, _LL, _LL, _LL, _LL, _P]),
     "ub_unpack_ncdhw": (_I, [_P, _I, _I, _I, _I, _LL, _P, _P]),
     "ub_conv1x1_workspace_bytes": (_LL, []),
-    "ub_conv1x1_to_ncdhw": (_I, [_P, _I, _P, _I, _P, _I, _I, _LL, _P, _P, _P]),
-    "ub_conv1x1_from_ncdhw_bwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _LL, _P, _P, _P, _P, _P]),
+    "ub_conv1x1_to_ncdhw": (_I, [_P, _I, _P, _I, _P, _I, _I, _LL, _P, _P, _AP, _P]),
+    "ub_conv1x1_from_ncdhw_bwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _LL, _P, _P, _P, _P, _AP, _P]),
     "ub_norm_finalize": (_I, [_P, _I, _I, _I, _I, _D, _P, _P, _F, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "ub_bn_running_update": (_I, [_P, _P, _I, _D, _F, _F, _P, _P, _P]),
     "ub_norm_act_fwd": (_I, [_P, _P, _P, _F, _F, _U32, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ub_norm_act_bwd_workspace_bytes": (_LL, [_I, _I]),
     "ub_norm_act_bwd": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _F, _F, _U32, _I, _LL, _I, _I, _P, _P, _P, _P, _P, _P, _I,
                              _P]),
-    "ub_maxpool_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "ub_maxpool_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _AP, _P]),
     "ub_colsum_workspace_bytes": (_LL, [_I]),
     "ub_colsum": (_I, [_P, _LL, _I, _I, _P, _P, _P]),
     "ub_l1_workspace_bytes": (_LL, []),

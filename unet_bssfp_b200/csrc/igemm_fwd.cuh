@@ -404,6 +404,7 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
           }
           tmem_ld_wait();
           uint32_t pk[16];
+          const bool acc_stats = do_stats && valid_hw;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 bv = b4[j];
@@ -413,8 +414,20 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
               x0 = x0 > 0.f ? x0 : x0 * slope; x1 = x1 > 0.f ? x1 : x1 * slope;
               x2 = x2 > 0.f ? x2 : x2 * slope; x3 = x3 > 0.f ? x3 : x3 * slope;
             }
-            pk[2 * j] = pack_bf16x2(x0, x1);
-            pk[2 * j + 1] = pack_bf16x2(x2, x3);
+            if (do_stats) {
+              // the raw output of a conv -> norm block: stored as fp16 (never an MMA operand), statistics from
+              // the fp32 accumulators
+              pk[2 * j] = pack_f16x2_sat(x0, x1);
+              pk[2 * j + 1] = pack_f16x2_sat(x2, x3);
+              if (acc_stats) {
+                st_a[4 * j] += x0; st_a[4 * j + 1] += x1; st_a[4 * j + 2] += x2; st_a[4 * j + 3] += x3;
+                st_b[4 * j] = fmaf(x0, x0, st_b[4 * j]); st_b[4 * j + 1] = fmaf(x1, x1, st_b[4 * j + 1]);
+                st_b[4 * j + 2] = fmaf(x2, x2, st_b[4 * j + 2]); st_b[4 * j + 3] = fmaf(x3, x3, st_b[4 * j + 3]);
+              }
+            } else {
+              pk[2 * j] = pack_bf16x2(x0, x1);
+              pk[2 * j + 1] = pack_bf16x2(x2, x3);
+            }
           }
           // ---- stores: the lane pair (2k, 2k+1) owns two neighbouring voxel rows (w, w+1). Exchange half
           // rows so that instruction j writes one whole 32-byte sector per lane pair:
@@ -441,17 +454,6 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
             if (valid_o) {
               __stcs(d_o + 0, odd ? make_uint4(pk[4], pk[5], pk[6], pk[7]) : make_uint4(rx[0], rx[1], rx[2], rx[3]));
               if (full32) __stcs(d_o + 2, odd ? make_uint4(pk[12], pk[13], pk[14], pk[15]) : make_uint4(rx[4], rx[5], rx[6], rx[7]));
-            }
-          }
-          if (do_stats && valid_hw) {
-            // statistics of the values as stored (bf16-rounded), so the consumer normalises exactly
-            // what it reads
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float lo = __uint_as_float(pk[j] << 16);
-              const float hi = __uint_as_float(pk[j] & 0xFFFF0000u);
-              st_a[2 * j] += lo; st_a[2 * j + 1] += hi;
-              st_b[2 * j] = fmaf(lo, lo, st_b[2 * j]); st_b[2 * j + 1] = fmaf(hi, hi, st_b[2 * j + 1]);
             }
           }
         }

@@ -20,6 +20,7 @@
 #pragma once
 #include "igemm_fwd.cuh"
 #include "pointwise.cuh"
+#include "deferred_tile.cuh"
 
 namespace ub {
 
@@ -45,6 +46,10 @@ struct MarchParams {
   const float* nb_rstd;             // [N][32]
   float nb_slope, nb_drop_p;
   uint32_t nb_drop_seed, nb_drop_thresh;
+  // kTf instantiation: source 0 (one 32-channel chunk) is the raw fp16 output y of a conv -> norm block and `tf`
+  // its deferred activation; two extra warps rewrite every halo plane of chunk 0 in shared memory
+  // (deferred_tile.cuh) between the TMA arrival and the MMAs.
+  NormActArgs tf;
 };
 
 constexpr int kMarchPlaneBytes = 12288;   // 180 rows x 64 B, padded to a multiple of 1024
@@ -53,6 +58,11 @@ constexpr int kMarchWTileBytes = 96 * 64;  // one (chunk, kh, kw) weight tile
 constexpr int kMarchRing = 5;       // TMEM accumulator ring: 5 x 96 columns
 constexpr int kMarchEpiWarps = 8;
 constexpr int kMarchThreads = (kMarchEpiWarps + 2) * 32;   // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
+// + warps 10-11: operand transform (kTf). Two warps, not four: the epilogue warps need ~166 registers and a
+// scheduler partition holds 16 K of them, so the CTA must stay at <= 3 warps per partition (12 warps); with
+// warp % 4 = partition the transform warps sit on partitions 2 and 3, away from the MMA (1) and TMA (0) warps.
+constexpr int kMarchTfThreads = 64;
+constexpr int kMarchThreadsTf = kMarchThreads + kMarchTfThreads;
 
 // kPair: two CTAs of a cluster (cta_group::2) own two neighbouring 16x8 columns and march together; every
 // UMMA is M = 256 x N = 96 with the 96 weight rows split 48 / 48 between the two CTAs' shared memories,
@@ -60,9 +70,14 @@ constexpr int kMarchThreads = (kMarchEpiWarps + 2) * 32;   // warps 0-7 epilogue
 // what bounds the single-CTA kernel (ncu: 81 % l1tex data-pipe, 69 % tensor-pipe active). The leader
 // (rank 0) issues the MMAs and owns w_full / a_full / acc_empty; the peer's TMA loads and epilogue arrive
 // on them remotely; tcgen05.commit multicasts a_empty / acc_full to both CTAs.
-template <bool kNormBwd, bool kPair>
-__global__ void __launch_bounds__(kMarchThreads, 1)
+// kTf (forward only): chunk 0 arrives as y and is transformed in place. Its TMA completes on a CTA-local barrier
+// a_loc[stage] (pair mode: each CTA waits for its own plane), the transform warps hand the stage to the MMA thread
+// through a_ready[stage] in the leader CTA (one arrival per CTA). Untransformed chunks keep the a_full path. A
+// stage alternates between the two paths, so the barrier phases are tracked per stage in bit masks.
+template <bool kNormBwd, bool kPair, bool kTf>
+__global__ void __launch_bounds__(kTf ? kMarchThreadsTf : kMarchThreads, 1)
 igemm_march_kernel(const __grid_constant__ MarchParams P) {
+  static_assert(!(kNormBwd && kTf), "the operand transform is a forward-path feature");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -74,11 +89,12 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
   const uint32_t w_base = base;
   const uint32_t a_base = w_base + nch * 9 * kWTile;
   const uint32_t bar_base = a_base + P.nsa * kMarchPlaneBytes;
-  // barriers: w_full | a_full[nsa] | a_empty[nsa] | acc_full[ring] | acc_empty[ring]
+  // barriers: w_full | a_full[nsa] | a_empty[nsa] | acc_full[ring] | acc_empty[ring] | a_loc[nsa] | a_ready[nsa]
   const uint32_t w_full = bar_base, a_full = w_full + 8, a_empty = a_full + 8 * P.nsa,
-                 acc_full = a_empty + 8 * P.nsa, acc_empty = acc_full + 8 * kMarchRing;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (acc_empty + 8 * kMarchRing - base));
-  float* red = reinterpret_cast<float*>(sm + (((acc_empty + 8 * kMarchRing + 16 + 15) & ~15u) - base));  // [8][2][32] + bias[32] + consts[4][32], 16-B aligned
+                 acc_full = a_empty + 8 * P.nsa, acc_empty = acc_full + 8 * kMarchRing,
+                 a_loc = acc_empty + 8 * kMarchRing, a_ready = a_loc + 8 * P.nsa, bar_end = a_ready + 8 * P.nsa;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (bar_end - base));
+  float* red = reinterpret_cast<float*>(sm + (((bar_end + 16 + 15) & ~15u) - base));  // [8][2][32] + bias[32] + consts[4][32], 16-B aligned
 
   // ---- work item: (n, h tile, w tile, d segment); a CTA pair takes the w tiles 2k and 2k+1
   int t = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -103,6 +119,7 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
       // warps meet at a named barrier first -- remote mbarrier arrivals are expensive)
       mbar_init(acc_empty + 8 * i, kPair ? 2 : kMarchEpiWarps);
     }
+    for (int i = 0; i < P.nsa; ++i) { mbar_init(a_loc + 8 * i, 1); mbar_init(a_ready + 8 * i, kPair ? 2 : 1); }
     fence_mbar_init();
   }
   if (warp == kMarchEpiWarps && lane == 0) {
@@ -123,6 +140,7 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
   const uint32_t w_full_ld = kPair ? mapa_shared(w_full, 0) : w_full;
   const uint32_t a_full_ld = kPair ? mapa_shared(a_full, 0) : a_full;
   const uint32_t acc_empty_ld = kPair ? mapa_shared(acc_empty, 0) : acc_empty;
+  const uint32_t a_ready_ld = kPair ? mapa_shared(a_ready, 0) : a_ready;
 
   if (warp == kMarchEpiWarps) {
     // =========================== TMA producer ===========================
@@ -139,6 +157,13 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
       for (int p = p_first; p <= p_last; ++p) {
         for (int c = 0; c < nch; ++c) {
           mbar_wait(a_empty + 8 * sa, pa ^ 1);
+          if (kTf && c == 0) {
+            // y plane of the deferred source: completes on this CTA's own barrier, the transform warps take over
+            mbar_expect_tx(a_loc + 8 * sa, 180 * 64);
+            tma_load_5d(a_base + sa * kMarchPlaneBytes, &P.tm_src[0], a_loc + 8 * sa, 0, w0 - 1, h0 - 1, p, nb);
+            if (++sa == P.nsa) { sa = 0; pa ^= 1; }
+            continue;
+          }
           if (rank == 0) mbar_expect_tx(a_full + 8 * sa, kPair ? 2 * 180 * 64 : 180 * 64);
           const bool s1 = c >= P.n_chunks_src0;
           if (kPair)
@@ -163,7 +188,7 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
       mbar_wait(w_full, 0);
       tc_fence_after();
       int sa = 0;
-      uint32_t pa = 0;
+      uint32_t ph_full = 0, ph_ready = 0;   // per-stage phase bits of a_full / a_ready
       int slot = 0;
       uint32_t pacc = 0;
       for (int p = p_first; p <= p_last; ++p) {
@@ -171,7 +196,13 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
         tc_fence_after();
         const uint32_t acc = tmem + slot * 96;
         for (int c = 0; c < nch; ++c) {
-          mbar_wait(a_full + 8 * sa, pa);
+          if (kTf && c == 0) {
+            mbar_wait(a_ready + 8 * sa, (ph_ready >> sa) & 1u);
+            ph_ready ^= 1u << sa;
+          } else {
+            mbar_wait(a_full + 8 * sa, (ph_full >> sa) & 1u);
+            ph_full ^= 1u << sa;
+          }
           tc_fence_after();
           if (leader) {
             const uint32_t a_lo = lbo_lo | ((a_base + sa * kMarchPlaneBytes) >> 4);
@@ -194,7 +225,7 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
             else umma_commit(a_empty + 8 * sa);
           }
           __syncwarp();
-          if (++sa == P.nsa) { sa = 0; pa ^= 1; }
+          if (++sa == P.nsa) sa = 0;
         }
         if (leader) {
           if (kPair) umma_commit_pair(acc_full + 8 * slot);
@@ -203,6 +234,27 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
         __syncwarp();
         if (++slot == kMarchRing) { slot = 0; pacc ^= 1; }
       }
+    }
+  } else if (kTf && warp >= kMarchEpiWarps + 2) {
+    // =========================== operand transform (warps 10-11) ===========================
+    const int t = (int)threadIdx.x - kMarchThreads;
+    HaloTransform<kMarchTfThreads> T;
+    T.setup(t, P.tf, nb, h0, w0, P.H, P.W);
+    const unsigned long long plane_vox = (unsigned long long)P.H * P.W;
+    int sa = 0;
+    uint32_t ph_loc = 0;
+    for (int p = p_first; p <= p_last; ++p) {
+      // chunk 0 of plane p sits in stage sa; the other chunks of the plane only advance the ring
+      mbar_wait(a_loc + 8 * sa, (ph_loc >> sa) & 1u);
+      ph_loc ^= 1u << sa;
+      T.apply(sm + (a_base - base) + sa * kMarchPlaneBytes, ((unsigned long long)nb * P.D + p) * plane_vox);
+      fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core's async proxy
+      named_bar_sync(3, kMarchTfThreads);
+      if (t == 0) {
+        if (kPair) mbar_arrive_cluster(a_ready_ld + 8 * sa, 1u);
+        else mbar_arrive(a_ready + 8 * sa);
+      }
+      sa = (sa + nch) % P.nsa;
     }
   } else {
     // =========================== epilogue (warps 0-7) ===========================
@@ -247,8 +299,13 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
     // finish output plane d from `fin` (all three depth contributions summed): bias, bf16, store, statistics
     auto finish_plane = [&](int d, const float (&fin)[16], const uint4 (&yv)[2]) {
       uint32_t pk[8];
+      // with statistics the tensor written here is the raw output of a conv -> norm block: fp16, never an MMA operand
+      const bool y16 = !kNormBwd && do_stats;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(fin[2 * j] + bias_r[2 * j], fin[2 * j + 1] + bias_r[2 * j + 1]);
+      for (int j = 0; j < 8; ++j) {
+        const float x0 = fin[2 * j] + bias_r[2 * j], x1 = fin[2 * j + 1] + bias_r[2 * j + 1];
+        pk[j] = y16 ? pack_f16x2_sat(x0, x1) : pack_bf16x2(x0, x1);
+      }
       const size_t vox = vox0 + (size_t)d * plane_vox;
       if (valid_hw) {
         // 16 channels = 32 bytes = one whole sector of this voxel row
@@ -257,12 +314,12 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
         __stcs(dst + 1, make_uint4(pk[4], pk[5], pk[6], pk[7]));
       }
       if (!kNormBwd && do_stats && valid_hw) {
+        // statistics from the fp32 accumulators
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float lo = __uint_as_float(pk[j] << 16);
-          const float hi = __uint_as_float(pk[j] & 0xFFFF0000u);
-          st_a[2 * j] += lo; st_a[2 * j + 1] += hi;
-          st_b[2 * j] = fmaf(lo, lo, st_b[2 * j]); st_b[2 * j + 1] = fmaf(hi, hi, st_b[2 * j + 1]);
+        for (int j = 0; j < 16; ++j) {
+          const float x = fin[j] + bias_r[j];
+          st_a[j] += x;
+          st_b[j] = fmaf(x, x, st_b[j]);
         }
       }
       if (kNormBwd && valid_hw) {
@@ -284,7 +341,7 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
             const int c = o8 * 8 + k;
             const uint32_t dw = pk[c >> 1], yy = yw[c >> 1];
             const float da = __uint_as_float((c & 1) ? (dw & 0xFFFF0000u) : (dw << 16));
-            const float yf = __uint_as_float((c & 1) ? (yy & 0xFFFF0000u) : (yy << 16));
+            const float yf = __half2float(__ushort_as_half((unsigned short)((c & 1) ? (yy >> 16) : (yy & 0xFFFFu))));   // y is fp16
             const float dz = da * (fmaf(yf, nbc[cb + c], nbc[32 + cb + c]) > 0.f ? f[k] : f[k] * P.nb_slope);
             st_a[c] += dz;
             st_b[c] = fmaf(dz, yf, st_b[c]);

@@ -7,7 +7,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
+#include "sm100_ptx.cuh"
 
 namespace ub {
 
@@ -43,6 +45,19 @@ __device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return p;
+}
+
+// The raw conv output y of a conv -> norm block is never an MMA operand: it is stored as IEEE fp16 (11-bit
+// significand instead of bf16's 8) so that the block's activations are rounded to bf16 ONCE, when they become the
+// next conv's operand. Same 16-byte vectors; conversion saturates at +-65504 instead of producing inf.
+__device__ __forceinline__ void unpack8h(const bf16x8& p, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
 }
 
 // Counter-based dropout mask (replaces torch's Philox stream, which cannot be reproduced bit-exactly;
@@ -123,26 +138,55 @@ struct NormActArgs {
   uint32_t drop_thresh; // round(p * 32768) in both 16-bit lanes
 };
 
-__device__ __forceinline__ void norm_act_apply8(float (&x)[8], const NormActArgs& A, int n, int Cp, int c0,
-                                                unsigned long long e0) {
-  if (A.scale != nullptr) {
-    const float4* sc = reinterpret_cast<const float4*>(A.scale + (size_t)n * Cp + c0);
-    const float4* sh = reinterpret_cast<const float4*>(A.shift + (size_t)n * Cp + c0);
-    const float4 s0 = __ldg(sc), s1 = __ldg(sc + 1), h0 = __ldg(sh), h1 = __ldg(sh + 1);
-    x[0] = fmaf(x[0], s0.x, h0.x); x[1] = fmaf(x[1], s0.y, h0.y);
-    x[2] = fmaf(x[2], s0.z, h0.z); x[3] = fmaf(x[3], s0.w, h0.w);
-    x[4] = fmaf(x[4], s1.x, h1.x); x[5] = fmaf(x[5], s1.y, h1.y);
-    x[6] = fmaf(x[6], s1.z, h1.z); x[7] = fmaf(x[7], s1.w, h1.w);
-  }
-  if (A.drop_p > 0.f) {
-    float f[8];
-    dropout_factors8(e0, A.drop_seed, A.drop_thresh, 1.f / (1.f - A.drop_p), f);
+// THE definition of a block's activations from its raw conv output (fp16 bits in `yraw`):
+//   a = bf16( LeakyReLU_slope( (y * scale + shift) / (1 - p) ) ) with dropped lanes cleared on the packed words.
+// Every consumer of a deferred activation (conv operand transform, weight-gradient operand transform, max-pool
+// forward / backward, the 1x1x1 output head) and the materialising pass (norm_act_fwd) call this one function,
+// so they all see bit-identical values. inv = 1 / (1 - p), slope_inv = slope * inv; e0 = element index of the
+// vector's first channel in the y tensor (dropout counter).
+__device__ __forceinline__ bf16x8 deferred_act8(const bf16x8& yraw, const float (&sc)[8], const float (&sh)[8], float inv,
+                                                float slope_inv, bool slope_le1, bool has_drop, unsigned long long e0,
+                                                uint32_t seed, uint32_t thresh) {
+  float x[8];
+  unpack8h(yraw, x);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] *= f[i];
+  for (int k = 0; k < 8; ++k) {
+    const float z = fmaf(x[k], sc[k], sh[k]);
+    const float hi = z * inv, lo = z * slope_inv;
+    x[k] = slope_le1 ? fmaxf(hi, lo) : (z > 0.f ? hi : lo);
   }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) x[i] = x[i] > 0.f ? x[i] : x[i] * A.slope;
+  bf16x8 o = pack8(x);
+  if (has_drop) {
+    uint32_t mw[4];
+    dropout_maskw(e0, seed, thresh, mw);
+    apply_maskw(o, mw);
+  }
+  return o;
 }
+// per-thread constants of a deferred activation for the channel octet starting at c0 of sample n
+struct DeferredOctet {
+  float sc[8], sh[8];
+  float inv, slope_inv;
+  bool slope_le1, has_drop;
+  uint32_t seed, thresh;
+  __device__ __forceinline__ void load(const NormActArgs& A, int n, int Cp, int c0) {
+    const bool has_norm = A.scale != nullptr;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      sc[k] = has_norm ? __ldg(A.scale + (size_t)n * Cp + c0 + k) : 1.f;
+      sh[k] = has_norm ? __ldg(A.shift + (size_t)n * Cp + c0 + k) : 0.f;
+    }
+    has_drop = A.drop_p > 0.f;
+    inv = has_drop ? 1.f / (1.f - A.drop_p) : 1.f;
+    slope_inv = A.slope * inv;
+    slope_le1 = A.slope <= 1.f;
+    seed = A.drop_seed;
+    thresh = A.drop_thresh;
+  }
+  __device__ __forceinline__ bf16x8 apply(const bf16x8& yraw, unsigned long long e0) const {
+    return deferred_act8(yraw, sc, sh, inv, slope_inv, slope_le1, has_drop, e0, seed, thresh);
+  }
+};
 
 // ------------------------------------------------------------------------------------------------
 // layout: NCDHW fp32 <-> NDHWC bf16 (channel padded)
@@ -425,7 +469,7 @@ __global__ void bn_stats_stage2_kernel(int Nb, int Cp, int C, double count_per_s
 // live in registers. No 64-bit divisions on the path.
 template <int UNROLL, bool FIXED>
 __global__ void __launch_bounds__(256)
-norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a, NormActArgs A, int Cp,
+norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y /* fp16 bits */, __nv_bfloat16* __restrict__ a, NormActArgs A, int Cp,
                     uint32_t vps) {
   const int n = blockIdx.y;
   const uint32_t c8 = (uint32_t)Cp >> 3;
@@ -433,20 +477,8 @@ norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restri
   const bf16x8* yv = reinterpret_cast<const bf16x8*>(y) + base;
   bf16x8* av = reinterpret_cast<bf16x8*>(a) + base;
   const uint32_t i0 = blockIdx.x * (256u * UNROLL) + threadIdx.x;
-  const bool has_norm = A.scale != nullptr;
-  const bool has_drop = A.drop_p > 0.f;
-  const bool slope_le1 = A.slope <= 1.f;
-  const float inv = has_drop ? 1.f / (1.f - A.drop_p) : 1.f;
-  const float slope_inv = A.slope * inv;
-  float sc[8], sh[8];
-  if (FIXED) {
-    const int c0 = (int)(threadIdx.x % c8) * 8;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      sc[k] = has_norm ? __ldg(A.scale + (size_t)n * Cp + c0 + k) : 1.f;
-      sh[k] = has_norm ? __ldg(A.shift + (size_t)n * Cp + c0 + k) : 0.f;
-    }
-  }
+  DeferredOctet K;
+  if (FIXED) K.load(A, n, Cp, (int)(threadIdx.x % c8) * 8);
   bf16x8 in[UNROLL];
 #pragma unroll
   for (int u = 0; u < UNROLL; ++u) {
@@ -457,39 +489,14 @@ norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restri
   for (int u = 0; u < UNROLL; ++u) {
     const uint32_t idx = i0 + u * 256u;
     if (idx >= vps) continue;
-    float x[8];
-    unpack8(in[u], x);
-    if (!FIXED && has_norm) {
-      const int c0 = (int)(idx % c8) * 8;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        sc[k] = __ldg(A.scale + (size_t)n * Cp + c0 + k);
-        sh[k] = __ldg(A.shift + (size_t)n * Cp + c0 + k);
-      }
-    }
-    if (has_norm) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) x[k] = fmaf(x[k], sc[k], sh[k]);
-    }
-    // dropout: the kept value is lrelu(x / (1-p)) = max(x * inv, x * slope * inv) (slope <= 1); dropped lanes
-    // are cleared on the packed words
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float hi = x[k] * inv, lo = x[k] * slope_inv;
-      x[k] = slope_le1 ? fmaxf(hi, lo) : (x[k] > 0.f ? hi : lo);
-    }
-    bf16x8 o = pack8(x);
-    if (has_drop) {
-      uint32_t mw[4];
-      dropout_maskw((unsigned long long)(base + idx) * 8ull, A.drop_seed, A.drop_thresh, mw);
-      apply_maskw(o, mw);
-    }
-    st_stream(av + idx, o);
+    if (!FIXED) K.load(A, n, Cp, (int)(idx % c8) * 8);
+    st_stream(av + idx, K.apply(in[u], (unsigned long long)(base + idx) * 8ull));
   }
 }
 
-// thread = (pooled voxel, 8 channels): writes the 8 activated voxels and their max
-__global__ void norm_act_pool_fwd_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ a,
+// thread = (pooled voxel, 8 channels): writes the 8 activated voxels (unless a == nullptr: the activations stay
+// deferred and only the pooled tensor is materialised) and their max
+__global__ void norm_act_pool_fwd_kernel(const __nv_bfloat16* __restrict__ y /* fp16 bits */, __nv_bfloat16* __restrict__ a,
                                          __nv_bfloat16* __restrict__ pooled, NormActArgs A, int Cp, int Nb, int D,
                                          int H, int W, uint32_t per_sample /* pooled voxels * Cp/8 of one sample */) {
   // grid = (blocks, N): 32-bit index math inside a sample
@@ -504,19 +511,24 @@ __global__ void norm_act_pool_fwd_kernel(const __nv_bfloat16* __restrict__ y, __
   const int wx = (int)(pv % Wp); pv /= Wp;
   const int hy = (int)(pv % Hp);
   const int dz = (int)(pv / Hp);
+  DeferredOctet K;
+  K.load(A, n, Cp, c0);
   float m[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+  bf16x8 raw[8];
+  size_t e[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int d = 2 * dz + (j >> 2), h = 2 * hy + ((j >> 1) & 1), w = 2 * wx + (j & 1);
     const size_t vox = (((size_t)n * D + d) * H + h) * W + w;
-    const size_t e = vox * c8 + (c0 >> 3);
-    float x[8];
-    unpack8(ld_stream(reinterpret_cast<const bf16x8*>(y) + e), x);
-    norm_act_apply8(x, A, n, Cp, c0, (unsigned long long)e * 8ull);
-    const bf16x8 pk = pack8(x);
-    st_stream(reinterpret_cast<bf16x8*>(a) + e, pk);
+    e[j] = vox * c8 + (c0 >> 3);
+    raw[j] = ld_stream(reinterpret_cast<const bf16x8*>(y) + e[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const bf16x8 pk = K.apply(raw[j], (unsigned long long)e[j] * 8ull);
+    if (a != nullptr) st_stream(reinterpret_cast<bf16x8*>(a) + e[j], pk);
     float xr[8];
     unpack8(pk, xr);  // max over the stored (rounded) values
 #pragma unroll
@@ -628,7 +640,7 @@ norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bflo
       const uint32_t idx = i + u * stride;
       if (idx >= vps) continue;
       float dz[8], yy[8];
-      unpack8(y_[u], yy);
+      unpack8h(y_[u], yy);
       if (from_y) dz1_from_y8(d_[u], yy, sc, sh_, B, (unsigned long long)(base + idx) * 8ull, dz);
       else dz1_8(d_[u], a_[u], B, (unsigned long long)(base + idx) * 8ull, dz);
 #pragma unroll
@@ -763,7 +775,7 @@ norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloa
     const uint32_t idx = i0 + u * 256u;
     if (idx >= vps) continue;
     float dz[8], yy[8];
-    if (has_norm) unpack8(y_[u], yy);
+    if (has_norm) unpack8h(y_[u], yy);
     if (from_y) dz1_from_y8(d_[u], yy, ka, sh_, B, (unsigned long long)(base + idx) * 8ull, dz);
     else dz1_8(d_[u], a_[u], B, (unsigned long long)(base + idx) * 8ull, dz);
     if (has_norm) {
@@ -778,9 +790,12 @@ norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloa
 // MaxPool3d(2) backward: route dP to the first maximum of each window (d,h,w scan order, as torch)
 // thread = (pooled voxel, 8 channels). accumulate != 0: dA += routed grad (skip-path grad already there)
 // ------------------------------------------------------------------------------------------------
+// DEFERRED: `a` points at the block's raw conv output y (fp16) and A describes its deferred activation; the
+// activated values are recomputed with deferred_act8 (bit-identical to what the pooling forward compared).
+template <bool DEFERRED>
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ dP,
                                    __nv_bfloat16* __restrict__ dA, int accumulate, int Cp, int Nb, int D, int H, int W,
-                                   uint32_t per_sample /* pooled voxels * Cp/8 of one sample */) {
+                                   uint32_t per_sample /* pooled voxels * Cp/8 of one sample */, NormActArgs A) {
   // grid = (blocks, N): 32-bit index math inside a sample
   const uint32_t j0 = blockIdx.x * blockDim.x + threadIdx.x;
   if (j0 >= per_sample) return;
@@ -793,6 +808,8 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __
   const int wx = (int)(pv % Wp); pv /= Wp;
   const int hy = (int)(pv % Hp);
   const int dz = (int)(pv / Hp);
+  DeferredOctet K;
+  if (DEFERRED) K.load(A, n, Cp, cidx * 8);
   float g[8];
   unpack8(ld_stream(reinterpret_cast<const bf16x8*>(dP) + i), g);
   float best[8];
@@ -800,12 +817,17 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __
 #pragma unroll
   for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; arg[k] = 0; }
   size_t e[8];
+  bf16x8 raw[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int d = 2 * dz + (j >> 2), h = 2 * hy + ((j >> 1) & 1), w = 2 * wx + (j & 1);
     e[j] = ((((size_t)n * D + d) * H + h) * W + w) * c8 + cidx;
+    raw[j] = ld_stream(reinterpret_cast<const bf16x8*>(a) + e[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
     float x[8];
-    unpack8(ld_stream(reinterpret_cast<const bf16x8*>(a) + e[j]), x);
+    unpack8(DEFERRED ? K.apply(raw[j], (unsigned long long)e[j] * 8ull) : raw[j], x);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       if (x[k] > best[k]) { best[k] = x[k]; arg[k] = j; }
@@ -881,10 +903,8 @@ __device__ __forceinline__ int concat_real_index(int p, int split_pad, int split
   const int r = p - split_pad + split_real;
   return r < n_real ? r : -1;
 }
-__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, WeightPackArgs A) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)A.nblocks * A.rows_pad * A.cols_pad;
-  if (i >= total) return;
+__device__ __forceinline__ void pack_weight_element(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                                    const WeightPackArgs& A, long long i) {
   const int col = (int)(i % A.cols_pad);
   int row = (int)((i / A.cols_pad) % A.rows_pad);
   const int blk = (int)(i / ((long long)A.cols_pad * A.rows_pad));
@@ -899,6 +919,43 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
   if (rr >= 0 && cc >= 0)
     v = w[(size_t)rr * A.stride_row + (size_t)cc * A.stride_col + (size_t)tap * A.src_tap_stride];
   out[i] = __float2bfloat16_rn(v);
+}
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, WeightPackArgs A) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)A.nblocks * A.rows_pad * A.cols_pad;
+  if (i >= total) return;
+  pack_weight_element(w, out, A, i);
+}
+
+// All the weights of a network in ONE launch (a forward / backward pass re-packs its bf16 operand copies from the
+// live fp32 Parameters every time it runs: ~25 us for the generator's 22.6 M weights, and no cache that an
+// out-of-band write to parameter memory could leave stale). The table is a __grid_constant__ kernel argument.
+constexpr int kPackMaxTensors = 32;
+constexpr int kPackBlockElems = 2048;     // elements per block (256 threads x 8)
+struct WeightPackBatch {
+  WeightPackArgs a[kPackMaxTensors];
+  const float* w[kPackMaxTensors];
+  __nv_bfloat16* out[kPackMaxTensors];
+  int block_begin[kPackMaxTensors + 1];
+  int count;
+};
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const __grid_constant__ WeightPackBatch B) {
+  __shared__ int s_t;
+  if (threadIdx.x == 0) {
+    int t = 0;
+    while (t + 1 < B.count && (int)blockIdx.x >= B.block_begin[t + 1]) ++t;
+    s_t = t;
+  }
+  __syncthreads();
+  const int t = s_t;
+  const WeightPackArgs& A = B.a[t];
+  const long long total = (long long)A.nblocks * A.rows_pad * A.cols_pad;
+  const long long begin = (long long)((int)blockIdx.x - B.block_begin[t]) * kPackBlockElems;
+#pragma unroll
+  for (int k = 0; k < kPackBlockElems / 256; ++k) {
+    const long long i = begin + k * 256 + threadIdx.x;
+    if (i < total) pack_weight_element(B.w[t], B.out[t], A, i);
+  }
 }
 
 // split-K reduction of wgrad partials [nsplit][ntap][ci_total][co_total] -> torch layout fp32 grad
@@ -1097,10 +1154,11 @@ struct Conv1x1Weights {
   float b[kC1MaxCo];
 };
 
-template <int CO>
+// DEFERRED: u is the raw conv output y (fp16) of the last block and A its deferred activation.
+template <int CO, bool DEFERRED>
 __global__ void __launch_bounds__(256)
 conv1x1_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ u, float* __restrict__ out, const Conv1x1Weights* __restrict__ Wg,
-                        uint32_t V) {
+                        uint32_t V, NormActArgs A) {
   // grid = (blocks, N): each block strides over the voxels of one sample; weights live in registers
   const int n = blockIdx.y;
   const int oct = threadIdx.x & 3;
@@ -1113,6 +1171,8 @@ conv1x1_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ u, float* __restrict__
   }
   const bf16x8* up = reinterpret_cast<const bf16x8*>(u + (size_t)n * V * 32);
   float* op = out + (size_t)n * CO * V;
+  DeferredOctet K;
+  if (DEFERRED) K.load(A, n, 32, oct * 8);
   constexpr int UNR = 4;             // independent 16-byte loads in flight per thread
   const uint32_t vstep = gridDim.x * (64 * UNR);
   // all lanes of a warp run the same number of iterations (the shuffles below need the full warp)
@@ -1128,7 +1188,7 @@ conv1x1_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ u, float* __restrict__
       const uint32_t v = vb + q * 64 + (threadIdx.x >> 2);
       const bool ok = v < V;
       float x[8];
-      unpack8(raw[q], x);
+      unpack8(DEFERRED ? K.apply(raw[q], ((unsigned long long)n * V + v) * 32ull + oct * 8) : raw[q], x);
       float mine0 = 0.f, mine1 = 0.f;   // outputs oct and oct + 4
 #pragma unroll
       for (int c = 0; c < CO; ++c) {
@@ -1152,11 +1212,11 @@ conv1x1_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ u, float* __restrict__
 //   dW[co][ci] = sum_v dout[co][v] * u[v][ci],  db[co] = sum_v dout[co][v]     (per-block partials)
 // thread = (voxel, octet of ci); grid = (blocks, N); part: [blocks * N][kC1MaxCo][33] floats (column 32 =
 // bias gradient).
-template <int CO>
+template <int CO, bool DEFERRED>
 __global__ void __launch_bounds__(256, 2)
 conv1x1_from_ncdhw_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ u,
                               __nv_bfloat16* __restrict__ du, const Conv1x1Weights* __restrict__ Wg, uint32_t V,
-                              int want_w, float* __restrict__ part) {
+                              int want_w, float* __restrict__ part, NormActArgs A) {
   __shared__ float red[8][CO][33];
   const int n = blockIdx.y;
   const int oct = threadIdx.x & 3;
@@ -1176,6 +1236,8 @@ conv1x1_from_ncdhw_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat1
   const float* gp = dout + (size_t)n * CO * V;
   const bf16x8* up = reinterpret_cast<const bf16x8*>(u) + (size_t)n * V * 4;
   bf16x8* dup = reinterpret_cast<bf16x8*>(du) + (size_t)n * V * 4;
+  DeferredOctet K;
+  if (DEFERRED) K.load(A, n, 32, oct * 8);
   constexpr int UNR = 2;
   const uint32_t vstep = gridDim.x * (64 * UNR);
   for (uint32_t vb = blockIdx.x * (64 * UNR) + (threadIdx.x >> 2); vb < V; vb += vstep) {
@@ -1207,7 +1269,7 @@ conv1x1_from_ncdhw_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat1
       }
       if (want_w) {
         float x[8];
-        unpack8(ux[q], x);
+        unpack8(DEFERRED ? K.apply(ux[q], ((unsigned long long)n * V + v) * 32ull + oct * 8) : ux[q], x);
 #pragma unroll
         for (int c = 0; c < CO; ++c) {
           gb[c] += g[q][c];

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace ub {
@@ -24,6 +25,13 @@ __device__ __forceinline__ bool elect_one() {
       "selp.u32 %0, 1, 0, P;\n\t}\n"
       : "=r"(pred));
   return pred != 0;
+}
+
+// two floats -> packed IEEE fp16 pair (lo in bits 0-15), round to nearest, saturating at +-65504 (no inf)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -153,12 +153,10 @@ extern "C" long long ub_packed_weight_elems(const ub_conv_desc* d, int dir) {
   return (long long)ntaps_of(d->kind) * d->cop * cin;
 }
 
-extern "C" int ub_pack_conv_weights(const ub_conv_desc* d, int dir, const float* w, void* packed, void* stream) {
-  if (int e = check_desc(d)) return e;
-  if (!w || !packed) return fail(-1, "null weight pointer");
+static void build_pack_args(const ub_conv_desc* d, int dir, WeightPackArgs* out) {
   const int nt = ntaps_of(d->kind);
   const int ci = d->c0 + d->c1;
-  WeightPackArgs A;
+  WeightPackArgs& A = *out;
   memset(&A, 0, sizeof(A));
   A.nblocks = nt;
   const bool deconv = d->kind == UB_DECONV_K2S2;
@@ -195,10 +193,44 @@ extern "C" int ub_pack_conv_weights(const ub_conv_desc* d, int dir, const float*
   A.split_pad = d->c1p ? d->c0p : 0;
   A.split_real = d->c1p ? d->c0 : 0;
   A.split_on_rows = dir == 1;
+}
+
+extern "C" int ub_pack_conv_weights(const ub_conv_desc* d, int dir, const float* w, void* packed, void* stream) {
+  if (int e = check_desc(d)) return e;
+  if (!w || !packed) return fail(-1, "null weight pointer");
+  WeightPackArgs A;
+  build_pack_args(d, dir, &A);
   const long long total = (long long)A.nblocks * A.rows_pad * A.cols_pad;
   pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       w, reinterpret_cast<__nv_bfloat16*>(packed), A);
   UB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ub_pack_conv_weights_multi(const ub_weight_pack_item* items, int count, void* stream) {
+  if (count < 0 || (count > 0 && !items)) return fail(-1, "bad arguments to ub_pack_conv_weights_multi");
+  static WeightPackBatch B;            // 11 KB table: built under a lock, copied into the launch by value
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  int i = 0;
+  while (i < count) {
+    B.count = 0;
+    B.block_begin[0] = 0;
+    while (i < count && B.count < kPackMaxTensors) {
+      const ub_weight_pack_item& it = items[i++];
+      if (int e = check_desc(&it.desc)) return e;
+      if (!it.w || !it.packed) return fail(-1, "ub_pack_conv_weights_multi: item %d has a null pointer", i - 1);
+      const int k = B.count++;
+      build_pack_args(&it.desc, it.dir, &B.a[k]);
+      B.w[k] = it.w;
+      B.out[k] = reinterpret_cast<__nv_bfloat16*>(it.packed);
+      const long long total = (long long)B.a[k].nblocks * B.a[k].rows_pad * B.a[k].cols_pad;
+      B.block_begin[k + 1] = B.block_begin[k] + (int)((total + kPackBlockElems - 1) / kPackBlockElems);
+    }
+    if (B.count == 0) break;
+    pack_weights_multi_kernel<<<(unsigned)B.block_begin[B.count], 256, 0, (cudaStream_t)stream>>>(B);
+    UB_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -213,17 +245,35 @@ struct IgemmPlan {
   int smem;
 };
 
+// Per-device state: the SM count and the "large dynamic shared memory" opt-in of every kernel are properties of
+// the CURRENT device (one process may drive several GPUs), so both are cached per device ordinal.
+static const int kMaxDevices = 64;
+static int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
 static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-      n = v;
-    else
-      n = 148;
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = current_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize of `fn` on the current device, once per (kernel, device)
+struct SmemOptIn {
+  std::atomic<unsigned long long> done{0};
+};
+static int opt_in_smem(SmemOptIn& st, const void* fn, const char* what) {
+  const int dev = current_device();
+  if (st.done.load(std::memory_order_acquire) & (1ull << dev)) return 0;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return fail(-3, "cudaFuncSetAttribute(%s): %s", what, cudaGetErrorString(e));
+  st.done.fetch_or(1ull << dev, std::memory_order_release);
+  return 0;
 }
 
 // Fill the smem plan / grid once the geometry fields of P are set. nt_max = widest N tile.
@@ -264,12 +314,8 @@ static int finish_plan(IgemmPlan* pl, int nt_max) {
 }
 
 static int launch_igemm(const IgemmPlan& pl, cudaStream_t st) {
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(igemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  if (attr_err != cudaSuccess) return fail(-3, "cudaFuncSetAttribute(igemm_fwd): %s", cudaGetErrorString(attr_err));
+  static SmemOptIn opt;
+  if (int e = opt_in_smem(opt, (const void*)igemm_fwd_kernel, "igemm_fwd")) return e;
   igemm_fwd_kernel<<<pl.grid, kFwdThreads, pl.smem, st>>>(pl.P);
   UB_LAUNCH_CHECK();
   return 0;
@@ -304,7 +350,7 @@ static void march_geometry(int n, int D, int H, int W, int* tiles_w, int* tiles_
   *tiles_w = cdiv(W, 8);
   *tiles_h = cdiv(H, 16);
   const int columns = n * *tiles_h * *tiles_w;
-  int ns = cdiv(4 * 148, columns);
+  int ns = cdiv(4 * sm_count(), columns);
   const int max_seg = D / 8 > 1 ? D / 8 : 1;
   if (ns > max_seg) ns = max_seg;
   if (ns < 1) ns = 1;
@@ -319,11 +365,24 @@ static uint32_t drop_thresh(float p) {
   return t * 0x00010001u;
 }
 
+static int fill_deferred(NormActArgs* A, const ub_deferred_act* tf) {
+  if (!tf->scale || !tf->shift) return fail(-1, "ub_deferred_act needs scale and shift");
+  if (tf->drop_p < 0.f || tf->drop_p >= 1.f) return fail(-1, "dropout p out of range");
+  A->scale = tf->scale; A->shift = tf->shift; A->slope = tf->slope; A->drop_p = tf->drop_p;
+  A->drop_seed = tf->drop_seed; A->drop_thresh = drop_thresh(tf->drop_p);
+  return 0;
+}
+
 static int launch_march(const void* src0, int c0p, const void* src1, int c1p, int n, int D, int H, int W,
                         const void* w_packed, const float* bias, int bias_n, void* out, float* stats,
-                        const ub_norm_bwd_fuse* fuse, cudaStream_t st) {
+                        const ub_norm_bwd_fuse* fuse, const ub_deferred_act* tf, cudaStream_t st) {
   MarchParams P;
   memset(&P, 0, sizeof(P));
+  if (tf) {
+    if (fuse) return fail(-1, "a deferred source and the norm-backward fusion are exclusive");
+    if (c0p != 32) return fail(-2, "a deferred activation source must have 32 padded channels (got %d)", c0p);
+    if (int e = fill_deferred(&P.tf, tf)) return e;
+  }
   if (fuse) {
     if (!fuse->y || !fuse->scale || !fuse->shift || !fuse->mean || !fuse->rstd || !fuse->partial)
       return fail(-1, "incomplete ub_norm_bwd_fuse");
@@ -345,7 +404,7 @@ static int launch_march(const void* src0, int c0p, const void* src1, int c1p, in
   static const int pair_min_chunks = getenv("UB_MARCH_PAIR_MIN_CHUNKS") ? atoi(getenv("UB_MARCH_PAIR_MIN_CHUNKS")) : 2;
   const bool pair = pair_enabled && (P.tiles_w % 2 == 0) && P.n_chunks_total >= pair_min_chunks;
   const int wbytes = P.n_chunks_total * 9 * (pair ? kMarchWTileBytes / 2 : kMarchWTileBytes);
-  const int misc = 8 * 32 + 64 + (kMarchEpiWarps * 2 * 32 + 32 + 128) * 4 + 64 + 1024;
+  const int misc = 8 * 48 + 64 + (kMarchEpiWarps * 2 * 32 + 32 + 128) * 4 + 64 + 1024;
   P.nsa = (220 * 1024 - wbytes - misc) / kMarchPlaneBytes;
   if (P.nsa > 8) P.nsa = 8;
   if (P.nsa < 2) return fail(-2, "march smem plan: no room for the plane ring");
@@ -354,22 +413,24 @@ static int launch_march(const void* src0, int c0p, const void* src1, int c1p, in
   if (c1p)
     if (int e = make_act_map(&P.tm_src[1], src1, c1p, W, H, D, n, 32, 10, 18, 1)) return e;
   if (int e = make_w_map(&P.tm_w, w_packed, c0p + c1p, 9 * 96, 32, pair ? 48 : 96)) return e;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    const void* fns[4] = {(const void*)igemm_march_kernel<false, false>, (const void*)igemm_march_kernel<true, false>,
-                          (const void*)igemm_march_kernel<false, true>, (const void*)igemm_march_kernel<true, true>};
-    for (int i = 0; i < 4 && attr_err == cudaSuccess; ++i)
-      attr_err = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  if (attr_err != cudaSuccess) return fail(-3, "cudaFuncSetAttribute(igemm_march): %s", cudaGetErrorString(attr_err));
+  // instantiation: [fuse | tf][pair]
+  typedef void (*MarchFn)(const MarchParams);
+  static const MarchFn fns[3][2] = {
+      {igemm_march_kernel<false, false, false>, igemm_march_kernel<false, true, false>},
+      {igemm_march_kernel<true, false, false>, igemm_march_kernel<true, true, false>},
+      {igemm_march_kernel<false, false, true>, igemm_march_kernel<false, true, true>}};
+  static SmemOptIn opt[3][2];
+  const int variant = fuse ? 1 : (tf ? 2 : 0);
+  MarchFn fn = fns[variant][pair ? 1 : 0];
+  if (int e = opt_in_smem(opt[variant][pair ? 1 : 0], (const void*)fn, "igemm_march")) return e;
   const unsigned grid = (unsigned)(n * P.tiles_h * P.tiles_w * P.nseg);
+  const unsigned threads = tf ? kMarchThreadsTf : kMarchThreads;
   if (pair) {
     // cluster of two CTAs along x: blocks (2k, 2k+1) take the w tiles (2j, 2j+1) of one column pair
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid, 1, 1);
-    cfg.blockDim = dim3(kMarchThreads, 1, 1);
+    cfg.blockDim = dim3(threads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -377,13 +438,10 @@ static int launch_march(const void* src0, int c0p, const void* src1, int c1p, in
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = fuse ? cudaLaunchKernelEx(&cfg, igemm_march_kernel<true, true>, P)
-                          : cudaLaunchKernelEx(&cfg, igemm_march_kernel<false, true>, P);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, fn, P);
     if (le != cudaSuccess) return fail(-3, "cluster launch of igemm_march failed: %s", cudaGetErrorString(le));
-  } else if (fuse) {
-    igemm_march_kernel<true, false><<<grid, kMarchThreads, smem, st>>>(P);
   } else {
-    igemm_march_kernel<false, false><<<grid, kMarchThreads, smem, st>>>(P);
+    fn<<<grid, threads, smem, st>>>(P);
   }
   UB_LAUNCH_CHECK();
   return 0;
@@ -429,9 +487,20 @@ extern "C" int ub_conv_num_tiles(const ub_conv_desc* d) {
   return d->n * cdiv(Dt, td) * cdiv(Ht, 16) * cdiv(Wt, 8);
 }
 
+// A deferred source 0 is served where BOTH consumers of the activations -- the forward conv and its weight
+// gradient -- run on the marching kernels: 3x3x3, 32 output channels, one 32-channel source 0, planes >= 16 x 8.
+static bool use_wgrad_march(const ub_conv_desc* d);
+extern "C" int ub_conv_deferred_src0_ok(const ub_conv_desc* d) {
+  if (check_desc(d)) return -1;
+  return (use_march(d, 0) && d->c0p == 32 && use_wgrad_march(d)) ? 1 : 0;
+}
+
 extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* src1, const void* w_packed,
-                           const float* bias, int act, float slope, void* out, float* stats_partial, void* stream) {
+                           const float* bias, int act, float slope, void* out, float* stats_partial,
+                           const ub_deferred_act* src0_act, void* stream) {
   if (int e = check_desc(d)) return e;
+  if (src0_act && ub_conv_deferred_src0_ok(d) != 1)
+    return fail(-2, "a deferred source activation is not supported for this convolution (ub_conv_deferred_src0_ok)");
   if (int e = ensure_encode()) return e;
   if (!src0 || !w_packed || !out) return fail(-1, "null pointer in ub_conv_fwd");
   if (d->c1p && !src1) return fail(-1, "second source missing");
@@ -443,7 +512,7 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
   if (use_march(d, 0)) {
     if (act) return fail(-2, "fused activation is not available on the marching conv path");
     return launch_march(src0, d->c0p, src1, d->c1p, d->n, d->d, d->h, d->w, w_packed, bias, d->co, out,
-                        stats_partial, nullptr, st);
+                        stats_partial, nullptr, src0_act, st);
   }
 
   IgemmPlan pl;
@@ -603,7 +672,8 @@ extern "C" int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const 
   const int ntaps = ntaps_of(d->kind);
   const int ncols = d->c0p + d->c1p;
   if (use_march(d, 1))
-    return launch_march(dy, d->cop, nullptr, 0, d->n, d->d, d->h, d->w, w_packed_dgrad, nullptr, 0, dsrc0, nullptr, fuse, st);
+    return launch_march(dy, d->cop, nullptr, 0, d->n, d->d, d->h, d->w, w_packed_dgrad, nullptr, 0, dsrc0, nullptr, fuse,
+                        nullptr, st);
 
   IgemmPlan pl;
   memset(&pl, 0, sizeof(pl));
@@ -817,8 +887,10 @@ extern "C" long long ub_conv_wgrad_workspace_bytes(const ub_conv_desc* d) {
 }
 
 extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void* src1, const void* dy,
-                             void* workspace, float* dw, void* stream) {
+                             void* workspace, float* dw, const ub_deferred_act* src0_act, void* stream) {
   if (int e = check_desc(d)) return e;
+  if (src0_act && ub_conv_deferred_src0_ok(d) != 1)
+    return fail(-2, "a deferred source activation is not supported for this weight gradient (ub_conv_deferred_src0_ok)");
   if (int e = ensure_encode()) return e;
   if (!src0 || !dy || !workspace || !dw) return fail(-1, "null pointer in ub_conv_wgrad");
   if (d->c1p && !src1) return fail(-1, "second source missing");
@@ -845,19 +917,17 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
     if (d->c1p)
       if (int e = make_act_map(&M.tm_x[1], src1, d->c1p, gw, gh, gd, d->n, 32, bw, bh, 1)) return e;
     if (int e = make_act_map(&M.tm_dy, dy, d->cop, gw, gh, gd, d->n, 32, 8, 16, 1)) return e;
-    static std::once_flag once_m;
-    static cudaError_t attr_err_m = cudaSuccess;
-    std::call_once(once_m, [] {
-      attr_err_m = cudaFuncSetAttribute(wgrad_march_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (attr_err_m == cudaSuccess)
-        attr_err_m = cudaFuncSetAttribute(wgrad_march_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    });
-    if (attr_err_m != cudaSuccess) return fail(-3, "cudaFuncSetAttribute(wgrad_march): %s", cudaGetErrorString(attr_err_m));
+    if (src0_act)
+      if (int e = fill_deferred(&M.tf, src0_act)) return e;
+    typedef void (*WmFn)(const WgradMarchParams);
+    static const WmFn wfns[3] = {wgrad_march_kernel<3, false>, wgrad_march_kernel<2, false>, wgrad_march_kernel<3, true>};
+    static SmemOptIn wopt[3];
+    const int wv = stem ? 1 : (src0_act ? 2 : 0);
+    if (int e = opt_in_smem(wopt[wv], (const void*)wfns[wv], "wgrad_march")) return e;
     const int nsplit = wgrad_march_splits(d);
     const int smem = kWmXStages * kWmXBytes + (kWmYSlots + kt - 1) * kWmYBytes + 8 * 32 + 64 + 1024;
     const dim3 grid((unsigned)nsplit, (unsigned)(M.n_chunks_total * M.n_cotiles * (stem ? 8 : 1)));
-    if (stem) wgrad_march_kernel<2><<<grid, kIgemmThreads, smem, st>>>(M);
-    else wgrad_march_kernel<3><<<grid, kIgemmThreads, smem, st>>>(M);
+    wfns[wv]<<<grid, kIgemmThreads, smem, st>>>(M);
     UB_LAUNCH_CHECK();
     WgradReduceArgs R;
     memset(&R, 0, sizeof(R));
@@ -889,12 +959,8 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
   if (d->c1p)
     if (int e = make_act_map(&P.tm_x[1], src1, d->c1p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, P.x_stride)) return e;
   if (int e = make_act_map(&P.tm_dy, dy, d->cop, ow, oh, od, d->n, P.ncb, 8, 16, P.dy_stride)) return e;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  if (attr_err != cudaSuccess) return fail(-3, "cudaFuncSetAttribute(igemm_wgrad): %s", cudaGetErrorString(attr_err));
+  static SmemOptIn gopt;
+  if (int e = opt_in_smem(gopt, (const void*)igemm_wgrad_kernel, "igemm_wgrad")) return e;
   igemm_wgrad_kernel<<<pl.grid, kIgemmThreads, pl.smem, st>>>(P);
   UB_LAUNCH_CHECK();
 
@@ -1044,7 +1110,7 @@ extern "C" int ub_norm_finalize(const float* stats_partial, int tiles_per_sample
 extern "C" int ub_norm_act_fwd(const void* y, const float* scale, const float* shift, float slope, float drop_p,
                                uint32_t drop_seed, int n, int d, int h, int w, int cp, void* a, void* pooled,
                                void* stream) {
-  if (!y || !a || cp % 8) return fail(-1, "bad arguments to ub_norm_act_fwd");
+  if (!y || (!a && !pooled) || cp % 8) return fail(-1, "bad arguments to ub_norm_act_fwd");
   if (drop_p < 0.f || drop_p >= 1.f) return fail(-1, "dropout p out of range");
   NormActArgs A{scale, shift, slope, drop_p, drop_seed, drop_thresh(drop_p)};
   const long long V = (long long)d * h * w;
@@ -1134,13 +1200,23 @@ extern "C" int ub_norm_act_bwd(const void* dA, const void* a, const void* y, int
 }
 
 extern "C" int ub_maxpool_bwd(const void* a, const void* dP, void* dA, int accumulate, int n, int d, int h, int w,
-                              int cp, void* stream) {
+                              int cp, const ub_deferred_act* a_act, void* stream) {
   if (!a || !dP || !dA || cp % 8 || ((d | h | w) & 1)) return fail(-1, "bad arguments to ub_maxpool_bwd");
+  NormActArgs A;
+  memset(&A, 0, sizeof(A));
+  if (a_act)
+    if (int e = fill_deferred(&A, a_act)) return e;
   const long long per_sample = ((long long)d * h * w / 8) * (cp / 8);
   if (per_sample >= (1ll << 31) || n <= 0 || n > 65535) return fail(-2, "ub_maxpool_bwd: sample too large");
-  maxpool_bwd_kernel<<<dim3((unsigned)((per_sample + 255) / 256), n), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(dP),
-      reinterpret_cast<__nv_bfloat16*>(dA), accumulate, cp, n, d, h, w, (uint32_t)per_sample);
+  const dim3 grid((unsigned)((per_sample + 255) / 256), n);
+  if (a_act)
+    maxpool_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(dP),
+        reinterpret_cast<__nv_bfloat16*>(dA), accumulate, cp, n, d, h, w, (uint32_t)per_sample, A);
+  else
+    maxpool_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(dP),
+        reinterpret_cast<__nv_bfloat16*>(dA), accumulate, cp, n, d, h, w, (uint32_t)per_sample, A);
   UB_LAUNCH_CHECK();
   return 0;
 }
@@ -1253,7 +1329,8 @@ static int fill_conv1x1_weights(const float* w, int ci, const float* bias, int c
 }
 
 extern "C" int ub_conv1x1_to_ncdhw(const void* u, int cp, const float* w, int ci, const float* bias, int co, int n,
-                                   long long voxels, void* workspace, float* out, void* stream) {
+                                   long long voxels, void* workspace, float* out, const ub_deferred_act* u_act,
+                                   void* stream) {
   if (!u || !w || !out || !workspace || n <= 0 || n > 65535 || voxels <= 0) return fail(-1, "bad arguments to ub_conv1x1_to_ncdhw");
   if (cp != 32 || ci <= 0 || ci > 32 || co <= 0 || co > kC1MaxCo)
     return fail(-2, "ub_conv1x1_to_ncdhw supports cp = 32, ci <= 32, co <= %d (got cp=%d ci=%d co=%d)", kC1MaxCo, cp, ci, co);
@@ -1266,8 +1343,15 @@ extern "C" int ub_conv1x1_to_ncdhw(const void* u, int cp, const float* w, int ci
   const dim3 grid((unsigned)blocks, n);
   const __nv_bfloat16* up = reinterpret_cast<const __nv_bfloat16*>(u);
   const Conv1x1Weights* T = reinterpret_cast<const Conv1x1Weights*>(workspace);
+  NormActArgs A;
+  memset(&A, 0, sizeof(A));
+  if (u_act)
+    if (int e = fill_deferred(&A, u_act)) return e;
   switch (co) {
-#define UB_C1_FWD(C_) case C_: conv1x1_to_ncdhw_kernel<C_><<<grid, 256, 0, st>>>(up, out, T, (uint32_t)voxels); break;
+#define UB_C1_FWD(C_) case C_: \
+    if (u_act) conv1x1_to_ncdhw_kernel<C_, true><<<grid, 256, 0, st>>>(up, out, T, (uint32_t)voxels, A); \
+    else conv1x1_to_ncdhw_kernel<C_, false><<<grid, 256, 0, st>>>(up, out, T, (uint32_t)voxels, A); \
+    break;
     UB_C1_FWD(1) UB_C1_FWD(2) UB_C1_FWD(3) UB_C1_FWD(4) UB_C1_FWD(5) UB_C1_FWD(6) UB_C1_FWD(7) UB_C1_FWD(8)
 #undef UB_C1_FWD
   }
@@ -1276,7 +1360,8 @@ extern "C" int ub_conv1x1_to_ncdhw(const void* u, int cp, const float* w, int ci
 }
 
 extern "C" int ub_conv1x1_from_ncdhw_bwd(const float* dout, int co, const void* u, int cp, const float* w, int ci, int n,
-                                         long long voxels, void* workspace, void* du, float* dw, float* db, void* stream) {
+                                         long long voxels, void* workspace, void* du, float* dw, float* db,
+                                         const ub_deferred_act* u_act, void* stream) {
   if (!dout || !w || !workspace || n <= 0 || voxels <= 0) return fail(-1, "bad arguments to ub_conv1x1_from_ncdhw_bwd");
   if ((dw || db) && !u) return fail(-1, "ub_conv1x1_from_ncdhw_bwd: weight / bias gradients need the forward input u");
   if (cp != 32 || ci <= 0 || ci > 32 || co <= 0 || co > kC1MaxCo)
@@ -1294,8 +1379,15 @@ extern "C" int ub_conv1x1_from_ncdhw_bwd(const float* dout, int co, const void* 
   const __nv_bfloat16* up = reinterpret_cast<const __nv_bfloat16*>(u);
   __nv_bfloat16* dup = reinterpret_cast<__nv_bfloat16*>(du);
   const Conv1x1Weights* T = reinterpret_cast<const Conv1x1Weights*>(workspace);
+  NormActArgs A;
+  memset(&A, 0, sizeof(A));
+  if (u_act)
+    if (int e = fill_deferred(&A, u_act)) return e;
   switch (co) {
-#define UB_C1_BWD(C_) case C_: conv1x1_from_ncdhw_bwd_kernel<C_><<<grid, 256, 0, st>>>(dout, up, dup, T, (uint32_t)voxels, want_w, part); break;
+#define UB_C1_BWD(C_) case C_: \
+    if (u_act) conv1x1_from_ncdhw_bwd_kernel<C_, true><<<grid, 256, 0, st>>>(dout, up, dup, T, (uint32_t)voxels, want_w, part, A); \
+    else conv1x1_from_ncdhw_bwd_kernel<C_, false><<<grid, 256, 0, st>>>(dout, up, dup, T, (uint32_t)voxels, want_w, part, A); \
+    break;
     UB_C1_BWD(1) UB_C1_BWD(2) UB_C1_BWD(3) UB_C1_BWD(4) UB_C1_BWD(5) UB_C1_BWD(6) UB_C1_BWD(7) UB_C1_BWD(8)
 #undef UB_C1_BWD
   }

@@ -20,6 +20,7 @@
 // fp32 partial record; wgrad_reduce_kernel sums the records in a fixed order.
 #pragma once
 #include "igemm_fwd.cuh"
+#include "deferred_tile.cuh"
 
 namespace ub {
 
@@ -33,14 +34,19 @@ struct WgradMarchParams {
   int co_total, n_cotiles;  // padded output channels, co_total / 32
   int ntaps;                // taps of the partial record (27 / 64)
   float* partial;           // [gridDim.x][ntaps][ci_total][co_total]
+  // kTf (KT = 3): source 0 (one 32-channel chunk) is the raw fp16 output y of a conv -> norm block and `tf` its
+  // deferred activation: the four epilogue warps, idle until the end, rewrite every X halo plane of chunk 0 in
+  // shared memory (deferred_tile.cuh) before the MMA thread reads it.
+  NormActArgs tf;
 };
 
 constexpr int kWmXStages = 4, kWmXBytes = 12288;
 constexpr int kWmYSlots = 8, kWmYBytes = 8192;   // + KT-1 mirror slots
 
-template <int KT>
+template <int KT, bool kTf>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
+  static_assert(!kTf || KT == 3, "the operand transform serves the 3x3x3 layers");
   constexpr int BW = 8 + KT - 1, BH = 16 + KT - 1;     // halo box
   constexpr int NN = KT * 32;                          // UMMA N
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -51,8 +57,8 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
   const uint32_t y_base = x_base + kWmXStages * kWmXBytes;
   const uint32_t bar_base = y_base + (kWmYSlots + KT - 1) * kWmYBytes;
   const uint32_t x_full = bar_base, x_empty = x_full + 8 * kWmXStages, y_full = x_empty + 8 * kWmXStages,
-                 y_empty = y_full + 8 * kWmYSlots, acc_full = y_empty + 8 * kWmYSlots;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (acc_full + 8 - base));
+                 y_empty = y_full + 8 * kWmYSlots, acc_full = y_empty + 8 * kWmYSlots, x_ready = acc_full + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (x_ready + 8 * kWmXStages - base));
 
   // blockIdx.y = ((parity) * chunks + chunk) * cotiles + cot   (parity only for KT = 2)
   int by = blockIdx.y;
@@ -62,6 +68,7 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
   const int pd = (parity >> 2) & 1, ph = (parity >> 1) & 1, pw = parity & 1;
   const bool s1 = chunk >= P.n_chunks_src0;
   const int c0 = (s1 ? chunk - P.n_chunks_src0 : chunk) * 32;
+  const bool tf_cta = kTf && chunk == 0;     // this CTA's X planes are y planes of the deferred source
   // X tile origin relative to the dY tile origin, and the dY plane paired with atom j of X plane p: p + doff + j
   const int xoff_w = KT == 3 ? -1 : (pw ? -1 : 0), xoff_h = KT == 3 ? -1 : (ph ? -1 : 0);
   const int doff = KT == 3 ? -1 : pd - 1;
@@ -72,7 +79,9 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
   int i_end = i_begin + per; if (i_end > items) i_end = items;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kWmXStages; ++i) { mbar_init(x_full + 8 * i, 1); mbar_init(x_empty + 8 * i, 1); }
+    for (int i = 0; i < kWmXStages; ++i) {
+      mbar_init(x_full + 8 * i, 1); mbar_init(x_empty + 8 * i, 1); mbar_init(x_ready + 8 * i, 1);
+    }
     for (int i = 0; i < kWmYSlots; ++i) { mbar_init(y_full + 8 * i, 1); mbar_init(y_empty + 8 * i, 1); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
@@ -154,7 +163,7 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
           if (s >= kWmYSlots) { s -= kWmYSlots; ph_ ^= 1; }
           mbar_wait(y_full + 8 * s, ph_);
         }
-        mbar_wait(x_full + 8 * xs, xp);
+        mbar_wait((tf_cta ? x_ready : x_full) + 8 * xs, xp);
         tc_fence_after();
         const bool last = p + 1 == d1;
         if (leader) {
@@ -187,6 +196,30 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
     if (leader) umma_commit(acc_full);
     __syncwarp();
   } else {
+    if (tf_cta) {
+      // =========================== operand transform (warps 0-3), then the epilogue ===========================
+      HaloTransform<128> T;
+      const unsigned long long plane_vox = (unsigned long long)P.H * P.W;
+      int xs = 0; uint32_t xp = 0;
+      for (int it = i_begin; it < i_end; ++it) {
+        int t = it;
+        const int seg = t % P.nseg; t /= P.nseg;
+        const int w0 = (t % P.tiles_w) * 8; t /= P.tiles_w;
+        const int h0 = (t % P.tiles_h) * 16; t /= P.tiles_h;
+        const int nb = t;
+        const int d0 = seg * P.seg_len;
+        int d1 = d0 + P.seg_len; if (d1 > P.D) d1 = P.D;
+        T.setup((int)threadIdx.x, P.tf, nb, h0, w0, P.H, P.W);
+        for (int p = d0; p < d1; ++p) {
+          mbar_wait(x_full + 8 * xs, xp);
+          T.apply(sm + (x_base - base) + xs * kWmXBytes, ((unsigned long long)nb * P.D + p) * plane_vox);
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (threadIdx.x == 0) mbar_arrive(x_ready + 8 * xs);
+          if (++xs == kWmXStages) { xs = 0; xp ^= 1; }
+        }
+      }
+    }
     // =========================== epilogue: TMEM -> partial record ===========================
     mbar_wait(acc_full, 0);
     tc_fence_after();

@@ -84,7 +84,9 @@ class _BlockFn(torch.autograd.Function):
         else:
             a = y
         ctx.cfg, ctx.desc = cfg, desc
-        ctx.saved = (s0, s1, w, y, a, scale, shift, mean, rstd)
+        # save_for_backward (also for the outputs): no output -> grad_fn -> ctx -> output reference cycle, autograd's
+        # in-place-modification checks apply, and a second backward (retain_graph) works
+        ctx.save_for_backward(s0, s1, w, y, a, scale, shift, mean, rstd)
         ctx.has_bias = bias is not None
         if pooled is None:
             return a, None
@@ -95,7 +97,7 @@ class _BlockFn(torch.autograd.Function):
         lib = _lib.load()
         st = _stream()
         cfg, desc = ctx.cfg, ctx.desc
-        s0, s1, w, y, a, scale, shift, mean, rstd = ctx.saved
+        s0, s1, w, y, a, scale, shift, mean, rstd = ctx.saved_tensors
         n, co, od, oh, ow = y.shape
         dA, dP = _f32(dA), _f32(dP)
         if dA is None and dP is None:
@@ -142,16 +144,17 @@ class _BlockFn(torch.autograd.Function):
                     d0 = None
                 if not need1:
                     d1 = None
-        ctx.saved = None
         return None, d0, d1, dw, db, dgamma if ctx.needs_input_grad[5] else None, dbeta if ctx.needs_input_grad[6] else None
 
 
-def run_block(blk, src0, src1, training, seed, pool=False):
-    """One ``modules._Block`` in fp32 mode -> (a, pooled)."""
+def run_block(blk, src0, src1, seed, pool=False):
+    """One ``modules._Block`` in fp32 mode -> (a, pooled). Train / eval behaviour follows the block's own norm and
+    dropout modules, as in the bf16 path."""
+    from .modules import _bn_momentum
     cfg = _Cfg()
     cfg.kind = blk.spec.kind
     cfg.slope, cfg.act, cfg.pool = float(blk.slope), bool(blk.fused_act), bool(pool)
-    cfg.drop_p = float(blk.drop_p) if training else 0.0
+    cfg.drop_p = blk.dropout_p()
     cfg.seed = int(seed) & 0x7FFFFFFF
     cfg.eps, cfg.momentum, cfg.running_mean, cfg.running_var = 1e-5, 0.1, None, None
     gamma = beta = None
@@ -164,9 +167,10 @@ def run_block(blk, src0, src1, training, seed, pool=False):
         if blk.norm_kind == "instance":
             cfg.mode = UB_NORM_INSTANCE
         else:
-            cfg.mode = UB_NORM_BATCH_TRAIN if (training or not nm.track_running_stats) else UB_NORM_BATCH_EVAL
+            cfg.mode = UB_NORM_BATCH_TRAIN if (nm.training or not nm.track_running_stats) else UB_NORM_BATCH_EVAL
             cfg.running_mean, cfg.running_var = nm.running_mean, nm.running_var
-            cfg.momentum = float(getattr(nm, "momentum", 0.1) or 0.1)
+            if cfg.mode == UB_NORM_BATCH_TRAIN and nm.running_mean is not None:
+                cfg.momentum = _bn_momentum(nm)
             if cfg.mode == UB_NORM_BATCH_TRAIN and nm.num_batches_tracked is not None:
                 nm.num_batches_tracked.add_(1)
     return _BlockFn.apply(cfg, src0, src1, blk.conv.weight, blk.conv.bias, gamma, beta)
@@ -174,18 +178,16 @@ def run_block(blk, src0, src1, training, seed, pool=False):
 
 def generator_forward(net, x, fresh_seed):
     """``modules._UNetGraph`` on an NCDHW fp32 input -> (B, 6, D, H, W) fp32 (ref:src/model.py:36-39)."""
-    training = net.training
-    head_training = net.head_mod.training if net.head_mod is not None else training
-    base_seed = fresh_seed() if training else 0
+    base_seed = fresh_seed() if any(b.dropout_p() > 0.0 for b in net.blocks) else 0
     lid = [0]
 
-    def run(blk, s0, s1=None, pool=False, tr=training):
+    def run(blk, s0, s1=None, pool=False):
         lid[0] += 1
-        return run_block(blk, s0, s1, tr, base_seed + 7919 * lid[0], pool=pool)
+        return run_block(blk, s0, s1, base_seed + 7919 * lid[0], pool=pool)
 
     cur = x.float()
     if net.head is not None:
-        cur, _ = run(net.head, cur, tr=head_training)
+        cur, _ = run(net.head, cur)
     skips = []
     for lvl, (c0, c1) in enumerate(net.enc):
         t, _ = run(c0, cur)
@@ -204,9 +206,8 @@ def generator_forward(net, x, fresh_seed):
 
 def chain_forward(chain, x, y=None):
     """``modules._Chain`` (Discriminator / a standalone DownSampleConv): cat[x, y] is the first conv's two sources."""
-    training = chain.owner.training
     a, s1 = x.float(), (None if y is None else y.float())
     for blk in chain.blocks:
-        a, _ = run_block(blk, a, s1, training, 0)
+        a, _ = run_block(blk, a, s1, 0)
         s1 = None
     return a.to(x.dtype)

@@ -29,9 +29,9 @@ class _GraphedForward:
     """``gen.forward_packed`` on one batch shape, captured once as a CUDA graph and replayed per batch (one launch
     instead of ~110). Measured on B200 at config 5 (160 x 192 x 160, 27 patches of 64^3): 5.9 ms per volume either
     way -- the eager path is already GPU-bound there -- so it is opt-in, for small patches / slow hosts.
-    Valid while nothing the graph baked in has moved: the parameters and
-    buffers (their storage, in-place version and optimizer generation -- the packed bf16 operands are re-created
-    when those change) and eval mode."""
+    Valid while nothing the graph baked in has moved: the storage of the parameters and buffers (the captured
+    forward re-packs its bf16 weight operands from the live parameter memory on every replay, so weight VALUES may
+    change freely) and eval mode."""
 
     def __init__(self, gen, shape, device):
         self.gen = gen
@@ -49,9 +49,7 @@ class _GraphedForward:
 
     @staticmethod
     def _fingerprint(gen):
-        from .modules import _param_generation
-        return tuple((t.data_ptr(), t._version, _param_generation.get(id(t), 0))
-                     for t in itertools.chain(gen.parameters(), gen.buffers()))
+        return tuple(t.data_ptr() for t in itertools.chain(gen.parameters(), gen.buffers()))
 
     def valid(self):
         return (not self.gen.training) and self.fingerprint == self._fingerprint(self.gen)

@@ -56,64 +56,47 @@ def set_precision(module: nn.Module, precision: str):
 
 
 # ---------------------------------------------------------------------------------------------------
-# packed-weight cache: bf16 operand copies of the fp32 Parameters, refreshed whenever the parameter may
-# have changed:
-#   * in-place autograd-visible writes (manual updates, load_state_dict, foreach optimizers) bump
-#     ``tensor._version``;
-#   * torch's FUSED optimizers (``AdamW(fused=True)``, what GanTrainer and Lightning's configure_optimizers
-#     would use on CUDA) write the parameters from a multi-tensor kernel WITHOUT bumping ``_version``, so
-#     a process-wide optimizer post-step hook stamps every parameter the optimizer owns with a new
-#     generation number;
-#   * ``.data`` / device moves change ``data_ptr``.
+# packed weights: bf16 operand copies of the fp32 Parameters. There is NO cross-call cache: every forward and every
+# backward pass of a network re-packs the weights it is about to use from the LIVE parameter memory, all of them in
+# one multi-tensor launch (``ub_pack_conv_weights_multi``: ~25 us for the generator's 22.6 M weights). The
+# reference reads its fp32 weights afresh in every call; so does this -- optimizer steps (fused or not),
+# ``load_state_dict``, ``p.data.copy_()``, EMA swaps or a foreign kernel writing parameter memory can never leave a
+# stale operand behind. (Round 1 kept a version-keyed cache, which out-of-band ``.data`` writes defeated.)
 # ---------------------------------------------------------------------------------------------------
-_param_generation = {}      # id(param) -> generation of the last optimizer step that owned it
-_generation_counter = [0]
-
-
-def _optimizer_post_step(optimizer, args, kwargs):
-    _generation_counter[0] += 1
-    g = _generation_counter[0]
-    for group in optimizer.param_groups:
-        for p in group["params"]:
-            _param_generation[id(p)] = g
-
-
-from torch.optim.optimizer import register_optimizer_step_post_hook as _register_post_step  # noqa: E402
-
-_register_post_step(_optimizer_post_step)
-
-
 def invalidate_packed_weights(module: nn.Module | None = None):
-    """Force a re-pack of the bf16 weight operands: of ``module``'s parameters, or of everything.
-    Needed only after writing parameter memory behind autograd's and torch.optim's back (a custom
-    kernel, ``cudaMemcpy`` into ``param.data_ptr()``)."""
-    _generation_counter[0] += 1
-    g = _generation_counter[0]
-    if module is None:
-        for k in list(_param_generation):
-            _param_generation[k] = g
-        _PackedWeights.global_floor = g
-    else:
-        for p in module.parameters():
-            _param_generation[id(p)] = g
+    """Kept for API compatibility: operand copies are rebuilt on every pass, there is nothing to invalidate."""
+    return None
 
 
 class _PackedWeights:
-    global_floor = 0
+    """Packed operands of the CURRENT pass of one network: ``refresh`` fills it, ``get`` reads it."""
 
     def __init__(self):
-        self._cache = {}
+        self._cur = {}
+
+    def refresh(self, blocks, direction):
+        """Re-pack the conv weights of ``blocks`` for ``direction`` (0 forward, 1 dgrad) from the live parameters."""
+        todo, seen = [], set()
+        for b in blocks:
+            key = (id(b.conv.weight), b.spec, direction)
+            if key not in seen:
+                seen.add(key)
+                todo.append((b.spec, b.conv.weight, direction))
+        outs = ops.pack_conv_weights_multi(todo)
+        for k in [k for k in self._cur if k[2] == direction]:
+            del self._cur[k]
+        for (spec, w, _), out in zip(todo, outs):
+            self._cur[(id(w), spec, direction)] = out
 
     def get(self, spec, weight, direction):
-        key = (id(weight), direction)
-        ver = (weight._version, weight.data_ptr(), weight.device,
-               max(_param_generation.get(id(weight), 0), _PackedWeights.global_floor))
-        hit = self._cache.get(key)
-        if hit is not None and hit[0] == ver:
-            return hit[1]
-        packed = ops.pack_conv_weights(spec, weight, direction)
-        self._cache[key] = (ver, packed)
-        return packed
+        hit = self._cur.get((id(weight), spec, direction))
+        if hit is None:      # a block run outside a refreshed pass: pack it alone, do not keep it
+            return ops.pack_conv_weights(spec, weight, direction)
+        return hit
+
+    def release(self, direction):
+        for k in [k for k in self._cur if k[2] == direction]:
+            del self._cur[k]
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -122,15 +105,20 @@ class _PackedWeights:
 class _Block:
     """conv -> [InstanceNorm | BatchNorm] -> [Dropout] -> [LeakyReLU] (-> MaxPool3d(2))."""
 
-    def __init__(self, name, spec, conv, norm=None, norm_kind=None, slope=1.0, drop_p=0.0, fused_act=False):
+    def __init__(self, name, spec, conv, norm=None, norm_kind=None, slope=1.0, drop_mod=None, fused_act=False):
         self.name = name
         self.spec = spec
         self.conv = conv            # nn.Conv3d / nn.ConvTranspose3d container
         self.norm = norm            # nn.InstanceNorm3d / nn.BatchNorm3d container or None
         self.norm_kind = norm_kind  # "instance" | "batch" | None
         self.slope = slope
-        self.drop_p = drop_p
+        self.drop_mod = drop_mod    # the block's nn.Dropout (monai ADN "D") or None: p and train/eval are read per call
         self.fused_act = fused_act  # activation applied in the conv epilogue (no norm in between)
+
+    def dropout_p(self):
+        """Dropout probability in effect NOW (0 in eval mode), as ``nn.Dropout.forward`` would use it."""
+        d = self.drop_mod
+        return float(d.p) if (d is not None and d.training) else 0.0
 
     def params(self):
         ps = [self.conv.weight, self.conv.bias]
@@ -147,6 +135,7 @@ class _Block:
 # ---------------------------------------------------------------------------------------------------
 import contextlib as _contextlib
 import threading as _threading
+import weakref as _weakref
 
 _bn_defer = _threading.local()
 
@@ -170,28 +159,33 @@ def apply_deferred_bn(log: list):
 
 
 def prepack_weights(module: nn.Module):
-    """Refresh the packed bf16 weight operands of a Discriminator / Generator now, on the current stream (they are
-    otherwise packed lazily by the first forward / backward that needs them)."""
+    """Pack the forward bf16 weight operands of a Discriminator / Generator now, on the current stream. The next
+    passes re-pack anyway; this exists for callers that want the first pack ordered on a particular stream."""
     if isinstance(module, Discriminator):
         chain = module._net()
-        for blk in chain.blocks:
-            chain.cache.get(blk.spec, blk.conv.weight, 0)
-            chain.cache.get(blk.spec, blk.conv.weight, 1)
+        chain.cache.refresh(chain.blocks, 0)
     elif isinstance(module, Generator):
         net = module._net()
-        for blk in net.blocks:
-            if blk is net.final and _final_is_fusable(net):
-                continue
-            net.cache.get(blk.spec, blk.conv.weight, 0)
-            net.cache.get(blk.spec, blk.conv.weight, 1)
+        net.cache.refresh(net.fwd_blocks(), 0)
 
 
 class _Saved:
     __slots__ = ("src0", "src1", "y", "a", "mean", "rstd", "scale", "shift", "seed", "mode", "in_dhw", "drop_p")
 
 
-def _block_forward(blk: _Block, cache: _PackedWeights, src0, src1, training, seed, pool=False, save=True):
-    """-> (a, pooled, saved)."""
+def _bn_momentum(nm) -> float:
+    """Exponential-average factor of a BatchNorm call in training mode (``momentum=None``: cumulative average)."""
+    if nm.momentum is not None:
+        return float(nm.momentum)
+    seen = int(nm.num_batches_tracked.item()) if nm.num_batches_tracked is not None else 0
+    return 1.0 / float(seen + 1)
+
+
+def _block_forward(blk: _Block, cache: _PackedWeights, src0, src1, seed, pool=False, save=True, defer=False):
+    """-> (a, pooled, saved). ``src0`` may be an ``ops.DeferredAct``. ``defer``: do not materialise this block's
+    activations -- ``a`` is returned as an ``ops.DeferredAct`` for consumers that apply it on their operand path
+    (with ``pool`` only the pooled tensor is written). Train / eval behaviour follows the block's own modules:
+    the norm layer's ``training`` flag (batch vs running statistics) and the dropout layer's ``p`` / ``training``."""
     spec = blk.spec
     w = cache.get(spec, blk.conv.weight, 0)
     n, d, h, wd = spec.in_dims(src0)
@@ -207,24 +201,32 @@ def _block_forward(blk: _Block, cache: _PackedWeights, src0, src1, training, see
         return a, None, sv
     y, stats = ops.conv_fwd(spec, src0, src1, w, blk.conv.bias, want_stats=True)
     nm = blk.norm
+    momentum = 0.1
     if blk.norm_kind == "instance":
         mode = UB_NORM_INSTANCE
         rm = rv = None
     else:
-        mode = UB_NORM_BATCH_TRAIN if (training or not nm.track_running_stats) else UB_NORM_BATCH_EVAL
+        mode = UB_NORM_BATCH_TRAIN if (nm.training or not nm.track_running_stats) else UB_NORM_BATCH_EVAL
         rm, rv = nm.running_mean, nm.running_var
-    momentum = getattr(nm, "momentum", 0.1) or 0.1
-    defer = getattr(_bn_defer, "log", None) if (mode == UB_NORM_BATCH_TRAIN and rm is not None) else None
-    if defer is not None:
+        if mode == UB_NORM_BATCH_TRAIN and rm is not None:
+            momentum = _bn_momentum(nm)
+    defer_log = getattr(_bn_defer, "log", None) if (mode == UB_NORM_BATCH_TRAIN and rm is not None) else None
+    if defer_log is not None:
         rm = rv = None
     elif mode == UB_NORM_BATCH_TRAIN and nm.num_batches_tracked is not None:
         nm.num_batches_tracked.add_(1)
     scale, shift, mean, rstd = ops.norm_finalize(stats, n, od * oh * ow, spec.cop, spec.co, nm.weight, nm.bias,
                                                  nm.eps, mode, momentum, rm, rv)
-    if defer is not None:
-        defer.append((nm, mean, rstd, spec.co, float(n) * od * oh * ow, momentum))
-    drop_p = blk.drop_p if training else 0.0
-    a, pooled = ops.norm_act_fwd(y, scale, shift, blk.slope, drop_p, seed, pool=pool)
+    if defer_log is not None:
+        defer_log.append((nm, mean, rstd, spec.co, float(n) * od * oh * ow, momentum))
+    drop_p = blk.dropout_p()
+    if defer:
+        pooled = None
+        if pool:
+            _, pooled = ops.norm_act_fwd(y, scale, shift, blk.slope, drop_p, seed, pool=True, materialize=False)
+        a = ops.DeferredAct(y, scale, shift, blk.slope, drop_p, seed)
+    else:
+        a, pooled = ops.norm_act_fwd(y, scale, shift, blk.slope, drop_p, seed, pool=pool)
     if save:
         sv.src0, sv.src1, sv.y, sv.a, sv.mode, sv.in_dhw = src0, src1, y, a, mode, (d, h, wd)
         sv.mean, sv.rstd, sv.scale, sv.shift, sv.seed, sv.drop_p = mean, rstd, scale, shift, seed, drop_p
@@ -268,7 +270,10 @@ def _wgrad_async(spec, src0, src1, dy, weight_shape, ready=None):
     with torch.cuda.stream(side):
         dw = ops.conv_wgrad(spec, src0, src1, dy, weight_shape)
     for t in (src0, src1, dy):
-        if t is not None:
+        if isinstance(t, ops.DeferredAct):
+            for u in (t.y, t.scale, t.shift):
+                u.record_stream(side)
+        elif t is not None:
             t.record_stream(side)          # the caching allocator must not recycle them under the side stream
     dw.record_stream(main)
     return dw
@@ -332,20 +337,27 @@ def _block_backward(blk: _Block, cache: _PackedWeights, sv: _Saved, dA, need_w, 
 
 class _InputPackCache:
     """bf16 NDHWC pack of the most recent module input. ``training_step`` feeds the same ``x`` to the
-    generator twice per step (ref:src/model.py:171,184); the second call reuses the pack. The entry is
-    keyed on the tensor object (kept alive, so its storage cannot be recycled under the cache), its
-    in-place version counter and its data pointer."""
+    generator twice per step (ref:src/model.py:171,184); the second call reuses the pack. The entry is keyed on
+    the identity of the tensor object (held WEAKLY: the cache never extends the life of a batch), its in-place
+    version counter and its data pointer; it is dropped as soon as the tensor dies or another input arrives."""
 
     def __init__(self):
-        self._x = self._key = self._packed = None
+        self._ref = self._key = self._packed = None
 
     def get(self, x):
         key = (x.data_ptr(), x._version, tuple(x.shape), x.dtype, x.device)
-        if self._x is x and self._key == key:
+        if self._ref is not None and self._ref() is x and self._key == key:
             return self._packed
         packed = ops.pack_ncdhw(x)
-        self._x, self._key, self._packed = x, key, packed
+        self._key, self._packed = key, packed
+        self._ref = _weakref.ref(x, self._drop)
         return packed
+
+    def _drop(self, _):
+        self._ref = self._key = self._packed = None
+
+    def clear(self):
+        self._drop(None)
 
 
 def _fresh_seed() -> int:
@@ -499,11 +511,11 @@ class _ChainFunction(torch.autograd.Function):
     def forward(ctx, x, y, chain: _Chain, grad_enabled, *params):
         need_bwd = grad_enabled and (x.requires_grad or (y is not None and y.requires_grad) or
                                      any(p.requires_grad for p in params))
-        training = chain.owner.training
+        chain.cache.refresh(chain.blocks, 0)
         a = ops.pack_ncdhw(x, y, s2d=chain.blocks[0].spec.kind == UB_CONV_K4S2P1_S2D)
         saved = []
         for blk in chain.blocks:
-            a, _, sv = _block_forward(blk, chain.cache, a, None, training, 0, save=need_bwd)
+            a, _, sv = _block_forward(blk, chain.cache, a, None, 0, save=need_bwd)
             saved.append(sv)
         out = ops.unpack_ncdhw(a, chain.out_channels)
         ctx.chain, ctx.saved = chain, saved
@@ -515,11 +527,15 @@ class _ChainFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         chain, saved = ctx.chain, ctx.saved
+        if saved is None or any(sv is None for sv in saved):
+            raise RuntimeError("backward called a second time (or without saved activations): the intermediate "
+                               "activations are freed as the first backward consumes them; run the forward again")
         need_x, need_y = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         pneed = {id(p): ctx.needs_input_grad[4 + i] for i, p in enumerate(chain.params)}
         grads = {}
         dA = ops.pack_ncdhw(dout.contiguous().float())
         nblk = len(chain.blocks)
+        chain.cache.refresh(chain.blocks[1:] if not (need_x or need_y) else chain.blocks, 1)
         d0 = None
         for i in range(nblk - 1, -1, -1):
             blk = chain.blocks[i]
@@ -545,12 +561,14 @@ class _UNetGraph:
         self.unet = unet
         self.cache = cache
         self.input_pack = _InputPackCache()
-        p = unet.dropout or 0.0
         f = unet.features
         K3 = UB_CONV_K3S1P1
 
         def cb(name, mod, cin, cout, c1=0):
-            return _Block(name, ops.ConvSpec(K3, cin, cout, c1), mod.conv, mod.adn.N, "instance", slope=0.1, drop_p=p)
+            # the block's own dropout layer (monai ADN "D", absent when dropout == 0) and activation slope are
+            # read at run time, so ``nn.Dropout.p`` / ``train()`` / ``eval()`` changes on the modules take effect
+            return _Block(name, ops.ConvSpec(K3, cin, cout, c1), mod.conv, mod.adn.N, "instance",
+                          slope=float(mod.adn.A.negative_slope), drop_mod=getattr(mod.adn, "D", None))
 
         self.head = head._block("head") if head is not None else None
         self.enc = [(cb("conv_0.conv_0", unet.conv_0.conv_0, unet.in_channels, f[0]),
@@ -570,6 +588,7 @@ class _UNetGraph:
                 cb(f"upcat_{k}.conv_1", up.convs.conv_1, cout, cout),
             ))
         self.final = _Block("final_conv", ops.ConvSpec(UB_CONV_K1, f[5], unet.out_channels), unet.final_conv)
+        self._defer_plans = {}
         self.blocks = ([self.head] if self.head else []) + [b for pair in self.enc for b in pair] + \
                       [b for tri in self.dec for b in tri] + [self.final]
         self.params = []
@@ -583,6 +602,43 @@ class _UNetGraph:
     @property
     def training(self):
         return self.unet.training
+
+    def fwd_blocks(self):
+        """Blocks whose forward runs on a conv kernel (the output head runs fused with the layout change)."""
+        return [b for b in self.blocks if not (b is self.final and _final_is_fusable(self))]
+
+    def defer_plan(self, n, d, h, w, ncdhw_out):
+        """Names of the blocks whose activations stay DEFERRED (never materialised): every consumer of the block
+        must be able to apply the norm + dropout + LeakyReLU on its own operand path -- a 3x3x3 conv on the marching
+        kernels (``ops.deferred_src0_ok``), the pooling pass, the fused output head. UB_DEFER=0 disables it."""
+        key = (n, d, h, w, ncdhw_out)
+        hit = self._defer_plans.get(key)
+        if hit is not None:
+            return hit
+        plan = set()
+        if _DEFER:
+            def ok(consumer, lvl):
+                return ops.deferred_src0_ok(consumer.spec, n, d >> lvl, h >> lvl, w >> lvl)
+
+            nlev = len(self.enc)
+            if self.head is not None and self.head.spec.cop == 32 and ok(self.enc[0][0], 0):
+                plan.add(self.head.name)
+            for lvl, (c0, c1) in enumerate(self.enc):
+                if ok(c1, lvl):
+                    plan.add(c0.name)
+                if lvl < nlev - 1 and ok(self.dec[nlev - 2 - lvl][1], lvl):   # consumers: pooling pass + the skip conv
+                    plan.add(c1.name)
+            for j, (dc, c0, c1) in enumerate(self.dec):
+                lvl = nlev - 2 - j
+                if ok(c1, lvl):
+                    plan.add(c0.name)
+                if j == len(self.dec) - 1 and ncdhw_out and _final_is_fusable(self) and c1.spec.cop == 32:
+                    plan.add(c1.name)
+        self._defer_plans[key] = plan
+        return plan
+
+
+_DEFER = _os_env.environ.get("UB_DEFER", "1") != "0"
 
 
 def _check_unet_dims(d, h, w):
@@ -601,22 +657,24 @@ def _generator_run(net: _UNetGraph, a, need_bwd: bool, ncdhw_out: bool = False):
     None). ``ncdhw_out``: the output head runs fused with the layout change and returns (N,6,D,H,W) fp32
     (module boundary); otherwise the packed (N,D,H,W,32) bf16 tensor (inference keeps it packed). The one
     place that sequences the generator's kernels."""
-    training = net.training
-    head_training = net.head_mod.training if net.head_mod is not None else training
-    base_seed = _fresh_seed() if training else 0
+    any_dropout = any(b.dropout_p() > 0.0 for b in net.blocks)
+    base_seed = _fresh_seed() if any_dropout else 0
     cache = net.cache
+    cache.refresh(net.fwd_blocks(), 0)
+    n, d, h, w, _ = a.shape
+    deferred = net.defer_plan(n, d, h, w, ncdhw_out)
     S = {}          # block name -> saved
     lid = [0]
 
-    def run(blk, s0, s1=None, pool=False, tr=training):
+    def run(blk, s0, s1=None, pool=False):
         lid[0] += 1
-        a_, pooled, sv = _block_forward(blk, cache, s0, s1, tr, (base_seed + 7919 * lid[0]) & 0x7FFFFFFF,
-                                        pool=pool, save=need_bwd)
+        a_, pooled, sv = _block_forward(blk, cache, s0, s1, (base_seed + 7919 * lid[0]) & 0x7FFFFFFF,
+                                        pool=pool, save=need_bwd, defer=blk.name in deferred)
         S[blk.name] = sv
         return a_, pooled
 
     if net.head is not None:
-        a, _ = run(net.head, a, tr=head_training)
+        a, _ = run(net.head, a)
     skips = []
     cur = a
     for lvl, (c0, c1) in enumerate(net.enc):
@@ -660,11 +718,15 @@ class _GeneratorFunction(torch.autograd.Function):
     def backward(ctx, dout):
         net, S = ctx.net, ctx.S
         if S is None:
-            raise RuntimeError("Generator backward called but no activations were saved")
+            raise RuntimeError("Generator backward called a second time (or without saved activations): the "
+                               "intermediate activations are freed as the first backward consumes them; run the "
+                               "forward again")
         cache = net.cache
         pneed = {id(p): ctx.needs_input_grad[3 + i] for i, p in enumerate(net.params)}
         need_x = ctx.needs_input_grad[0]
         grads = {}
+        first_blk = net.head if net.head is not None else net.enc[0][0]
+        cache.refresh([b for b in net.fwd_blocks() if need_x or b is not first_blk], 1)
 
         def bwd(blk, dA, need_in=True, partial=None, producer=None):
             """-> (d_src0, d_src1, partial of ``producer``)."""
@@ -734,10 +796,16 @@ class Generator(nn.Module):
         })
         self._cache = _PackedWeights()
         self._graph = None
+        self._graph_key = None
 
     def _net(self):
-        if self._graph is None:
-            self._graph = _UNetGraph(self.blocks[self.input_modality], self.blocks["unet"], self._cache)
+        # the graph only wires modules together (hyper-parameters are read from them per call); it is rebuilt when
+        # the input modality -- i.e. which head module is wired in -- changes
+        head = self.blocks[self.input_modality]
+        key = (self.input_modality, id(head), id(self.blocks["unet"]))
+        if self._graph is None or self._graph_key != key:
+            self._graph = _UNetGraph(head, self.blocks["unet"], self._cache)
+            self._graph_key = key
         return self._graph
 
     def forward(self, x):
@@ -778,13 +846,16 @@ class Discriminator(nn.Module):
         self.final = nn.Conv3d(512, 1, kernel_size=1)
         self._cache = _PackedWeights()
         self._chain = None
+        self._chain_key = None
 
     def _net(self):
-        if self._chain is None:
+        key = (self.modality, id(self.d1[self.modality]))
+        if self._chain is None or self._chain_key != key:
             blocks = [self.d1[self.modality]._block("d1", s2d_input=True), self.d2._block("d2"), self.d3._block("d3"),
                       self.d4._block("d4"), self.d5._block("d5"),
                       _Block("final", ops.ConvSpec(UB_CONV_K1, 512, 1), self.final)]
             self._chain = _Chain(blocks, self._cache, self, 1)
+            self._chain_key = key
         return self._chain
 
     def forward(self, x, y):

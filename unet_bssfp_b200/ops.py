@@ -2,8 +2,9 @@
 
 torch is plumbing here: device memory (caching allocator), the current CUDA stream, dtype tags.
 Every function enqueues hand-written sm_100a kernels through ``libubssfp.so`` and never falls back
-to a torch / cuDNN op. Internal activations are ``(N, D, H, W, Cp)`` bf16 tensors, ``Cp`` = channel
-count padded to a multiple of 32.
+to a torch / cuDNN op. Internal activations and gradients are ``(N, D, H, W, Cp)`` bf16 tensors, ``Cp`` =
+channel count padded to a multiple of 32; the raw output ``y`` of a conv that feeds a normalisation is a
+``float16`` tensor of the same shape (never a tensor-core operand; see ``include/ub_api.h``).
 """
 from __future__ import annotations
 
@@ -17,7 +18,7 @@ from ._lib import (ConvDesc, UB_CONV_K1, UB_CONV_K3S1P1, UB_CONV_K4S2P1, UB_CONV
                    UB_NORM_BATCH_EVAL, UB_NORM_BATCH_TRAIN, UB_NORM_INSTANCE, UB_NORM_NONE)
 
 __all__ = [
-    "ConvSpec", "pad32", "pack_conv_weights", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv1x1_to_ncdhw", "conv1x1_from_ncdhw_bwd", "pack_ncdhw", "unpack_ncdhw",
+    "ConvSpec", "DeferredAct", "deferred_src0_ok", "pad32", "pack_conv_weights", "pack_conv_weights_multi", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv1x1_to_ncdhw", "conv1x1_from_ncdhw_bwd", "pack_ncdhw", "unpack_ncdhw",
     "pack_patches", "unpack_patch", "paste_patch",
     "norm_finalize", "bn_running_update", "norm_act_fwd", "norm_act_bwd", "maxpool_bwd", "colsum", "l1_fwd", "l1_bwd", "bce_logits",
     "scale_by", "relerr_map_reduce", "dti_scalar_maps", "denorm_to_nifti",
@@ -36,10 +37,54 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _require_dtype(t, dtype, what):
+    if t is not None and t.dtype != dtype:
+        raise RuntimeError(f"{what} must be {dtype}, got {t.dtype}")
+
+
 def _require_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
             raise RuntimeError("unet_bssfp_b200 kernels run on CUDA tensors only (there is no CPU fallback)")
+
+
+@dataclass
+class DeferredAct:
+    """The activations ``LeakyReLU(Dropout(y * scale + shift))`` of a conv -> norm -> dropout -> LeakyReLU block,
+    kept as the block's raw fp16 output and its per-(n, c) constants (``ub_deferred_act``). Consumers apply it on
+    their operand path; the activation tensor itself is never materialised."""
+    y: torch.Tensor          # (N, D, H, W, 32) float16
+    scale: torch.Tensor      # [N][32] fp32
+    shift: torch.Tensor
+    slope: float
+    drop_p: float = 0.0
+    drop_seed: int = 0
+
+    @property
+    def shape(self):
+        return self.y.shape
+
+    @property
+    def device(self):
+        return self.y.device
+
+    @property
+    def is_cuda(self):
+        return self.y.is_cuda
+
+    def struct(self):
+        if self.y.dtype != torch.float16 or self.y.shape[-1] != 32:
+            raise RuntimeError("a deferred activation needs a (N, D, H, W, 32) float16 conv output")
+        return _lib.DeferredAct(self.scale.data_ptr(), self.shift.data_ptr(), self.slope, self.drop_p,
+                                self.drop_seed & 0xFFFFFFFF)
+
+
+def _split_deferred(src):
+    """-> (tensor whose pointer crosses the ABI, byref(ub_deferred_act) | None, keep-alive)."""
+    if isinstance(src, DeferredAct):
+        st = src.struct()
+        return src.y, C.byref(st), st
+    return src, None, None
 
 
 @dataclass(frozen=True)
@@ -98,20 +143,63 @@ def pack_conv_weights(spec: ConvSpec, w: torch.Tensor, direction: int) -> torch.
     return out
 
 
+def deferred_src0_ok(spec: ConvSpec, n, d, h, w) -> bool:
+    """True when source 0 of this convolution may be a ``DeferredAct`` (forward and weight gradient)."""
+    desc = spec.desc(n, d, h, w)
+    r = _lib.load().ub_conv_deferred_src0_ok(C.byref(desc))
+    if r < 0:
+        _lib.check(-1, "ub_conv_deferred_src0_ok")
+    return r == 1
+
+
+def pack_conv_weights_multi(items):
+    """``items``: list of (spec, fp32 weight, direction). One multi-tensor launch (per 32 weights) -> list of packed
+    bf16 tensors, read from the live parameter memory."""
+    if not items:
+        return []
+    lib = _lib.load()
+    table = (_lib.WeightPackItem * len(items))()
+    outs, keep = [], []
+    for k, (spec, w, direction) in enumerate(items):
+        _require_cuda(w)
+        d = spec.desc(1, 2, 2, 2)
+        n = lib.ub_packed_weight_elems(C.byref(d), direction)
+        if n < 0:
+            _lib.check(-1, "ub_packed_weight_elems")
+        w32 = w.detach()
+        if w32.dtype != torch.float32 or not w32.is_contiguous():
+            w32 = w32.contiguous().float()
+        keep.append(w32)
+        out = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+        outs.append(out)
+        table[k].desc = d
+        table[k].dir = direction
+        table[k].w = w32.data_ptr()
+        table[k].packed = out.data_ptr()
+    _lib.check(lib.ub_pack_conv_weights_multi(table, len(items), _stream()), "ub_pack_conv_weights_multi")
+    return outs
+
+
 def conv_fwd(spec: ConvSpec, src0, src1, w_packed, bias, act=0, slope=0.0, want_stats=False):
-    """-> (out (N,Do,Ho,Wo,cop) bf16, stats_partial [tiles][2][cop] fp32 | None)."""
+    """-> (out (N,Do,Ho,Wo,cop), stats_partial [tiles][2][cop] fp32 | None). ``out`` is bf16, or -- with
+    ``want_stats``, where it is the raw input ``y`` of a normalisation -- float16. ``src0`` may be a
+    ``DeferredAct`` where ``deferred_src0_ok``."""
     _require_cuda(src0, src1, w_packed, bias)
     lib = _lib.load()
     n, d, h, w = spec.in_dims(src0)
     desc = spec.desc(n, d, h, w)
     od, oh, ow = spec.out_dims(d, h, w)
-    out = torch.empty((n, od, oh, ow, spec.cop), dtype=torch.bfloat16, device=src0.device)
+    s0, act0, _keep = _split_deferred(src0)
+    if act0 is None:
+        _require_dtype(s0, torch.bfloat16, "conv_fwd: src0")
+    _require_dtype(src1, torch.bfloat16, "conv_fwd: src1")
+    out = torch.empty((n, od, oh, ow, spec.cop), dtype=torch.float16 if want_stats else torch.bfloat16, device=s0.device)
     stats = None
     if want_stats:
         tiles = lib.ub_conv_num_tiles(C.byref(desc))
-        stats = torch.empty((tiles, 2, spec.cop), dtype=torch.float32, device=src0.device)
-    _lib.check(lib.ub_conv_fwd(C.byref(desc), _p(src0), _p(src1), _p(w_packed), _p(bias), act, slope, _p(out),
-                               _p(stats), _stream()), "ub_conv_fwd")
+        stats = torch.empty((tiles, 2, spec.cop), dtype=torch.float32, device=s0.device)
+    _lib.check(lib.ub_conv_fwd(C.byref(desc), _p(s0), _p(src1), _p(w_packed), _p(bias), act, slope, _p(out),
+                               _p(stats), act0, _stream()), "ub_conv_fwd")
     return out, stats
 
 
@@ -171,23 +259,30 @@ def conv_wgrad(spec: ConvSpec, src0, src1, dy, weight_shape):
     nbytes = lib.ub_conv_wgrad_workspace_bytes(C.byref(desc))
     if nbytes < 0:
         _lib.check(-1, "ub_conv_wgrad_workspace_bytes")
+    s0, act0, _keep = _split_deferred(src0)
+    if act0 is None:
+        _require_dtype(s0, torch.bfloat16, "conv_wgrad: src0")
+    _require_dtype(dy, torch.bfloat16, "conv_wgrad: dy")
     ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dy.device)
     dw = torch.zeros(weight_shape, dtype=torch.float32, device=dy.device)
-    _lib.check(lib.ub_conv_wgrad(C.byref(desc), _p(src0), _p(src1), _p(dy), _p(ws), _p(dw), _stream()), "ub_conv_wgrad")
+    _lib.check(lib.ub_conv_wgrad(C.byref(desc), _p(s0), _p(src1), _p(dy), _p(ws), _p(dw), act0, _stream()),
+               "ub_conv_wgrad")
     return dw
 
 
 def conv1x1_to_ncdhw(u, weight, bias):
-    """Generator output head: u (N,D,H,W,32) bf16, weight (co, ci, 1,1,1) fp32, bias (co) -> (N,co,D,H,W) fp32."""
+    """Generator output head: u (N,D,H,W,32) bf16 (or a ``DeferredAct``), weight (co, ci, 1,1,1) fp32, bias (co)
+    -> (N,co,D,H,W) fp32."""
     _require_cuda(u, weight, bias)
     lib = _lib.load()
+    u, act0, _keep = _split_deferred(u)
     n, d, h, w, cp = u.shape
     co, ci = weight.shape[0], weight.shape[1]
     ws = torch.empty(lib.ub_conv1x1_workspace_bytes() // 4, dtype=torch.float32, device=u.device)
     out = torch.empty((n, co, d, h, w), dtype=torch.float32, device=u.device)
     wt = weight.detach().contiguous().float()
-    _lib.check(lib.ub_conv1x1_to_ncdhw(_p(u), cp, _p(wt), ci, _p(bias), co, n, d * h * w, _p(ws), _p(out), _stream()),
-               "ub_conv1x1_to_ncdhw")
+    _lib.check(lib.ub_conv1x1_to_ncdhw(_p(u), cp, _p(wt), ci, _p(bias), co, n, d * h * w, _p(ws), _p(out), act0,
+                                       _stream()), "ub_conv1x1_to_ncdhw")
     return out
 
 
@@ -195,16 +290,17 @@ def conv1x1_from_ncdhw_bwd(dout, u, weight, need_input=True, need_params=True):
     """Backward of ``conv1x1_to_ncdhw`` in one pass: -> (du (N,D,H,W,32) bf16 | None, dweight | None, dbias | None)."""
     _require_cuda(dout, u, weight)
     lib = _lib.load()
+    u, act0, _keep = _split_deferred(u)
     n, d, h, w, cp = u.shape
     co, ci = weight.shape[0], weight.shape[1]
     dout = dout.contiguous().float()
     ws = torch.empty(lib.ub_conv1x1_workspace_bytes() // 4, dtype=torch.float32, device=u.device)
-    du = torch.empty_like(u) if need_input else None
+    du = torch.empty(u.shape, dtype=torch.bfloat16, device=u.device) if need_input else None
     dw = torch.empty(tuple(weight.shape), dtype=torch.float32, device=u.device) if need_params else None
     db = torch.empty(co, dtype=torch.float32, device=u.device) if need_params else None
     wt = weight.detach().contiguous().float()
     _lib.check(lib.ub_conv1x1_from_ncdhw_bwd(_p(dout), co, _p(u), cp, _p(wt), ci, n, d * h * w, _p(ws), _p(du), _p(dw),
-                                             _p(db), _stream()), "ub_conv1x1_from_ncdhw_bwd")
+                                             _p(db), act0, _stream()), "ub_conv1x1_from_ncdhw_bwd")
     return du, dw, db
 
 
@@ -329,12 +425,16 @@ def bn_running_update(mean, rstd, c, count, eps, momentum, running_mean, running
                                                 _p(running_var), _stream()), "ub_bn_running_update")
 
 
-def norm_act_fwd(y, scale, shift, slope, drop_p=0.0, drop_seed=0, pool=False):
-    """-> (a, pooled|None)."""
+def norm_act_fwd(y, scale, shift, slope, drop_p=0.0, drop_seed=0, pool=False, materialize=True):
+    """y (float16) -> (a bf16 | None, pooled bf16 | None). ``materialize=False`` (needs ``pool``): only the pooled
+    tensor is written, the activations stay deferred."""
     lib = _lib.load()
+    _require_dtype(y, torch.float16, "norm_act_fwd: y")
+    if not materialize and not pool:
+        raise RuntimeError("norm_act_fwd: nothing to compute (materialize=False without pool)")
     n, d, h, w, cp = y.shape
-    a = torch.empty_like(y)
-    pooled = torch.empty((n, d // 2, h // 2, w // 2, cp), dtype=y.dtype, device=y.device) if pool else None
+    a = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device) if materialize else None
+    pooled = torch.empty((n, d // 2, h // 2, w // 2, cp), dtype=torch.bfloat16, device=y.device) if pool else None
     _lib.check(lib.ub_norm_act_fwd(_p(y), _p(scale), _p(shift), slope, drop_p, drop_seed & 0xFFFFFFFF, n, d, h, w, cp,
                                    _p(a), _p(pooled), _stream()), "ub_norm_act_fwd")
     return a, pooled
@@ -346,6 +446,8 @@ def norm_act_bwd(dA, a, y, mode, mean, rstd, scale, slope, drop_p, drop_seed, c,
     recomputed from ``y`` and ``a`` is not read (may be None). ``partial``: reduction records already
     accumulated by ``conv_dgrad(..., fuse=)`` -- the reduction pass is skipped."""
     lib = _lib.load()
+    _require_dtype(dA, torch.bfloat16, "norm_act_bwd: dA")
+    _require_dtype(y, torch.float16, "norm_act_bwd: y")
     n, d, h, w, cp = dA.shape
     voxels = d * h * w
     dev = dA.device
@@ -367,14 +469,16 @@ def norm_act_bwd(dA, a, y, mode, mean, rstd, scale, slope, drop_p, drop_seed, c,
 
 
 def maxpool_bwd(a, dP, dA=None):
-    """Route dP to the arg-max voxels of ``a``; accumulates onto ``dA`` if given, else creates it."""
+    """Route dP to the arg-max voxels of ``a`` (bf16 tensor or ``DeferredAct``); accumulates onto ``dA`` if given,
+    else creates it."""
     lib = _lib.load()
+    a, act0, _keep = _split_deferred(a)
     n, d, h, w, cp = a.shape
     acc = 1
     if dA is None:
-        dA = torch.empty_like(a)
+        dA = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
         acc = 0
-    _lib.check(lib.ub_maxpool_bwd(_p(a), _p(dP), _p(dA), acc, n, d, h, w, cp, _stream()), "ub_maxpool_bwd")
+    _lib.check(lib.ub_maxpool_bwd(_p(a), _p(dP), _p(dA), acc, n, d, h, w, cp, act0, _stream()), "ub_maxpool_bwd")
     return dA
 
 
