@@ -99,11 +99,11 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_run(steps, warmup, size=64, modality="bssfp"):
+def cpu_reference_run(steps, warmup, size=64, modality="bssfp", threads=None):
     """The reference arithmetic (oracle restatement of ref:src/model.py) on the host cores: full GAN
     step at batch 1, size^3 (a bounded sample of the workload). -> (voxels/s, ms/step, cores)."""
     from oracle import model_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     torch.manual_seed(0)
     og, od = O.Generator(modality), O.Discriminator(modality)
     opt_g, opt_d = O.make_optimizers(og, od)
@@ -117,6 +117,47 @@ def cpu_reference_run(steps, warmup, size=64, modality="bssfp"):
         O.gan_step(og, od, opt_g, opt_d, x, y)
     dt = (time.perf_counter() - t0) / max(steps, 1)
     return size ** 3 / dt, dt * 1e3, torch.get_num_threads()
+
+
+def cpu_config1_run(steps, warmup, threads=None, size=64):
+    """BASELINE config 1: U-Net generator forward + backward on one 64^3 bSSFP patch, batch 1, fp32, train mode,
+    L1 loss (the oracle restatement of ref:src/model.py:15-39,126). -> (voxels/s, ms, cores)."""
+    from oracle import model_oracle as O
+    torch.set_num_threads(threads or os.cpu_count() or 1)
+    torch.manual_seed(0)
+    og = O.Generator("bssfp").train()
+    torch.manual_seed(1234)
+    x, y = torch.rand(1, 24, size, size, size), torch.rand(1, 6, size, size, size)
+
+    def one():
+        for p in og.parameters():
+            p.grad = None
+        torch.nn.functional.l1_loss(og(x), y).backward()
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return size ** 3 / dt, dt * 1e3, torch.get_num_threads()
+
+
+def cpu_eval_run(shape=(160, 192, 160)):
+    """NumPy restatement of ref:src/eval.py:154-166,217-258 on one float64 volume of config 5's size, single
+    process (relative-error map + masked, probseg-weighted ROI means). -> (voxels/s, ms)."""
+    import numpy as np
+    from oracle import eval_oracle as E
+    rng = np.random.default_rng(0)
+    pred = rng.random(shape + (6,))
+    tgt = rng.random(shape + (6,)) * 0.95 + 0.05
+    mask = (rng.random(shape) > 0.3).astype(np.uint8)
+    probseg = rng.random(shape + (3,))
+    t0 = time.perf_counter()
+    diff = E.rel_error_map(pred, tgt)
+    E.roi_error_avg(diff, mask, probseg)
+    dt = time.perf_counter() - t0
+    return shape[0] * shape[1] * shape[2] / dt, dt * 1e3
 
 
 def run_reference(args):
@@ -138,38 +179,130 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def dominant_kernel_roofline(dev, batch, size, peaks, iters=5):
-    """Time the dominant launch in isolation: igemm_fwd_kernel on upcat_1.conv_0 (skip-concat
-    [32 | 64] -> 32 channels, 3x3x3) at the bench shape; 29.9 % of the generator FLOPs."""
+TENSOR_CLASSES = ("igemm_fwd_kernel", "igemm_march_kernel", "wgrad_march_kernel", "igemm_wgrad_kernel")
+
+
+def roofline_table(trainer, batches, peaks, flop_step, ms_step, profile_steps=2):
+    """Per-kernel-class roofline of the step, measured IN THIS RUN: ``profile_steps`` further steps run under the
+    per-op CUDA-event profiler (unet_bssfp_b200/profiler.py; serial times, weight gradients on the main stream).
+    Tensor-core classes: algorithmic conv FLOPs / time against the SUSTAINED bf16 peak (kernels timed inside a long
+    step); memory-bound ops: tensor bytes (inputs once + outputs once) / time against the measured HBM copy peak.
+    ``kernel`` names the class with the largest share of the step time."""
+    from unet_bssfp_b200 import profiler
+    with profiler.profile() as records:
+        for i in range(profile_steps):
+            trainer.step(*batches[i % len(batches)])
+        torch.cuda.synchronize()
+    per_class, per_op = profiler.summarize(records, steps=profile_steps)
+    covered = sum(v["ms"] for v in per_class.values())
+    classes = {}
+    for cls, v in sorted(per_class.items(), key=lambda kv: -kv[1]["ms"]):
+        if v["ms"] < 0.05:
+            continue
+        e = {"ms_per_step": round(v["ms"], 3), "share": round(v["ms"] / covered, 4), "calls_per_step": v["calls"]}
+        if cls in TENSOR_CLASSES:
+            tf = v["flops"] / (v["ms"] * 1e-3) / 1e12
+            e.update({"bound": "tensor", "flops": v["flops"], "achieved": round(tf, 1), "unit": "TFLOP/s",
+                      "frac": round(tf / peaks["bf16_sustained"], 4)})
+        else:
+            gb = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+            e.update({"bound": "hbm", "bytes": v["bytes"], "achieved": round(gb, 1), "unit": "GB/s",
+                      "frac": round(gb / peaks["hbm"], 4)})
+        classes[cls] = e
+    dom = max(classes, key=lambda c: classes[c]["ms_per_step"])
+    # the longest single launch of the dominant class
+    tops = [(k, v) for k, v in per_op.items() if k[1] == dom]
+    (op, _, label), tv = max(tops, key=lambda kv: kv[1]["ms"] / kv[1]["calls"])
+    top_ms = tv["ms"] / tv["calls"]
+    top = {"op": op, "shape": label, "ms_per_launch": round(top_ms, 4)}
+    if tv["flops"]:
+        top["achieved"] = round(tv["flops"] / tv["calls"] / (top_ms * 1e-3) / 1e12, 1)
+        top["unit"] = "TFLOP/s"
+    d = classes[dom]
+    step_tf = flop_step / (ms_step * 1e-3) / 1e12
+    conv_ms = sum(classes[c]["ms_per_step"] for c in classes if c in TENSOR_CLASSES)
+    conv_fl = sum(classes[c]["flops"] for c in classes if c in TENSOR_CLASSES)
+    return {
+        "bound": d["bound"], "kernel": dom + " (time-dominant kernel class of the step)",
+        "achieved": d["achieved"], "peak": peaks["bf16_sustained"] if d["bound"] == "tensor" else peaks["hbm"],
+        "peak_src": peaks["src"] + (" (sustained: kernels timed inside a long step)" if d["bound"] == "tensor" else ""),
+        "unit": d["unit"], "frac": d["frac"], "share_of_step": d["share"], "longest_launch": top,
+        "traffic": None,
+        "traffic_note": "per-launch DRAM traffic is in the committed ncu summaries (profiles/r02_*_ncu_summary.txt)",
+        "how": f"{profile_steps} profiled steps, CUDA events around every op on its launching stream",
+        "profiled_ms_per_step_serial": round(covered, 3),
+        "classes": classes,
+        "all_conv_kernels": {"ms_per_step": round(conv_ms, 3), "achieved": round(conv_fl / (conv_ms * 1e-3) / 1e12, 1),
+                             "unit": "TFLOP/s", "frac_of_sustained": round(conv_fl / (conv_ms * 1e-3) / 1e12 / peaks["bf16_sustained"], 4)},
+        "step_tflops": step_tf, "step_frac_of_burst_peak": step_tf / peaks["bf16_burst"],
+        "step_frac_of_sustained_peak": step_tf / peaks["bf16_sustained"],
+        "flop_per_step": flop_step,
+    }
+
+
+def secondary_configs(dev, skip4=False):
+    """BASELINE configs 4 and 5 as secondary, driver-run numbers (N = 1 only; a few steps each)."""
     import unet_bssfp_b200 as ub
-    ops = ub.ops
-    spec = ops.ConvSpec(0, 32, 32, 64)
-    g = torch.Generator(device=dev).manual_seed(1)
-    s0 = torch.randn((batch, size, size, size, 32), device=dev, generator=g).to(torch.bfloat16)
-    s1 = torch.randn((batch, size, size, size, 64), device=dev, generator=g).to(torch.bfloat16)
-    w = torch.randn((32, 96, 3, 3, 3), device=dev, generator=g) * 0.02
-    wpk = ops.pack_conv_weights(spec, w, 0)
-    bias = torch.zeros(32, device=dev)
-    for _ in range(2):
-        ops.conv_fwd(spec, s0, s1, wpk, bias, want_stats=True)
-    torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
-    ev[0].record()
-    for i in range(iters):
-        ops.conv_fwd(spec, s0, s1, wpk, bias, want_stats=True)
-        ev[i + 1].record()
-    torch.cuda.synchronize()
-    ms = statistics.median(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
-    flops = 2.0 * batch * size ** 3 * 27 * 96 * 32
-    ach = flops / (ms * 1e-3) / 1e12
-    # DRAM traffic of this launch from the committed `ncu --set full` capture of the CTA-pair kernel
-    # (profiles/r01w_march96_pair_ncu_summary.txt): dram__bytes_read.sum 3.267 GB + dram__bytes_write.sum 1.053 GB;
-    # algorithmic bytes = both sources once + the output once = (32 + 64 + 32) ch * 2 B * 8 * 128^3 voxels = 4.295 GB
-    traffic = 3.267318e9 + 1.052962e9 if (batch, size) == (8, 128) else None
-    return {"bound": "tensor", "kernel": "igemm_march_kernel[upcat_1.conv_0 fwd, cat[32|64]->32 k3, 8x128^3]", "achieved": ach,
-            "peak": peaks["bf16_burst"], "peak_src": peaks["src"] + " (burst: kernel timed alone)", "unit": "TFLOP/s",
-            "frac": ach / peaks["bf16_burst"], "ms_per_launch": ms, "flops_per_launch": flops, "traffic": traffic,
-            "traffic_unit": "bytes per launch (ncu dram read + write)", "algorithmic_bytes": 2.0 * batch * size ** 3 * 128}
+    from unet_bssfp_b200.train_step import GanTrainer
+    out = {}
+    if not skip4:
+        try:
+            torch.manual_seed(0)
+            g, d = ub.Generator("t1w").to(dev), ub.Discriminator("t1w").to(dev)
+            tr = GanTrainer(g, d)
+            B, S = 16, 128
+            torch.manual_seed(99)
+            bs = [(torch.rand(B, 6, S, S, S, device=dev), torch.rand(B, 6, S, S, S, device=dev)) for _ in range(2)]
+            for i in range(3):
+                tr.step(*bs[i % 2])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            K = 6
+            e0.record()
+            for i in range(K):
+                tr.step(*bs[i % 2])
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / K
+            fl = FLOP_PER_VOXEL["t1w"] * B * S ** 3
+            out["config4_t1w_batch16_128"] = {"ms_per_step": ms, "value": B * S ** 3 / (ms * 1e-3), "unit": UNIT, "steps": K,
+                                              "warmup": 3, "step_tflops": fl / (ms * 1e-3) / 1e12,
+                                              "workload": "full GAN step, t1w (6 input channels, D sees 12), batch 16 x 128^3"}
+            del tr, g, d, bs
+            torch.cuda.empty_cache()
+        except Exception as ex:   # reported, never fatal for the headline line
+            out["config4_t1w_batch16_128"] = {"error": repr(ex)[:300]}
+    try:
+        shape = (160, 192, 160)
+        torch.manual_seed(0)
+        g = ub.Generator("bssfp").to(dev).eval()
+        vol = torch.rand((24,) + shape, device=dev)
+        tgt = torch.rand((6,) + shape, device=dev) * 0.95 + 0.05
+        mask = (torch.rand(shape, device=dev) > 0.3).to(torch.uint8)
+        probseg = torch.rand(shape + (3,), device=dev)
+
+        def timed(fn, iters=5):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                r = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters, r
+
+        vox = shape[0] * shape[1] * shape[2]
+        ms_p, pred = timed(lambda: ub.inference.predict_volume(g, vol, patch=64, batch=9, use_graph=False))
+        ms_r, _ = timed(lambda: ub.inference.relative_error(pred, tgt, mask, probseg))
+        ms_m, _ = timed(lambda: ub.ops.dti_scalar_maps(pred.permute(1, 2, 3, 0).contiguous()))
+        out["config5_inference_160x192x160"] = {
+            "predict_volume_ms": ms_p, "value": vox / (ms_p * 1e-3), "unit": "output voxels/s", "patches": 27, "patch": 64,
+            "relative_error_ms": ms_r, "dti_scalar_maps_ms": ms_m,
+            "workload": "sliding-window inference (27 patches of 64^3, later patch wins) + relative-error map and ROI means + DTI maps"}
+    except Exception as ex:
+        out["config5_inference_160x192x160"] = {"error": repr(ex)[:300]}
+    return out
 
 
 def main():
@@ -184,6 +317,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config-4 / config-5 secondary numbers")
+    ap.add_argument("--e2e-x-dtype", default="bf16", choices=["bf16", "fp32"],
+                    help="host dtype of the conditioning input x in the end-to-end loop (bf16: same packed bits, "
+                         "half the H2D bytes of x)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -213,16 +350,19 @@ def main():
     # one process per GPU: stage the pinned input batch on the NUMA node of this rank's GPU (before allocating it)
     numa_cpus = hostmem.bind_to_gpu(local) if (world > 1 and os.environ.get("UB_BIND_NUMA", "1") != "0") else None
 
-    torch.manual_seed(0)  # same initial weights on every rank (DDP would broadcast rank 0's)
+    torch.manual_seed(1000 + rank)    # DIFFERENT initial weights per rank: GanTrainer broadcasts rank 0's (as DDP does)
     gen = ub.Generator(args.modality).to(dev)
     dis = ub.Discriminator(args.modality).to(dev)
     trainer = GanTrainer(gen, dis)
     cin = 24 if args.modality in ("bssfp", "pc-bssfp") else 6
     B, S = args.batch, args.size
-    torch.manual_seed(1234 + rank)
-    x_host = torch.rand(B, cin, S, S, S).pin_memory()
-    y_host = torch.rand(B, 6, S, S, S).pin_memory()
-    x, y = x_host.to(dev), y_host.to(dev)
+    # two different synthetic batches per rank, alternated step by step: every timed step packs a NEW input, as a
+    # real loader would deliver one (no cross-step reuse of the packed input)
+    host = []
+    for k in range(2):
+        torch.manual_seed(1234 + 7919 * k + rank)
+        host.append((torch.rand(B, cin, S, S, S).pin_memory(), torch.rand(B, 6, S, S, S).pin_memory()))
+    batches = [(xh.to(dev), yh.to(dev)) for xh, yh in host]
     voxels_per_step = B * S ** 3 * world
 
     def barrier():
@@ -231,8 +371,8 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput ("value") ----------------
-    for _ in range(args.warmup):
-        trainer.step(x, y)
+    for i in range(args.warmup):
+        trainer.step(*batches[i % 2])
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -240,8 +380,8 @@ def main():
     n0 = lib.ub_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        g_loss, d_loss = trainer.step(x, y)
+    for i in range(args.steps):
+        g_loss, d_loss = trainer.step(*batches[i % 2])
     e1.record()
     barrier()
     launches = lib.ub_launch_count() - n0
@@ -256,7 +396,10 @@ def main():
     e2e = None
     if not args.no_e2e:
         copy_stream = torch.cuda.Stream(device=dev)
-        bufs = [(torch.empty_like(x), torch.empty_like(y)) for _ in range(2)]
+        xdt = torch.bfloat16 if args.e2e_x_dtype == "bf16" else torch.float32
+        # the loader's host batches: x in its transport dtype (bf16 packs to the same bits as fp32), y in fp32
+        host_e = [(xh.to(xdt).pin_memory(), yh) for xh, yh in host]
+        bufs = [(torch.empty(batches[0][0].shape, dtype=xdt, device=dev), torch.empty_like(batches[0][1])) for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
         done = [torch.cuda.Event() for _ in range(2)]
         loss_host = torch.zeros(2, 2).pin_memory()
@@ -264,8 +407,8 @@ def main():
         def prefetch(i):
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(done[i % 2])
-                bufs[i % 2][0].copy_(x_host, non_blocking=True)
-                bufs[i % 2][1].copy_(y_host, non_blocking=True)
+                bufs[i % 2][0].copy_(host_e[i % 2][0], non_blocking=True)
+                bufs[i % 2][1].copy_(host_e[i % 2][1], non_blocking=True)
                 ready[i % 2].record(copy_stream)
 
         def e2e_loop(nsteps):
@@ -283,9 +426,8 @@ def main():
             torch.cuda.synchronize()
             return float(loss_host[(nsteps - 1) % 2, 0])
 
-        e2e_loop(1)
+        e2e_loop(2)
         barrier()
-        t0 = time.perf_counter()
         e0.record()
         e2e_loop(args.steps)
         e1.record()
@@ -294,23 +436,51 @@ def main():
         if world > 1:
             dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
         ms_e_step = ms_e.item() / args.steps
+        h2d = int(host_e[0][0].numel() * host_e[0][0].element_size() + host_e[0][1].numel() * 4)
         e2e = {"value": voxels_per_step / (ms_e_step * 1e-3), "unit": UNIT, "ms_per_step": ms_e_step,
-               "h2d_bytes_per_step": int((x_host.numel() + y_host.numel()) * 4), "d2h_bytes_per_step": 8,
-               "how": "pinned host batch -> double-buffered H2D on a copy stream -> GanTrainer.step -> losses D2H",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+               "x_host_dtype": args.e2e_x_dtype, "y_host_dtype": "fp32",
+               "how": "pinned host batch (a new one every step) -> double-buffered H2D on a copy stream -> "
+                      "GanTrainer.step (packs the input) -> losses D2H",
                "numa_bound_cpus": len(numa_cpus) if numa_cpus else None}
 
-    roof = cpu = None
-    if rank == 0:
-        roof = dominant_kernel_roofline(dev, B, S, peaks) if not args.no_roofline else {"bound": "tensor"}
-        flop_step = FLOP_PER_VOXEL[args.modality] * B * S ** 3
-        roof["step_tflops"] = flop_step / (ms_step * 1e-3) / 1e12
-        roof["step_frac_of_sustained_peak"] = roof["step_tflops"] / peaks["bf16_sustained"]
-        if not args.no_cpu_baseline and world == 1:   # reported at N = 1 only (torchrun pins OMP_NUM_THREADS=1)
+    roof = cpu = secondary = None
+    flop_step = FLOP_PER_VOXEL[args.modality] * B * S ** 3
+    if rank == 0 and not args.no_roofline:
+        roof = roofline_table(trainer, batches, peaks, flop_step, ms_step)
+    elif world > 1 and not args.no_roofline:
+        # the other ranks run the same profiled steps (the all-reduce inside trainer.step is collective)
+        for i in range(2):
+            trainer.step(*batches[i % 2])
+        torch.cuda.synchronize()
+    if rank == 0 and roof is None:
+        step_tf = flop_step / (ms_step * 1e-3) / 1e12
+        roof = {"bound": "tensor", "step_tflops": step_tf, "step_frac_of_burst_peak": step_tf / peaks["bf16_burst"],
+                "step_frac_of_sustained_peak": step_tf / peaks["bf16_sustained"]}
+    if world > 1:
+        dist.barrier()
+    if rank == 0 and world == 1:
+        del trainer, gen, dis, batches
+        torch.cuda.empty_cache()
+        if not args.no_secondary:
+            secondary = secondary_configs(dev)
+        if not args.no_cpu_baseline:   # reported at N = 1 only (torchrun pins OMP_NUM_THREADS=1)
             v, ms, cores = cpu_reference_run(steps=2, warmup=1, size=64, modality=args.modality)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
                    "sample": f"full GAN step, batch 1 x 64^3 ({args.modality}), fp32 torch CPU oracle, 2 timed steps after 1 warm-up"}
-    if world > 1:
-        dist.barrier()
+            legs = {}
+            v1, ms1, _ = cpu_reference_run(steps=1, warmup=1, size=64, modality=args.modality, threads=1)
+            legs["full_step_1_thread"] = {"value": v1, "unit": UNIT, "ms_per_step": ms1, "cores": 1,
+                                          "note": "the reference's job script exports OMP_NUM_THREADS=1 (ref:run.sh:51)"}
+            vc, msc, cc = cpu_config1_run(steps=2, warmup=1)
+            legs["config1_G_fwd_bwd_64"] = {"value": vc, "unit": "voxels/s", "ms": msc, "cores": cc,
+                                            "sample": "BASELINE config 1: generator fwd + bwd, 1 x 24 x 64^3, L1 loss, train mode"}
+            vc1, msc1, _ = cpu_config1_run(steps=1, warmup=1, threads=1)
+            legs["config1_G_fwd_bwd_64_1_thread"] = {"value": vc1, "unit": "voxels/s", "ms": msc1, "cores": 1}
+            ve, mse = cpu_eval_run()
+            legs["eval_relerr_roi_numpy_160x192x160"] = {"value": ve, "unit": "voxels/s", "ms": mse, "cores": 1,
+                                                         "sample": "NumPy restatement of ref:eval.py:154-166,217-258, float64, single process"}
+            cpu["legs"] = legs
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -319,8 +489,11 @@ def main():
             "config": {"workload": f"full GAN step (U-Net G + PatchGAN D, L1+adversarial, 2x AdamW), {args.modality}, "
                                    f"batch {B} x {S}^3 per GPU", "global_batch": B * world, "patch": S,
                        "parallelism": f"dp{world}", "l2": "inputs larger than L2 (activations are GBs per step)",
+                       "input_batches": "two synthetic batches alternated: every step packs a new input",
+                       "intermediates": "bf16 operands, fp32 accumulate; raw conv outputs feeding a norm stored as fp16",
                        "losses": [float(g_loss), float(d_loss)]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "secondary": secondary,
         }
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())

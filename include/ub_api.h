@@ -52,6 +52,8 @@ typedef struct {
 
 /* number of bf16 elements of a packed weight buffer; dir 0 = forward, 1 = dgrad */
 long long ub_packed_weight_elems(const ub_conv_desc* d, int dir);
+/* OR-ed into `dir` of the pack calls: the K columns of source 0 are written as fp16 (see ub_deferred_act.f16_operand) */
+#define UB_PACK_F16_SRC0 2
 /* torch-layout fp32 weights ([co][ci][k..] or [ci][co][2][2][2] for the transposed conv) -> packed bf16 */
 int ub_pack_conv_weights(const ub_conv_desc* d, int dir, const float* w, void* packed, void* stream);
 /* the same for `count` weights in as few launches as the pointer table allows (`items` is a HOST array; only kind
@@ -79,6 +81,11 @@ typedef struct {
   const float* shift;      /* [n][32] */
   float slope, drop_p;
   uint32_t drop_seed;
+  int f16_operand;         /* ub_conv_fwd only: evaluate the activations in packed fp16 arithmetic and multiply them
+                              as an fp16 x fp16 tensor-core operand (three instructions per element pair instead of the
+                              fp32 path's conversions; relative error ~3 * 2^-12, below bf16 rounding). The weights
+                              must be packed with UB_PACK_F16_SRC0. For passes without a backward (inference, the
+                              generator forward of the discriminator phase): a backward would need the bf16 form. */
 } ub_deferred_act;
 /* 1 when source 0 of this convolution may be a deferred activation in ub_conv_fwd AND ub_conv_wgrad (3x3x3 convs
  * with 32 output channels and a 32-channel source 0: the full-resolution layers), else 0 */
@@ -113,6 +120,9 @@ typedef struct {
 int ub_conv_dgrad_fuse_records(const ub_conv_desc* d);   /* records (n-major, records / n per sample); 0 = unsupported */
 int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const void* w_packed_dgrad, void* dsrc0,
                         void* dsrc1, const ub_norm_bwd_fuse* fuse, void* stream);
+/* which kernel serves (desc, dir), dir 0 forward / 1 dgrad / 2 wgrad: 0 igemm_fwd_kernel (generic tap-table
+ * implicit GEMM), 1 igemm_march_kernel, 2 wgrad_march_kernel, 3 igemm_wgrad_kernel (profiling / roofline tables) */
+int ub_conv_kernel_class(const ub_conv_desc* d, int dir);
 /* dw (fp32, torch layout) = sum_voxels src (x) dy; workspace holds the split-K partials */
 long long ub_conv_wgrad_workspace_bytes(const ub_conv_desc* d);
 /* src0_act != NULL: src0 points at the producer's y (fp16) and is a deferred activation (ub_conv_deferred_src0_ok) */
@@ -121,13 +131,15 @@ int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void* src1, con
 
 /* ---- layout at the module boundary --------------------------------------------------------- */
 /* cat[a (ca ch), b (cb ch)] NCDHW fp32 -> NDHWC bf16 with cp channels (b may be NULL); replaces the
- * torch.cat of ref:model.py:86 and Lightning's host tensor layout */
-int ub_pack_ncdhw(const float* a, int ca, const float* b, int cb, int n, long long voxels, int cp,
+ * torch.cat of ref:model.py:86 and Lightning's host tensor layout. a_bf16 != 0: `a` is NCDHW bf16 (a loader that
+ * ships the conditioning input in bf16 halves its host-to-device bytes; the result is bit-identical because fp32
+ * inputs are rounded to bf16 by this very kernel) */
+int ub_pack_ncdhw(const void* a, int a_bf16, int ca, const float* b, int cb, int n, long long voxels, int cp,
                   void* out, void* stream);
 /* same, but the destination is the parity-planar space-to-depth layout
  * [n][(pd,ph,pw)][d/2][h/2][w/2][cp] (eight dense half-resolution sub-volumes per sample) read by
  * UB_CONV_K4S2P1_S2D (the PatchGAN stem d1, ref:model.py:72-73,86); d, h, w must be even */
-int ub_pack_ncdhw_s2d(const float* a, int ca, const float* b, int cb, int n, int d, int h, int w, int cp,
+int ub_pack_ncdhw_s2d(const void* a, int a_bf16, int ca, const float* b, int cb, int n, int d, int h, int w, int cp,
                       void* out, void* stream);
 /* Sliding-window inference (ref:model.py:315-333, ref:data_module.py:168-183; torchio==0.19.6
  * GridSampler / GridAggregator with patch_overlap 0). ub_pack_patches gathers n (<= 64) d x h x w patches of

@@ -128,6 +128,33 @@ def test_three_training_steps_follow_the_reference():
     np.testing.assert_allclose(g.blocks["bssfp"].bn.running_var.numpy(), REF["bssfp_train3_head_running_var"], rtol=1e-3)
 
 
+def test_lightning_shell_restatement_is_pinned_by_the_reference_run():
+    """oracle/lightning_shell.py (the LightningModule statements with injectable classes) driven with the oracle's
+    classes reproduces what the REAL ``bSSFPToDWITensorModel.training_step`` x 3 logged and left behind; the GPU test
+    then injects the sm_100a drop-in classes into this same shell."""
+    from oracle.lightning_shell import LightningShell, OracleClasses
+    torch.manual_seed(0)
+    lm = LightningShell("bssfp", OracleClasses)
+    if abs(state_checksum(lm.gen) - float(REF["bssfp_lm_gen_checksum0"])) > 1e-9 * float(REF["bssfp_lm_gen_checksum0"]):
+        pytest.skip("default torch init differs from the torch version that generated the goldens")
+    assert abs(state_checksum(lm.discr) - float(REF["bssfp_lm_discr_checksum0"])) <= 1e-9 * float(REF["bssfp_lm_discr_checksum0"])
+    zero_dropout(lm)
+    lm.train()
+    xb, yb = synth_batch(24)
+    gls, dls = [], []
+    for it in range(3):
+        lm.training_step({"bssfp": {"data": xb}, "dwi-tensor_orig": {"data": yb}}, it)
+        gls.append(lm.logged["train_gen_loss"]); dls.append(lm.logged["train_discr_loss"])
+    np.testing.assert_allclose(gls, REF["bssfp_train3_gen_loss"], rtol=2e-3)
+    np.testing.assert_allclose(dls, REF["bssfp_train3_discr_loss"], rtol=2e-3, atol=1e-4)
+    assert abs(state_checksum(lm.gen) / float(REF["bssfp_train3_gen_checksum"]) - 1) < 1e-4
+    assert abs(state_checksum(lm.discr) / float(REF["bssfp_train3_discr_checksum"]) - 1) < 1e-4
+    assert all(p.requires_grad for p in lm.parameters())            # untoggled again
+    lm.eval()
+    with torch.no_grad():
+        np.testing.assert_allclose(lm(xb[:1]).numpy(), REF["bssfp_train3_g_eval_32"], rtol=5e-2, atol=5e-3)
+
+
 def test_eval_arithmetic_is_the_references():
     pred, tgt, mask, probseg = REF["eval_pred"], REF["eval_target"], REF["eval_mask"], REF["eval_probseg"]
     diff = E.rel_error_map(pred, tgt)

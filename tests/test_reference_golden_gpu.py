@@ -145,6 +145,59 @@ def test_three_training_steps_track_the_reference():
                                rtol=2e-2)
 
 
+def _drop_in_lightning_module(monkeypatch):
+    """The reference's LightningModule with the sm_100a classes swapped in: the REAL ``bSSFPToDWITensorModel`` where
+    /root/reference is mounted (classes monkey-patched into the imported module), else its statement-by-statement
+    restatement ``oracle/lightning_shell.py`` (pinned to the real module's run by the CPU test)."""
+    import unet_bssfp_b200 as ub
+    if os.path.isdir(os.environ.get("UB_REFERENCE_SRC", "/root/reference/src")):
+        from tests.golden import make_golden_ref as M
+        R, _ = M.load_reference()
+        M.unload_stubs()
+        monkeypatch.setattr(R, "Generator", ub.Generator)
+        monkeypatch.setattr(R, "Discriminator", ub.Discriminator)
+        monkeypatch.setattr(torch.nn, "L1Loss", ub.L1Loss)                       # PerceptualL1Loss builds torch.nn.L1Loss()
+        monkeypatch.setattr(torch.nn, "BCEWithLogitsLoss", ub.BCEWithLogitsLoss)
+        return R.bSSFPToDWITensorModel("bssfp"), "reference module"
+    from oracle.lightning_shell import LightningShell
+    return LightningShell("bssfp", ub), "restated shell"
+
+
+def test_reference_lightning_module_runs_on_the_drop_in_classes(monkeypatch):
+    """VERDICT r1 missing #2: the reference's own ``training_step`` (ref:src/model.py:259-281: toggle_optimizer,
+    _gen_step, manual_backward, torch.optim.AdamW as configure_optimizers builds it, _discr_step ...) with
+    Generator / Discriminator / L1Loss / BCEWithLogitsLoss replaced by the drop-ins, three steps on the GPU, against
+    what the unmodified reference logged on the same weights and batch."""
+    import unet_bssfp_b200 as ub
+    torch.manual_seed(0)
+    lm, how = _drop_in_lightning_module(monkeypatch)
+    assert isinstance(lm.gen, ub.Generator) and isinstance(lm.discr, ub.Discriminator)
+    assert isinstance(lm.adversarial_criterion, ub.BCEWithLogitsLoss) and isinstance(lm.recon_criterion.l1, ub.L1Loss)
+    if abs(state_checksum(lm.gen) - float(REF["bssfp_lm_gen_checksum0"])) > 1e-9 * float(REF["bssfp_lm_gen_checksum0"]):
+        pytest.skip("default torch init differs from the torch version that generated the goldens")
+    no_dropout(lm)
+    lm = lm.to(DEV)
+    lm.train()
+    xb, yb = synth_batch(24)
+    xb, yb = xb.to(DEV), yb.to(DEV)
+    gls, dls = [], []
+    for it in range(3):
+        lm.training_step({"bssfp": {"data": xb}, "dwi-tensor_orig": {"data": yb}}, it)
+        gls.append(lm.logged["train_gen_loss"]); dls.append(lm.logged["train_discr_loss"])
+        if it == 0:   # before any weight update the phase losses are a forward-parity quantity
+            assert abs(gls[0] / REF["bssfp_train3_gen_loss"][0] - 1) < 1e-2, (how, gls[0])
+            assert abs(lm.logged["train_gen_loss_recon_L1"] / float(REF["bssfp_gen_loss_recon_L1"]) - 1) < 1e-2
+    np.testing.assert_allclose(gls, REF["bssfp_train3_gen_loss"], rtol=0.05, err_msg=how)
+    np.testing.assert_allclose(dls, REF["bssfp_train3_discr_loss"], rtol=0.15, atol=0.05, err_msg=how)
+    assert all(p.requires_grad for p in lm.parameters())
+    assert int(lm.discr.d2.bn.num_batches_tracked) == int(REF["bssfp_train3_num_batches_tracked_d2"])
+    np.testing.assert_allclose(lm.gen.blocks["bssfp"].bn.running_var.cpu().numpy(), REF["bssfp_train3_head_running_var"],
+                               rtol=2e-2)
+    # the optimizers configure_optimizers built are stock torch.optim.AdamW over the drop-ins' ordinary Parameters
+    g_opt, d_opt = lm.optimizers()
+    assert type(g_opt) is torch.optim.AdamW and len(g_opt.state) > 80 and len(d_opt.state) > 10
+
+
 def test_eval_kernels_match_reference_outputs():
     from unet_bssfp_b200 import ops
     pred, tgt = torch.from_numpy(REF["eval_pred"]).to(DEV), torch.from_numpy(REF["eval_target"]).to(DEV)

@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("UB_LIB_PATH") or os.path.join(_HERE, "libubssfp.so")
 
 UB_CONV_K3S1P1, UB_CONV_K1, UB_CONV_K4S2P1, UB_DECONV_K2S2, UB_CONV_K4S2P1_S2D = 0, 1, 2, 3, 4
 UB_NORM_INSTANCE, UB_NORM_BATCH_TRAIN, UB_NORM_BATCH_EVAL, UB_NORM_NONE = 0, 1, 2, 3
+UB_PACK_F16_SRC0 = 2
 
 
 class NormBwdFuse(C.Structure):
@@ -26,7 +27,7 @@ class NormBwdFuse(C.Structure):
 class DeferredAct(C.Structure):
     """Mirror of ``ub_deferred_act`` (include/ub_api.h)."""
     _fields_ = [("scale", C.c_void_p), ("shift", C.c_void_p), ("slope", C.c_float), ("drop_p", C.c_float),
-                ("drop_seed", C.c_uint32)]
+                ("drop_seed", C.c_uint32), ("f16_operand", C.c_int)]
 
 
 class AdamWTensor(C.Structure):
@@ -72,10 +73,11 @@ SIGNATURES = {
     "ub_conv_dgrad": (_I, [_DP, _P, _P, _P, _P, _P]),
     "ub_conv_dgrad_fuse_records": (_I, [_DP]),
     "ub_conv_dgrad_fused": (_I, [_DP, _P, _P, _P, _P, C.POINTER(NormBwdFuse), _P]),
+    "ub_conv_kernel_class": (_I, [_DP, _I]),
     "ub_conv_wgrad_workspace_bytes": (_LL, [_DP]),
     "ub_conv_wgrad": (_I, [_DP, _P, _P, _P, _P, _P, _AP, _P]),
-    "ub_pack_ncdhw": (_I, [_P, _I, _P, _I, _I, _LL, _I, _P, _P]),
-    "ub_pack_ncdhw_s2d": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "ub_pack_ncdhw": (_I, [_P, _I, _I, _P, _I, _I, _LL, _I, _P, _P]),
+    "ub_pack_ncdhw_s2d": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "ub_pack_patches": (_I, [_P, _I, _I, C.POINTER(C.c_longlong), _I, _I, _I, _LL, _LL, _LL, _I, _P, _P]),
     "ub_unpack_patch": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _LL, _LL, _LL, _LL, _P]),
     "ub_paste_patch": (_I, [_P, _I, _I, _I, _I, _P, _LL, _LL, _LL, _LL, _P]),

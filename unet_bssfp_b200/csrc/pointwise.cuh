@@ -139,21 +139,23 @@ struct NormActArgs {
 };
 
 // THE definition of a block's activations from its raw conv output (fp16 bits in `yraw`):
-//   a = bf16( LeakyReLU_slope( (y * scale + shift) / (1 - p) ) ) with dropped lanes cleared on the packed words.
+//   a = bf16( LeakyReLU_slope( y * (scale / (1-p)) + shift / (1-p) ) ) with dropped lanes cleared on the packed words
+// -- the inverted-dropout factor 1 / (1 - p) is folded into the affine constants (sc = scale * inv, sh = shift * inv,
+// both rounded once in fp32), so an element costs one fma, one multiply and one max.
 // Every consumer of a deferred activation (conv operand transform, weight-gradient operand transform, max-pool
-// forward / backward, the 1x1x1 output head) and the materialising pass (norm_act_fwd) call this one function,
-// so they all see bit-identical values. inv = 1 / (1 - p), slope_inv = slope * inv; e0 = element index of the
-// vector's first channel in the y tensor (dropout counter).
-__device__ __forceinline__ bf16x8 deferred_act8(const bf16x8& yraw, const float (&sc)[8], const float (&sh)[8], float inv,
-                                                float slope_inv, bool slope_le1, bool has_drop, unsigned long long e0,
+// forward / backward, the 1x1x1 output head), the materialising pass (norm_act_fwd) AND the backward passes (which
+// need the sign of the same fma) use these constants and this function, so they all see bit-identical values.
+// e0 = element index of the vector's first channel in the y tensor (dropout counter).
+__device__ __forceinline__ bf16x8 deferred_act8(const bf16x8& yraw, const float (&sc)[8], const float (&sh)[8],
+                                                float slope, bool slope_le1, bool has_drop, unsigned long long e0,
                                                 uint32_t seed, uint32_t thresh) {
   float x[8];
   unpack8h(yraw, x);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const float z = fmaf(x[k], sc[k], sh[k]);
-    const float hi = z * inv, lo = z * slope_inv;
-    x[k] = slope_le1 ? fmaxf(hi, lo) : (z > 0.f ? hi : lo);
+    const float hi = fmaf(x[k], sc[k], sh[k]);
+    const float lo = hi * slope;
+    x[k] = slope_le1 ? fmaxf(hi, lo) : (hi > 0.f ? hi : lo);
   }
   bf16x8 o = pack8(x);
   if (has_drop) {
@@ -163,28 +165,59 @@ __device__ __forceinline__ bf16x8 deferred_act8(const bf16x8& yraw, const float 
   }
   return o;
 }
+// The fp16-OPERAND form of the same activations, for a conv that multiplies them as an fp16 x fp16 tensor-core
+// operand (no backward pass will need them in bf16): packed half2 arithmetic straight on the fp16 y -- one HFMA2,
+// one HMUL2 and one HMNMX2 per PAIR of elements, no conversions -- with the affine constants rounded to fp16.
+// Relative error ~3 * 2^-12, i.e. tighter than the bf16 rounding of the canonical form.
+__device__ __forceinline__ bf16x8 deferred_act8_f16(const bf16x8& yraw, const __half2 (&sc)[4], const __half2 (&sh)[4],
+                                                    __half2 slope2, bool slope_le1, bool has_drop,
+                                                    unsigned long long e0, uint32_t seed, uint32_t thresh) {
+  bf16x8 o;
+  const __half2* y2 = reinterpret_cast<const __half2*>(&yraw);
+  __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __half2 hi = __hfma2(y2[k], sc[k], sh[k]);
+    const __half2 lo = __hmul2(hi, slope2);
+    if (slope_le1) {
+      o2[k] = __hmax2(hi, lo);
+    } else {
+      const __half2 pos = __hgt2(hi, __float2half2_rn(0.f));     // 1.0 / 0.0 per lane
+      o2[k] = __hfma2(pos, __hsub2(hi, lo), lo);
+    }
+  }
+  if (has_drop) {
+    uint32_t mw[4];
+    dropout_maskw(e0, seed, thresh, mw);
+    apply_maskw(o, mw);
+  }
+  return o;
+}
+
+// folded affine constant: the one place that defines the rounding of scale * inv / shift * inv
+__device__ __forceinline__ float fold_inv(float v, float inv) { return v * inv; }
 // per-thread constants of a deferred activation for the channel octet starting at c0 of sample n
 struct DeferredOctet {
   float sc[8], sh[8];
-  float inv, slope_inv;
+  float slope;
   bool slope_le1, has_drop;
   uint32_t seed, thresh;
   __device__ __forceinline__ void load(const NormActArgs& A, int n, int Cp, int c0) {
     const bool has_norm = A.scale != nullptr;
+    has_drop = A.drop_p > 0.f;
+    const float inv = has_drop ? 1.f / (1.f - A.drop_p) : 1.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      sc[k] = has_norm ? __ldg(A.scale + (size_t)n * Cp + c0 + k) : 1.f;
-      sh[k] = has_norm ? __ldg(A.shift + (size_t)n * Cp + c0 + k) : 0.f;
+      sc[k] = fold_inv(has_norm ? __ldg(A.scale + (size_t)n * Cp + c0 + k) : 1.f, inv);
+      sh[k] = fold_inv(has_norm ? __ldg(A.shift + (size_t)n * Cp + c0 + k) : 0.f, inv);
     }
-    has_drop = A.drop_p > 0.f;
-    inv = has_drop ? 1.f / (1.f - A.drop_p) : 1.f;
-    slope_inv = A.slope * inv;
+    slope = A.slope;
     slope_le1 = A.slope <= 1.f;
     seed = A.drop_seed;
     thresh = A.drop_thresh;
   }
   __device__ __forceinline__ bf16x8 apply(const bf16x8& yraw, unsigned long long e0) const {
-    return deferred_act8(yraw, sc, sh, inv, slope_inv, slope_le1, has_drop, e0, seed, thresh);
+    return deferred_act8(yraw, sc, sh, slope, slope_le1, has_drop, e0, seed, thresh);
   }
 };
 
@@ -199,27 +232,43 @@ struct DeferredOctet {
 // S2D: the destination is the parity-planar space-to-depth layout [N][(pd,ph,pw)][D/2][H/2][W/2][CP]
 // (eight dense half-resolution sub-volumes per sample) that the stride-2 PatchGAN stem reads with
 // plain, unstrided TMA boxes whose rows are contiguous in memory.
-template <int CP, bool S2D, int UNROLL>
+// a_bf16: input a is NCDHW bf16 instead of fp32 (a host pipeline that ships the network input in bf16 halves the
+// host-to-device bytes; the packed result is bit-identical, since fp32 inputs are rounded to bf16 here anyway).
+template <int CP, bool S2D, int UNROLL, bool A16>
 __global__ void __launch_bounds__(256)
-pack_ncdhw_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb,
+pack_ncdhw_kernel(const void* __restrict__ a_raw, int ca, const float* __restrict__ b, int cb,
                   __nv_bfloat16* __restrict__ dst, long long V, int D, int H, int W) {
   constexpr int OCT = CP / 8;            // octets per voxel
   constexpr int VPB = 256 / OCT;         // voxels per block pass
   const int n = blockIdx.y;
   const int oct = threadIdx.x % OCT;
   const long long v0 = (long long)blockIdx.x * (VPB * UNROLL) + threadIdx.x / OCT;
-  const float* src[8];
+  // source plane of channel k: a (fp32, or bf16 when A16) for c < ca, b (fp32) for ca <= c < ca + cb, else nullptr.
+  // With A16 the planes of a are addressed in 2-byte elements; `from_a` tells the two apart.
+  const void* src[8];
+  bool from_a[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int c = oct * 8 + k;
-    src[k] = c < ca ? a + ((size_t)n * ca + c) * V : (c < ca + cb ? b + ((size_t)n * cb + (c - ca)) * V : nullptr);
+    const size_t off_a = ((size_t)n * ca + c) * V;
+    from_a[k] = c < ca;
+    if (c < ca) src[k] = A16 ? (const void*)(reinterpret_cast<const __nv_bfloat16*>(a_raw) + off_a)
+                             : (const void*)(reinterpret_cast<const float*>(a_raw) + off_a);
+    else src[k] = c < ca + cb ? (const void*)(b + ((size_t)n * cb + (c - ca)) * V) : nullptr;
   }
   float g[UNROLL][8];
 #pragma unroll
   for (int u = 0; u < UNROLL; ++u) {
     const long long v = v0 + (long long)u * VPB;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g[u][k] = (src[k] != nullptr && v < V) ? __ldg(src[k] + v) : 0.f;
+    for (int k = 0; k < 8; ++k) {
+      float val = 0.f;
+      if (src[k] != nullptr && v < V) {
+        if (A16 && from_a[k]) val = __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(src[k]) + v));
+        else val = __ldg(reinterpret_cast<const float*>(src[k]) + v);
+      }
+      g[u][k] = val;
+    }
   }
 #pragma unroll
   for (int u = 0; u < UNROLL; ++u) {
@@ -573,7 +622,8 @@ __device__ __forceinline__ void dz1_8(const bf16x8& da8, const bf16x8& a8, const
   for (int i = 0; i < 8; ++i) dz[i] = da[i] * (av[i] > 0.f ? inv : sinv);
 }
 
-// Same with the activation sign recomputed from the raw conv output y (no read of `a`).
+// Same with the activation sign recomputed from the raw conv output y (no read of `a`): sc / sh are the FOLDED
+// forward constants (scale * inv, shift * inv -- fold_inv), i.e. the very fma whose sign the forward took.
 __device__ __forceinline__ void dz1_from_y8(const bf16x8& da8, const float (&yy)[8], const float (&sc)[8],
                                             const float (&sh)[8], const NormBwdArgs& B, unsigned long long e0,
                                             float (&dz)[8]) {
@@ -612,13 +662,14 @@ norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bflo
   float rstd[8], moff[8];   // xhat = y * rstd + moff
   float sc[8], sh_[8];
   const bool from_y = B.fshift != nullptr;
+  const float finv = B.drop_p > 0.f ? 1.f / (1.f - B.drop_p) : 1.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const float m = B.mean ? B.mean[(size_t)n * Cp + c0 + k] : 0.f;
     rstd[k] = B.rstd ? B.rstd[(size_t)n * Cp + c0 + k] : 0.f;
     moff[k] = -m * rstd[k];
-    sc[k] = from_y ? B.gscale[(size_t)n * Cp + c0 + k] : 0.f;
-    sh_[k] = from_y ? B.fshift[(size_t)n * Cp + c0 + k] : 0.f;
+    sc[k] = from_y ? fold_inv(B.gscale[(size_t)n * Cp + c0 + k], finv) : 0.f;
+    sh_[k] = from_y ? fold_inv(B.fshift[(size_t)n * Cp + c0 + k], finv) : 0.f;
   }
   float s1[8], s2[8];
 #pragma unroll
@@ -747,16 +798,18 @@ norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloa
   bf16x8* dyv = reinterpret_cast<bf16x8*>(dy) + base;
   const bool has_norm = B.mean != nullptr;
   const bool from_y = B.fshift != nullptr;
-  float ka[8], kb[8], kc[8], sh_[8];
+  float ka[8], kb[8], kc[8], sc_f[8], sh_f[8];   // sc_f / sh_f: the forward's folded affine constants (sign test)
   if (has_norm) {
     const size_t o = (size_t)n * Cp + (threadIdx.x % c8) * 8;
+    const float finv = B.drop_p > 0.f ? 1.f / (1.f - B.drop_p) : 1.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float g = B.gscale[o + k], r = B.rstd[o + k], m = B.mean[o + k];
       ka[k] = g;
       kc[k] = -g * r * B.c2[o + k];
       kb[k] = -g * B.c1[o + k] - kc[k] * m;
-      sh_[k] = from_y ? B.fshift[o + k] : 0.f;
+      sc_f[k] = fold_inv(g, finv);
+      sh_f[k] = from_y ? fold_inv(B.fshift[o + k], finv) : 0.f;
     }
   }
   const uint32_t i0 = blockIdx.x * (256u * UNROLL) + threadIdx.x;
@@ -776,7 +829,7 @@ norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloa
     if (idx >= vps) continue;
     float dz[8], yy[8];
     if (has_norm) unpack8h(y_[u], yy);
-    if (from_y) dz1_from_y8(d_[u], yy, ka, sh_, B, (unsigned long long)(base + idx) * 8ull, dz);
+    if (from_y) dz1_from_y8(d_[u], yy, sc_f, sh_f, B, (unsigned long long)(base + idx) * 8ull, dz);
     else dz1_8(d_[u], a_[u], B, (unsigned long long)(base + idx) * 8ull, dz);
     if (has_norm) {
 #pragma unroll
@@ -894,6 +947,8 @@ struct WeightPackArgs {
   int split_pad, split_real;         // concat: padded channel p >= split_pad maps to real p - split_pad + split_real
   int split_on_rows;                 // the concatenated (input-channel) axis is rows (dgrad) or cols (fwd)
   int rows_fold, fold_tap_stride;    // rows_fold > 0: row = fold * rows_fold + r, source tap += fold * fold_tap_stride
+  int f16_cols;                      // columns [0, f16_cols) are written as IEEE fp16 instead of bf16 (the K range of
+                                     // a source whose activations the consumer evaluates as an fp16 operand)
   int tapmap[64];                    // packed block -> source tap index
 };
 // padded concat index -> real channel index, or -1 for a pad slot
@@ -918,7 +973,8 @@ __device__ __forceinline__ void pack_weight_element(const float* __restrict__ w,
   float v = 0.f;
   if (rr >= 0 && cc >= 0)
     v = w[(size_t)rr * A.stride_row + (size_t)cc * A.stride_col + (size_t)tap * A.src_tap_stride];
-  out[i] = __float2bfloat16_rn(v);
+  if (col < A.f16_cols) reinterpret_cast<__half*>(out)[i] = __float2half_rn(v);
+  else out[i] = __float2bfloat16_rn(v);
 }
 __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, WeightPackArgs A) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

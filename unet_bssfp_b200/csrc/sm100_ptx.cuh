@@ -299,4 +299,9 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_
   return d;
 }
 
+// the same instruction descriptor with fp16 (instead of bf16) A and B operands
+__host__ __device__ __forceinline__ uint32_t idesc_f16_operands(uint32_t idesc) {
+  return idesc & ~((7u << 7) | (7u << 10));
+}
+
 }  // namespace ub

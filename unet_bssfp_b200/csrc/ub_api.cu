@@ -153,7 +153,14 @@ extern "C" long long ub_packed_weight_elems(const ub_conv_desc* d, int dir) {
   return (long long)ntaps_of(d->kind) * d->cop * cin;
 }
 
-static void build_pack_args(const ub_conv_desc* d, int dir, WeightPackArgs* out) {
+extern "C" int ub_conv_deferred_src0_ok(const ub_conv_desc* d);
+// dir: bit 0 = direction (0 forward, 1 dgrad); UB_PACK_F16_SRC0: the K columns of source 0 are packed as fp16
+// (forward packs of convs whose source 0 is a deferred activation evaluated as an fp16 operand)
+static int build_pack_args(const ub_conv_desc* d, int dir_flags, WeightPackArgs* out) {
+  const int dir = dir_flags & 1;
+  if (dir_flags & ~(1 | UB_PACK_F16_SRC0)) return fail(-1, "bad weight pack direction / flags %d", dir_flags);
+  if ((dir_flags & UB_PACK_F16_SRC0) && (dir != 0 || ub_conv_deferred_src0_ok(d) != 1))
+    return fail(-2, "UB_PACK_F16_SRC0 applies to the forward pack of a conv that accepts a deferred source 0");
   const int nt = ntaps_of(d->kind);
   const int ci = d->c0 + d->c1;
   WeightPackArgs& A = *out;
@@ -193,13 +200,15 @@ static void build_pack_args(const ub_conv_desc* d, int dir, WeightPackArgs* out)
   A.split_pad = d->c1p ? d->c0p : 0;
   A.split_real = d->c1p ? d->c0 : 0;
   A.split_on_rows = dir == 1;
+  A.f16_cols = (dir_flags & UB_PACK_F16_SRC0) ? d->c0p : 0;
+  return 0;
 }
 
 extern "C" int ub_pack_conv_weights(const ub_conv_desc* d, int dir, const float* w, void* packed, void* stream) {
   if (int e = check_desc(d)) return e;
   if (!w || !packed) return fail(-1, "null weight pointer");
   WeightPackArgs A;
-  build_pack_args(d, dir, &A);
+  if (int e = build_pack_args(d, dir, &A)) return e;
   const long long total = (long long)A.nblocks * A.rows_pad * A.cols_pad;
   pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       w, reinterpret_cast<__nv_bfloat16*>(packed), A);
@@ -221,7 +230,7 @@ extern "C" int ub_pack_conv_weights_multi(const ub_weight_pack_item* items, int 
       if (int e = check_desc(&it.desc)) return e;
       if (!it.w || !it.packed) return fail(-1, "ub_pack_conv_weights_multi: item %d has a null pointer", i - 1);
       const int k = B.count++;
-      build_pack_args(&it.desc, it.dir, &B.a[k]);
+      if (int e = build_pack_args(&it.desc, it.dir, &B.a[k])) return e;
       B.w[k] = it.w;
       B.out[k] = reinterpret_cast<__nv_bfloat16*>(it.packed);
       const long long total = (long long)B.a[k].nblocks * B.a[k].rows_pad * B.a[k].cols_pad;
@@ -382,6 +391,8 @@ static int launch_march(const void* src0, int c0p, const void* src1, int c1p, in
     if (fuse) return fail(-1, "a deferred source and the norm-backward fusion are exclusive");
     if (c0p != 32) return fail(-2, "a deferred activation source must have 32 padded channels (got %d)", c0p);
     if (int e = fill_deferred(&P.tf, tf)) return e;
+    P.tf_f16 = tf->f16_operand ? 1 : 0;
+    P.tf_y = src0;
   }
   if (fuse) {
     if (!fuse->y || !fuse->scale || !fuse->shift || !fuse->mean || !fuse->rstd || !fuse->partial)
@@ -878,6 +889,16 @@ static int wgrad_march_splits(const ub_conv_desc* d) {
   return ns < 1 ? 1 : ns;
 }
 
+// Which kernel serves (desc, dir): 0 = igemm_fwd_kernel (generic tap-table implicit GEMM), 1 = igemm_march_kernel,
+// 2 = wgrad_march_kernel, 3 = igemm_wgrad_kernel. dir: 0 forward, 1 dgrad, 2 wgrad. Used by the profiler / bench.py
+// to attribute time and FLOPs to kernel classes.
+extern "C" int ub_conv_kernel_class(const ub_conv_desc* d, int dir) {
+  if (check_desc(d)) return -1;
+  if (dir == 2) return use_wgrad_march(d) ? 2 : 3;
+  if (dir != 0 && dir != 1) return fail(-1, "dir must be 0 (forward), 1 (dgrad) or 2 (wgrad)");
+  return use_march(d, dir) ? 1 : 0;
+}
+
 extern "C" long long ub_conv_wgrad_workspace_bytes(const ub_conv_desc* d) {
   if (check_desc(d)) return -1;
   if (use_wgrad_march(d)) return (long long)wgrad_march_splits(d) * ntaps_of(d->kind) * (d->c0p + d->c1p) * d->cop * 4;
@@ -891,6 +912,8 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
   if (int e = check_desc(d)) return e;
   if (src0_act && ub_conv_deferred_src0_ok(d) != 1)
     return fail(-2, "a deferred source activation is not supported for this weight gradient (ub_conv_deferred_src0_ok)");
+  if (src0_act && src0_act->f16_operand)
+    return fail(-2, "the weight gradient pairs the activations with bf16 gradients: a deferred source must use the bf16 form");
   if (int e = ensure_encode()) return e;
   if (!src0 || !dy || !workspace || !dw) return fail(-1, "null pointer in ub_conv_wgrad");
   if (d->c1p && !src1) return fail(-1, "second source missing");
@@ -917,8 +940,10 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
     if (d->c1p)
       if (int e = make_act_map(&M.tm_x[1], src1, d->c1p, gw, gh, gd, d->n, 32, bw, bh, 1)) return e;
     if (int e = make_act_map(&M.tm_dy, dy, d->cop, gw, gh, gd, d->n, 32, 8, 16, 1)) return e;
-    if (src0_act)
+    if (src0_act) {
       if (int e = fill_deferred(&M.tf, src0_act)) return e;
+      M.tf_y = src0;
+    }
     typedef void (*WmFn)(const WgradMarchParams);
     static const WmFn wfns[3] = {wgrad_march_kernel<3, false>, wgrad_march_kernel<2, false>, wgrad_march_kernel<3, true>};
     static SmemOptIn wopt[3];
@@ -990,34 +1015,36 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
 // layout
 // --------------------------------------------------------------------------------------------------
 template <bool S2D>
-static int launch_pack(const float* a, int ca, const float* b, int cb, int n, long long voxels, int d, int h, int w,
+static int launch_pack(const void* a, int a_bf16, int ca, const float* b, int cb, int n, long long voxels, int d, int h, int w,
                        int cp, void* out, cudaStream_t st) {
   constexpr int UNROLL = 4;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   if (cp == 32) {
-    const unsigned blocks = (unsigned)((voxels + 64 * UNROLL - 1) / (64 * UNROLL));
-    pack_ncdhw_kernel<32, S2D, UNROLL><<<dim3(blocks, n), 256, 0, st>>>(a, ca, b, cb, o, voxels, d, h, w);
+    const dim3 grid((unsigned)((voxels + 64 * UNROLL - 1) / (64 * UNROLL)), n);
+    if (a_bf16) pack_ncdhw_kernel<32, S2D, UNROLL, true><<<grid, 256, 0, st>>>(a, ca, b, cb, o, voxels, d, h, w);
+    else pack_ncdhw_kernel<32, S2D, UNROLL, false><<<grid, 256, 0, st>>>(a, ca, b, cb, o, voxels, d, h, w);
   } else {
-    const unsigned blocks = (unsigned)((voxels + 32 * UNROLL - 1) / (32 * UNROLL));
-    pack_ncdhw_kernel<64, S2D, UNROLL><<<dim3(blocks, n), 256, 0, st>>>(a, ca, b, cb, o, voxels, d, h, w);
+    const dim3 grid((unsigned)((voxels + 32 * UNROLL - 1) / (32 * UNROLL)), n);
+    if (a_bf16) pack_ncdhw_kernel<64, S2D, UNROLL, true><<<grid, 256, 0, st>>>(a, ca, b, cb, o, voxels, d, h, w);
+    else pack_ncdhw_kernel<64, S2D, UNROLL, false><<<grid, 256, 0, st>>>(a, ca, b, cb, o, voxels, d, h, w);
   }
   UB_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int ub_pack_ncdhw(const float* a, int ca, const float* b, int cb, int n, long long voxels, int cp,
+extern "C" int ub_pack_ncdhw(const void* a, int a_bf16, int ca, const float* b, int cb, int n, long long voxels, int cp,
                              void* out, void* stream) {
   if (!a || !out || ca <= 0 || n <= 0 || n > 65535 || (cb > 0 && !b)) return fail(-1, "bad arguments to ub_pack_ncdhw");
   if (ca + cb > cp || cp % 32 || cp > 64) return fail(-1, "ub_pack_ncdhw supports cp in {32, 64}, got ca=%d cb=%d cp=%d", ca, cb, cp);
-  return launch_pack<false>(a, ca, b, cb, n, voxels, 0, 0, 0, cp, out, (cudaStream_t)stream);
+  return launch_pack<false>(a, a_bf16, ca, b, cb, n, voxels, 0, 0, 0, cp, out, (cudaStream_t)stream);
 }
 
-extern "C" int ub_pack_ncdhw_s2d(const float* a, int ca, const float* b, int cb, int n, int d, int h, int w, int cp,
+extern "C" int ub_pack_ncdhw_s2d(const void* a, int a_bf16, int ca, const float* b, int cb, int n, int d, int h, int w, int cp,
                                  void* out, void* stream) {
   if (!a || !out || ca <= 0 || n <= 0 || n > 65535 || (cb > 0 && !b)) return fail(-1, "bad arguments to ub_pack_ncdhw_s2d");
   if (ca + cb > cp || cp % 32 || cp > 64) return fail(-1, "ub_pack_ncdhw_s2d supports cp in {32, 64}, got ca=%d cb=%d cp=%d", ca, cb, cp);
   if (d <= 0 || h <= 0 || w <= 0 || ((d | h | w) & 1)) return fail(-1, "ub_pack_ncdhw_s2d needs even positive dims");
-  return launch_pack<true>(a, ca, b, cb, n, (long long)d * h * w, d, h, w, cp, out, (cudaStream_t)stream);
+  return launch_pack<true>(a, a_bf16, ca, b, cb, n, (long long)d * h * w, d, h, w, cp, out, (cudaStream_t)stream);
 }
 
 extern "C" int ub_pack_patches(const float* a, int ca, int n, const long long* offsets, int d, int h, int w,

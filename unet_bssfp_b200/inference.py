@@ -20,7 +20,7 @@ import torch
 
 from . import ops
 
-__all__ = ["grid_locations", "predict_volume", "relative_error"]
+__all__ = ["grid_locations", "shard_indices", "predict_volume", "relative_error"]
 
 _USE_GRAPH = os.environ.get("UB_INFER_GRAPH", "0") == "1"
 
@@ -84,19 +84,55 @@ def grid_locations(shape, patch):
     return list(itertools.product(*per_axis))
 
 
+def shard_indices(n: int, rank: int, world: int):
+    """Round-robin share of ``n`` independent work items (patches of one volume, or volumes of a test set)."""
+    return list(range(rank, n, world))
+
+
 @torch.no_grad()
-def predict_volume(gen, volume: torch.Tensor, patch=64, batch: int = 8, use_graph: bool | None = None) -> torch.Tensor:
+def predict_volume(gen, volume: torch.Tensor, patch=64, batch: int = 8, use_graph: bool | None = None,
+                   group=None, shard: bool | None = None) -> torch.Tensor:
     """``volume``: (C,D,H,W) or (1,C,D,H,W) fp32 CUDA tensor. Returns the aggregated prediction
     (6,D,H,W) fp32 on the same device. ``gen`` is a ``unet_bssfp_b200.Generator`` (its train/eval mode is
     respected, as in the reference where ``predict_step`` runs under ``model.eval()``).
     ``use_graph`` (default off; ``UB_INFER_GRAPH=1`` turns it on, eval mode only): replay the generator forward as
-    a CUDA graph on a static batch buffer; a short last batch is padded by repeating its last patch."""
+    a CUDA graph on a static batch buffer; a short last batch is padded by repeating its last patch.
+
+    Multi-GPU (``shard``; default: on when ``torch.distributed`` is initialised with more than one rank, every rank
+    holding the same volume and weights): the patches are dealt round-robin over the ranks of ``group`` -- the
+    generator work, which is all of the cost, needs no exchange -- and the per-rank partial volumes are combined so
+    that the result is bit-identical to the single-process one, including the sampler-order rule "the later patch
+    wins": every rank records which patch wrote each voxel last, an all-reduce (MAX) of that owner map decides the
+    winner, and an all-reduce (SUM) of the partial volumes masked to the winners delivers it to every rank. (For
+    a test SET, give each rank its own volumes -- ``shard_indices`` -- and no collective is needed at all.)"""
     vol = volume if volume.dim() == 4 else volume[0]
     if not vol.is_cuda:
         raise RuntimeError("predict_volume runs on CUDA tensors only (there is no CPU fallback)")
     patch = (patch,) * 3 if isinstance(patch, int) else tuple(patch)
     origins = grid_locations(tuple(vol.shape[1:]), patch)
     out_c = gen.blocks["unet"].out_channels
+    import torch.distributed as dist
+    dist_on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if shard is None:
+        shard = dist_on
+    if shard and dist_on:
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        mine = shard_indices(len(origins), rank, world)
+        part = torch.zeros((out_c,) + tuple(vol.shape[1:]), dtype=torch.float32, device=vol.device)
+        owner = torch.full(tuple(vol.shape[1:]), -1, dtype=torch.int32, device=vol.device)
+        for i in range(0, len(mine), batch):
+            idx = mine[i:i + batch]
+            a = ops.pack_patches(vol, [origins[k] for k in idx], patch)
+            y = gen.forward_packed(a)
+            for j, k in enumerate(idx):          # increasing sampler index: locally the later patch wins
+                z, yy, x = origins[k]
+                ops.paste_patch(y[j], part, origins[k])
+                owner[z:z + patch[0], yy:yy + patch[1], x:x + patch[2]] = k
+        winner = owner.clone()
+        dist.all_reduce(winner, op=dist.ReduceOp.MAX, group=group)
+        part.mul_((owner == winner).unsqueeze(0))
+        dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+        return part
     out = torch.zeros((out_c,) + tuple(vol.shape[1:]), dtype=torch.float32, device=vol.device)
     from .modules import _precision_of
     if use_graph is None:
@@ -125,6 +161,7 @@ def relative_error(pred: torch.Tensor, target: torch.Tensor, mask=None, probseg=
     """``pred`` / ``target``: (C,D,H,W) fp32 volumes (module layout). Returns ``(diff (D,H,W,C), errs [R][C] |
     None)``: the map of ``do_calc_diff_maps`` (channel-last, as the reference stores NIfTI volumes) and the
     per-ROI probseg-weighted means of ``do_calc_error_avg``."""
+    # module layout (C,D,H,W) -> the channel-last layout of the reference's NIfTI volumes (one strided copy each)
     p = pred.permute(1, 2, 3, 0).contiguous().float()
     t = target.permute(1, 2, 3, 0).contiguous().float()
     diff, sums, norms = ops.relerr_map_reduce(p, t, mask, probseg, angular=angular)

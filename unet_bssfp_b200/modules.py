@@ -74,19 +74,21 @@ class _PackedWeights:
     def __init__(self):
         self._cur = {}
 
-    def refresh(self, blocks, direction):
-        """Re-pack the conv weights of ``blocks`` for ``direction`` (0 forward, 1 dgrad) from the live parameters."""
+    def refresh(self, blocks, direction, f16_src0=frozenset()):
+        """Re-pack the conv weights of ``blocks`` for ``direction`` (0 forward, 1 dgrad) from the live parameters.
+        ``f16_src0``: names of blocks whose source 0 arrives as an fp16-operand deferred activation in this pass
+        (their source-0 weight columns are packed as fp16, ``UB_PACK_F16_SRC0``)."""
         todo, seen = [], set()
         for b in blocks:
             key = (id(b.conv.weight), b.spec, direction)
             if key not in seen:
                 seen.add(key)
-                todo.append((b.spec, b.conv.weight, direction))
+                todo.append((b.spec, b.conv.weight, direction | (ops.UB_PACK_F16_SRC0 if b.name in f16_src0 else 0)))
         outs = ops.pack_conv_weights_multi(todo)
         for k in [k for k in self._cur if k[2] == direction]:
             del self._cur[k]
         for (spec, w, _), out in zip(todo, outs):
-            self._cur[(id(w), spec, direction)] = out
+            self._cur[(id(w), spec, direction)] = out       # valid for THIS pass (fp16 columns included, if any)
 
     def get(self, spec, weight, direction):
         hit = self._cur.get((id(weight), spec, direction))
@@ -181,7 +183,8 @@ def _bn_momentum(nm) -> float:
     return 1.0 / float(seen + 1)
 
 
-def _block_forward(blk: _Block, cache: _PackedWeights, src0, src1, seed, pool=False, save=True, defer=False):
+def _block_forward(blk: _Block, cache: _PackedWeights, src0, src1, seed, pool=False, save=True, defer=False,
+                   defer_f16=False):
     """-> (a, pooled, saved). ``src0`` may be an ``ops.DeferredAct``. ``defer``: do not materialise this block's
     activations -- ``a`` is returned as an ``ops.DeferredAct`` for consumers that apply it on their operand path
     (with ``pool`` only the pooled tensor is written). Train / eval behaviour follows the block's own modules:
@@ -224,7 +227,7 @@ def _block_forward(blk: _Block, cache: _PackedWeights, src0, src1, seed, pool=Fa
         pooled = None
         if pool:
             _, pooled = ops.norm_act_fwd(y, scale, shift, blk.slope, drop_p, seed, pool=True, materialize=False)
-        a = ops.DeferredAct(y, scale, shift, blk.slope, drop_p, seed)
+        a = ops.DeferredAct(y, scale, shift, blk.slope, drop_p, seed, f16_operand=defer_f16)
     else:
         a, pooled = ops.norm_act_fwd(y, scale, shift, blk.slope, drop_p, seed, pool=pool)
     if save:
@@ -358,6 +361,13 @@ class _InputPackCache:
 
     def clear(self):
         self._drop(None)
+
+
+def _out_dtype(x):
+    """Module outputs follow the input dtype, except for a bf16 input: that is a TRANSPORT format of the fp32 pipeline
+    (it halves the host-to-device bytes of the conditioning input and packs to the same bits), so the result stays
+    fp32 and the whole step is bit-identical to feeding the fp32 tensor."""
+    return torch.float32 if x.dtype == torch.bfloat16 else x.dtype
 
 
 def _fresh_seed() -> int:
@@ -522,7 +532,8 @@ class _ChainFunction(torch.autograd.Function):
         ctx.cx = x.shape[1]
         ctx.cy = y.shape[1] if y is not None else 0
         ctx.in_dtype = x.dtype
-        return out.to(x.dtype)
+        ctx.y_dtype = y.dtype if y is not None else None
+        return out.to(_out_dtype(x))
 
     @staticmethod
     def backward(ctx, dout):
@@ -545,7 +556,7 @@ class _ChainFunction(torch.autograd.Function):
             saved[i] = None
             dA = d0
         dx = ops.unpack_ncdhw(d0, ctx.cx, 0).to(ctx.in_dtype) if need_x else None
-        dy = ops.unpack_ncdhw(d0, ctx.cy, ctx.cx).to(ctx.in_dtype) if need_y else None
+        dy = ops.unpack_ncdhw(d0, ctx.cy, ctx.cx).to(ctx.y_dtype) if need_y else None
         _join_side_stream(dout.device)
         ctx.saved = None
         pg = [grads.get(id(p)) if pneed[id(p)] else None for p in chain.params]
@@ -607,35 +618,44 @@ class _UNetGraph:
         """Blocks whose forward runs on a conv kernel (the output head runs fused with the layout change)."""
         return [b for b in self.blocks if not (b is self.final and _final_is_fusable(self))]
 
-    def defer_plan(self, n, d, h, w, ncdhw_out):
-        """Names of the blocks whose activations stay DEFERRED (never materialised): every consumer of the block
-        must be able to apply the norm + dropout + LeakyReLU on its own operand path -- a 3x3x3 conv on the marching
-        kernels (``ops.deferred_src0_ok``), the pooling pass, the fused output head. UB_DEFER=0 disables it."""
-        key = (n, d, h, w, ncdhw_out)
+    def defer_plan(self, n, d, h, w, ncdhw_out, need_bwd):
+        """-> (names of the blocks whose activations stay DEFERRED -- never materialised --, names of the conv blocks
+        that consume one as an fp16 operand). Every consumer of a deferred block must be able to apply the norm +
+        dropout + LeakyReLU on its own operand path:
+          * the fused output head and the pooling passes (memory-bound kernels: in registers) -- always;
+          * a 3x3x3 conv on the marching kernel (``ops.deferred_src0_ok``: in shared memory, between the TMA arrival
+            and the MMAs) -- in passes WITHOUT a backward (inference, the generator forward of the discriminator
+            phase), where the operand can take the cheap fp16 form. With a backward to come the weight gradient
+            needs the activations in bf16 next to its bf16 gradients, and materialising them once (one pass at HBM
+            speed) is cheaper than transforming them twice on the tensor-core kernels' operand paths (measured:
+            profiles/r02_deferred_microbench.txt), so those blocks are materialised as in round 1.
+        UB_DEFER=0 disables deferral altogether."""
+        key = (n, d, h, w, ncdhw_out, need_bwd)
         hit = self._defer_plans.get(key)
         if hit is not None:
             return hit
-        plan = set()
+        plan, f16 = set(), set()
         if _DEFER:
-            def ok(consumer, lvl):
-                return ops.deferred_src0_ok(consumer.spec, n, d >> lvl, h >> lvl, w >> lvl)
-
             nlev = len(self.enc)
-            if self.head is not None and self.head.spec.cop == 32 and ok(self.enc[0][0], 0):
-                plan.add(self.head.name)
-            for lvl, (c0, c1) in enumerate(self.enc):
-                if ok(c1, lvl):
-                    plan.add(c0.name)
-                if lvl < nlev - 1 and ok(self.dec[nlev - 2 - lvl][1], lvl):   # consumers: pooling pass + the skip conv
-                    plan.add(c1.name)
-            for j, (dc, c0, c1) in enumerate(self.dec):
-                lvl = nlev - 2 - j
-                if ok(c1, lvl):
-                    plan.add(c0.name)
-                if j == len(self.dec) - 1 and ncdhw_out and _final_is_fusable(self) and c1.spec.cop == 32:
-                    plan.add(c1.name)
-        self._defer_plans[key] = plan
-        return plan
+            last_c1 = self.dec[-1][2]
+            if ncdhw_out and _final_is_fusable(self) and last_c1.spec.cop == 32:
+                plan.add(last_c1.name)                         # consumer: the fused output head
+            if not need_bwd:
+                def ok(consumer, lvl):
+                    return ops.deferred_src0_ok(consumer.spec, n, d >> lvl, h >> lvl, w >> lvl)
+
+                if self.head is not None and self.head.spec.cop == 32 and ok(self.enc[0][0], 0):
+                    plan.add(self.head.name); f16.add(self.enc[0][0].name)
+                for lvl, (c0, c1) in enumerate(self.enc):
+                    if ok(c1, lvl):
+                        plan.add(c0.name); f16.add(c1.name)
+                    if lvl < nlev - 1 and ok(self.dec[nlev - 2 - lvl][1], lvl):   # consumers: pooling pass + the skip conv
+                        plan.add(c1.name); f16.add(self.dec[nlev - 2 - lvl][1].name)
+                for j, (dc, c0, c1) in enumerate(self.dec):
+                    if ok(c1, nlev - 2 - j):
+                        plan.add(c0.name); f16.add(c1.name)
+        self._defer_plans[key] = (frozenset(plan), frozenset(f16))
+        return self._defer_plans[key]
 
 
 _DEFER = _os_env.environ.get("UB_DEFER", "1") != "0"
@@ -660,16 +680,17 @@ def _generator_run(net: _UNetGraph, a, need_bwd: bool, ncdhw_out: bool = False):
     any_dropout = any(b.dropout_p() > 0.0 for b in net.blocks)
     base_seed = _fresh_seed() if any_dropout else 0
     cache = net.cache
-    cache.refresh(net.fwd_blocks(), 0)
     n, d, h, w, _ = a.shape
-    deferred = net.defer_plan(n, d, h, w, ncdhw_out)
+    deferred, f16_consumers = net.defer_plan(n, d, h, w, ncdhw_out, need_bwd)
+    cache.refresh(net.fwd_blocks(), 0, f16_src0=f16_consumers)
     S = {}          # block name -> saved
     lid = [0]
 
     def run(blk, s0, s1=None, pool=False):
         lid[0] += 1
         a_, pooled, sv = _block_forward(blk, cache, s0, s1, (base_seed + 7919 * lid[0]) & 0x7FFFFFFF,
-                                        pool=pool, save=need_bwd, defer=blk.name in deferred)
+                                        pool=pool, save=need_bwd, defer=blk.name in deferred,
+                                        defer_f16=bool(f16_consumers))
         S[blk.name] = sv
         return a_, pooled
 
@@ -712,7 +733,7 @@ class _GeneratorFunction(torch.autograd.Function):
         ctx.net, ctx.S = net, S
         ctx.cx = x.shape[1]
         ctx.in_dtype = x.dtype
-        return out.to(x.dtype)
+        return out.to(_out_dtype(x))
 
     @staticmethod
     def backward(ctx, dout):

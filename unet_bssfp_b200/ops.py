@@ -14,11 +14,11 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import (ConvDesc, UB_CONV_K1, UB_CONV_K3S1P1, UB_CONV_K4S2P1, UB_CONV_K4S2P1_S2D, UB_DECONV_K2S2,
+from ._lib import (ConvDesc, UB_PACK_F16_SRC0, UB_CONV_K1, UB_CONV_K3S1P1, UB_CONV_K4S2P1, UB_CONV_K4S2P1_S2D, UB_DECONV_K2S2,
                    UB_NORM_BATCH_EVAL, UB_NORM_BATCH_TRAIN, UB_NORM_INSTANCE, UB_NORM_NONE)
 
 __all__ = [
-    "ConvSpec", "DeferredAct", "deferred_src0_ok", "pad32", "pack_conv_weights", "pack_conv_weights_multi", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv1x1_to_ncdhw", "conv1x1_from_ncdhw_bwd", "pack_ncdhw", "unpack_ncdhw",
+    "ConvSpec", "DeferredAct", "UB_PACK_F16_SRC0", "deferred_src0_ok", "pad32", "pack_conv_weights", "pack_conv_weights_multi", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv1x1_to_ncdhw", "conv1x1_from_ncdhw_bwd", "pack_ncdhw", "unpack_ncdhw",
     "pack_patches", "unpack_patch", "paste_patch",
     "norm_finalize", "bn_running_update", "norm_act_fwd", "norm_act_bwd", "maxpool_bwd", "colsum", "l1_fwd", "l1_bwd", "bce_logits",
     "scale_by", "relerr_map_reduce", "dti_scalar_maps", "denorm_to_nifti",
@@ -59,6 +59,7 @@ class DeferredAct:
     slope: float
     drop_p: float = 0.0
     drop_seed: int = 0
+    f16_operand: bool = False   # conv_fwd only: evaluate in packed fp16 and multiply with fp16-packed weights (no backward)
 
     @property
     def shape(self):
@@ -76,7 +77,7 @@ class DeferredAct:
         if self.y.dtype != torch.float16 or self.y.shape[-1] != 32:
             raise RuntimeError("a deferred activation needs a (N, D, H, W, 32) float16 conv output")
         return _lib.DeferredAct(self.scale.data_ptr(), self.shift.data_ptr(), self.slope, self.drop_p,
-                                self.drop_seed & 0xFFFFFFFF)
+                                self.drop_seed & 0xFFFFFFFF, 1 if self.f16_operand else 0)
 
 
 def _split_deferred(src):
@@ -130,11 +131,12 @@ class ConvSpec:
 # convolution family
 # ---------------------------------------------------------------------------------------------------
 def pack_conv_weights(spec: ConvSpec, w: torch.Tensor, direction: int) -> torch.Tensor:
-    """fp32 torch-layout weight -> packed bf16 [tap][rows_pad][cols_pad]; direction 0 fwd, 1 dgrad."""
+    """fp32 torch-layout weight -> packed bf16 [tap][rows_pad][cols_pad]; direction 0 fwd, 1 dgrad, optionally
+    OR-ed with ``UB_PACK_F16_SRC0`` (source-0 columns as fp16, for ``DeferredAct(f16_operand=True)`` sources)."""
     _require_cuda(w)
     lib = _lib.load()
-    d = spec.desc(1, 2, 2, 2)
-    n = lib.ub_packed_weight_elems(C.byref(d), direction)
+    d = spec.desc(1, 32, 32, 32)
+    n = lib.ub_packed_weight_elems(C.byref(d), direction & 1)
     if n < 0:
         _lib.check(-1, "ub_packed_weight_elems")
     out = torch.empty(n, dtype=torch.bfloat16, device=w.device)
@@ -162,8 +164,8 @@ def pack_conv_weights_multi(items):
     outs, keep = [], []
     for k, (spec, w, direction) in enumerate(items):
         _require_cuda(w)
-        d = spec.desc(1, 2, 2, 2)
-        n = lib.ub_packed_weight_elems(C.byref(d), direction)
+        d = spec.desc(1, 32, 32, 32)
+        n = lib.ub_packed_weight_elems(C.byref(d), direction & 1)
         if n < 0:
             _lib.check(-1, "ub_packed_weight_elems")
         w32 = w.detach()
@@ -312,7 +314,8 @@ def pack_ncdhw(a: torch.Tensor, b: torch.Tensor | None = None, s2d: bool = False
     (N, 8 = (pd,ph,pw), D/2, H/2, W/2, Cp) -- the input layout of the stride-2 PatchGAN stem."""
     _require_cuda(a, b)
     lib = _lib.load()
-    a = a.contiguous().float()
+    a16 = 1 if a.dtype == torch.bfloat16 else 0          # a bf16 input is read as it is (bit-identical pack)
+    a = a.contiguous() if a16 else a.contiguous().float()
     n, ca, d, h, w = a.shape
     cb = 0
     if b is not None:
@@ -321,10 +324,11 @@ def pack_ncdhw(a: torch.Tensor, b: torch.Tensor | None = None, s2d: bool = False
     cp = pad32(ca + cb)
     if s2d:
         out = torch.empty((n, 8, d // 2, h // 2, w // 2, cp), dtype=torch.bfloat16, device=a.device)
-        _lib.check(lib.ub_pack_ncdhw_s2d(_p(a), ca, _p(b), cb, n, d, h, w, cp, _p(out), _stream()), "ub_pack_ncdhw_s2d")
+        _lib.check(lib.ub_pack_ncdhw_s2d(_p(a), a16, ca, _p(b), cb, n, d, h, w, cp, _p(out), _stream()),
+                   "ub_pack_ncdhw_s2d")
         return out
     out = torch.empty((n, d, h, w, cp), dtype=torch.bfloat16, device=a.device)
-    _lib.check(lib.ub_pack_ncdhw(_p(a), ca, _p(b), cb, n, d * h * w, cp, _p(out), _stream()), "ub_pack_ncdhw")
+    _lib.check(lib.ub_pack_ncdhw(_p(a), a16, ca, _p(b), cb, n, d * h * w, cp, _p(out), _stream()), "ub_pack_ncdhw")
     return out
 
 

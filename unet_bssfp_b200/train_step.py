@@ -26,32 +26,75 @@ def _set_requires_grad(module, flag):
         p.requires_grad_(flag)
 
 
+def _dist_on(group=None) -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def broadcast_module_state(module, group=None, src=0, buffers_only=False):
+    """What DDP does at construction (parameters + buffers) and before every forward
+    (``broadcast_buffers=True``: the BatchNorm running statistics, C4): rank ``src``'s tensors replace everyone's,
+    in ONE broadcast per dtype on a flat staging buffer."""
+    if not _dist_on(group):
+        return
+    tensors = list(module.buffers()) if buffers_only else list(module.parameters()) + list(module.buffers())
+    by_dtype = {}
+    for t in tensors:
+        by_dtype.setdefault(t.dtype, []).append(t)
+    with torch.no_grad():
+        for dtype, ts in by_dtype.items():
+            flat = torch.cat([t.detach().reshape(-1) for t in ts])
+            dist.broadcast(flat, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+            off = 0
+            for t in ts:
+                n = t.numel()
+                t.copy_(flat[off:off + n].view_as(t))     # in place: same storage, version bumped
+                off += n
+
+
 class GradAllReducer:
-    """Averages the gradients of one network over the data-parallel ranks with ONE NCCL all-reduce on
-    a persistent flat fp32 buffer (what DDP's bucketed reducer does for the live network's slots)."""
+    """Averages the gradients of one network over the data-parallel ranks with ONE NCCL all-reduce on a persistent
+    flat fp32 buffer with a FIXED layout over all of the module's parameters (what DDP's reducer does for the live
+    network's slots, ref:src/train.py:30-32 ``ddp_find_unused_parameters_true``): a parameter without a gradient on
+    this rank contributes zeros, so ranks never disagree about the payload. After the call every ``p.grad`` that any
+    rank produced is a VIEW of the reduced buffer holding the SUM; ``scale`` (1 / world size) is handed to the
+    optimizer (``FusedAdamW.grad_scale``) or applied here for foreign optimizers."""
 
     def __init__(self, module, group=None):
         self.params = [p for p in module.parameters()]
         self.group = group
         self.flat = None
+        self.offsets = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += p.numel()
+        self.numel = off
 
-    def __call__(self):
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
-            return
-        live = [p for p in self.params if p.grad is not None]
-        if not live:
-            return
-        n = sum(p.grad.numel() for p in live)
-        if self.flat is None or self.flat.numel() != n or self.flat.device != live[0].grad.device:
-            self.flat = torch.empty(n, dtype=torch.float32, device=live[0].grad.device)
-        views, off = [], 0
-        for p in live:
-            views.append(self.flat[off:off + p.grad.numel()].view_as(p.grad))
-            off += p.grad.numel()
-        torch._foreach_copy_(views, [p.grad for p in live])
+    def __call__(self, apply_scale=True):
+        """-> the factor still to be applied to the gradients (1.0 when ``apply_scale`` or single-process)."""
+        if not _dist_on(self.group):
+            return 1.0
+        world = dist.get_world_size(self.group)
+        dev = self.params[0].device
+        if self.flat is None or self.flat.device != dev:
+            self.flat = torch.empty(self.numel, dtype=torch.float32, device=dev)
+        views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
+        have = torch.tensor([0.0 if p.grad is None else 1.0 for p in self.params], device=dev)
+        live = [(v, p.grad) for v, p in zip(views, self.params) if p.grad is not None]
+        dead = [v for v, p in zip(views, self.params) if p.grad is None]
+        if live:
+            torch._foreach_copy_([v for v, _ in live], [g for _, g in live])
+        if dead:
+            torch._foreach_zero_(dead)
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)   # SUM + scale: works on nccl and gloo
-        self.flat.mul_(1.0 / dist.get_world_size(self.group))
-        torch._foreach_copy_([p.grad for p in live], views)
+        dist.all_reduce(have, op=dist.ReduceOp.MAX, group=self.group)        # which slots ANY rank produced
+        if apply_scale:
+            self.flat.mul_(1.0 / world)
+        have = have.tolist()
+        for v, p, h in zip(views, self.params, have):
+            if h > 0:
+                p.grad = v                  # alias the reduced buffer: no copy back
+        return 1.0 if apply_scale else 1.0 / world
 
 
 class GanTrainer:
@@ -82,6 +125,10 @@ class GanTrainer:
         self.bce = BCEWithLogitsLoss()
         self.reduce_g = GradAllReducer(gen)
         self.reduce_d = GradAllReducer(discr)
+        # DDP construction semantics: every rank starts from rank 0's parameters and buffers (C6)
+        broadcast_module_state(gen)
+        broadcast_module_state(discr)
+        self.broadcast_buffers = True       # DDP default: rank 0's BatchNorm running statistics before every step (C4)
 
     def recon_loss(self, y_hat, y):
         return self.l1(y_hat, y) / N_RECON_TERMS * RECON_FACTOR
@@ -130,14 +177,23 @@ class GanTrainer:
         loss.record_stream(main)
         return (loss + loss_hat) / 2
 
+    def _reduce_and_step(self, reducer, opt):
+        fused = isinstance(opt, FusedAdamW)
+        scale = reducer(apply_scale=not fused)
+        if fused:
+            opt.grad_scale = scale          # 1 / world folded into the AdamW kernel's gradient read
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
     def step(self, x, y):
         """One ``training_step``: G phase (D frozen), AdamW, D phase on a fresh G forward, AdamW."""
+        if self.broadcast_buffers and _dist_on():
+            broadcast_module_state(self.gen, buffers_only=True)
+            broadcast_module_state(self.discr, buffers_only=True)
         _set_requires_grad(self.discr, False)
         g_loss, _ = self.gen_loss(x, y)
         g_loss.backward()
-        self.reduce_g()
-        self.opt_g.step()
-        self.opt_g.zero_grad(set_to_none=True)
+        self._reduce_and_step(self.reduce_g, self.opt_g)
         _set_requires_grad(self.discr, True)
 
         _set_requires_grad(self.gen, False)
@@ -145,8 +201,6 @@ class GanTrainer:
         d_loss.backward()
         if self._branch_stream is not None:
             torch.cuda.current_stream().wait_stream(self._branch_stream)   # the real pass's backward ran there
-        self.reduce_d()
-        self.opt_d.step()
-        self.opt_d.zero_grad(set_to_none=True)
+        self._reduce_and_step(self.reduce_d, self.opt_d)
         _set_requires_grad(self.gen, True)
         return g_loss.detach(), d_loss.detach()
