@@ -94,9 +94,12 @@ int ub_conv_deferred_src0_ok(const ub_conv_desc* d);
  * stats_partial: [ub_conv_num_tiles][2][cop] floats or NULL. With stats_partial the output is the raw input y of
  * a normalisation and is written as fp16 (statistics from the fp32 accumulators); otherwise bf16.
  * src0_act != NULL: src0 points at the producer's y (fp16) and is a deferred activation. */
+/* src0_f16 != 0: src0 is a MATERIALISED fp16 activation tensor (ub_norm_act_fwd's a_f16 output) and the weights were
+ * packed with UB_PACK_F16_SRC0: its K chunks run as fp16 x fp16 MMAs into the same fp32 accumulators (the forward
+ * pass then carries 1/8 of bf16's operand rounding on those layers). Same availability as a deferred source. */
 int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* src1, const void* w_packed,
                 const float* bias, int act, float slope, void* out, float* stats_partial,
-                const ub_deferred_act* src0_act, void* stream);
+                const ub_deferred_act* src0_act, int src0_f16, void* stream);
 /* d src = conv_transpose(dy); dsrc1 may be NULL when the op has one source */
 int ub_conv_dgrad(const ub_conv_desc* d, const void* dy, const void* w_packed_dgrad, void* dsrc0,
                   void* dsrc1, void* stream);
@@ -190,10 +193,12 @@ int ub_norm_finalize(const float* stats_partial, int tiles_per_sample, int n, in
 int ub_bn_running_update(const float* mean, const float* rstd, int c, double count, float eps, float momentum,
                          float* running_mean, float* running_var, void* stream);
 /* a = LeakyReLU_slope(Dropout_p(y * scale + shift)); pooled (may be NULL) = MaxPool3d(2)(a). y is fp16, a and
- * pooled bf16. scale == NULL: no normalisation. a may be NULL when pooled is given (the activations stay
- * deferred, only the pooled tensor is materialised). ref: monai ADN "NDA" + Down.max_pooling */
+ * pooled bf16. scale == NULL: no normalisation. a may be NULL when pooled or a_f16 is given (the activations stay
+ * deferred / only the requested copies are materialised). ref: monai ADN "NDA" + Down.max_pooling */
+/* a_f16 (may be NULL): the SAME fp32 values rounded to fp16 -- the operand copy for a forward conv called with
+ * src0_f16 (the bf16 copy `a` is what the weight gradient needs; a pass without a backward writes only a_f16) */
 int ub_norm_act_fwd(const void* y, const float* scale, const float* shift, float slope, float drop_p,
-                    uint32_t drop_seed, int n, int d, int h, int w, int cp, void* a, void* pooled,
+                    uint32_t drop_seed, int n, int d, int h, int w, int cp, void* a, void* a_f16, void* pooled,
                     void* stream);
 long long ub_norm_act_bwd_workspace_bytes(int n, int cp);
 /* backward of the block above: dy from dA; dgamma/dbeta/dbias (fp32 [c]) may be NULL.

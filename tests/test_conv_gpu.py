@@ -231,7 +231,7 @@ def test_no_out_of_bounds_writes(kind, c0, c1, co, shape):
     tiles = lib.ub_conv_num_tiles(C.byref(desc))
     sbuf, stats = arena(tiles * 2 * spec.cop, torch.float32)
     _lib.check(lib.ub_conv_fwd(C.byref(desc), P(s0), P(s1), P(wf), P(b), 0, 0.0, P(y), P(stats) if want_stats else None,
-                               None, st))
+                               None, 0, st))
     torch.cuda.synchronize()
     assert intact(ybuf) and intact(sbuf)
     assert not torch.isnan(y.float()).any()
@@ -255,3 +255,24 @@ def test_no_out_of_bounds_writes(kind, c0, c1, co, shape):
     _lib.check(lib.ub_conv_wgrad(C.byref(desc), P(s0), P(s1), P(dy), P(ws), P(dw), None, st))
     torch.cuda.synchronize()
     assert intact(wsbuf) and intact(dwbuf) and not torch.isnan(dw).any()
+
+
+def test_multi_tensor_weight_pack_equals_single_packs():
+    """ub_pack_conv_weights_multi (one launch for a network's weights, coalesced (row, column)-per-thread mapping)
+    writes exactly what ub_pack_conv_weights writes, for every conv kind, both directions and the fp16-column form."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    items = []
+    for kind, c0, c1, co in [(0, 24, 0, 32), (0, 32, 64, 32), (0, 64, 64, 64), (0, 128, 0, 256), (1, 24, 0, 24), (1, 512, 0, 1),
+                             (2, 32, 0, 64), (3, 128, 0, 64), (4, 30, 0, 32), (0, 32, 0, 32)]:
+        spec = ops.ConvSpec(kind, c0, co, c1)
+        wt = torch.randn(_weight_shape(kind, c0 + c1, co), device="cuda", generator=g)
+        for direction in (0, 1):
+            items.append((spec, wt, direction))
+    for spec, c in ((ops.ConvSpec(0, 32, 32, 64), 96), (ops.ConvSpec(0, 24, 32), 24)):
+        items.append((spec, torch.randn((32, c, 3, 3, 3), device="cuda", generator=g), ops.UB_PACK_F16_SRC0))
+    multi = ops.pack_conv_weights_multi(items)
+    torch.cuda.synchronize()
+    assert len(multi) == len(items) > 16
+    for (spec, wt, direction), got in zip(items, multi):
+        assert torch.equal(got.view(torch.int16), ops.pack_conv_weights(spec, wt, direction).view(torch.int16)), (spec, direction)

@@ -83,7 +83,7 @@ if len(sys.argv) > 4:
     def raw_fwd(yx, outx):
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         p = lambda t: C.c_void_p(t.data_ptr())
-        _lib.check(lib.ub_norm_act_fwd(p(yx), p(scale), p(shift), 0.1, 0.05, 123, N, S, S, S, CP, p(outx), None, st))
+        _lib.check(lib.ub_norm_act_fwd(p(yx), p(scale), p(shift), 0.1, 0.05, 123, N, S, S, S, CP, p(outx), None, None, st))
 
     timeit("  skewed norm_act_bwd from y p=0.05", lambda: raw_bwd(dA2, y2, out), elems * 10)
     timeit("  skewed norm_act_fwd p=0.05", lambda: raw_fwd(y2, out), elems * 4)

@@ -69,7 +69,7 @@ SIGNATURES = {
     "ub_pack_conv_weights_multi": (_I, [C.POINTER(WeightPackItem), _I, _P]),
     "ub_conv_num_tiles": (_I, [_DP]),
     "ub_conv_deferred_src0_ok": (_I, [_DP]),
-    "ub_conv_fwd": (_I, [_DP, _P, _P, _P, _P, _I, _F, _P, _P, _AP, _P]),
+    "ub_conv_fwd": (_I, [_DP, _P, _P, _P, _P, _I, _F, _P, _P, _AP, _I, _P]),
     "ub_conv_dgrad": (_I, [_DP, _P, _P, _P, _P, _P]),
     "ub_conv_dgrad_fuse_records": (_I, [_DP]),
     "ub_conv_dgrad_fused": (_I, [_DP, _P, _P, _P, _P, C.POINTER(NormBwdFuse), _P]),
@@ -87,7 +87,7 @@ SIGNATURES = {
     "ub_conv1x1_from_ncdhw_bwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _LL, _P, _P, _P, _P, _AP, _P]),
     "ub_norm_finalize": (_I, [_P, _I, _I, _I, _I, _D, _P, _P, _F, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "ub_bn_running_update": (_I, [_P, _P, _I, _D, _F, _F, _P, _P, _P]),
-    "ub_norm_act_fwd": (_I, [_P, _P, _P, _F, _F, _U32, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "ub_norm_act_fwd": (_I, [_P, _P, _P, _F, _F, _U32, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "ub_norm_act_bwd_workspace_bytes": (_LL, [_I, _I]),
     "ub_norm_act_bwd": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _F, _F, _U32, _I, _LL, _I, _I, _P, _P, _P, _P, _P, _P, _I,
                              _P]),

@@ -21,7 +21,6 @@
 #include "igemm_fwd.cuh"
 #include "pointwise.cuh"
 #include "deferred_tile.cuh"
-#include <type_traits>
 
 namespace ub {
 
@@ -50,8 +49,9 @@ struct MarchParams {
   // kTf instantiation: source 0 (one 32-channel chunk) is the raw fp16 output y of a conv -> norm block and `tf`
   // its deferred activation; two extra warps rewrite every halo plane of chunk 0 in shared memory
   // (deferred_tile.cuh) between the TMA arrival and the MMAs.
+  int src0_f16;                     // source 0 is a MATERIALISED fp16 activation tensor (its chunks are fp16 x fp16 MMAs
+                                    // against weight columns packed as fp16, UB_PACK_F16_SRC0)
   NormActArgs tf;
-  const void* tf_y;                 // the deferred source's y tensor [N][D][H][W][32] fp16 (= source 0)
   int tf_f16;                       // the transformed chunk is an fp16 operand (its weight columns are packed as fp16)
 };
 
@@ -74,11 +74,10 @@ constexpr int kMarchThreadsTf = kMarchThreads + kMarchTfThreads;
 // what bounds the single-CTA kernel (ncu: 81 % l1tex data-pipe, 69 % tensor-pipe active). The leader
 // (rank 0) issues the MMAs and owns w_full / a_full / acc_empty; the peer's TMA loads and epilogue arrive
 // on them remotely; tcgen05.commit multicasts a_empty / acc_full to both CTAs.
-// kTf (forward only): chunk 0 is the deferred source. Its planes are not loaded by TMA: the transform warps read y
-// from global memory, evaluate the activations in registers and write the stage (deferred_tile.cuh); they wait for
-// the stage's a_empty themselves and hand it to the MMA thread through a_ready[stage] in the leader CTA (one arrival
-// per CTA; pair mode: each CTA fills its own half). The other chunks keep the TMA / a_full path. A stage alternates
-// between the two paths, so the MMA thread tracks the barrier phases per stage in bit masks.
+// kTf (forward only): chunk 0 arrives as y and is transformed in place. Its TMA completes on a CTA-local barrier
+// a_loc[stage] (pair mode: each CTA waits for its own plane), the transform warps hand the stage to the MMA thread
+// through a_ready[stage] in the leader CTA (one arrival per CTA). Untransformed chunks keep the a_full path. A
+// stage alternates between the two paths, so the barrier phases are tracked per stage in bit masks.
 template <bool kNormBwd, bool kPair, bool kTf>
 __global__ void __launch_bounds__(kTf ? kMarchThreadsTf : kMarchThreads, 1)
 igemm_march_kernel(const __grid_constant__ MarchParams P) {
@@ -163,12 +162,14 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
       uint32_t pa = 0;
       for (int p = p_first; p <= p_last; ++p) {
         for (int c = 0; c < nch; ++c) {
+          mbar_wait(a_empty + 8 * sa, pa ^ 1);
           if (kTf && c == 0) {
-            // the plane of the deferred source is written by the transform warps (they wait for the stage themselves)
+            // y plane of the deferred source: completes on this CTA's own barrier, the transform warps take over
+            mbar_expect_tx(a_loc + 8 * sa, 180 * 64);
+            tma_load_5d(a_base + sa * kMarchPlaneBytes, &P.tm_src[0], a_loc + 8 * sa, 0, w0 - 1, h0 - 1, p, nb);
             if (++sa == P.nsa) { sa = 0; pa ^= 1; }
             continue;
           }
-          mbar_wait(a_empty + 8 * sa, pa ^ 1);
           if (rank == 0) mbar_expect_tx(a_full + 8 * sa, kPair ? 2 * 180 * 64 : 180 * 64);
           const bool s1 = c >= P.n_chunks_src0;
           if (kPair)
@@ -186,7 +187,8 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
     // =========================== MMA issuer (leader CTA only in pair mode) ===========================
     if (rank == 0) {
       const uint32_t idesc_bf = make_idesc_bf16(kPair ? 256 : 128, 96, 0, 0);
-      const uint32_t idesc_tf = (kTf && P.tf_f16) ? idesc_f16_operands(idesc_bf) : idesc_bf;   // chunk 0 of a kTf CTA
+      const uint32_t idesc_h = idesc_f16_operands(idesc_bf);
+      const uint32_t idesc_tf = (kTf && P.tf_f16) ? idesc_h : idesc_bf;   // chunk 0 of a kTf CTA
       const uint32_t a_hi = (uint32_t)(make_smem_desc(0, 16, 10 * 64, SWZ_64B) >> 32);
       const uint32_t b_hi = (uint32_t)(make_smem_desc(0, 16, 8 * 64, SWZ_64B) >> 32);
       const uint32_t lbo_lo = 1u << 16;
@@ -194,7 +196,9 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
       mbar_wait(w_full, 0);
       tc_fence_after();
       int sa = 0;
-      uint32_t ph_full = 0, ph_ready = 0;   // per-stage phase bits of a_full / a_ready
+      uint32_t pa = 0;                      // !kTf: every stage use completes a_full -- one ring parity
+      uint32_t ph_full = 0, ph_ready = 0;   // kTf: a stage alternates between a_full and a_ready -- per-stage phase bits
+      const int n_f16 = P.src0_f16 ? P.n_chunks_src0 : 0;   // chunks of a materialised fp16 source 0
       int slot = 0;
       uint32_t pacc = 0;
       for (int p = p_first; p <= p_last; ++p) {
@@ -202,7 +206,9 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
         tc_fence_after();
         const uint32_t acc = tmem + slot * 96;
         for (int c = 0; c < nch; ++c) {
-          if (kTf && c == 0) {
+          if (!kTf) {
+            mbar_wait(a_full + 8 * sa, pa);
+          } else if (c == 0) {
             mbar_wait(a_ready + 8 * sa, (ph_ready >> sa) & 1u);
             ph_ready ^= 1u << sa;
           } else {
@@ -211,7 +217,7 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
           }
           tc_fence_after();
           if (leader) {
-            const uint32_t idesc = (kTf && c == 0) ? idesc_tf : idesc_bf;
+            const uint32_t idesc = kTf ? (c == 0 ? idesc_tf : idesc_bf) : (c < n_f16 ? idesc_h : idesc_bf);
             const uint32_t a_lo = lbo_lo | ((a_base + sa * kMarchPlaneBytes) >> 4);
             const uint32_t b_lo = lbo_lo | ((w_base + c * 9 * kWTile) >> 4);
 #pragma unroll
@@ -232,7 +238,7 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
             else umma_commit(a_empty + 8 * sa);
           }
           __syncwarp();
-          if (++sa == P.nsa) sa = 0;
+          if (++sa == P.nsa) { sa = 0; pa ^= 1; }
         }
         if (leader) {
           if (kPair) umma_commit_pair(acc_full + 8 * slot);
@@ -245,30 +251,23 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
   } else if (kTf && warp >= kMarchEpiWarps) {
     // =========================== operand transform (warps 8-9) ===========================
     const int t = (int)threadIdx.x - kMarchEpiWarps * 32;
-    const size_t plane_bytes = (size_t)P.H * P.W * 64;                 // one y plane: H x W voxels x 32 fp16
-    const uint8_t* ysrc = reinterpret_cast<const uint8_t*>(P.tf_y) + (size_t)nb * P.D * plane_bytes;
+    const unsigned long long plane_vox = (unsigned long long)P.H * P.W;
     auto run = [&](auto& T) {
-      using TT = typename std::remove_reference<decltype(T)>::type;
       T.setup(t, P.tf, nb, h0, w0, P.H, P.W);
-      uint4 buf[2][TT::NK];
-      T.load(buf[0], ysrc + (size_t)p_first * plane_bytes);
-      auto step = [&](int p, const uint4 (&cur)[TT::NK], uint4 (&nxt)[TT::NK]) {
-        if (p < p_last) T.load(nxt, ysrc + (size_t)(p + 1) * plane_bytes);     // one plane ahead
-        const int use = (p - p_first) * nch;                                    // chunk 0 of plane p in the stage ring
-        const int sa = use % P.nsa;
-        mbar_wait(a_empty + 8 * sa, (((uint32_t)(use / P.nsa)) & 1u) ^ 1u);      // the MMAs of the previous use are done
-        T.store(cur, sm + (a_base - base) + sa * kMarchPlaneBytes,
-                ((unsigned long long)nb * P.D + p) * (unsigned long long)(plane_bytes >> 1));
+      int sa = 0;
+      uint32_t ph_loc = 0;
+      for (int p = p_first; p <= p_last; ++p) {
+        // chunk 0 of plane p sits in stage sa; the other chunks of the plane only advance the ring
+        mbar_wait(a_loc + 8 * sa, (ph_loc >> sa) & 1u);
+        ph_loc ^= 1u << sa;
+        T.apply(sm + (a_base - base) + sa * kMarchPlaneBytes, ((unsigned long long)nb * P.D + p) * plane_vox);
         fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core's async proxy
         named_bar_sync(3, kMarchTfThreads);
         if (t == 0) {
           if (kPair) mbar_arrive_cluster(a_ready_ld + 8 * sa, 1u);
           else mbar_arrive(a_ready + 8 * sa);
         }
-      };
-      for (int p = p_first; p <= p_last; p += 2) {
-        step(p, buf[0], buf[1]);
-        if (p + 1 <= p_last) step(p + 1, buf[1], buf[0]);
+        sa = (sa + nch) % P.nsa;
       }
     };
     if (P.tf_f16) {

@@ -146,9 +146,12 @@ struct NormActArgs {
 // forward / backward, the 1x1x1 output head), the materialising pass (norm_act_fwd) AND the backward passes (which
 // need the sign of the same fma) use these constants and this function, so they all see bit-identical values.
 // e0 = element index of the vector's first channel in the y tensor (dropout counter).
+// `o16` (optional): the SAME fp32 values rounded to fp16 instead of bf16 -- the operand copy a forward conv
+// multiplies with fp16-packed weights (11-bit significand: the forward pass then carries 1/8 of bf16's operand
+// rounding); the bf16 form is what a weight gradient pairs with its bf16 gradients.
 __device__ __forceinline__ bf16x8 deferred_act8(const bf16x8& yraw, const float (&sc)[8], const float (&sh)[8],
                                                 float slope, bool slope_le1, bool has_drop, unsigned long long e0,
-                                                uint32_t seed, uint32_t thresh) {
+                                                uint32_t seed, uint32_t thresh, bf16x8* o16 = nullptr) {
   float x[8];
   unpack8h(yraw, x);
 #pragma unroll
@@ -158,10 +161,16 @@ __device__ __forceinline__ bf16x8 deferred_act8(const bf16x8& yraw, const float 
     x[k] = slope_le1 ? fmaxf(hi, lo) : (hi > 0.f ? hi : lo);
   }
   bf16x8 o = pack8(x);
+  uint32_t mw[4];
   if (has_drop) {
-    uint32_t mw[4];
     dropout_maskw(e0, seed, thresh, mw);
     apply_maskw(o, mw);
+  }
+  if (o16 != nullptr) {
+    uint32_t* w16 = reinterpret_cast<uint32_t*>(o16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w16[k] = pack_f16x2_sat(x[2 * k], x[2 * k + 1]);
+    if (has_drop) apply_maskw(*o16, mw);
   }
   return o;
 }
@@ -216,8 +225,8 @@ struct DeferredOctet {
     seed = A.drop_seed;
     thresh = A.drop_thresh;
   }
-  __device__ __forceinline__ bf16x8 apply(const bf16x8& yraw, unsigned long long e0) const {
-    return deferred_act8(yraw, sc, sh, slope, slope_le1, has_drop, e0, seed, thresh);
+  __device__ __forceinline__ bf16x8 apply(const bf16x8& yraw, unsigned long long e0, bf16x8* o16 = nullptr) const {
+    return deferred_act8(yraw, sc, sh, slope, slope_le1, has_drop, e0, seed, thresh, o16);
   }
 };
 
@@ -516,15 +525,17 @@ __global__ void bn_stats_stage2_kernel(int Nb, int Cp, int C, double count_per_s
 // grid = (ceil(vps / (256 * UNROLL)), N), vps = vectors (8 channels) per sample. FIXED: Cp/8 divides
 // 256, so a thread keeps the same channel octet for all its vectors and the per-channel scale / shift
 // live in registers. No 64-bit divisions on the path.
+// a (bf16) and / or a16 (the fp16 operand copy of the same values) are written; either may be nullptr.
 template <int UNROLL, bool FIXED>
 __global__ void __launch_bounds__(256)
-norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y /* fp16 bits */, __nv_bfloat16* __restrict__ a, NormActArgs A, int Cp,
-                    uint32_t vps) {
+norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y /* fp16 bits */, __nv_bfloat16* __restrict__ a,
+                    __nv_bfloat16* __restrict__ a16 /* fp16 bits */, NormActArgs A, int Cp, uint32_t vps) {
   const int n = blockIdx.y;
   const uint32_t c8 = (uint32_t)Cp >> 3;
   const size_t base = (size_t)n * vps;
   const bf16x8* yv = reinterpret_cast<const bf16x8*>(y) + base;
   bf16x8* av = reinterpret_cast<bf16x8*>(a) + base;
+  bf16x8* av16 = reinterpret_cast<bf16x8*>(a16) + base;
   const uint32_t i0 = blockIdx.x * (256u * UNROLL) + threadIdx.x;
   DeferredOctet K;
   if (FIXED) K.load(A, n, Cp, (int)(threadIdx.x % c8) * 8);
@@ -539,13 +550,17 @@ norm_act_fwd_kernel(const __nv_bfloat16* __restrict__ y /* fp16 bits */, __nv_bf
     const uint32_t idx = i0 + u * 256u;
     if (idx >= vps) continue;
     if (!FIXED) K.load(A, n, Cp, (int)(idx % c8) * 8);
-    st_stream(av + idx, K.apply(in[u], (unsigned long long)(base + idx) * 8ull));
+    bf16x8 h;
+    const bf16x8 o = K.apply(in[u], (unsigned long long)(base + idx) * 8ull, a16 != nullptr ? &h : nullptr);
+    if (a != nullptr) st_stream(av + idx, o);
+    if (a16 != nullptr) st_stream(av16 + idx, h);
   }
 }
 
 // thread = (pooled voxel, 8 channels): writes the 8 activated voxels (unless a == nullptr: the activations stay
 // deferred and only the pooled tensor is materialised) and their max
 __global__ void norm_act_pool_fwd_kernel(const __nv_bfloat16* __restrict__ y /* fp16 bits */, __nv_bfloat16* __restrict__ a,
+                                         __nv_bfloat16* __restrict__ a16 /* fp16 bits, may be nullptr */,
                                          __nv_bfloat16* __restrict__ pooled, NormActArgs A, int Cp, int Nb, int D,
                                          int H, int W, uint32_t per_sample /* pooled voxels * Cp/8 of one sample */) {
   // grid = (blocks, N): 32-bit index math inside a sample
@@ -576,8 +591,10 @@ __global__ void norm_act_pool_fwd_kernel(const __nv_bfloat16* __restrict__ y /* 
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const bf16x8 pk = K.apply(raw[j], (unsigned long long)e[j] * 8ull);
+    bf16x8 h;
+    const bf16x8 pk = K.apply(raw[j], (unsigned long long)e[j] * 8ull, a16 != nullptr ? &h : nullptr);
     if (a != nullptr) st_stream(reinterpret_cast<bf16x8*>(a) + e[j], pk);
+    if (a16 != nullptr) st_stream(reinterpret_cast<bf16x8*>(a16) + e[j], h);
     float xr[8];
     unpack8(pk, xr);  // max over the stored (rounded) values
 #pragma unroll
@@ -987,7 +1004,6 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
 // live fp32 Parameters every time it runs: ~25 us for the generator's 22.6 M weights, and no cache that an
 // out-of-band write to parameter memory could leave stale). The table is a __grid_constant__ kernel argument.
 constexpr int kPackMaxTensors = 32;
-constexpr int kPackBlockElems = 2048;     // elements per block (256 threads x 8)
 struct WeightPackBatch {
   WeightPackArgs a[kPackMaxTensors];
   const float* w[kPackMaxTensors];
@@ -995,6 +1011,9 @@ struct WeightPackBatch {
   int block_begin[kPackMaxTensors + 1];
   int count;
 };
+// thread = one (packed row, packed column) pair, looping over the packed tap blocks: the taps of one (co, ci) pair
+// are contiguous in the torch layout (<= 256 bytes), so a warp reads whole cache lines once and every block's
+// write is a contiguous run of columns (the per-element kernel above gathers with a 108-byte stride instead).
 __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const __grid_constant__ WeightPackBatch B) {
   __shared__ int s_t;
   if (threadIdx.x == 0) {
@@ -1005,12 +1024,28 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const __grid_co
   __syncthreads();
   const int t = s_t;
   const WeightPackArgs& A = B.a[t];
-  const long long total = (long long)A.nblocks * A.rows_pad * A.cols_pad;
-  const long long begin = (long long)((int)blockIdx.x - B.block_begin[t]) * kPackBlockElems;
-#pragma unroll
-  for (int k = 0; k < kPackBlockElems / 256; ++k) {
-    const long long i = begin + k * 256 + threadIdx.x;
-    if (i < total) pack_weight_element(B.w[t], B.out[t], A, i);
+  const float* __restrict__ w = B.w[t];
+  __nv_bfloat16* __restrict__ out = B.out[t];
+  const long long plane = (long long)A.rows_pad * A.cols_pad;
+  const long long j = (long long)((int)blockIdx.x - B.block_begin[t]) * 256 + threadIdx.x;
+  if (j >= plane) return;
+  const int col = (int)(j % A.cols_pad);
+  int row = (int)(j / A.cols_pad);
+  int fold_tap = 0;
+  if (A.rows_fold > 0) {
+    fold_tap = (row / A.rows_fold) * A.fold_tap_stride;
+    row = row % A.rows_fold;
+  }
+  const int rr = A.split_on_rows ? concat_real_index(row, A.split_pad, A.split_real, A.rows) : (row < A.rows ? row : -1);
+  const int cc = A.split_on_rows ? (col < A.cols ? col : -1) : concat_real_index(col, A.split_pad, A.split_real, A.cols);
+  const bool real = rr >= 0 && cc >= 0;
+  const float* src = w + (real ? (size_t)rr * A.stride_row + (size_t)cc * A.stride_col : 0);
+  const bool f16 = col < A.f16_cols;
+  for (int blk = 0; blk < A.nblocks; ++blk) {
+    const float v = real ? __ldg(src + (size_t)(A.tapmap[blk] + fold_tap) * A.src_tap_stride) : 0.f;
+    const long long i = blk * plane + j;
+    if (f16) reinterpret_cast<__half*>(out)[i] = __float2half_rn(v);
+    else out[i] = __float2bfloat16_rn(v);
   }
 }
 

@@ -233,8 +233,8 @@ extern "C" int ub_pack_conv_weights_multi(const ub_weight_pack_item* items, int 
       if (int e = build_pack_args(&it.desc, it.dir, &B.a[k])) return e;
       B.w[k] = it.w;
       B.out[k] = reinterpret_cast<__nv_bfloat16*>(it.packed);
-      const long long total = (long long)B.a[k].nblocks * B.a[k].rows_pad * B.a[k].cols_pad;
-      B.block_begin[k + 1] = B.block_begin[k] + (int)((total + kPackBlockElems - 1) / kPackBlockElems);
+      const long long plane = (long long)B.a[k].rows_pad * B.a[k].cols_pad;      // one thread per (row, column)
+      B.block_begin[k + 1] = B.block_begin[k] + (int)((plane + 255) / 256);
     }
     if (B.count == 0) break;
     pack_weights_multi_kernel<<<(unsigned)B.block_begin[B.count], 256, 0, (cudaStream_t)stream>>>(B);
@@ -384,15 +384,15 @@ static int fill_deferred(NormActArgs* A, const ub_deferred_act* tf) {
 
 static int launch_march(const void* src0, int c0p, const void* src1, int c1p, int n, int D, int H, int W,
                         const void* w_packed, const float* bias, int bias_n, void* out, float* stats,
-                        const ub_norm_bwd_fuse* fuse, const ub_deferred_act* tf, cudaStream_t st) {
+                        const ub_norm_bwd_fuse* fuse, const ub_deferred_act* tf, int src0_f16, cudaStream_t st) {
   MarchParams P;
   memset(&P, 0, sizeof(P));
+  P.src0_f16 = src0_f16 ? 1 : 0;
   if (tf) {
     if (fuse) return fail(-1, "a deferred source and the norm-backward fusion are exclusive");
     if (c0p != 32) return fail(-2, "a deferred activation source must have 32 padded channels (got %d)", c0p);
     if (int e = fill_deferred(&P.tf, tf)) return e;
     P.tf_f16 = tf->f16_operand ? 1 : 0;
-    P.tf_y = src0;
   }
   if (fuse) {
     if (!fuse->y || !fuse->scale || !fuse->shift || !fuse->mean || !fuse->rstd || !fuse->partial)
@@ -508,10 +508,11 @@ extern "C" int ub_conv_deferred_src0_ok(const ub_conv_desc* d) {
 
 extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* src1, const void* w_packed,
                            const float* bias, int act, float slope, void* out, float* stats_partial,
-                           const ub_deferred_act* src0_act, void* stream) {
+                           const ub_deferred_act* src0_act, int src0_f16, void* stream) {
   if (int e = check_desc(d)) return e;
-  if (src0_act && ub_conv_deferred_src0_ok(d) != 1)
-    return fail(-2, "a deferred source activation is not supported for this convolution (ub_conv_deferred_src0_ok)");
+  if ((src0_act || src0_f16) && ub_conv_deferred_src0_ok(d) != 1)
+    return fail(-2, "a deferred / fp16 source 0 is not supported for this convolution (ub_conv_deferred_src0_ok)");
+  if (src0_act && src0_f16) return fail(-1, "src0_f16 describes a materialised fp16 tensor: exclusive with src0_act");
   if (int e = ensure_encode()) return e;
   if (!src0 || !w_packed || !out) return fail(-1, "null pointer in ub_conv_fwd");
   if (d->c1p && !src1) return fail(-1, "second source missing");
@@ -523,7 +524,7 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
   if (use_march(d, 0)) {
     if (act) return fail(-2, "fused activation is not available on the marching conv path");
     return launch_march(src0, d->c0p, src1, d->c1p, d->n, d->d, d->h, d->w, w_packed, bias, d->co, out,
-                        stats_partial, nullptr, src0_act, st);
+                        stats_partial, nullptr, src0_act, src0_f16, st);
   }
 
   IgemmPlan pl;
@@ -684,7 +685,7 @@ extern "C" int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const 
   const int ncols = d->c0p + d->c1p;
   if (use_march(d, 1))
     return launch_march(dy, d->cop, nullptr, 0, d->n, d->d, d->h, d->w, w_packed_dgrad, nullptr, 0, dsrc0, nullptr, fuse,
-                        nullptr, st);
+                        nullptr, 0, st);
 
   IgemmPlan pl;
   memset(&pl, 0, sizeof(pl));
@@ -940,10 +941,8 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
     if (d->c1p)
       if (int e = make_act_map(&M.tm_x[1], src1, d->c1p, gw, gh, gd, d->n, 32, bw, bh, 1)) return e;
     if (int e = make_act_map(&M.tm_dy, dy, d->cop, gw, gh, gd, d->n, 32, 8, 16, 1)) return e;
-    if (src0_act) {
+    if (src0_act)
       if (int e = fill_deferred(&M.tf, src0_act)) return e;
-      M.tf_y = src0;
-    }
     typedef void (*WmFn)(const WgradMarchParams);
     static const WmFn wfns[3] = {wgrad_march_kernel<3, false>, wgrad_march_kernel<2, false>, wgrad_march_kernel<3, true>};
     static SmemOptIn wopt[3];
@@ -1135,9 +1134,9 @@ extern "C" int ub_norm_finalize(const float* stats_partial, int tiles_per_sample
 }
 
 extern "C" int ub_norm_act_fwd(const void* y, const float* scale, const float* shift, float slope, float drop_p,
-                               uint32_t drop_seed, int n, int d, int h, int w, int cp, void* a, void* pooled,
+                               uint32_t drop_seed, int n, int d, int h, int w, int cp, void* a, void* a_f16, void* pooled,
                                void* stream) {
-  if (!y || (!a && !pooled) || cp % 8) return fail(-1, "bad arguments to ub_norm_act_fwd");
+  if (!y || (!a && !a_f16 && !pooled) || cp % 8) return fail(-1, "bad arguments to ub_norm_act_fwd");
   if (drop_p < 0.f || drop_p >= 1.f) return fail(-1, "dropout p out of range");
   NormActArgs A{scale, shift, slope, drop_p, drop_seed, drop_thresh(drop_p)};
   const long long V = (long long)d * h * w;
@@ -1149,15 +1148,17 @@ extern "C" int ub_norm_act_fwd(const void* y, const float* scale, const float* s
     const dim3 grid((unsigned)((vps + 256 * UNROLL - 1) / (256 * UNROLL)), n);
     const __nv_bfloat16* yp = reinterpret_cast<const __nv_bfloat16*>(y);
     __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(a);
-    if (256 % (cp / 8) == 0) norm_act_fwd_kernel<UNROLL, true><<<grid, 256, 0, st>>>(yp, ap, A, cp, (uint32_t)vps);
-    else norm_act_fwd_kernel<UNROLL, false><<<grid, 256, 0, st>>>(yp, ap, A, cp, (uint32_t)vps);
+    __nv_bfloat16* ap16 = reinterpret_cast<__nv_bfloat16*>(a_f16);
+    if (256 % (cp / 8) == 0) norm_act_fwd_kernel<UNROLL, true><<<grid, 256, 0, st>>>(yp, ap, ap16, A, cp, (uint32_t)vps);
+    else norm_act_fwd_kernel<UNROLL, false><<<grid, 256, 0, st>>>(yp, ap, ap16, A, cp, (uint32_t)vps);
   } else {
     if ((d | h | w) & 1) return fail(-1, "fused max-pool needs even dims");
     const long long per_sample = (V / 8) * (cp / 8);
     if (per_sample >= (1ll << 31) || n > 65535) return fail(-2, "ub_norm_act_fwd: sample too large");
     norm_act_pool_fwd_kernel<<<dim3((unsigned)((per_sample + 255) / 256), n), 256, 0, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<__nv_bfloat16*>(a),
-        reinterpret_cast<__nv_bfloat16*>(pooled), A, cp, n, d, h, w, (uint32_t)per_sample);
+        reinterpret_cast<__nv_bfloat16*>(a_f16), reinterpret_cast<__nv_bfloat16*>(pooled), A, cp, n, d, h, w,
+        (uint32_t)per_sample);
   }
   UB_LAUNCH_CHECK();
   return 0;

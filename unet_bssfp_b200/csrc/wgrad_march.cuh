@@ -38,7 +38,6 @@ struct WgradMarchParams {
   // deferred activation: the four epilogue warps, idle until the end, rewrite every X halo plane of chunk 0 in
   // shared memory (deferred_tile.cuh) before the MMA thread reads it.
   NormActArgs tf;
-  const void* tf_y;         // the deferred source's y tensor [N][D][H][W][32] fp16 (= source 0)
 };
 
 constexpr int kWmXStages = 4, kWmXBytes = 12288;
@@ -125,12 +124,10 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
         for (int j = 0; j < KT - 1; ++j) load_dy(d0 + doff + j, nb, h0, w0);
         for (int p = d0; p < d1; ++p) {
           load_dy(p + doff + KT - 1, nb, h0, w0);
-          if (!tf_cta) {          // (a deferred source's X planes are written by the transform warps)
-            mbar_wait(x_empty + 8 * xs, xp ^ 1);
-            mbar_expect_tx(x_full + 8 * xs, BW * BH * 64);
-            tma_load_5d(x_base + xs * kWmXBytes, tmx, x_full + 8 * xs, c0, w0 + xoff_w, h0 + xoff_h, p,
-                        KT == 2 ? nb * 8 + parity : nb);
-          }
+          mbar_wait(x_empty + 8 * xs, xp ^ 1);
+          mbar_expect_tx(x_full + 8 * xs, BW * BH * 64);
+          tma_load_5d(x_base + xs * kWmXBytes, tmx, x_full + 8 * xs, c0, w0 + xoff_w, h0 + xoff_h, p,
+                      KT == 2 ? nb * 8 + parity : nb);
           if (++xs == kWmXStages) { xs = 0; xp ^= 1; }
         }
       }
@@ -201,11 +198,8 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
   } else {
     if (tf_cta) {
       // =========================== operand transform (warps 0-3), then the epilogue ===========================
-      // y planes from global memory -> activations in registers -> the X stage in TMA's layout (deferred_tile.cuh)
       HaloTransform<128> T;
-      constexpr int NK = HaloTransform<128>::NK;
-      const size_t plane_bytes = (size_t)P.H * P.W * 64;
-      const uint8_t* ysrc = reinterpret_cast<const uint8_t*>(P.tf_y);
+      const unsigned long long plane_vox = (unsigned long long)P.H * P.W;
       int xs = 0; uint32_t xp = 0;
       for (int it = i_begin; it < i_end; ++it) {
         int t = it;
@@ -216,22 +210,13 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
         const int d0 = seg * P.seg_len;
         int d1 = d0 + P.seg_len; if (d1 > P.D) d1 = P.D;
         T.setup((int)threadIdx.x, P.tf, nb, h0, w0, P.H, P.W);
-        const uint8_t* ysample = ysrc + (size_t)nb * P.D * plane_bytes;
-        uint4 buf[2][NK];
-        T.load(buf[0], ysample + (size_t)d0 * plane_bytes);
-        auto step = [&](int p, const uint4 (&cur)[NK], uint4 (&nxt)[NK]) {
-          if (p + 1 < d1) T.load(nxt, ysample + (size_t)(p + 1) * plane_bytes);
-          mbar_wait(x_empty + 8 * xs, xp ^ 1);
-          T.store(cur, sm + (x_base - base) + xs * kWmXBytes,
-                  ((unsigned long long)nb * P.D + p) * (unsigned long long)(plane_bytes >> 1));
+        for (int p = d0; p < d1; ++p) {
+          mbar_wait(x_full + 8 * xs, xp);
+          T.apply(sm + (x_base - base) + xs * kWmXBytes, ((unsigned long long)nb * P.D + p) * plane_vox);
           fence_proxy_async();
           named_bar_sync(1, 128);
           if (threadIdx.x == 0) mbar_arrive(x_ready + 8 * xs);
           if (++xs == kWmXStages) { xs = 0; xp ^= 1; }
-        };
-        for (int p = d0; p < d1; p += 2) {
-          step(p, buf[0], buf[1]);
-          if (p + 1 < d1) step(p + 1, buf[1], buf[0]);
         }
       }
     }

@@ -183,12 +183,25 @@ def _bn_momentum(nm) -> float:
     return 1.0 / float(seen + 1)
 
 
+class _Act:
+    """A block's materialised activations: the bf16 tensor ``a`` (what a weight gradient, a max-pool backward or a
+    generic-kernel conv reads; None when no consumer of this pass needs it) and, for blocks that feed a marching
+    forward conv, ``a16``: the same fp32 values rounded to fp16, multiplied against fp16-packed weight columns."""
+    __slots__ = ("a", "a16")
+
+    def __init__(self, a, a16):
+        self.a, self.a16 = a, a16
+
+
 def _block_forward(blk: _Block, cache: _PackedWeights, src0, src1, seed, pool=False, save=True, defer=False,
-                   defer_f16=False):
+                   defer_f16=False, f16_copy=False, keep_bf16=True, src0_saved=None):
     """-> (a, pooled, saved). ``src0`` may be an ``ops.DeferredAct``. ``defer``: do not materialise this block's
     activations -- ``a`` is returned as an ``ops.DeferredAct`` for consumers that apply it on their operand path
-    (with ``pool`` only the pooled tensor is written). Train / eval behaviour follows the block's own modules:
-    the norm layer's ``training`` flag (batch vs running statistics) and the dropout layer's ``p`` / ``training``."""
+    (with ``pool`` only the pooled tensor is written). ``f16_copy``: return an ``_Act`` that also carries the fp16
+    operand copy (``keep_bf16=False``: without the bf16 tensor). ``src0_saved``: what the weight gradient of this
+    block should read as source 0 when the forward consumed the fp16 copy. Train / eval behaviour follows the
+    block's own modules: the norm layer's ``training`` flag (batch vs running statistics) and the dropout layer's
+    ``p`` / ``training``."""
     spec = blk.spec
     w = cache.get(spec, blk.conv.weight, 0)
     n, d, h, wd = spec.in_dims(src0)
@@ -198,7 +211,8 @@ def _block_forward(blk: _Block, cache: _PackedWeights, src0, src1, seed, pool=Fa
         act = 1 if blk.fused_act else 0
         a, _ = ops.conv_fwd(spec, src0, src1, w, blk.conv.bias, act=act, slope=blk.slope)
         if save:
-            sv.src0, sv.src1, sv.y, sv.a, sv.mode, sv.in_dhw = src0, src1, None, a, UB_NORM_NONE, (d, h, wd)
+            sv.src0, sv.src1, sv.y, sv.a, sv.mode, sv.in_dhw = src0_saved if src0_saved is not None else src0, src1, None, a, \
+                UB_NORM_NONE, (d, h, wd)
             sv.mean = sv.rstd = sv.scale = sv.shift = None
             sv.seed, sv.drop_p = 0, 0.0
         return a, None, sv
@@ -228,10 +242,15 @@ def _block_forward(blk: _Block, cache: _PackedWeights, src0, src1, seed, pool=Fa
         if pool:
             _, pooled = ops.norm_act_fwd(y, scale, shift, blk.slope, drop_p, seed, pool=True, materialize=False)
         a = ops.DeferredAct(y, scale, shift, blk.slope, drop_p, seed, f16_operand=defer_f16)
+    elif f16_copy:
+        a_bf, pooled, a16 = ops.norm_act_fwd(y, scale, shift, blk.slope, drop_p, seed, pool=pool, materialize=keep_bf16,
+                                             f16_copy=True)
+        a = _Act(a_bf, a16)
     else:
         a, pooled = ops.norm_act_fwd(y, scale, shift, blk.slope, drop_p, seed, pool=pool)
     if save:
-        sv.src0, sv.src1, sv.y, sv.a, sv.mode, sv.in_dhw = src0, src1, y, a, mode, (d, h, wd)
+        sv.src0, sv.src1, sv.y, sv.mode, sv.in_dhw = src0_saved if src0_saved is not None else src0, src1, y, mode, (d, h, wd)
+        sv.a = a.a if isinstance(a, _Act) else a
         sv.mean, sv.rstd, sv.scale, sv.shift, sv.seed, sv.drop_p = mean, rstd, scale, shift, seed, drop_p
     return a, pooled, sv
 
@@ -619,46 +638,59 @@ class _UNetGraph:
         return [b for b in self.blocks if not (b is self.final and _final_is_fusable(self))]
 
     def defer_plan(self, n, d, h, w, ncdhw_out, need_bwd):
-        """-> (names of the blocks whose activations stay DEFERRED -- never materialised --, names of the conv blocks
-        that consume one as an fp16 operand). Every consumer of a deferred block must be able to apply the norm +
-        dropout + LeakyReLU on its own operand path:
-          * the fused output head and the pooling passes (memory-bound kernels: in registers) -- always;
-          * a 3x3x3 conv on the marching kernel (``ops.deferred_src0_ok``: in shared memory, between the TMA arrival
-            and the MMAs) -- in passes WITHOUT a backward (inference, the generator forward of the discriminator
-            phase), where the operand can take the cheap fp16 form. With a backward to come the weight gradient
-            needs the activations in bf16 next to its bf16 gradients, and materialising them once (one pass at HBM
-            speed) is cheaper than transforming them twice on the tensor-core kernels' operand paths (measured:
-            profiles/r02_deferred_microbench.txt), so those blocks are materialised as in round 1.
-        UB_DEFER=0 disables deferral altogether."""
+        """-> (deferred, f16_consumers, f16_producers): names of
+          * the blocks whose activations stay DEFERRED (never materialised): every consumer applies the norm + dropout +
+            LeakyReLU on its own operand path. By default that is the block in front of the fused output head (a
+            memory-bound consumer: in registers). With UB_DEFER_CONV=1, in passes without a backward, also the blocks
+            in front of 3x3x3 convs on the marching kernel (in shared memory, between the TMA arrival and the MMAs;
+            measured on B200 NOT to pay on these shared-memory-bound kernels, profiles/r02_deferred_microbench.txt);
+          * the conv blocks that read source 0 as an fp16 operand against fp16-packed weight columns, and
+          * the blocks that therefore write an fp16 copy of their activations beside (or, without a backward to
+            come, instead of) the bf16 tensor. These are the full-resolution 32-channel layers: they carry the skip
+            path straight to the output, and their bf16 operand rounding was the largest single term of the
+            end-to-end error (generator output rel-L2 1.25e-2 -> 0.86e-2 at 8 x 128^3).
+        UB_DEFER=0 / UB_FWD_F16=0 disable the two mechanisms."""
         key = (n, d, h, w, ncdhw_out, need_bwd)
         hit = self._defer_plans.get(key)
         if hit is not None:
             return hit
-        plan, f16 = set(), set()
+        plan, f16c, f16p = set(), set(), set()
+        nlev = len(self.enc)
+
+        def ok(consumer, lvl):
+            return ops.deferred_src0_ok(consumer.spec, n, d >> lvl, h >> lvl, w >> lvl)
+
+        edges = []          # (producer block, consumer conv block, level) along which source 0 travels
+        if self.head is not None and self.head.spec.cop == 32:
+            edges.append((self.head, self.enc[0][0], 0))
+        for lvl, (c0, c1) in enumerate(self.enc):
+            edges.append((c0, c1, lvl))
+            if lvl < nlev - 1:
+                edges.append((c1, self.dec[nlev - 2 - lvl][1], lvl))      # the skip conv (+ the pooling pass)
+        for j, (dc, c0, c1) in enumerate(self.dec):
+            edges.append((c0, c1, nlev - 2 - j))
+        edges = [(p, c, lvl) for p, c, lvl in edges if ok(c, lvl)]
         if _DEFER:
-            nlev = len(self.enc)
             last_c1 = self.dec[-1][2]
             if ncdhw_out and _final_is_fusable(self) and last_c1.spec.cop == 32:
                 plan.add(last_c1.name)                         # consumer: the fused output head
-            if not need_bwd:
-                def ok(consumer, lvl):
-                    return ops.deferred_src0_ok(consumer.spec, n, d >> lvl, h >> lvl, w >> lvl)
-
-                if self.head is not None and self.head.spec.cop == 32 and ok(self.enc[0][0], 0):
-                    plan.add(self.head.name); f16.add(self.enc[0][0].name)
-                for lvl, (c0, c1) in enumerate(self.enc):
-                    if ok(c1, lvl):
-                        plan.add(c0.name); f16.add(c1.name)
-                    if lvl < nlev - 1 and ok(self.dec[nlev - 2 - lvl][1], lvl):   # consumers: pooling pass + the skip conv
-                        plan.add(c1.name); f16.add(self.dec[nlev - 2 - lvl][1].name)
-                for j, (dc, c0, c1) in enumerate(self.dec):
-                    if ok(c1, nlev - 2 - j):
-                        plan.add(c0.name); f16.add(c1.name)
-        self._defer_plans[key] = (frozenset(plan), frozenset(f16))
+            if not need_bwd and _DEFER_CONV:
+                for p, c, _ in edges:
+                    plan.add(p.name); f16c.add(c.name)
+        if _FWD_F16:
+            for p, c, _ in edges:
+                if p.name not in plan:
+                    f16p.add(p.name); f16c.add(c.name)
+        self._defer_plans[key] = (frozenset(plan), frozenset(f16c), frozenset(f16p))
         return self._defer_plans[key]
 
 
 _DEFER = _os_env.environ.get("UB_DEFER", "1") != "0"
+# the conv operand path of deferred activations (deferred_tile.cuh): correct and tested, but on these shared-memory-
+# bound kernels it does not beat one materialising pass at HBM speed (profiles/r02_deferred_microbench.txt): opt-in
+_DEFER_CONV = _os_env.environ.get("UB_DEFER_CONV", "0") == "1"
+# fp16 operand copies of the activations in front of the marching forward convs (see _UNetGraph.defer_plan)
+_FWD_F16 = _os_env.environ.get("UB_FWD_F16", "1") != "0"
 
 
 def _check_unet_dims(d, h, w):
@@ -681,16 +713,26 @@ def _generator_run(net: _UNetGraph, a, need_bwd: bool, ncdhw_out: bool = False):
     base_seed = _fresh_seed() if any_dropout else 0
     cache = net.cache
     n, d, h, w, _ = a.shape
-    deferred, f16_consumers = net.defer_plan(n, d, h, w, ncdhw_out, need_bwd)
+    deferred, f16_consumers, f16_producers = net.defer_plan(n, d, h, w, ncdhw_out, need_bwd)
     cache.refresh(net.fwd_blocks(), 0, f16_src0=f16_consumers)
     S = {}          # block name -> saved
     lid = [0]
 
-    def run(blk, s0, s1=None, pool=False):
+    def run(blk, s0, s1=None, pool=False, bf16_consumer=False):
+        """``s0`` may be an ``_Act``: a conv listed in ``f16_consumers`` reads its fp16 copy, everything else (and
+        the weight gradient later) its bf16 tensor. ``bf16_consumer``: somebody downstream in THIS pass reads the
+        block's bf16 tensor (a generic-kernel conv), so it is written even without a backward."""
         lid[0] += 1
-        a_, pooled, sv = _block_forward(blk, cache, s0, s1, (base_seed + 7919 * lid[0]) & 0x7FFFFFFF,
+        fwd_src, saved_src = s0, None
+        if isinstance(s0, _Act):
+            fwd_src = s0.a16 if blk.name in f16_consumers else s0.a
+            saved_src = s0.a
+            if fwd_src is None:
+                raise RuntimeError(f"{blk.name}: the producer's bf16 activations were not materialised in this pass")
+        a_, pooled, sv = _block_forward(blk, cache, fwd_src, s1, (base_seed + 7919 * lid[0]) & 0x7FFFFFFF,
                                         pool=pool, save=need_bwd, defer=blk.name in deferred,
-                                        defer_f16=bool(f16_consumers))
+                                        defer_f16=bool(f16_consumers), f16_copy=blk.name in f16_producers,
+                                        keep_bf16=need_bwd or bf16_consumer, src0_saved=saved_src)
         S[blk.name] = sv
         return a_, pooled
 

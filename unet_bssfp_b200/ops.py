@@ -192,7 +192,8 @@ def conv_fwd(spec: ConvSpec, src0, src1, w_packed, bias, act=0, slope=0.0, want_
     desc = spec.desc(n, d, h, w)
     od, oh, ow = spec.out_dims(d, h, w)
     s0, act0, _keep = _split_deferred(src0)
-    if act0 is None:
+    src0_f16 = 1 if (act0 is None and s0.dtype == torch.float16) else 0     # a materialised fp16 operand copy
+    if act0 is None and not src0_f16:
         _require_dtype(s0, torch.bfloat16, "conv_fwd: src0")
     _require_dtype(src1, torch.bfloat16, "conv_fwd: src1")
     out = torch.empty((n, od, oh, ow, spec.cop), dtype=torch.float16 if want_stats else torch.bfloat16, device=s0.device)
@@ -201,7 +202,7 @@ def conv_fwd(spec: ConvSpec, src0, src1, w_packed, bias, act=0, slope=0.0, want_
         tiles = lib.ub_conv_num_tiles(C.byref(desc))
         stats = torch.empty((tiles, 2, spec.cop), dtype=torch.float32, device=s0.device)
     _lib.check(lib.ub_conv_fwd(C.byref(desc), _p(s0), _p(src1), _p(w_packed), _p(bias), act, slope, _p(out),
-                               _p(stats), act0, _stream()), "ub_conv_fwd")
+                               _p(stats), act0, src0_f16, _stream()), "ub_conv_fwd")
     return out, stats
 
 
@@ -429,19 +430,21 @@ def bn_running_update(mean, rstd, c, count, eps, momentum, running_mean, running
                                                 _p(running_var), _stream()), "ub_bn_running_update")
 
 
-def norm_act_fwd(y, scale, shift, slope, drop_p=0.0, drop_seed=0, pool=False, materialize=True):
-    """y (float16) -> (a bf16 | None, pooled bf16 | None). ``materialize=False`` (needs ``pool``): only the pooled
-    tensor is written, the activations stay deferred."""
+def norm_act_fwd(y, scale, shift, slope, drop_p=0.0, drop_seed=0, pool=False, materialize=True, f16_copy=False):
+    """y (float16) -> (a bf16 | None, pooled bf16 | None), or with ``f16_copy`` -> (a, pooled, a16): ``a16`` holds the
+    same fp32 values rounded to float16 -- the operand copy a marching forward conv takes as source 0 (fp16 x fp16
+    MMAs). ``materialize=False`` (needs ``pool`` or ``f16_copy``): the bf16 tensor is not written."""
     lib = _lib.load()
     _require_dtype(y, torch.float16, "norm_act_fwd: y")
-    if not materialize and not pool:
-        raise RuntimeError("norm_act_fwd: nothing to compute (materialize=False without pool)")
+    if not materialize and not pool and not f16_copy:
+        raise RuntimeError("norm_act_fwd: nothing to compute (materialize=False without pool / f16_copy)")
     n, d, h, w, cp = y.shape
     a = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device) if materialize else None
+    a16 = torch.empty(y.shape, dtype=torch.float16, device=y.device) if f16_copy else None
     pooled = torch.empty((n, d // 2, h // 2, w // 2, cp), dtype=torch.bfloat16, device=y.device) if pool else None
     _lib.check(lib.ub_norm_act_fwd(_p(y), _p(scale), _p(shift), slope, drop_p, drop_seed & 0xFFFFFFFF, n, d, h, w, cp,
-                                   _p(a), _p(pooled), _stream()), "ub_norm_act_fwd")
-    return a, pooled
+                                   _p(a), _p(a16), _p(pooled), _stream()), "ub_norm_act_fwd")
+    return (a, pooled, a16) if f16_copy else (a, pooled)
 
 
 def norm_act_bwd(dA, a, y, mode, mean, rstd, scale, slope, drop_p, drop_seed, c, want_param_grads=True,
