@@ -48,7 +48,7 @@ def _worker(rank, world, port, q):
     out = two["a"](x).sum() + (two["b"](x).sum() if rank == 0 else 0.0)
     out.backward()
     gb0 = two["b"].weight.grad.clone() if rank == 0 else torch.zeros_like(two["b"].weight)
-    GradAllReducer(two)()                             # must not hang; missing slots count as zeros
+    GradAllReducer(two, check_unused=True)()          # must not hang; missing slots count as zeros
     gb = [None] * world
     dist.all_gather_object(gb, gb0)
     ok = ok and two["b"].weight.grad is not None and torch.allclose(two["b"].weight.grad, sum(gb) / world)

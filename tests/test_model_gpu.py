@@ -458,6 +458,14 @@ def test_bf16_input_is_a_bit_identical_transport_format():
     y = torch.rand(2, 6, 32, 32, 32, device=DEV)
     assert torch.equal(ub.ops.pack_ncdhw(x16), ub.ops.pack_ncdhw(x32))
     assert torch.equal(ub.ops.pack_ncdhw(x16, y, s2d=True), ub.ops.pack_ncdhw(x32, y, s2d=True))
+    ub.ops._WIDEN_BF16_INPUT = False            # the kernels' own bf16 read path (ub_pack_ncdhw with a_bf16 = 1)
+    try:
+        assert torch.equal(ub.ops.pack_ncdhw(x16), ub.ops.pack_ncdhw(x32))
+        assert torch.equal(ub.ops.pack_ncdhw(x16, y, s2d=True), ub.ops.pack_ncdhw(x32, y, s2d=True))
+        odd = x16[:, :, :5, :5, :5].contiguous()        # odd voxel count: the one-voxel-per-thread kernel
+        assert torch.equal(ub.ops.pack_ncdhw(odd), ub.ops.pack_ncdhw(odd.float()))
+    finally:
+        ub.ops._WIDEN_BF16_INPUT = True
     outs = []
     for x in (x16, x32):
         for p in list(g.parameters()) + list(d.parameters()):

@@ -297,6 +297,69 @@ pack_ncdhw_kernel(const void* __restrict__ a_raw, int ca, const float* __restric
   }
 }
 
+// The same pack for a bf16 input `a` (NCDHW bf16: the transport format of the conditioning input), two voxels per
+// thread: a 4-byte load per channel plane covers the voxel pair (v, v + 1), so a warp reads whole 32-byte sectors
+// like the fp32 kernel does (one bf16 per lane would touch twice the sectors per byte). V (and for S2D: W) even.
+template <int CP, bool S2D, int UNROLL>
+__global__ void __launch_bounds__(256)
+pack_ncdhw_a16_kernel(const __nv_bfloat16* __restrict__ a, int ca, const float* __restrict__ b, int cb,
+                      __nv_bfloat16* __restrict__ dst, long long V, int D, int H, int W) {
+  constexpr int OCT = CP / 8;
+  constexpr int PPB = 256 / OCT;         // voxel pairs per block pass
+  const int n = blockIdx.y;
+  const int oct = threadIdx.x % OCT;
+  const long long p0 = (long long)blockIdx.x * (PPB * UNROLL) + threadIdx.x / OCT;
+  const __nv_bfloat16* sa[8];
+  const float* sb[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = oct * 8 + k;
+    sa[k] = c < ca ? a + ((size_t)n * ca + c) * V : nullptr;
+    sb[k] = (c >= ca && c < ca + cb) ? b + ((size_t)n * cb + (c - ca)) * V : nullptr;
+  }
+  float g0[UNROLL][8], g1[UNROLL][8];
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    const long long v = 2 * (p0 + (long long)u * PPB);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float x0 = 0.f, x1 = 0.f;
+      if (v < V) {
+        if (sa[k] != nullptr) {
+          const uint32_t w2 = __ldg(reinterpret_cast<const uint32_t*>(sa[k] + v));
+          x0 = __uint_as_float(w2 << 16);
+          x1 = __uint_as_float(w2 & 0xFFFF0000u);
+        } else if (sb[k] != nullptr) {
+          const float2 f2 = __ldg(reinterpret_cast<const float2*>(sb[k] + v));
+          x0 = f2.x; x1 = f2.y;
+        }
+      }
+      g0[u][k] = x0; g1[u][k] = x1;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < UNROLL; ++u) {
+    const long long v = 2 * (p0 + (long long)u * PPB);
+    if (v >= V) continue;
+    size_t row0, row1;
+    if (S2D) {
+      const int w = (int)(v % W);          // even
+      const long long t = v / W;
+      const int h = (int)(t % H), d = (int)(t / H);
+      const size_t par = (size_t)n * 8 + ((d & 1) * 4 + (h & 1) * 2);
+      const size_t inner = ((size_t)(d >> 1) * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
+      const size_t sub = (size_t)(D >> 1) * (H >> 1) * (W >> 1);
+      row0 = par * sub + inner;            // parity (.., .., 0)
+      row1 = (par + 1) * sub + inner;      // parity (.., .., 1): the odd neighbour lands at the same sub-volume offset
+    } else {
+      row0 = (size_t)n * V + v;
+      row1 = row0 + 1;
+    }
+    st_stream(reinterpret_cast<bf16x8*>(dst + row0 * CP) + oct, pack8(g0[u]));
+    st_stream(reinterpret_cast<bf16x8*>(dst + row1 * CP) + oct, pack8(g1[u]));
+  }
+}
+
 // Patch gather (sliding-window inference): sample n of the output batch is the d x h x w sub-volume of an
 // NCDHW fp32 tensor that starts at element offset G.offset[n]; element (c, z, y, x) of it lives at
 // + c * stride_c + z * stride_d + y * stride_h + x. Replaces torchio's GridSampler patch extraction

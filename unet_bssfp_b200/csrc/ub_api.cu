@@ -1018,14 +1018,27 @@ static int launch_pack(const void* a, int a_bf16, int ca, const float* b, int cb
                        int cp, void* out, cudaStream_t st) {
   constexpr int UNROLL = 4;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  // bf16 input: the two-voxels-per-thread kernel (needs an even voxel count; S2D always has even dims)
+  const bool pairs = a_bf16 && (voxels % 2 == 0) && (!S2D || w % 2 == 0);
+  const __nv_bfloat16* a16 = reinterpret_cast<const __nv_bfloat16*>(a);
   if (cp == 32) {
-    const dim3 grid((unsigned)((voxels + 64 * UNROLL - 1) / (64 * UNROLL)), n);
-    if (a_bf16) pack_ncdhw_kernel<32, S2D, UNROLL, true><<<grid, 256, 0, st>>>(a, ca, b, cb, o, voxels, d, h, w);
-    else pack_ncdhw_kernel<32, S2D, UNROLL, false><<<grid, 256, 0, st>>>(a, ca, b, cb, o, voxels, d, h, w);
+    if (pairs) {
+      const dim3 grid((unsigned)((voxels / 2 + 64 * UNROLL - 1) / (64 * UNROLL)), n);
+      pack_ncdhw_a16_kernel<32, S2D, UNROLL><<<grid, 256, 0, st>>>(a16, ca, b, cb, o, voxels, d, h, w);
+    } else {
+      const dim3 grid((unsigned)((voxels + 64 * UNROLL - 1) / (64 * UNROLL)), n);
+      if (a_bf16) pack_ncdhw_kernel<32, S2D, UNROLL, true><<<grid, 256, 0, st>>>(a, ca, b, cb, o, voxels, d, h, w);
+      else pack_ncdhw_kernel<32, S2D, UNROLL, false><<<grid, 256, 0, st>>>(a, ca, b, cb, o, voxels, d, h, w);
+    }
   } else {
-    const dim3 grid((unsigned)((voxels + 32 * UNROLL - 1) / (32 * UNROLL)), n);
-    if (a_bf16) pack_ncdhw_kernel<64, S2D, UNROLL, true><<<grid, 256, 0, st>>>(a, ca, b, cb, o, voxels, d, h, w);
-    else pack_ncdhw_kernel<64, S2D, UNROLL, false><<<grid, 256, 0, st>>>(a, ca, b, cb, o, voxels, d, h, w);
+    if (pairs) {
+      const dim3 grid((unsigned)((voxels / 2 + 32 * UNROLL - 1) / (32 * UNROLL)), n);
+      pack_ncdhw_a16_kernel<64, S2D, UNROLL><<<grid, 256, 0, st>>>(a16, ca, b, cb, o, voxels, d, h, w);
+    } else {
+      const dim3 grid((unsigned)((voxels + 32 * UNROLL - 1) / (32 * UNROLL)), n);
+      if (a_bf16) pack_ncdhw_kernel<64, S2D, UNROLL, true><<<grid, 256, 0, st>>>(a, ca, b, cb, o, voxels, d, h, w);
+      else pack_ncdhw_kernel<64, S2D, UNROLL, false><<<grid, 256, 0, st>>>(a, ca, b, cb, o, voxels, d, h, w);
+    }
   }
   UB_LAUNCH_CHECK();
   return 0;

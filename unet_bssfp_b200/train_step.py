@@ -59,9 +59,13 @@ class GradAllReducer:
     rank produced is a VIEW of the reduced buffer holding the SUM; ``scale`` (1 / world size) is handed to the
     optimizer (``FusedAdamW.grad_scale``) or applied here for foreign optimizers."""
 
-    def __init__(self, module, group=None):
+    def __init__(self, module, group=None, check_unused=False):
         self.params = [p for p in module.parameters()]
         self.group = group
+        # check_unused: agree across ranks on WHICH parameters received a gradient (one more small all-reduce and a
+        # host sync per call). Off by default: in this model the set is a function of the phase, not of the data, so
+        # every rank has the same one and the local answer is the global one.
+        self.check_unused = check_unused
         self.flat = None
         self.offsets = []
         off = 0
@@ -79,7 +83,7 @@ class GradAllReducer:
         if self.flat is None or self.flat.device != dev:
             self.flat = torch.empty(self.numel, dtype=torch.float32, device=dev)
         views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
-        have = torch.tensor([0.0 if p.grad is None else 1.0 for p in self.params], device=dev)
+        have = [0.0 if p.grad is None else 1.0 for p in self.params]
         live = [(v, p.grad) for v, p in zip(views, self.params) if p.grad is not None]
         dead = [v for v, p in zip(views, self.params) if p.grad is None]
         if live:
@@ -87,10 +91,12 @@ class GradAllReducer:
         if dead:
             torch._foreach_zero_(dead)
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)   # SUM + scale: works on nccl and gloo
-        dist.all_reduce(have, op=dist.ReduceOp.MAX, group=self.group)        # which slots ANY rank produced
+        if self.check_unused:
+            have_t = torch.tensor(have, device=dev)
+            dist.all_reduce(have_t, op=dist.ReduceOp.MAX, group=self.group)  # which slots ANY rank produced
+            have = have_t.tolist()
         if apply_scale:
             self.flat.mul_(1.0 / world)
-        have = have.tolist()
         for v, p, h in zip(views, self.params, have):
             if h > 0:
                 p.grad = v                  # alias the reduced buffer: no copy back
