@@ -175,6 +175,17 @@ int ub_conv1x1_to_ncdhw(const void* u, int cp, const float* w, int ci, const flo
 int ub_conv1x1_from_ncdhw_bwd(const float* dout, int co, const void* u, int cp, const float* w, int ci, int n,
                               long long voxels, void* workspace, void* du, float* dw, float* db,
                               const ub_deferred_act* u_act, void* stream);
+/* The backward of the head when its input is the DEFERRED activation of a conv -> norm -> dropout -> LeakyReLU block
+ * (`blk`: that block's y (fp16, 32 channels), scale / shift / mean / rstd [n][32]; blk->partial is not used), fused
+ * with that block's norm backward: returns the block's dy (NDHWC bf16) straight from dout, without materialising du
+ * (two passes over dout and y instead of three passes over du, dA and y), plus the block's dgamma / dbeta / dbias
+ * ([c], may be NULL) and the head's dw [co][ci] / db [co] (may be NULL). mode: UB_NORM_* of the block; c: its real
+ * channels. voxels per sample must be a multiple of 16. workspace: ub_head_bwd_fused_workspace_bytes(n) bytes.
+ * ref: monai BasicUNet.final_conv after upcat_1 (TwoConv -> ADN "NDA"), ref:model.py:22-28 */
+long long ub_head_bwd_fused_workspace_bytes(int n);
+int ub_head_bwd_fused(const float* dout, int co, const float* w, int ci, int n, long long voxels,
+                      const ub_norm_bwd_fuse* blk, int mode, int c, void* workspace, void* dy, float* dgamma,
+                      float* dbeta, float* dbias, float* dw, float* db, void* stream);
 
 /* ---- normalisation + dropout + activation --------------------------------------------------- */
 enum { UB_NORM_INSTANCE = 0, UB_NORM_BATCH_TRAIN = 1, UB_NORM_BATCH_EVAL = 2, UB_NORM_NONE = 3 };
@@ -216,6 +227,14 @@ int ub_norm_act_bwd(const void* dA, const void* a, const void* y, int mode, cons
  * a_act != NULL: `a` points at the block's y (fp16) and is a deferred activation */
 int ub_maxpool_bwd(const void* a, const void* dP, void* dA, int accumulate, int n, int d, int h, int w,
                    int cp, const ub_deferred_act* a_act, void* stream);
+/* The same routing for a conv -> norm -> dropout -> LeakyReLU block whose dA is COMPLETE after this pass (skip
+ * gradient + routed pool gradient: the second conv of every encoder level), fused with that block's norm-backward
+ * reduction: the activations are recomputed from fuse->y (cp channels here, constants [n][cp]) and the kernel also
+ * accumulates S1 / S2 (see ub_norm_bwd_fuse) into fuse->partial[ub_maxpool_bwd_fuse_records()][2][cp]; pass them to
+ * ub_norm_act_bwd as ext_partial. ref: monai Down = MaxPool3d(2) + TwoConv, ref:model.py:22-28 */
+int ub_maxpool_bwd_fuse_records(int n, int d, int h, int w, int cp);   /* n-major; 0 = unsupported shape */
+int ub_maxpool_bwd_fused(const void* dP, void* dA, int accumulate, int n, int d, int h, int w, int cp,
+                         const ub_norm_bwd_fuse* fuse, void* stream);
 /* out[c] = sum over rows of x[rows][cp] (bias gradients of convs without a following norm) */
 long long ub_colsum_workspace_bytes(int cp);
 int ub_colsum(const void* x, long long rows, int cp, int c, void* workspace, float* out, void* stream);

@@ -134,6 +134,66 @@ def test_output_head_on_deferred_activations(drop_p):
     assert torch.equal(du, du2) and torch.equal(dw, dw2) and torch.equal(db, db2)
 
 
+@pytest.mark.parametrize("drop_p", [0.0, 0.05])
+@pytest.mark.parametrize("co,shape", [(6, (2, 4, 6, 10)), (6, (1, 16, 16, 32)), (3, (1, 2, 4, 4))])
+def test_output_head_mma_form_equals_cuda_core_form(co, shape, drop_p, monkeypatch):
+    """The warp-MMA output head (fp32 weights as three bf16 terms) against the CUDA-core kernel it replaces."""
+    ops = _ops()
+    n, d, h, w = shape
+    lazy, a = _producer(n, d, h, w, seed=12, drop_p=drop_p)
+    g = torch.Generator(device=DEV).manual_seed(13)
+    wt = torch.randn((co, 32, 1, 1, 1), device=DEV, generator=g) * 0.3
+    b = torch.randn((co,), device=DEV, generator=g)
+    got = ops.conv1x1_to_ncdhw(lazy, wt, b)
+    monkeypatch.setenv("UB_HEAD_CUDA_CORES", "1")
+    ref = ops.conv1x1_to_ncdhw(lazy, wt, b)
+    torch.cuda.synchronize()
+    assert ((got - ref).abs().max() / ref.abs().max()).item() < 2e-6
+
+
+@pytest.mark.parametrize("mode", ["instance", "batch_train"])
+@pytest.mark.parametrize("drop_p", [0.0, 0.05])
+@pytest.mark.parametrize("c,shape", [(32, (2, 4, 8, 10)), (32, (1, 16, 16, 32)), (24, (2, 2, 4, 4))])
+def test_head_backward_fused_with_norm_backward(c, shape, drop_p, mode):
+    """ub_head_bwd_fused (two warp-MMA passes over dout and y, du never written) against the chain it replaces:
+    ub_conv1x1_from_ncdhw_bwd -> ub_norm_act_bwd on the deferred block. Differences: dout and W enter the MMAs as bf16
+    and du is not rounded to bf16 in between."""
+    ops = _ops()
+    from unet_bssfp_b200 import _lib
+    n, d, h, w = shape
+    g = torch.Generator(device=DEV).manual_seed(21)
+    y = to_internal(torch.randn((n, c, d, h, w), device=DEV, generator=g) * 1.5 + 0.25, dtype=torch.float16)
+    yf = y[..., :c].float()
+    dims = (1, 2, 3) if mode == "instance" else (0, 1, 2, 3)
+    mean_c = yf.mean(dims, keepdim=True).expand(n, 1, 1, 1, c).reshape(n, c)
+    rstd_c = (yf.var(dims, unbiased=False, keepdim=True).expand(n, 1, 1, 1, c).reshape(n, c) + 1e-5).rsqrt()
+    gamma = torch.rand((c,), device=DEV, generator=g) + 0.5
+    beta = torch.randn((c,), device=DEV, generator=g) * 0.3
+    pad = lambda t: torch.cat([t, torch.zeros((n, 32 - c), device=DEV)], 1).contiguous()
+    mean, rstd = pad(mean_c), pad(rstd_c)
+    scale, shift = pad(gamma * rstd_c), pad(beta - mean_c * gamma * rstd_c)
+    seed, slope = 555, 0.1
+    imode = {"instance": _lib.UB_NORM_INSTANCE, "batch_train": _lib.UB_NORM_BATCH_TRAIN}[mode]
+    lazy = ops.DeferredAct(y, scale, shift, slope, drop_p, seed)
+    wt = torch.randn((6, c, 1, 1, 1), device=DEV, generator=g) * 0.3
+    go = torch.randn((n, 6, d, h, w), device=DEV, generator=g)
+    du, dw, db = ops.conv1x1_from_ncdhw_bwd(go, lazy, wt)
+    ref = ops.norm_act_bwd(du, None, y, imode, mean, rstd, scale, slope, drop_p, seed, c, shift=shift)
+    fuse = ops.NormBwdFusion(y, scale, shift, mean, rstd, slope, drop_p, seed)
+    assert ops.head_bwd_fused_ok(go, fuse)
+    dy, dgamma, dbeta, dbias, dw2, db2 = ops.head_bwd_fused(go, fuse, wt, imode, c)
+    torch.cuda.synchronize()
+    assert rel_l2(dy.float(), ref[0].float()) < 8e-3
+    if c < 32:
+        assert dy[..., c:].float().abs().max().item() == 0.0
+    assert rel_l2(dgamma, ref[1]) < 5e-3 and rel_l2(dbeta, ref[2]) < 5e-3
+    assert dbias.abs().max().item() == 0.0
+    assert rel_l2(dw2, dw) < 5e-3 and rel_l2(db2, db) < 1e-5
+    # and against fp32 torch autograd through the same (materialised) activations' mask / sign decisions
+    nograd = ops.head_bwd_fused(go, fuse, wt, imode, c, need_params=False, want_block_grads=False)
+    assert torch.equal(nograd[0], dy) and nograd[4] is None and nograd[1] is None
+
+
 @pytest.mark.parametrize("f16", [False, True])
 @pytest.mark.parametrize("drop_p", [0.0, 0.05])
 @pytest.mark.parametrize("c0,c1,co,shape", CONV_CASES[:4])

@@ -122,6 +122,71 @@ def test_maxpool_bwd_ties_and_accumulate():
     assert rel_to_max(from_internal(acc, c), base + ar.grad) < 5e-3
 
 
+@pytest.mark.parametrize("mode,drop_p", [("instance", 0.05), ("instance", 0.0), ("batch_train", 0.0)])
+@pytest.mark.parametrize("c,shape,accumulate", [(32, (2, 8, 16, 8), True), (64, (2, 4, 8, 8), True), (128, (1, 4, 4, 8), False),
+                                                (24, (1, 36, 40, 24), True)])
+def test_maxpool_bwd_fused_with_norm_backward_reduction(mode, drop_p, c, shape, accumulate):
+    """ub_maxpool_bwd_fused: the gradient it writes is bit-identical to ub_maxpool_bwd on the materialised
+    activations, and ub_norm_act_bwd fed with its partial records agrees with the separate reduction pass
+    (different summation order only)."""
+    strict_fp32()
+    ops = _ops()
+    from unet_bssfp_b200 import _lib
+    n, d, h, w = shape
+    cp = (c + 31) // 32 * 32
+    g = torch.Generator(device="cuda").manual_seed(11)
+    y = to_internal(torch.randn((n, c, d, h, w), device="cuda", generator=g) * 1.3 + 0.2, dtype=torch.float16)
+    gamma = torch.rand((c,), device="cuda", generator=g) + 0.5
+    beta = torch.randn((c,), device="cuda", generator=g) * 0.2
+    yf = from_internal(y, c)
+    imode = {"instance": _lib.UB_NORM_INSTANCE, "batch_train": _lib.UB_NORM_BATCH_TRAIN}[mode]
+    dims = (2, 3, 4) if mode == "instance" else (0, 2, 3, 4)
+    mean_t = yf.mean(dims, keepdim=True).expand(n, c, 1, 1, 1).reshape(n, c)
+    var_t = yf.var(dims, unbiased=False, keepdim=True).expand(n, c, 1, 1, 1).reshape(n, c)
+    rstd_t = (var_t + 1e-5).rsqrt()
+    pad = lambda t, v=0.0: torch.cat([t, torch.full((n, cp - c), v, device="cuda")], 1).contiguous()
+    mean, rstd = pad(mean_t), pad(rstd_t)
+    scale, shift = pad(gamma * rstd_t), pad(beta - mean_t * gamma * rstd_t)
+    seed = 777
+    a, _ = ops.norm_act_fwd(y, scale, shift, 0.1, drop_p, seed)
+    dP = to_internal(bf16_round(torch.randn((n, c, d // 2, h // 2, w // 2), device="cuda", generator=g)))
+    base = to_internal(bf16_round(torch.randn((n, c, d, h, w), device="cuda", generator=g))) if accumulate else None
+    want = ops.maxpool_bwd(a, dP, base.clone() if accumulate else None)
+    fuse = ops.NormBwdFusion(y, scale, shift, mean, rstd, 0.1, drop_p, seed)
+    assert ops.maxpool_bwd_fuse_records(n, d, h, w, cp) > 0
+    got, partial = ops.maxpool_bwd_fused(dP, base.clone() if accumulate else None, fuse)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    ref = ops.norm_act_bwd(want, None, y, imode, mean, rstd, scale, 0.1, drop_p, seed, c, shift=shift)
+    fus = ops.norm_act_bwd(got, None, y, imode, mean, rstd, scale, 0.1, drop_p, seed, c, shift=shift, partial=partial)
+    torch.cuda.synchronize()
+    assert rel_l2(fus[1], ref[1]) < 1e-4 and rel_l2(fus[2], ref[2]) < 1e-4          # dgamma, dbeta
+    assert rel_l2(fus[0].float(), ref[0].float()) < 1e-3
+    assert rel_to_max(fus[0].float(), ref[0].float()) < 1e-2
+
+
+@pytest.mark.parametrize("drop_p", [0.0, 0.05])
+@pytest.mark.parametrize("c,shape", [(32, (2, 8, 16, 8)), (64, (1, 5, 7, 9)), (512, (2, 2, 2, 2)), (24, (1, 33, 16, 20))])
+def test_lean_norm_backward_apply_equals_generic_kernel(drop_p, c, shape, monkeypatch):
+    """The instruction-lean apply kernel (statistics present, sign from y) is bit-identical to the generic one."""
+    ops = _ops()
+    from unet_bssfp_b200 import _lib
+    n, d, h, w = shape
+    cp = (c + 31) // 32 * 32
+    g = torch.Generator(device="cuda").manual_seed(3)
+    y = to_internal(torch.randn((n, c, d, h, w), device="cuda", generator=g), dtype=torch.float16)
+    dA = to_internal(bf16_round(torch.randn((n, c, d, h, w), device="cuda", generator=g)))
+    mean, rstd = torch.randn((n, cp), device="cuda", generator=g) * 0.1, torch.rand((n, cp), device="cuda", generator=g) + 0.5
+    scale, shift = torch.rand((n, cp), device="cuda", generator=g) + 0.5, torch.randn((n, cp), device="cuda", generator=g) * 0.1
+    args = (dA, None, y, _lib.UB_NORM_INSTANCE, mean, rstd, scale, 0.1, drop_p, 99, c)
+    lean = ops.norm_act_bwd(*args, shift=shift)
+    monkeypatch.setenv("UB_NAB_GENERIC", "1")
+    generic = ops.norm_act_bwd(*args, shift=shift)
+    torch.cuda.synchronize()
+    assert torch.equal(lean[0], generic[0])
+    assert torch.equal(lean[1], generic[1]) and torch.equal(lean[2], generic[2])
+
+
 def test_dropout_statistics_and_backward_mask():
     ops = _ops()
     from unet_bssfp_b200 import _lib

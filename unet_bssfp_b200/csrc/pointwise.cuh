@@ -919,6 +919,90 @@ norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloa
   }
 }
 
+// The same apply pass for the case every normed block of the networks takes (statistics present, activation sign
+// recomputed from y), written for the INSTRUCTION roof: ncu showed the generic kernel above issue-bound, not
+// HBM-bound (profiles/r02b_nab_apply_ncu_summary.txt: 219 warp instructions per 16-byte vector, 48 scalar constant
+// loads + ~100 ALU instructions of per-thread prologue amortised over only 4 vectors, DRAM at 4.3 of 6.5 TB/s).
+// Here the block derives the five per-channel constants ONCE into shared memory (thread = channel), every thread
+// reads its octet's 40 floats as ten 16-byte shared loads and then streams kApplyVPT vectors in rounds of four loads
+// in flight; dropout is a template parameter (no uniform branches in the loop), the tail test is one compare per
+// round for whole blocks. Arithmetic and rounding are those of the generic kernel (same expressions).
+constexpr int kApplyVPT = 8;   // 16-byte vectors per thread
+template <bool DROP>
+__global__ void __launch_bounds__(256, 2)
+norm_act_bwd_apply_y_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ y,
+                            __nv_bfloat16* __restrict__ dy, NormBwdArgs B, int Cp, uint32_t vps) {
+  __shared__ __align__(16) float ks[5][512];   // ka | kb | kc | sign-test scale | sign-test shift
+  const int n = blockIdx.y;
+  const float finv = DROP ? 1.f / (1.f - B.drop_p) : 1.f;
+  for (int c = threadIdx.x; c < Cp; c += 256) {
+    const size_t o = (size_t)n * Cp + c;
+    const float g = B.gscale[o], r = B.rstd[o], m = B.mean[o];
+    const float kc = -g * r * B.c2[o];
+    ks[0][c] = g;
+    ks[1][c] = -g * B.c1[o] - kc * m;
+    ks[2][c] = kc;
+    ks[3][c] = fold_inv(g, finv);
+    ks[4][c] = fold_inv(B.fshift[o], finv);
+  }
+  __syncthreads();
+  const uint32_t c8 = (uint32_t)Cp >> 3;
+  const int c0 = (int)(threadIdx.x % c8) * 8;
+  float ka[8], kb[8], kc[8], sc[8], sh[8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float4 a4 = *reinterpret_cast<const float4*>(&ks[0][c0 + 4 * h]);
+    const float4 b4 = *reinterpret_cast<const float4*>(&ks[1][c0 + 4 * h]);
+    const float4 c4 = *reinterpret_cast<const float4*>(&ks[2][c0 + 4 * h]);
+    const float4 s4 = *reinterpret_cast<const float4*>(&ks[3][c0 + 4 * h]);
+    const float4 t4 = *reinterpret_cast<const float4*>(&ks[4][c0 + 4 * h]);
+    ka[4 * h] = a4.x; ka[4 * h + 1] = a4.y; ka[4 * h + 2] = a4.z; ka[4 * h + 3] = a4.w;
+    kb[4 * h] = b4.x; kb[4 * h + 1] = b4.y; kb[4 * h + 2] = b4.z; kb[4 * h + 3] = b4.w;
+    kc[4 * h] = c4.x; kc[4 * h + 1] = c4.y; kc[4 * h + 2] = c4.z; kc[4 * h + 3] = c4.w;
+    sc[4 * h] = s4.x; sc[4 * h + 1] = s4.y; sc[4 * h + 2] = s4.z; sc[4 * h + 3] = s4.w;
+    sh[4 * h] = t4.x; sh[4 * h + 1] = t4.y; sh[4 * h + 2] = t4.z; sh[4 * h + 3] = t4.w;
+  }
+  const size_t base = (size_t)n * vps;
+  const bf16x8* dAv = reinterpret_cast<const bf16x8*>(dA) + base;
+  const bf16x8* yv = reinterpret_cast<const bf16x8*>(y) + base;
+  bf16x8* dyv = reinterpret_cast<bf16x8*>(dy) + base;
+  const float sinv = B.slope * finv;
+  const uint32_t blk0 = blockIdx.x * (256u * kApplyVPT);
+  const bool whole = blk0 + 256u * kApplyVPT <= vps;
+#pragma unroll 1
+  for (int rnd = 0; rnd < kApplyVPT / 4; ++rnd) {
+    const uint32_t i0 = blk0 + rnd * 1024u + threadIdx.x;
+    bf16x8 d_[4], y_[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t idx = i0 + u * 256u;
+      if (whole || idx < vps) {
+        d_[u] = ld_stream(dAv + idx);
+        y_[u] = ld_stream(yv + idx);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t idx = i0 + u * 256u;
+      if (!whole && idx >= vps) continue;
+      if (DROP) {
+        uint32_t mw[4];
+        dropout_maskw((unsigned long long)(base + idx) * 8ull, B.drop_seed, B.drop_thresh, mw);
+        apply_maskw(d_[u], mw);
+      }
+      float da[8], yy[8], o[8];
+      unpack8(d_[u], da);
+      unpack8h(y_[u], yy);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float dz = da[k] * (fmaf(yy[k], sc[k], sh[k]) > 0.f ? finv : sinv);
+        o[k] = fmaf(ka[k], dz, fmaf(kc[k], yy[k], kb[k]));
+      }
+      st_stream(dyv + idx, pack8(o));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // MaxPool3d(2) backward: route dP to the first maximum of each window (d,h,w scan order, as torch)
 // thread = (pooled voxel, 8 channels). accumulate != 0: dA += routed grad (skip-path grad already there)
@@ -972,6 +1056,123 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = (accumulate ? o[k] : 0.f) + (arg[k] == j ? g[k] : 0.f);
     st_stream(reinterpret_cast<bf16x8*>(dA) + e[j], pack8(o));
+  }
+}
+
+// The same routing for a block whose dA is COMPLETE after this pass (skip gradient + routed pool gradient), fused with
+// that block's norm-backward reduction: the kernel already holds the block's raw output y (the activations it
+// compares are recomputed from it, bit-identical to the materialised tensor), so it also accumulates
+//   S1[n,c] = sum dz,  S2[n,c] = sum dz * xhat,   dz = bf16(dA) * lrelu'(y * sc + sh) * keep / (1 - p)
+// into per-block records part[(n * gridDim.x + blockIdx.x)][2][Cp] (the format ub_norm_act_bwd takes as
+// ext_partial), and the separate reduction pass over dA and y (4 B / element) is not run for the encoder blocks.
+// Each block walks `iters` groups of 256 thread items so that a sample yields a few hundred records at most.
+// blockDim.x = 256 and Cp / 8 divides 256: a thread keeps one channel octet.
+__global__ void __launch_bounds__(256, 2)
+maxpool_bwd_sums_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dP,
+                        __nv_bfloat16* __restrict__ dA, int accumulate, int Cp, int D, int H, int W,
+                        uint32_t per_sample, int iters, NormActArgs A, const float* __restrict__ mean,
+                        const float* __restrict__ rstd, float* __restrict__ part) {
+  extern __shared__ float sh[];  // [2][256][8]
+  const int n = blockIdx.y;
+  const uint32_t c8 = (uint32_t)Cp >> 3;
+  const int cidx = (int)(threadIdx.x % c8);
+  const uint32_t Wp = W >> 1, Hp = H >> 1;
+  DeferredOctet K;
+  K.load(A, n, Cp, cidx * 8);
+  const float inv = K.has_drop ? 1.f / (1.f - A.drop_p) : 1.f;
+  const float sinv = A.slope * inv;
+  // 32-bit vector offsets inside the sample (vectors per sample < 2^31): window voxel j = (jd, jh, jw)
+  const uint32_t vps = (uint32_t)D * H * W * c8;
+  const uint32_t off_w = c8, off_h = (uint32_t)W * c8, off_d = (uint32_t)H * W * c8;
+  const bf16x8* ys = reinterpret_cast<const bf16x8*>(y) + (size_t)n * vps;
+  bf16x8* dAs = reinterpret_cast<bf16x8*>(dA) + (size_t)n * vps;
+  const bf16x8* dPs = reinterpret_cast<const bf16x8*>(dP) + (size_t)n * per_sample;
+  const unsigned long long ebase = (unsigned long long)n * vps * 8ull;   // element index of the sample's first channel
+  float s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+    const uint32_t j0 = (blockIdx.x * (uint32_t)iters + it) * 256u + threadIdx.x;
+    if (j0 >= per_sample) break;
+    uint32_t pv = j0 / c8;
+    const uint32_t wx = pv % Wp; pv /= Wp;
+    const uint32_t hy = pv % Hp;
+    const uint32_t dz_ = pv / Hp;
+    const uint32_t e00 = ((2 * dz_ * H + 2 * hy) * W + 2 * wx) * c8 + cidx;     // window voxel (0, 0, 0)
+    uint32_t arg = 0;          // 3 bits per channel: index of the first maximum of the window
+    {
+      // y is read through L1 (default caching): the second phase below re-reads the same 8 rows a few hundred
+      // cycles later instead of holding them in 32 registers (the kernel was register-bound at one block per SM)
+      bf16x8 raw[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(ys + e00 + (j >> 2) * off_d + ((j >> 1) & 1) * off_h + (j & 1) * off_w));
+        *reinterpret_cast<uint4*>(&raw[j]) = t;
+      }
+      float best[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) best[k] = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t ej = e00 + (j >> 2) * off_d + ((j >> 1) & 1) * off_h + (j & 1) * off_w;
+        float x[8];
+        unpack8(K.apply(raw[j], ebase + (unsigned long long)ej * 8ull), x);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (x[k] > best[k]) { best[k] = x[k]; arg = (arg & ~(7u << (3 * k))) | ((uint32_t)j << (3 * k)); }
+      }
+    }
+    float g[8];
+    unpack8(ld_stream(dPs + j0), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t ej = e00 + (j >> 2) * off_d + ((j >> 1) & 1) * off_h + (j & 1) * off_w;
+      float o[8];
+      if (accumulate) unpack8(ld_stream(dAs + ej), o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (accumulate ? o[k] : 0.f) + (((arg >> (3 * k)) & 7u) == (uint32_t)j ? g[k] : 0.f);
+      bf16x8 pk = pack8(o);
+      st_stream(dAs + ej, pk);
+      // reduction terms from the ROUNDED gradient (what the apply pass reads back) and the forward's own fma
+      if (K.has_drop) {
+        uint32_t mw[4];
+        dropout_maskw(ebase + (unsigned long long)ej * 8ull, K.seed, K.thresh, mw);
+        apply_maskw(pk, mw);
+      }
+      float da[8], yy[8];
+      unpack8(pk, da);
+      bf16x8 yraw;
+      *reinterpret_cast<uint4*>(&yraw) = __ldg(reinterpret_cast<const uint4*>(ys + ej));
+      unpack8h(yraw, yy);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float dz = da[k] * (fmaf(yy[k], K.sc[k], K.sh[k]) > 0.f ? inv : sinv);
+        s1[k] += dz;
+        s2[k] = fmaf(dz, yy[k], s2[k]);
+      }
+    }
+  }
+  // S2 = sum dz * xhat = rstd * sum dz*y - mean*rstd * sum dz
+  float* sh1 = sh;
+  float* sh2 = sh + 256 * 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float r = rstd[(size_t)n * Cp + cidx * 8 + k], m = mean[(size_t)n * Cp + cidx * 8 + k];
+    sh1[threadIdx.x * 8 + k] = s1[k];
+    sh2[threadIdx.x * 8 + k] = fmaf(r, s2[k], -m * r * s1[k]);
+  }
+  __syncthreads();
+  const int lanes_v = 256 / (int)c8;
+  for (int c = threadIdx.x; c < Cp; c += 256) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int l = 0; l < lanes_v; ++l) {
+      t1 += sh1[(l * c8 + (c >> 3)) * 8 + (c & 7)];
+      t2 += sh2[(l * c8 + (c >> 3)) * 8 + (c & 7)];
+    }
+    float* p = part + ((size_t)(n * gridDim.x + blockIdx.x) * 2) * Cp;
+    p[c] = t1;
+    p[Cp + c] = t2;
   }
 }
 
@@ -1104,7 +1305,22 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const __grid_co
   const bool real = rr >= 0 && cc >= 0;
   const float* src = w + (real ? (size_t)rr * A.stride_row + (size_t)cc * A.stride_col : 0);
   const bool f16 = col < A.f16_cols;
-  for (int blk = 0; blk < A.nblocks; ++blk) {
+  // the taps of a thread are independent loads from one or two cache lines: keep several in flight (the serial
+  // loop was latency-bound: 64 us for the generator's 135 MB of traffic)
+  int blk = 0;
+  for (; blk + 4 <= A.nblocks; blk += 4) {
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      v[q] = real ? __ldg(src + (size_t)(A.tapmap[blk + q] + fold_tap) * A.src_tap_stride) : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long i = (blk + q) * plane + j;
+      if (f16) reinterpret_cast<__half*>(out)[i] = __float2half_rn(v[q]);
+      else out[i] = __float2bfloat16_rn(v[q]);
+    }
+  }
+  for (; blk < A.nblocks; ++blk) {
     const float v = real ? __ldg(src + (size_t)(A.tapmap[blk] + fold_tap) * A.src_tap_stride) : 0.f;
     const long long i = blk * plane + j;
     if (f16) reinterpret_cast<__half*>(out)[i] = __float2half_rn(v);

@@ -12,6 +12,7 @@
 #include "igemm_march.cuh"
 #include "wgrad_march.cuh"
 #include "pointwise.cuh"
+#include "head_mma.cuh"
 #include "optim_io.cuh"
 #include "fp32_path.cuh"
 
@@ -40,6 +41,12 @@ static std::atomic<long long> g_launches{0};
     cudaError_t e_ = cudaGetLastError();                                                   \
     if (e_ != cudaSuccess) return fail(-3, "kernel launch failed: %s", cudaGetErrorString(e_)); \
   } while (0)
+
+// A/B switches for measurements (read on every call: tests and tools flip them inside one process)
+static bool env_flag(const char* name) {
+  const char* v = getenv(name);
+  return v && atoi(v) != 0;
+}
 
 extern "C" int ub_version(void) { return 100; }
 extern "C" const char* ub_last_error(void) { return g_err; }
@@ -1232,6 +1239,20 @@ extern "C" int ub_norm_act_bwd(const void* dA, const void* a, const void* y, int
                                                            dgamma, dbeta, dbias);
     UB_LAUNCH_CHECK();
   }
+  if (mode != UB_NORM_NONE && shift != nullptr && !env_flag("UB_NAB_GENERIC")) {
+    // statistics present, sign from y: the instruction-lean kernel
+    const dim3 grid((unsigned)((vps + 256 * kApplyVPT - 1) / (256 * kApplyVPT)), n);
+    if (drop_p > 0.f)
+      norm_act_bwd_apply_y_kernel<true><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dA),
+                                                              reinterpret_cast<const __nv_bfloat16*>(y),
+                                                              reinterpret_cast<__nv_bfloat16*>(dy), B, cp, (uint32_t)vps);
+    else
+      norm_act_bwd_apply_y_kernel<false><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dA),
+                                                               reinterpret_cast<const __nv_bfloat16*>(y),
+                                                               reinterpret_cast<__nv_bfloat16*>(dy), B, cp, (uint32_t)vps);
+    UB_LAUNCH_CHECK();
+    return 0;
+  }
   constexpr int UNROLL = 4;
   norm_act_bwd_apply_kernel<UNROLL><<<dim3((unsigned)((vps + 256 * UNROLL - 1) / (256 * UNROLL)), n), 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dA), reinterpret_cast<const __nv_bfloat16*>(a),
@@ -1258,6 +1279,42 @@ extern "C" int ub_maxpool_bwd(const void* a, const void* dP, void* dA, int accum
     maxpool_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(dP),
         reinterpret_cast<__nv_bfloat16*>(dA), accumulate, cp, n, d, h, w, (uint32_t)per_sample, A);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- max-pool backward fused with the norm-backward reduction of the block it completes ----
+static void maxpool_fuse_plan(int d, int h, int w, int cp, long long* per_sample, int* iters, int* blocks) {
+  *per_sample = ((long long)d * h * w / 8) * (cp / 8);
+  const long long nblk = (*per_sample + 255) / 256;
+  long long it = (nblk + 295) / 296;       // a few hundred records per sample at most (the finalize walks them)
+  if (it < 1) it = 1;
+  *iters = (int)it;
+  *blocks = (int)((nblk + it - 1) / it);
+}
+extern "C" int ub_maxpool_bwd_fuse_records(int n, int d, int h, int w, int cp) {
+  if (n <= 0 || cp % 8 || cp > 512 || 256 % (cp / 8) || ((d | h | w) & 1)) return 0;
+  long long ps; int it, nb;
+  maxpool_fuse_plan(d, h, w, cp, &ps, &it, &nb);
+  return n * nb;
+}
+extern "C" int ub_maxpool_bwd_fused(const void* dP, void* dA, int accumulate, int n, int d, int h, int w, int cp,
+                                    const ub_norm_bwd_fuse* f, void* stream) {
+  if (!dP || !dA || !f || !f->y || !f->scale || !f->shift || !f->mean || !f->rstd || !f->partial)
+    return fail(-1, "bad arguments to ub_maxpool_bwd_fused");
+  if (ub_maxpool_bwd_fuse_records(n, d, h, w, cp) <= 0 || n > 65535)
+    return fail(-2, "ub_maxpool_bwd_fused: unsupported shape (cp/8 must divide 256, even sizes)");
+  long long per_sample; int iters, blocks;
+  maxpool_fuse_plan(d, h, w, cp, &per_sample, &iters, &blocks);
+  if (per_sample >= (1ll << 31)) return fail(-2, "ub_maxpool_bwd_fused: sample too large");
+  NormActArgs A;
+  memset(&A, 0, sizeof(A));
+  A.scale = f->scale; A.shift = f->shift; A.slope = f->slope; A.drop_p = f->drop_p; A.drop_seed = f->drop_seed;
+  A.drop_thresh = drop_thresh(f->drop_p);
+  maxpool_bwd_sums_kernel<<<dim3((unsigned)blocks, n), 256, 2 * 256 * 8 * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(f->y), reinterpret_cast<const __nv_bfloat16*>(dP),
+      reinterpret_cast<__nv_bfloat16*>(dA), accumulate, cp, d, h, w, (uint32_t)per_sample, iters, A, f->mean, f->rstd,
+      f->partial);
   UB_LAUNCH_CHECK();
   return 0;
 }
@@ -1388,6 +1445,22 @@ extern "C" int ub_conv1x1_to_ncdhw(const void* u, int cp, const float* w, int ci
   memset(&A, 0, sizeof(A));
   if (u_act)
     if (int e = fill_deferred(&A, u_act)) return e;
+  if (voxels % 8 == 0 && !env_flag("UB_HEAD_CUDA_CORES")) {
+    // warp-level MMA form (head_mma.cuh): a warp takes kHeadFwdUnroll groups of 8 voxels per iteration
+    long long mb = (voxels / 8 + 8 * kHeadFwdUnroll - 1) / (8 * kHeadFwdUnroll);
+    if (mb > cap) mb = cap;
+    const dim3 mgrid((unsigned)mb, n);
+    switch (co) {
+#define UB_C1_FWD(C_) case C_: \
+      if (u_act) head_fwd_mma_kernel<C_, true><<<mgrid, 256, 0, st>>>(up, out, T, (uint32_t)voxels, A); \
+      else head_fwd_mma_kernel<C_, false><<<mgrid, 256, 0, st>>>(up, out, T, (uint32_t)voxels, A); \
+      break;
+      UB_C1_FWD(1) UB_C1_FWD(2) UB_C1_FWD(3) UB_C1_FWD(4) UB_C1_FWD(5) UB_C1_FWD(6) UB_C1_FWD(7) UB_C1_FWD(8)
+#undef UB_C1_FWD
+    }
+    UB_LAUNCH_CHECK();
+    return 0;
+  }
   switch (co) {
 #define UB_C1_FWD(C_) case C_: \
     if (u_act) conv1x1_to_ncdhw_kernel<C_, true><<<grid, 256, 0, st>>>(up, out, T, (uint32_t)voxels, A); \
@@ -1437,6 +1510,80 @@ extern "C" int ub_conv1x1_from_ncdhw_bwd(const float* dout, int co, const void* 
     conv1x1_bwd_finish_kernel<<<(kC1MaxCo * 33 + 3) / 4, dim3(32, 4), 0, st>>>(part, (int)(blocks * n), co, ci, dw, db);
     UB_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+// ---- output head backward fused with the norm backward of the block in front of it (head_mma.cuh) ----
+static int head_fused_bps(int n) {
+  int b = (2 * 148 + n - 1) / n;     // two resident blocks per SM over the whole grid
+  return b < 1 ? 1 : b;
+}
+extern "C" long long ub_head_bwd_fused_workspace_bytes(int n) {
+  const long long recs = (long long)n * head_fused_bps(n);
+  // [weight table | dW/db partials | S1/S2 partials | c1 | c2]
+  return (long long)sizeof(Conv1x1Weights) + (recs * kC1MaxCo * 33 + recs * 64 + 2ll * n * 32) * 4;
+}
+extern "C" int ub_head_bwd_fused(const float* dout, int co, const float* w, int ci, int n, long long voxels,
+                                 const ub_norm_bwd_fuse* blk, int mode, int c, void* workspace, void* dy,
+                                 float* dgamma, float* dbeta, float* dbias, float* dw, float* db, void* stream) {
+  if (!dout || !w || !blk || !blk->y || !blk->scale || !blk->shift || !blk->mean || !blk->rstd || !workspace || !dy ||
+      n <= 0 || n > 65535 || voxels <= 0)
+    return fail(-1, "bad arguments to ub_head_bwd_fused");
+  if (ci <= 0 || ci > 32 || co <= 0 || co > kC1MaxCo || c <= 0 || c > 32)
+    return fail(-2, "ub_head_bwd_fused supports ci <= 32, co <= %d (got ci=%d co=%d)", kC1MaxCo, ci, co);
+  if (voxels % 16 || voxels >= (1ll << 31)) return fail(-2, "ub_head_bwd_fused: voxels per sample must be a multiple of 16");
+  if (mode == UB_NORM_NONE) return fail(-2, "ub_head_bwd_fused: the block in front of the head must have a norm");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = fill_conv1x1_weights(w, ci, nullptr, co, workspace, st)) return e;
+  long long bps = head_fused_bps(n);
+  const long long max_b = (voxels / 16 + 7) / 8;
+  if (bps > max_b) bps = max_b;
+  const long long recs = (long long)n * head_fused_bps(n);
+  float* part_w = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + sizeof(Conv1x1Weights));
+  float* part_n = part_w + recs * kC1MaxCo * 33;
+  float* c1 = part_n + recs * 64;
+  float* c2 = c1 + (size_t)n * 32;
+  const Conv1x1Weights* T = reinterpret_cast<const Conv1x1Weights*>(workspace);
+  NormActArgs A;
+  memset(&A, 0, sizeof(A));
+  A.scale = blk->scale; A.shift = blk->shift; A.slope = blk->slope; A.drop_p = blk->drop_p; A.drop_seed = blk->drop_seed;
+  A.drop_thresh = drop_thresh(blk->drop_p);
+  const int want_w = (dw || db) ? 1 : 0;
+  const dim3 grid((unsigned)bps, n);
+  const __nv_bfloat16* yp = reinterpret_cast<const __nv_bfloat16*>(blk->y);
+  switch (co) {
+#define UB_HEAD_K1(C_) case C_: \
+    head_bwd_sums_mma_kernel<C_><<<grid, 256, 0, st>>>(dout, yp, T, (uint32_t)voxels, A, blk->mean, blk->rstd, want_w, part_w, part_n); \
+    break;
+    UB_HEAD_K1(1) UB_HEAD_K1(2) UB_HEAD_K1(3) UB_HEAD_K1(4) UB_HEAD_K1(5) UB_HEAD_K1(6) UB_HEAD_K1(7) UB_HEAD_K1(8)
+#undef UB_HEAD_K1
+  }
+  UB_LAUNCH_CHECK();
+  if (want_w) {
+    conv1x1_bwd_finish_kernel<<<(kC1MaxCo * 33 + 3) / 4, dim3(32, 4), 0, st>>>(part_w, (int)(bps * n), co, ci, dw, db);
+    UB_LAUNCH_CHECK();
+  }
+  norm_bwd_finalize_kernel<<<1, dim3(32, 32), 0, st>>>(part_n, (int)bps, n, 32, c, (double)voxels, mode, blk->scale, c1, c2,
+                                                      dgamma, dbeta, dbias);
+  UB_LAUNCH_CHECK();
+  NormBwdArgs B;
+  memset(&B, 0, sizeof(B));
+  B.slope = blk->slope; B.drop_p = blk->drop_p; B.drop_seed = blk->drop_seed; B.drop_thresh = drop_thresh(blk->drop_p);
+  B.mean = blk->mean; B.rstd = blk->rstd; B.gscale = blk->scale; B.c1 = c1; B.c2 = c2; B.fshift = blk->shift;
+  long long ab = (4ll * sm_count() + n - 1) / n;
+  if (ab > max_b) ab = max_b;
+  const dim3 agrid((unsigned)ab, n);
+  __nv_bfloat16* dyp = reinterpret_cast<__nv_bfloat16*>(dy);
+  const bool drop = blk->drop_p > 0.f;
+  switch (co) {
+#define UB_HEAD_K2(C_) case C_: \
+    if (drop) head_bwd_apply_mma_kernel<C_, true><<<agrid, 256, 0, st>>>(dout, yp, dyp, T, (uint32_t)voxels, B); \
+    else head_bwd_apply_mma_kernel<C_, false><<<agrid, 256, 0, st>>>(dout, yp, dyp, T, (uint32_t)voxels, B); \
+    break;
+    UB_HEAD_K2(1) UB_HEAD_K2(2) UB_HEAD_K2(3) UB_HEAD_K2(4) UB_HEAD_K2(5) UB_HEAD_K2(6) UB_HEAD_K2(7) UB_HEAD_K2(8)
+#undef UB_HEAD_K2
+  }
+  UB_LAUNCH_CHECK();
   return 0;
 }
 

@@ -306,23 +306,38 @@ def _join_side_stream(device):
         torch.cuda.current_stream().wait_stream(_side_streams[device])
 
 
-def _fusion_of(blk: _Block, sv: _Saved):
-    """Norm-backward fusion descriptor of a block whose dA a downstream dgrad is about to produce."""
-    if blk.norm is None or sv is None or sv.y is None or sv.y.shape[-1] != 32:
+def _fusion_of(blk: _Block, sv: _Saved, any_width=False):
+    """Norm-backward fusion descriptor of a block whose dA a downstream dgrad (32-channel blocks: the marching
+    kernel's epilogue) or, with ``any_width``, the max-pool backward is about to produce."""
+    if blk.norm is None or sv is None or sv.y is None or (sv.y.shape[-1] != 32 and not any_width):
         return None
     return ops.NormBwdFusion(sv.y, sv.scale, sv.shift, sv.mean, sv.rstd, blk.slope, sv.drop_p, sv.seed)
 
 
+# the max-pool backward of an encoder level completes dA of the level's second conv block: it accumulates that
+# block's norm-backward reductions on the way (ub_maxpool_bwd_fused), UB_POOL_FUSE=0 runs the separate pass
+_POOL_FUSE = _os.environ.get("UB_POOL_FUSE", "1") != "0"
+# the output head's backward runs fused with the norm backward of the (deferred) block in front of it
+_HEAD_FUSE = _os.environ.get("UB_HEAD_FUSE", "1") != "0"
+
+
 def _block_backward(blk: _Block, cache: _PackedWeights, sv: _Saved, dA, need_w, need_in, grads, partial=None,
-                    producer=None):
+                    producer=None, dy_pre=None):
     """Accumulates parameter grads into ``grads`` (dict id(param) -> tensor); returns
     (d_src0, d_src1, partial_of_producer). ``partial``: this block's norm-backward reductions if the
     dgrad that produced ``dA`` already accumulated them. ``producer`` = (block, saved) of the block
     whose activations are this conv's src0: when the dgrad runs on the marching kernel its epilogue
-    accumulates the producer's reductions."""
+    accumulates the producer's reductions. ``dy_pre`` = (dy, dgamma, dbeta, dbias): the norm / activation backward of
+    this block already ran (fused into the output head's backward); ``dA`` is not used."""
     spec = blk.spec
     co = spec.co
-    if blk.norm is not None:
+    if dy_pre is not None:
+        dy, dgamma, dbeta, dbias = dy_pre
+        if need_w:
+            grads[id(blk.norm.weight)] = dgamma
+            grads[id(blk.norm.bias)] = dbeta
+            grads[id(blk.conv.bias)] = dbias
+    elif blk.norm is not None:
         dy, dgamma, dbeta, dbias = ops.norm_act_bwd(dA, None, sv.y, sv.mode, sv.mean, sv.rstd, sv.scale, blk.slope,
                                                     sv.drop_p, sv.seed, co, want_param_grads=need_w,
                                                     want_bias_grad=need_w, shift=sv.shift, partial=partial)
@@ -791,19 +806,33 @@ class _GeneratorFunction(torch.autograd.Function):
         first_blk = net.head if net.head is not None else net.enc[0][0]
         cache.refresh([b for b in net.fwd_blocks() if need_x or b is not first_blk], 1)
 
-        def bwd(blk, dA, need_in=True, partial=None, producer=None):
+        def bwd(blk, dA, need_in=True, partial=None, producer=None, dy_pre=None):
             """-> (d_src0, d_src1, partial of ``producer``)."""
             need_w = any(pneed[id(p)] for p in blk.params())
             prod = (producer, S[producer.name]) if producer is not None else None
-            r = _block_backward(blk, cache, S[blk.name], dA, need_w, need_in, grads, partial=partial, producer=prod)
+            r = _block_backward(blk, cache, S[blk.name], dA, need_w, need_in, grads, partial=partial, producer=prod,
+                                dy_pre=dy_pre)
             S[blk.name] = None
             return r
 
+        head_dy = None      # (dy, dgamma, dbeta, dbias) of upcat_1.conv_1 when the head's backward produced them
         if _final_is_fusable(net):
             # output head: dgrad, wgrad and bias gradient in one pass over dout (NCDHW) and the saved input
             fw, fb = net.final.conv.weight, net.final.conv.bias
             need_w = pneed[id(fw)] or pneed[id(fb)]
-            du, dw_, db_ = ops.conv1x1_from_ncdhw_bwd(dout, S[net.final.name].src0, fw, need_input=True, need_params=need_w)
+            last_c1 = net.dec[-1][2]
+            src = S[net.final.name].src0
+            fuse = _fusion_of(last_c1, S[last_c1.name]) if (_HEAD_FUSE and isinstance(src, ops.DeferredAct)) else None
+            if fuse is not None and ops.head_bwd_fused_ok(dout, fuse):
+                # the block in front of the head is deferred: its norm backward runs inside the head's backward
+                # (ub_head_bwd_fused) and du is never written
+                need_blk = any(pneed[id(p)] for p in last_c1.params())
+                dy_, dg_, dbt_, dbs_, dw_, db_ = ops.head_bwd_fused(dout, fuse, fw, S[last_c1.name].mode, last_c1.spec.co,
+                                                                    need_params=need_w, want_block_grads=need_blk)
+                head_dy = (dy_, dg_, dbt_, dbs_)
+                du = None
+            else:
+                du, dw_, db_ = ops.conv1x1_from_ncdhw_bwd(dout, src, fw, need_input=True, need_params=need_w)
             if need_w:
                 grads[id(fw)], grads[id(fb)] = dw_, db_
             S[net.final.name] = None
@@ -814,7 +843,8 @@ class _GeneratorFunction(torch.autograd.Function):
         dskip = [None] * nlev
         for j in range(len(net.dec) - 1, -1, -1):      # upcat_1 first
             dc, c0, c1 = net.dec[j]
-            dt, _, part = bwd(c1, du, producer=c0)      # dt = dA of c0 (same resolution, chained)
+            dt, _, part = bwd(c1, du, producer=c0, dy_pre=head_dy)      # dt = dA of c0 (same resolution, chained)
+            head_dy = None
             d_xe, d_up, _ = bwd(c0, dt, partial=part)
             dskip[nlev - 2 - j] = d_xe
             du, _, _ = bwd(dc, d_up)
@@ -822,11 +852,15 @@ class _GeneratorFunction(torch.autograd.Function):
         part_head = None
         for lvl in range(nlev - 1, -1, -1):
             c0, c1 = net.enc[lvl]
+            part_c1 = None
             if lvl != nlev - 1:
                 # dcur is the grad of the pooled tensor; route it onto the skip grad of x_lvl
-                xk = S[c1.name].a
-                dcur = ops.maxpool_bwd(xk, dcur, dskip[lvl])
-            dt, _, part = bwd(c1, dcur, producer=c0)
+                fuse = _fusion_of(c1, S[c1.name], any_width=True) if _POOL_FUSE else None
+                if fuse is not None and ops.maxpool_bwd_fuse_records(*fuse.y.shape) > 0:
+                    dcur, part_c1 = ops.maxpool_bwd_fused(dcur, dskip[lvl], fuse)
+                else:
+                    dcur = ops.maxpool_bwd(S[c1.name].a, dcur, dskip[lvl])
+            dt, _, part = bwd(c1, dcur, partial=part_c1, producer=c0)
             first = lvl == 0
             dcur, _, part_head = bwd(c0, dt, need_in=(not first) or net.head is not None or need_x, partial=part,
                                      producer=net.head if (first and net.head is not None) else None)

@@ -307,6 +307,43 @@ def conv1x1_from_ncdhw_bwd(dout, u, weight, need_input=True, need_params=True):
     return du, dw, db
 
 
+def head_bwd_fused_ok(dout, fuse) -> bool:
+    """``head_bwd_fused`` serves this call: 32-channel block, voxels per sample a multiple of 16, <= 8 outputs."""
+    n, co = dout.shape[0], dout.shape[1]
+    vox = dout.shape[2] * dout.shape[3] * dout.shape[4]
+    return fuse is not None and fuse.y.shape[-1] == 32 and vox % 16 == 0 and co <= 8
+
+
+def head_bwd_fused(dout, fuse: NormBwdFusion, weight, mode, c, need_params=True, want_block_grads=True):
+    """Backward of ``conv1x1_to_ncdhw`` on the DEFERRED activations of the block described by ``fuse``, fused with that
+    block's norm backward (``ub_head_bwd_fused``): -> (dy of the block (N,D,H,W,32) bf16, dgamma, dbeta, dbias of the
+    block | None, dweight, dbias of the head | None). ``du`` is never materialised."""
+    _require_cuda(dout, weight)
+    lib = _lib.load()
+    y = fuse.y
+    _require_dtype(y, torch.float16, "head_bwd_fused: y")
+    n, d, h, w, cp = y.shape
+    co, ci = weight.shape[0], weight.shape[1]
+    dev = y.device
+    dout = dout.contiguous().float()
+    ws = torch.empty(lib.ub_head_bwd_fused_workspace_bytes(n) // 4, dtype=torch.float32, device=dev)
+    dy = torch.empty(y.shape, dtype=torch.bfloat16, device=dev)
+    dgamma = dbeta = dbias = dw = db = None
+    if want_block_grads:
+        dgamma = torch.empty(c, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(c, dtype=torch.float32, device=dev)
+        dbias = torch.empty(c, dtype=torch.float32, device=dev)
+    if need_params:
+        dw = torch.empty(tuple(weight.shape), dtype=torch.float32, device=dev)
+        db = torch.empty(co, dtype=torch.float32, device=dev)
+    wt = weight.detach().contiguous().float()
+    f = _lib.NormBwdFuse(y.data_ptr(), fuse.scale.data_ptr(), fuse.shift.data_ptr(), fuse.mean.data_ptr(),
+                         fuse.rstd.data_ptr(), fuse.slope, fuse.drop_p, fuse.drop_seed & 0xFFFFFFFF, None)
+    _lib.check(lib.ub_head_bwd_fused(_p(dout), co, _p(wt), ci, n, d * h * w, C.byref(f), mode, c, _p(ws), _p(dy),
+                                     _p(dgamma), _p(dbeta), _p(dbias), _p(dw), _p(db), _stream()), "ub_head_bwd_fused")
+    return dy, dgamma, dbeta, dbias, dw, db
+
+
 # ---------------------------------------------------------------------------------------------------
 # layout
 # ---------------------------------------------------------------------------------------------------
@@ -518,6 +555,34 @@ def maxpool_bwd(a, dP, dA=None):
         acc = 0
     _lib.check(lib.ub_maxpool_bwd(_p(a), _p(dP), _p(dA), acc, n, d, h, w, cp, act0, _stream()), "ub_maxpool_bwd")
     return dA
+
+
+def maxpool_bwd_fuse_records(n, d, h, w, cp) -> int:
+    """Partial records ``maxpool_bwd_fused`` emits for an (n, d, h, w, cp) activation tensor; 0 = unsupported."""
+    return _lib.load().ub_maxpool_bwd_fuse_records(n, d, h, w, cp)
+
+
+def maxpool_bwd_fused(dP, dA, fuse: NormBwdFusion):
+    """Max-pool backward of a conv -> norm block whose dA is complete after this pass, fused with that block's
+    norm-backward reduction: routes ``dP`` onto the arg-max voxels of the activations recomputed from ``fuse.y``
+    (accumulating onto ``dA`` if given) -> (dA, partial [records][2][cp]) for ``norm_act_bwd(partial=)``."""
+    lib = _lib.load()
+    y = fuse.y
+    _require_dtype(y, torch.float16, "maxpool_bwd_fused: y")
+    n, d, h, w, cp = y.shape
+    records = lib.ub_maxpool_bwd_fuse_records(n, d, h, w, cp)
+    if records <= 0:
+        raise RuntimeError("maxpool_bwd_fused: unsupported shape")
+    acc = 1
+    if dA is None:
+        dA = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device)
+        acc = 0
+    partial = torch.empty((records, 2, cp), dtype=torch.float32, device=y.device)
+    f = _lib.NormBwdFuse(y.data_ptr(), fuse.scale.data_ptr(), fuse.shift.data_ptr(), fuse.mean.data_ptr(),
+                         fuse.rstd.data_ptr(), fuse.slope, fuse.drop_p, fuse.drop_seed & 0xFFFFFFFF, partial.data_ptr())
+    _lib.check(lib.ub_maxpool_bwd_fused(_p(dP), _p(dA), acc, n, d, h, w, cp, C.byref(f), _stream()),
+               "ub_maxpool_bwd_fused")
+    return dA, partial
 
 
 def colsum(x, c):

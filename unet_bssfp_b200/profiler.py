@@ -20,7 +20,7 @@ KIND = {0: "k3", 1: "k1", 2: "k4s2", 3: "dc2", 4: "k4s2d"}
 TAPS = {0: 27, 1: 1, 2: 64, 3: 8, 4: 64}
 CONV_CLASS = {0: "igemm_fwd_kernel", 1: "igemm_march_kernel", 2: "wgrad_march_kernel", 3: "igemm_wgrad_kernel"}
 MEMORY_OPS = ("conv1x1_to_ncdhw", "conv1x1_from_ncdhw_bwd", "pack_ncdhw", "unpack_ncdhw", "norm_finalize", "norm_act_fwd",
-              "norm_act_bwd", "maxpool_bwd", "colsum", "l1_fwd", "l1_bwd", "bce_logits", "scale_by",
+              "norm_act_bwd", "maxpool_bwd", "maxpool_bwd_fused", "head_bwd_fused", "colsum", "l1_fwd", "l1_bwd", "bce_logits", "scale_by",
               "pack_conv_weights", "pack_conv_weights_multi")
 
 
@@ -103,7 +103,8 @@ def profile():
 
     def d_mem(name):
         def describe(out, *a, **k):
-            ts = list(_tensors(list(a) + list(k.values()) + [out]))
+            objs = [getattr(o, "y", o) if isinstance(o, ops.NormBwdFusion) else o for o in list(a) + list(k.values())]
+            ts = list(_tensors(objs + [out]))
             big = max(ts, key=lambda t: t.numel()) if ts else None
             return name, f"{tuple(big.shape) if big is not None else ()}", 0.0, _nbytes(*ts)
         return describe
