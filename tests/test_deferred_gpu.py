@@ -245,8 +245,8 @@ def test_fp16_operand_form_is_forward_only():
                                             ("bssfp", (1, 64, 64, 64), True)])
 def test_generator_with_and_without_deferral(mod, shape, train, monkeypatch):
     """The whole generator. WITH a backward to come only the block in front of the fused output head stays deferred
-    (a memory-bound consumer evaluating the canonical bf16 form): outputs, input gradient and every parameter
-    gradient agree BIT FOR BIT with the materialising path (dropout active in train mode: the mask is a counter
+    (a memory-bound consumer evaluating the canonical bf16 form): with the unfused head backward outputs, input
+    gradient and every parameter gradient agree BIT FOR BIT with the materialising path (dropout active in train mode: the mask is a counter
     hash, identical in both runs for the same seed). WITHOUT a backward (no_grad) all five full-resolution 32-channel
     blocks stay deferred and their conv consumers take the fp16-operand form: the output agrees with the
     materialising path to well below the bf16 noise of the network."""
@@ -261,9 +261,10 @@ def test_generator_with_and_without_deferral(mod, shape, train, monkeypatch):
     x = torch.rand(n, cin, d, h, w, device=DEV)
     dY = torch.randn(n, 6, d, h, w, device=DEV)
 
-    def run(defer):
+    def run(defer, head_fuse=False):
         monkeypatch.setattr(modules, "_DEFER", defer)
         monkeypatch.setattr(modules, "_DEFER_CONV", defer)      # the opt-in conv operand path as well
+        monkeypatch.setattr(modules, "_HEAD_FUSE", head_fuse)   # the head backward fused with the block's norm backward
         g._net()._defer_plans.clear()
         plan_bwd = g._net().defer_plan(n, d, h, w, True, True)[:2]
         plan_inf = g._net().defer_plan(n, d, h, w, True, False)[:2]
@@ -295,6 +296,16 @@ def test_generator_with_and_without_deferral(mod, shape, train, monkeypatch):
         assert torch.equal(gr1[k], gr0[k]), k
     assert torch.equal(inf0, out0)                               # materialising path: grad mode does not matter
     assert rel_l2(inf1, inf0) < 1.5e-2, rel_l2(inf1, inf0)       # fp16-operand form vs bf16 form of five blocks: bf16 noise
+    # The default backward of the deferred head (ub_head_bwd_fused: two warp-MMA passes, du never written, dout and W
+    # as bf16 MMA operands) is the same mathematics with different roundings: same forward bits, gradients within the
+    # bf16 noise of the chain it replaces.
+    _, _, out2, dx2, gr2, _ = run(True, head_fuse=True)
+    assert torch.equal(out2, out0)
+    assert rel_l2(dx2, dx0) < 3e-2, rel_l2(dx2, dx0)
+    worst = max((rel_l2(gr2[k], gr0[k]), k) for k in gr0 if gr0[k].norm() > 0)
+    assert worst[0] < 6e-2, worst
+    tot = torch.cat([(gr2[k] - gr0[k]).flatten() for k in gr0]).norm() / torch.cat([gr0[k].flatten() for k in gr0]).norm()
+    assert tot.item() < 2e-2, tot.item()
 
 
 @pytest.mark.parametrize("drop_p", [0.0, 0.05])

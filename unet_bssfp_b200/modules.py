@@ -314,9 +314,11 @@ def _fusion_of(blk: _Block, sv: _Saved, any_width=False):
     return ops.NormBwdFusion(sv.y, sv.scale, sv.shift, sv.mean, sv.rstd, blk.slope, sv.drop_p, sv.seed)
 
 
-# the max-pool backward of an encoder level completes dA of the level's second conv block: it accumulates that
-# block's norm-backward reductions on the way (ub_maxpool_bwd_fused), UB_POOL_FUSE=0 runs the separate pass
-_POOL_FUSE = _os.environ.get("UB_POOL_FUSE", "1") != "0"
+# the max-pool backward of an encoder level completes dA of the level's second conv block and CAN accumulate that
+# block's norm-backward reductions on the way (ub_maxpool_bwd_fused). Measured on B200 at 8 x 128^3 x 32 it does not
+# pay: 1.10 ms fused against 0.54 + 0.49 ms for the two passes (the fused kernel is issue- and latency-bound at 128
+# registers, profiles/r02d_pool_fused_ncu_summary.txt): opt-in with UB_POOL_FUSE=1
+_POOL_FUSE = _os.environ.get("UB_POOL_FUSE", "0") == "1"
 # the output head's backward runs fused with the norm backward of the (deferred) block in front of it
 _HEAD_FUSE = _os.environ.get("UB_HEAD_FUSE", "1") != "0"
 
