@@ -277,10 +277,21 @@ def _side_stream(device):
     return st
 
 
+_side_keep = {}     # device -> tensors the side stream may still be reading: held until the join
+
+
 def _wgrad_async(spec, src0, src1, dy, weight_shape, ready=None):
     """conv_wgrad on the side stream, ordered after ``ready`` (an event recorded once dy was complete; default:
     everything enqueued so far on the current stream). The caller joins with ``_join_side_stream`` before
-    the gradients leave the backward function."""
+    the gradients leave the backward function.
+
+    Memory: the operands stay referenced (``_side_keep``) until the join, after which the main stream is ordered
+    behind every side-stream kernel and freeing them is safe -- no ``Tensor.record_stream``. (With record_stream the
+    caching allocator could not reuse a freed operand until it had polled the side stream's events, answered with
+    fresh cudaMallocs instead, and kept growing for ~20 steps: 80 GiB reserved for 26 GiB of live tensors, with
+    synchronising device allocations inside timed steps -- tools/step_jitter.py, profiles/r02f_step_jitter.txt.)
+    The output and the workspace are allocated by ``ops.conv_wgrad`` while the side stream is current, i.e. from the
+    side stream's own pool, and ``dw`` is only read after the join."""
     if not _WGRAD_SIDE:
         return ops.conv_wgrad(spec, src0, src1, dy, weight_shape)
     main = torch.cuda.current_stream()
@@ -291,19 +302,14 @@ def _wgrad_async(spec, src0, src1, dy, weight_shape, ready=None):
         side.wait_stream(main)
     with torch.cuda.stream(side):
         dw = ops.conv_wgrad(spec, src0, src1, dy, weight_shape)
-    for t in (src0, src1, dy):
-        if isinstance(t, ops.DeferredAct):
-            for u in (t.y, t.scale, t.shift):
-                u.record_stream(side)
-        elif t is not None:
-            t.record_stream(side)          # the caching allocator must not recycle them under the side stream
-    dw.record_stream(main)
+    _side_keep.setdefault(dy.device, []).append((src0, src1, dy))
     return dw
 
 
 def _join_side_stream(device):
     if _WGRAD_SIDE and device in _side_streams:
         torch.cuda.current_stream().wait_stream(_side_streams[device])
+        _side_keep.pop(device, None)      # ordered behind the side stream now: the operands may be recycled
 
 
 def _fusion_of(blk: _Block, sv: _Saved, any_width=False):

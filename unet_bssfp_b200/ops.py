@@ -348,12 +348,13 @@ def head_bwd_fused(dout, fuse: NormBwdFusion, weight, mode, c, need_params=True,
 # layout
 # ---------------------------------------------------------------------------------------------------
 class _WidenedInput:
-    """fp32 image of the most recent bf16 module input. A bf16 ``x`` is a transport format (half the host-to-device
-    bytes of the conditioning input); one training step packs it four times (generator input + the three PatchGAN
-    calls), and the fp32 pack kernels read whole sectors where a 2-byte-per-lane read does not, so the input is
-    widened ONCE per tensor version (0.4 ms at 8 x 24 x 128^3) and every pack of that step uses the fast path. The
-    widening is exact, so the packed bits are those of packing the bf16 tensor directly. Held through a weak
-    reference: the cache never extends the life of a batch."""
+    """fp32 image of the most recent bf16 module input (opt-in, ``UB_WIDEN_BF16=1``). A bf16 ``x`` is a transport format
+    (half the host-to-device bytes of the conditioning input); one training step packs it four times (generator
+    input + the three PatchGAN calls). Round 2 first widened it once per tensor version because the two-voxels-per-
+    thread bf16 pack kernel ran at 2.25 ms against 0.41 ms for the fp32 kernel; that was a code-generation problem
+    (loads in separate basic blocks, then funnelled through one register -- see pack_ncdhw_a16_kernel), fixed since:
+    0.45 / 0.68 ms plain / space-to-depth, and a whole step is ~1 ms faster without the 1.6 GB widened copy. Kept for
+    A/B. Held through a weak reference: the cache never extends the life of a batch."""
 
     def __init__(self):
         self._ref = self._key = self._wide = None
@@ -373,7 +374,8 @@ class _WidenedInput:
 
 
 _widened_input = _WidenedInput()
-_WIDEN_BF16_INPUT = True      # False: feed bf16 inputs to the pack kernels directly (ub_pack_ncdhw a_bf16 = 1)
+import os as _os
+_WIDEN_BF16_INPUT = _os.environ.get("UB_WIDEN_BF16", "0") == "1"      # default: bf16 inputs go to the pack kernels as they are
 
 
 def pack_ncdhw(a: torch.Tensor, b: torch.Tensor | None = None, s2d: bool = False) -> torch.Tensor:
