@@ -285,9 +285,12 @@ pack_ncdhw_kernel(const void* __restrict__ a_raw, int ca, const float* __restric
     if (v >= V) continue;
     size_t row;
     if (S2D) {
-      const int w = (int)(v % W);
-      const long long t = v / W;
-      const int h = (int)(t % H), d = (int)(t / H);
+      // 32-bit index math (the host checks voxels per sample < 2^31): 64-bit divisions by run-time values cost
+      // ~100 instructions each and made the space-to-depth pack 25 % slower than the plain one
+      const uint32_t v32 = (uint32_t)v;
+      const int w = (int)(v32 % (uint32_t)W);
+      const uint32_t t = v32 / (uint32_t)W;
+      const int h = (int)(t % (uint32_t)H), d = (int)(t / (uint32_t)H);
       const size_t par = (size_t)n * 8 + ((d & 1) * 4 + (h & 1) * 2 + (w & 1));
       row = ((par * (D >> 1) + (d >> 1)) * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
     } else {
@@ -347,9 +350,10 @@ pack_ncdhw_a16_kernel(const __nv_bfloat16* __restrict__ a, int ca, const float* 
     if (v >= V) continue;
     size_t row0, row1;
     if (S2D) {
-      const int w = (int)(v % W);          // even
-      const long long t = v / W;
-      const int h = (int)(t % H), d = (int)(t / H);
+      const uint32_t v32 = (uint32_t)v;    // 32-bit index math, see pack_ncdhw_kernel
+      const int w = (int)(v32 % (uint32_t)W);          // even
+      const uint32_t t = v32 / (uint32_t)W;
+      const int h = (int)(t % (uint32_t)H), d = (int)(t / (uint32_t)H);
       const size_t par = (size_t)n * 8 + ((d & 1) * 4 + (h & 1) * 2);
       const size_t inner = ((size_t)(d >> 1) * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
       const size_t sub = (size_t)(D >> 1) * (H >> 1) * (W >> 1);

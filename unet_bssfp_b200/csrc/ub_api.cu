@@ -1063,6 +1063,7 @@ extern "C" int ub_pack_ncdhw_s2d(const void* a, int a_bf16, int ca, const float*
   if (!a || !out || ca <= 0 || n <= 0 || n > 65535 || (cb > 0 && !b)) return fail(-1, "bad arguments to ub_pack_ncdhw_s2d");
   if (ca + cb > cp || cp % 32 || cp > 64) return fail(-1, "ub_pack_ncdhw_s2d supports cp in {32, 64}, got ca=%d cb=%d cp=%d", ca, cb, cp);
   if (d <= 0 || h <= 0 || w <= 0 || ((d | h | w) & 1)) return fail(-1, "ub_pack_ncdhw_s2d needs even positive dims");
+  if ((long long)d * h * w >= (1ll << 31)) return fail(-2, "ub_pack_ncdhw_s2d: sample too large");
   return launch_pack<true>(a, a_bf16, ca, b, cb, n, (long long)d * h * w, d, h, w, cp, out, (cudaStream_t)stream);
 }
 
