@@ -2,12 +2,14 @@
 on the same weights and inputs, and against the committed goldens.
 
 Tolerances. north_star asks for 1e-2 relative in bf16. Per-op on identical inputs that bar is met
-(tests/test_conv_gpu.py). End to end through 24 stacked bf16 layers the reference *itself* does not
-meet it: torch's own bf16 autocast of the oracle is ~1.4e-2 rel-L2 on the generator output, and
-LeakyReLU / max-pool sign flips make per-tensor weight-gradient errors ~0.3.
-So the end-to-end bar is: forward rel-L2 <= 2e-2, and every error <= 1.25 x the error of the
-oracle run under torch.autocast(bf16) (measured in the same test), i.e. "as close to the fp32
-reference as stock bf16 PyTorch is"."""
+(tests/test_conv_gpu.py). End to end through 24 stacked layers the generator's eval forward is at
+rel-L2 6.8e-3 ... 8.9e-3 against the fp32 oracle for every shape tested here (32^3 ... 8 x 128^3, both
+modalities; tools/parity_values.py, profiles/r02f_parity_values.txt) -- torch's own bf16 autocast of the
+oracle is at 1.5e-2 ... 2.2e-2 on the same inputs -- so the forward tests assert the literal 1e-2.
+Weight gradients: LeakyReLU / max-pool sign flips make per-tensor errors of ANY bf16 evaluation ~0.3 at
+the deep levels, so gradient tests use the yardstick "every error <= 1.25 x the
+error of the oracle run under torch.autocast(bf16), measured in the same test", plus the well-conditioned
+VJP check against the fp64 oracle further down."""
 import copy
 import os
 
@@ -52,8 +54,8 @@ def test_generator_eval_forward(mod, shape):
             yard = og(x).float()
     assert got.shape == ref.shape and got.dtype == torch.float32
     e, ey = rel_l2(got, ref), rel_l2(yard, ref)
-    assert e < 2e-2, e
-    assert e < 1.25 * ey + 1e-3, (e, ey)
+    assert e < 1e-2, e                       # the north_star bar, literally (measured 6.8e-3 ... 7.3e-3)
+    assert e < ey, (e, ey)                   # and closer to fp32 than stock bf16 autocast (1.5e-2 ... 1.7e-2)
 
 
 @pytest.mark.parametrize("mod", ["bssfp", "t1w"])
@@ -70,7 +72,7 @@ def test_generator_matches_golden(mod):
     with torch.no_grad():
         got = g(x.to(DEV)).cpu()
     ref = torch.from_numpy(GOLD[f"{mod}_g_eval_32"])
-    assert rel_l2(got, ref) < 2e-2
+    assert rel_l2(got, ref) < 1e-2
 
 
 def test_generator_train_backward_vs_autocast_yardstick():
@@ -420,7 +422,7 @@ def test_full_size_128_eval_forward_vs_oracle(mod, batch):
         ref = og(x)
     e_g = rel_l2(got, ref)
     print(f"\n[{mod} batch {batch} @128^3] generator eval rel-L2 vs fp32 oracle: {e_g:.3e}")
-    assert got.shape == ref.shape and e_g < 1.5e-2, e_g
+    assert got.shape == ref.shape and e_g < 1e-2, e_g           # measured 8.6e-3 (stock autocast: 1.7e-2 ... 2.2e-2)
     # the discriminator in TRAIN mode: its BatchNorm layers take batch statistics (over 8 x 64^3 ... 8 x 4^3 values)
     d.train(); od.train()
     with torch.no_grad():

@@ -103,8 +103,10 @@ def test_phase_gradients_match_reference():
             continue                                  # analytically zero (bias in front of a batch-statistics norm)
         e, ey = rel_l2(gp[name].grad.cpu(), ref), rel_l2(yard[name].grad.float().cpu(), ref)
         ours.append(e); theirs.append(ey)
-        # yardstick errors above 0.5 mean the quantity is rounding noise in bf16 whoever computes it: sanity only
-        assert e < (1.25 * ey + 2e-2 if ey < 0.5 else 2.0), (name, e, ey)
+        # no escape clause: even where the quantity is mostly rounding noise in bf16 (the L1 sign gradient at random
+        # initialisation: stock autocast is at rel-L2 1.1 ... 1.2 against the reference's fp32 run on these tensors)
+        # this path is at 0.59 ... 0.75, i.e. every tensor is bounded by the yardstick measured in this very test
+        assert e < 1.25 * ey + 2e-2, (name, e, ey)
     assert float(np.median(ours)) < 1.25 * float(np.median(theirs)) + 2e-2, (ours, theirs)
     for p in d.parameters():
         p.requires_grad_(True)
@@ -121,7 +123,7 @@ def test_phase_gradients_match_reference():
         if name.endswith("conv.bias") and not name.startswith("d1"):
             continue
         e, ey = rel_l2(dp[name].grad.cpu(), ref), rel_l2(yard[name].grad.float().cpu(), ref)
-        assert e < (1.25 * ey + 2e-2 if ey < 0.5 else 2.0), (name, e, ey)
+        assert e < 1.25 * ey + 2e-2, (name, e, ey)
 
 
 def test_three_training_steps_track_the_reference():
