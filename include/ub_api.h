@@ -144,6 +144,10 @@ int ub_pack_ncdhw(const void* a, int a_bf16, int ca, const float* b, int cb, int
  * UB_CONV_K4S2P1_S2D (the PatchGAN stem d1, ref:model.py:72-73,86); d, h, w must be even */
 int ub_pack_ncdhw_s2d(const void* a, int a_bf16, int ca, const float* b, int cb, int n, int d, int h, int w, int cp,
                       void* out, void* stream);
+/* NDHWC bf16 (n, d, h, w, cp) -> the same tensor in the parity-planar space-to-depth layout
+ * [n][(pd,ph,pw)][d/2][h/2][w/2][cp] (a permuting copy; d, h, w even). The PatchGAN body d2 .. d5 (ref:model.py:74-82)
+ * reads its input this way through UB_CONV_K4S2P1_S2D instead of strided TMA boxes. */
+int ub_to_s2d(const void* src, int n, int d, int h, int w, int cp, void* dst, void* stream);
 /* Sliding-window inference (ref:model.py:315-333, ref:data_module.py:168-183; torchio==0.19.6
  * GridSampler / GridAggregator with patch_overlap 0). ub_pack_patches gathers n (<= 64) d x h x w patches of
  * an NCDHW fp32 volume into one NDHWC bf16 batch: patch i starts at element offsets[i] (HOST array) of `a`,

@@ -53,6 +53,10 @@ CASES = [
     (4, 30, 0, 32, (1, 16, 32, 16)),     # PatchGAN stem reading the space-to-depth pack
     (4, 12, 0, 32, (2, 6, 36, 20)),      # ragged tiles
     (4, 64, 0, 64, (1, 8, 8, 8)),        # two 32-channel chunks per parity group
+    (4, 32, 0, 64, (2, 16, 16, 16)),     # PatchGAN d2 on a space-to-depth copy: one chunk, N = 2 x 64 folded
+    (4, 64, 0, 128, (1, 8, 16, 8)),      # d3: two chunks per group, N = 2 x 128
+    (4, 128, 0, 256, (2, 8, 8, 8)),      # d4: two N tiles, depth shifts not folded
+    (4, 256, 0, 512, (2, 4, 4, 4)),      # d5: planes smaller than the tile, four N tiles
     (3, 64, 0, 64, (1, 4, 16, 8)),
     (3, 512, 0, 256, (2, 2, 4, 4)),
     (3, 128, 0, 64, (1, 3, 6, 5)),

@@ -48,6 +48,17 @@ def test_pack_space_to_depth(ca, cb, shape):
     assert torch.equal(s2d, want)
 
 
+@pytest.mark.parametrize("c,shape", [(32, (2, 4, 6, 10)), (64, (1, 8, 8, 8)), (256, (2, 2, 4, 2))])
+def test_to_space_to_depth_copy(c, shape):
+    """ub_to_s2d == the plain tensor regrouped by parity (bit-exact)."""
+    ops = _ops()
+    n, d, h, w = shape
+    a = to_internal(bf16_round(_rand((n, c, d, h, w), 4)))
+    got = ops.to_s2d(a)
+    want = a.view(n, d // 2, 2, h // 2, 2, w // 2, 2, c).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(got.shape)
+    assert got.shape == (n, 8, d // 2, h // 2, w // 2, c) and torch.equal(got, want)
+
+
 @pytest.mark.parametrize("mode", ["instance", "batch_train", "batch_eval"])
 @pytest.mark.parametrize("c,shape,pool", [(32, (2, 4, 16, 8), True), (24, (3, 4, 8, 8), False), (64, (1, 8, 8, 16), True)])
 def test_norm_act_forward_backward(mode, c, shape, pool):

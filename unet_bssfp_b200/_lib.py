@@ -94,6 +94,7 @@ SIGNATURES = {
     "ub_maxpool_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _AP, _P]),
     "ub_head_bwd_fused_workspace_bytes": (_LL, [_I]),
     "ub_head_bwd_fused": (_I, [_P, _I, _P, _I, _I, _LL, C.POINTER(NormBwdFuse), _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ub_to_s2d": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "ub_maxpool_bwd_fuse_records": (_I, [_I, _I, _I, _I, _I]),
     "ub_maxpool_bwd_fused": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(NormBwdFuse), _P]),
     "ub_colsum_workspace_bytes": (_LL, [_I]),

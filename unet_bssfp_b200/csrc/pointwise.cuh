@@ -374,6 +374,31 @@ pack_ncdhw_a16_kernel(const __nv_bfloat16* __restrict__ a, int ca, const float* 
   }
 }
 
+// NDHWC bf16 -> the parity-planar space-to-depth layout [N][(pd,ph,pw)][D/2][H/2][W/2][Cp] of the same tensor (a
+// permuting copy): what a stride-2 4x4x4 conv reads with plain, unstrided TMA boxes (UB_CONV_K4S2P1_S2D). The
+// PatchGAN body d2 .. d5 (ref: model.py:74-82) converts its input this way instead of loading 8 parity tiles with
+// element stride 2 (6.4 x L2 -> SM over-fetch on d2); the copy of a layer input costs a few tens of microseconds.
+// thread = (destination voxel, channel octet): whole 16-byte vectors on both sides. grid = (blocks, N).
+__global__ void __launch_bounds__(256)
+to_s2d_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Cp, int D, int H, int W,
+              uint32_t per_sample /* voxels * Cp/8 of one sample */) {
+  const uint32_t j = blockIdx.x * 256u + threadIdx.x;
+  if (j >= per_sample) return;
+  const int n = blockIdx.y;
+  const uint32_t c8 = (uint32_t)Cp >> 3;
+  uint32_t r = j / c8;                      // destination row inside the sample: ((par * D2 + d2) * H2 + h2) * W2 + w2
+  const uint32_t oct = j - r * c8;
+  const uint32_t W2 = W >> 1, H2 = H >> 1, D2 = D >> 1;
+  const uint32_t w2 = r % W2; r /= W2;
+  const uint32_t h2 = r % H2; r /= H2;
+  const uint32_t d2 = r % D2;
+  const uint32_t par = r / D2;
+  const uint32_t d = 2 * d2 + (par >> 2), h = 2 * h2 + ((par >> 1) & 1), w = 2 * w2 + (par & 1);
+  const size_t srow = (((size_t)n * D + d) * H + h) * W + w;
+  const bf16x8 v = ld_stream(reinterpret_cast<const bf16x8*>(src) + srow * c8 + oct);
+  st_stream(reinterpret_cast<bf16x8*>(dst) + (size_t)n * per_sample + j, v);
+}
+
 // Patch gather (sliding-window inference): sample n of the output batch is the d x h x w sub-volume of an
 // NCDHW fp32 tensor that starts at element offset G.offset[n]; element (c, z, y, x) of it lives at
 // + c * stride_c + z * stride_d + y * stride_h + x. Replaces torchio's GridSampler patch extraction

@@ -1067,6 +1067,17 @@ extern "C" int ub_pack_ncdhw_s2d(const void* a, int a_bf16, int ca, const float*
   return launch_pack<true>(a, a_bf16, ca, b, cb, n, (long long)d * h * w, d, h, w, cp, out, (cudaStream_t)stream);
 }
 
+extern "C" int ub_to_s2d(const void* src, int n, int d, int h, int w, int cp, void* dst, void* stream) {
+  if (!src || !dst || n <= 0 || n > 65535 || d <= 0 || h <= 0 || w <= 0 || ((d | h | w) & 1) || cp <= 0 || cp % 8)
+    return fail(-1, "bad arguments to ub_to_s2d (even positive dims, cp a multiple of 8)");
+  const long long per_sample = (long long)d * h * w * (cp / 8);
+  if (per_sample >= (1ll << 31)) return fail(-2, "ub_to_s2d: sample too large");
+  to_s2d_kernel<<<dim3((unsigned)((per_sample + 255) / 256), n), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), cp, d, h, w, (uint32_t)per_sample);
+  UB_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int ub_pack_patches(const float* a, int ca, int n, const long long* offsets, int d, int h, int w,
                                long long stride_c, long long stride_d, long long stride_h, int cp, void* out,
                                void* stream) {

@@ -107,9 +107,12 @@ class _PackedWeights:
 class _Block:
     """conv -> [InstanceNorm | BatchNorm] -> [Dropout] -> [LeakyReLU] (-> MaxPool3d(2))."""
 
-    def __init__(self, name, spec, conv, norm=None, norm_kind=None, slope=1.0, drop_mod=None, fused_act=False):
+    def __init__(self, name, spec, conv, norm=None, norm_kind=None, slope=1.0, drop_mod=None, fused_act=False,
+                 s2d_convert=False):
         self.name = name
         self.spec = spec
+        self.s2d_convert = s2d_convert   # spec.kind is UB_CONV_K4S2P1_S2D and the source arrives as a plain NDHWC tensor:
+                                         # the forward makes the space-to-depth copy (ops.to_s2d) and saves THAT
         self.conv = conv            # nn.Conv3d / nn.ConvTranspose3d container
         self.norm = norm            # nn.InstanceNorm3d / nn.BatchNorm3d container or None
         self.norm_kind = norm_kind  # "instance" | "batch" | None
@@ -204,6 +207,8 @@ def _block_forward(blk: _Block, cache: _PackedWeights, src0, src1, seed, pool=Fa
     ``p`` / ``training``."""
     spec = blk.spec
     w = cache.get(spec, blk.conv.weight, 0)
+    if blk.s2d_convert and src0.dim() == 5:
+        src0 = ops.to_s2d(src0)        # the saved source (weight gradient) is the space-to-depth copy
     n, d, h, wd = spec.in_dims(src0)
     od, oh, ow = spec.out_dims(d, h, wd)
     sv = _Saved() if save else None
@@ -325,6 +330,8 @@ def _fusion_of(blk: _Block, sv: _Saved, any_width=False):
 # pay: 1.10 ms fused against 0.54 + 0.49 ms for the two passes (the fused kernel is issue- and latency-bound at 128
 # registers, profiles/r02d_pool_fused_ncu_summary.txt): opt-in with UB_POOL_FUSE=1
 _POOL_FUSE = _os.environ.get("UB_POOL_FUSE", "0") == "1"
+# the PatchGAN body d2 .. d5 reads space-to-depth copies of its inputs (UB_D_S2D=0: strided TMA on the plain tensors)
+_D_S2D = _os.environ.get("UB_D_S2D", "1") != "0"
 # the output head's backward runs fused with the norm backward of the (deferred) block in front of it
 _HEAD_FUSE = _os.environ.get("UB_HEAD_FUSE", "1") != "0"
 
@@ -443,15 +450,23 @@ class DownSampleConv(nn.Module):
         self._cache = _PackedWeights()
         self._kind = kind
 
-    def _block(self, name="dsc", s2d_input=False):
+    def _block(self, name="dsc", s2d_input=False, s2d_convert=False):
         """``s2d_input``: the block is the first of a chain and reads the space-to-depth pack of the
-        module input (stride-2 stem of the PatchGAN)."""
-        kind = UB_CONV_K4S2P1_S2D if (s2d_input and self._kind == UB_CONV_K4S2P1) else self._kind
+        module input (stride-2 stem of the PatchGAN). ``s2d_convert``: a stride-2 block inside a chain reads a
+        space-to-depth COPY of its input (made in the forward, ``ops.to_s2d``) with unstrided TMA boxes instead of
+        eight parity tiles with element stride 2."""
+        # copies pay where the output tile is one N tile (depth shifts folded into N = 2 * co <= 256): measured at the
+        # bench shapes d2 forward 0.225 -> 0.086 ms, d3 0.075 -> 0.057, but d4 0.072 -> 0.115 and d5 0.129 -> 0.213
+        # (profiles/r02g_patchgan_s2d.txt), so the wide layers keep the strided boxes
+        s2d_convert = s2d_convert and self.conv.out_channels <= 128
+        s2d = (s2d_input or s2d_convert) and self._kind == UB_CONV_K4S2P1
+        kind = UB_CONV_K4S2P1_S2D if s2d else self._kind
         spec = ops.ConvSpec(kind, self.conv.in_channels, self.conv.out_channels)
         slope = 0.2 if self.activation else 1.0
+        conv = s2d_convert and s2d
         if self.batchnorm:
-            return _Block(name, spec, self.conv, self.bn, "batch", slope=slope)
-        return _Block(name, spec, self.conv, None, None, slope=slope, fused_act=self.activation)
+            return _Block(name, spec, self.conv, self.bn, "batch", slope=slope, s2d_convert=conv)
+        return _Block(name, spec, self.conv, None, None, slope=slope, fused_act=self.activation, s2d_convert=conv)
 
     def forward(self, x):
         blk = self._block()
@@ -956,8 +971,10 @@ class Discriminator(nn.Module):
     def _net(self):
         key = (self.modality, id(self.d1[self.modality]))
         if self._chain is None or self._chain_key != key:
-            blocks = [self.d1[self.modality]._block("d1", s2d_input=True), self.d2._block("d2"), self.d3._block("d3"),
-                      self.d4._block("d4"), self.d5._block("d5"),
+            cv = _D_S2D
+            blocks = [self.d1[self.modality]._block("d1", s2d_input=True), self.d2._block("d2", s2d_convert=cv),
+                      self.d3._block("d3", s2d_convert=cv), self.d4._block("d4", s2d_convert=cv),
+                      self.d5._block("d5", s2d_convert=cv),
                       _Block("final", ops.ConvSpec(UB_CONV_K1, 512, 1), self.final)]
             self._chain = _Chain(blocks, self._cache, self, 1)
             self._chain_key = key

@@ -403,6 +403,17 @@ def pack_ncdhw(a: torch.Tensor, b: torch.Tensor | None = None, s2d: bool = False
     return out
 
 
+def to_s2d(a: torch.Tensor) -> torch.Tensor:
+    """(N,D,H,W,Cp) bf16 -> (N, 8 = (pd,ph,pw), D/2, H/2, W/2, Cp): the parity-planar space-to-depth layout a
+    ``UB_CONV_K4S2P1_S2D`` conv reads (a permuting copy)."""
+    _require_cuda(a)
+    _require_dtype(a, torch.bfloat16, "to_s2d")
+    n, d, h, w, cp = a.shape
+    out = torch.empty((n, 8, d // 2, h // 2, w // 2, cp), dtype=torch.bfloat16, device=a.device)
+    _lib.check(_lib.load().ub_to_s2d(_p(a.contiguous()), n, d, h, w, cp, _p(out), _stream()), "ub_to_s2d")
+    return out
+
+
 def pack_patches(volume: torch.Tensor, origins, patch, out: torch.Tensor | None = None) -> torch.Tensor:
     """Gather ``len(origins)`` patches of an NCDHW fp32 volume (1,C,D,H,W) or (C,D,H,W) into one
     (n, pd, ph, pw, Cp) bf16 batch. ``origins``: (z, y, x) starts; ``patch``: (pd, ph, pw). ``out``: write into the
