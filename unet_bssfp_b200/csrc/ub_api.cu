@@ -740,7 +740,19 @@ extern "C" int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const 
     P.td = od < 4 ? od : 4;
     P.Do = od; P.Ho = oh; P.Wo = ow;  // tile space = q grid (same size as dy)
     P.n_atiles = 1; P.bw = 9; P.bh = 17; P.n_in_planes = P.td + 1; P.in_stride = 1;
-    P.ntaps = 8;
+    // One N tile per class of <= 128 columns: fold the two depth shifts of a class into one UMMA of N = 2 * nt, as the
+    // space-to-depth forward does (dy plane p of the halo feeds the output planes p-1 (sd = 1) and p (sd = 0) of the
+    // class). With nt = 32 (stem, d2) the unfolded launches are bound by the MMA thread's instruction issue
+    // (profiles/r02f_stem_fwd_ncu_summary.txt); folding halves the number of UMMAs. The sd = 0 tap block lies 32 taps
+    // BEHIND the sd = 1 block in the [tap][cin][cop] pack (kd = 3 - 2 sd or 2 - 2 sd).
+    static const bool k4_fold = !(getenv("UB_K4_DGRAD_FOLD") && atoi(getenv("UB_K4_DGRAD_FOLD")) == 0);
+    const bool fold = k4_fold && P.n_ntiles == 1 && nt_max <= 128 && od >= 2;
+    if (fold) {
+      P.kd_fold = 2;
+      P.fold_nd = 2;
+      P.fold_row_step = 32 * ncols;
+    }
+    P.ntaps = fold ? 4 : 8;
     P.out_s = 2;
     if (int e = make_act_map(&P.tm_src[0], dy, d->cop, ow, oh, od, d->n, 32, P.bw, P.bh, 1)) return e;
     // one launch: the 8 parity classes are extra N tiles (blockIdx.y), each with its own tap set,
@@ -763,14 +775,14 @@ extern "C" int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const 
             T.out_p[0] = pw; T.out_p[1] = ph; T.out_p[2] = pd;
           }
           int t = 0;
-          for (int sd = 0; sd < 2; ++sd)
+          for (int sd = fold ? 1 : 0; sd < 2; ++sd)        // folded: the table entry names the sd = 1 tap (block j = 0)
             for (int sh = 0; sh < 2; ++sh)
               for (int sw = 0; sw < 2; ++sw, ++t) {
                 // shift s of class p: p=0 -> k = 3 - 2 s ; p=1 -> k = 2 - 2 s
                 const int kd = pd ? 2 - 2 * sd : 3 - 2 * sd;
                 const int kh = ph ? 2 - 2 * sh : 3 - 2 * sh;
                 const int kw = pw ? 2 - 2 * sw : 3 - 2 * sw;
-                P.taps[cls * 8 + t] = IgemmTap{0, (uint16_t)(sh * P.bw + sw), (uint16_t)sd, (uint16_t)((kd * 4 + kh) * 4 + kw)};
+                P.taps[cls * P.ntaps + t] = IgemmTap{0, (uint16_t)(sh * P.bw + sw), (uint16_t)sd, (uint16_t)((kd * 4 + kh) * 4 + kw)};
               }
         }
     if (int e = finish_plan(&pl, nt_max)) return e;
