@@ -30,6 +30,7 @@
 namespace ub {
 
 constexpr int kMaxTaps = 64;
+constexpr int kMaxAccSets = 4;   // TMEM accumulator sets of the generic kernel (tiles whose epilogue may be pending)
 constexpr int kMaxATiles = 8;
 constexpr int kMaxNTiles = 16;
 
@@ -92,7 +93,7 @@ struct IgemmParams {
   float* stats;                  // [tile][2][w_rows_per_block] partial sum / sumsq, or nullptr
   // shared memory plan (bytes)
   int plane_stride, a_stage_bytes, b_stage_bytes, nsa, nsb, tmem_cols;
-  int nacc;                      // TMEM accumulator sets (2: the epilogue of a tile overlaps the next tile's MMAs)
+  int nacc;                      // TMEM accumulator sets (>= 2: the epilogue of a tile overlaps the next tiles' MMAs; <= kMaxAccSets)
   int total_tiles;
 };
 
@@ -161,11 +162,11 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
   const uint32_t a_base = base;
   const uint32_t b_base = a_base + P.nsa * P.a_stage_bytes;
   const uint32_t bar_base = b_base + P.nsb * P.b_stage_bytes;  // 8-byte mbarriers
-  // barrier layout: a_full[nsa] a_empty[nsa] b_full[nsb] b_empty[nsb] acc_full[2] acc_empty[2]
+  // barrier layout: a_full[nsa] a_empty[nsa] b_full[nsb] b_empty[nsb] acc_full[kMaxAccSets] acc_empty[kMaxAccSets]
   const uint32_t a_full = bar_base, a_empty = a_full + 8 * P.nsa, b_full = a_empty + 8 * P.nsa,
-                 b_empty = b_full + 8 * P.nsb, acc_full = b_empty + 8 * P.nsb, acc_empty = acc_full + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (acc_empty + 16 - base));
-  float* red = reinterpret_cast<float*>(sm + (((acc_empty + 32 + 15) & ~15u) - base));  // kFwdRedFloats, 16-B aligned
+                 b_empty = b_full + 8 * P.nsb, acc_full = b_empty + 8 * P.nsb, acc_empty = acc_full + 8 * kMaxAccSets;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (acc_empty + 8 * kMaxAccSets - base));
+  float* red = reinterpret_cast<float*>(sm + (((acc_empty + 8 * kMaxAccSets + 16 + 15) & ~15u) - base));  // kFwdRedFloats, 16-B aligned
 
   const IgemmNTile NT = P.ntile[blockIdx.y];
   const int ntc = (NT.nt + 31) & ~31;  // TMEM columns per plane accumulator
@@ -174,7 +175,7 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < P.nsa; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < P.nsb; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, kFwdEpiWarps); }
+    for (int i = 0; i < kMaxAccSets; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, kFwdEpiWarps); }
     fence_mbar_init();
   }
   if (warp == kFwdEpiWarps && lane == 0) {

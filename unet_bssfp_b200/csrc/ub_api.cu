@@ -316,7 +316,15 @@ static int finish_plan(IgemmPlan* pl, int nt_max) {
   if (pl->smem < 120 * 1024) pl->smem = 120 * 1024;   // never two CTAs on one SM (persistent: one per SM)
   const int set_cols = P.td * align_up(nt_max, 32);
   if (set_cols > 512) return fail(-2, "igemm TMEM plan too large: %d columns", set_cols);
-  P.nacc = 2 * set_cols <= 512 ? 2 : 1;
+  // Two accumulator sets: the epilogue of a tile overlaps the next tile's MMAs. The kernel takes up to kMaxAccSets
+  // (UB_NACC_MAX=4); measured on the narrow-tile launches (1x1x1 head, stem forward / dgrad, d2: <= 128 columns per
+  // set) four sets change nothing (profiles/r02g_nacc.txt) -- those launches are bound by the epilogue's per-tile
+  // instruction count (statistics transpose) or the MMA thread's issue rate, not by the hand-off depth.
+  static const int nacc_max = getenv("UB_NACC_MAX") ? atoi(getenv("UB_NACC_MAX")) : 2;
+  P.nacc = 512 / set_cols;
+  if (P.nacc > nacc_max) P.nacc = nacc_max;
+  if (P.nacc > kMaxAccSets) P.nacc = kMaxAccSets;
+  if (P.nacc < 1) P.nacc = 1;
   P.tmem_cols = next_pow2_cols(P.nacc * set_cols);
   P.tiles_w = cdiv(P.Wo, 8);
   P.tiles_h = cdiv(P.Ho, 16);
