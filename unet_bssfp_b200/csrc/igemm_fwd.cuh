@@ -88,6 +88,7 @@ struct IgemmParams {
   int oD, oH, oW;                // destination tensor dims
   const float* bias;             // [bias_n] real output channels, or nullptr
   int bias_n;
+  int bias_wrap;                 // see the epilogue's bias load (0: plain)
   int act;                       // 0 none, 1 LeakyReLU(act_slope)
   float act_slope;
   float* stats;                  // [tile][2][w_rows_per_block] partial sum / sumsq, or nullptr
@@ -359,7 +360,10 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
     float* bias_s = red + 2 * kFwdEpiWarps * 2 * 128;  // [128]
     if (threadIdx.x < 128) {
       const int c = threadIdx.x;
-      bias_s[c] = (P.bias != nullptr && c < NT.nt && NT.n0 + c < P.bias_n) ? __ldg(P.bias + NT.n0 + c) : 0.f;
+      // bias_wrap > 0: the N tile holds several copies of the output channels (two sub-positions of a transposed conv
+      // side by side): column c carries channel (n0 + c) mod bias_wrap
+      const int bc = P.bias_wrap > 0 ? (NT.n0 + c) % P.bias_wrap : NT.n0 + c;
+      bias_s[c] = (P.bias != nullptr && c < NT.nt && bc < P.bias_n) ? __ldg(P.bias + bc) : 0.f;
     }
     named_bar_sync(1, kFwdEpiWarps * 32);
     __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(NT.out);

@@ -655,6 +655,31 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
   P.out_s = 2;
   P.taps[0] = IgemmTap{0, 0, 0, 0};
   if (stats_partial) return fail(-1, "statistics are not produced by the transposed conv forward");
+  static const bool dc_pair = !(getenv("UB_DECONV_PAIR") && atoi(getenv("UB_DECONV_PAIR")) == 0);
+  if (dc_pair && d->cop == 64) {
+    // 64 output channels: the sub-positions (pd, ph, 0) and (pd, ph, 1) share ONE N tile of 128 columns -- their
+    // weight blocks are adjacent in the [sub-position][co][ci] pack and their voxels (2w, 2w+1) adjacent in the
+    // output, so columns [64, 128) go to the same tensor one voxel further (the two-destination store of the
+    // skip-concat dgrad). Four CTAs instead of eight read each input tile (the launch was bound by L2 traffic: 8 x
+    // re-read of the input, profiles/r02b_deconv64_ncu_summary.txt), every UMMA is N = 128 and a lane pair writes
+    // 256 contiguous bytes. Two planes per tile keep the 2 x 128-column accumulators double-buffered.
+    P.td = d->d < 2 ? d->d : 2;
+    P.n_in_planes = P.td;
+    P.bias_wrap = 64;
+    P.n_ntiles = 4;
+    for (int sp2 = 0; sp2 < 4; ++sp2) {
+      IgemmNTile& T = P.ntile[sp2];
+      memset(&T, 0, sizeof(T));
+      T.n0 = 0; T.nt = 128; T.out = out; T.out_cpitch = 64; T.out_coff = 0;
+      T.split = 64; T.out2 = reinterpret_cast<__nv_bfloat16*>(out) + 64; T.out2_cpitch = 64;
+      T.wblock_add = 2 * sp2;
+      T.out_p[0] = 0; T.out_p[1] = sp2 & 1; T.out_p[2] = (sp2 >> 1) & 1;
+    }
+    if (int e = make_w_map(&P.tm_w, w_packed, ktot, (long long)ntaps * d->cop, 32, 128)) return e;
+    if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 1)) return e;
+    if (int e = finish_plan(&pl, 128)) return e;
+    return launch_igemm(pl, st);
+  }
   {
     const int base_tiles = P.n_ntiles;
     if (base_tiles * 8 > kMaxNTiles) return fail(-2, "transposed conv: too many output channels (%d)", d->cop);
