@@ -135,7 +135,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 constexpr int kIgemmThreads = 192;  // marching / wgrad kernels: warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
+// Epilogue warps of the generic kernel. With statistics (forward convs in front of a norm) a thread carries 64
+// per-channel accumulators. WITHOUT statistics -- every dgrad, the transposed convs, the PatchGAN stem -- a separate
+// instantiation drops that code and its registers (168 -> 120): ncu showed the output-heavy launches of that group
+// (transposed conv 64 -> 64: 2.1 GB written for 16 UMMAs per tile) bound by the epilogue's instruction stream, not by
+// HBM or L2 (profiles/r02g_deconv_pair.txt). It would also fit 16 epilogue warps (kFwdEpiWarpsWide); measured, that
+// does not pay (profiles/r02g_epi16.txt).
 constexpr int kFwdEpiWarps = 8;
+constexpr int kFwdEpiWarpsWide = 16;
 constexpr int kFwdThreads = (kFwdEpiWarps + 2) * 32;  // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
 constexpr int kFwdRedFloats = 2 * kFwdEpiWarps * 2 * 128 + 128;  // [parity][warp][sum|sumsq][128] + bias[128]
 
@@ -153,8 +160,10 @@ __device__ __forceinline__ IgemmTileCoord igemm_tile(const IgemmParams& P, int t
   return c;
 }
 
-__global__ void __launch_bounds__(kFwdThreads, 1)
+template <int kEpi, bool kStats>
+__global__ void __launch_bounds__((kEpi + 2) * 32, 1)
 igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
+  static_assert(!kStats || kEpi == kFwdEpiWarps, "the statistics staging area is sized for kFwdEpiWarps warps");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -176,22 +185,22 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < P.nsa; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < P.nsb; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
-    for (int i = 0; i < kMaxAccSets; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, kFwdEpiWarps); }
+    for (int i = 0; i < kMaxAccSets; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, kEpi); }
     fence_mbar_init();
   }
-  if (warp == kFwdEpiWarps && lane == 0) {
+  if (warp == kEpi && lane == 0) {
     tma_prefetch_desc(&P.tm_src[0]);
     if (P.n_chunks_total > P.n_chunks_src0) tma_prefetch_desc(&P.tm_src[1]);
     tma_prefetch_desc(&P.tm_w);
   }
-  if (warp == kFwdEpiWarps + 1) tmem_alloc_rt(smem_u32(tmem_slot), P.tmem_cols);
+  if (warp == kEpi + 1) tmem_alloc_rt(smem_u32(tmem_slot), P.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int pitch = P.kc * 2;
 
-  if (warp == kFwdEpiWarps) {
+  if (warp == kEpi) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       const uint32_t a_bytes = (uint32_t)(P.n_atiles * P.n_in_planes * P.bh * P.bw * pitch);
@@ -237,7 +246,7 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
       }
     }
     __syncwarp();
-  } else if (warp == kFwdEpiWarps + 1) {
+  } else if (warp == kEpi + 1) {
     // =========================== MMA issuer ===========================
     // The whole warp walks the pipeline (uniform control flow); one elected lane issues.
     const uint32_t swz = P.kc == 32 ? SWZ_64B : (P.kc == 16 ? SWZ_32B : SWZ_128B);
@@ -347,12 +356,13 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
       if (++slot == P.nacc) { slot = 0; pacc ^= 1; }
     }
   } else {
-    // =========================== epilogue (warps 0-7) ===========================
-    // warp w reads TMEM lanes 32*(w%4)..+31 (accumulator rows); the two warps of a lane quarter split
+    // =========================== epilogue (warps 0 .. kEpi-1) ===========================
+    // warp w reads TMEM lanes 32*(w%4)..+31 (accumulator rows); the kEpi / 4 warps of a lane quarter split
     // the (plane, 32-column chunk) units of a tile between them.
     const int q = warp & 3, grp = warp >> 2;
+    constexpr int kGroups = kEpi / 4;
     const int r = q * 32 + lane;
-    const bool do_stats = P.stats != nullptr;
+    const bool do_stats = kStats && P.stats != nullptr;
     const bool do_act = P.act == 1;
     const float slope = P.act_slope;
     const int nchunks = (NT.nt + 31) >> 5;
@@ -365,7 +375,7 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
       const int bc = P.bias_wrap > 0 ? (NT.n0 + c) % P.bias_wrap : NT.n0 + c;
       bias_s[c] = (P.bias != nullptr && c < NT.nt && bc < P.bias_n) ? __ldg(P.bias + bc) : 0.f;
     }
-    named_bar_sync(1, kFwdEpiWarps * 32);
+    named_bar_sync(1, kEpi * 32);
     __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(NT.out);
     __nv_bfloat16* outp2 = reinterpret_cast<__nv_bfloat16*>(NT.out2);
     const bool odd = (lane & 1) != 0;
@@ -383,124 +393,137 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
       mbar_wait(acc_full + 8 * slot, pacc);
       tc_fence_after();
       const uint32_t acc0 = tmem + ((uint32_t)(q * 32) << 16) + slot * acc_cols;
-      // the two warps of a lane quarter split the tile by 32-column chunk when their number is even,
-      // else by plane; per-channel statistics are summed in registers over the planes of a chunk and
-      // transposed once per (chunk, tile)
-      const bool by_chunk = (nchunks & 1) == 0;
-      for (int cc = by_chunk ? grp : 0; cc < nchunks; cc += by_chunk ? 2 : 1) {
+
+      // one (32-column chunk cc, plane o) unit of the tile: TMEM -> bias / activation -> 16-bit -> global
+      auto unit = [&](int cc, int o, float (&st_a)[kStats ? 32 : 1], float (&st_b)[kStats ? 32 : 1]) {
         const bool full32 = (NT.nt - cc * 32) >= 32;
         const bool to2 = cc * 32 >= NT.split;
         const float4* b4 = reinterpret_cast<const float4*>(bias_s + cc * 32);
-        float st_a[32], st_b[32];
+        const int d = T.d0 + o;
+        const size_t vox_e = ((size_t)T.nb * P.oD + (size_t)(d * P.out_s + NT.out_p[2])) * P.oH * P.oW + vox_hw;
+        uint32_t rr[32];
+        const uint32_t taddr = acc0 + o * ntc + cc * 32;
+        if (full32) {
+          tmem_ld_32x32b_x32(taddr, rr);
+        } else {
+          uint32_t r16[16];
+          tmem_ld_32x32b_x16(taddr, r16);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { st_a[j] = 0.f; st_b[j] = 0.f; }
-        for (int o = by_chunk ? 0 : grp; o < T.planes; o += by_chunk ? 1 : 2) {
-          const int d = T.d0 + o;
-          const size_t vox_e = ((size_t)T.nb * P.oD + (size_t)(d * P.out_s + NT.out_p[2])) * P.oH * P.oW + vox_hw;
-          uint32_t rr[32];
-          const uint32_t taddr = acc0 + o * ntc + cc * 32;
-          if (full32) {
-            tmem_ld_32x32b_x32(taddr, rr);
-          } else {
-            uint32_t r16[16];
-            tmem_ld_32x32b_x16(taddr, r16);
+          for (int j = 0; j < 16; ++j) { rr[j] = r16[j]; rr[j + 16] = 0u; }
+        }
+        tmem_ld_wait();
+        uint32_t pk[16];
+        const bool acc_stats = do_stats && valid_hw;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { rr[j] = r16[j]; rr[j + 16] = 0u; }
+        for (int j = 0; j < 8; ++j) {
+          const float4 bv = b4[j];
+          float x0 = __uint_as_float(rr[4 * j + 0]) + bv.x, x1 = __uint_as_float(rr[4 * j + 1]) + bv.y;
+          float x2 = __uint_as_float(rr[4 * j + 2]) + bv.z, x3 = __uint_as_float(rr[4 * j + 3]) + bv.w;
+          if (do_act) {
+            x0 = x0 > 0.f ? x0 : x0 * slope; x1 = x1 > 0.f ? x1 : x1 * slope;
+            x2 = x2 > 0.f ? x2 : x2 * slope; x3 = x3 > 0.f ? x3 : x3 * slope;
           }
-          tmem_ld_wait();
-          uint32_t pk[16];
-          const bool acc_stats = do_stats && valid_hw;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bv = b4[j];
-            float x0 = __uint_as_float(rr[4 * j + 0]) + bv.x, x1 = __uint_as_float(rr[4 * j + 1]) + bv.y;
-            float x2 = __uint_as_float(rr[4 * j + 2]) + bv.z, x3 = __uint_as_float(rr[4 * j + 3]) + bv.w;
-            if (do_act) {
-              x0 = x0 > 0.f ? x0 : x0 * slope; x1 = x1 > 0.f ? x1 : x1 * slope;
-              x2 = x2 > 0.f ? x2 : x2 * slope; x3 = x3 > 0.f ? x3 : x3 * slope;
-            }
-            if (do_stats) {
-              // the raw output of a conv -> norm block: stored as fp16 (never an MMA operand), statistics from
-              // the fp32 accumulators
-              pk[2 * j] = pack_f16x2_sat(x0, x1);
-              pk[2 * j + 1] = pack_f16x2_sat(x2, x3);
-              if (acc_stats) {
+          if (kStats && do_stats) {
+            // the raw output of a conv -> norm block: stored as fp16 (never an MMA operand), statistics from
+            // the fp32 accumulators
+            pk[2 * j] = pack_f16x2_sat(x0, x1);
+            pk[2 * j + 1] = pack_f16x2_sat(x2, x3);
+            if (acc_stats) {
+              if constexpr (kStats) {
                 st_a[4 * j] += x0; st_a[4 * j + 1] += x1; st_a[4 * j + 2] += x2; st_a[4 * j + 3] += x3;
                 st_b[4 * j] = fmaf(x0, x0, st_b[4 * j]); st_b[4 * j + 1] = fmaf(x1, x1, st_b[4 * j + 1]);
                 st_b[4 * j + 2] = fmaf(x2, x2, st_b[4 * j + 2]); st_b[4 * j + 3] = fmaf(x3, x3, st_b[4 * j + 3]);
               }
-            } else {
-              pk[2 * j] = pack_bf16x2(x0, x1);
-              pk[2 * j + 1] = pack_bf16x2(x2, x3);
             }
-          }
-          // ---- stores: the lane pair (2k, 2k+1) owns two neighbouring voxel rows (w, w+1). Exchange half
-          // rows so that instruction j writes one whole 32-byte sector per lane pair:
-          //   even lane: row_e chunk 0 | row_e chunk 2 | row_o chunk 0 | row_o chunk 2
-          //   odd  lane: row_e chunk 1 | row_e chunk 3 | row_o chunk 1 | row_o chunk 3
-          {
-            uint32_t sx[8], rx[8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              sx[j] = odd ? pk[j] : pk[4 + j];            // odd sends chunk 0, even sends chunk 1
-              sx[4 + j] = odd ? pk[8 + j] : pk[12 + j];   // odd sends chunk 2, even sends chunk 3
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) rx[j] = __shfl_xor_sync(0xffffffffu, sx[j], 1);
-            __nv_bfloat16* be = to2 ? outp2 + vox_e * NT.out2_cpitch + (cc * 32 - NT.split)
-                                    : outp + vox_e * NT.out_cpitch + NT.out_coff + cc * 32;
-            const size_t row_step = (size_t)P.out_s * (to2 ? NT.out2_cpitch : NT.out_cpitch);
-            uint4* de = reinterpret_cast<uint4*>(be) + (odd ? 1 : 0);
-            uint4* d_o = reinterpret_cast<uint4*>(be + row_step) + (odd ? 1 : 0);
-            if (valid_e) {
-              __stcs(de + 0, odd ? make_uint4(rx[0], rx[1], rx[2], rx[3]) : make_uint4(pk[0], pk[1], pk[2], pk[3]));
-              if (full32) __stcs(de + 2, odd ? make_uint4(rx[4], rx[5], rx[6], rx[7]) : make_uint4(pk[8], pk[9], pk[10], pk[11]));
-            }
-            if (valid_o) {
-              __stcs(d_o + 0, odd ? make_uint4(pk[4], pk[5], pk[6], pk[7]) : make_uint4(rx[0], rx[1], rx[2], rx[3]));
-              if (full32) __stcs(d_o + 2, odd ? make_uint4(pk[12], pk[13], pk[14], pk[15]) : make_uint4(rx[4], rx[5], rx[6], rx[7]));
-            }
+          } else {
+            pk[2 * j] = pack_bf16x2(x0, x1);
+            pk[2 * j + 1] = pack_bf16x2(x2, x3);
           }
         }
-        if (do_stats) {
-          const float sa_ = warp_transpose_reduce32(st_a, lane);
-          const float sq_ = warp_transpose_reduce32(st_b, lane);
+        // ---- stores: the lane pair (2k, 2k+1) owns two neighbouring voxel rows (w, w+1). Exchange half
+        // rows so that instruction j writes one whole 32-byte sector per lane pair:
+        //   even lane: row_e chunk 0 | row_e chunk 2 | row_o chunk 0 | row_o chunk 2
+        //   odd  lane: row_e chunk 1 | row_e chunk 3 | row_o chunk 1 | row_o chunk 3
+        uint32_t sx[8], rx[8];
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (k == cc) { s_acc[k] = sa_; q_acc[k] = sq_; }
+        for (int j = 0; j < 4; ++j) {
+          sx[j] = odd ? pk[j] : pk[4 + j];            // odd sends chunk 0, even sends chunk 1
+          sx[4 + j] = odd ? pk[8 + j] : pk[12 + j];   // odd sends chunk 2, even sends chunk 3
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rx[j] = __shfl_xor_sync(0xffffffffu, sx[j], 1);
+        __nv_bfloat16* be = to2 ? outp2 + vox_e * NT.out2_cpitch + (cc * 32 - NT.split)
+                                : outp + vox_e * NT.out_cpitch + NT.out_coff + cc * 32;
+        const size_t row_step = (size_t)P.out_s * (to2 ? NT.out2_cpitch : NT.out_cpitch);
+        uint4* de = reinterpret_cast<uint4*>(be) + (odd ? 1 : 0);
+        uint4* d_o = reinterpret_cast<uint4*>(be + row_step) + (odd ? 1 : 0);
+        if (valid_e) {
+          __stcs(de + 0, odd ? make_uint4(rx[0], rx[1], rx[2], rx[3]) : make_uint4(pk[0], pk[1], pk[2], pk[3]));
+          if (full32) __stcs(de + 2, odd ? make_uint4(rx[4], rx[5], rx[6], rx[7]) : make_uint4(pk[8], pk[9], pk[10], pk[11]));
+        }
+        if (valid_o) {
+          __stcs(d_o + 0, odd ? make_uint4(pk[4], pk[5], pk[6], pk[7]) : make_uint4(rx[0], rx[1], rx[2], rx[3]));
+          if (full32) __stcs(d_o + 2, odd ? make_uint4(pk[12], pk[13], pk[14], pk[15]) : make_uint4(rx[4], rx[5], rx[6], rx[7]));
+        }
+      };
+
+      if constexpr (kStats) {
+        // the two warps of a lane quarter split the tile by 32-column chunk when their number is even,
+        // else by plane; per-channel statistics are summed in registers over the planes of a chunk and
+        // transposed once per (chunk, tile)
+        const bool by_chunk = (nchunks & 1) == 0;
+        for (int cc = by_chunk ? grp : 0; cc < nchunks; cc += by_chunk ? 2 : 1) {
+          float st_a[32], st_b[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { st_a[j] = 0.f; st_b[j] = 0.f; }
+          for (int o = by_chunk ? 0 : grp; o < T.planes; o += by_chunk ? 1 : 2) unit(cc, o, st_a, st_b);
+          if (do_stats) {
+            const float sa_ = warp_transpose_reduce32(st_a, lane);
+            const float sq_ = warp_transpose_reduce32(st_b, lane);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k == cc) { s_acc[k] = sa_; q_acc[k] = sq_; }
+          }
+        }
+      } else {
+        // no statistics: the (chunk, plane) units go round-robin over the kEpi / 4 warps of the lane quarter
+        float dummy_a[1], dummy_b[1];
+        const int nunits = nchunks * T.planes;
+        for (int u = grp; u < nunits; u += kGroups) unit(u % nchunks, u / nchunks, dummy_a, dummy_b);
       }
       // all TMEM reads of this tile are done: hand the accumulator set back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + 8 * slot);
       if (++slot == P.nacc) { slot = 0; pacc ^= 1; }
-      if (do_stats) {
-        float* rd = red + (it & 1) * (kFwdEpiWarps * 2 * 128);
-        for (int cc = 0; cc < nchunks; ++cc) {
-          float s = 0.f, qq = 0.f;
+      if constexpr (kStats) {
+        if (do_stats) {
+          float* rd = red + (it & 1) * (kFwdEpiWarps * 2 * 128);
+          for (int cc = 0; cc < nchunks; ++cc) {
+            float s = 0.f, qq = 0.f;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (k == cc) { s = s_acc[k]; qq = q_acc[k]; }
-          rd[(warp * 2 + 0) * 128 + cc * 32 + lane] = s;
-          rd[(warp * 2 + 1) * 128 + cc * 32 + lane] = qq;
-        }
-        named_bar_sync(1, kFwdEpiWarps * 32);
-        const int c = threadIdx.x;
-        if (c < NT.nt) {
-          float s = 0.f, qq = 0.f;
+            for (int k = 0; k < 4; ++k)
+              if (k == cc) { s = s_acc[k]; qq = q_acc[k]; }
+            rd[(warp * 2 + 0) * 128 + cc * 32 + lane] = s;
+            rd[(warp * 2 + 1) * 128 + cc * 32 + lane] = qq;
+          }
+          named_bar_sync(1, kEpi * 32);
+          const int c = threadIdx.x;
+          if (c < NT.nt) {
+            float s = 0.f, qq = 0.f;
 #pragma unroll
-          for (int wq = 0; wq < kFwdEpiWarps; ++wq) { s += rd[(wq * 2 + 0) * 128 + c]; qq += rd[(wq * 2 + 1) * 128 + c]; }
-          float* st = P.stats + (size_t)t * 2 * P.w_rows_per_block;
-          st[NT.n0 + c] = s;
-          st[P.w_rows_per_block + NT.n0 + c] = qq;
+            for (int wq = 0; wq < kFwdEpiWarps; ++wq) { s += rd[(wq * 2 + 0) * 128 + c]; qq += rd[(wq * 2 + 1) * 128 + c]; }
+            float* st = P.stats + (size_t)t * 2 * P.w_rows_per_block;
+            st[NT.n0 + c] = s;
+            st[P.w_rows_per_block + NT.n0 + c] = qq;
+          }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kFwdEpiWarps + 1) tmem_dealloc_rt(tmem, P.tmem_cols);
+  if (warp == kEpi + 1) tmem_dealloc_rt(tmem, P.tmem_cols);
 }
 
 }  // namespace ub

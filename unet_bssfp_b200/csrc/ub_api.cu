@@ -338,9 +338,23 @@ static int finish_plan(IgemmPlan* pl, int nt_max) {
 }
 
 static int launch_igemm(const IgemmPlan& pl, cudaStream_t st) {
-  static SmemOptIn opt;
-  if (int e = opt_in_smem(opt, (const void*)igemm_fwd_kernel, "igemm_fwd")) return e;
-  igemm_fwd_kernel<<<pl.grid, kFwdThreads, pl.smem, st>>>(pl.P);
+  // three instantiations: with statistics (8 epilogue warps, 64 accumulator registers per thread), and without
+  // statistics with 8 (default) or 16 (UB_EPI16=1) epilogue warps. Measured (profiles/r02g_epi16.txt): dropping the
+  // statistics code alone takes the transposed conv 64 -> 64 from 0.568 to 0.503 ms and the stem dgrad from 0.69 to
+  // 0.64 ms (120 instead of 168 registers); sixteen warps add little there (0.486) and cost elsewhere (32 -> 96-column
+  // dgrad 2.39 -> 2.47 ms, stem dgrad 0.70), so eight it stays.
+  static SmemOptIn opt[3];
+  static const bool epi16 = getenv("UB_EPI16") && atoi(getenv("UB_EPI16")) != 0;
+  if (pl.P.stats != nullptr) {
+    if (int e = opt_in_smem(opt[0], (const void*)igemm_fwd_kernel<kFwdEpiWarps, true>, "igemm_fwd")) return e;
+    igemm_fwd_kernel<kFwdEpiWarps, true><<<pl.grid, (kFwdEpiWarps + 2) * 32, pl.smem, st>>>(pl.P);
+  } else if (epi16) {
+    if (int e = opt_in_smem(opt[1], (const void*)igemm_fwd_kernel<kFwdEpiWarpsWide, false>, "igemm_fwd")) return e;
+    igemm_fwd_kernel<kFwdEpiWarpsWide, false><<<pl.grid, (kFwdEpiWarpsWide + 2) * 32, pl.smem, st>>>(pl.P);
+  } else {
+    if (int e = opt_in_smem(opt[2], (const void*)igemm_fwd_kernel<kFwdEpiWarps, false>, "igemm_fwd")) return e;
+    igemm_fwd_kernel<kFwdEpiWarps, false><<<pl.grid, (kFwdEpiWarps + 2) * 32, pl.smem, st>>>(pl.P);
+  }
   UB_LAUNCH_CHECK();
   return 0;
 }
