@@ -381,6 +381,14 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
     const bool odd = (lane & 1) != 0;
     int slot = 0, it = 0;
     uint32_t pacc = 0;
+    // per-thread channel sums (statistics variant). With ONE 32-column chunk per tile (the 1x1x1 input head) they are
+    // carried over the CTA's consecutive tiles of a sample and transposed / written only when the sample changes or the
+    // CTA runs out of tiles -- the other tiles write a zero record. That launch has 8 UMMAs per tile and was bound by
+    // the epilogue's per-tile transpose-reduce (2 x 31 shuffle steps, a block barrier and a shared-memory round trip).
+    float st_a[kStats ? 32 : 1], st_b[kStats ? 32 : 1];
+#pragma unroll
+    for (int j = 0; j < (kStats ? 32 : 1); ++j) { st_a[j] = 0.f; st_b[j] = 0.f; }
+    const bool carry = kStats && do_stats && nchunks == 1;
     for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
       const IgemmTileCoord T = igemm_tile(P, t);
       const int h = T.h0 + (r >> 3), w = T.w0 + (r & 7);
@@ -467,22 +475,32 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
         }
       };
 
+      bool flush = true;       // this tile writes a real statistics record (always, unless the sums are carried on)
       if constexpr (kStats) {
         // the two warps of a lane quarter split the tile by 32-column chunk when their number is even,
         // else by plane; per-channel statistics are summed in registers over the planes of a chunk and
         // transposed once per (chunk, tile)
         const bool by_chunk = (nchunks & 1) == 0;
+        if (carry) {
+          const int tn = t + (int)gridDim.x;
+          flush = tn >= P.total_tiles || igemm_tile(P, tn).nb != T.nb;
+        }
         for (int cc = by_chunk ? grp : 0; cc < nchunks; cc += by_chunk ? 2 : 1) {
-          float st_a[32], st_b[32];
+          if (!carry) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { st_a[j] = 0.f; st_b[j] = 0.f; }
+            for (int j = 0; j < 32; ++j) { st_a[j] = 0.f; st_b[j] = 0.f; }
+          }
           for (int o = by_chunk ? 0 : grp; o < T.planes; o += by_chunk ? 1 : 2) unit(cc, o, st_a, st_b);
-          if (do_stats) {
-            const float sa_ = warp_transpose_reduce32(st_a, lane);
+          if (do_stats && flush) {
+            const float sa_ = warp_transpose_reduce32(st_a, lane);     // (destroys its argument)
             const float sq_ = warp_transpose_reduce32(st_b, lane);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               if (k == cc) { s_acc[k] = sa_; q_acc[k] = sq_; }
+            if (carry) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { st_a[j] = 0.f; st_b[j] = 0.f; }
+            }
           }
         }
       } else {
@@ -497,7 +515,15 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
       if (lane == 0) mbar_arrive(acc_empty + 8 * slot);
       if (++slot == P.nacc) { slot = 0; pacc ^= 1; }
       if constexpr (kStats) {
-        if (do_stats) {
+        if (do_stats && !flush) {
+          // sums carried on to the CTA's next tile of this sample: this tile's record is zero
+          const int c = threadIdx.x;
+          if (c < NT.nt) {
+            float* st = P.stats + (size_t)t * 2 * P.w_rows_per_block;
+            st[NT.n0 + c] = 0.f;
+            st[P.w_rows_per_block + NT.n0 + c] = 0.f;
+          }
+        } else if (do_stats) {
           float* rd = red + (it & 1) * (kFwdEpiWarps * 2 * 128);
           for (int cc = 0; cc < nchunks; ++cc) {
             float s = 0.f, qq = 0.f;
