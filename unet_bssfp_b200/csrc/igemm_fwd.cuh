@@ -160,10 +160,19 @@ __device__ __forceinline__ IgemmTileCoord igemm_tile(const IgemmParams& P, int t
   return c;
 }
 
-template <int kEpi, bool kStats>
-__global__ void __launch_bounds__((kEpi + 2) * 32, 1)
+// kMma = 2: TWO MMA-issuing warps. Every 32-channel K chunk of a tap is a pair of K = 16 UMMAs; warp kEpi + 1 issues
+// the first of each pair, warp kEpi + 2 the second, into the same accumulators. Why: the issue loop costs ~8
+// instructions per UMMA (each operand crosses from vector to uniform registers, R2UR), 113 cycles per N = 64 UMMA
+// measured against ~50 for its shared-memory operands (profiles/r02f_stem_fwd_ncu_summary.txt), so every launch with
+// N <= 128 per instruction is bound by ONE thread's issue rate. Accumulation order between the two streams is
+// free, except that the second stream must not touch an accumulator before the first stream's overwriting UMMA
+// (first tap of a tile) has been issued: `first_bar`, one arrival per tile, orders exactly that (tcgen05 fences on
+// both sides; the tensor pipe executes in issue order). The stage / accumulator barriers count two commits.
+template <int kEpi, bool kStats, int kMma = 1>
+__global__ void __launch_bounds__((kEpi + 1 + kMma) * 32, 1)
 igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
   static_assert(!kStats || kEpi == kFwdEpiWarps, "the statistics staging area is sized for kFwdEpiWarps warps");
+  static_assert(kMma == 1 || kMma == 2, "one or two MMA-issuing warps");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -174,18 +183,21 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
   const uint32_t bar_base = b_base + P.nsb * P.b_stage_bytes;  // 8-byte mbarriers
   // barrier layout: a_full[nsa] a_empty[nsa] b_full[nsb] b_empty[nsb] acc_full[kMaxAccSets] acc_empty[kMaxAccSets]
   const uint32_t a_full = bar_base, a_empty = a_full + 8 * P.nsa, b_full = a_empty + 8 * P.nsa,
-                 b_empty = b_full + 8 * P.nsb, acc_full = b_empty + 8 * P.nsb, acc_empty = acc_full + 8 * kMaxAccSets;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (acc_empty + 8 * kMaxAccSets - base));
-  float* red = reinterpret_cast<float*>(sm + (((acc_empty + 8 * kMaxAccSets + 16 + 15) & ~15u) - base));  // kFwdRedFloats, 16-B aligned
+                 b_empty = b_full + 8 * P.nsb, acc_full = b_empty + 8 * P.nsb, acc_empty = acc_full + 8 * kMaxAccSets,
+                 first_bar = acc_empty + 8 * kMaxAccSets;   // [kMaxAccSets]: first tap of the tile issued (kMma == 2)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (first_bar + 8 * kMaxAccSets - base));
+  float* red = reinterpret_cast<float*>(sm + (((first_bar + 8 * kMaxAccSets + 16 + 15) & ~15u) - base));  // kFwdRedFloats, 16-B aligned
 
   const IgemmNTile NT = P.ntile[blockIdx.y];
   const int ntc = (NT.nt + 31) & ~31;  // TMEM columns per plane accumulator
   const int acc_cols = P.td * ntc;     // columns of one accumulator set
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < P.nsa; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
-    for (int i = 0; i < P.nsb; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
-    for (int i = 0; i < kMaxAccSets; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, kEpi); }
+    for (int i = 0; i < P.nsa; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, kMma); }
+    for (int i = 0; i < P.nsb; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, kMma); }
+    for (int i = 0; i < kMaxAccSets; ++i) {
+      mbar_init(acc_full + 8 * i, kMma); mbar_init(acc_empty + 8 * i, kEpi); mbar_init(first_bar + 8 * i, 1);
+    }
     fence_mbar_init();
   }
   if (warp == kEpi && lane == 0) {
@@ -246,9 +258,11 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
       }
     }
     __syncwarp();
-  } else if (warp == kEpi + 1) {
-    // =========================== MMA issuer ===========================
+  } else if (warp >= kEpi + 1) {
+    // =========================== MMA issuer(s) ===========================
     // The whole warp walks the pipeline (uniform control flow); one elected lane issues.
+    const int half = kMma == 2 ? warp - (kEpi + 1) : 0;     // which UMMA of every K = 16 pair this warp issues (kMma == 2)
+    const uint32_t koff = 2u * (uint32_t)half;              // its K offset in 16-byte units
     const uint32_t swz = P.kc == 32 ? SWZ_64B : (P.kc == 16 ? SWZ_32B : SWZ_128B);
     const uint32_t idesc = make_idesc_bf16(128, NT.nt, 0, 0);
     const uint32_t a_hi = (uint32_t)(make_smem_desc(0, 16, P.bw * pitch, swz) >> 32);
@@ -301,6 +315,12 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
         for (int tp = 0; tp < P.ntaps; ++tp) {
           mbar_wait(b_full + 8 * sb, pb);
           tc_fence_after();
+          const bool first_tap = (ch | tp) == 0;
+          if (kMma == 2 && first_tap && half == 1) {
+            // the first stream's overwriting UMMAs of this tile must be in the pipe before anything accumulates
+            mbar_wait(first_bar + 8 * slot, pacc);
+            tc_fence_after();
+          }
           if (leader && P.kd_fold) {
             const IgemmTap Tp = P.taps[tbase + tp];
             const uint32_t a_tap = lbo_lo | ((a_stage + Tp.row_off * pitch) >> 4);
@@ -310,8 +330,12 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
 #pragma unroll
               for (int e = 0; e < 12; ++e) {
                 if ((fs_valid >> e) & 1u) {
-                  umma_bf16_lohi(acc0 + fs_d[e], a_tap + fs_a[e], a_hi, b_lo0 + fs_b[e], b_hi, fs_i[e], 1u);
-                  umma_bf16_lohi(acc0 + fs_d[e], a_tap + fs_a[e] + 2, a_hi, b_lo0 + fs_b[e] + 2, b_hi, fs_i[e], 1u);
+                  if (kMma == 2) {
+                    umma_bf16_lohi(acc0 + fs_d[e], a_tap + fs_a[e] + koff, a_hi, b_lo0 + fs_b[e] + koff, b_hi, fs_i[e], 1u);
+                  } else {
+                    umma_bf16_lohi(acc0 + fs_d[e], a_tap + fs_a[e], a_hi, b_lo0 + fs_b[e], b_hi, fs_i[e], 1u);
+                    umma_bf16_lohi(acc0 + fs_d[e], a_tap + fs_a[e] + 2, a_hi, b_lo0 + fs_b[e] + 2, b_hi, fs_i[e], 1u);
+                  }
                 }
               }
             } else {
@@ -323,8 +347,12 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
                 for (int o = o_lo; o <= o_hi; ++o) {
                   const int kd = p_in - o;
                   const uint32_t b_lo = b_lo0 + (uint32_t)(ndm1 - kd) * kd_rows16;
-                  umma_bf16_lohi(acc0 + o * ntc, a_lo, a_hi, b_lo, b_hi, idesc, (uint32_t)(kd != 0));
-                  umma_bf16_lohi(acc0 + o * ntc, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                  if (kMma == 2) {
+                    umma_bf16_lohi(acc0 + o * ntc, a_lo + koff, a_hi, b_lo + koff, b_hi, idesc, half ? 1u : (uint32_t)(kd != 0));
+                  } else {
+                    umma_bf16_lohi(acc0 + o * ntc, a_lo, a_hi, b_lo, b_hi, idesc, (uint32_t)(kd != 0));
+                    umma_bf16_lohi(acc0 + o * ntc, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                  }
                 }
               }
             }
@@ -338,11 +366,19 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
               if (o < T.planes) {
-                umma_bf16_lohi(acc0 + o * ntc, a_lo + o * plane16, a_hi, b_lo, b_hi, idesc, acc);
-                umma_bf16_lohi(acc0 + o * ntc, a_lo + o * plane16 + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                if (kMma == 2) {
+                  umma_bf16_lohi(acc0 + o * ntc, a_lo + o * plane16 + koff, a_hi, b_lo + koff, b_hi, idesc, half ? 1u : acc);
+                } else {
+                  umma_bf16_lohi(acc0 + o * ntc, a_lo + o * plane16, a_hi, b_lo, b_hi, idesc, acc);
+                  umma_bf16_lohi(acc0 + o * ntc, a_lo + o * plane16 + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                }
               }
             }
             umma_commit(b_empty + 8 * sb);
+          }
+          if (kMma == 2 && first_tap && half == 0) {
+            tc_fence_before();
+            if (leader) mbar_arrive(first_bar + 8 * slot);
           }
           __syncwarp();
           if (++sb == P.nsb) { sb = 0; pb ^= 1; }

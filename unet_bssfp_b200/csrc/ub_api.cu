@@ -343,8 +343,21 @@ static int launch_igemm(const IgemmPlan& pl, cudaStream_t st) {
   // statistics code alone takes the transposed conv 64 -> 64 from 0.568 to 0.503 ms and the stem dgrad from 0.69 to
   // 0.64 ms (120 instead of 168 registers); sixteen warps add little there (0.486) and cost elsewhere (32 -> 96-column
   // dgrad 2.39 -> 2.47 ms, stem dgrad 0.70), so eight it stays.
-  static SmemOptIn opt[3];
+  static SmemOptIn opt[5];
   static const bool epi16 = getenv("UB_EPI16") && atoi(getenv("UB_EPI16")) != 0;
+  static const bool mma2 = getenv("UB_MMA2") && atoi(getenv("UB_MMA2")) != 0;
+  if (mma2 && pl.P.kc == 32) {
+    // two MMA-issuing warps (see igemm_fwd.cuh)
+    if (pl.P.stats != nullptr) {
+      if (int e = opt_in_smem(opt[3], (const void*)igemm_fwd_kernel<kFwdEpiWarps, true, 2>, "igemm_fwd")) return e;
+      igemm_fwd_kernel<kFwdEpiWarps, true, 2><<<pl.grid, (kFwdEpiWarps + 3) * 32, pl.smem, st>>>(pl.P);
+    } else {
+      if (int e = opt_in_smem(opt[4], (const void*)igemm_fwd_kernel<kFwdEpiWarps, false, 2>, "igemm_fwd")) return e;
+      igemm_fwd_kernel<kFwdEpiWarps, false, 2><<<pl.grid, (kFwdEpiWarps + 3) * 32, pl.smem, st>>>(pl.P);
+    }
+    UB_LAUNCH_CHECK();
+    return 0;
+  }
   if (pl.P.stats != nullptr) {
     if (int e = opt_in_smem(opt[0], (const void*)igemm_fwd_kernel<kFwdEpiWarps, true>, "igemm_fwd")) return e;
     igemm_fwd_kernel<kFwdEpiWarps, true><<<pl.grid, (kFwdEpiWarps + 2) * 32, pl.smem, st>>>(pl.P);
