@@ -159,6 +159,7 @@ head_bwd_sums_mma_kernel(const float* __restrict__ dout, const __nv_bfloat16* __
   DeferredOctet K;
   K.load(A, n, 32, tig * 8);
   const float inv = K.has_drop ? 1.f / (1.f - A.drop_p) : 1.f;
+  const float sinv = K.slope * inv;
   const float* gp = dout + (size_t)n * CO * V;
   const bf16x8* yp = reinterpret_cast<const bf16x8*>(y) + (size_t)n * V * 4;
   float dw[4][4];
@@ -195,18 +196,17 @@ head_bwd_sums_mma_kernel(const float* __restrict__ dout, const __nv_bfloat16* __
       const uint32_t* aw = reinterpret_cast<const uint32_t*>(&a8);
 #pragma unroll
       for (int r = 0; r < 4; ++r) (grp ? Ub : Ua)[r] = aw[r];
-      float f[8], yy[8];
-      if (K.has_drop) {
-        dropout_factors8(e0, K.seed, K.thresh, inv, f);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = 1.f;
-      }
+      // d act / d pre-activation from the activation itself (already computed for dW): LeakyReLU keeps the sign and a
+      // dropped element is exactly 0, so u > 0 -> inv, u < 0 -> slope * inv, u == 0 -> dropped (or a pre-activation of
+      // exactly 0, a null set) -> 0. Saves the second dropout hash and the per-element mask decode of the generic form.
+      float uu[8], yy[8];
+      unpack8(a8, uu);
       unpack8h(yraw, yy);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float d_ = du[k >> 1][2 * grp + (k & 1)];
-        const float dz = d_ * (fmaf(yy[k], K.sc[k], K.sh[k]) > 0.f ? f[k] : f[k] * K.slope);
+        const float fac = uu[k] > 0.f ? inv : (uu[k] < 0.f ? sinv : 0.f);
+        const float dz = d_ * fac;
         s1[k] += dz;
         s2[k] = fmaf(dz, yy[k], s2[k]);
       }
