@@ -155,3 +155,96 @@ def test_norm_finalize_entries(n, tiles, cp, c, mode):
     got_rstd = outs[3][1].view(n, cp)[:, :c].double()
     torch.testing.assert_close(got_mean, mean, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(got_rstd, 1.0 / torch.sqrt(var + 1e-5), rtol=1e-4, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: the warp-MMA output head (forward, fused backward), the space-to-depth copy, the fused pooling backward,
+# the instruction-lean norm-backward apply -- ragged / minimal shapes, every output inside a NaN arena
+# ---------------------------------------------------------------------------------------------------------------
+def _norm_block(n, d, h, w, c, seed=0):
+    """y (fp16, 32 padded channels, c real) and its per-(n, c) constants."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    y = torch.zeros((n, d, h, w, 32), dtype=torch.float16, device="cuda")
+    y[..., :c] = (torch.randn((n, d, h, w, c), device="cuda", generator=g) * 1.5 + 0.2).half()
+    pad = lambda t: torch.cat([t, torch.zeros((n, 32 - c), device="cuda")], 1).contiguous()
+    scale, shift = pad(torch.rand((n, c), device="cuda", generator=g) + 0.5), pad(torch.randn((n, c), device="cuda", generator=g) * 0.2)
+    mean, rstd = pad(torch.randn((n, c), device="cuda", generator=g) * 0.1), pad(torch.rand((n, c), device="cuda", generator=g) + 0.5)
+    return y, scale, shift, mean, rstd
+
+
+@pytest.mark.parametrize("co,c,shape,drop_p", [(6, 32, (2, 2, 4, 6), 0.05), (3, 24, (1, 1, 4, 4), 0.0), (8, 32, (1, 3, 2, 8), 0.0)])
+def test_output_head_warp_mma_entries(co, c, shape, drop_p):
+    from unet_bssfp_b200 import _lib
+    lib = _lib.load()
+    n, d, h, w = shape
+    vox = d * h * w
+    assert vox % 16 == 0
+    y, scale, shift, mean, rstd = _norm_block(n, d, h, w, c)
+    torch.manual_seed(1)
+    wt = torch.randn(co, c, device="cuda") * 0.3
+    bias = torch.randn(co, device="cuda")
+    act = _lib.DeferredAct(scale.data_ptr(), shift.data_ptr(), 0.1, drop_p, 77, 0)
+    ws = torch.empty(lib.ub_conv1x1_workspace_bytes() // 4, device="cuda")
+    obuf, out = arena(n * co * vox)
+    _lib.check(lib.ub_conv1x1_to_ncdhw(P(y), 32, P(wt), c, P(bias), co, n, vox, P(ws), P(out), C.byref(act), _st()))
+    dout = torch.randn(n, co, vox, device="cuda")
+    fuse = _lib.NormBwdFuse(y.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(), 0.1,
+                            drop_p, 77, None)
+    ws2 = torch.empty(lib.ub_head_bwd_fused_workspace_bytes(n) // 4, device="cuda")
+    dybuf, dy = arena(n * vox * 32, torch.bfloat16)
+    dgbuf, dg = arena(c); dbtbuf, dbt = arena(c); dbsbuf, dbs = arena(c)
+    dwbuf, dw = arena(co * c); dbbuf, db = arena(co)
+    _lib.check(lib.ub_head_bwd_fused(P(dout), co, P(wt), c, n, vox, C.byref(fuse), _lib.UB_NORM_INSTANCE, c, P(ws2), P(dy),
+                                     P(dg), P(dbt), P(dbs), P(dw), P(db), _st()))
+    torch.cuda.synchronize()
+    assert intact(obuf, dybuf, dgbuf, dbtbuf, dbsbuf, dwbuf, dbbuf)
+    assert written(out, dy, dg, dbt, dbs, dw, db)
+
+
+@pytest.mark.parametrize("cp,shape", [(32, (2, 2, 4, 6)), (64, (1, 4, 2, 2)), (512, (1, 2, 2, 2))])
+def test_space_to_depth_copy_and_fused_pool_backward_entries(cp, shape):
+    from unet_bssfp_b200 import _lib
+    lib = _lib.load()
+    n, d, h, w = shape
+    torch.manual_seed(2)
+    src = torch.randn(n, d, h, w, cp, device="cuda").bfloat16()
+    obuf, out = arena(src.numel(), torch.bfloat16)
+    _lib.check(lib.ub_to_s2d(P(src), n, d, h, w, cp, P(out), _st()))
+    # fused pooling backward: dA (accumulated in place) and the partial records
+    g = torch.Generator(device="cuda").manual_seed(3)
+    y = (torch.randn((n, d, h, w, cp), device="cuda", generator=g)).half()
+    scale, shift = torch.rand((n, cp), device="cuda") + 0.5, torch.randn((n, cp), device="cuda") * 0.2
+    mean, rstd = torch.randn((n, cp), device="cuda") * 0.1, torch.rand((n, cp), device="cuda") + 0.5
+    records = lib.ub_maxpool_bwd_fuse_records(n, d, h, w, cp)
+    assert records > 0
+    pbuf, part = arena(records * 2 * cp)
+    dabuf, dA = arena(y.numel(), torch.bfloat16)
+    dP = torch.randn(n, d // 2, h // 2, w // 2, cp, device="cuda").bfloat16()
+    fuse = _lib.NormBwdFuse(y.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(), 0.1,
+                            0.05, 5, part.data_ptr())
+    _lib.check(lib.ub_maxpool_bwd_fused(P(dP), P(dA), 0, n, d, h, w, cp, C.byref(fuse), _st()))
+    torch.cuda.synchronize()
+    assert intact(obuf, pbuf, dabuf)
+    assert written(out, part, dA)
+
+
+@pytest.mark.parametrize("c,shape,drop_p", [(24, (1, 3, 5, 7), 0.05), (512, (2, 1, 1, 3), 0.0), (64, (1, 9, 17, 5), 0.05)])
+def test_lean_norm_backward_apply_entry(c, shape, drop_p):
+    from unet_bssfp_b200 import _lib
+    lib = _lib.load()
+    n, d, h, w = shape
+    cp = (c + 31) // 32 * 32
+    vox = d * h * w
+    torch.manual_seed(4)
+    y = torch.randn(n, d, h, w, cp, device="cuda").half()
+    dA = torch.randn(n, d, h, w, cp, device="cuda").bfloat16()
+    scale, shift = torch.rand((n, cp), device="cuda") + 0.5, torch.randn((n, cp), device="cuda") * 0.2
+    mean, rstd = torch.randn((n, cp), device="cuda") * 0.1, torch.rand((n, cp), device="cuda") + 0.5
+    ws = torch.empty(lib.ub_norm_act_bwd_workspace_bytes(n, cp) // 4, device="cuda")
+    dybuf, dy = arena(y.numel(), torch.bfloat16)
+    dgbuf, dg = arena(c); dbbuf, db = arena(c); dsbuf, ds = arena(c)
+    _lib.check(lib.ub_norm_act_bwd(P(dA), None, P(y), _lib.UB_NORM_INSTANCE, P(mean), P(rstd), P(scale), P(shift), 0.1, drop_p,
+                                   9, n, vox, cp, c, P(ws), P(dy), P(dg), P(db), P(ds), None, 0, _st()))
+    torch.cuda.synchronize()
+    assert intact(dybuf, dgbuf, dbbuf, dsbuf)
+    assert written(dy, dg, db, ds)
