@@ -219,6 +219,49 @@ def test_full_step_runs_and_updates_both_networks():
     assert all(p.requires_grad for p in list(g.parameters()) + list(d.parameters()))
 
 
+def test_step_shares_discriminator_operand_packs_bit_identically(monkeypatch):
+    """``GanTrainer.step`` declares the discriminator constant up to ``opt_d.step()`` (``weights_unchanged``): its six
+    passes share two operand packs. Same losses and same parameters, bit for bit, as with a pack per pass -- and
+    after the scope a pass packs from the live parameters again (an out-of-band write is seen)."""
+    import contextlib
+    from unet_bssfp_b200 import modules as M, ops
+    from unet_bssfp_b200.train_step import GanTrainer
+    torch.manual_seed(5)
+    x = torch.rand(2, 6, 32, 32, 32, device=DEV)
+    y = torch.rand(2, 6, 32, 32, 32, device=DEV)
+    results, packs = [], []
+    real_pack = ops.pack_conv_weights_multi
+    for shared in (True, False):
+        O, og, od, g, d = _pair("t1w")
+        for m in g.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        if not shared:
+            monkeypatch.setattr(M, "weights_unchanged", lambda module: contextlib.nullcontext())
+        count = [0]
+        def counting(items, _c=count):
+            _c[0] += 1
+            return real_pack(items)
+        monkeypatch.setattr(ops, "pack_conv_weights_multi", counting)
+        tr = GanTrainer(g, d)
+        out = [tr.step(x, y) for _ in range(2)]
+        torch.cuda.synchronize()
+        results.append(([t.item() for pair in out for t in pair], [p.detach().clone() for p in d.parameters()]))
+        packs.append(count[0])
+        monkeypatch.setattr(ops, "pack_conv_weights_multi", real_pack)
+        if shared:
+            assert not d._cache.hold and not d._cache._cur          # nothing outlives the scope
+            d.eval()
+            with torch.no_grad():
+                before = d(x, y).clone()
+                d.final.weight.data.mul_(0.0)
+                after = d(x, y)
+            assert not torch.equal(before, after)
+    assert results[0][0] == results[1][0]
+    assert all(torch.equal(a, b) for a, b in zip(results[0][1], results[1][1]))
+    assert packs[1] - packs[0] == 2 * 4       # four discriminator packs less per step
+
+
 @pytest.mark.parametrize("optimizer", ["ub", "torch_fused", "torch"])
 def test_updated_weights_are_used_after_optimizer_steps(optimizer):
     """The bf16 operand copies of the weights must follow the fp32 Parameters through optimizer steps.

@@ -160,6 +160,66 @@ __device__ __forceinline__ IgemmTileCoord igemm_tile(const IgemmParams& P, int t
   return c;
 }
 
+// First tap of a full folded tile: every output plane's first contribution (kd = 0) overwrites its accumulator, so
+// the depth taps cannot share an instruction; same compile-time schedule, N = nt per UMMA.
+template <int ND, int PL, int kMma>
+__device__ __forceinline__ void issue_first_tap(uint32_t acc0, uint32_t a_tap, uint32_t a_hi, uint32_t b_lo0, uint32_t b_hi,
+                                                uint32_t ntc, uint32_t plane16, uint32_t kd_rows16, uint32_t idesc,
+                                                uint32_t koff, int half) {
+  constexpr int ndm1 = ND - 1;
+#pragma unroll
+  for (int p_in = 0; p_in < PL + ndm1; ++p_in) {
+    const int o_lo = p_in - ndm1 > 0 ? p_in - ndm1 : 0;
+    const int o_hi = p_in < PL - 1 ? p_in : PL - 1;
+#pragma unroll
+    for (int o = o_lo; o <= o_hi; ++o) {
+      const int kd = p_in - o;
+      const uint32_t d = acc0 + (uint32_t)o * ntc;
+      const uint32_t a = a_tap + (uint32_t)p_in * plane16;
+      const uint32_t b = b_lo0 + (uint32_t)(ndm1 - kd) * kd_rows16;
+      if (kMma == 2) {
+        umma_bf16_lohi(d, a + koff, a_hi, b + koff, b_hi, idesc, half ? 1u : (uint32_t)(kd != 0));
+      } else {
+        umma_bf16_lohi(d, a, a_hi, b, b_hi, idesc, (uint32_t)(kd != 0));
+        umma_bf16_lohi(d, a + 2, a_hi, b + 2, b_hi, idesc, 1u);
+      }
+    }
+  }
+}
+
+template <int V> struct IntC { static constexpr int value = V; };
+
+// Straight-line issue of one non-overwriting tap of a FULL folded tile (ND depth taps, FOLD of them per UMMA, PL output
+// planes): the schedule of (halo plane, output-plane group) entries is a compile-time constant, so every operand is a
+// constant multiple of three warp-uniform strides on top of three bases and the compiler keeps the whole run in the
+// uniform datapath. The generic per-tile table (fs_* below) costs ~9 instructions per UMMA, most of them vector ->
+// uniform register moves: 113 cycles per N = 64 UMMA against ~50 for its operands (profiles/r02f_stem_fwd_ncu_summary.txt).
+template <int ND, int FOLD, int PL, int kMma>
+__device__ __forceinline__ void issue_folded_tap(uint32_t acc0, uint32_t a_tap, uint32_t a_hi, uint32_t b_lo0, uint32_t b_hi,
+                                                 uint32_t ntc, uint32_t plane16, uint32_t kd_rows16,
+                                                 const uint32_t (&idesc_blk)[3], uint32_t koff) {
+  constexpr int ndm1 = ND - 1;
+#pragma unroll
+  for (int p_in = 0; p_in < PL + ndm1; ++p_in) {
+    const int o_lo = p_in - ndm1 > 0 ? p_in - ndm1 : 0;
+    const int o_hi = p_in < PL - 1 ? p_in : PL - 1;
+#pragma unroll
+    for (int oa = o_lo; oa <= o_hi; oa += FOLD) {
+      const int ob = oa + FOLD - 1 < o_hi ? oa + FOLD - 1 : o_hi;
+      const uint32_t d = acc0 + (uint32_t)oa * ntc;
+      const uint32_t a = a_tap + (uint32_t)p_in * plane16;
+      const uint32_t b = b_lo0 + (uint32_t)(ndm1 - (p_in - oa)) * kd_rows16;
+      const uint32_t id = idesc_blk[ob - oa];
+      if (kMma == 2) {
+        umma_bf16_lohi(d, a + koff, a_hi, b + koff, b_hi, id, 1u);
+      } else {
+        umma_bf16_lohi(d, a, a_hi, b, b_hi, id, 1u);
+        umma_bf16_lohi(d, a + 2, a_hi, b + 2, b_hi, id, 1u);
+      }
+    }
+  }
+}
+
 // kMma = 2: TWO MMA-issuing warps. Every 32-channel K chunk of a tap is a pair of K = 16 UMMAs; warp kEpi + 1 issues
 // the first of each pair, warp kEpi + 2 the second, into the same accumulators. Why: the issue loop costs ~8
 // instructions per UMMA (each operand crosses from vector to uniform registers, R2UR), 113 cycles per N = 64 UMMA
@@ -284,7 +344,12 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
       // folded schedule of this tile: entry e = (halo plane p_in, UMMA group gi): accumulator column
       // offset, A plane offset, weight block offset, instruction descriptor (N = 1..3 depth blocks)
       uint32_t fs_d[12], fs_a[12], fs_b[12], fs_i[12], fs_valid = 0;
-      if (fold) {
+      // 1: (3 depth taps, 3 per UMMA, 4 planes)  2: (3, 2, 2)  3: (2, 2, 4)  0: the table
+      const int sched = !fold ? 0
+                        : (P.fold_nd == 3 && fold == 3 && T.planes == 4) ? 1
+                        : (P.fold_nd == 3 && fold == 2 && T.planes == 2) ? 2
+                        : (P.fold_nd == 2 && fold == 2 && T.planes == 4) ? 3 : 0;
+      if (fold && sched == 0) {
 #pragma unroll
         for (int p_in = 0; p_in < 6; ++p_in) {
 #pragma unroll
@@ -325,8 +390,13 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
             const IgemmTap Tp = P.taps[tbase + tp];
             const uint32_t a_tap = lbo_lo | ((a_stage + Tp.row_off * pitch) >> 4);
             const uint32_t b_lo0 = lbo_lo | ((b_base + sb * P.b_stage_bytes) >> 4);
-            if ((ch | tp) != 0) {
-              // the per-tile schedule (fs_*) makes this a straight run of UMMAs: ~8 integer ops each
+            if ((ch | tp) != 0 && sched != 0) {
+              // full tile of one of the three shapes the step uses: compile-time schedule
+              if (sched == 1) issue_folded_tap<3, 3, 4, kMma>(acc0, a_tap, a_hi, b_lo0, b_hi, (uint32_t)ntc, plane16, kd_rows16, idesc_blk, koff);
+              else if (sched == 2) issue_folded_tap<3, 2, 2, kMma>(acc0, a_tap, a_hi, b_lo0, b_hi, (uint32_t)ntc, plane16, kd_rows16, idesc_blk, koff);
+              else issue_folded_tap<2, 2, 4, kMma>(acc0, a_tap, a_hi, b_lo0, b_hi, (uint32_t)ntc, plane16, kd_rows16, idesc_blk, koff);
+            } else if ((ch | tp) != 0) {
+              // any other tile (ragged depth, other fold shapes): the per-tile schedule table (fs_*)
 #pragma unroll
               for (int e = 0; e < 12; ++e) {
                 if ((fs_valid >> e) & 1u) {
@@ -338,6 +408,10 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
                   }
                 }
               }
+            } else if (sched != 0) {
+              if (sched == 1) issue_first_tap<3, 4, kMma>(acc0, a_tap, a_hi, b_lo0, b_hi, (uint32_t)ntc, plane16, kd_rows16, idesc, koff, half);
+              else if (sched == 2) issue_first_tap<3, 2, kMma>(acc0, a_tap, a_hi, b_lo0, b_hi, (uint32_t)ntc, plane16, kd_rows16, idesc, koff, half);
+              else issue_first_tap<2, 4, kMma>(acc0, a_tap, a_hi, b_lo0, b_hi, (uint32_t)ntc, plane16, kd_rows16, idesc, koff, half);
             } else {
               // first tap of the tile: each output plane's first contribution (kd = 0) overwrites
               for (int p_in = 0; p_in < n_pin; ++p_in) {
@@ -363,9 +437,11 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
                                              Tp.row_off * pitch) >> 4);
             const uint32_t b_lo = lbo_lo | ((b_base + sb * P.b_stage_bytes) >> 4);
             const uint32_t acc = (ch | tp) != 0;
+            // one branch per tap, not per plane: the planes of a tap are then one straight run of UMMAs (every branch
+            // in between makes the compiler move all seven operands to uniform registers again)
+            auto planes = [&](auto pl) {
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-              if (o < T.planes) {
+              for (int o = 0; o < decltype(pl)::value; ++o) {
                 if (kMma == 2) {
                   umma_bf16_lohi(acc0 + o * ntc, a_lo + o * plane16 + koff, a_hi, b_lo + koff, b_hi, idesc, half ? 1u : acc);
                 } else {
@@ -373,7 +449,11 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
                   umma_bf16_lohi(acc0 + o * ntc, a_lo + o * plane16 + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
                 }
               }
-            }
+            };
+            if (T.planes == 4) planes(IntC<4>{});
+            else if (T.planes == 2) planes(IntC<2>{});
+            else if (T.planes == 1) planes(IntC<1>{});
+            else planes(IntC<3>{});
             umma_commit(b_empty + 8 * sb);
           }
           if (kMma == 2 && first_tap && half == 0) {

@@ -43,6 +43,12 @@ struct WgradParams {
   int ci_total, co_total;                // padded totals (partial buffer pitch)
   float* partial;                        // [nsplit][n_variants*ngroups*natoms][ci_total][co_total]
   int x_stage_bytes, dy_stage_bytes, nstages, tmem_cols;
+  // Transposed conv ("dc mode", chunk_atoms > 0): the four M atoms are up to four 32-channel CHUNKS of X (their tiles
+  // sit 8 KB apart in the stage, LBO = 8 KB) instead of kw taps, and N = var_boxes sub-positions x nt channels: one
+  // CTA reads its X tiles and dY parity tiles once for chunk_atoms x var_boxes (chunk, sub-position) pairs. Before,
+  // every chunk re-read dY and every sub-position re-read X: 6.4 GB through L2 for 2.4 GB of operands on the
+  // 64 -> 64 layer, which bound the launch (profiles/r02h_deconv_wgrad_ncu_summary.txt).
+  int chunk_atoms, var_boxes;
 };
 
 __global__ void __launch_bounds__(kIgemmThreads, 1)
@@ -57,14 +63,20 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + (acc_full + 8 - base));
 
   // ---- work item
+  const bool dc = P.chunk_atoms > 0;
+  const int vboxes = dc ? P.var_boxes : 1;
   int y = blockIdx.y;
   const int cot = y % P.n_cotiles; y /= P.n_cotiles;
-  const int var = y % P.n_variants; y /= P.n_variants;
-  const int chunk = y;
+  const int nvg = P.n_variants / vboxes;             // variant groups (dc mode: var_boxes sub-positions each)
+  const int var = (y % nvg) * vboxes; y /= nvg;      // first variant of the group
+  const int chunk = dc ? y * P.chunk_atoms : y;      // first chunk of the group
+  int ca_eff = dc ? P.n_chunks_total - chunk : 1;    // chunks of this group
+  if (dc && ca_eff > P.chunk_atoms) ca_eff = P.chunk_atoms;
   const int n0 = cot * P.nt;
   const bool s1 = chunk >= P.n_chunks_src0;
   const int c0 = (s1 ? chunk - P.n_chunks_src0 : chunk) * 32;
-  const int ntc = (P.nt + 31) & ~31;
+  const int nn = vboxes * P.nt;                      // UMMA N
+  const int ntc = (nn + 31) & ~31;
 
   // ---- this CTA's share of the plane tiles
   const long long total = (long long)P.Nb * P.Dt * P.tiles_h * P.tiles_w;
@@ -92,7 +104,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
 
   if (warp == 4) {
     if (lane == 0) {
-      const uint32_t bytes = (uint32_t)(P.bh * P.bw * 64 + 128 * P.nt * 2);
+      const uint32_t bytes = (uint32_t)(ca_eff * P.bh * P.bw * 64 + vboxes * 128 * P.nt * 2);
       const CUtensorMap* tmx = &P.tm_x[s1 ? 1 : 0];
       long long tt = t_begin;
       int tw_i = (int)(tt % P.tiles_w); tt /= P.tiles_w;
@@ -105,13 +117,15 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
         mbar_wait(empty + 8 * st, ph ^ 1);
         mbar_expect_tx(full + 8 * st, bytes);
         const uint32_t xs = base + st * stage_bytes;
-        tma_load_5d(xs, tmx, full + 8 * st, c0, tw_i * 8 * P.x_stride + P.x_off[var][0],
-                    th_i * 16 * P.x_stride + P.x_off[var][1], d * P.x_stride + P.x_off[var][2],
-                    nb * P.x_nmul + P.x_nadd[var]);
-        for (int b = 0; b < nboxes; ++b)
-          tma_load_5d(xs + P.x_stage_bytes + b * 128 * dy_pitch, &P.tm_dy, full + 8 * st, n0 + b * P.ncb,
-                      tw_i * 8 * P.dy_stride + P.dy_off[var][0], th_i * 16 * P.dy_stride + P.dy_off[var][1],
-                      d * P.dy_stride + P.dy_off[var][2], nb);
+        for (int a = 0; a < ca_eff; ++a)     // dc mode: the chunks of the group, 8 KB apart (bw x bh = 8 x 16 rows of 64 B)
+          tma_load_5d(xs + a * (P.bh * P.bw * 64), tmx, full + 8 * st, c0 + a * 32, tw_i * 8 * P.x_stride + P.x_off[var][0],
+                      th_i * 16 * P.x_stride + P.x_off[var][1], d * P.x_stride + P.x_off[var][2],
+                      nb * P.x_nmul + P.x_nadd[var]);
+        for (int vb = 0; vb < vboxes; ++vb)
+          for (int b = 0; b < nboxes; ++b)
+            tma_load_5d(xs + P.x_stage_bytes + (vb * nboxes + b) * 128 * dy_pitch, &P.tm_dy, full + 8 * st, n0 + b * P.ncb,
+                        tw_i * 8 * P.dy_stride + P.dy_off[var + vb][0], th_i * 16 * P.dy_stride + P.dy_off[var + vb][1],
+                        d * P.dy_stride + P.dy_off[var + vb][2], nb);
         if (++st == P.nstages) { st = 0; ph ^= 1; }
         if (++tw_i == P.tiles_w) {
           tw_i = 0;
@@ -125,8 +139,9 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
     __syncwarp();
   } else if (warp == 5) {
     const uint32_t swz_b = dy_pitch == 128 ? SWZ_128B : (dy_pitch == 64 ? SWZ_64B : SWZ_32B);
-    const uint32_t idesc = make_idesc_bf16(128, P.nt, 1, 1);
-    const uint64_t a_desc0 = make_smem_desc(0, /*lbo: next atom = next row*/ 64, /*sbo*/ P.bw * 64, SWZ_64B);
+    const uint32_t idesc = make_idesc_bf16(128, nn, 1, 1);
+    const uint64_t a_desc0 = make_smem_desc(0, /*lbo: next atom = next row (dc mode: next chunk tile)*/ dc ? P.bh * P.bw * 64 : 64,
+                                            /*sbo*/ P.bw * 64, SWZ_64B);
     const uint64_t b_desc0 = make_smem_desc(0, /*lbo: next 64-channel box*/ 128 * dy_pitch, 8 * dy_pitch, swz_b);
     const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
     const uint32_t a_lo0 = (uint32_t)a_desc0, b_lo0 = (uint32_t)b_desc0;   // LBO fields, address 0
@@ -163,10 +178,11 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
     const size_t tap_elems = (size_t)P.ci_total * P.co_total;
     float* outb = P.partial + (size_t)blockIdx.x * ((size_t)P.n_variants * ntaps_v) * tap_elems;
     for (int g = 0; g < P.ngroups; ++g) {
-      const int tap = (var * P.ngroups + g) * P.natoms + warp;
-      float* dst = outb + (size_t)tap * tap_elems + (size_t)(chunk * 32 + lane) * P.co_total + n0;
-      for (int cc = 0; cc * 32 < P.nt; ++cc) {
-        const int ncol = (P.nt - cc * 32) >= 32 ? 32 : 16;
+      // legacy: warp = kw atom of chunk `chunk`; dc mode: warp = chunk of the group, the columns run over var_boxes taps
+      const int tap = dc ? var : (var * P.ngroups + g) * P.natoms + warp;
+      float* dst = outb + (size_t)tap * tap_elems + (size_t)((dc ? chunk + warp : chunk) * 32 + lane) * P.co_total + n0;
+      for (int cc = 0; cc * 32 < nn; ++cc) {
+        const int ncol = (nn - cc * 32) >= 32 ? 32 : 16;
         uint32_t rr[32];
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + g * ntc + cc * 32;
         if (ncol == 32) {
@@ -178,8 +194,9 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
           for (int j = 0; j < 16; ++j) { rr[j] = r16[j]; rr[j + 16] = 0u; }
         }
         tmem_ld_wait();
-        if (warp < P.natoms) {
-          float4* d4 = reinterpret_cast<float4*>(dst + cc * 32);
+        if (warp < (dc ? ca_eff : P.natoms)) {
+          // dc mode: column cc * 32 belongs to sub-position var + (cc * 32) / nt, channel n0 + (cc * 32) % nt
+          float4* d4 = reinterpret_cast<float4*>(dc ? dst + (size_t)((cc * 32) / P.nt) * tap_elems + (cc * 32) % P.nt : dst + cc * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             if (j * 4 < ncol) {

@@ -1388,6 +1388,41 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
   for (int k = 0; k < A.nsplit; ++k) s += part[(size_t)k * per_split + i];
   grad[(size_t)cir * A.stride_ci + (size_t)co * A.stride_co + (size_t)A.tapmap[tap] * A.dst_tap_stride] = s;
 }
+// Tiled variant for the LARGE outputs (>= 512 blocks of one padded input-channel row x 64 output channels): a block
+// sums the splits reading 256-byte runs of the partial records, transposes (co, tap) through shared memory and writes
+// runs of `taps` contiguous floats of the torch layout -- the kernel above scatters single floats 108 bytes
+// ([co][ci][27]) or more apart, 32 sectors per warp store. Measured per launch (profiles/r02i_reduce_pack_ab.txt):
+// 512 x 256 x 4^3 89 -> 51 us, 512 x 512 x 3^3 88 -> 45 us, 256 x 512 x 3^3 38 -> 27 us; with fewer blocks the
+// scatter kernel's 27x finer grid wins (64 -> 64 x 3^3, 37 splits: 10 us against 43 us) and keeps the job.
+constexpr int kRedTileCols = 64;
+__global__ void __launch_bounds__(256) wgrad_reduce_tiled_kernel(const float* __restrict__ part, float* __restrict__ grad,
+                                                                 WgradReduceArgs A, int dst_ntaps) {
+  __shared__ float tile[kRedTileCols * 65];
+  const int ctiles = (A.co_total + kRedTileCols - 1) / kRedTileCols;
+  const int ci = (int)blockIdx.x / ctiles, co0 = ((int)blockIdx.x % ctiles) * kRedTileCols;
+  const int cir = concat_real_index(ci, A.split_pad, A.split_real, A.ci);
+  if (cir < 0) return;
+  const int TP = dst_ntaps | 1;
+  const long long per_split = (long long)A.ntap * A.ci_total * A.co_total;
+  for (int idx = threadIdx.x; idx < kRedTileCols * dst_ntaps; idx += 256) tile[(idx / dst_ntaps) * TP + idx % dst_ntaps] = 0.f;
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < A.ntap * kRedTileCols; idx += 256) {
+    const int c = idx & (kRedTileCols - 1), tap = idx / kRedTileCols;
+    const int dt = A.tapmap[tap];
+    if (dt < 0 || co0 + c >= A.co_total) continue;
+    const float* p = part + ((size_t)tap * A.ci_total + ci) * A.co_total + co0 + c;
+    float s = 0.f;
+    for (int k = 0; k < A.nsplit; ++k) s += __ldg(p + (size_t)k * per_split);
+    tile[c * TP + dt] = s;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < kRedTileCols * dst_ntaps; idx += 256) {
+    const int c = idx / dst_ntaps, t = idx - c * dst_ntaps;
+    const int co = co0 + c;
+    if (co >= A.co) continue;
+    grad[(size_t)cir * A.stride_ci + (size_t)co * A.stride_co + (size_t)t * A.dst_tap_stride] = tile[c * TP + t];
+  }
+}
 // Same reduction for SMALL outputs with many splits (the 32-channel layers: 27.6 k outputs x 148 splits): eight lanes
 // share one output and stride over the splits, so the serial chain is 8x shorter; shuffle tree, fixed order.
 __global__ void wgrad_reduce_wide_kernel(const float* __restrict__ part, float* __restrict__ grad, WgradReduceArgs A) {

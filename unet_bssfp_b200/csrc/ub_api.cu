@@ -849,7 +849,13 @@ extern "C" int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const 
     return launch_igemm(pl, st);
   }
   // UB_DECONV_K2S2 dgrad: gather the 8 fine sub-positions (parity tiles of dy, element stride 2)
-  P.td = d->d < 2 ? d->d : 2;
+  // Two output planes per tile: the stage holds the 8 parity tiles of every plane (64 KB per plane and 32-channel
+  // chunk), which leaves room for ONE stage (profiles/r02h_deconv_dgrad_ncu_summary.txt: 4 TB/s, tensor pipe 10 %,
+  // nothing near a roof). One-plane tiles with two or three stages (UB_DC_DGRAD_TD=1) are SLOWER on every level
+  // (64 -> 64 @64^3 0.61 -> 0.79 ms, profiles/r02i_wgrad_split_ab.txt): the launch is bound by the number of
+  // element-strided TMA boxes, not by exposed load latency.
+  static const int dc_td = getenv("UB_DC_DGRAD_TD") ? atoi(getenv("UB_DC_DGRAD_TD")) : 2;
+  P.td = d->d < dc_td ? d->d : dc_td;
   P.Do = d->d; P.Ho = d->h; P.Wo = d->w;
   P.n_atiles = 8; P.bw = 8; P.bh = 16; P.n_in_planes = P.td; P.in_stride = 2;
   P.ntaps = 8;
@@ -940,15 +946,45 @@ static int plan_wgrad(const ub_conv_desc* d, WgradPlan* pl) {
   P.tiles_h = cdiv(P.Ht, 16);
   P.x_stage_bytes = align_up(P.bh * P.bw * 64, 1024);
   P.dy_stage_bytes = 128 * P.nt * 2;
+  static const bool dc_mode = !(getenv("UB_DC_WGRAD_MODE") && atoi(getenv("UB_DC_WGRAD_MODE")) == 0);
+  if (dc_mode && d->kind == UB_DECONV_K2S2 && d->c1p == 0) {
+    // chunks on the M atoms, sub-positions side by side in N (igemm_wgrad.cuh, "dc mode")
+    P.chunk_atoms = P.n_chunks_total < 4 ? P.n_chunks_total : 4;
+    P.var_boxes = 256 / P.nt >= 8 ? 8 : (256 / P.nt >= 4 ? 4 : (256 / P.nt >= 2 ? 2 : 1));
+    P.x_stage_bytes = P.chunk_atoms * P.bh * P.bw * 64;      // 8 KB tiles, already 1024-aligned
+    P.dy_stage_bytes = P.var_boxes * 128 * P.nt * 2;
+  }
   const int stage = P.x_stage_bytes + P.dy_stage_bytes;
   P.nstages = (200 * 1024) / stage;
   if (P.nstages > 4) P.nstages = 4;
   if (P.nstages < 2) return fail(-2, "wgrad stage too large");
   pl->smem = P.nstages * stage + 8 * 16 + 64 + 1024;
-  P.tmem_cols = next_pow2_cols(P.ngroups * align_up(P.nt, 32));
+  P.tmem_cols = next_pow2_cols(P.ngroups * align_up((P.chunk_atoms ? P.var_boxes : 1) * P.nt, 32));
   const long long total_tiles = (long long)P.Nb * P.Dt * P.tiles_h * P.tiles_w;
-  const int items = P.n_chunks_total * P.n_variants * P.n_cotiles;
+  const int items = P.chunk_atoms ? cdiv(P.n_chunks_total, P.chunk_atoms) * (P.n_variants / P.var_boxes) * P.n_cotiles
+                                  : P.n_chunks_total * P.n_variants * P.n_cotiles;
+  // Splits of the voxel range per (chunk, variant, co tile) item. The CTAs are not persistent, so the grid must fill
+  // whole waves of the CTAs an SM can hold (shared memory and TMEM columns decide: one or two, three for the narrow
+  // layers). The old rule, cdiv(2 * 148, items), put 304 CTAs on 296 slots for the 64 -> 64 transposed conv: a second
+  // wave of 8 CTAs, SMs active 57 % of the launch (profiles/r02h_deconv_wgrad_ncu_summary.txt). Now: the split count
+  // that minimises waves x tiles-per-split, up to four waves' worth; UB_WGRAD_SPLIT_OLD=1 restores the old rule.
+  static const bool old_rule = getenv("UB_WGRAD_SPLIT_OLD") && atoi(getenv("UB_WGRAD_SPLIT_OLD")) != 0;
   long long nsplit = cdiv(2 * 148, items);
+  if (!old_rule) {
+    int occ = (228 * 1024) / (pl->smem + 1024);
+    if (occ > 512 / P.tmem_cols) occ = 512 / P.tmem_cols;
+    if (occ > 4) occ = 4;
+    if (occ < 1) occ = 1;
+    const long long cap = (long long)occ * sm_count();
+    long long best = 1, best_cost = -1;
+    const long long ns_max = cdiv(4 * cap, items) < total_tiles ? cdiv(4 * cap, items) : total_tiles;
+    for (long long ns = 1; ns <= ns_max; ++ns) {
+      // time ~ waves x (tiles per split + a fixed per-CTA cost: pipeline fill, TMEM read-out, partial record)
+      const long long cost = cdiv(items * ns, cap) * (cdiv(total_tiles, ns) + 32);
+      if (best_cost < 0 || cost < best_cost) { best = ns; best_cost = cost; }
+    }
+    nsplit = best;
+  }
   if (nsplit > total_tiles) nsplit = total_tiles;
   if (nsplit < 1) nsplit = 1;
   pl->grid = dim3((unsigned)nsplit, (unsigned)items, 1);
@@ -967,6 +1003,25 @@ static int wgrad_march_splits(const ub_conv_desc* d) {
   if (d->kind == UB_CONV_K4S2P1_S2D) cols *= 8;
   int ns = sm_count() / cols;
   return ns < 1 ? 1 : ns;
+}
+
+// split-K reduction of the weight-gradient partial records into the torch layout: many splits of a small output ->
+// the 8-lanes-per-output kernel; large outputs -> the tiled transpose; the rest -> one thread per output
+// (UB_WGRAD_REDUCE_OLD=1: never the tiled kernel, for A/B).
+static void launch_wgrad_reduce(const float* partial, float* dw, const WgradReduceArgs& R, cudaStream_t st) {
+  const long long per_split = (long long)R.ntap * R.ci_total * R.co_total;
+  const bool old_reduce = getenv("UB_WGRAD_REDUCE_OLD") && atoi(getenv("UB_WGRAD_REDUCE_OLD")) != 0;
+  int dst_ntaps = 0;
+  bool unit_taps = R.dst_tap_stride == 1;
+  for (int i = 0; i < R.ntap && i < 64; ++i)
+    if (R.tapmap[i] + 1 > dst_ntaps) dst_ntaps = R.tapmap[i] + 1;
+  if (per_split <= 65536 && R.nsplit >= 32)
+    wgrad_reduce_wide_kernel<<<(unsigned)((per_split * 8 + 255) / 256), 256, 0, st>>>(partial, dw, R);
+  else if (old_reduce || !unit_taps || dst_ntaps < 1 || dst_ntaps > 64 || R.ntap > 64 ||
+           R.ci_total * cdiv(R.co_total, kRedTileCols) < 512)
+    wgrad_reduce_kernel<<<(unsigned)((per_split + 255) / 256), 256, 0, st>>>(partial, dw, R);
+  else
+    wgrad_reduce_tiled_kernel<<<(unsigned)(R.ci_total * cdiv(R.co_total, kRedTileCols)), 256, 0, st>>>(partial, dw, R, dst_ntaps);
 }
 
 // Which kernel serves (desc, dir): 0 = igemm_fwd_kernel (generic tap-table implicit GEMM), 1 = igemm_march_kernel,
@@ -1040,11 +1095,7 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
     R.split_pad = d->c1p ? d->c0p : 0;
     R.split_real = d->c1p ? d->c0 : 0;
     for (int i = 0; i < 64; ++i) R.tapmap[i] = i < ntap ? i : -1;
-    const long long per_split = (long long)ntap * R.ci_total * d->cop;
-    if (per_split <= 65536 && nsplit >= 32)
-      wgrad_reduce_wide_kernel<<<(unsigned)((per_split * 8 + 255) / 256), 256, 0, st>>>(M.partial, dw, R);
-    else
-      wgrad_reduce_kernel<<<(unsigned)((per_split + 255) / 256), 256, 0, st>>>(M.partial, dw, R);
+    launch_wgrad_reduce(M.partial, dw, R, st);
     UB_LAUNCH_CHECK();
     return 0;
   }
@@ -1080,11 +1131,7 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
   R.split_pad = d->c1p ? d->c0p : 0;
   R.split_real = d->c1p ? d->c0 : 0;
   for (int i = 0; i < 64; ++i) R.tapmap[i] = i < pl.ntap_lin ? pl.tapmap[i] : -1;
-  const long long per_split = (long long)R.ntap * R.ci_total * R.co_total;
-  if (per_split <= 65536 && R.nsplit >= 32)
-    wgrad_reduce_wide_kernel<<<(unsigned)((per_split * 8 + 255) / 256), 256, 0, st>>>(P.partial, dw, R);
-  else
-    wgrad_reduce_kernel<<<(unsigned)((per_split + 255) / 256), 256, 0, st>>>(P.partial, dw, R);
+  launch_wgrad_reduce(P.partial, dw, R, st);
   UB_LAUNCH_CHECK();
   return 0;
 }

@@ -73,6 +73,7 @@ class _PackedWeights:
 
     def __init__(self):
         self._cur = {}
+        self.hold = False      # inside ``weights_unchanged``: operand copies packed in the scope stay valid until it ends
 
     def refresh(self, blocks, direction, f16_src0=frozenset()):
         """Re-pack the conv weights of ``blocks`` for ``direction`` (0 forward, 1 dgrad) from the live parameters.
@@ -81,12 +82,15 @@ class _PackedWeights:
         todo, seen = [], set()
         for b in blocks:
             key = (id(b.conv.weight), b.spec, direction)
-            if key not in seen:
+            if key not in seen and not (self.hold and key in self._cur):
                 seen.add(key)
                 todo.append((b.spec, b.conv.weight, direction | (ops.UB_PACK_F16_SRC0 if b.name in f16_src0 else 0)))
+        if not self.hold:
+            for k in [k for k in self._cur if k[2] == direction]:
+                del self._cur[k]
+        if not todo:
+            return
         outs = ops.pack_conv_weights_multi(todo)
-        for k in [k for k in self._cur if k[2] == direction]:
-            del self._cur[k]
         for (spec, w, _), out in zip(todo, outs):
             self._cur[(id(w), spec, direction)] = out       # valid for THIS pass (fp16 columns included, if any)
 
@@ -161,6 +165,25 @@ def apply_deferred_bn(log: list):
         if nm.num_batches_tracked is not None:
             nm.num_batches_tracked.add_(1)
     log.clear()
+
+
+@_contextlib.contextmanager
+def weights_unchanged(module: nn.Module):
+    """Caller's promise that the parameters of ``module`` (a Discriminator) are not written inside the scope: the
+    passes inside it share ONE bf16 operand copy per direction instead of re-packing per pass. ``GanTrainer.step``
+    wraps the part of a training step in which the discriminator is constant by construction -- the G phase's pass,
+    the D phase's two passes and their backwards all precede ``opt_d.step()`` (ref:src/model.py:259-281) -- which
+    takes 4 of the 6 discriminator packs out of a step. Leaving the scope drops the copies; outside it every pass
+    packs from the live parameters as before."""
+    caches = [m._cache for m in module.modules() if isinstance(getattr(m, "_cache", None), _PackedWeights)]
+    for c in caches:
+        c.hold = True
+    try:
+        yield module
+    finally:
+        for c in caches:
+            c.hold = False
+            c._cur.clear()
 
 
 def prepack_weights(module: nn.Module):

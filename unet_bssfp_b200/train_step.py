@@ -11,6 +11,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
+import contextlib
 import os
 
 from . import modules as _modules
@@ -196,17 +197,20 @@ class GanTrainer:
         if self.broadcast_buffers and _dist_on():
             broadcast_module_state(self.gen, buffers_only=True)
             broadcast_module_state(self.discr, buffers_only=True)
-        _set_requires_grad(self.discr, False)
-        g_loss, _ = self.gen_loss(x, y)
-        g_loss.backward()
-        self._reduce_and_step(self.reduce_g, self.opt_g)
-        _set_requires_grad(self.discr, True)
+        # the discriminator's parameters are constant from here to opt_d.step(): its six passes share two operand packs
+        hold = _modules.weights_unchanged(self.discr) if isinstance(self.discr, _modules.Discriminator) else contextlib.nullcontext()
+        with hold:
+            _set_requires_grad(self.discr, False)
+            g_loss, _ = self.gen_loss(x, y)
+            g_loss.backward()
+            self._reduce_and_step(self.reduce_g, self.opt_g)
+            _set_requires_grad(self.discr, True)
 
-        _set_requires_grad(self.gen, False)
-        d_loss = self.discr_loss(x, y)
-        d_loss.backward()
-        if self._branch_stream is not None:
-            torch.cuda.current_stream().wait_stream(self._branch_stream)   # the real pass's backward ran there
+            _set_requires_grad(self.gen, False)
+            d_loss = self.discr_loss(x, y)
+            d_loss.backward()
+            if self._branch_stream is not None:
+                torch.cuda.current_stream().wait_stream(self._branch_stream)   # the real pass's backward ran there
         self._reduce_and_step(self.reduce_d, self.opt_d)
         _set_requires_grad(self.gen, True)
         return g_loss.detach(), d_loss.detach()
