@@ -94,6 +94,7 @@ struct IgemmParams {
   float* stats;                  // [tile][2][w_rows_per_block] partial sum / sumsq, or nullptr
   // shared memory plan (bytes)
   int plane_stride, a_stage_bytes, b_stage_bytes, nsa, nsb, tmem_cols;
+  int box_planes;                // > 1: ONE TMA box carries all n_in_planes planes of an A tile (planes bh * bw * pitch apart)
   int nacc;                      // TMEM accumulator sets (>= 2: the epilogue of a tile overlaps the next tiles' MMAs; <= kMaxAccSets)
   int total_tiles;
 };
@@ -143,7 +144,7 @@ constexpr int kIgemmThreads = 192;  // marching / wgrad kernels: warps 0-3 epilo
 // does not pay (profiles/r02g_epi16.txt).
 constexpr int kFwdEpiWarps = 8;
 constexpr int kFwdEpiWarpsWide = 16;
-constexpr int kFwdThreads = (kFwdEpiWarps + 2) * 32;  // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
+constexpr int kFwdThreads = (kFwdEpiWarps + 3) * 32;  // warps 0-7 epilogue, 8 TMA producer (A), 9 MMA issuer, 10 TMA producer (B)
 constexpr int kFwdRedFloats = 2 * kFwdEpiWarps * 2 * 128 + 128;  // [parity][warp][sum|sumsq][128] + bias[128]
 
 struct IgemmTileCoord {
@@ -228,8 +229,12 @@ __device__ __forceinline__ void issue_folded_tap(uint32_t acc0, uint32_t a_tap, 
 // free, except that the second stream must not touch an accumulator before the first stream's overwriting UMMA
 // (first tap of a tile) has been issued: `first_bar`, one arrival per tile, orders exactly that (tcgen05 fences on
 // both sides; the tensor pipe executes in issue order). The stage / accumulator barriers count two commits.
+// Warp roles: 0 .. kEpi-1 epilogue, kEpi: TMA producer of the activation (A) stages, kEpi+1 (.. +kMma): MMA issuer(s),
+// last warp: TMA producer of the weight (B) ring. Two producers because ONE thread issuing every TMA operation bound the
+// launches with little MMA work per box: the stem forward needs 40 A + 64 B boxes per tile, ~290 cycles each
+// = the 30 k cycles per tile the launch took, against 16 k cycles of UMMAs (profiles/r02i_producer_ab.txt).
 template <int kEpi, bool kStats, int kMma = 1>
-__global__ void __launch_bounds__((kEpi + 1 + kMma) * 32, 1)
+__global__ void __launch_bounds__((kEpi + 2 + kMma) * 32, 1)
 igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
   static_assert(!kStats || kEpi == kFwdEpiWarps, "the statistics staging area is sized for kFwdEpiWarps warps");
   static_assert(kMma == 1 || kMma == 2, "one or two MMA-issuing warps");
@@ -263,8 +268,8 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
   if (warp == kEpi && lane == 0) {
     tma_prefetch_desc(&P.tm_src[0]);
     if (P.n_chunks_total > P.n_chunks_src0) tma_prefetch_desc(&P.tm_src[1]);
-    tma_prefetch_desc(&P.tm_w);
   }
+  if (warp == kEpi + 1 + kMma && lane == 0) tma_prefetch_desc(&P.tm_w);
   if (warp == kEpi + 1) tmem_alloc_rt(smem_u32(tmem_slot), P.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -273,12 +278,11 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
   const int pitch = P.kc * 2;
 
   if (warp == kEpi) {
-    // =========================== TMA producer ===========================
+    // =========================== TMA producer: activation stages ===========================
     if (lane == 0) {
       const uint32_t a_bytes = (uint32_t)(P.n_atiles * P.n_in_planes * P.bh * P.bw * pitch);
-      const uint32_t b_bytes = (uint32_t)((P.kd_fold ? P.fold_nd : 1) * NT.nt * pitch);
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
+      int sa = 0;
+      uint32_t pa = 0;
       for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
         const IgemmTileCoord T = igemm_tile(P, t);
         for (int ch = 0; ch < P.n_chunks_total; ++ch) {
@@ -294,11 +298,31 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
             const int oi = P.chunks_per_group ? grp : at + NT.tapset;
             const int cw = T.w0 * P.in_stride + P.atile_off[oi][0];
             const int chh = T.h0 * P.in_stride + P.atile_off[oi][1];
-            for (int p = 0; p < P.n_in_planes; ++p, dst += P.plane_stride) {
-              const int cd = (T.d0 + p) * P.in_stride + P.atile_off[oi][2];
-              tma_load_5d(dst, tm, a_full + 8 * sa, c0, cw, chh, cd, nb5);
+            if (P.box_planes > 1) {
+              // one box for all the planes of the tile (out-of-volume planes are zero-filled like the halo rows)
+              tma_load_5d(dst, tm, a_full + 8 * sa, c0, cw, chh, T.d0 * P.in_stride + P.atile_off[oi][2], nb5);
+              dst += P.n_in_planes * P.plane_stride;
+            } else {
+              for (int p = 0; p < P.n_in_planes; ++p, dst += P.plane_stride) {
+                const int cd = (T.d0 + p) * P.in_stride + P.atile_off[oi][2];
+                tma_load_5d(dst, tm, a_full + 8 * sa, c0, cw, chh, cd, nb5);
+              }
             }
           }
+          if (++sa == P.nsa) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kEpi + 1 + kMma) {
+    // =========================== TMA producer: weight ring ===========================
+    if (lane == 0) {
+      const uint32_t b_bytes = (uint32_t)((P.kd_fold ? P.fold_nd : 1) * NT.nt * pitch);
+      int sb = 0;
+      uint32_t pb = 0;
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        for (int ch = 0; ch < P.n_chunks_total; ++ch) {
+          const int grp = P.chunks_per_group ? ch / P.chunks_per_group : 0;
           const int wk = (P.chunks_per_group ? ch % P.chunks_per_group : ch) * P.kc;
           const IgemmTap* taps = P.taps + (P.chunks_per_group ? grp : NT.tapset) * P.ntaps;
           for (int tp = 0; tp < P.ntaps; ++tp) {
@@ -313,13 +337,12 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
             }
             if (++sb == P.nsb) { sb = 0; pb ^= 1; }
           }
-          if (++sa == P.nsa) { sa = 0; pa ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp >= kEpi + 1) {
-    // =========================== MMA issuer(s) ===========================
+    // =========================== MMA issuer(s): warps kEpi+1 .. kEpi+kMma ===========================
     // The whole warp walks the pipeline (uniform control flow); one elected lane issues.
     const int half = kMma == 2 ? warp - (kEpi + 1) : 0;     // which UMMA of every K = 16 pair this warp issues (kMma == 2)
     const uint32_t koff = 2u * (uint32_t)half;              // its K offset in 16-byte units

@@ -51,7 +51,10 @@ struct WgradParams {
   int chunk_atoms, var_boxes;
 };
 
-__global__ void __launch_bounds__(kIgemmThreads, 1)
+// Warps 0-3 epilogue, 4 TMA producer of the X tiles, 5 MMA issuer, 6 TMA producer of the dY tiles (two producer threads:
+// a stage of the transposed-conv form is 2-4 X boxes + 4 dY boxes for 8 UMMAs, one thread's issue rate was the bound).
+constexpr int kWgradThreads = kIgemmThreads + 32;
+__global__ void __launch_bounds__(kWgradThreads, 1)
 igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -86,14 +89,12 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
   const int niter = t_end > t_begin ? (int)(t_end - t_begin) : 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < P.nstages; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); }
+    for (int i = 0; i < P.nstages; ++i) { mbar_init(full + 8 * i, 2); mbar_init(empty + 8 * i, 1); }   // full: both producers arrive
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
-  if (warp == 4 && lane == 0) {
-    tma_prefetch_desc(&P.tm_x[s1 ? 1 : 0]);
-    tma_prefetch_desc(&P.tm_dy);
-  }
+  if (warp == 4 && lane == 0) tma_prefetch_desc(&P.tm_x[s1 ? 1 : 0]);
+  if (warp == 6 && lane == 0) tma_prefetch_desc(&P.tm_dy);
   if (warp == 5) tmem_alloc_rt(smem_u32(tmem_slot), P.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -102,9 +103,10 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
   const int nboxes = P.nt / P.ncb;
   const int dy_pitch = P.ncb * 2;
 
-  if (warp == 4) {
+  if (warp == 4 || warp == 6) {
     if (lane == 0) {
-      const uint32_t bytes = (uint32_t)(ca_eff * P.bh * P.bw * 64 + vboxes * 128 * P.nt * 2);
+      const bool xprod = warp == 4;     // this thread loads the X tiles, the other one the dY tiles
+      const uint32_t bytes = xprod ? (uint32_t)(ca_eff * P.bh * P.bw * 64) : (uint32_t)(vboxes * 128 * P.nt * 2);
       const CUtensorMap* tmx = &P.tm_x[s1 ? 1 : 0];
       long long tt = t_begin;
       int tw_i = (int)(tt % P.tiles_w); tt /= P.tiles_w;
@@ -117,15 +119,18 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
         mbar_wait(empty + 8 * st, ph ^ 1);
         mbar_expect_tx(full + 8 * st, bytes);
         const uint32_t xs = base + st * stage_bytes;
-        for (int a = 0; a < ca_eff; ++a)     // dc mode: the chunks of the group, 8 KB apart (bw x bh = 8 x 16 rows of 64 B)
-          tma_load_5d(xs + a * (P.bh * P.bw * 64), tmx, full + 8 * st, c0 + a * 32, tw_i * 8 * P.x_stride + P.x_off[var][0],
-                      th_i * 16 * P.x_stride + P.x_off[var][1], d * P.x_stride + P.x_off[var][2],
-                      nb * P.x_nmul + P.x_nadd[var]);
-        for (int vb = 0; vb < vboxes; ++vb)
-          for (int b = 0; b < nboxes; ++b)
-            tma_load_5d(xs + P.x_stage_bytes + (vb * nboxes + b) * 128 * dy_pitch, &P.tm_dy, full + 8 * st, n0 + b * P.ncb,
-                        tw_i * 8 * P.dy_stride + P.dy_off[var + vb][0], th_i * 16 * P.dy_stride + P.dy_off[var + vb][1],
-                        d * P.dy_stride + P.dy_off[var + vb][2], nb);
+        if (xprod) {
+          for (int a = 0; a < ca_eff; ++a)     // dc mode: the chunks of the group, 8 KB apart (bw x bh = 8 x 16 rows of 64 B)
+            tma_load_5d(xs + a * (P.bh * P.bw * 64), tmx, full + 8 * st, c0 + a * 32, tw_i * 8 * P.x_stride + P.x_off[var][0],
+                        th_i * 16 * P.x_stride + P.x_off[var][1], d * P.x_stride + P.x_off[var][2],
+                        nb * P.x_nmul + P.x_nadd[var]);
+        } else {
+          for (int vb = 0; vb < vboxes; ++vb)
+            for (int b = 0; b < nboxes; ++b)
+              tma_load_5d(xs + P.x_stage_bytes + (vb * nboxes + b) * 128 * dy_pitch, &P.tm_dy, full + 8 * st, n0 + b * P.ncb,
+                          tw_i * 8 * P.dy_stride + P.dy_off[var + vb][0], th_i * 16 * P.dy_stride + P.dy_off[var + vb][1],
+                          d * P.dy_stride + P.dy_off[var + vb][2], nb);
+        }
         if (++st == P.nstages) { st = 0; ph ^= 1; }
         if (++tw_i == P.tiles_w) {
           tw_i = 0;

@@ -83,12 +83,12 @@ static CUtensorMapSwizzle swz_for_bytes(int b) {
 }
 // NDHWC bf16 activation: dims (C, W, H, D, N); box (box_c, bw*es, bh*es, 1, 1); element stride es on w,h
 static int make_act_map(CUtensorMap* m, const void* ptr, int cp, int W, int H, int D, int N, int box_c, int bw,
-                        int bh, int es) {
+                        int bh, int es, int bd = 1) {
   cuuint64_t gd[5] = {(cuuint64_t)cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
   cuuint64_t gs[4] = {(cuuint64_t)cp * 2, (cuuint64_t)W * cp * 2, (cuuint64_t)H * W * cp * 2,
                       (cuuint64_t)D * H * W * cp * 2};
-  cuuint32_t bx[5] = {(cuuint32_t)box_c, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), 1, 1};
-  cuuint32_t st[5] = {1, (cuuint32_t)es, (cuuint32_t)es, 1, 1};
+  cuuint32_t bx[5] = {(cuuint32_t)box_c, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), (cuuint32_t)(bd > 1 ? bd * es : 1), 1};
+  cuuint32_t st[5] = {1, (cuuint32_t)es, (cuuint32_t)es, (cuuint32_t)(bd > 1 ? es : 1), 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), gd, gs, bx, st,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz_for_bytes(box_c * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -292,13 +292,26 @@ static int opt_in_smem(SmemOptIn& st, const void* fn, const char* what) {
   return 0;
 }
 
+// Planes per activation TMA box of the generic kernel: all the planes of a tile in ONE box (the producer thread's
+// issue rate bounds the launches with little MMA work per box); UB_PLANE_BOX=0: one box per plane, as before.
+static int plane_box(const IgemmParams& P) {
+  static const bool on = !(getenv("UB_PLANE_BOX") && atoi(getenv("UB_PLANE_BOX")) == 0);
+  if (!on || P.n_in_planes <= 1 || P.n_in_planes * P.in_stride > 256) return 1;
+  // several A tiles per stage: every tile's box must start on a 128-byte boundary
+  if (P.n_atiles > 1 && (P.n_in_planes * P.bh * P.bw * P.kc * 2) % 128 != 0) return 1;
+  return P.n_in_planes;
+}
+
 // Fill the smem plan / grid once the geometry fields of P are set. nt_max = widest N tile.
 // The kernel is persistent with one CTA per SM: the whole shared memory goes to the TMA rings.
 static int finish_plan(IgemmPlan* pl, int nt_max) {
   IgemmParams& P = pl->P;
   const int pitch = P.kc * 2;
-  P.plane_stride = align_up(P.bh * P.bw * pitch, 1024);
-  P.a_stage_bytes = P.n_atiles * P.n_in_planes * P.plane_stride;
+  P.box_planes = plane_box(P);
+  // a multi-plane box writes its planes back to back; the swizzle is a function of the absolute shared-memory address
+  // (tools/probe_umma.cu), so a plane may start at any multiple of 128 bytes
+  P.plane_stride = P.box_planes > 1 ? P.bh * P.bw * pitch : align_up(P.bh * P.bw * pitch, 1024);
+  P.a_stage_bytes = align_up(P.n_atiles * P.n_in_planes * P.plane_stride, 1024);
   P.b_stage_bytes = align_up((P.kd_fold ? P.fold_nd : 1) * nt_max * pitch, 1024);
   const int misc = 8 * 80 + 64 + kFwdRedFloats * 4 + 1024;
   // A stages: two (the next chunk / next tile loads while this one is multiplied) when they fit.
@@ -350,23 +363,23 @@ static int launch_igemm(const IgemmPlan& pl, cudaStream_t st) {
     // two MMA-issuing warps (see igemm_fwd.cuh)
     if (pl.P.stats != nullptr) {
       if (int e = opt_in_smem(opt[3], (const void*)igemm_fwd_kernel<kFwdEpiWarps, true, 2>, "igemm_fwd")) return e;
-      igemm_fwd_kernel<kFwdEpiWarps, true, 2><<<pl.grid, (kFwdEpiWarps + 3) * 32, pl.smem, st>>>(pl.P);
+      igemm_fwd_kernel<kFwdEpiWarps, true, 2><<<pl.grid, (kFwdEpiWarps + 4) * 32, pl.smem, st>>>(pl.P);
     } else {
       if (int e = opt_in_smem(opt[4], (const void*)igemm_fwd_kernel<kFwdEpiWarps, false, 2>, "igemm_fwd")) return e;
-      igemm_fwd_kernel<kFwdEpiWarps, false, 2><<<pl.grid, (kFwdEpiWarps + 3) * 32, pl.smem, st>>>(pl.P);
+      igemm_fwd_kernel<kFwdEpiWarps, false, 2><<<pl.grid, (kFwdEpiWarps + 4) * 32, pl.smem, st>>>(pl.P);
     }
     UB_LAUNCH_CHECK();
     return 0;
   }
   if (pl.P.stats != nullptr) {
     if (int e = opt_in_smem(opt[0], (const void*)igemm_fwd_kernel<kFwdEpiWarps, true>, "igemm_fwd")) return e;
-    igemm_fwd_kernel<kFwdEpiWarps, true><<<pl.grid, (kFwdEpiWarps + 2) * 32, pl.smem, st>>>(pl.P);
+    igemm_fwd_kernel<kFwdEpiWarps, true><<<pl.grid, (kFwdEpiWarps + 3) * 32, pl.smem, st>>>(pl.P);
   } else if (epi16) {
     if (int e = opt_in_smem(opt[1], (const void*)igemm_fwd_kernel<kFwdEpiWarpsWide, false>, "igemm_fwd")) return e;
-    igemm_fwd_kernel<kFwdEpiWarpsWide, false><<<pl.grid, (kFwdEpiWarpsWide + 2) * 32, pl.smem, st>>>(pl.P);
+    igemm_fwd_kernel<kFwdEpiWarpsWide, false><<<pl.grid, (kFwdEpiWarpsWide + 3) * 32, pl.smem, st>>>(pl.P);
   } else {
     if (int e = opt_in_smem(opt[2], (const void*)igemm_fwd_kernel<kFwdEpiWarps, false>, "igemm_fwd")) return e;
-    igemm_fwd_kernel<kFwdEpiWarps, false><<<pl.grid, (kFwdEpiWarps + 2) * 32, pl.smem, st>>>(pl.P);
+    igemm_fwd_kernel<kFwdEpiWarps, false><<<pl.grid, (kFwdEpiWarps + 3) * 32, pl.smem, st>>>(pl.P);
   }
   UB_LAUNCH_CHECK();
   return 0;
@@ -605,9 +618,9 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
         for (int kw = 0; kw < k; ++kw, ++t)
           P.taps[t] = IgemmTap{0, (uint16_t)(kh * P.bw + kw), (uint16_t)kd, (uint16_t)t};
     if (P.kd_fold) P.ntaps = 9;   // taps 0..8 are (kd = 0, kh, kw): row offsets and weight blocks of the folded pack
-    if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 1)) return e;
+    if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 1, plane_box(P))) return e;
     if (d->c1p)
-      if (int e = make_act_map(&P.tm_src[1], src1, d->c1p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 1)) return e;
+      if (int e = make_act_map(&P.tm_src[1], src1, d->c1p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 1, plane_box(P))) return e;
     if (int e = finish_plan(&pl, nt_max)) return e;
     return launch_igemm(pl, st);
   }
@@ -642,7 +655,7 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
                 P.taps[g * P.ntaps + t] = IgemmTap{0, (uint16_t)(sh * P.bw + sw), (uint16_t)sd, (uint16_t)((kd * 4 + kh) * 4 + kw)};
               }
         }
-    if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w / 2, d->h / 2, d->d / 2, d->n * 8, 32, P.bw, P.bh, 1)) return e;
+    if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w / 2, d->h / 2, d->d / 2, d->n * 8, 32, P.bw, P.bh, 1, plane_box(P))) return e;
     if (int e = finish_plan(&pl, nt_max)) return e;
     return launch_igemm(pl, st);
   }
@@ -667,9 +680,9 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
           P.taps[t] = IgemmTap{(uint16_t)at, (uint16_t)(k4_shift(kh) * P.bw + k4_shift(kw)), (uint16_t)k4_shift(kd),
                                (uint16_t)t};
         }
-    if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 2)) return e;
+    if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 2, plane_box(P))) return e;
     if (d->c1p)
-      if (int e = make_act_map(&P.tm_src[1], src1, d->c1p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 2)) return e;
+      if (int e = make_act_map(&P.tm_src[1], src1, d->c1p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 2, plane_box(P))) return e;
     if (int e = finish_plan(&pl, nt_max)) return e;
     return launch_igemm(pl, st);
   }
@@ -703,7 +716,7 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
       T.out_p[0] = 0; T.out_p[1] = sp2 & 1; T.out_p[2] = (sp2 >> 1) & 1;
     }
     if (int e = make_w_map(&P.tm_w, w_packed, ktot, (long long)ntaps * d->cop, 32, 128)) return e;
-    if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 1)) return e;
+    if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 1, plane_box(P))) return e;
     if (int e = finish_plan(&pl, 128)) return e;
     return launch_igemm(pl, st);
   }
@@ -720,7 +733,7 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
       }
     P.n_ntiles = base_tiles * 8;
   }
-  if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 1)) return e;
+  if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 1, plane_box(P))) return e;
   if (int e = finish_plan(&pl, nt_max)) return e;
   return launch_igemm(pl, st);
 }
@@ -791,7 +804,7 @@ extern "C" int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const 
         for (int kw = 0; kw < k; ++kw, ++t)
           P.taps[t] = IgemmTap{0, (uint16_t)(kh * P.bw + kw), (uint16_t)kd, (uint16_t)t};
     if (P.kd_fold) P.ntaps = 9;
-    if (int e = make_act_map(&P.tm_src[0], dy, d->cop, ow, oh, od, d->n, 32, P.bw, P.bh, 1)) return e;
+    if (int e = make_act_map(&P.tm_src[0], dy, d->cop, ow, oh, od, d->n, 32, P.bw, P.bh, 1, plane_box(P))) return e;
     if (int e = finish_plan(&pl, nt_max)) return e;
     return launch_igemm(pl, st);
   }
@@ -814,7 +827,7 @@ extern "C" int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const 
     }
     P.ntaps = fold ? 4 : 8;
     P.out_s = 2;
-    if (int e = make_act_map(&P.tm_src[0], dy, d->cop, ow, oh, od, d->n, 32, P.bw, P.bh, 1)) return e;
+    if (int e = make_act_map(&P.tm_src[0], dy, d->cop, ow, oh, od, d->n, 32, P.bw, P.bh, 1, plane_box(P))) return e;
     // one launch: the 8 parity classes are extra N tiles (blockIdx.y), each with its own tap set,
     // tile origin and scatter offset
     const int base_tiles = P.n_ntiles;
@@ -866,7 +879,7 @@ extern "C" int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const 
         P.atile_off[at][0] = k; P.atile_off[at][1] = j; P.atile_off[at][2] = i;
         P.taps[at] = IgemmTap{(uint16_t)at, 0, 0, (uint16_t)at};
       }
-  if (int e = make_act_map(&P.tm_src[0], dy, d->cop, ow, oh, od, d->n, 32, P.bw, P.bh, 2)) return e;
+  if (int e = make_act_map(&P.tm_src[0], dy, d->cop, ow, oh, od, d->n, 32, P.bw, P.bh, 2, plane_box(P))) return e;
   if (int e = finish_plan(&pl, nt_max)) return e;
   return launch_igemm(pl, st);
 }
@@ -1115,7 +1128,7 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
   if (int e = make_act_map(&P.tm_dy, dy, d->cop, ow, oh, od, d->n, P.ncb, 8, 16, P.dy_stride)) return e;
   static SmemOptIn gopt;
   if (int e = opt_in_smem(gopt, (const void*)igemm_wgrad_kernel, "igemm_wgrad")) return e;
-  igemm_wgrad_kernel<<<pl.grid, kIgemmThreads, pl.smem, st>>>(P);
+  igemm_wgrad_kernel<<<pl.grid, kWgradThreads, pl.smem, st>>>(P);
   UB_LAUNCH_CHECK();
 
   // split-K reduce + conversion to the torch layout
