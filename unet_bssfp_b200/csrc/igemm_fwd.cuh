@@ -95,6 +95,8 @@ struct IgemmParams {
   // shared memory plan (bytes)
   int plane_stride, a_stage_bytes, b_stage_bytes, nsa, nsb, tmem_cols;
   int box_planes;                // > 1: ONE TMA box carries all n_in_planes planes of an A tile (planes bh * bw * pitch apart)
+  int b_boxes, b_box_rows;       // b_boxes > 0 (folded 3x3x3 tiles, depth-tap blocks adjacent in the pack): the weight tile
+                                 // of a tap arrives as b_boxes boxes of b_box_rows rows instead of one box per depth tap
   int nacc;                      // TMEM accumulator sets (>= 2: the epilogue of a tile overlaps the next tiles' MMAs; <= kMaxAccSets)
   int total_tiles;
 };
@@ -329,6 +331,13 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
             mbar_wait(b_empty + 8 * sb, pb ^ 1);
             mbar_expect_tx(b_full + 8 * sb, b_bytes);
             const int brow = (taps[tp].wblock + NT.wblock_add) * P.b_block_rows + NT.n0;
+            if (P.b_boxes) {
+              for (int j = 0; j < P.b_boxes; ++j)
+                tma_load_2d(b_base + sb * P.b_stage_bytes + j * P.b_box_rows * pitch, &P.tm_w, b_full + 8 * sb, wk,
+                            brow + j * P.b_box_rows);
+              if (++sb == P.nsb) { sb = 0; pb ^= 1; }
+              continue;
+            }
             tma_load_2d(b_base + sb * P.b_stage_bytes, &P.tm_w, b_full + 8 * sb, wk, brow);
             if (P.kd_fold) {   // the other depth-tap blocks of the folded tile (TMA boxes hold <= 256 rows)
               for (int j = 1; j < P.fold_nd; ++j)

@@ -302,6 +302,19 @@ static int plane_box(const IgemmParams& P) {
   return P.n_in_planes;
 }
 
+// Folded 3x3x3 tiles: the three depth-tap blocks of a (chunk, kh, kw) weight tile are adjacent rows of the pack
+// (fold_row_step == nt), so the tile can arrive as ONE TMA box of 3 * nt rows (two boxes beyond 256 rows) instead of
+// three. Measured neutral on every 3x3x3 shape of the step (profiles/r02i_wbox_ab.txt: these launches are not bound
+// by the producer's issue rate), so it stays opt-in: UB_WBOX_MERGE=1.
+static void merged_weight_boxes(IgemmParams& P, int nt) {
+  static const bool on = getenv("UB_WBOX_MERGE") && atoi(getenv("UB_WBOX_MERGE")) != 0;
+  P.b_boxes = 0; P.b_box_rows = 0;
+  if (!on || !P.kd_fold || P.fold_nd != 3 || P.fold_row_step != nt) return;
+  const int rows = 3 * nt, nb = cdiv(rows, 256);
+  if (rows % nb != 0 || (rows / nb) % 8 != 0) return;
+  P.b_boxes = nb; P.b_box_rows = rows / nb;
+}
+
 // Fill the smem plan / grid once the geometry fields of P are set. nt_max = widest N tile.
 // The kernel is persistent with one CTA per SM: the whole shared memory goes to the TMA rings.
 static int finish_plan(IgemmPlan* pl, int nt_max) {
@@ -603,7 +616,8 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
   P.fold_nd = 3;
   P.fold_row_step = nt_max;
   P.b_block_rows = P.kd_fold ? 3 * d->cop : d->cop;
-  if (int e = make_w_map(&P.tm_w, w_packed, ktot, (long long)ntaps * d->cop, 32, nt_max)) return e;
+  merged_weight_boxes(P, nt_max);
+  if (int e = make_w_map(&P.tm_w, w_packed, ktot, (long long)ntaps * d->cop, 32, P.b_boxes ? P.b_box_rows : nt_max)) return e;
 
   if (d->kind == UB_CONV_K3S1P1 || d->kind == UB_CONV_K1) {
     const int k = d->kind == UB_CONV_K3S1P1 ? 3 : 1;
@@ -786,7 +800,8 @@ extern "C" int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const 
   P.fold_nd = 3;
   P.fold_row_step = nt_max;
   P.b_block_rows = P.kd_fold ? 3 * ncols : ncols;
-  if (int e = make_w_map(&P.tm_w, w_packed_dgrad, d->cop, (long long)ntaps * ncols, 32, nt_max)) return e;
+  merged_weight_boxes(P, nt_max);
+  if (int e = make_w_map(&P.tm_w, w_packed_dgrad, d->cop, (long long)ntaps * ncols, 32, P.b_boxes ? P.b_box_rows : nt_max)) return e;
   bool uniform = true;
   for (int i = 0; i < P.n_ntiles; ++i) uniform = uniform && P.ntile[i].nt == nt_max;
   if (!uniform) return fail(-2, "dgrad N tiles of unequal width are not supported (c0p=%d c1p=%d)", d->c0p, d->c1p);
@@ -1098,7 +1113,7 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
     const int nsplit = wgrad_march_splits(d);
     const int smem = kWmXStages * kWmXBytes + (kWmYSlots + kt - 1) * kWmYBytes + 8 * 32 + 64 + 1024;
     const dim3 grid((unsigned)nsplit, (unsigned)(M.n_chunks_total * M.n_cotiles * (stem ? 8 : 1)));
-    wfns[wv]<<<grid, kIgemmThreads, smem, st>>>(M);
+    wfns[wv]<<<grid, kWgradMarchThreads, smem, st>>>(M);
     UB_LAUNCH_CHECK();
     WgradReduceArgs R;
     memset(&R, 0, sizeof(R));

@@ -43,8 +43,11 @@ struct WgradMarchParams {
 constexpr int kWmXStages = 4, kWmXBytes = 12288;
 constexpr int kWmYSlots = 8, kWmYBytes = 8192;   // + KT-1 mirror slots
 
+// Warps 0-3 epilogue (kTf: operand transform first), 4 TMA producer of the X planes, 5 MMA issuer, 6 TMA producer of the
+// dY planes (two producer threads: the stem form has 16 UMMAs of 48 cycles per plane against two to three TMA boxes).
+constexpr int kWgradMarchThreads = kIgemmThreads + 32;
 template <int KT, bool kTf>
-__global__ void __launch_bounds__(kIgemmThreads, 1)
+__global__ void __launch_bounds__(kWgradMarchThreads, 1)
 wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
   static_assert(!kTf || KT == 3, "the operand transform serves the 3x3x3 layers");
   constexpr int BW = 8 + KT - 1, BH = 16 + KT - 1;     // halo box
@@ -86,10 +89,8 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
-  if (warp == 4 && lane == 0) {
-    tma_prefetch_desc(&P.tm_x[s1 ? 1 : 0]);
-    tma_prefetch_desc(&P.tm_dy);
-  }
+  if (warp == 4 && lane == 0) tma_prefetch_desc(&P.tm_x[s1 ? 1 : 0]);
+  if (warp == 6 && lane == 0) tma_prefetch_desc(&P.tm_dy);
   if (warp == 5) tmem_alloc_rt(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
@@ -97,10 +98,31 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 4) {
-    // =========================== TMA producer ===========================
+    // =========================== TMA producer: X planes ===========================
     if (lane == 0) {
       const CUtensorMap* tmx = &P.tm_x[s1 ? 1 : 0];
       int xs = 0; uint32_t xp = 0;    // X ring
+      for (int it = i_begin; it < i_end; ++it) {
+        int t = it;
+        const int seg = t % P.nseg; t /= P.nseg;
+        const int w0 = (t % P.tiles_w) * 8; t /= P.tiles_w;
+        const int h0 = (t % P.tiles_h) * 16; t /= P.tiles_h;
+        const int nb = t;
+        const int d0 = seg * P.seg_len;
+        int d1 = d0 + P.seg_len; if (d1 > P.D) d1 = P.D;
+        for (int p = d0; p < d1; ++p) {
+          mbar_wait(x_empty + 8 * xs, xp ^ 1);
+          mbar_expect_tx(x_full + 8 * xs, BW * BH * 64);
+          tma_load_5d(x_base + xs * kWmXBytes, tmx, x_full + 8 * xs, c0, w0 + xoff_w, h0 + xoff_h, p,
+                      KT == 2 ? nb * 8 + parity : nb);
+          if (++xs == kWmXStages) { xs = 0; xp ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 6) {
+    // =========================== TMA producer: dY planes ===========================
+    if (lane == 0) {
       int ys = 0; uint32_t yp = 0;    // dY ring
       auto load_dy = [&](int q, int nb, int h0, int w0) {
         mbar_wait(y_empty + 8 * ys, yp ^ 1);
@@ -122,14 +144,7 @@ wgrad_march_kernel(const __grid_constant__ WgradMarchParams P) {
         // outside [0, D) are out-of-bounds TMA coordinates (zero fill = the conv padding in depth)
 #pragma unroll
         for (int j = 0; j < KT - 1; ++j) load_dy(d0 + doff + j, nb, h0, w0);
-        for (int p = d0; p < d1; ++p) {
-          load_dy(p + doff + KT - 1, nb, h0, w0);
-          mbar_wait(x_empty + 8 * xs, xp ^ 1);
-          mbar_expect_tx(x_full + 8 * xs, BW * BH * 64);
-          tma_load_5d(x_base + xs * kWmXBytes, tmx, x_full + 8 * xs, c0, w0 + xoff_w, h0 + xoff_h, p,
-                      KT == 2 ? nb * 8 + parity : nb);
-          if (++xs == kWmXStages) { xs = 0; xp ^= 1; }
-        }
+        for (int p = d0; p < d1; ++p) load_dy(p + doff + KT - 1, nb, h0, w0);
       }
     }
     __syncwarp();
