@@ -471,21 +471,28 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
             const uint32_t acc = (ch | tp) != 0;
             // one branch per tap, not per plane: the planes of a tap are then one straight run of UMMAs (every branch
             // in between makes the compiler move all seven operands to uniform registers again)
-            auto planes = [&](auto pl) {
+            auto planes = [&](auto pl, auto ks) {
 #pragma unroll
               for (int o = 0; o < decltype(pl)::value; ++o) {
                 if (kMma == 2) {
                   umma_bf16_lohi(acc0 + o * ntc, a_lo + o * plane16 + koff, a_hi, b_lo + koff, b_hi, idesc, half ? 1u : acc);
                 } else {
-                  umma_bf16_lohi(acc0 + o * ntc, a_lo + o * plane16, a_hi, b_lo, b_hi, idesc, acc);
-                  umma_bf16_lohi(acc0 + o * ntc, a_lo + o * plane16 + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                  // K = 16 steps of the chunk: two for 32-channel chunks, four for 64-channel chunks (128-byte rows)
+#pragma unroll
+                  for (int k = 0; k < decltype(ks)::value; ++k)
+                    umma_bf16_lohi(acc0 + o * ntc, a_lo + o * plane16 + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k == 0 ? acc : 1u);
                 }
               }
             };
-            if (T.planes == 4) planes(IntC<4>{});
-            else if (T.planes == 2) planes(IntC<2>{});
-            else if (T.planes == 1) planes(IntC<1>{});
-            else planes(IntC<3>{});
+            if (P.kc == 64) {
+              if (T.planes == 4) planes(IntC<4>{}, IntC<4>{});
+              else if (T.planes == 2) planes(IntC<2>{}, IntC<4>{});
+              else if (T.planes == 1) planes(IntC<1>{}, IntC<4>{});
+              else planes(IntC<3>{}, IntC<4>{});
+            } else if (T.planes == 4) planes(IntC<4>{}, IntC<2>{});
+            else if (T.planes == 2) planes(IntC<2>{}, IntC<2>{});
+            else if (T.planes == 1) planes(IntC<1>{}, IntC<2>{});
+            else planes(IntC<3>{}, IntC<2>{});
             umma_commit(b_empty + 8 * sb);
           }
           if (kMma == 2 && first_tap && half == 0) {

@@ -292,6 +292,16 @@ static int opt_in_smem(SmemOptIn& st, const void* fn, const char* what) {
   return 0;
 }
 
+// Channels per K chunk of the generic kernel. The TMA unit fetches ~one row per 5 cycles per SM whatever its length
+// (tools/tma_rate.cu); 64-channel chunks -- 128-byte rows, four K = 16 UMMAs per chunk -- halve the rows of a layer
+// with >= 64 input channels. Built for the transposed convs (no halo, so the wider stages fit) and measured there
+// (profiles/r02j_kc64_ab.txt): 64 -> 64 forward 0.496 -> 0.507 ms (bound by its 2.1 GB of output stores, not by the
+// loads), 128 -> 64 0.083 -> 0.078, dgrads equal or slower (one-plane tiles). Opt-in: UB_KC64 bit 0 forward, bit 1 dgrad.
+static int chunk_channels(int kind, int channels, int dir) {
+  static const int mask = getenv("UB_KC64") ? atoi(getenv("UB_KC64")) : 0;
+  return ((mask >> dir) & 1) && kind == UB_DECONV_K2S2 && channels % 64 == 0 ? 64 : 32;
+}
+
 // Planes per activation TMA box of the generic kernel: all the planes of a tile in ONE box (the producer thread's
 // issue rate bounds the launches with little MMA work per box); UB_PLANE_BOX=0: one box per plane, as before.
 static int plane_box(const IgemmParams& P) {
@@ -598,9 +608,9 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
   IgemmPlan pl;
   memset(&pl, 0, sizeof(pl));
   IgemmParams& P = pl.P;
-  P.kc = 32;
-  P.n_chunks_src0 = d->c0p / 32;
-  P.n_chunks_total = ktot / 32;
+  P.kc = d->c1p == 0 ? chunk_channels(d->kind, d->c0p, 0) : 32;
+  P.n_chunks_src0 = d->c0p / P.kc;
+  P.n_chunks_total = ktot / P.kc;
   P.w_rows_per_block = d->cop;
   P.Nb = d->n;
   P.bias = bias;
@@ -617,7 +627,7 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
   P.fold_row_step = nt_max;
   P.b_block_rows = P.kd_fold ? 3 * d->cop : d->cop;
   merged_weight_boxes(P, nt_max);
-  if (int e = make_w_map(&P.tm_w, w_packed, ktot, (long long)ntaps * d->cop, 32, P.b_boxes ? P.b_box_rows : nt_max)) return e;
+  if (int e = make_w_map(&P.tm_w, w_packed, ktot, (long long)ntaps * d->cop, P.kc, P.b_boxes ? P.b_box_rows : nt_max)) return e;
 
   if (d->kind == UB_CONV_K3S1P1 || d->kind == UB_CONV_K1) {
     const int k = d->kind == UB_CONV_K3S1P1 ? 3 : 1;
@@ -729,8 +739,8 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
       T.wblock_add = 2 * sp2;
       T.out_p[0] = 0; T.out_p[1] = sp2 & 1; T.out_p[2] = (sp2 >> 1) & 1;
     }
-    if (int e = make_w_map(&P.tm_w, w_packed, ktot, (long long)ntaps * d->cop, 32, 128)) return e;
-    if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 1, plane_box(P))) return e;
+    if (int e = make_w_map(&P.tm_w, w_packed, ktot, (long long)ntaps * d->cop, P.kc, 128)) return e;
+    if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w, d->h, d->d, d->n, P.kc, P.bw, P.bh, 1, plane_box(P))) return e;
     if (int e = finish_plan(&pl, 128)) return e;
     return launch_igemm(pl, st);
   }
@@ -747,7 +757,7 @@ extern "C" int ub_conv_fwd(const ub_conv_desc* d, const void* src0, const void* 
       }
     P.n_ntiles = base_tiles * 8;
   }
-  if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w, d->h, d->d, d->n, 32, P.bw, P.bh, 1, plane_box(P))) return e;
+  if (int e = make_act_map(&P.tm_src[0], src0, d->c0p, d->w, d->h, d->d, d->n, P.kc, P.bw, P.bh, 1, plane_box(P))) return e;
   if (int e = finish_plan(&pl, nt_max)) return e;
   return launch_igemm(pl, st);
 }
@@ -784,9 +794,9 @@ extern "C" int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const 
   IgemmPlan pl;
   memset(&pl, 0, sizeof(pl));
   IgemmParams& P = pl.P;
-  P.kc = 32;
-  P.n_chunks_src0 = d->cop / 32;
-  P.n_chunks_total = d->cop / 32;
+  P.kc = chunk_channels(d->kind, d->cop, 1);
+  P.n_chunks_src0 = d->cop / P.kc;
+  P.n_chunks_total = d->cop / P.kc;
   P.w_rows_per_block = ncols;
   P.Nb = d->n;
   P.oD = d->d; P.oH = d->h; P.oW = d->w;
@@ -801,7 +811,7 @@ extern "C" int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const 
   P.fold_row_step = nt_max;
   P.b_block_rows = P.kd_fold ? 3 * ncols : ncols;
   merged_weight_boxes(P, nt_max);
-  if (int e = make_w_map(&P.tm_w, w_packed_dgrad, d->cop, (long long)ntaps * ncols, 32, P.b_boxes ? P.b_box_rows : nt_max)) return e;
+  if (int e = make_w_map(&P.tm_w, w_packed_dgrad, d->cop, (long long)ntaps * ncols, P.kc, P.b_boxes ? P.b_box_rows : nt_max)) return e;
   bool uniform = true;
   for (int i = 0; i < P.n_ntiles; ++i) uniform = uniform && P.ntile[i].nt == nt_max;
   if (!uniform) return fail(-2, "dgrad N tiles of unequal width are not supported (c0p=%d c1p=%d)", d->c0p, d->c1p);
@@ -884,6 +894,7 @@ extern "C" int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const 
   // element-strided TMA boxes, not by exposed load latency.
   static const int dc_td = getenv("UB_DC_DGRAD_TD") ? atoi(getenv("UB_DC_DGRAD_TD")) : 2;
   P.td = d->d < dc_td ? d->d : dc_td;
+  if (P.kc == 64) P.td = 1;      // 8 parity tiles x 16 KB per plane: one plane per stage
   P.Do = d->d; P.Ho = d->h; P.Wo = d->w;
   P.n_atiles = 8; P.bw = 8; P.bh = 16; P.n_in_planes = P.td; P.in_stride = 2;
   P.ntaps = 8;
@@ -894,7 +905,7 @@ extern "C" int ub_conv_dgrad_fused(const ub_conv_desc* d, const void* dy, const 
         P.atile_off[at][0] = k; P.atile_off[at][1] = j; P.atile_off[at][2] = i;
         P.taps[at] = IgemmTap{(uint16_t)at, 0, 0, (uint16_t)at};
       }
-  if (int e = make_act_map(&P.tm_src[0], dy, d->cop, ow, oh, od, d->n, 32, P.bw, P.bh, 2, plane_box(P))) return e;
+  if (int e = make_act_map(&P.tm_src[0], dy, d->cop, ow, oh, od, d->n, P.kc, P.bw, P.bh, 2, plane_box(P))) return e;
   if (int e = finish_plan(&pl, nt_max)) return e;
   return launch_igemm(pl, st);
 }
