@@ -53,6 +53,7 @@ struct MarchParams {
                                     // against weight columns packed as fp16, UB_PACK_F16_SRC0)
   NormActArgs tf;
   int tf_f16;                       // the transformed chunk is an fp16 operand (its weight columns are packed as fp16)
+  int mma2;                         // single-CTA, untransformed variants: TWO MMA-issuing warps, planes alternating
 };
 
 constexpr int kMarchPlaneBytes = 12288;   // 180 rows x 64 B, padded to a multiple of 1024
@@ -68,6 +69,54 @@ constexpr int kMarchThreads = (kMarchEpiWarps + 2) * 32;   // warps 0-7 epilogue
 constexpr int kMarchTfThreads = 64;
 constexpr int kMarchThreadsTf = kMarchThreads + kMarchTfThreads;
 
+// One MMA issuer of the single-CTA, untransformed kernel taking planes p_first + me, + step, ...: ring slot, stage and
+// barrier phases follow from the plane index alone, so several issuers need no shared state.
+template <bool kPairUnused>
+__device__ __forceinline__ void march_issue_planes(const MarchParams& P, int me, int step, int p_first, int p_last, int nch,
+                                                   uint32_t tmem, uint32_t w_base, uint32_t a_base, uint32_t w_full,
+                                                   uint32_t a_full, uint32_t a_empty, uint32_t acc_full, uint32_t acc_empty) {
+  const uint32_t idesc_bf = make_idesc_bf16(128, 96, 0, 0);
+  const uint32_t idesc_h = idesc_f16_operands(idesc_bf);
+  const uint32_t a_hi = (uint32_t)(make_smem_desc(0, 16, 10 * 64, SWZ_64B) >> 32);
+  const uint32_t b_hi = (uint32_t)(make_smem_desc(0, 16, 8 * 64, SWZ_64B) >> 32);
+  const uint32_t lbo_lo = 1u << 16;
+  const bool leader = elect_one();
+  const int n_f16 = P.src0_f16 ? P.n_chunks_src0 : 0;
+  mbar_wait(w_full, 0);
+  tc_fence_after();
+  for (int p = p_first + me; p <= p_last; p += step) {
+    const int pi = p - p_first;
+    const int slot = pi % kMarchRing;
+    mbar_wait(acc_empty + 8 * slot, (((uint32_t)(pi / kMarchRing)) & 1u) ^ 1u);
+    tc_fence_after();
+    const uint32_t acc = tmem + slot * 96;
+    for (int c = 0; c < nch; ++c) {
+      const int si = pi * nch + c;
+      const int sa = si % P.nsa;
+      mbar_wait(a_full + 8 * sa, ((uint32_t)(si / P.nsa)) & 1u);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t idesc = c < n_f16 ? idesc_h : idesc_bf;
+        const uint32_t a_lo = lbo_lo | ((a_base + sa * kMarchPlaneBytes) >> 4);
+        const uint32_t b_lo = lbo_lo | ((w_base + c * 9 * kMarchWTileBytes) >> 4);
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const uint32_t ao = (uint32_t)((kh * 10 + kw) * 64) >> 4;
+            const uint32_t bo = (uint32_t)((kh * 3 + kw) * kMarchWTileBytes) >> 4;
+            umma_bf16_lohi(acc, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc, (uint32_t)((c | kh | kw) != 0));
+            umma_bf16_lohi(acc, a_lo + ao + 2, a_hi, b_lo + bo + 2, b_hi, idesc, 1u);
+          }
+        umma_commit(a_empty + 8 * sa);
+      }
+      __syncwarp();
+    }
+    if (leader) umma_commit(acc_full + 8 * slot);
+    __syncwarp();
+  }
+}
+
 // kPair: two CTAs of a cluster (cta_group::2) own two neighbouring 16x8 columns and march together; every
 // UMMA is M = 256 x N = 96 with the 96 weight rows split 48 / 48 between the two CTAs' shared memories,
 // so each SM reads 4 KB (A) + 1.5 KB (B) per instruction instead of 4 + 3 KB -- the shared-memory pipe is
@@ -78,8 +127,13 @@ constexpr int kMarchThreadsTf = kMarchThreads + kMarchTfThreads;
 // a_loc[stage] (pair mode: each CTA waits for its own plane), the transform warps hand the stage to the MMA thread
 // through a_ready[stage] in the leader CTA (one arrival per CTA). Untransformed chunks keep the a_full path. A
 // stage alternates between the two paths, so the barrier phases are tracked per stage in bit masks.
+// mma2 (!kTf, !kPair, opt-in): warp kMmaWarp + 1 is a second MMA issuer. The two warps take alternating planes -- different
+// accumulator slots and different A stages, so nothing orders them against each other -- and one warp's per-plane
+// hand-off (two barrier waits, two fences, two commits) runs while the other one's UMMAs are in the pipe. Unlike the
+// generic kernel's UB_MMA2 (two warps feeding the SAME accumulators) the streams are independent.
+constexpr int kMarchThreads2 = kMarchThreads + 32;
 template <bool kNormBwd, bool kPair, bool kTf>
-__global__ void __launch_bounds__(kTf ? kMarchThreadsTf : kMarchThreads, 1)
+__global__ void __launch_bounds__(kTf ? kMarchThreadsTf : kMarchThreads2, 1)
 igemm_march_kernel(const __grid_constant__ MarchParams P) {
   static_assert(!(kNormBwd && kTf), "the operand transform is a forward-path feature");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -185,7 +239,9 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
     __syncwarp();
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer (leader CTA only in pair mode) ===========================
-    if (rank == 0) {
+    if (!kTf && !kPair && P.mma2) {
+      march_issue_planes<kPair>(P, 0, 2, p_first, p_last, nch, tmem, w_base, a_base, w_full, a_full, a_empty, acc_full, acc_empty);
+    } else if (rank == 0) {
       const uint32_t idesc_bf = make_idesc_bf16(kPair ? 256 : 128, 96, 0, 0);
       const uint32_t idesc_h = idesc_f16_operands(idesc_bf);
       const uint32_t idesc_tf = (kTf && P.tf_f16) ? idesc_h : idesc_bf;   // chunk 0 of a kTf CTA
@@ -248,6 +304,10 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
         if (++slot == kMarchRing) { slot = 0; pacc ^= 1; }
       }
     }
+  } else if (!kTf && warp == kMmaWarp + 1) {
+    // =========================== second MMA issuer (mma2): odd planes ===========================
+    if (!kPair && P.mma2) march_issue_planes<kPair>(P, 1, 2, p_first, p_last, nch, tmem, w_base, a_base, w_full, a_full, a_empty,
+                                                    acc_full, acc_empty);
   } else if (kTf && warp >= kMarchEpiWarps) {
     // =========================== operand transform (warps 8-9) ===========================
     const int t = (int)threadIdx.x - kMarchEpiWarps * 32;

@@ -513,7 +513,12 @@ static int launch_march(const void* src0, int c0p, const void* src1, int c1p, in
   MarchFn fn = fns[variant][pair ? 1 : 0];
   if (int e = opt_in_smem(opt[variant][pair ? 1 : 0], (const void*)fn, "igemm_march")) return e;
   const unsigned grid = (unsigned)(n * P.tiles_h * P.tiles_w * P.nseg);
-  const unsigned threads = tf ? kMarchThreadsTf : kMarchThreads;
+  const unsigned threads = tf ? kMarchThreadsTf : kMarchThreads2;
+  // two MMA-issuing warps on alternating planes in every single-CTA launch (one-chunk 32 -> 32 forward 0.875 -> 0.71 ms,
+  // its dgrad 0.85 -> 0.70, 24 -> 32 0.85 -> 0.68; three chunks without CTA pairs 2.18 -> 2.05: profiles/r02j_march_mma2.txt);
+  // UB_MARCH_MMA2=n: only layers with <= n chunks, 0: one issuer
+  static const int march_mma2 = getenv("UB_MARCH_MMA2") ? atoi(getenv("UB_MARCH_MMA2")) : 3;
+  P.mma2 = (!tf && !pair && march_mma2 && P.n_chunks_total <= march_mma2) ? 1 : 0;
   if (pair) {
     // cluster of two CTAs along x: blocks (2k, 2k+1) take the w tiles (2j, 2j+1) of one column pair
     cudaLaunchConfig_t cfg;
@@ -1121,6 +1126,8 @@ extern "C" int ub_conv_wgrad(const ub_conv_desc* d, const void* src0, const void
     static SmemOptIn wopt[3];
     const int wv = stem ? 1 : (src0_act ? 2 : 0);
     if (int e = opt_in_smem(wopt[wv], (const void*)wfns[wv], "wgrad_march")) return e;
+    static const bool wm_mma2 = !(getenv("UB_WGRAD_MMA2") && atoi(getenv("UB_WGRAD_MMA2")) == 0);
+    M.mma2 = wm_mma2 ? 1 : 0;
     const int nsplit = wgrad_march_splits(d);
     const int smem = kWmXStages * kWmXBytes + (kWmYSlots + kt - 1) * kWmYBytes + 8 * 32 + 64 + 1024;
     const dim3 grid((unsigned)nsplit, (unsigned)(M.n_chunks_total * M.n_cotiles * (stem ? 8 : 1)));
