@@ -95,6 +95,8 @@ struct IgemmParams {
   // shared memory plan (bytes)
   int plane_stride, a_stage_bytes, b_stage_bytes, nsa, nsb, tmem_cols;
   int box_planes;                // > 1: ONE TMA box carries all n_in_planes planes of an A tile (planes bh * bw * pitch apart)
+  int mma_planes;                // kMma == 2 instantiations: the two issuing warps split the PLANES of a tile (separate
+                                 // accumulators, both K = 16 halves each) instead of the K halves of every instruction
   int b_boxes, b_box_rows;       // b_boxes > 0 (folded 3x3x3 tiles, depth-tap blocks adjacent in the pack): the weight tile
                                  // of a tap arrives as b_boxes boxes of b_box_rows rows instead of one box per depth tap
   int nacc;                      // TMEM accumulator sets (>= 2: the epilogue of a tile overlaps the next tiles' MMAs; <= kMaxAccSets)
@@ -353,8 +355,10 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
   } else if (warp >= kEpi + 1) {
     // =========================== MMA issuer(s): warps kEpi+1 .. kEpi+kMma ===========================
     // The whole warp walks the pipeline (uniform control flow); one elected lane issues.
-    const int half = kMma == 2 ? warp - (kEpi + 1) : 0;     // which UMMA of every K = 16 pair this warp issues (kMma == 2)
-    const uint32_t koff = 2u * (uint32_t)half;              // its K offset in 16-byte units
+    const bool split_planes = kMma == 2 && P.mma_planes != 0;
+    const int ph = kMma == 2 ? warp - (kEpi + 1) : 0;        // this warp's index among the issuers
+    const int half = split_planes ? 0 : ph;                  // which UMMA of every K = 16 pair this warp issues (K-half mode)
+    const uint32_t koff = 2u * (uint32_t)half;               // its K offset in 16-byte units
     const uint32_t swz = P.kc == 32 ? SWZ_64B : (P.kc == 16 ? SWZ_32B : SWZ_128B);
     const uint32_t idesc = make_idesc_bf16(128, NT.nt, 0, 0);
     const uint32_t a_hi = (uint32_t)(make_smem_desc(0, 16, P.bw * pitch, swz) >> 32);
@@ -413,7 +417,7 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
           mbar_wait(b_full + 8 * sb, pb);
           tc_fence_after();
           const bool first_tap = (ch | tp) == 0;
-          if (kMma == 2 && first_tap && half == 1) {
+          if (kMma == 2 && !split_planes && first_tap && half == 1) {
             // the first stream's overwriting UMMAs of this tile must be in the pipe before anything accumulates
             mbar_wait(first_bar + 8 * slot, pacc);
             tc_fence_after();
@@ -422,7 +426,23 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
             const IgemmTap Tp = P.taps[tbase + tp];
             const uint32_t a_tap = lbo_lo | ((a_stage + Tp.row_off * pitch) >> 4);
             const uint32_t b_lo0 = lbo_lo | ((b_base + sb * P.b_stage_bytes) >> 4);
-            if ((ch | tp) != 0 && sched != 0) {
+            if (split_planes && sched != 0) {
+              // plane-split issuers: each warp runs the schedule of HALF the tile's planes on its own accumulators --
+              // (3, 3, 4) -> two (3, 2, 2) halves, (3, 2, 2) -> two (3, 1, 1), (2, 2, 4) -> two (2, 2, 2)
+              const uint32_t nh = sched == 2 ? 1u : 2u;                       // output planes per issuer
+              const uint32_t accp = acc0 + (uint32_t)ph * nh * (uint32_t)ntc, a_p = a_tap + (uint32_t)ph * nh * plane16;
+              if ((ch | tp) != 0) {
+                if (sched == 1) issue_folded_tap<3, 2, 2, 1>(accp, a_p, a_hi, b_lo0, b_hi, (uint32_t)ntc, plane16, kd_rows16, idesc_blk, 0u);
+                else if (sched == 2) issue_folded_tap<3, 1, 1, 1>(accp, a_p, a_hi, b_lo0, b_hi, (uint32_t)ntc, plane16, kd_rows16, idesc_blk, 0u);
+                else issue_folded_tap<2, 2, 2, 1>(accp, a_p, a_hi, b_lo0, b_hi, (uint32_t)ntc, plane16, kd_rows16, idesc_blk, 0u);
+              } else {
+                if (sched == 1) issue_first_tap<3, 2, 1>(accp, a_p, a_hi, b_lo0, b_hi, (uint32_t)ntc, plane16, kd_rows16, idesc, 0u, 0);
+                else if (sched == 2) issue_first_tap<3, 1, 1>(accp, a_p, a_hi, b_lo0, b_hi, (uint32_t)ntc, plane16, kd_rows16, idesc, 0u, 0);
+                else issue_first_tap<2, 2, 1>(accp, a_p, a_hi, b_lo0, b_hi, (uint32_t)ntc, plane16, kd_rows16, idesc, 0u, 0);
+              }
+            } else if (split_planes && ph == 1) {
+              // ragged tile: the first issuer runs the whole table, this one only commits
+            } else if ((ch | tp) != 0 && sched != 0) {
               // full tile of one of the three shapes the step uses: compile-time schedule
               if (sched == 1) issue_folded_tap<3, 3, 4, kMma>(acc0, a_tap, a_hi, b_lo0, b_hi, (uint32_t)ntc, plane16, kd_rows16, idesc_blk, koff);
               else if (sched == 2) issue_folded_tap<3, 2, 2, kMma>(acc0, a_tap, a_hi, b_lo0, b_hi, (uint32_t)ntc, plane16, kd_rows16, idesc_blk, koff);
@@ -432,7 +452,7 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
 #pragma unroll
               for (int e = 0; e < 12; ++e) {
                 if ((fs_valid >> e) & 1u) {
-                  if (kMma == 2) {
+                  if (kMma == 2 && !split_planes) {
                     umma_bf16_lohi(acc0 + fs_d[e], a_tap + fs_a[e] + koff, a_hi, b_lo0 + fs_b[e] + koff, b_hi, fs_i[e], 1u);
                   } else {
                     umma_bf16_lohi(acc0 + fs_d[e], a_tap + fs_a[e], a_hi, b_lo0 + fs_b[e], b_hi, fs_i[e], 1u);
@@ -453,7 +473,7 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
                 for (int o = o_lo; o <= o_hi; ++o) {
                   const int kd = p_in - o;
                   const uint32_t b_lo = b_lo0 + (uint32_t)(ndm1 - kd) * kd_rows16;
-                  if (kMma == 2) {
+                  if (kMma == 2 && !split_planes) {
                     umma_bf16_lohi(acc0 + o * ntc, a_lo + koff, a_hi, b_lo + koff, b_hi, idesc, half ? 1u : (uint32_t)(kd != 0));
                   } else {
                     umma_bf16_lohi(acc0 + o * ntc, a_lo, a_hi, b_lo, b_hi, idesc, (uint32_t)(kd != 0));
@@ -472,9 +492,12 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
             // one branch per tap, not per plane: the planes of a tap are then one straight run of UMMAs (every branch
             // in between makes the compiler move all seven operands to uniform registers again)
             auto planes = [&](auto pl, auto ks) {
+              constexpr int PL = decltype(pl)::value;
 #pragma unroll
-              for (int o = 0; o < decltype(pl)::value; ++o) {
-                if (kMma == 2) {
+              for (int o = 0; o < PL; ++o) {
+                // plane-split issuers: even plane counts are halved between the two warps, odd ones stay with the first
+                if (split_planes && ((PL % 2 == 0) ? (o / (PL / 2) != ph) : (ph != 0))) continue;
+                if (kMma == 2 && !split_planes) {
                   umma_bf16_lohi(acc0 + o * ntc, a_lo + o * plane16 + koff, a_hi, b_lo + koff, b_hi, idesc, half ? 1u : acc);
                 } else {
                   // K = 16 steps of the chunk: two for 32-channel chunks, four for 64-channel chunks (128-byte rows)
@@ -495,7 +518,7 @@ igemm_fwd_kernel(const __grid_constant__ IgemmParams P) {
             else planes(IntC<3>{}, IntC<2>{});
             umma_commit(b_empty + 8 * sb);
           }
-          if (kMma == 2 && first_tap && half == 0) {
+          if (kMma == 2 && !split_planes && first_tap && half == 0) {
             tc_fence_before();
             if (leader) mbar_arrive(first_bar + 8 * slot);
           }

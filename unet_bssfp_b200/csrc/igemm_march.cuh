@@ -71,11 +71,12 @@ constexpr int kMarchThreadsTf = kMarchThreads + kMarchTfThreads;
 
 // One MMA issuer of the single-CTA, untransformed kernel taking planes p_first + me, + step, ...: ring slot, stage and
 // barrier phases follow from the plane index alone, so several issuers need no shared state.
-template <bool kPairUnused>
+template <bool kPair>
 __device__ __forceinline__ void march_issue_planes(const MarchParams& P, int me, int step, int p_first, int p_last, int nch,
                                                    uint32_t tmem, uint32_t w_base, uint32_t a_base, uint32_t w_full,
                                                    uint32_t a_full, uint32_t a_empty, uint32_t acc_full, uint32_t acc_empty) {
-  const uint32_t idesc_bf = make_idesc_bf16(128, 96, 0, 0);
+  constexpr int kWTile = kPair ? kMarchWTileBytes / 2 : kMarchWTileBytes;   // this CTA's share of a weight tile
+  const uint32_t idesc_bf = make_idesc_bf16(kPair ? 256 : 128, 96, 0, 0);
   const uint32_t idesc_h = idesc_f16_operands(idesc_bf);
   const uint32_t a_hi = (uint32_t)(make_smem_desc(0, 16, 10 * 64, SWZ_64B) >> 32);
   const uint32_t b_hi = (uint32_t)(make_smem_desc(0, 16, 8 * 64, SWZ_64B) >> 32);
@@ -98,21 +99,30 @@ __device__ __forceinline__ void march_issue_planes(const MarchParams& P, int me,
       if (leader) {
         const uint32_t idesc = c < n_f16 ? idesc_h : idesc_bf;
         const uint32_t a_lo = lbo_lo | ((a_base + sa * kMarchPlaneBytes) >> 4);
-        const uint32_t b_lo = lbo_lo | ((w_base + c * 9 * kMarchWTileBytes) >> 4);
+        const uint32_t b_lo = lbo_lo | ((w_base + c * 9 * kWTile) >> 4);
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
             const uint32_t ao = (uint32_t)((kh * 10 + kw) * 64) >> 4;
-            const uint32_t bo = (uint32_t)((kh * 3 + kw) * kMarchWTileBytes) >> 4;
-            umma_bf16_lohi(acc, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc, (uint32_t)((c | kh | kw) != 0));
-            umma_bf16_lohi(acc, a_lo + ao + 2, a_hi, b_lo + bo + 2, b_hi, idesc, 1u);
+            const uint32_t bo = (uint32_t)((kh * 3 + kw) * kWTile) >> 4;
+            if (kPair) {
+              umma_bf16_lohi_pair(acc, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc, (uint32_t)((c | kh | kw) != 0));
+              umma_bf16_lohi_pair(acc, a_lo + ao + 2, a_hi, b_lo + bo + 2, b_hi, idesc, 1u);
+            } else {
+              umma_bf16_lohi(acc, a_lo + ao, a_hi, b_lo + bo, b_hi, idesc, (uint32_t)((c | kh | kw) != 0));
+              umma_bf16_lohi(acc, a_lo + ao + 2, a_hi, b_lo + bo + 2, b_hi, idesc, 1u);
+            }
           }
-        umma_commit(a_empty + 8 * sa);
+        if (kPair) umma_commit_pair(a_empty + 8 * sa);
+        else umma_commit(a_empty + 8 * sa);
       }
       __syncwarp();
     }
-    if (leader) umma_commit(acc_full + 8 * slot);
+    if (leader) {
+      if (kPair) umma_commit_pair(acc_full + 8 * slot);
+      else umma_commit(acc_full + 8 * slot);
+    }
     __syncwarp();
   }
 }
@@ -239,8 +249,9 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
     __syncwarp();
   } else if (warp == kMmaWarp) {
     // =========================== MMA issuer (leader CTA only in pair mode) ===========================
-    if (!kTf && !kPair && P.mma2) {
-      march_issue_planes<kPair>(P, 0, 2, p_first, p_last, nch, tmem, w_base, a_base, w_full, a_full, a_empty, acc_full, acc_empty);
+    if (!kTf && P.mma2) {
+      if (rank == 0)
+        march_issue_planes<kPair>(P, 0, 2, p_first, p_last, nch, tmem, w_base, a_base, w_full, a_full, a_empty, acc_full, acc_empty);
     } else if (rank == 0) {
       const uint32_t idesc_bf = make_idesc_bf16(kPair ? 256 : 128, 96, 0, 0);
       const uint32_t idesc_h = idesc_f16_operands(idesc_bf);
@@ -306,8 +317,8 @@ igemm_march_kernel(const __grid_constant__ MarchParams P) {
     }
   } else if (!kTf && warp == kMmaWarp + 1) {
     // =========================== second MMA issuer (mma2): odd planes ===========================
-    if (!kPair && P.mma2) march_issue_planes<kPair>(P, 1, 2, p_first, p_last, nch, tmem, w_base, a_base, w_full, a_full, a_empty,
-                                                    acc_full, acc_empty);
+    if (P.mma2 && rank == 0) march_issue_planes<kPair>(P, 1, 2, p_first, p_last, nch, tmem, w_base, a_base, w_full, a_full, a_empty,
+                                                       acc_full, acc_empty);
   } else if (kTf && warp >= kMarchEpiWarps) {
     // =========================== operand transform (warps 8-9) ===========================
     const int t = (int)threadIdx.x - kMarchEpiWarps * 32;

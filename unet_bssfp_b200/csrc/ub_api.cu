@@ -373,16 +373,8 @@ static int finish_plan(IgemmPlan* pl, int nt_max) {
   return 0;
 }
 
-static int launch_igemm(const IgemmPlan& pl, cudaStream_t st) {
-  // three instantiations: with statistics (8 epilogue warps, 64 accumulator registers per thread), and without
-  // statistics with 8 (default) or 16 (UB_EPI16=1) epilogue warps. Measured (profiles/r02g_epi16.txt): dropping the
-  // statistics code alone takes the transposed conv 64 -> 64 from 0.568 to 0.503 ms and the stem dgrad from 0.69 to
-  // 0.64 ms (120 instead of 168 registers); sixteen warps add little there (0.486) and cost elsewhere (32 -> 96-column
-  // dgrad 2.39 -> 2.47 ms, stem dgrad 0.70), so eight it stays.
+static int launch_igemm_mma2(const IgemmPlan& pl, cudaStream_t st) {
   static SmemOptIn opt[5];
-  static const bool epi16 = getenv("UB_EPI16") && atoi(getenv("UB_EPI16")) != 0;
-  static const bool mma2 = getenv("UB_MMA2") && atoi(getenv("UB_MMA2")) != 0;
-  if (mma2 && pl.P.kc == 32) {
     // two MMA-issuing warps (see igemm_fwd.cuh)
     if (pl.P.stats != nullptr) {
       if (int e = opt_in_smem(opt[3], (const void*)igemm_fwd_kernel<kFwdEpiWarps, true, 2>, "igemm_fwd")) return e;
@@ -393,6 +385,29 @@ static int launch_igemm(const IgemmPlan& pl, cudaStream_t st) {
     }
     UB_LAUNCH_CHECK();
     return 0;
+}
+
+static int launch_igemm(const IgemmPlan& pl, cudaStream_t st) {
+  // three instantiations: with statistics (8 epilogue warps, 64 accumulator registers per thread), and without
+  // statistics with 8 (default) or 16 (UB_EPI16=1) epilogue warps. Measured (profiles/r02g_epi16.txt): dropping the
+  // statistics code alone takes the transposed conv 64 -> 64 from 0.568 to 0.503 ms and the stem dgrad from 0.69 to
+  // 0.64 ms (120 instead of 168 registers); sixteen warps add little there (0.486) and cost elsewhere (32 -> 96-column
+  // dgrad 2.39 -> 2.47 ms, stem dgrad 0.70), so eight it stays.
+  static SmemOptIn opt[5];
+  static const bool epi16 = getenv("UB_EPI16") && atoi(getenv("UB_EPI16")) != 0;
+  static const bool mma2 = getenv("UB_MMA2") && atoi(getenv("UB_MMA2")) != 0;
+  // Two issuing warps that split the PLANES of a tile (independent accumulators, igemm_fwd.cuh `mma_planes`). Measured per
+  // shape (profiles/r02j_fwd_mma_planes.txt): the four-plane tiles with three depth taps per UMMA -- the 64-channel 3x3x3
+  // layers -- gain 6-9 % (64 -> 64 @64^3 forward 0.365 -> 0.341 ms, dgrad 0.357 -> 0.325, 64+64 -> 64 0.679 -> 0.640,
+  // 32 -> 64 0.210 -> 0.195); two-plane tiles (128 channels, the 96-column dgrad) do not move, the stem, the transposed
+  // convs, the 1x1x1 head and the 8^3 level lose 2-20 %. So: on for that schedule only. UB_MMA_PLANES=0: off, 2: everywhere.
+  static const int mma_planes_env = getenv("UB_MMA_PLANES") ? atoi(getenv("UB_MMA_PLANES")) : 1;
+  const bool mma_planes = mma_planes_env == 2 ? pl.P.td >= 2
+                                              : (mma_planes_env == 1 && pl.P.kd_fold == 3 && pl.P.fold_nd == 3 && pl.P.td == 4);
+  if ((mma2 || mma_planes) && pl.P.kc == 32) {
+    IgemmPlan plm = pl;
+    plm.P.mma_planes = (!mma2 && mma_planes) ? 1 : 0;
+    return launch_igemm_mma2(plm, st);
   }
   if (pl.P.stats != nullptr) {
     if (int e = opt_in_smem(opt[0], (const void*)igemm_fwd_kernel<kFwdEpiWarps, true>, "igemm_fwd")) return e;
@@ -518,7 +533,8 @@ static int launch_march(const void* src0, int c0p, const void* src1, int c1p, in
   // its dgrad 0.85 -> 0.70, 24 -> 32 0.85 -> 0.68; three chunks without CTA pairs 2.18 -> 2.05: profiles/r02j_march_mma2.txt);
   // UB_MARCH_MMA2=n: only layers with <= n chunks, 0: one issuer
   static const int march_mma2 = getenv("UB_MARCH_MMA2") ? atoi(getenv("UB_MARCH_MMA2")) : 3;
-  P.mma2 = (!tf && !pair && march_mma2 && P.n_chunks_total <= march_mma2) ? 1 : 0;
+  static const bool pair_mma2 = getenv("UB_MARCH_PAIR_MMA2") && atoi(getenv("UB_MARCH_PAIR_MMA2")) != 0;   // under test
+  P.mma2 = (!tf && (!pair || pair_mma2) && march_mma2 && P.n_chunks_total <= march_mma2) ? 1 : 0;
   if (pair) {
     // cluster of two CTAs along x: blocks (2k, 2k+1) take the w tiles (2j, 2j+1) of one column pair
     cudaLaunchConfig_t cfg;
