@@ -61,7 +61,7 @@ constexpr int kMarchWTileBytes = 96 * 64;  // one (chunk, kh, kw) weight tile
 
 constexpr int kMarchRing = 5;       // TMEM accumulator ring: 5 x 96 columns
 constexpr int kMarchEpiWarps = 8;
-constexpr int kMarchThreads = (kMarchEpiWarps + 2) * 32;   // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer
+constexpr int kMarchThreads = (kMarchEpiWarps + 2) * 32;   // warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issuer (+ warp 10: second issuer, kMarchThreads2)
 // kTf: + two operand-transform warps. Two, not four: the epilogue warps need ~166 registers and a scheduler
 // partition holds 16 K of them, so the CTA must stay at <= 3 warps per partition (12 warps). Role order in a kTf
 // CTA: warps 0-7 epilogue, 8-9 transform, 10 TMA producer, 11 MMA issuer -- the warp scheduler prefers the
